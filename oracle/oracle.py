@@ -1,0 +1,337 @@
+"""ctypes binding of the CPU oracle (oracle/ceno_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+`ceno_b200` never imports this module.
+
+Arrays are numpy uint64; an extension element is two consecutive u64 limbs
+[c0, c1] (the host in-memory layout of GoldilocksExt2 the reference transmutes,
+gkr_iop/src/gpu/mod.rs:311-324).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libceno_oracle.so")
+P = 0xFFFFFFFF00000001
+
+u64p = C.POINTER(C.c_uint64)
+u32p = C.POINTER(C.c_uint32)
+
+
+def build(force=False):
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "ceno_oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+class OrMle(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("num_vars", C.c_uint32), ("is_ext", C.c_uint32)]
+
+
+class OrTranscript(C.Structure):
+    _fields_ = [("h", C.c_uint64)]
+
+
+CHALLENGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, u64p, C.c_uint32, u64p)
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.or_gl_add.restype = C.c_uint64
+        _lib.or_gl_sub.restype = C.c_uint64
+        _lib.or_gl_mul.restype = C.c_uint64
+        _lib.or_gl_mul_slow.restype = C.c_uint64
+        _lib.or_gl_inv.restype = C.c_uint64
+        for f in ("or_gl_add", "or_gl_sub", "or_gl_mul", "or_gl_mul_slow"):
+            getattr(_lib, f).argtypes = [C.c_uint64, C.c_uint64]
+        _lib.or_gl_inv.argtypes = [C.c_uint64]
+        _lib.or_interleave_out_len.restype = C.c_uint64
+        _lib.or_interleave_out_len.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32]
+        _lib.or_tower_create_proof.restype = C.c_int64
+        _lib.or_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def num_threads():
+    return lib().or_num_threads()
+
+
+# ------------------------------------------------------------------ field
+def gl_mul(a, b):
+    return lib().or_gl_mul(a, b)
+
+
+def ext_mul(a, b):
+    a, b = _u64(a), _u64(b)
+    o = np.zeros(2, np.uint64)
+    lib().or_ext_mul(_p(a), _p(b), _p(o))
+    return o
+
+
+def ext_inv(a):
+    a = _u64(a)
+    o = np.zeros(2, np.uint64)
+    lib().or_ext_inv(_p(a), _p(o))
+    return o
+
+
+# ----------------------------------------------------------------- inputs
+def fill_ext(seed, n):
+    out = np.empty(2 * n, np.uint64)
+    lib().or_fill_ext(C.c_uint64(seed), C.c_uint64(n), _p(out))
+    return out
+
+
+def fill_base(seed, n):
+    out = np.empty(n, np.uint64)
+    lib().or_fill_base(C.c_uint64(seed), C.c_uint64(n), _p(out))
+    return out
+
+
+# ------------------------------------------------------------- transcript
+class Transcript:
+    """Stand-in transcript (splitmix64); same call order as BasicTranscript."""
+
+    def __init__(self, label=b"test"):
+        self.t = OrTranscript()
+        buf = (C.c_uint8 * len(label)).from_buffer_copy(label) if label else None
+        lib().or_tr_init(C.byref(self.t), buf, C.c_uint64(len(label)))
+
+    def append_message(self, msg: bytes):
+        buf = (C.c_uint8 * len(msg)).from_buffer_copy(msg)
+        lib().or_tr_append_message(C.byref(self.t), buf, C.c_uint64(len(msg)))
+
+    def append_ext(self, e):
+        e = _u64(e)
+        lib().or_tr_append_ext(C.byref(self.t), _p(e), C.c_uint64(e.size // 2))
+
+    def sample(self, label: bytes):
+        o = np.zeros(2, np.uint64)
+        lib().or_tr_sample(C.byref(self.t), C.c_char_p(label), _p(o))
+        return o
+
+    @property
+    def state(self):
+        return int(self.t.h)
+
+
+# ----------------------------------------------------------------- eq/MLE
+def build_eq_x_r_vec(r):
+    r = _u64(r)
+    k = r.size // 2
+    out = np.empty(2 << k, np.uint64)
+    lib().or_build_eq_x_r_vec(_p(r), C.c_uint32(k), _p(out))
+    return out
+
+
+def eq_eval(a, b):
+    a, b = _u64(a), _u64(b)
+    o = np.zeros(2, np.uint64)
+    lib().or_eq_eval(_p(a), _p(b), C.c_uint32(a.size // 2), _p(o))
+    return o
+
+
+def eq_eval_less_or_equal_than(max_idx, a, b):
+    a, b = _u64(a), _u64(b)
+    o = np.zeros(2, np.uint64)
+    lib().or_eq_eval_less_or_equal_than(C.c_uint64(max_idx), _p(a), C.c_uint32(a.size // 2), _p(b), C.c_uint32(b.size // 2), _p(o))
+    return o
+
+
+def mle_evaluate(evals, is_ext, point):
+    evals, point = _u64(evals), _u64(point)
+    nv = point.size // 2
+    assert evals.size == (2 if is_ext else 1) << nv
+    o = np.zeros(2, np.uint64)
+    lib().or_mle_evaluate(_p(evals), C.c_uint32(1 if is_ext else 0), C.c_uint32(nv), _p(point), _p(o))
+    return o
+
+
+def fix_variable(evals, is_ext, r):
+    evals, r = _u64(evals), _u64(r)
+    n = evals.size // (2 if is_ext else 1)
+    out = np.empty(n, np.uint64)  # n/2 ext
+    lib().or_fix_variable(_p(evals), C.c_uint32(1 if is_ext else 0), C.c_uint64(n), _p(r), _p(out))
+    return out
+
+
+def eval_wellform_address_vec(offset, scaled, r, descending=False):
+    r = _u64(r)
+    o = np.zeros(2, np.uint64)
+    lib().or_eval_wellform_address_vec(C.c_uint64(offset), C.c_uint64(scaled), _p(r), C.c_uint32(r.size // 2), C.c_int(int(descending)), _p(o))
+    return o
+
+
+def eval_stacked_wellform_address_vec(r):
+    r = _u64(r)
+    o = np.zeros(2, np.uint64)
+    lib().or_eval_stacked_wellform_address_vec(_p(r), C.c_uint32(r.size // 2), _p(o))
+    return o
+
+
+def eval_stacked_constant_vec(r):
+    r = _u64(r)
+    o = np.zeros(2, np.uint64)
+    lib().or_eval_stacked_constant_vec(_p(r), C.c_uint32(r.size // 2), _p(o))
+    return o
+
+
+SEL_WHOLE, SEL_PREFIX, SEL_ORDERED_SPARSE, SEL_QUARK_LT = 0, 1, 2, 3
+
+
+def selector_compute(kind, point, offset=0, num_instances=0, indices=(), inner_vars=0):
+    point = _u64(point)
+    nv = point.size // 2
+    idx = _u64(np.array(list(indices), dtype=np.uint64))
+    out = np.empty(2 << nv, np.uint64)
+    rc = lib().or_selector_compute(C.c_int(kind), _p(point), C.c_uint32(nv), C.c_uint64(offset), C.c_uint64(num_instances),
+                                   _p(idx), C.c_uint32(idx.size), C.c_uint32(inner_vars), _p(out))
+    if rc:
+        raise ValueError(f"or_selector_compute rc={rc}")
+    return out
+
+
+# --------------------------------------------------------------- sumcheck
+def _mk_mles(mles):
+    """mles: list of (np.uint64 array, is_ext, num_vars)."""
+    arr = (OrMle * len(mles))()
+    keep = []
+    for i, (d, is_ext, nv) in enumerate(mles):
+        d = _u64(d)
+        keep.append(d)
+        arr[i].data = d.ctypes.data
+        arr[i].num_vars = nv
+        arr[i].is_ext = 1 if is_ext else 0
+    return arr, keep
+
+
+def _mk_terms(terms):
+    """terms: list of (coeff_ext(2,), [mle idx...])."""
+    coeff = np.zeros(2 * len(terms), np.uint64)
+    off = np.zeros(len(terms) + 1, np.uint32)
+    idx = []
+    for t, (c, ids) in enumerate(terms):
+        coeff[2 * t:2 * t + 2] = _u64(c)
+        off[t] = len(idx)
+        idx.extend(ids)
+    off[len(terms)] = len(idx)
+    return coeff, off, np.array(idx, dtype=np.uint32)
+
+
+def sumcheck_prove(mles, terms, num_vars, degree, transcript=None, challenge_fn=None):
+    """Returns (round_evals[num_vars, degree, 2], final_evals[n_mles, 2], challenges[num_vars, 2]).
+
+    With `transcript` (a stand-in Transcript) the protocol order of SURVEY §A2 is
+    used; with `challenge_fn(round, evals)->ext` an arbitrary host source."""
+    arr, keep = _mk_mles(mles)
+    coeff, off, idx = _mk_terms(terms)
+    rounds = np.zeros(max(num_vars, 1) * degree * 2, np.uint64)
+    fin = np.zeros(len(mles) * 2, np.uint64)
+    chal = np.zeros(max(num_vars, 1) * 2, np.uint64)
+    L = lib()
+    if transcript is not None:
+        rc = L.or_sumcheck_prove_standin(arr, C.c_uint32(len(mles)), _p(coeff), _p(off), _p(idx), C.c_uint32(len(terms)),
+                                         C.c_uint32(num_vars), C.c_uint32(degree), C.byref(transcript.t), _p(rounds), _p(fin), _p(chal))
+    else:
+        def _cb(user, rnd, evals, deg, out):
+            e = np.ctypeslib.as_array(evals, shape=(deg * 2,)).copy()
+            r = _u64(challenge_fn(rnd, e))
+            out[0] = int(r[0])
+            out[1] = int(r[1])
+        cb = CHALLENGE_FN(_cb)
+        rc = L.or_sumcheck_prove(arr, C.c_uint32(len(mles)), _p(coeff), _p(off), _p(idx), C.c_uint32(len(terms)),
+                                 C.c_uint32(num_vars), C.c_uint32(degree), cb, None, _p(rounds), _p(fin), _p(chal))
+    if rc:
+        raise ValueError(f"or_sumcheck_prove rc={rc}")
+    return (rounds[:num_vars * degree * 2].reshape(num_vars, degree, 2), fin.reshape(-1, 2), chal[:num_vars * 2].reshape(num_vars, 2))
+
+
+def extrapolate_uni_poly(eval0, evals, r):
+    eval0, evals, r = _u64(eval0), _u64(evals), _u64(r)
+    o = np.zeros(2, np.uint64)
+    lib().or_extrapolate_uni_poly(_p(eval0), _p(evals), C.c_uint32(evals.size // 2), _p(r), _p(o))
+    return o
+
+
+# ------------------------------------------------------------------ tower
+def interleaving_mles_to_mles(mles, num_instances, num_limbs, default):
+    """mles: list of (array, is_ext); returns list of num_limbs ext arrays."""
+    n = len(mles)
+    arrs = [_u64(m[0]) for m in mles]
+    mle_len = arrs[0].size // (2 if mles[0][1] else 1)
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    is_ext = np.array([1 if m[1] else 0 for m in mles], dtype=np.uint32)
+    out_len = lib().or_interleave_out_len(n, num_instances, num_limbs)
+    out = np.empty(num_limbs * out_len * 2, np.uint64)
+    d = _u64(default)
+    lib().or_interleaving_mles_to_mles(ptrs, _p(is_ext), C.c_uint32(n), C.c_uint64(mle_len), C.c_uint64(num_instances),
+                                       C.c_uint32(num_limbs), _p(d), _p(out))
+    return [out[i * out_len * 2:(i + 1) * out_len * 2].copy() for i in range(num_limbs)]
+
+
+def infer_tower_product_witness(num_vars, f1, f2):
+    """Returns packed witness (see ceno_oracle.c) and a list of layers [[a, b], ...]."""
+    f1, f2 = _u64(f1), _u64(f2)
+    total = 2 * ((1 << num_vars) - 1)  # sum_{l<num_vars} 2*2^l ext
+    out = np.empty(total * 2, np.uint64)
+    lib().or_infer_tower_product_witness(C.c_uint32(num_vars), _p(f1), _p(f2), _p(out))
+    layers = []
+    for l in range(num_vars):
+        n = 1 << l
+        off = 2 * (n - 1)
+        layers.append([out[2 * off:2 * (off + n)], out[2 * (off + n):2 * (off + 2 * n)]])
+    return out, layers
+
+
+def infer_tower_logup_witness(nv, p1, p2, q1, q2):
+    q1, q2 = _u64(q1), _u64(q2)
+    if p1 is not None:
+        p1, p2 = _u64(p1), _u64(p2)
+    total = 4 * ((2 << nv) - 1)
+    out = np.empty(total * 2, np.uint64)
+    lib().or_infer_tower_logup_witness(C.c_uint32(nv), _p(p1) if p1 is not None else None, _p(p2) if p2 is not None else None,
+                                       _p(q1), _p(q2), _p(out))
+    layers = []
+    for l in range(nv + 1):
+        n = 1 << l
+        off = 4 * (n - 1)
+        layers.append([out[2 * (off + z * n):2 * (off + (z + 1) * n)] for z in range(4)])
+    return out, layers
+
+
+def tower_create_proof(prod_wits, logup_wits, transcript):
+    """prod_wits: list of (packed, n_layers); logup_wits likewise.  Returns (proof u64 array, point ext array)."""
+    npd, nl = len(prod_wits), len(logup_wits)
+    pk = [_u64(w[0]) for w in prod_wits]
+    lk = [_u64(w[0]) for w in logup_wits]
+    pl = np.array([w[1] for w in prod_wits], dtype=np.uint32)
+    ll = np.array([w[1] for w in logup_wits], dtype=np.uint32)
+    pp = (C.c_void_p * max(npd, 1))(*[a.ctypes.data for a in pk])
+    lp = (C.c_void_p * max(nl, 1))(*[a.ctypes.data for a in lk])
+    maxr = max([int(x) for x in pl] + [int(x) for x in ll]) - 1
+    cap = sum((r * 3 + 2 * npd + 4 * nl) * 2 for r in range(1, maxr + 1)) + 16
+    proof = np.zeros(cap, np.uint64)
+    point = np.zeros(2 * (maxr + 2), np.uint64)
+    plen = C.c_uint32(0)
+    w = lib().or_tower_create_proof(C.c_uint32(npd), _p(pl), pp, C.c_uint32(nl), _p(ll), lp, C.byref(transcript.t),
+                                    _p(proof), _p(point), C.byref(plen))
+    if w < 0:
+        raise ValueError(f"or_tower_create_proof rc={w}")
+    return proof[:w].copy(), point[:2 * plen.value].copy()

@@ -1,0 +1,355 @@
+"""Pins the CPU oracle (oracle/ceno_oracle.c) against every known-answer relation the
+reference tree holds for this path and against the independent
+big-int restatement oracle/pyref.py.  CPU-only."""
+import itertools
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import pyref as pr
+
+P = pr.P
+
+
+def rnd_ext(rng):
+    return (rng.randrange(P), rng.randrange(P))
+
+
+def ext_arr(pairs):
+    return pr.from_pairs(pairs)
+
+
+def E(x):
+    return (x % P, 0)
+
+
+# ---------------------------------------------------------------- field
+def test_gl_mul_fast_equals_slow_and_edge_cases():
+    rng = random.Random(1)
+    L = orc.lib()
+    edge = [0, 1, 2, P - 1, P - 2, 0xFFFFFFFF, 0xFFFFFFFF00000000, 1 << 32, (1 << 32) - 1, (1 << 63) % P]
+    for a, b in itertools.product(edge, edge):
+        assert L.or_gl_mul(a, b) == a * b % P == L.or_gl_mul_slow(a, b)
+        assert L.or_gl_add(a, b) == (a + b) % P
+        assert L.or_gl_sub(a, b) == (a - b) % P
+    for _ in range(20000):
+        a, b = rng.randrange(P), rng.randrange(P)
+        assert L.or_gl_mul(a, b) == a * b % P
+    for a in edge[1:]:
+        assert L.or_gl_mul(a, L.or_gl_inv(a)) == 1
+
+
+def test_ext_mul_w7_and_inverse():
+    # X^2 = 7 (p3-goldilocks 0.4.3 BinomiallyExtendable<2>)
+    assert tuple(int(x) for x in orc.ext_mul([0, 1], [0, 1])) == (7, 0)
+    rng = random.Random(2)
+    for _ in range(2000):
+        a, b = rnd_ext(rng), rnd_ext(rng)
+        assert tuple(int(x) for x in orc.ext_mul(list(a), list(b))) == pr.emul(a, b)
+    a = rnd_ext(rng)
+    assert pr.emul(a, tuple(int(x) for x in orc.ext_inv(list(a)))) == pr.ONE
+
+
+# ------------------------------------------------- eq table and evaluate
+@pytest.mark.parametrize("k", [0, 1, 2, 5, 9])
+def test_build_eq_matches_definition(k):
+    rng = random.Random(10 + k)
+    r = [rnd_ext(rng) for _ in range(k)]
+    got = pr.to_pairs(orc.build_eq_x_r_vec(ext_arr(r)))
+    assert got == pr.build_eq_x_r_vec(r)
+    s = pr.ZERO
+    for e in got:
+        s = pr.eadd(s, e)
+    assert s == pr.ONE  # sum_b eq(r,b) = 1
+
+
+def test_mle_evaluate_is_lsb_first():
+    # point[i] pairs with index bit i (gkr_iop/src/utils.rs:209-232): evaluating at a
+    # boolean point returns evals[sum b_i 2^i].
+    rng = random.Random(3)
+    k = 4
+    evals = [rnd_ext(rng) for _ in range(1 << k)]
+    for b in range(1 << k):
+        pt = [E((b >> i) & 1) for i in range(k)]
+        assert tuple(int(x) for x in orc.mle_evaluate(ext_arr(evals), True, ext_arr(pt))) == evals[b]
+    pt = [rnd_ext(rng) for _ in range(k)]
+    assert tuple(int(x) for x in orc.mle_evaluate(ext_arr(evals), True, ext_arr(pt))) == pr.mle_evaluate(evals, pt)
+    base = np.array([rng.randrange(P) for _ in range(1 << k)], dtype=np.uint64)
+    assert tuple(int(x) for x in orc.mle_evaluate(base, False, ext_arr(pt))) == pr.mle_evaluate([E(int(x)) for x in base], pt)
+
+
+R5 = [E(123), E(456), E(789), E(3210), E(9876)]  # gkr_iop/src/utils.rs:357-363
+
+
+def test_kat_eval_stacked_wellform_address_vec():
+    # gkr_iop/src/utils.rs:355-374
+    for n in range(len(R5)):
+        v = [pr.ZERO] + [E(x) for i in range(n + 1) for x in range(1 << i)]
+        r = R5[: n + 1]
+        want = tuple(int(x) for x in orc.mle_evaluate(ext_arr(v), True, ext_arr(r)))
+        assert tuple(int(x) for x in orc.eval_stacked_wellform_address_vec(ext_arr(r))) == want == pr.mle_evaluate(v, r)
+
+
+def test_kat_eval_stacked_constant_vec():
+    # gkr_iop/src/utils.rs:376-395
+    for n in range(len(R5)):
+        v = [pr.ZERO] + [E(i) for i in range(n + 1) for _ in range(1 << i)]
+        r = R5[: n + 1]
+        want = tuple(int(x) for x in orc.mle_evaluate(ext_arr(v), True, ext_arr(r)))
+        assert tuple(int(x) for x in orc.eval_stacked_constant_vec(ext_arr(r))) == want
+
+
+def test_kat_inner_outer_repeated_incremental_vec():
+    # gkr_iop/src/utils.rs:397-441
+    for n in range(1, len(R5) + 1):
+        for k in range(n + 1):
+            r = R5[:n]
+            inner = [E(i) for i in range(1 << (n - k)) for _ in range(1 << k)]
+            got = tuple(int(x) for x in orc.eval_wellform_address_vec(0, 1, ext_arr(r[k:]) if k < n else np.zeros(0, np.uint64)))
+            assert got == tuple(int(x) for x in orc.mle_evaluate(ext_arr(inner), True, ext_arr(r)))
+            outer = [E(x) for _ in range(1 << (n - k)) for x in range(1 << k)]
+            got = tuple(int(x) for x in orc.eval_wellform_address_vec(0, 1, ext_arr(r[:k]) if k else np.zeros(0, np.uint64)))
+            assert got == tuple(int(x) for x in orc.mle_evaluate(ext_arr(outer), True, ext_arr(r)))
+
+
+def test_eq_eval_and_less_or_equal_than():
+    rng = random.Random(4)
+    n = 5
+    a = [rnd_ext(rng) for _ in range(n)]
+    b = [rnd_ext(rng) for _ in range(n)]
+    eqa, eqb = pr.build_eq_x_r_vec(a), pr.build_eq_x_r_vec(b)
+    full = pr.ZERO
+    for x, y in zip(eqa, eqb):
+        full = pr.eadd(full, pr.emul(x, y))
+    assert tuple(int(x) for x in orc.eq_eval(ext_arr(a), ext_arr(b))) == full
+    for max_idx in [0, 1, 5, 0b10101, 30, 31]:
+        want = pr.ZERO
+        for i in range(max_idx + 1):
+            want = pr.eadd(want, pr.emul(eqa[i], eqb[i]))
+        assert tuple(int(x) for x in orc.eq_eval_less_or_equal_than(max_idx, ext_arr(a), ext_arr(b))) == want
+
+
+# ------------------------------------------------------------ selectors
+def test_kat_quark_lt_selector():
+    # gkr_iop/src/selector.rs:396-435: n_points = 5 -> n_vars = 3
+    rng = random.Random(5)
+    out_rt = [rnd_ext(rng) for _ in range(3)]
+    eq = pr.build_eq_x_r_vec(out_rt)
+    sel = pr.to_pairs(orc.selector_compute(orc.SEL_QUARK_LT, ext_arr(out_rt), num_instances=5))
+    assert sel == [eq[0], eq[1], pr.ZERO, pr.ZERO, eq[4], pr.ZERO, eq[6], pr.ZERO]
+
+
+def test_selector_prefix_and_sparse_evaluate_relation():
+    # compute() vs evaluate() closed forms (gkr_iop/src/selector.rs:262-303)
+    rng = random.Random(6)
+    nv = 5
+    out_pt = [rnd_ext(rng) for _ in range(nv)]
+    in_pt = [rnd_ext(rng) for _ in range(nv)]
+    for offset, ninst in [(0, 32), (0, 7), (3, 11), (31, 1), (0, 0)]:
+        sel = orc.selector_compute(orc.SEL_PREFIX, ext_arr(out_pt), offset=offset, num_instances=ninst)
+        got = tuple(int(x) for x in orc.mle_evaluate(sel, True, ext_arr(in_pt)))
+        end = offset + ninst
+        if end == 0:
+            want = pr.ZERO
+        else:
+            want = tuple(int(x) for x in orc.eq_eval_less_or_equal_than(end - 1, ext_arr(out_pt), ext_arr(in_pt)))
+            if offset > 0:
+                want = pr.esub(want, tuple(int(x) for x in orc.eq_eval_less_or_equal_than(offset - 1, ext_arr(out_pt), ext_arr(in_pt))))
+        assert got == want
+    # OrderedSparse: inner 3 vars, indices {1,4,6}, 3 instances of 4 chunks
+    indices, inner = [1, 4, 6], 3
+    ninst = 3
+    sel = orc.selector_compute(orc.SEL_ORDERED_SPARSE, ext_arr(out_pt), num_instances=ninst, indices=indices, inner_vars=inner)
+    got = tuple(int(x) for x in orc.mle_evaluate(sel, True, ext_arr(in_pt)))
+    oe, ie = pr.build_eq_x_r_vec(out_pt[:inner]), pr.build_eq_x_r_vec(in_pt[:inner])
+    ev = pr.ZERO
+    for i in indices:
+        ev = pr.eadd(ev, pr.emul(oe[i], ie[i]))
+    s = tuple(int(x) for x in orc.eq_eval_less_or_equal_than(ninst - 1, ext_arr(out_pt[inner:]), ext_arr(in_pt[inner:])))
+    assert got == pr.emul(ev, s)
+
+
+# ------------------------------------------------------- tower witnesses
+def test_kat_interleaving_mles_to_mles():
+    # ceno_zkvm/src/scheme/utils.rs:968-1065 literal vectors
+    def mle(*xs):
+        return (ext_arr([E(x) for x in xs]), True)
+
+    res = orc.interleaving_mles_to_mles([mle(1, 2), mle(3, 4), mle(5, 6), mle(7, 8)], 2, 2, [1, 0])
+    assert pr.to_pairs(res[0]) == [E(1), E(3), E(5), E(7)]
+    assert pr.to_pairs(res[1]) == [E(2), E(4), E(6), E(8)]
+    res = orc.interleaving_mles_to_mles([mle(1, 2), mle(3, 4), mle(5, 6)], 2, 2, [0, 0])
+    assert pr.to_pairs(res[0]) == [E(1), E(3), E(5), E(0)]
+    assert pr.to_pairs(res[1]) == [E(2), E(4), E(6), E(0)]
+    res = orc.interleaving_mles_to_mles([mle(1, 0), mle(3, 0), mle(5, 0)], 1, 2, [1, 0])
+    assert pr.to_pairs(res[0]) == [E(1), E(3), E(5), E(1)]
+    assert pr.to_pairs(res[1]) == [E(1)] * 4
+    res = orc.interleaving_mles_to_mles([mle(2), mle(3)], 1, 2, [1, 0])
+    assert pr.to_pairs(res[0]) == [E(2), E(3)]
+    assert pr.to_pairs(res[1]) == [E(1), E(1)]
+
+
+def test_kat_infer_tower_product_witness():
+    # ceno_zkvm/src/scheme/utils.rs:934-966
+    _, layers = orc.infer_tower_product_witness(2, ext_arr([E(1), E(2)]), ext_arr([E(3), E(4)]))
+    assert len(layers) == 2
+    left, right = pr.to_pairs(layers[0][0]), pr.to_pairs(layers[0][1])
+    assert len(left) == 1 and len(right) == 1
+    assert pr.emul(left[0], right[0]) == E(1 * 2 * 3 * 4)
+
+
+def test_kat_infer_tower_logup_witness():
+    # ceno_zkvm/src/scheme/utils.rs:1067-1195 literal vectors
+    q1 = ext_arr([E(x) for x in (1, 2, 3, 4)])
+    q2 = ext_arr([E(x) for x in (5, 6, 7, 8)])
+    _, layers = orc.infer_tower_logup_witness(2, None, None, q1, q2)
+    assert len(layers) == 3
+    L = [[pr.to_pairs(a) for a in lay] for lay in layers]
+    assert L[2][0] == [E(1)] * 4 and L[2][1] == [E(1)] * 4
+    assert L[2][2] == [E(1), E(2), E(3), E(4)] and L[2][3] == [E(5), E(6), E(7), E(8)]
+    assert L[1][0] == [E(1 + 5), E(2 + 6)]
+    assert L[1][1] == [E(3 + 7), E(4 + 8)]
+    assert L[1][2] == [E(5), E(2 * 6)]
+    assert L[1][3] == [E(3 * 7), E(4 * 8)]
+    assert L[0][0] == [E((1 + 5) * (3 * 7) + (3 + 7) * 5)]
+    assert L[0][1] == [E((2 + 6) * (4 * 8) + (4 + 8) * (2 * 6))]
+    assert L[0][2] == [E((3 * 7) * 5)]
+    assert L[0][3] == [E((4 * 8) * (2 * 6))]
+
+
+# ------------------------------------------------------------- sumcheck
+def _standin_cb(seed):
+    def cb(j, msg):
+        t = orc.Transcript(b"cb%d" % seed)
+        t.append_message(int(j).to_bytes(8, "little"))
+        t.append_ext(np.array(msg, dtype=np.uint64).reshape(-1))
+        return t.sample(b"r")
+    return cb
+
+
+@pytest.mark.parametrize("k,degree", [(1, 3), (3, 3), (6, 3), (5, 2), (4, 5)])
+def test_sumcheck_matches_pyref_and_verifier_relations(k, degree):
+    rng = random.Random(100 * k + degree)
+    m = degree
+    mles_p = [[rnd_ext(rng) for _ in range(1 << k)] for _ in range(m)]
+    # one full-degree product term + a lower-degree term (extrapolated up)
+    terms = [(rnd_ext(rng), list(range(m))), (rnd_ext(rng), [0])]
+    cb = _standin_cb(k)
+    rounds, fin, chal = orc.sumcheck_prove([(ext_arr(x), True, k) for x in mles_p],
+                                           [(list(c), ids) for c, ids in terms], k, degree, challenge_fn=cb)
+    pmsgs, pfin, pchal = pr.sumcheck_prove(mles_p, terms, k, degree,
+                                           lambda j, msg: tuple(int(x) for x in cb(j, [v for e in msg for v in e])))
+    assert [[tuple(int(x) for x in e) for e in r] for r in rounds] == pmsgs
+    assert [tuple(int(x) for x in e) for e in fin] == pfin
+    assert [tuple(int(x) for x in e) for e in chal] == pchal
+    # verifier (ceno_recursion_v2/src/main/mod.rs:3513-3526): eval_0 = claim - evals[0]; claim' = interp(r)
+    claim = pr.ZERO
+    for b in range(1 << k):
+        claim = pr.eadd(claim, pr.poly_eval(mles_p, terms, b))
+    for j in range(k):
+        e0 = pr.esub(claim, pmsgs[j][0])
+        claim = tuple(int(x) for x in orc.extrapolate_uni_poly(list(e0), rounds[j].reshape(-1), chal[j]))
+        assert claim == pr.lagrange_eval([e0] + pmsgs[j], pchal[j])
+    # final check: sum_t c_t prod f_i(r) == last claim, f_i(r) by direct MLE evaluation
+    direct = [pr.mle_evaluate(m_, pchal) for m_ in mles_p]
+    assert direct == pfin
+    acc = pr.ZERO
+    for c, ids in terms:
+        p = c
+        for i in ids:
+            p = pr.emul(p, direct[i])
+        acc = pr.eadd(acc, p)
+    assert acc == claim
+
+
+def test_sumcheck_base_field_mles_and_transcript_order():
+    rng = random.Random(77)
+    k = 5
+    a = np.array([rng.randrange(P) for _ in range(1 << k)], dtype=np.uint64)
+    b = [rnd_ext(rng) for _ in range(1 << k)]
+    terms = [([1, 0], [0, 1])]
+    t1 = orc.Transcript(b"order")
+    rounds, fin, chal = orc.sumcheck_prove([(a, False, k), (ext_arr(b), True, k)], terms, k, 2, transcript=t1)
+    # replay the protocol order of SURVEY §A2 by hand
+    t2 = orc.Transcript(b"order")
+    t2.append_message((k).to_bytes(8, "little"))
+    t2.append_message((2).to_bytes(8, "little"))
+    for j in range(k):
+        t2.append_ext(rounds[j].reshape(-1))
+        assert tuple(t2.sample(b"Internal round")) == tuple(chal[j])
+    assert t1.state == t2.state
+    pt = [tuple(int(x) for x in c) for c in chal]
+    assert tuple(int(x) for x in fin[0]) == pr.mle_evaluate([E(int(x)) for x in a], pt)
+
+
+def test_tower_proof_verifies():
+    """Prover->verifier round trip in the style of test_tower_proof_various_prod_size
+    (ceno_zkvm/src/scheme/tests.rs:447-500): replay the transcript, check every layer's
+    sumcheck and the claim flow of TowerVerify (ceno_zkvm/src/scheme/verifier.rs:1543-1700)."""
+    rng = random.Random(9)
+    nv_prod, nv_lk = 4, 3
+    f1 = [rnd_ext(rng) for _ in range(1 << (nv_prod - 1))]
+    f2 = [rnd_ext(rng) for _ in range(1 << (nv_prod - 1))]
+    pw, players = orc.infer_tower_product_witness(nv_prod, ext_arr(f1), ext_arr(f2))
+    q1 = [rnd_ext(rng) for _ in range(1 << nv_lk)]
+    q2 = [rnd_ext(rng) for _ in range(1 << nv_lk)]
+    lw, llayers = orc.infer_tower_logup_witness(nv_lk, None, None, ext_arr(q1), ext_arr(q2))
+    tr = orc.Transcript(b"tower")
+    proof, point = orc.tower_create_proof([(pw, nv_prod)], [(lw, nv_lk + 1)], tr)
+    # ---- verifier
+    tv = orc.Transcript(b"tower")
+    alpha = tuple(int(x) for x in tv.sample(b"combine subset evals"))
+    apow = [pr.ONE, alpha, pr.emul(alpha, alpha)]
+    rt = [tuple(int(x) for x in tv.sample(b"product_sum"))]
+    po = [pr.to_pairs(x)[0] for x in players[0]]
+    lo = [pr.to_pairs(x)[0] for x in llayers[0]]
+    # initial claims: evaluate the 1-var MLE of the two output values at rt
+    def mle1(v0, v1, r):
+        return pr.eadd(v0, pr.emul(r, pr.esub(v1, v0)))
+    prod_claim = mle1(po[0], po[1], rt[0])
+    p_claim = mle1(lo[0], lo[1], rt[0])
+    q_claim = mle1(lo[2], lo[3], rt[0])
+    pos = 0
+    pp = pr.to_pairs(proof)
+    max_round = 3
+    for rnd in range(1, max_round + 1):
+        nv = rnd
+        claim = pr.eadd(pr.emul(apow[0], prod_claim), pr.eadd(pr.emul(apow[1], p_claim), pr.emul(apow[2], q_claim)))
+        tv.append_message(nv.to_bytes(8, "little"))
+        tv.append_message((3).to_bytes(8, "little"))
+        chal = []
+        for j in range(nv):
+            msg = pp[pos:pos + 3]
+            pos += 3
+            e0 = pr.esub(claim, msg[0])
+            tv.append_ext(pr.from_pairs(msg))
+            r = tuple(int(x) for x in tv.sample(b"Internal round"))
+            chal.append(r)
+            claim = pr.lagrange_eval([e0] + msg, r)
+        pe = pp[pos:pos + 2]
+        pos += 2
+        tv.append_ext(pr.from_pairs(pe))
+        le = pp[pos:pos + 4]
+        pos += 4
+        tv.append_ext(pr.from_pairs(le))
+        eqv = tuple(int(x) for x in orc.eq_eval(ext_arr(rt), ext_arr(chal)))
+        inner = pr.eadd(pr.emul(apow[0], pr.emul(pe[0], pe[1])),
+                        pr.eadd(pr.emul(apow[1], pr.eadd(pr.emul(le[0], le[3]), pr.emul(le[1], le[2]))),
+                                pr.emul(apow[2], pr.emul(le[2], le[3]))))
+        assert pr.emul(eqv, inner) == claim
+        rm = tuple(int(x) for x in tv.sample(b"merge"))
+        rt = chal + [rm]
+        prod_claim = mle1(pe[0], pe[1], rm)
+        p_claim = mle1(le[0], le[1], rm)
+        q_claim = mle1(le[2], le[3], rm)
+        alpha = tuple(int(x) for x in tv.sample(b"combine subset evals"))
+        apow = [pr.ONE, alpha, pr.emul(alpha, alpha)]
+    assert pos == len(pp)
+    assert pr.to_pairs(point) == rt
+    assert tv.state == tr.state
+    # leaf claims equal direct evaluation of the input layer at rt (tests.rs:490-499)
+    full = [x for x in f1] + [x for x in f2]  # top variable selects the half
+    assert pr.mle_evaluate(full, rt) == prod_claim
+    assert pr.mle_evaluate(q1 + q2, rt) == q_claim
