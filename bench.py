@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py — the hot path's headline benchmark (BASELINE.json): a degree-3 sumcheck
+P = eq(w,x)*A(x)*B(x) over GoldilocksExt2 on a 2^24-variable instance ("T3-24"), rounds + folds,
+reported as Goldilocks field-ops/s (99 base-field ops per pair per round), plus
+hypercube points/s and rounds/s, the HBM-roofline fraction of the dominant kernel measured live
+with CUDA events, and a CPU baseline (the oracle port of the reference algorithm) on the host cores.
+
+  python bench.py --gpus N --steps K --warmup W        (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                 CPU arm: the reference algorithm's port
+
+A "step" is one full sumcheck (k rounds of evaluate+fold) over the resident instance.
+`value`  : inputs resident in HBM, transcript on the host behind the C-ABI callback (the
+           reference's flow: it hands &mut BasicTranscript to the device crate).
+`e2e`    : same call with HOST buffers — H2D of A and B from pinned memory, eq-build, prove, results
+           back on the host — inside the timed region.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OPS_PER_PAIR = 99            # 12 ext add + 6 ext mul (eval) + 3*(sub+mul+add) (fold) in base-field ops
+SEED_A, SEED_B, SEED_W = 0xC0FFEE ^ 1, 0xC0FFEE ^ 2, 0xE9
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------- CPU arm
+def cpu_run(k, threads=None):
+    """One T3-k step on the host cores with the oracle port: eq-build + sumcheck (rounds + folds)."""
+    from oracle import oracle as orc
+    n = 1 << k
+    w = orc.fill_ext(SEED_W, k)
+    a, b = orc.fill_ext(SEED_A, n), orc.fill_ext(SEED_B, n)
+    eq = orc.build_eq_x_r_vec(w)
+    t0 = time.perf_counter()
+    orc.sumcheck_prove([(eq, True, k), (a, True, k), (b, True, k)], [([1, 0], [0, 1, 2])], k, 3, transcript=orc.Transcript(b"bench"))
+    return time.perf_counter() - t0
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    k = args.cpu_k
+    for _ in range(max(args.warmup, 1) if args.warmup else 0):
+        cpu_run(min(k, 18))
+    ts = [cpu_run(k) for _ in range(args.steps)]
+    t = float(np.mean(ts))
+    val = OPS_PER_PAIR * (1 << k) / t / 1e9
+    cores = orc.num_threads()
+    line = {
+        "impl": "reference", "metric": "sumcheck Gfield-ops/s", "value": val, "unit": "Gfield-ops/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u64 (Goldilocks, ext2)", "data": "synthetic",
+        "config": {"workload": f"T3-{args.k}: eq(w,x)*A(x)*B(x), degree 3, GoldilocksExt2; CPU arm times a bounded sample T3-{k}",
+                   "k": args.k, "degree": 3, "n_mles": 3},
+        "points_per_s": (1 << k) / t, "rounds_per_s": k / t,
+        "cpu_baseline": {"value": val, "unit": "Gfield-ops/s", "cores": cores, "kind": "port",
+                         "sample": f"T3-{k} full sumcheck (2^{k} points, {k} rounds), OpenMP {cores} threads; reference is Rust (Rayon) and cannot be built here"},
+        "e2e": {"value": val, "unit": "Gfield-ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+def gpu_arm(args):
+    import torch
+    import ceno_b200 as cb
+    from ceno_b200 import _lib, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from ceno_b200 import dist as cdist
+        return cdist.bench_sharded(args, rank, world, local)
+
+    dev = cb.Device(local)
+    lib = dev.lib
+    k, deg = args.k, 3
+    n = 1 << k
+    stream = torch.cuda.Stream()
+    sh = stream.cuda_stream
+
+    # ---- synthetic inputs, pinned on the host (e2e source) and resident on the device
+    nbytes = 16 * n
+    a_h, a_hp = dev.pinned(nbytes)
+    b_h, b_hp = dev.pinned(nbytes)
+    synth.fill_ext(SEED_A, n, out=a_h)
+    synth.fill_ext(SEED_B, n, out=b_h)
+    w = synth.fill_ext(SEED_W, k)
+    a_d, b_d, eq_d = dev.alloc(nbytes), dev.alloc(nbytes), dev.alloc(nbytes)
+    dev.h2d(a_d.ptr, a_hp, nbytes, sh)
+    dev.h2d(b_d.ptr, b_hp, nbytes, sh)
+    A = cb.MultilinearExtension(dev, a_d, k, True)
+    B = cb.MultilinearExtension(dev, b_d, k, True)
+    EQ = cb.build_eq_x_r_vec(dev, w, stream=sh, out=eq_d)
+    stream.synchronize()
+    mles, terms = [EQ, A, B], [([1, 0], [0, 1, 2])]
+
+    def step(device_challenger=False, flags=0):
+        return cb.IOPProverState.prove(dev, mles, terms, k, deg, transcript=cb.StandInTranscript(b"bench"), flags=flags,
+                                       device_challenger=device_challenger, stream=sh)
+
+    def e2e_step():
+        dev.h2d(a_d.ptr, a_hp, nbytes, sh)
+        dev.h2d(b_d.ptr, b_hp, nbytes, sh)
+        cb.build_eq_x_r_vec(dev, w, stream=sh, out=eq_d)
+        return step()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, out
+
+    for _ in range(args.warmup):
+        ref_out = step()
+        step(True)
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = dev.launch_count()
+    ms, out = timed(step, args.steps)
+    launches = dev.launch_count() - l0
+    ms_dev, out_dev = timed(lambda: step(True), args.steps)
+    # EQ-k (build_eq_x_r alone), timed separately
+    ms_eq, _ = timed(lambda: cb.build_eq_x_r_vec(dev, w, stream=sh, out=eq_d), max(args.steps, 5))
+    clk = clocks.stop()
+    for g, d in zip(out, out_dev):
+        assert np.array_equal(g, d), "host-transcript and device-challenger runs disagree"
+
+    # ---- per-kernel roofline, measured live with CUDA events on the launching stream (CG_SC_PROFILE)
+    prof = []
+    for _ in range(max(3, min(args.steps, 10))):
+        step(True, flags=4)
+        prof.append(dev.profile_last())
+    prof = np.mean(np.array(prof), axis=0)       # ms per round
+    m, s = 3, 16
+    fused_bytes = [1.5 * m * s * (1 << (k - j + 1)) for j in range(1, k)]     # round j>=1: read 2^(k-j+1), write half
+    fused_ms = [float(prof[j]) for j in range(1, k)]
+    peak, peak_src = read_peaks()
+    ach_all = sum(fused_bytes) / (sum(fused_ms) * 1e-3) / 1e9
+    ach_top = fused_bytes[0] / (fused_ms[0] * 1e-3) / 1e9
+    r0_bytes = m * s * n
+    roofline = {
+        "bound": "hbm", "kernel": "tower_round_kernel<FOLD=1> (fused fix_variable + next-round evaluation)",
+        "achieved": ach_all, "peak": peak, "unit": "GB/s", "frac": ach_all / peak, "peak_source": peak_src,
+        "traffic": None,
+        "launches_per_step": k - 1, "algorithmic_bytes_per_step": sum(fused_bytes), "ms_per_step_in_kernel": sum(fused_ms),
+        "top_launch": {"round": 1, "bytes": fused_bytes[0], "ms": fused_ms[0], "achieved": ach_top, "frac": ach_top / peak},
+        "round0_eval": {"bytes": r0_bytes, "ms": float(prof[0]), "achieved": r0_bytes / (float(prof[0]) * 1e-3) / 1e9},
+        "eq_build": {"bytes": 16 * n, "ms": ms_eq, "achieved": 16 * n / (ms_eq * 1e-3) / 1e9},
+        "round_ms": [round(float(x), 5) for x in prof],
+    }
+
+    # ---- e2e: host buffers, copies inside the timed region
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    ms_e2e, out_e2e = timed(e2e_step, max(1, min(args.steps, 5)))
+    for g, d in zip(out, out_e2e):
+        assert np.array_equal(g, d)
+
+    # ---- CPU baseline on this box's host cores (bounded sample)
+    from oracle import oracle as orc
+    cpu_run(min(args.cpu_k, 16))
+    t_cpu = cpu_run(args.cpu_k)
+    cpu_val = OPS_PER_PAIR * (1 << args.cpu_k) / t_cpu / 1e9
+    cores = orc.num_threads()
+
+    ops = OPS_PER_PAIR * n
+    value = ops / (ms * 1e-3) / 1e9
+    line = {
+        "metric": "sumcheck Gfield-ops/s", "value": value, "unit": "Gfield-ops/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64 (Goldilocks, ext2)", "data": "synthetic",
+        "config": {"workload": f"T3-{k}: eq(w,x)*A(x)*B(x), 2^{k}-point hypercube, degree 3, GoldilocksExt2 (3 ext MLEs x {nbytes >> 20} MiB)",
+                   "k": k, "degree": deg, "n_mles": 3, "parallelism": "1 GPU",
+                   "l2": f"inputs {3 * nbytes >> 20} MiB > L2 126 MB (no flush needed)",
+                   "transcript": "stand-in sponge on the host behind cg_challenge_cb (reference flow); Poseidon2 constants are upstream-only"},
+        "points_per_s": n / (ms * 1e-3), "rounds_per_s": k / (ms * 1e-3),
+        "device_challenger": {"ms_per_step": ms_dev, "value": ops / (ms_dev * 1e-3) / 1e9, "unit": "Gfield-ops/s",
+                              "note": "same kernels, stand-in challenger on the device: no host round trip per round"},
+        "e2e": {"value": ops / (ms_e2e * 1e-3) / 1e9, "unit": "Gfield-ops/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": 2 * nbytes + 16 * k, "d2h_bytes_per_step": 16 * (k * deg + 3 + k),
+                "note": "H2D of A,B from pinned host memory + eq-build + prove through cg_sumcheck_prove, results on the host"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": {"value": cpu_val, "unit": "Gfield-ops/s", "cores": cores, "kind": "port", "ms": t_cpu * 1e3,
+                         "sample": f"T3-{args.cpu_k} full sumcheck (1/{1 << (k - args.cpu_k)} of the workload's points), oracle port, OpenMP {cores} threads"},
+        "clocks": clk,
+    }
+    print(json.dumps(line))
+    dev.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--k", type=int, default=24, help="log2 hypercube size of the T3 instance")
+    ap.add_argument("--cpu-k", type=int, default=22, help="log2 size of the bounded CPU sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

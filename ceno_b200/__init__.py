@@ -1,0 +1,7 @@
+"""ceno_b200 — B200-native (sm_100a) device backend for the GKR-sumcheck hot path of scroll-tech/ceno.
+
+The product is the C ABI in include/ceno_b200.h implemented by ceno_b200/csrc (hand-written CUDA);
+this package is the thin host-side mirror of the reference's interface used by tests and bench.py.
+"""
+from .api import (CenoB200Error, Device, DeviceBuffer, IOPProverState, MultilinearExtension, SelectorType,  # noqa: F401
+                  StandInTranscript, TowerProver, TowerProverSpec, build_eq_x_r_vec, wit_infer_by_monomial_expr)

@@ -1,0 +1,365 @@
+"""Host-side mirror (Python) of the reference interface for the hot path, over the C ABI.
+
+Names follow the reference so the parity tests read like its own tests:
+  MultilinearExtension        multilinear_extensions::mle::MultilinearExtension (device-resident;
+                              the role MultilinearExtensionGpu plays, gkr_iop/src/gpu/mod.rs:157-161)
+  build_eq_x_r_vec            multilinear_extensions::virtual_poly::build_eq_x_r_vec
+  SelectorType.compute        gkr_iop/src/selector.rs:131-245
+  IOPProverState.prove        sumcheck::structs::IOPProverState (call sites gkr_iop/src/gkr/layer/cpu/mod.rs:217-237)
+  TowerProver.create_proof    ceno_zkvm/src/scheme/cpu/mod.rs:346-554 (CpuTowerProver) / hal.rs:173-207
+  StandInTranscript           stand-in for transcript::BasicTranscript (NOT Poseidon2)
+
+Everything here only marshals arguments; all arithmetic happens in libceno_b200.so on the GPU.
+Arrays are numpy uint64; an extension element is two consecutive limbs [c0, c1].
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+P = 0xFFFFFFFF00000001
+
+
+class CenoB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{_lib.ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+class Device:
+    """A cg_ctx: one GPU, its stream and pooled allocator (cuda_hal context, gkr_iop/src/gpu/mod.rs:53-66)."""
+
+    def __init__(self, device_id=0):
+        self.lib = _lib.load()
+        self.ctx = C.c_void_p()
+        rc = self.lib.cg_init(device_id, C.byref(self.ctx))
+        if rc != _lib.CG_OK:
+            raise CenoB200Error(rc, "cg_init failed: an sm_100 (B200) GPU is required; there is no CPU fallback")
+        self.device_id = device_id
+
+    def check(self, rc):
+        if rc != _lib.CG_OK:
+            raise CenoB200Error(rc, self.lib.cg_last_error(self.ctx).decode())
+
+    def close(self):
+        if self.ctx:
+            self.lib.cg_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def info(self):
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        fr, to = C.c_size_t(), C.c_size_t()
+        self.check(self.lib.cg_device_info(self.ctx, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(fr), C.byref(to)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "free": fr.value, "total": to.value}
+
+    def launch_count(self):
+        return int(self.lib.cg_launch_count(self.ctx))
+
+    def sync(self):
+        self.check(self.lib.cg_stream_sync(self.ctx, None))
+
+    # -- memory
+    def alloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(self.lib.cg_alloc(self.ctx, nbytes, C.byref(p)))
+        return DeviceBuffer(self, p.value, nbytes)
+
+    def to_device(self, arr):
+        arr = _u64(arr)
+        buf = self.alloc(arr.nbytes)
+        self.check(self.lib.cg_h2d(self.ctx, buf.ptr, _vp(arr), arr.nbytes, None))
+        self.sync()
+        return buf
+
+    def h2d(self, dst_ptr, host_ptr, nbytes, stream=None):
+        self.check(self.lib.cg_h2d(self.ctx, C.c_void_p(dst_ptr), C.c_void_p(host_ptr), nbytes, C.c_void_p(stream) if stream else None))
+
+    def pinned(self, nbytes):
+        """Pinned host buffer as a numpy uint64 view (kept alive by the Device)."""
+        p = C.c_void_p()
+        self.check(self.lib.cg_host_alloc_pinned(self.ctx, nbytes, C.byref(p)))
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(nbytes // 8,))
+        return arr, p.value
+
+    def profile_last(self):
+        n = C.c_uint32()
+        buf = np.zeros(64, np.float32)
+        self.check(self.lib.cg_profile_last(self.ctx, _vp(buf), 64, C.byref(n)))
+        return buf[:n.value].copy()
+
+    def pool_stats(self):
+        u, r = C.c_size_t(), C.c_size_t()
+        self.check(self.lib.cg_pool_stats(self.ctx, C.byref(u), C.byref(r)))
+        return u.value, r.value
+
+
+class DeviceBuffer:
+    def __init__(self, dev, ptr, nbytes, owner=True):
+        self.dev, self.ptr, self.nbytes, self.owner = dev, ptr, nbytes, owner
+
+    def to_host(self, nbytes=None, offset=0):
+        nbytes = self.nbytes - offset if nbytes is None else nbytes
+        out = np.empty(nbytes // 8, np.uint64)
+        self.dev.check(self.dev.lib.cg_d2h(self.dev.ctx, _vp(out), C.c_void_p(self.ptr + offset), nbytes, None))
+        self.dev.sync()
+        return out
+
+    def free(self):
+        if self.owner and self.ptr:
+            self.dev.lib.cg_free(self.dev.ctx, C.c_void_p(self.ptr))
+            self.ptr = 0
+
+
+class MultilinearExtension:
+    """Dense device MLE: 2^num_vars evaluations, base (8 B) or ext (16 B)."""
+
+    def __init__(self, dev, buf, num_vars, is_ext, length=None):
+        self.dev, self.buf, self.num_vars, self.is_ext = dev, buf, num_vars, bool(is_ext)
+        self.len = (1 << num_vars) if length is None else length
+
+    @classmethod
+    def from_evaluations_vec(cls, dev, num_vars, evals):          # base field
+        evals = _u64(evals)
+        assert evals.size <= (1 << num_vars)
+        return cls(dev, dev.to_device(evals), num_vars, False, evals.size)
+
+    @classmethod
+    def from_evaluations_ext_vec(cls, dev, num_vars, evals):      # extension field, limbs interleaved
+        evals = _u64(evals)
+        assert evals.size % 2 == 0 and evals.size // 2 <= (1 << num_vars)
+        return cls(dev, dev.to_device(evals), num_vars, True, evals.size // 2)
+
+    def desc(self):
+        return _lib.CgMleDesc(self.buf.ptr, self.len, self.num_vars, 1 if self.is_ext else 0)
+
+    def evaluations(self):
+        return self.buf.to_host(self.len * (16 if self.is_ext else 8))
+
+    def evaluate(self, point):
+        point = _u64(point)
+        assert point.size == 2 * self.num_vars
+        out = np.zeros(2, np.uint64)
+        d = self.desc()
+        self.dev.check(self.dev.lib.cg_mle_evaluate(self.dev.ctx, C.byref(d), _vp(point), _vp(out), None))
+        return out
+
+    def fix_variable(self, r):
+        """Out-of-place LSB fold; returns a new ext MLE with one variable fewer."""
+        r = _u64(r)
+        out = self.dev.alloc(16 << (self.num_vars - 1))
+        d = (_lib.CgMleDesc * 1)(self.desc())
+        outs = (C.c_void_p * 1)(out.ptr)
+        self.dev.check(self.dev.lib.cg_fix_variable(self.dev.ctx, d, 1, _vp(r), outs, None))
+        self.dev.sync()
+        return MultilinearExtension(self.dev, out, self.num_vars - 1, True)
+
+    def free(self):
+        self.buf.free()
+
+
+def build_eq_x_r_vec(dev, r, offset=0, num_instances=None, stream=None, out=None):
+    """eq table of point r (k ext) as a device ext MLE; optional prefix mask (build_mle_as_ceno).
+    With `stream` (a cudaStream_t handle) the call is asynchronous on that stream."""
+    r = _u64(r)
+    k = r.size // 2
+    n = 1 << k
+    num_instances = n - offset if num_instances is None else num_instances
+    out = dev.alloc(16 * n) if out is None else out
+    dev.check(dev.lib.cg_build_eq(dev.ctx, _vp(r), k, C.c_void_p(out.ptr), offset, num_instances, C.c_void_p(stream) if stream else None))
+    if not stream:
+        dev.sync()
+    return MultilinearExtension(dev, out, k, True)
+
+
+class SelectorType:
+    WHOLE, PREFIX, ORDERED_SPARSE, QUARK_LT = 0, 1, 2, 3
+
+    @staticmethod
+    def compute(dev, kind, out_point, offset=0, num_instances=0, indices=(), inner_vars=0):
+        out_point = _u64(out_point)
+        nv = out_point.size // 2
+        idx = _u64(np.array(list(indices), dtype=np.uint64))
+        out = dev.alloc(16 << nv)
+        dev.check(dev.lib.cg_selector_compute(dev.ctx, kind, _vp(out_point), nv, offset, num_instances, _vp(idx), idx.size,
+                                              inner_vars, C.c_void_p(out.ptr), None))
+        dev.sync()
+        return MultilinearExtension(dev, out, nv, True)
+
+
+class StandInTranscript:
+    """Stand-in sponge (splitmix64) with BasicTranscript's call order. Not Poseidon2."""
+
+    def __init__(self, label=b"test"):
+        self.lib = _lib.load()
+        self.state = np.zeros(1, np.uint64)
+        buf = (C.c_uint8 * max(len(label), 1)).from_buffer_copy(label or b"\0")
+        self.lib.cg_standin_init(_vp(self.state), buf, len(label))
+
+    def append_message(self, msg: bytes):
+        buf = (C.c_uint8 * max(len(msg), 1)).from_buffer_copy(msg or b"\0")
+        self.lib.cg_standin_append_message(_vp(self.state), buf, len(msg))
+
+    def append_field_element_exts(self, e):
+        e = _u64(e)
+        self.lib.cg_standin_append_ext(_vp(self.state), _vp(e), e.size // 2)
+
+    def sample_and_append_challenge(self, label: bytes):
+        out = np.zeros(2, np.uint64)
+        self.lib.cg_standin_sample(_vp(self.state), C.c_char_p(label), _vp(out))
+        return out
+
+    def vtable(self):
+        vt = _lib.CgTranscriptVt()
+        self.lib.cg_standin_vt(_vp(self.state), C.byref(vt))
+        return vt
+
+
+def _terms(terms):
+    coeff = np.zeros(2 * max(len(terms), 1), np.uint64)
+    off = np.zeros(len(terms) + 1, np.uint32)
+    idx = []
+    for t, (c, ids) in enumerate(terms):
+        coeff[2 * t:2 * t + 2] = _u64(c)
+        off[t] = len(idx)
+        idx.extend(ids)
+    off[len(terms)] = len(idx)
+    return coeff, off, np.array(idx if idx else [0], dtype=np.uint32)
+
+
+class IOPProverState:
+    """Device sumcheck prover for P(x) = sum_t c_t prod_{i in S_t} mle_i(x).
+
+    `prove(...)` mirrors IOPProverState::prove(virtual_polys, transcript) -> (proof, state);
+    the step API (round_eval / bind) is what a multi-GPU or Rust-transcript host drives."""
+
+    FORCE_GENERIC, NO_FUSE = 1, 2
+
+    def __init__(self, dev, mles, terms, num_vars, degree, flags=0):
+        self.dev, self.mles, self.num_vars, self.degree = dev, mles, num_vars, degree
+        descs = (_lib.CgMleDesc * max(len(mles), 1))(*[m.desc() for m in mles])
+        coeff, off, idx = _terms(terms)
+        self.h = C.c_void_p()
+        dev.check(dev.lib.cg_sumcheck_create(dev.ctx, descs, len(mles), _vp(coeff), _vp(off), _vp(idx), len(terms),
+                                             num_vars, degree, flags, None, C.byref(self.h)))
+        self._keep = (descs, coeff, off, idx)
+
+    def round_eval(self):
+        out = np.zeros(2 * self.degree, np.uint64)
+        self.dev.check(self.dev.lib.cg_sumcheck_round_eval(self.h, _vp(out)))
+        return out
+
+    def bind(self, r):
+        r = _u64(r)
+        self.dev.check(self.dev.lib.cg_sumcheck_bind(self.h, _vp(r)))
+
+    def get_mle_flatten_final_evaluations(self):
+        out = np.zeros(2 * max(len(self.mles), 1), np.uint64)
+        self.dev.check(self.dev.lib.cg_sumcheck_final_evals(self.h, _vp(out)))
+        return out[:2 * len(self.mles)].reshape(-1, 2)
+
+    def peek(self, i):
+        p, n, e = C.c_void_p(), C.c_uint64(), C.c_uint32()
+        self.dev.check(self.dev.lib.cg_sumcheck_peek(self.h, i, C.byref(p), C.byref(n), C.byref(e)))
+        buf = DeviceBuffer(self.dev, p.value, n.value * (16 if e.value else 8), owner=False)
+        return buf.to_host()
+
+    def close(self):
+        if self.h:
+            self.dev.lib.cg_sumcheck_destroy(self.h)
+            self.h = C.c_void_p()
+
+    @staticmethod
+    def prove(dev, mles, terms, num_vars, degree, transcript=None, challenge_fn=None, flags=0, device_challenger=False, stream=None):
+        """Returns (round_evals[num_vars,degree,2], final_evals[n_mles,2], challenges[num_vars,2]).
+
+        transcript: a StandInTranscript driven in the reference order; challenge_fn(round, evals)->ext:
+        an arbitrary host source (this is where a real BasicTranscript plugs in)."""
+        lib = dev.lib
+        descs = (_lib.CgMleDesc * max(len(mles), 1))(*[m.desc() for m in mles])
+        coeff, off, idx = _terms(terms)
+        rounds = np.zeros(2 * degree * max(num_vars, 1), np.uint64)
+        fin = np.zeros(2 * max(len(mles), 1), np.uint64)
+        chal = np.zeros(2 * max(num_vars, 1), np.uint64)
+        st = C.c_void_p(stream) if stream else None
+        if transcript is not None:
+            transcript.append_message(int(num_vars).to_bytes(8, "little"))
+            transcript.append_message(int(degree).to_bytes(8, "little"))
+            if device_challenger:
+                dev.check(lib.cg_sumcheck_prove_standin_device(dev.ctx, descs, len(mles), _vp(coeff), _vp(off), _vp(idx), len(terms),
+                                                               num_vars, degree, flags, _vp(transcript.state), _vp(rounds), _vp(fin),
+                                                               _vp(chal), st))
+            else:
+                cb = C.cast(lib.cg_standin_challenge_cb, _lib.CHALLENGE_CB)
+                dev.check(lib.cg_sumcheck_prove(dev.ctx, descs, len(mles), _vp(coeff), _vp(off), _vp(idx), len(terms), num_vars,
+                                                degree, flags, cb, _vp(transcript.state), _vp(rounds), _vp(fin), _vp(chal), st))
+        else:
+            def _cb(user, rnd, evals, deg, out):
+                e = np.ctypeslib.as_array(evals, shape=(deg * 2,)).copy()
+                r = _u64(challenge_fn(rnd, e))
+                out[0], out[1] = int(r[0]), int(r[1])
+            cb = _lib.CHALLENGE_CB(_cb)
+            dev.check(lib.cg_sumcheck_prove(dev.ctx, descs, len(mles), _vp(coeff), _vp(off), _vp(idx), len(terms), num_vars,
+                                            degree, flags, cb, None, _vp(rounds), _vp(fin), _vp(chal), st))
+        return (rounds[:2 * degree * num_vars].reshape(num_vars, degree, 2), fin[:2 * len(mles)].reshape(-1, 2),
+                chal[:2 * num_vars].reshape(num_vars, 2))
+
+
+def wit_infer_by_monomial_expr(dev, mles, terms, num_vars):
+    descs = (_lib.CgMleDesc * max(len(mles), 1))(*[m.desc() for m in mles])
+    coeff, off, idx = _terms(terms)
+    out = dev.alloc(16 << num_vars)
+    dev.check(dev.lib.cg_wit_infer_by_monomial_expr(dev.ctx, descs, len(mles), _vp(coeff), _vp(off), _vp(idx), len(terms), num_vars,
+                                                    C.c_void_p(out.ptr), None))
+    dev.sync()
+    return MultilinearExtension(dev, out, num_vars, True)
+
+
+class TowerProverSpec:
+    """Leaves of one tower: product (a, b of 2^(num_vars-1)) or logup (p1, p2, q1, q2 of 2^num_vars;
+    p1 = p2 = None -> numerators are ones)."""
+
+    def __init__(self, leaves, num_vars, is_logup):
+        self.leaves, self.num_vars, self.is_logup = leaves, num_vars, is_logup
+
+
+class TowerProver:
+    def __init__(self, dev, specs):
+        self.dev = dev
+        arr = (_lib.CgTowerSpec * len(specs))()
+        for i, s in enumerate(specs):
+            for z in range(4):
+                m = s.leaves[z] if z < len(s.leaves) else None
+                arr[i].leaves[z] = m.buf.ptr if m is not None else None
+            arr[i].num_vars = s.num_vars
+            arr[i].is_logup = 1 if s.is_logup else 0
+        self.h = C.c_void_p()
+        dev.check(dev.lib.cg_tower_build(dev.ctx, arr, len(specs), None, C.byref(self.h)))
+        self.specs = specs
+
+    def output_evals(self, i):
+        out = np.zeros(8, np.uint64)
+        self.dev.check(self.dev.lib.cg_tower_output_evals(self.h, i, _vp(out)))
+        return out
+
+    def create_proof(self, transcript):
+        """(proof u64 array, point ext array) — flattened TowerProofs (see include/ceno_b200.h)."""
+        lib = self.dev.lib
+        proof = np.zeros(max(int(lib.cg_tower_proof_len(self.h)), 1), np.uint64)
+        point = np.zeros(2 * int(lib.cg_tower_point_len(self.h)), np.uint64)
+        vt = transcript.vtable()
+        self.dev.check(lib.cg_tower_create_proof(self.h, C.byref(vt), _vp(proof), _vp(point)))
+        return proof[:int(lib.cg_tower_proof_len(self.h))], point
+
+    def close(self):
+        if self.h:
+            self.dev.lib.cg_tower_destroy(self.h)
+            self.h = C.c_void_p()

@@ -1,0 +1,1167 @@
+// cabi.cu — host side of the C ABI declared in include/ceno_b200.h.
+//
+// Owns: context (device, stream, pooled allocator, pinned staging), the sumcheck round loop
+// (the device-side counterpart of IOPProverState, external sumcheck crate),
+// eq/selector builders, tower build + prover.  All arithmetic runs in the kernels of
+// sumcheck_kernels.cuh; there is no CPU fallback — every entry point fails with an error code
+// when the device is missing.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ceno_b200.h"
+#include "sumcheck_kernels.cuh"
+
+#define CG_EXPORT extern "C" __attribute__((visibility("default")))
+
+// ------------------------------------------------------------------------------------------ ctx
+struct cg_ctx {
+    int device = 0;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    cudaStream_t own_stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    std::multimap<size_t, void*> free_blocks;
+    std::unordered_map<void*, size_t> live;
+    size_t used = 0, reserved = 0;
+    uint64_t launches = 0;
+    std::vector<std::pair<size_t, void*>> pinned_cache;   // reusable pinned staging buffers
+    std::vector<float> profile_ms;                        // per-round device time of the last CG_SC_PROFILE run
+};
+
+static int set_err(cg_ctx* c, int code, const std::string& msg) {
+    if (c) { std::lock_guard<std::mutex> g(c->mu); c->err = msg; }
+    return code;
+}
+#define CU(c, call)                                                                                  \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return set_err((c), e__ == cudaErrorMemoryAllocation ? CG_ERR_OOM : CG_ERR_CUDA,         \
+                           std::string(#call) + ": " + cudaGetErrorString(e__));                     \
+    } while (0)
+#define CHK(expr)                     \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != CG_OK) return rc__; \
+    } while (0)
+
+static inline cudaStream_t S(cg_ctx* c, cg_stream s) { return s ? (cudaStream_t)s : c->own_stream; }
+static inline unsigned grid_for(cg_ctx* c, uint64_t items, unsigned per_sm = 4) {
+    uint64_t b = (items + CG_THREADS - 1) / CG_THREADS;
+    uint64_t cap = (uint64_t)c->sm_count * per_sm;
+    if (cap > CG_MAX_BLOCKS) cap = CG_MAX_BLOCKS;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+#define LAUNCHED(c) ((c)->launches++)
+
+CG_EXPORT const char* cg_version(void) { return "ceno_b200 0.1 (sm_100a)"; }
+
+CG_EXPORT int cg_init(int device_id, cg_ctx** out) {
+    if (!out) return CG_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device_id < 0 || device_id >= n) return CG_ERR_NO_DEVICE;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device_id) != cudaSuccess) return CG_ERR_NO_DEVICE;
+    if (p.major != 10) return CG_ERR_NO_DEVICE;   // built for sm_100a only — no other code path exists
+    cg_ctx* c = new cg_ctx();
+    c->device = device_id;
+    c->sm_count = p.multiProcessorCount;
+    c->cc_major = p.major;
+    c->cc_minor = p.minor;
+    if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return CG_ERR_CUDA;
+    }
+    // internal temporaries are stream-ordered (cudaMallocAsync); keep freed memory cached in the pool
+    cudaMemPool_t mp;
+    if (cudaDeviceGetDefaultMemPool(&mp, device_id) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = c;
+    return CG_OK;
+}
+// stream-ordered temporaries: safe under the reference's one-stream-per-thread concurrency
+static int tmp_alloc(cg_ctx* c, size_t bytes, void** p, cudaStream_t st) {
+    if (bytes == 0) bytes = 256;
+    cudaError_t e = cudaMallocAsync(p, bytes, st);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(c, e == cudaErrorMemoryAllocation ? CG_ERR_OOM : CG_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+    }
+    return CG_OK;
+}
+static void tmp_free(void* p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+static void* pinned_get(cg_ctx* c, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        for (size_t i = 0; i < c->pinned_cache.size(); i++)
+            if (c->pinned_cache[i].first >= bytes) {
+                void* p = c->pinned_cache[i].second;
+                c->pinned_cache.erase(c->pinned_cache.begin() + i);
+                return p;
+            }
+    }
+    void* p = nullptr;
+    if (bytes < 4096) bytes = 4096;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+static void pinned_put(cg_ctx* c, void* p, size_t bytes) {
+    std::lock_guard<std::mutex> g(c->mu);
+    c->pinned_cache.emplace_back(bytes < 4096 ? 4096 : bytes, p);
+}
+CG_EXPORT int cg_pool_trim(cg_ctx* c) {
+    if (!c) return CG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    for (auto& kv : c->free_blocks) { cudaFree(kv.second); c->reserved -= kv.first; }
+    c->free_blocks.clear();
+    return CG_OK;
+}
+CG_EXPORT int cg_destroy(cg_ctx* c) {
+    if (!c) return CG_ERR_INVALID;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    cg_pool_trim(c);
+    for (auto& kv : c->live) cudaFree(kv.first);
+    for (auto& pc : c->pinned_cache) cudaFreeHost(pc.second);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return CG_OK;
+}
+CG_EXPORT const char* cg_last_error(cg_ctx* c) { return c ? c->err.c_str() : "null context"; }
+CG_EXPORT uint64_t cg_launch_count(cg_ctx* c) { return c ? c->launches : 0; }
+CG_EXPORT int cg_device_info(cg_ctx* c, int* sm, int* maj, int* min, size_t* fr, size_t* tot) {
+    if (!c) return CG_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    size_t f = 0, t = 0;
+    CU(c, cudaMemGetInfo(&f, &t));
+    if (sm) *sm = c->sm_count;
+    if (maj) *maj = c->cc_major;
+    if (min) *min = c->cc_minor;
+    if (fr) *fr = f;
+    if (tot) *tot = t;
+    return CG_OK;
+}
+
+// pooled allocator: exact-size free lists rounded to 2 MiB (sumcheck workspaces recur per layer)
+static size_t round_size(size_t b) {
+    const size_t g = b <= (1u << 16) ? 256 : (b <= (1u << 21) ? (1u << 16) : (1u << 21));
+    return (b + g - 1) / g * g;
+}
+CG_EXPORT int cg_alloc(cg_ctx* c, size_t bytes, void** dptr) {
+    if (!c || !dptr) return CG_ERR_INVALID;
+    if (bytes == 0) bytes = 256;
+    const size_t sz = round_size(bytes);
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        auto it = c->free_blocks.find(sz);
+        if (it != c->free_blocks.end()) {
+            *dptr = it->second;
+            c->free_blocks.erase(it);
+            c->live[*dptr] = sz;
+            c->used += sz;
+            return CG_OK;
+        }
+    }
+    CU(c, cudaSetDevice(c->device));
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, sz);
+    if (e == cudaErrorMemoryAllocation) {   // retry once after releasing the cache
+        cudaGetLastError();
+        cg_pool_trim(c);
+        e = cudaMalloc(&p, sz);
+    }
+    if (e != cudaSuccess) return set_err(c, e == cudaErrorMemoryAllocation ? CG_ERR_OOM : CG_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    std::lock_guard<std::mutex> g(c->mu);
+    c->live[p] = sz;
+    c->used += sz;
+    c->reserved += sz;
+    *dptr = p;
+    return CG_OK;
+}
+CG_EXPORT int cg_free(cg_ctx* c, void* p) {
+    if (!c) return CG_ERR_INVALID;
+    if (!p) return CG_OK;
+    std::lock_guard<std::mutex> g(c->mu);
+    auto it = c->live.find(p);
+    if (it == c->live.end()) { c->err = "cg_free: pointer not owned by this context"; return CG_ERR_INVALID; }
+    c->free_blocks.emplace(it->second, p);
+    c->used -= it->second;
+    c->live.erase(it);
+    return CG_OK;
+}
+CG_EXPORT int cg_pool_stats(cg_ctx* c, size_t* used, size_t* reserved) {
+    if (!c) return CG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(c->mu);
+    if (used) *used = c->used;
+    if (reserved) *reserved = c->reserved;
+    return CG_OK;
+}
+CG_EXPORT int cg_h2d(cg_ctx* c, void* dst, const void* src, size_t bytes, cg_stream s) {
+    if (!c) return CG_ERR_INVALID;
+    CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, S(c, s)));
+    return CG_OK;
+}
+CG_EXPORT int cg_d2h(cg_ctx* c, void* dst, const void* src, size_t bytes, cg_stream s) {
+    if (!c) return CG_ERR_INVALID;
+    CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, S(c, s)));
+    return CG_OK;
+}
+CG_EXPORT int cg_d2d(cg_ctx* c, void* dst, const void* src, size_t bytes, cg_stream s) {
+    if (!c) return CG_ERR_INVALID;
+    CU(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, S(c, s)));
+    return CG_OK;
+}
+CG_EXPORT int cg_stream_sync(cg_ctx* c, cg_stream s) {
+    if (!c) return CG_ERR_INVALID;
+    CU(c, cudaStreamSynchronize(S(c, s)));
+    return CG_OK;
+}
+CG_EXPORT int cg_host_alloc_pinned(cg_ctx* c, size_t bytes, void** h) {
+    if (!c || !h) return CG_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaHostAlloc(h, bytes, cudaHostAllocDefault));
+    return CG_OK;
+}
+CG_EXPORT int cg_host_free_pinned(cg_ctx* c, void* h) {
+    if (!c) return CG_ERR_INVALID;
+    CU(c, cudaFreeHost(h));
+    return CG_OK;
+}
+
+// ------------------------------------------------------------------------ stand-in transcript
+CG_EXPORT void cg_standin_init(uint64_t* st, const uint8_t* label, uint64_t len) {
+    uint64_t h = 0x43454E4F42323030ULL;
+    cg_tr_absorb(h, len);
+    for (uint64_t i = 0; i < len; i += 8) {
+        uint64_t w = 0;
+        for (uint64_t j = 0; j < 8 && i + j < len; j++) w |= (uint64_t)label[i + j] << (8 * j);
+        cg_tr_absorb(h, w);
+    }
+    *st = h;
+}
+CG_EXPORT void cg_standin_append_message(uint64_t* st, const uint8_t* msg, uint64_t len) { cg_tr_append_message(*st, msg, len); }
+CG_EXPORT void cg_standin_append_ext(uint64_t* st, const uint64_t* e, uint64_t n) {
+    for (uint64_t i = 0; i < 2 * n; i++) cg_tr_absorb(*st, e[i]);
+}
+CG_EXPORT void cg_standin_sample(uint64_t* st, const char* label, uint64_t out[2]) {
+    cg_tr_append_message(*st, (const uint8_t*)label, strlen(label));
+    out[0] = cg_tr_squeeze(*st);
+    out[1] = cg_tr_squeeze(*st);
+}
+CG_EXPORT void cg_standin_challenge_cb(void* user, uint32_t, const uint64_t* evals, uint32_t degree, uint64_t out[2]) {
+    uint64_t* st = (uint64_t*)user;
+    cg_standin_append_ext(st, evals, degree);
+    cg_standin_sample(st, "Internal round", out);
+}
+static void standin_vt_sample(void* u, const char* l, uint64_t o[2]) { cg_standin_sample((uint64_t*)u, l, o); }
+static void standin_vt_append(void* u, const uint64_t* e, uint64_t n) { cg_standin_append_ext((uint64_t*)u, e, n); }
+static void standin_vt_begin(void* u, uint64_t nv, uint64_t dg) {
+    cg_standin_append_message((uint64_t*)u, (const uint8_t*)&nv, 8);
+    cg_standin_append_message((uint64_t*)u, (const uint8_t*)&dg, 8);
+}
+CG_EXPORT void cg_standin_vt(uint64_t* st, cg_transcript_vt* o) {
+    o->user = st;
+    o->sample = standin_vt_sample;
+    o->append_exts = standin_vt_append;
+    o->sumcheck_begin = standin_vt_begin;
+    o->round_challenge = cg_standin_challenge_cb;
+}
+
+// ------------------------------------------------------------------------------------- eq build
+static int upload_small(cg_ctx* c, const void* h, size_t bytes, void** d, cudaStream_t st) {
+    CHK(tmp_alloc(c, bytes, d, st));
+    CU(c, cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, st));   // pageable source: staged synchronously
+    return CG_OK;
+}
+static int eq_small(cg_ctx* c, const ext_t* d_point, uint32_t k, ext_t* d_out, cudaStream_t st) {
+    const size_t smem = sizeof(ext_t) << k;
+    if (smem > 48 * 1024) CU(c, cudaFuncSetAttribute(eq_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned threads = k >= 10 ? 1024 : (k >= 5 ? (1u << k) : 32);
+    eq_small_kernel<<<1, threads, smem, st>>>(d_point, k, d_out);
+    LAUNCHED(c);
+    CU(c, cudaGetLastError());
+    return CG_OK;
+}
+// d_point: k ext on device.  Recursive two-level build.
+static int build_eq_dev(cg_ctx* c, const ext_t* d_point, uint32_t k, ext_t* d_out, uint64_t start, uint64_t end, cudaStream_t st) {
+    const uint64_t n = 1ULL << k;
+    if (k <= CG_EQ_SMALL_K) {
+        CHK(eq_small(c, d_point, k, d_out, st));
+        if (start > 0 || end < n) {
+            prefix_mask_kernel<<<grid_for(c, n), CG_THREADS, 0, st>>>(d_out, n, start, end);
+            LAUNCHED(c);
+            CU(c, cudaGetLastError());
+        }
+        return CG_OK;
+    }
+    const uint32_t lo_k = CG_EQ_SMALL_K, hi_k = k - lo_k;
+    void *L = nullptr, *H = nullptr;
+    CHK(tmp_alloc(c, sizeof(ext_t) << lo_k, &L, st));
+    CHK(tmp_alloc(c, sizeof(ext_t) << hi_k, &H, st));
+    int rc = eq_small(c, d_point, lo_k, (ext_t*)L, st);
+    if (rc == CG_OK) rc = build_eq_dev(c, d_point + lo_k, hi_k, (ext_t*)H, 0, 1ULL << hi_k, st);
+    if (rc == CG_OK) {
+        eq_outer_kernel<<<grid_for(c, n / 2, 8), CG_THREADS, 0, st>>>((const ext_t*)L, (const ext_t*)H, lo_k, n, start, end, d_out);
+        LAUNCHED(c);
+        if (cudaGetLastError() != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "eq_outer_kernel launch failed");
+    }
+    tmp_free(L, st);   // stream-ordered: released after the kernels above
+    tmp_free(H, st);
+    return rc;
+}
+CG_EXPORT int cg_build_eq(cg_ctx* c, const uint64_t* h_point, uint32_t k, uint64_t* d_out, uint64_t offset,
+                          uint64_t num_instances, cg_stream s) {
+    if (!c || !d_out || (k && !h_point) || k > 40) return set_err(c, CG_ERR_INVALID, "cg_build_eq: bad argument");
+    const uint64_t n = 1ULL << k;
+    if (offset > n || num_instances > n - offset) return set_err(c, CG_ERR_INVALID, "cg_build_eq: offset + num_instances > 2^k");
+    cudaStream_t st = S(c, s);
+    CU(c, cudaSetDevice(c->device));
+    void* d_point = nullptr;
+    uint64_t dummy[2] = {0, 0};
+    CHK(upload_small(c, k ? (const void*)h_point : (const void*)dummy, k ? sizeof(ext_t) * k : 16, &d_point, st));
+    int rc = build_eq_dev(c, (const ext_t*)d_point, k, (ext_t*)d_out, offset, offset + num_instances, st);
+    tmp_free(d_point, st);
+    return rc;
+}
+CG_EXPORT int cg_selector_compute(cg_ctx* c, int kind, const uint64_t* h_point, uint32_t nv, uint64_t offset,
+                                  uint64_t num_instances, const uint64_t* h_indices, uint32_t n_indices,
+                                  uint32_t inner_vars, uint64_t* d_out, cg_stream s) {
+    if (!c) return CG_ERR_INVALID;
+    const uint64_t n = 1ULL << nv;
+    cudaStream_t st = S(c, s);
+    switch (kind) {
+        case CG_SEL_WHOLE: return cg_build_eq(c, h_point, nv, d_out, 0, n, s);
+        case CG_SEL_PREFIX:
+            if (offset + num_instances > n) return set_err(c, CG_ERR_INVALID, "selector Prefix: end > 2^num_vars (selector.rs:144-150)");
+            return cg_build_eq(c, h_point, nv, d_out, offset, num_instances, s);
+        case CG_SEL_ORDERED_SPARSE: {
+            if (inner_vars > nv || inner_vars > 20) return set_err(c, CG_ERR_INVALID, "selector OrderedSparse: bad inner_vars");
+            CHK(cg_build_eq(c, h_point, nv, d_out, 0, n, s));
+            std::vector<uint8_t> keep(1ULL << inner_vars, 0);
+            // the reference walks `indices` in order and keeps i only when it equals the NEXT
+            // expected index (selector.rs:176-186): out-of-order entries stall the iterator.
+            uint32_t it = 0;
+            for (uint64_t i = 0; i < keep.size(); i++)
+                if (it < n_indices && h_indices[it] == i) { keep[i] = 1; it++; }
+            void* d_keep = nullptr;
+            CHK(upload_small(c, keep.data(), keep.size(), &d_keep, st));
+            sparse_mask_kernel<<<grid_for(c, n), CG_THREADS, 0, st>>>((ext_t*)d_out, n, inner_vars, num_instances, (const uint8_t*)d_keep);
+            LAUNCHED(c);
+            tmp_free(d_keep, st);
+            CU(c, cudaGetLastError());
+            return CG_OK;
+        }
+        case CG_SEL_QUARK_LT: {
+            if (offset != 0) return set_err(c, CG_ERR_INVALID, "selector QuarkBinaryTreeLessThan: offset must be 0 (selector.rs:192)");
+            if (nv == 0 || nv > 63) return set_err(c, CG_ERR_INVALID, "selector QuarkBinaryTreeLessThan: num_vars out of range");
+            CHK(cg_build_eq(c, h_point, nv, d_out, 0, n, s));
+            QuarkArgs q;
+            memset(&q, 0, sizeof(q));
+            q.num_vars = nv;
+            uint64_t ni = num_instances;
+            for (uint32_t i = 0; i < nv; i++) { q.seq[i] = ni / 2; ni = (ni + 1) / 2; }
+            quark_mask_kernel<<<grid_for(c, n), CG_THREADS, 0, st>>>((ext_t*)d_out, n, q);
+            LAUNCHED(c);
+            CU(c, cudaGetLastError());
+            return CG_OK;
+        }
+        default: return set_err(c, CG_ERR_INVALID, "cg_selector_compute: unknown kind");
+    }
+}
+
+// --------------------------------------------------------------------------------- sumcheck
+struct MleState {
+    const void* orig = nullptr;
+    uint32_t orig_is_ext = 0;
+    void* padded = nullptr;   // pooled zero-padded copy when len < 2^num_vars
+};
+struct TowerLayout {           // MLE indices of the specialised (tower-shaped) kernel
+    bool on = false;
+    uint32_t eq = 0;
+    std::vector<uint32_t> prod;   // 2 per spec
+    std::vector<ext_t> prod_alpha;
+    std::vector<uint32_t> lk;     // 4 per spec
+    std::vector<ext_t> lk_an, lk_ad;
+    bool alpha_one = false;
+};
+struct cg_sumcheck {
+    cg_ctx* ctx = nullptr;
+    cudaStream_t stream = nullptr;
+    uint32_t n_mles = 0, num_vars = 0, degree = 0, flags = 0, n_terms = 0;
+    uint32_t round = 0;        // binds so far
+    uint32_t folds = 0;        // folds applied so far
+    bool evaluated = false;    // round_eval done for the current round
+    bool pending = false;
+    ext_t pending_r;
+    const ext_t* pending_r_ptr = nullptr;   // device challenger: challenge lives on the device
+    std::vector<MleState> mles;
+    TowerLayout tl;
+    // device state
+    void* ws = nullptr;        // workspace: per MLE [n/2 | n/4] ext
+    ext_t* d_final = nullptr;  // n_mles ext
+    ext_t* d_coeff = nullptr;
+    uint32_t *d_off = nullptr, *d_idx = nullptr;
+    MleSlot* d_slots = nullptr;   // [(num_vars+1) * n_mles]  state after f folds
+    FoldSlot* d_fold = nullptr;   // [num_vars * n_mles]      fold f -> f+1
+    RoundOut out{};
+    ext_t* d_msgs = nullptr;      // num_vars * degree (device challenger) or degree
+    uint64_t* h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+    // device challenger
+    uint64_t* d_tr_state = nullptr;
+    ext_t* d_chal = nullptr;
+    std::vector<void*> owned;
+    std::vector<cudaEvent_t> ev;   // CG_SC_PROFILE: 2 events per round on the launching stream
+};
+
+// ext elements of workspace per MLE: [n/2 | n/4], kept even so every buffer stays 32-byte aligned
+static uint64_t ws_per(uint64_t n) { uint64_t p = n / 2 + n / 4; p = (p + 1) & ~1ULL; return p < 2 ? 2 : p; }
+// state of MLE i after f folds
+static const void* mle_buf(const cg_sumcheck* sc, uint32_t i, uint32_t f) {
+    if (f == 0) return sc->mles[i].padded ? sc->mles[i].padded : sc->mles[i].orig;
+    const uint64_t n = 1ULL << sc->num_vars;
+    const uint64_t per = ws_per(n);
+    ext_t* base = (ext_t*)sc->ws + (uint64_t)i * per;
+    return (f & 1) ? (const void*)base : (const void*)(base + n / 2);
+}
+static uint32_t mle_is_ext(const cg_sumcheck* sc, uint32_t i, uint32_t f) { return f == 0 ? sc->mles[i].orig_is_ext : 1u; }
+
+static int sc_alloc(cg_sumcheck* sc, size_t bytes, void** p) {
+    CHK(tmp_alloc(sc->ctx, bytes, p, sc->stream));
+    sc->owned.push_back(*p);
+    return CG_OK;
+}
+
+CG_EXPORT int cg_sumcheck_destroy(cg_sumcheck* sc) {
+    if (!sc) return CG_ERR_INVALID;
+    for (void* p : sc->owned) tmp_free(p, sc->stream);   // stream-ordered: no synchronisation needed
+    if (sc->h_pinned) pinned_put(sc->ctx, sc->h_pinned, sc->h_pinned_bytes);
+    delete sc;
+    return CG_OK;
+}
+
+static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, uint32_t num_vars, uint32_t degree,
+                            uint32_t flags, cudaStream_t st, cg_sumcheck** out) {
+    if (!c || !out || (n_mles && !mles)) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: null argument");
+    if (degree == 0 || degree > CG_MAX_DEGREE) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: degree must be in 1..8");
+    if (num_vars > 34) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: num_vars too large");
+    for (uint32_t i = 0; i < n_mles; i++) {
+        if (mles[i].num_vars != num_vars)
+            return set_err(c, CG_ERR_UNSUPPORTED,
+                           "mixed num_vars (frontloaded batched sumcheck) is defined only in the un-vendored upstream crate (SURVEY §C-1)");
+        if (!mles[i].dptr || mles[i].len > (1ULL << num_vars) || ((uintptr_t)mles[i].dptr & 15))
+            return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: MLE pointer null/unaligned or len > 2^num_vars");
+    }
+    CU(c, cudaSetDevice(c->device));
+    cg_sumcheck* sc = new cg_sumcheck();
+    sc->ctx = c;
+    sc->stream = st;
+    sc->n_mles = n_mles;
+    sc->num_vars = num_vars;
+    sc->degree = degree;
+    sc->flags = flags;
+    sc->mles.resize(n_mles);
+    const uint64_t n = 1ULL << num_vars;
+    int rc = CG_OK;
+    for (uint32_t i = 0; i < n_mles && rc == CG_OK; i++) {
+        sc->mles[i].orig = mles[i].dptr;
+        sc->mles[i].orig_is_ext = mles[i].is_ext ? 1 : 0;
+        const size_t es = mles[i].is_ext ? 16 : 8;
+        const bool misaligned32 = ((uintptr_t)mles[i].dptr & 31) != 0;   // 256-bit loads need 32 B
+        if (mles[i].len < n || misaligned32) {   // occupied prefix / odd alignment: pooled zero-padded copy
+            rc = sc_alloc(sc, es * n, &sc->mles[i].padded);
+            if (rc == CG_OK && cudaMemsetAsync(sc->mles[i].padded, 0, es * n, st) != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "memset failed");
+            if (rc == CG_OK && cudaMemcpyAsync(sc->mles[i].padded, mles[i].dptr, es * mles[i].len, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+                rc = set_err(c, CG_ERR_CUDA, "pad copy failed");
+        }
+    }
+    if (rc == CG_OK && num_vars >= 1) rc = sc_alloc(sc, (size_t)n_mles * ws_per(n) * sizeof(ext_t), &sc->ws);
+    void* p = nullptr;
+    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(ext_t) * (n_mles + 1), &p); sc->d_final = (ext_t*)p; }
+    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(ext_t) * CG_MAX_BLOCKS * CG_MAX_DEGREE, &p); sc->out.partials = (ext_t*)p; }
+    if (rc == CG_OK) { rc = sc_alloc(sc, 256, &p); sc->out.ticket = (unsigned*)p; }
+    if (rc == CG_OK && cudaMemsetAsync(sc->out.ticket, 0, 256, st) != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "memset failed");
+    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(ext_t) * (size_t)(num_vars + 1) * degree, &p); sc->d_msgs = (ext_t*)p; }
+    if (rc == CG_OK) {
+        sc->h_pinned_bytes = sizeof(ext_t) * (CG_MAX_DEGREE + 4);
+        sc->h_pinned = (uint64_t*)pinned_get(c, sc->h_pinned_bytes);
+        if (!sc->h_pinned) rc = set_err(c, CG_ERR_CUDA, "cudaHostAlloc failed");
+    }
+    if (rc != CG_OK) { cg_sumcheck_destroy(sc); return rc; }
+    *out = sc;
+    return CG_OK;
+}
+
+// upload per-round slot tables for the generic kernels
+static int sc_upload_tables(cg_sumcheck* sc) {
+    cg_ctx* c = sc->ctx;
+    const uint32_t m = sc->n_mles, nv = sc->num_vars;
+    std::vector<MleSlot> slots((size_t)(nv + 1) * m);
+    std::vector<FoldSlot> folds((size_t)(nv ? nv : 1) * m);
+    for (uint32_t f = 0; f <= nv; f++)
+        for (uint32_t i = 0; i < m; i++) {
+            if (f == nv && nv > 0) { slots[(size_t)f * m + i] = MleSlot{sc->d_final + i, 1u, 0u}; continue; }
+            slots[(size_t)f * m + i] = MleSlot{mle_buf(sc, i, f), mle_is_ext(sc, i, f), f == 0 ? 1u : 0u};
+        }
+    for (uint32_t f = 0; f < nv; f++)
+        for (uint32_t i = 0; i < m; i++) {
+            ext_t* dst = (f + 1 == nv) ? sc->d_final + i : (ext_t*)mle_buf(sc, i, f + 1);
+            folds[(size_t)f * m + i] = FoldSlot{mle_buf(sc, i, f), dst, mle_is_ext(sc, i, f), f == 0 ? 1u : 0u};
+        }
+    void* p = nullptr;
+    CHK(sc_alloc(sc, sizeof(MleSlot) * slots.size() + 16, &p));
+    sc->d_slots = (MleSlot*)p;
+    CU(c, cudaMemcpyAsync(p, slots.data(), sizeof(MleSlot) * slots.size(), cudaMemcpyHostToDevice, sc->stream));
+    CHK(sc_alloc(sc, sizeof(FoldSlot) * folds.size() + 16, &p));
+    sc->d_fold = (FoldSlot*)p;
+    CU(c, cudaMemcpyAsync(p, folds.data(), sizeof(FoldSlot) * folds.size(), cudaMemcpyHostToDevice, sc->stream));
+    CU(c, cudaStreamSynchronize(sc->stream));   // host vectors go out of scope
+    return CG_OK;
+}
+
+CG_EXPORT int cg_sumcheck_create(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t* coeff,
+                                 const uint32_t* off, const uint32_t* idx, uint32_t n_terms, uint32_t num_vars,
+                                 uint32_t degree, uint32_t flags, cg_stream s, cg_sumcheck** out) {
+    if (!c) return CG_ERR_INVALID;
+    if (n_terms && (!coeff || !off || !idx)) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: null term table");
+    for (uint32_t t = 0; t < n_terms; t++) {
+        if (off[t + 1] < off[t] || off[t + 1] - off[t] > degree) return set_err(c, CG_ERR_INVALID, "term has more factors than `degree`");
+        for (uint32_t q = off[t]; q < off[t + 1]; q++)
+            if (idx[q] >= n_mles) return set_err(c, CG_ERR_INVALID, "term references an MLE index out of range");
+    }
+    cudaStream_t st = S(c, s);
+    cg_sumcheck* sc = nullptr;
+    CHK(sc_create_common(c, mles, n_mles, num_vars, degree, flags, st, &sc));
+    sc->n_terms = n_terms;
+    int rc = CG_OK;
+    void* p = nullptr;
+    const uint32_t n_idx = n_terms ? off[n_terms] : 0;
+    rc = sc_alloc(sc, sizeof(ext_t) * (n_terms + 1), &p); sc->d_coeff = (ext_t*)p;
+    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(uint32_t) * (n_terms + 2), &p); sc->d_off = (uint32_t*)p; }
+    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(uint32_t) * (n_idx + 1), &p); sc->d_idx = (uint32_t*)p; }
+    if (rc == CG_OK && n_terms) {
+        // canonicalise coefficients on the host (inputs may be any u64)
+        std::vector<uint64_t> cc(2 * (size_t)n_terms);
+        for (size_t i = 0; i < cc.size(); i++) cc[i] = coeff[i] >= GL_P ? coeff[i] - GL_P : coeff[i];
+        if (cudaMemcpyAsync(sc->d_coeff, cc.data(), sizeof(ext_t) * n_terms, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(sc->d_off, off, sizeof(uint32_t) * (n_terms + 1), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            (n_idx && cudaMemcpyAsync(sc->d_idx, idx, sizeof(uint32_t) * n_idx, cudaMemcpyHostToDevice, st) != cudaSuccess) ||
+            cudaStreamSynchronize(st) != cudaSuccess)
+            rc = set_err(c, CG_ERR_CUDA, "term table upload failed");
+    } else if (rc == CG_OK) {
+        uint32_t z = 0;
+        if (cudaMemcpyAsync(sc->d_off, &z, 4, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "upload failed");
+    }
+    if (rc == CG_OK) rc = sc_upload_tables(sc);
+    // shape detection: one degree-3 product of three distinct ext MLEs -> tower kernel (T3)
+    if (rc == CG_OK && !(flags & CG_SC_FORCE_GENERIC) && n_terms == 1 && degree == 3 && off[1] - off[0] == 3 && num_vars >= 1) {
+        const uint32_t a = idx[off[0]], b = idx[off[0] + 1], d = idx[off[0] + 2];
+        if (a != b && b != d && a != d && mles[a].is_ext && mles[b].is_ext && mles[d].is_ext) {
+            sc->tl.on = true;
+            sc->tl.eq = a;
+            sc->tl.prod = {b, d};
+            ext_t al = ext_t{coeff[0] >= GL_P ? coeff[0] - GL_P : coeff[0], coeff[1] >= GL_P ? coeff[1] - GL_P : coeff[1]};
+            sc->tl.prod_alpha = {al};
+            sc->tl.alpha_one = (al.c0 == 1 && al.c1 == 0);
+        }
+    }
+    if (rc != CG_OK) { cg_sumcheck_destroy(sc); return rc; }
+    *out = sc;
+    return CG_OK;
+}
+
+CG_EXPORT uint32_t cg_sumcheck_round(const cg_sumcheck* sc) { return sc ? sc->round : 0; }
+
+static int launch_fold(cg_sumcheck* sc, uint32_t f) {   // fold state f -> f+1
+    cg_ctx* c = sc->ctx;
+    const uint64_t n_out = 1ULL << (sc->num_vars - f - 1);
+    dim3 grid(grid_for(c, n_out), sc->n_mles);
+    if (sc->n_mles == 0) return CG_OK;
+    fold_kernel<<<grid, CG_THREADS, 0, sc->stream>>>(sc->d_fold + (size_t)f * sc->n_mles, n_out, sc->pending_r, sc->pending_r_ptr);
+    LAUNCHED(c);
+    CU(c, cudaGetLastError());
+    return CG_OK;
+}
+template <int D>
+static void launch_generic_d(cg_sumcheck* sc, const GenericArgs& a, unsigned grid) {
+    generic_round_kernel<D><<<grid, CG_THREADS, 0, sc->stream>>>(a);
+}
+static int launch_generic_eval(cg_sumcheck* sc, uint32_t f, const RoundOut& ro) {   // evaluate state f
+    cg_ctx* c = sc->ctx;
+    GenericArgs a;
+    a.mles = sc->d_slots + (size_t)f * sc->n_mles;
+    a.coeff = sc->d_coeff;
+    a.off = sc->d_off;
+    a.idx = sc->d_idx;
+    a.n_terms = sc->n_terms;
+    a.n_pairs = 1ULL << (sc->num_vars - f - 1);
+    a.out = ro;
+    const unsigned grid = grid_for(c, a.n_pairs);
+    switch (sc->degree) {
+        case 1: launch_generic_d<1>(sc, a, grid); break;
+        case 2: launch_generic_d<2>(sc, a, grid); break;
+        case 3: launch_generic_d<3>(sc, a, grid); break;
+        case 4: launch_generic_d<4>(sc, a, grid); break;
+        case 5: launch_generic_d<5>(sc, a, grid); break;
+        case 6: launch_generic_d<6>(sc, a, grid); break;
+        case 7: launch_generic_d<7>(sc, a, grid); break;
+        default: launch_generic_d<8>(sc, a, grid); break;
+    }
+    LAUNCHED(c);
+    CU(c, cudaGetLastError());
+    return CG_OK;
+}
+// tower-shaped kernel: evaluate state f (fold==false) or fold f-1 -> f and evaluate (fold==true)
+static int launch_tower(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro) {
+    cg_ctx* c = sc->ctx;
+    const TowerLayout& tl = sc->tl;
+    TowerArgs a;
+    memset(&a, 0, sizeof(a));
+    const uint32_t src = fold ? f - 1 : f;
+    auto in = [&](uint32_t i) { return (const ext_t*)mle_buf(sc, i, src); };
+    auto outp = [&](uint32_t i) { return fold ? (ext_t*)mle_buf(sc, i, f) : (ext_t*)nullptr; };
+    a.eq_in = in(tl.eq);
+    a.eq_out = outp(tl.eq);
+    a.n_prod = (int)tl.prod_alpha.size();
+    a.n_logup = (int)tl.lk_an.size();
+    for (int p = 0; p < a.n_prod; p++) {
+        for (int z = 0; z < 2; z++) { a.prod_in[p][z] = in(tl.prod[2 * p + z]); a.prod_out[p][z] = outp(tl.prod[2 * p + z]); }
+        a.alpha_prod[p] = tl.prod_alpha[p];
+    }
+    for (int l = 0; l < a.n_logup; l++) {
+        for (int z = 0; z < 4; z++) { a.lk_in[l][z] = in(tl.lk[4 * l + z]); a.lk_out[l][z] = outp(tl.lk[4 * l + z]); }
+        a.alpha_num[l] = tl.lk_an[l];
+        a.alpha_den[l] = tl.lk_ad[l];
+    }
+    a.alpha_one = tl.alpha_one ? 1 : 0;
+    a.n_pairs = 1ULL << (sc->num_vars - f - 1);
+    a.r = sc->pending_r;
+    a.r_ptr = sc->pending_r_ptr;
+    a.out = ro;
+    const unsigned grid = grid_for(c, a.n_pairs);
+    const bool canon = (src == 0);   // reading caller-provided buffers
+    if (fold) {
+        if (canon) tower_round_kernel<true, true><<<grid, CG_THREADS, 0, sc->stream>>>(a);
+        else tower_round_kernel<true, false><<<grid, CG_THREADS, 0, sc->stream>>>(a);
+    } else {
+        if (canon) tower_round_kernel<false, true><<<grid, CG_THREADS, 0, sc->stream>>>(a);
+        else tower_round_kernel<false, false><<<grid, CG_THREADS, 0, sc->stream>>>(a);
+    }
+    LAUNCHED(c);
+    CU(c, cudaGetLastError());
+    return CG_OK;
+}
+
+// enqueue the kernels of the current round's evaluation (applying a pending fold first)
+static int sc_enqueue_round(cg_sumcheck* sc, const RoundOut& ro) {
+    if (sc->round >= sc->num_vars) return set_err(sc->ctx, CG_ERR_STATE, "round_eval: all variables are already bound");
+    if (sc->pending) {
+        const uint32_t f = sc->folds;   // fold f -> f+1, then evaluate state f+1
+        if (sc->tl.on && !(sc->flags & CG_SC_NO_FUSE)) {
+            CHK(launch_tower(sc, f + 1, true, ro));
+        } else {
+            CHK(launch_fold(sc, f));
+            if (sc->tl.on) CHK(launch_tower(sc, f + 1, false, ro));
+            else CHK(launch_generic_eval(sc, f + 1, ro));
+        }
+        sc->folds++;
+        sc->pending = false;
+    } else {
+        if (sc->tl.on) CHK(launch_tower(sc, sc->folds, false, ro));
+        else CHK(launch_generic_eval(sc, sc->folds, ro));
+    }
+    sc->evaluated = true;
+    return CG_OK;
+}
+
+CG_EXPORT int cg_sumcheck_round_eval(cg_sumcheck* sc, uint64_t* h_out) {
+    if (!sc || !h_out) return CG_ERR_INVALID;
+    cg_ctx* c = sc->ctx;
+    CU(c, cudaSetDevice(c->device));
+    RoundOut ro = sc->out;
+    ro.d_out = sc->d_msgs;
+    ro.d_tr_state = nullptr;
+    ro.d_r_out = nullptr;
+    CHK(sc_enqueue_round(sc, ro));
+    CU(c, cudaMemcpyAsync(sc->h_pinned, sc->d_msgs, sizeof(ext_t) * sc->degree, cudaMemcpyDeviceToHost, sc->stream));
+    CU(c, cudaStreamSynchronize(sc->stream));
+    memcpy(h_out, sc->h_pinned, sizeof(ext_t) * sc->degree);
+    return CG_OK;
+}
+
+static int sc_apply_pending_fold_only(cg_sumcheck* sc) {
+    if (!sc->pending) return CG_OK;
+    CHK(launch_fold(sc, sc->folds));
+    sc->folds++;
+    sc->pending = false;
+    return CG_OK;
+}
+
+static int sc_bind_common(cg_sumcheck* sc) {
+    sc->round++;
+    sc->evaluated = false;
+    if (sc->round == sc->num_vars) CHK(sc_apply_pending_fold_only(sc));   // last variable: produce the final evaluations
+    return CG_OK;
+}
+CG_EXPORT int cg_sumcheck_bind(cg_sumcheck* sc, const uint64_t r[2]) {
+    if (!sc || !r) return CG_ERR_INVALID;
+    if (sc->round >= sc->num_vars) return set_err(sc->ctx, CG_ERR_STATE, "bind: all variables are already bound");
+    CU(sc->ctx, cudaSetDevice(sc->ctx->device));
+    CHK(sc_apply_pending_fold_only(sc));   // bind without an intervening round_eval: plain fold
+    sc->pending = true;
+    sc->pending_r = ext_t{r[0] >= GL_P ? r[0] - GL_P : r[0], r[1] >= GL_P ? r[1] - GL_P : r[1]};
+    sc->pending_r_ptr = nullptr;
+    return sc_bind_common(sc);
+}
+
+CG_EXPORT int cg_sumcheck_final_evals(cg_sumcheck* sc, uint64_t* h_out) {
+    if (!sc || !h_out) return CG_ERR_INVALID;
+    cg_ctx* c = sc->ctx;
+    if (sc->round != sc->num_vars) return set_err(c, CG_ERR_STATE, "final_evals: not all variables are bound yet");
+    CU(c, cudaSetDevice(c->device));
+    if (sc->num_vars == 0) {   // zero-variable sumcheck is a no-op: the single value of each MLE
+        for (uint32_t i = 0; i < sc->n_mles; i++) {
+            uint64_t v[2] = {0, 0};
+            CU(c, cudaMemcpyAsync(v, sc->mles[i].padded ? sc->mles[i].padded : sc->mles[i].orig, sc->mles[i].orig_is_ext ? 16 : 8,
+                                  cudaMemcpyDeviceToHost, sc->stream));
+            CU(c, cudaStreamSynchronize(sc->stream));
+            h_out[2 * i] = v[0] >= GL_P ? v[0] - GL_P : v[0];
+            h_out[2 * i + 1] = v[1] >= GL_P ? v[1] - GL_P : v[1];
+        }
+        return CG_OK;
+    }
+    CU(c, cudaMemcpyAsync(h_out, sc->d_final, sizeof(ext_t) * sc->n_mles, cudaMemcpyDeviceToHost, sc->stream));
+    CU(c, cudaStreamSynchronize(sc->stream));
+    return CG_OK;
+}
+
+CG_EXPORT int cg_sumcheck_peek(cg_sumcheck* sc, uint32_t i, const void** dptr, uint64_t* len, uint32_t* is_ext) {
+    if (!sc || i >= sc->n_mles) return CG_ERR_INVALID;
+    CHK(sc_apply_pending_fold_only(sc));
+    CU(sc->ctx, cudaStreamSynchronize(sc->stream));
+    const uint32_t f = sc->folds;
+    if (dptr) *dptr = (f == sc->num_vars && f > 0) ? (const void*)(sc->d_final + i) : mle_buf(sc, i, f);
+    if (len) *len = 1ULL << (sc->num_vars - f);
+    if (is_ext) *is_ext = mle_is_ext(sc, i, f);
+    return CG_OK;
+}
+
+static void prof_begin(cg_sumcheck* sc) {
+    if (!(sc->flags & CG_SC_PROFILE)) return;
+    sc->ev.resize(2 * (size_t)sc->num_vars);
+    for (auto& e : sc->ev) cudaEventCreate(&e);
+}
+static void prof_mark(cg_sumcheck* sc, uint32_t j, int end) {
+    if (sc->flags & CG_SC_PROFILE) cudaEventRecord(sc->ev[2 * j + end], sc->stream);
+}
+static void prof_end(cg_sumcheck* sc) {
+    if (!(sc->flags & CG_SC_PROFILE)) return;
+    cudaStreamSynchronize(sc->stream);
+    std::lock_guard<std::mutex> g(sc->ctx->mu);
+    sc->ctx->profile_ms.assign(sc->num_vars, 0.f);
+    for (uint32_t j = 0; j < sc->num_vars; j++) cudaEventElapsedTime(&sc->ctx->profile_ms[j], sc->ev[2 * j], sc->ev[2 * j + 1]);
+    for (auto& e : sc->ev) cudaEventDestroy(e);
+    sc->ev.clear();
+}
+CG_EXPORT int cg_profile_last(cg_ctx* c, float* ms_out, uint32_t cap, uint32_t* n) {
+    if (!c || !n) return CG_ERR_INVALID;
+    std::lock_guard<std::mutex> g(c->mu);
+    *n = (uint32_t)c->profile_ms.size();
+    for (uint32_t i = 0; i < *n && i < cap && ms_out; i++) ms_out[i] = c->profile_ms[i];
+    return CG_OK;
+}
+
+static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t* h_rounds, uint64_t* h_final, uint64_t* h_chal) {
+    prof_begin(sc);
+    for (uint32_t j = 0; j < sc->num_vars; j++) {
+        uint64_t* msg = h_rounds + (size_t)j * sc->degree * 2;
+        prof_mark(sc, j, 0);
+        {   // round_eval with the end-of-kernels mark placed before the D2H copy
+            cg_ctx* c = sc->ctx;
+            RoundOut ro = sc->out;
+            ro.d_out = sc->d_msgs;
+            ro.d_tr_state = nullptr;
+            ro.d_r_out = nullptr;
+            CHK(sc_enqueue_round(sc, ro));
+            prof_mark(sc, j, 1);
+            CU(c, cudaMemcpyAsync(sc->h_pinned, sc->d_msgs, sizeof(ext_t) * sc->degree, cudaMemcpyDeviceToHost, sc->stream));
+            CU(c, cudaStreamSynchronize(sc->stream));
+            memcpy(msg, sc->h_pinned, sizeof(ext_t) * sc->degree);
+        }
+        uint64_t r[2] = {0, 0};
+        cb(user, j, msg, sc->degree, r);
+        if (h_chal) { h_chal[2 * j] = r[0]; h_chal[2 * j + 1] = r[1]; }
+        CHK(cg_sumcheck_bind(sc, r));
+    }
+    prof_end(sc);
+    if (h_final) CHK(cg_sumcheck_final_evals(sc, h_final));
+    return CG_OK;
+}
+
+CG_EXPORT int cg_sumcheck_prove(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t* coeff,
+                                const uint32_t* off, const uint32_t* idx, uint32_t n_terms, uint32_t num_vars,
+                                uint32_t degree, uint32_t flags, cg_challenge_cb cb, void* user, uint64_t* h_rounds,
+                                uint64_t* h_final, uint64_t* h_chal, cg_stream s) {
+    if (!cb || (!h_rounds && num_vars)) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_prove: null callback/output");
+    cg_sumcheck* sc = nullptr;
+    CHK(cg_sumcheck_create(c, mles, n_mles, coeff, off, idx, n_terms, num_vars, degree, flags, s, &sc));
+    int rc = sc_run_host(sc, cb, user, h_rounds, h_final, h_chal);
+    cg_sumcheck_destroy(sc);
+    return rc;
+}
+
+// device-resident challenger: enqueue every round back to back, read everything once at the end
+static int sc_run_device(cg_sumcheck* sc, uint64_t* h_state, uint64_t* h_rounds, uint64_t* h_final, uint64_t* h_chal) {
+    cg_ctx* c = sc->ctx;
+    void* p = nullptr;
+    CHK(sc_alloc(sc, 256, &p));
+    sc->d_tr_state = (uint64_t*)p;
+    CHK(sc_alloc(sc, sizeof(ext_t) * (sc->num_vars + 1), &p));
+    sc->d_chal = (ext_t*)p;
+    CU(c, cudaMemcpyAsync(sc->d_tr_state, h_state, 8, cudaMemcpyHostToDevice, sc->stream));
+    prof_begin(sc);
+    for (uint32_t j = 0; j < sc->num_vars; j++) {
+        RoundOut ro = sc->out;
+        ro.d_out = sc->d_msgs + (size_t)j * sc->degree;
+        ro.d_tr_state = sc->d_tr_state;
+        ro.d_r_out = sc->d_chal + j;
+        prof_mark(sc, j, 0);
+        CHK(sc_enqueue_round(sc, ro));
+        prof_mark(sc, j, 1);
+        CHK(sc_apply_pending_fold_only(sc));
+        sc->pending = true;
+        sc->pending_r_ptr = sc->d_chal + j;
+        CHK(sc_bind_common(sc));
+    }
+    if (sc->num_vars) {
+        CU(c, cudaMemcpyAsync(h_rounds, sc->d_msgs, sizeof(ext_t) * sc->num_vars * sc->degree, cudaMemcpyDeviceToHost, sc->stream));
+        if (h_chal) CU(c, cudaMemcpyAsync(h_chal, sc->d_chal, sizeof(ext_t) * sc->num_vars, cudaMemcpyDeviceToHost, sc->stream));
+    }
+    CU(c, cudaMemcpyAsync(h_state, sc->d_tr_state, 8, cudaMemcpyDeviceToHost, sc->stream));
+    CU(c, cudaStreamSynchronize(sc->stream));
+    prof_end(sc);
+    if (h_final) CHK(cg_sumcheck_final_evals(sc, h_final));
+    return CG_OK;
+}
+CG_EXPORT int cg_sumcheck_prove_standin_device(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t* coeff,
+                                               const uint32_t* off, const uint32_t* idx, uint32_t n_terms, uint32_t num_vars,
+                                               uint32_t degree, uint32_t flags, uint64_t* h_state, uint64_t* h_rounds,
+                                               uint64_t* h_final, uint64_t* h_chal, cg_stream s) {
+    if (!h_state || (!h_rounds && num_vars)) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_prove_standin_device: null output");
+    cg_sumcheck* sc = nullptr;
+    CHK(cg_sumcheck_create(c, mles, n_mles, coeff, off, idx, n_terms, num_vars, degree, flags, s, &sc));
+    int rc = sc_run_device(sc, h_state, h_rounds, h_final, h_chal);
+    cg_sumcheck_destroy(sc);
+    return rc;
+}
+
+// ------------------------------------------------------------------- fold / evaluate helpers
+CG_EXPORT int cg_fix_variable(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t r[2],
+                              uint64_t* const* d_out, cg_stream s) {
+    if (!c || !mles || !r || !d_out) return CG_ERR_INVALID;
+    if (n_mles == 0) return CG_OK;
+    cudaStream_t st = S(c, s);
+    CU(c, cudaSetDevice(c->device));
+    const uint32_t nv = mles[0].num_vars;
+    if (nv == 0) return set_err(c, CG_ERR_INVALID, "cg_fix_variable: MLE has no variables");
+    std::vector<FoldSlot> slots(n_mles);
+    for (uint32_t i = 0; i < n_mles; i++) {
+        if (mles[i].num_vars != nv) return set_err(c, CG_ERR_INVALID, "cg_fix_variable: all MLEs must have the same num_vars");
+        if (mles[i].len != (1ULL << nv)) return set_err(c, CG_ERR_UNSUPPORTED, "cg_fix_variable: len must equal 2^num_vars");
+        if (((uintptr_t)mles[i].dptr & 31) || ((uintptr_t)d_out[i] & 15)) return set_err(c, CG_ERR_INVALID, "cg_fix_variable: pointers must be 32-byte (in) / 16-byte (out) aligned");
+        slots[i] = FoldSlot{mles[i].dptr, (ext_t*)d_out[i], mles[i].is_ext ? 1u : 0u, 1u};
+    }
+    void* d_slots = nullptr;
+    CHK(upload_small(c, slots.data(), sizeof(FoldSlot) * n_mles, &d_slots, st));
+    const uint64_t n_out = 1ULL << (nv - 1);
+    ext_t rv{r[0] >= GL_P ? r[0] - GL_P : r[0], r[1] >= GL_P ? r[1] - GL_P : r[1]};
+    fold_kernel<<<dim3(grid_for(c, n_out), n_mles), CG_THREADS, 0, st>>>((const FoldSlot*)d_slots, n_out, rv, nullptr);
+    LAUNCHED(c);
+    tmp_free(d_slots, st);
+    CU(c, cudaGetLastError());
+    return CG_OK;
+}
+
+CG_EXPORT int cg_mle_evaluate(cg_ctx* c, const cg_mle_desc* mle, const uint64_t* h_point, uint64_t h_out[2], cg_stream s) {
+    if (!c || !mle || !h_out) return CG_ERR_INVALID;
+    cg_sumcheck* sc = nullptr;
+    CHK(cg_sumcheck_create(c, mle, 1, nullptr, nullptr, nullptr, 0, mle->num_vars, 1, CG_SC_FORCE_GENERIC, s, &sc));
+    int rc = CG_OK;
+    for (uint32_t j = 0; j < mle->num_vars && rc == CG_OK; j++) rc = cg_sumcheck_bind(sc, h_point + 2 * j);
+    if (rc == CG_OK) rc = cg_sumcheck_final_evals(sc, h_out);
+    cg_sumcheck_destroy(sc);
+    return rc;
+}
+
+CG_EXPORT int cg_wit_infer_by_monomial_expr(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t* coeff,
+                                            const uint32_t* off, const uint32_t* idx, uint32_t n_terms, uint32_t num_vars,
+                                            uint64_t* d_out, cg_stream s) {
+    if (!c || !d_out || (n_terms && (!coeff || !off || !idx))) return CG_ERR_INVALID;
+    cudaStream_t st = S(c, s);
+    CU(c, cudaSetDevice(c->device));
+    const uint64_t n = 1ULL << num_vars;
+    std::vector<MleSlot> slots(n_mles ? n_mles : 1);
+    for (uint32_t i = 0; i < n_mles; i++) {
+        if (mles[i].num_vars != num_vars || mles[i].len != n) return set_err(c, CG_ERR_UNSUPPORTED, "wit_infer: every MLE must be full length 2^num_vars");
+        slots[i] = MleSlot{mles[i].dptr, mles[i].is_ext ? 1u : 0u, 1u};
+    }
+    const uint32_t n_idx = n_terms ? off[n_terms] : 0;
+    for (uint32_t q = 0; q < n_idx; q++) if (idx[q] >= n_mles) return set_err(c, CG_ERR_INVALID, "wit_infer: MLE index out of range");
+    std::vector<uint64_t> cc(2 * (size_t)(n_terms ? n_terms : 1), 0);
+    for (size_t i = 0; i < 2 * (size_t)n_terms; i++) cc[i] = coeff[i] >= GL_P ? coeff[i] - GL_P : coeff[i];
+    std::vector<uint32_t> offv(n_terms + 1, 0), idxv(n_idx ? n_idx : 1, 0);
+    if (n_terms) memcpy(offv.data(), off, sizeof(uint32_t) * (n_terms + 1));
+    if (n_idx) memcpy(idxv.data(), idx, sizeof(uint32_t) * n_idx);
+    void *d_slots = nullptr, *d_c = nullptr, *d_o = nullptr, *d_i = nullptr;
+    int rc = upload_small(c, slots.data(), sizeof(MleSlot) * slots.size(), &d_slots, st);
+    if (rc == CG_OK) rc = upload_small(c, cc.data(), sizeof(uint64_t) * cc.size(), &d_c, st);
+    if (rc == CG_OK) rc = upload_small(c, offv.data(), sizeof(uint32_t) * offv.size(), &d_o, st);
+    if (rc == CG_OK) rc = upload_small(c, idxv.data(), sizeof(uint32_t) * idxv.size(), &d_i, st);
+    if (rc == CG_OK) {
+        InferArgs a{(const MleSlot*)d_slots, (const ext_t*)d_c, (const uint32_t*)d_o, (const uint32_t*)d_i, n_terms, n, (ext_t*)d_out};
+        wit_infer_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, st>>>(a);
+        LAUNCHED(c);
+        if (cudaGetLastError() != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "wit_infer_kernel launch failed");
+    }
+    tmp_free(d_slots, st); tmp_free(d_c, st); tmp_free(d_o, st); tmp_free(d_i, st);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------- tower
+struct TowerSpecState {
+    bool is_logup = false;
+    uint32_t num_vars = 0;
+    uint32_t layers = 0;             // witness.len(): product num_vars, logup num_vars + 1
+    std::vector<const ext_t*> layer; // layer[l] -> base of [a|b] or [p1|p2|q1|q2] with arrays of 2^l ext
+    const ext_t* leaves[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ones = false;               // logup numerators implicit ones
+};
+struct cg_tower {
+    cg_ctx* ctx = nullptr;
+    cudaStream_t stream = nullptr;
+    std::vector<TowerSpecState> specs;
+    std::vector<void*> owned;
+    uint32_t max_round = 0;          // max_round_index
+    uint32_t n_prod = 0, n_logup = 0;
+};
+CG_EXPORT int cg_tower_destroy(cg_tower* tw) {
+    if (!tw) return CG_ERR_INVALID;
+    for (void* p : tw->owned) tmp_free(p, tw->stream);
+    delete tw;
+    return CG_OK;
+}
+// array z of layer l of spec sp
+static const ext_t* tower_arr(const TowerSpecState& sp, uint32_t l, uint32_t z) {
+    if (l + 1 == sp.layers && !(sp.is_logup && sp.ones && z < 2)) {
+        if (!sp.is_logup) return sp.leaves[z];
+        return sp.leaves[z];
+    }
+    return sp.layer[l] + ((uint64_t)z << l);
+}
+CG_EXPORT int cg_tower_build(cg_ctx* c, const cg_tower_spec* specs, uint32_t n_specs, cg_stream s, cg_tower** out) {
+    if (!c || !specs || !out || n_specs == 0) return set_err(c, CG_ERR_INVALID, "cg_tower_build: bad argument");
+    cudaStream_t st = S(c, s);
+    CU(c, cudaSetDevice(c->device));
+    cg_tower* tw = new cg_tower();
+    tw->ctx = c;
+    tw->stream = st;
+    int rc = CG_OK;
+    // reference order: product specs first, then logup specs (cpu/mod.rs:405-413)
+    for (int pass = 0; pass < 2 && rc == CG_OK; pass++)
+        for (uint32_t i = 0; i < n_specs && rc == CG_OK; i++) {
+            const cg_tower_spec& in = specs[i];
+            if ((in.is_logup != 0) != (pass == 1)) continue;
+            TowerSpecState sp;
+            sp.is_logup = in.is_logup != 0;
+            sp.num_vars = in.num_vars;
+            if (in.num_vars == 0 || in.num_vars > 32) { rc = set_err(c, CG_ERR_INVALID, "tower spec: num_vars out of range"); break; }
+            sp.layers = sp.is_logup ? in.num_vars + 1 : in.num_vars;
+            for (int z = 0; z < 4; z++) sp.leaves[z] = (const ext_t*)in.leaves[z];
+            sp.ones = sp.is_logup && !in.leaves[0];
+            if (sp.is_logup ? (!in.leaves[2] || !in.leaves[3] || (!in.leaves[0] != !in.leaves[1])) : (!in.leaves[0] || !in.leaves[1])) {
+                rc = set_err(c, CG_ERR_INVALID, "tower spec: missing leaf pointer");
+                break;
+            }
+            sp.layer.assign(sp.layers, nullptr);
+            const uint32_t arrs = sp.is_logup ? 4 : 2;
+            // upper layers l = layers-2 .. 0, one pooled block: sum_l arrs * 2^l ext
+            const uint64_t top = sp.layers - 1;   // leaf layer index; arrays there have 2^top ext
+            void* blk = nullptr;
+            const uint64_t total = (uint64_t)arrs * ((1ULL << top) - 1) + (sp.ones ? (2ULL << top) : 0);
+            if (total) {
+                rc = tmp_alloc(c, sizeof(ext_t) * total, &blk, st);
+                if (rc != CG_OK) break;
+                tw->owned.push_back(blk);
+            }
+            ext_t* base = (ext_t*)blk;
+            for (uint32_t l = 0; l < top; l++) { sp.layer[l] = base; base += (uint64_t)arrs << l; }
+            if (sp.ones) {   // input-layer numerators materialised as ones (utils.rs:556-577)
+                sp.layer[top] = base;   // only arrays 0,1 live here; q1,q2 stay in the caller's buffers
+                fill_ext_kernel<<<grid_for(c, 2ULL << top), CG_THREADS, 0, st>>>(base, 2ULL << top, ext_t{1, 0});
+                LAUNCHED(c);
+            }
+            for (int32_t l = (int32_t)top - 1; l >= 0 && rc == CG_OK; l--) {
+                const uint64_t n = 2ULL << l;   // points combined = length of layer l+1 arrays
+                ext_t* dst = (ext_t*)sp.layer[l];
+                const bool from_leaves = ((uint32_t)l + 1 == top);
+                if (!sp.is_logup) {
+                    tower_prod_layer_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, st>>>(tower_arr(sp, l + 1, 0), tower_arr(sp, l + 1, 1), n, dst, from_leaves);
+                } else {
+                    const bool implicit_ones = from_leaves && sp.ones;
+                    tower_logup_layer_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, st>>>(
+                        implicit_ones ? nullptr : tower_arr(sp, l + 1, 0), implicit_ones ? nullptr : tower_arr(sp, l + 1, 1),
+                        tower_arr(sp, l + 1, 2), tower_arr(sp, l + 1, 3), n, dst, dst + n, from_leaves);
+                }
+                LAUNCHED(c);
+                if (cudaGetLastError() != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "tower layer kernel launch failed");
+            }
+            if (sp.layers - 1 > tw->max_round) tw->max_round = sp.layers - 1;
+            if (sp.is_logup) tw->n_logup++; else tw->n_prod++;
+            tw->specs.push_back(std::move(sp));
+        }
+    if (rc != CG_OK) { cg_tower_destroy(tw); return rc; }
+    *out = tw;
+    return CG_OK;
+}
+CG_EXPORT int cg_tower_output_evals(cg_tower* tw, uint32_t spec, uint64_t* h_out) {
+    if (!tw || spec >= tw->specs.size() || !h_out) return CG_ERR_INVALID;
+    const TowerSpecState& sp = tw->specs[spec];
+    const uint32_t arrs = sp.is_logup ? 4 : 2;
+    for (uint32_t z = 0; z < arrs; z++)
+        CU(tw->ctx, cudaMemcpyAsync(h_out + 2 * z, tower_arr(sp, 0, z), sizeof(ext_t), cudaMemcpyDeviceToHost, tw->stream));
+    CU(tw->ctx, cudaStreamSynchronize(tw->stream));
+    for (uint32_t z = 0; z < 2 * arrs; z++) if (h_out[z] >= GL_P) h_out[z] -= GL_P;
+    return CG_OK;
+}
+CG_EXPORT uint64_t cg_tower_proof_len(const cg_tower* tw) {
+    if (!tw) return 0;
+    uint64_t w = 0;
+    for (uint32_t r = 1; r <= tw->max_round; r++) {
+        w += (uint64_t)r * 3 * 2;
+        for (const auto& sp : tw->specs) if (r < sp.layers) w += sp.is_logup ? 8 : 4;
+    }
+    return w;
+}
+CG_EXPORT uint32_t cg_tower_point_len(const cg_tower* tw) { return tw ? tw->max_round + 1 : 0; }
+
+static void alpha_pows(const cg_transcript_vt* tr, uint32_t n, std::vector<ext_t>& out) {
+    // get_challenge_pows: label "combine subset evals", one alpha, [1, a, a^2, ...]
+    uint64_t a[2];
+    tr->sample(tr->user, "combine subset evals", a);
+    out.resize(n);
+    unsigned __int128 P = GL_P;
+    uint64_t p0 = 1, p1 = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        out[i] = ext_t{p0, p1};
+        // (p0 + p1 X)(a0 + a1 X), X^2 = 7 — transcript-side scalar work stays on the host like the reference
+        unsigned __int128 c0 = ((unsigned __int128)p0 * a[0]) % P + (((unsigned __int128)p1 * a[1]) % P) * 7 % P;
+        unsigned __int128 c1 = ((unsigned __int128)p0 * a[1]) % P + ((unsigned __int128)p1 * a[0]) % P;
+        p0 = (uint64_t)(c0 % P);
+        p1 = (uint64_t)(c1 % P);
+    }
+}
+
+CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, uint64_t* h_proof, uint64_t* h_point) {
+    if (!tw || !tr || !h_proof || !h_point) return CG_ERR_INVALID;
+    cg_ctx* c = tw->ctx;
+    CU(c, cudaSetDevice(c->device));
+    const uint32_t n_alpha = tw->n_prod + 2 * tw->n_logup;
+    std::vector<ext_t> alpha;
+    alpha_pows(tr, n_alpha, alpha);
+    std::vector<uint64_t> rt(2 * (size_t)(tw->max_round + 2), 0);
+    uint32_t rt_len = 1;
+    tr->sample(tr->user, "product_sum", rt.data());
+    uint64_t w = 0;
+    for (uint32_t round = 1; round <= tw->max_round; round++) {
+        const uint32_t nv = rt_len;
+        const uint64_t n = 1ULL << nv;
+        void* d_eq = nullptr;
+        CHK(tmp_alloc(c, sizeof(ext_t) * n, &d_eq, tw->stream));
+        int rc = cg_build_eq(c, rt.data(), nv, (uint64_t*)d_eq, 0, n, tw->stream);
+        // MLE list in the reference's lift order: eq, then live product specs, then live logup specs
+        std::vector<cg_mle_desc> mles;
+        mles.push_back(cg_mle_desc{d_eq, n, nv, 1});
+        TowerLayout tl;
+        tl.on = true;
+        tl.eq = 0;
+        std::vector<uint32_t> first(tw->specs.size(), 0);
+        uint32_t pi = 0, li = 0;
+        for (size_t si = 0; si < tw->specs.size(); si++) {
+            const TowerSpecState& sp = tw->specs[si];
+            const uint32_t my = sp.is_logup ? li++ : pi++;
+            if (round >= sp.layers) continue;
+            first[si] = (uint32_t)mles.size();
+            const uint32_t arrs = sp.is_logup ? 4 : 2;
+            for (uint32_t z = 0; z < arrs; z++) {
+                mles.push_back(cg_mle_desc{tower_arr(sp, round, z), n, nv, 1});
+                (sp.is_logup ? tl.lk : tl.prod).push_back((uint32_t)mles.size() - 1);
+            }
+            if (sp.is_logup) { tl.lk_an.push_back(alpha[tw->n_prod + 2 * my]); tl.lk_ad.push_back(alpha[tw->n_prod + 2 * my + 1]); }
+            else tl.prod_alpha.push_back(alpha[my]);
+        }
+        tl.alpha_one = false;
+        cg_sumcheck* sc = nullptr;
+        const bool fits = tl.prod_alpha.size() <= CG_TOWER_MAX_PROD && tl.lk_an.size() <= CG_TOWER_MAX_LOGUP;
+        std::vector<uint64_t> coeff;
+        std::vector<uint32_t> off{0}, idx;
+        if (rc == CG_OK) {
+            // monomial terms of the layer expression (cpu/mod.rs:441-485) — used by the generic kernel
+            // when the spec count exceeds the specialised kernel's table
+            for (size_t p = 0; p < tl.prod_alpha.size(); p++) {
+                coeff.push_back(tl.prod_alpha[p].c0); coeff.push_back(tl.prod_alpha[p].c1);
+                idx.insert(idx.end(), {0u, tl.prod[2 * p], tl.prod[2 * p + 1]}); off.push_back((uint32_t)idx.size());
+            }
+            for (size_t l = 0; l < tl.lk_an.size(); l++) {
+                const uint32_t p1 = tl.lk[4 * l], p2 = tl.lk[4 * l + 1], q1 = tl.lk[4 * l + 2], q2 = tl.lk[4 * l + 3];
+                coeff.push_back(tl.lk_an[l].c0); coeff.push_back(tl.lk_an[l].c1);
+                idx.insert(idx.end(), {0u, p1, q2}); off.push_back((uint32_t)idx.size());
+                coeff.push_back(tl.lk_an[l].c0); coeff.push_back(tl.lk_an[l].c1);
+                idx.insert(idx.end(), {0u, p2, q1}); off.push_back((uint32_t)idx.size());
+                coeff.push_back(tl.lk_ad[l].c0); coeff.push_back(tl.lk_ad[l].c1);
+                idx.insert(idx.end(), {0u, q1, q2}); off.push_back((uint32_t)idx.size());
+            }
+            rc = cg_sumcheck_create(c, mles.data(), (uint32_t)mles.size(), coeff.data(), off.data(), idx.data(),
+                                    (uint32_t)off.size() - 1, nv, 3, CG_SC_FORCE_GENERIC, tw->stream, &sc);
+        }
+        std::vector<uint64_t> fin(2 * mles.size()), chal(2 * (size_t)nv);
+        if (rc == CG_OK) {
+            if (fits) sc->tl = tl;
+            tr->sumcheck_begin(tr->user, nv, 3);
+            rc = sc_run_host(sc, tr->round_challenge, tr->user, h_proof + w, fin.data(), chal.data());
+        }
+        if (sc) cg_sumcheck_destroy(sc);
+        tmp_free(d_eq, tw->stream);
+        if (rc != CG_OK) return rc;
+        w += (uint64_t)nv * 3 * 2;
+        for (int pass = 0; pass < 2; pass++)
+            for (size_t si = 0; si < tw->specs.size(); si++) {
+                const TowerSpecState& sp = tw->specs[si];
+                if ((sp.is_logup ? 1 : 0) != pass || round >= sp.layers) continue;
+                const uint32_t arrs = sp.is_logup ? 4 : 2;
+                tr->append_exts(tr->user, fin.data() + 2 * first[si], arrs);
+                memcpy(h_proof + w, fin.data() + 2 * first[si], sizeof(ext_t) * arrs);
+                w += 2 * arrs;
+            }
+        uint64_t rm[2];
+        tr->sample(tr->user, "merge", rm);
+        memcpy(rt.data(), chal.data(), sizeof(uint64_t) * 2 * nv);
+        rt[2 * nv] = rm[0];
+        rt[2 * nv + 1] = rm[1];
+        rt_len = nv + 1;
+        alpha_pows(tr, n_alpha, alpha);
+    }
+    memcpy(h_point, rt.data(), sizeof(uint64_t) * 2 * rt_len);
+    return CG_OK;
+}

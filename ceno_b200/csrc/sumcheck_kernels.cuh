@@ -1,0 +1,430 @@
+// sumcheck_kernels.cuh — the hot kernels of the GKR-sumcheck path, hand-written for sm_100a.
+//
+//   (i)  round evaluation  : [p(1)..p(d)] = sum over the remaining hypercube pairs
+//   (ii) fix_variable fold : f'[b] = f[2b] + r (f[2b+1] - f[2b])
+//   fused (ii)+(i)         : one pass per round — reads 4 consecutive elements per MLE, writes the
+//                            folded pair, accumulates the next round's evaluations from registers.
+//   (iii) build_eq_x_r     : two-level outer product L[b_lo] * H[b_hi] with the selector mask fused.
+//
+// Memory plan (HBM-bound integer streaming; no tensor-core path): every thread issues 256-bit
+// global loads (LDG.E.ENL2.256) of consecutive elements, a warp covers one contiguous 2 KB span per
+// MLE, stores are 256-bit; grids are sized in multiples of the SM count with a grid-stride loop;
+// reductions are warp-shuffle -> shared -> one partial per block -> last-block finish (ticket).
+// Field arithmetic never leaves registers (gl64.cuh).
+//
+// Reference semantics: IOPProverState::prove round loop (external sumcheck crate; SURVEY.md §8a1,
+// §A1-A3), call sites gkr_iop/src/gkr/layer/cpu/mod.rs:217-237, ceno_zkvm/src/scheme/cpu/mod.rs:490-498.
+#pragma once
+#include "gl64.cuh"
+
+#define CG_THREADS 256
+#define CG_MAX_DEGREE 8
+#define CG_MAX_BLOCKS 2048
+#define CG_TOWER_MAX_PROD 8
+#define CG_TOWER_MAX_LOGUP 4
+
+// ---------------------------------------------------------------------------------------------
+// round output / finish
+struct RoundOut {
+    ext_t* partials;          // [CG_MAX_BLOCKS * CG_MAX_DEGREE]
+    unsigned int* ticket;     // zero on entry, zero on exit
+    ext_t* d_out;             // device: degree ext (this round's message)
+    // device-resident stand-in challenger (optional): absorbs the message, squeezes r
+    uint64_t* d_tr_state;     // nullptr -> host transcript
+    ext_t* d_r_out;           // where to put the challenge for the next launch
+};
+
+template <int D>
+GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out) {
+    __shared__ ext_t s_part[CG_THREADS / 32][D];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int x = 0; x < D; x++) {
+        ext_t v = warp_reduce_ext(acc[x]);
+        if (lane == 0) s_part[warp][x] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int x = 0; x < D; x++) {
+            ext_t v = lane < (CG_THREADS / 32) ? s_part[lane][x] : ext_zero();
+            v = warp_reduce_ext(v);
+            if (lane == 0) out.partials[(size_t)blockIdx.x * D + x] = v;
+        }
+        if (lane == 0) {
+            __threadfence();
+            unsigned t = atomicAdd(out.ticket, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last block: sum the per-block partials
+#pragma unroll
+    for (int x = 0; x < D; x++) {
+        ext_t v = ext_zero();
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+            const ulonglong2 p = __ldcg(reinterpret_cast<const ulonglong2*>(&out.partials[(size_t)b * D + x]));
+            v = ext_add(v, ext_make(p.x, p.y));
+        }
+        v = warp_reduce_ext(v);
+        if (lane == 0) s_part[warp][x] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        ext_t res[D];
+#pragma unroll
+        for (int x = 0; x < D; x++) {
+            ext_t v = lane < (CG_THREADS / 32) ? s_part[lane][x] : ext_zero();
+            res[x] = warp_reduce_ext(v);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int x = 0; x < D; x++) out.d_out[x] = res[x];
+            if (out.d_tr_state) {   // stand-in challenger: absorb evals, label "Internal round", squeeze
+                uint64_t h = *out.d_tr_state;
+#pragma unroll
+                for (int x = 0; x < D; x++) { cg_tr_absorb(h, res[x].c0); cg_tr_absorb(h, res[x].c1); }
+                const uint8_t label[14] = {'I','n','t','e','r','n','a','l',' ','r','o','u','n','d'};
+                cg_tr_append_message(h, label, 14);
+                ext_t r;
+                r.c0 = cg_tr_squeeze(h);
+                r.c1 = cg_tr_squeeze(h);
+                *out.d_tr_state = h;
+                *out.d_r_out = r;
+            }
+            *out.ticket = 0;
+            __threadfence();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair loader: FOLD = read 4 consecutive ext, fold by r, write the pair; else read 2.
+template <bool FOLD, bool CANON>
+GL_DEV void load_pair(const ext_t* __restrict__ in, ext_t* __restrict__ out, uint64_t item,
+                      const extmul_t& r, ext_t& lo, ext_t& hi) {
+    if (FOLD) {
+        ext_t x0, x1, x2, x3;
+        ld_ext2(in + 4 * item, x0, x1);
+        ld_ext2(in + 4 * item + 2, x2, x3);
+        if (CANON) { x0 = ext_canon(x0); x1 = ext_canon(x1); x2 = ext_canon(x2); x3 = ext_canon(x3); }
+        lo = ext_add(x0, ext_mul_prep(ext_sub(x1, x0), r));
+        hi = ext_add(x2, ext_mul_prep(ext_sub(x3, x2), r));
+        st_ext2(out + 2 * item, lo, hi);
+    } else {
+        ld_ext2(in + 2 * item, lo, hi);
+        if (CANON) { lo = ext_canon(lo); hi = ext_canon(hi); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tower-layer round kernel (degree 3):
+//   p(X) = sum_b eq(X,b) * ( sum_i alpha_i a_i(X,b) b_i(X,b)
+//                          + sum_j [ an_j (p1_j q2_j + p2_j q1_j) + ad_j q1_j q2_j ](X,b) )
+// = the expression CpuTowerProver::create_proof builds per layer
+//   (ceno_zkvm/src/scheme/cpu/mod.rs:417-485).  T3 (eq*A*B) is n_prod = 1, n_logup = 0.
+struct TowerArgs {
+    const ext_t* eq_in;
+    ext_t* eq_out;
+    const ext_t* prod_in[CG_TOWER_MAX_PROD][2];
+    ext_t* prod_out[CG_TOWER_MAX_PROD][2];
+    ext_t alpha_prod[CG_TOWER_MAX_PROD];
+    const ext_t* lk_in[CG_TOWER_MAX_LOGUP][4];
+    ext_t* lk_out[CG_TOWER_MAX_LOGUP][4];
+    ext_t alpha_num[CG_TOWER_MAX_LOGUP];
+    ext_t alpha_den[CG_TOWER_MAX_LOGUP];
+    int n_prod, n_logup;
+    int alpha_one;            // every alpha_prod is 1 and n_logup == 0: skip the alpha multiply
+    uint64_t n_pairs;         // pairs evaluated this launch (after the fold, if FOLD)
+    ext_t r;                  // fold challenge (FOLD only) ...
+    const ext_t* r_ptr;       // ... or read it from device memory (device challenger)
+    RoundOut out;
+};
+
+template <bool FOLD, bool CANON>
+__global__ void __launch_bounds__(CG_THREADS, 2) tower_round_kernel(const __grid_constant__ TowerArgs a) {
+    extmul_t rm;
+    if (FOLD) rm = extmul_prep(a.r_ptr ? ld_ext(a.r_ptr) : a.r);
+    ext_t acc[3] = {ext_zero(), ext_zero(), ext_zero()};
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < a.n_pairs; item += stride) {
+        ext_t in1 = ext_zero(), in2 = ext_zero(), in3 = ext_zero();
+        for (int p = 0; p < a.n_prod; p++) {
+            ext_t alo, ahi, blo, bhi;
+            load_pair<FOLD, CANON>(a.prod_in[p][0], a.prod_out[p][0], item, rm, alo, ahi);
+            load_pair<FOLD, CANON>(a.prod_in[p][1], a.prod_out[p][1], item, rm, blo, bhi);
+            if (!a.alpha_one) {   // fold alpha into a (2 muls) instead of into the 3 products
+                extmul_t al = extmul_prep(a.alpha_prod[p]);
+                alo = ext_mul_prep(alo, al);
+                ahi = ext_mul_prep(ahi, al);
+            }
+            const ext_t ad = ext_sub(ahi, alo), bd = ext_sub(bhi, blo);
+            const ext_t a2 = ext_add(ahi, ad), b2 = ext_add(bhi, bd);
+            const ext_t a3 = ext_add(a2, ad), b3 = ext_add(b2, bd);
+            in1 = ext_add(in1, ext_mul(ahi, bhi));
+            in2 = ext_add(in2, ext_mul(a2, b2));
+            in3 = ext_add(in3, ext_mul(a3, b3));
+        }
+        for (int l = 0; l < a.n_logup; l++) {
+            ext_t p1lo, p1hi, p2lo, p2hi, q1lo, q1hi, q2lo, q2hi;
+            load_pair<FOLD, CANON>(a.lk_in[l][0], a.lk_out[l][0], item, rm, p1lo, p1hi);
+            load_pair<FOLD, CANON>(a.lk_in[l][1], a.lk_out[l][1], item, rm, p2lo, p2hi);
+            load_pair<FOLD, CANON>(a.lk_in[l][2], a.lk_out[l][2], item, rm, q1lo, q1hi);
+            load_pair<FOLD, CANON>(a.lk_in[l][3], a.lk_out[l][3], item, rm, q2lo, q2hi);
+            const extmul_t an = extmul_prep(a.alpha_num[l]), adn = extmul_prep(a.alpha_den[l]);
+            const ext_t p1d = ext_sub(p1hi, p1lo), p2d = ext_sub(p2hi, p2lo);
+            const ext_t q1d = ext_sub(q1hi, q1lo), q2d = ext_sub(q2hi, q2lo);
+            ext_t p1 = p1hi, p2 = p2hi, q1 = q1hi, q2 = q2hi;
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                const ext_t num = ext_add(ext_mul(p1, q2), ext_mul(p2, q1));
+                const ext_t den = ext_mul(q1, q2);
+                const ext_t v = ext_add(ext_mul_prep(num, an), ext_mul_prep(den, adn));
+                if (t == 0) in1 = ext_add(in1, v);
+                if (t == 1) in2 = ext_add(in2, v);
+                if (t == 2) in3 = ext_add(in3, v);
+                p1 = ext_add(p1, p1d); p2 = ext_add(p2, p2d); q1 = ext_add(q1, q1d); q2 = ext_add(q2, q2d);
+            }
+        }
+        ext_t elo, ehi;
+        load_pair<FOLD, CANON>(a.eq_in, a.eq_out, item, rm, elo, ehi);
+        const ext_t ed = ext_sub(ehi, elo);
+        const ext_t e2 = ext_add(ehi, ed), e3 = ext_add(e2, ed);
+        acc[0] = ext_add(acc[0], ext_mul(in1, ehi));
+        acc[1] = ext_add(acc[1], ext_mul(in2, e2));
+        acc[2] = ext_add(acc[2], ext_mul(in3, e3));
+    }
+    block_finish<3>(acc, a.out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic monomial-term round evaluation: P = sum_t c_t prod_{i in S_t} f_i, base or ext MLEs
+// (the table extract_mle_relationships_from_monomial_terms hands to prove_generic_sumcheck_gpu,
+//  gkr_iop/src/gkr/layer/gpu/mod.rs:204-215).  Products of fewer than D factors are evaluated at all
+// D points too — bit-identical to extrapolation because field arithmetic is exact.
+struct MleSlot {
+    const void* ptr;
+    uint32_t is_ext;
+    uint32_t canon;   // caller-provided buffer: canonicalise on load
+};
+struct GenericArgs {
+    const MleSlot* mles;
+    const ext_t* coeff;
+    const uint32_t* off;
+    const uint32_t* idx;
+    uint32_t n_terms;
+    uint64_t n_pairs;
+    RoundOut out;
+};
+
+template <int D>
+__global__ void __launch_bounds__(CG_THREADS) generic_round_kernel(const __grid_constant__ GenericArgs a) {
+    ext_t acc[D];
+#pragma unroll
+    for (int x = 0; x < D; x++) acc[x] = ext_zero();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < a.n_pairs; item += stride) {
+        for (uint32_t t = 0; t < a.n_terms; t++) {
+            ext_t prod[D];
+            const ext_t c = a.coeff[t];
+#pragma unroll
+            for (int x = 0; x < D; x++) prod[x] = c;
+            const uint32_t q0 = a.off[t], q1 = a.off[t + 1];
+            for (uint32_t q = q0; q < q1; q++) {
+                const MleSlot s = a.mles[a.idx[q]];
+                if (s.is_ext) {
+                    ext_t lo = ld_ext(reinterpret_cast<const ext_t*>(s.ptr) + 2 * item);
+                    ext_t hi = ld_ext(reinterpret_cast<const ext_t*>(s.ptr) + 2 * item + 1);
+                    if (s.canon) { lo = ext_canon(lo); hi = ext_canon(hi); }
+                    const ext_t d = ext_sub(hi, lo);
+                    ext_t v = hi;
+#pragma unroll
+                    for (int x = 0; x < D; x++) { prod[x] = ext_mul(prod[x], v); v = ext_add(v, d); }
+                } else {
+                    const ulonglong2 pr = *(reinterpret_cast<const ulonglong2*>(s.ptr) + item);
+                    uint64_t lo = pr.x, hi = pr.y;
+                    if (s.canon) { lo = gl_canon(lo); hi = gl_canon(hi); }
+                    const uint64_t d = gl_sub(hi, lo);
+                    uint64_t v = hi;
+#pragma unroll
+                    for (int x = 0; x < D; x++) { prod[x] = ext_mul_base(prod[x], v); v = gl_add(v, d); }
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < D; x++) acc[x] = ext_add(acc[x], prod[x]);
+        }
+    }
+    block_finish<D>(acc, a.out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fold of many MLEs in one launch: grid.y = MLE.  Output always ext.
+struct FoldSlot {
+    const void* in;
+    ext_t* out;
+    uint32_t is_ext;
+    uint32_t canon;
+};
+__global__ void __launch_bounds__(CG_THREADS) fold_kernel(const FoldSlot* __restrict__ slots, uint64_t n_out,
+                                                           ext_t r_val, const ext_t* r_ptr) {
+    const FoldSlot s = slots[blockIdx.y];
+    const extmul_t rm = extmul_prep(r_ptr ? ld_ext(r_ptr) : r_val);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_out; b += stride) {
+        if (s.is_ext) {
+            ext_t lo, hi;
+            ld_ext2(reinterpret_cast<const ext_t*>(s.in) + 2 * b, lo, hi);
+            if (s.canon) { lo = ext_canon(lo); hi = ext_canon(hi); }
+            st_ext(s.out + b, ext_add(lo, ext_mul_prep(ext_sub(hi, lo), rm)));
+        } else {
+            const ulonglong2 pr = *(reinterpret_cast<const ulonglong2*>(s.in) + b);
+            uint64_t lo = pr.x, hi = pr.y;
+            if (s.canon) { lo = gl_canon(lo); hi = gl_canon(hi); }
+            const uint64_t d = gl_sub(hi, lo);
+            st_ext(s.out + b, ext_make(gl_add(lo, gl_mul(d, rm.c0)), gl_mul(d, rm.c1)));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// build_eq_x_r.  Small table: one block, doubling in shared memory (k <= 12).
+// eq[b + 2^i] = eq[b] r_i ; eq[b] -= eq[b + 2^i]   (any order gives the same bits — exact field).
+#define CG_EQ_SMALL_K 12
+__global__ void __launch_bounds__(1024) eq_small_kernel(const ext_t* __restrict__ point, uint32_t k, ext_t* __restrict__ out) {
+    extern __shared__ ext_t s_eq[];
+    if (threadIdx.x == 0) s_eq[0] = ext_one();
+    __syncthreads();
+    for (uint32_t i = 0; i < k; i++) {
+        const ext_t ri = ext_canon(point[i]);
+        const uint32_t n = 1u << i;
+        for (uint32_t b = threadIdx.x; b < n; b += blockDim.x) {
+            const ext_t lo = s_eq[b];
+            const ext_t hi = ext_mul(lo, ri);
+            s_eq[b + n] = hi;
+            s_eq[b] = ext_sub(lo, hi);
+        }
+        __syncthreads();
+    }
+    for (uint32_t b = threadIdx.x; b < (1u << k); b += blockDim.x) out[b] = s_eq[b];
+}
+// Large table: out[hi * 2^lo_k + lo] = L[lo] * H[hi], prefix mask [start, end) fused.
+// Each thread produces 2 consecutive outputs (one 256-bit store).
+__global__ void __launch_bounds__(CG_THREADS) eq_outer_kernel(const ext_t* __restrict__ L, const ext_t* __restrict__ H,
+                                                               uint32_t lo_k, uint64_t n, uint64_t start, uint64_t end,
+                                                               ext_t* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t lo_mask = (1ULL << lo_k) - 1;
+    for (uint64_t pair = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; pair < n / 2; pair += stride) {
+        const uint64_t b = 2 * pair;
+        const ext_t h = ld_ext(H + (b >> lo_k));
+        ext_t l0, l1;
+        ld_ext2(L + (b & lo_mask), l0, l1);
+        ext_t v0 = ext_mul(l0, h), v1 = ext_mul(l1, h);
+        if (b < start || b >= end) v0 = ext_zero();
+        if (b + 1 < start || b + 1 >= end) v1 = ext_zero();
+        st_ext2(out + b, v0, v1);
+    }
+}
+// generic mask passes for the selector variants (gkr_iop/src/selector.rs:141-243)
+__global__ void prefix_mask_kernel(ext_t* __restrict__ v, uint64_t n, uint64_t start, uint64_t end) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride)
+        if (b < start || b >= end) v[b] = ext_zero();
+}
+// OrderedSparse: keep[i] bitmap over the inner 2^inner_vars indices (device), zero chunks >= num_instances
+__global__ void sparse_mask_kernel(ext_t* __restrict__ v, uint64_t n, uint32_t inner_vars, uint64_t num_instances,
+                                   const uint8_t* __restrict__ keep) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t mask = (1ULL << inner_vars) - 1;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride) {
+        const uint64_t chunk = b >> inner_vars;
+        if (chunk >= num_instances || !keep[b & mask]) v[b] = ext_zero();
+    }
+}
+// QuarkBinaryTreeLessThan: region i = [n - n/2^i ... ) of length n/2^(i+1), keep first seq[i] entries
+struct QuarkArgs {
+    uint64_t seq[64];
+    uint32_t num_vars;
+};
+__global__ void quark_mask_kernel(ext_t* __restrict__ v, uint64_t n, const __grid_constant__ QuarkArgs q) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride) {
+        if (b == n - 1) { v[b] = ext_zero(); continue; }
+        // region index i: b in [n - n>>i, n - n>>(i+1))  <=>  i = number of leading ones of b (k-bit)
+        const uint64_t inv = (~b) & (n - 1);
+        const uint32_t i = q.num_vars - 1 - (63 - __clzll(inv));   // inv != 0 because b != n-1
+        const uint64_t region_start = n - (n >> i);
+        const uint64_t keep = i < q.num_vars ? q.seq[i] : 0;
+        if (b - region_start >= keep) v[b] = ext_zero();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tower witness layers (infer_tower_product_witness / infer_tower_logup_witness,
+// ceno_zkvm/src/scheme/utils.rs:488-659).  Layer l buffer = [a | b] (product) or [p1|p2|q1|q2]
+// (logup), each 2^l ext; layer l = pointwise combination of layer l+1's arrays over 2^(l+1) points.
+__global__ void __launch_bounds__(CG_THREADS) tower_prod_layer_kernel(const ext_t* __restrict__ a, const ext_t* __restrict__ b,
+                                                                       uint64_t n, ext_t* __restrict__ out, int canon) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) {
+        ext_t u = ld_ext(a + x), v = ld_ext(b + x);
+        if (canon) { u = ext_canon(u); v = ext_canon(v); }
+        st_ext(out + x, ext_mul(u, v));
+    }
+}
+// p_out[x] = q1 p2 + q2 p1 (or q1 + q2 when numerators are implicit ones), q_out[x] = q1 q2
+__global__ void __launch_bounds__(CG_THREADS) tower_logup_layer_kernel(const ext_t* __restrict__ p1, const ext_t* __restrict__ p2,
+                                                                        const ext_t* __restrict__ q1, const ext_t* __restrict__ q2,
+                                                                        uint64_t n, ext_t* __restrict__ p_out, ext_t* __restrict__ q_out,
+                                                                        int canon) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) {
+        ext_t a1 = ld_ext(q1 + x), a2 = ld_ext(q2 + x);
+        if (canon) { a1 = ext_canon(a1); a2 = ext_canon(a2); }
+        ext_t p;
+        if (p1) {
+            ext_t u1 = ld_ext(p1 + x), u2 = ld_ext(p2 + x);
+            if (canon) { u1 = ext_canon(u1); u2 = ext_canon(u2); }
+            p = ext_add(ext_mul(a1, u2), ext_mul(a2, u1));
+        } else {
+            p = ext_add(a1, a2);
+        }
+        st_ext(p_out + x, p);
+        st_ext(q_out + x, ext_mul(a1, a2));
+    }
+}
+__global__ void fill_ext_kernel(ext_t* __restrict__ v, uint64_t n, ext_t val) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride) v[b] = val;
+}
+
+// ---------------------------------------------------------------------------------------------
+// wit_infer_by_monomial_expr: out[b] = sum_t c_t prod f_i[b]   (gkr_iop/src/gpu/mod.rs:599-609)
+struct InferArgs {
+    const MleSlot* mles;
+    const ext_t* coeff;
+    const uint32_t* off;
+    const uint32_t* idx;
+    uint32_t n_terms;
+    uint64_t n;
+    ext_t* out;
+};
+__global__ void __launch_bounds__(CG_THREADS) wit_infer_kernel(const __grid_constant__ InferArgs a) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < a.n; b += stride) {
+        ext_t acc = ext_zero();
+        for (uint32_t t = 0; t < a.n_terms; t++) {
+            ext_t prod = a.coeff[t];
+            for (uint32_t q = a.off[t]; q < a.off[t + 1]; q++) {
+                const MleSlot s = a.mles[a.idx[q]];
+                if (s.is_ext) prod = ext_mul(prod, ext_canon(ld_ext(reinterpret_cast<const ext_t*>(s.ptr) + b)));
+                else prod = ext_mul_base(prod, reinterpret_cast<const uint64_t*>(s.ptr)[b]);
+            }
+            acc = ext_add(acc, prod);
+        }
+        st_ext(a.out + b, acc);
+    }
+}

@@ -1,0 +1,243 @@
+/*
+ * ceno_b200.h — C ABI of the B200-native GKR-sumcheck device backend.
+ *
+ * This is the drop-in boundary for the ONE hot path of scroll-tech/ceno named by
+ * BASELINE.json: per-round sumcheck evaluation, fix_variable fold, build_eq_x_r (+ selector
+ * masks), the tower (grand-product / logUp) prover built from them, and the Merkle leaf hash.
+ * The reference funnels that path into ~10 calls on its private `cuda_hal` crate
+ * (SURVEY.md §2.3 / §B); each entry point below names the reference interface it replaces.
+ * INTEGRATION.md shows the Rust `extern "C"` binding a maintainer would add.
+ *
+ * Conventions
+ *  - Field: Goldilocks p = 2^64 - 2^32 + 1.  A base element is one canonical u64; an
+ *    extension element (GoldilocksExt2, X^2 = 7) is two consecutive u64 limbs [c0, c1] — the
+ *    host in-memory layout of the field type, which the reference transmutes to/from the
+ *    device representation (gkr_iop/src/gpu/mod.rs:311-324, gkr_iop/src/gkr/layer/gpu/mod.rs:252-280).
+ *    Inputs may be any u64 < 2^64 (p3's Goldilocks is not always canonical); outputs are canonical.
+ *  - MLE index b = sum_i b_i 2^i; sumcheck round j binds variable j (LSB first), i.e. round 0
+ *    folds adjacent pairs (2b, 2b+1)  (gkr_iop/src/utils.rs:209-232).
+ *  - Every call returns 0 on success or a CG_ERR_* code; cg_last_error(ctx) gives the text.
+ *    Nothing aborts (reference: Result<_, HalError> mapped to ZKVMError::BackendError,
+ *    ceno_zkvm/src/scheme/gpu/mod.rs:347-351).
+ *  - All device work is issued on the caller's stream (reference binds one CUDA stream per OS
+ *    thread and forbids default-stream fallback, gkr_iop/src/gpu/mod.rs:79-154); the library is
+ *    re-entrant per (ctx, stream).  `stream` is a cudaStream_t passed as void*; NULL = the
+ *    context's own non-blocking stream.
+ *  - The library never frees or writes caller MLE buffers: like the reference's
+ *    prove_generic_sumcheck_gpu it takes shared inputs and folds into pooled workspace.
+ *  - There is no CPU fallback: cg_init fails with CG_ERR_NO_DEVICE when no sm_100 GPU is present.
+ */
+#ifndef CENO_B200_H
+#define CENO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CG_OK 0
+#define CG_ERR_CUDA 1        /* a CUDA runtime call failed */
+#define CG_ERR_INVALID 2     /* bad argument */
+#define CG_ERR_UNSUPPORTED 3 /* valid in the reference but not implemented here (see message) */
+#define CG_ERR_OOM 4
+#define CG_ERR_NO_DEVICE 5
+#define CG_ERR_STATE 6       /* call order violated (e.g. bind before round_eval) */
+
+typedef struct cg_ctx cg_ctx;
+typedef struct cg_sumcheck cg_sumcheck;
+typedef void* cg_stream; /* cudaStream_t */
+
+/* Device MLE descriptor.  Mirrors what MultilinearExtensionGpu carries
+ * (gkr_iop/src/gpu/mod.rs:157-161, 331-344): a pointer into a (possibly larger, column-major)
+ * device allocation, the occupied prefix `len` (<= 2^num_vars; the implicit tail is zero,
+ * SURVEY §A9) and whether elements are base (8 B) or ext (16 B).  dptr must be 16-byte aligned
+ * (32-byte for best bandwidth). */
+typedef struct cg_mle_desc {
+    const void* dptr;
+    uint64_t len;
+    uint32_t num_vars;
+    uint32_t is_ext;
+} cg_mle_desc;
+
+/* ---- lifecycle / memory: replaces cuda_hal context + mem_pool
+ * (gkr_iop/src/gpu/mod.rs:53-66 get_cuda_hal; alloc_*_on_device / alloc_*_from_host / to_cpu_vec,
+ *  gkr_iop/src/gpu/mod.rs:260-320, 593; mem_pool stats ceno_zkvm/src/scheme/gpu/mod.rs:226-269) */
+int cg_init(int device_id, cg_ctx** ctx);
+int cg_destroy(cg_ctx* ctx);
+const char* cg_last_error(cg_ctx* ctx);
+const char* cg_version(void);
+int cg_device_info(cg_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes, size_t* total_bytes);
+int cg_alloc(cg_ctx* ctx, size_t bytes, void** dptr);   /* pooled; 256-byte aligned */
+int cg_free(cg_ctx* ctx, void* dptr);                   /* returns the block to the pool */
+int cg_pool_stats(cg_ctx* ctx, size_t* used_bytes, size_t* reserved_bytes);
+int cg_pool_trim(cg_ctx* ctx);                          /* cudaFree every cached block */
+int cg_h2d(cg_ctx* ctx, void* dst, const void* src, size_t bytes, cg_stream s); /* async on s */
+int cg_d2h(cg_ctx* ctx, void* dst, const void* src, size_t bytes, cg_stream s); /* async on s */
+int cg_d2d(cg_ctx* ctx, void* dst, const void* src, size_t bytes, cg_stream s); /* dtod_copy_sync, scheme/gpu/mod.rs:3274 */
+int cg_stream_sync(cg_ctx* ctx, cg_stream s);
+int cg_host_alloc_pinned(cg_ctx* ctx, size_t bytes, void** hptr);
+int cg_host_free_pinned(cg_ctx* ctx, void* hptr);
+/* number of kernels this context has launched (bench.py's gpu_launches) */
+uint64_t cg_launch_count(cg_ctx* ctx);
+
+/* ---- kernel (iii-eq): build_eq_x_r_vec with prefix masking.
+ * Replaces build_mle_as_ceno(hal.inner, gpu_points, &mut out, offset, num_instances, stream)
+ * (gkr_iop/src/gkr/layer/gpu/utils.rs:172-180, 211-219) and the CPU build_eq_x_r_vec call sites
+ * (gkr_iop/src/selector.rs:140,152; ceno_zkvm/src/scheme/cpu/mod.rs:121,417).
+ * out[b] = prod_i (b_i r_i + (1-b_i)(1-r_i)) for offset <= b < offset+num_instances, else 0.
+ * Pass offset = 0, num_instances = 2^k for the unmasked table.  h_point_ext: k ext elements on
+ * the HOST (k*2 u64).  d_out_ext: 2^k ext elements on the device. */
+int cg_build_eq(cg_ctx* ctx, const uint64_t* h_point_ext, uint32_t k, uint64_t* d_out_ext,
+                uint64_t offset, uint64_t num_instances, cg_stream s);
+
+/* SelectorType::compute (gkr_iop/src/selector.rs:131-245); replaces build_eq_x_r_with_sel_gpu /
+ * ordered_sparse_selector_gpu (gkr_iop/src/gkr/layer/gpu/utils.rs:121-229).
+ * kind: 0 Whole, 1 Prefix, 2 OrderedSparse{indices (sorted, host), inner_vars}, 3 QuarkBinaryTreeLessThan. */
+#define CG_SEL_WHOLE 0
+#define CG_SEL_PREFIX 1
+#define CG_SEL_ORDERED_SPARSE 2
+#define CG_SEL_QUARK_LT 3
+int cg_selector_compute(cg_ctx* ctx, int kind, const uint64_t* h_point_ext, uint32_t num_vars,
+                        uint64_t offset, uint64_t num_instances, const uint64_t* h_indices,
+                        uint32_t n_indices, uint32_t inner_vars, uint64_t* d_out_ext, cg_stream s);
+
+/* ---- kernel (ii): fix_variable, one variable (LSB).  MultilinearExtension::fix_variables*
+ * (external multilinear_extensions; invoked inside IOPProverState).
+ * d_out[b] = f[2b] + r (f[2b+1] - f[2b]), b < 2^(num_vars-1); output is always ext.
+ * Out of place (d_out must not overlap the input). */
+int cg_fix_variable(cg_ctx* ctx, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t r_ext[2],
+                    uint64_t* const* d_out_ext, cg_stream s);
+
+/* MultilinearExtension::evaluate(point) for a device MLE (used for final-evaluation checks,
+ * eval_cols_at_point_gpu in ceno_zkvm/src/scheme/gpu/mod.rs:24-40). */
+int cg_mle_evaluate(cg_ctx* ctx, const cg_mle_desc* mle, const uint64_t* h_point_ext, uint64_t h_out_ext[2], cg_stream s);
+
+/* ---- kernel (i) + round loop: IOPProverState (external sumcheck crate; call sites
+ * gkr_iop/src/gkr/layer/cpu/mod.rs:87-91, 217-237; ceno_zkvm/src/scheme/cpu/mod.rs:273-279, 490-498).
+ * Replaces CudaHalBB31::prove_generic_sumcheck_gpu(mles, mle_size_info, term_coefficients,
+ * mle_indices_per_term, max_num_var, max_degree, plan, transcript, stream)
+ * (gkr_iop/src/gkr/layer/gpu/mod.rs:259-271).
+ *
+ * P(x) = sum_t coeff_t * prod_{i in term t} mle_i(x) over {0,1}^num_vars.
+ *   term_coeff_ext : n_terms ext (HOST)      (extract_mle_relationships_from_monomial_terms)
+ *   term_offsets   : n_terms+1 u32 (HOST), CSR offsets into term_mle_idx
+ *   term_mle_idx   : indices into `mles`
+ * Round message = [p(1) .. p(degree)] (p(0) is not sent).
+ * All MLEs must have num_vars variables; mixed sizes ("frontload") return CG_ERR_UNSUPPORTED
+ * because that embedding is defined only in the un-vendored upstream crate. */
+#define CG_SC_DEFAULT 0u
+#define CG_SC_FORCE_GENERIC 1u /* disable shape-specialised kernels (testing) */
+#define CG_SC_NO_FUSE 2u       /* separate fold and eval launches (testing / profiling) */
+#define CG_SC_PROFILE 4u       /* time each round's kernels with CUDA events on the launching stream */
+int cg_sumcheck_create(cg_ctx* ctx, const cg_mle_desc* mles, uint32_t n_mles,
+                       const uint64_t* term_coeff_ext, const uint32_t* term_offsets,
+                       const uint32_t* term_mle_idx, uint32_t n_terms, uint32_t num_vars,
+                       uint32_t degree, uint32_t flags, cg_stream s, cg_sumcheck** out);
+/* Evaluate the current round's message into h_out_ext (degree ext = degree*2 u64).  Blocks until
+ * the values are on the host.  A pending challenge from cg_sumcheck_bind is applied first (the
+ * fold of round j-1 is fused with the evaluation of round j). */
+int cg_sumcheck_round_eval(cg_sumcheck* sc, uint64_t* h_out_ext);
+/* Bind the current round's variable to r (the transcript's challenge). */
+int cg_sumcheck_bind(cg_sumcheck* sc, const uint64_t r_ext[2]);
+/* After num_vars binds: get_mle_flatten_final_evaluations() — one ext per MLE, input order. */
+int cg_sumcheck_final_evals(cg_sumcheck* sc, uint64_t* h_out_ext);
+uint32_t cg_sumcheck_round(const cg_sumcheck* sc);
+/* current (partially folded) contents of MLE i: device pointer to 2^(num_vars-round) ext
+ * (or the caller's original buffer before the first fold).  Valid until the next call on sc. */
+int cg_sumcheck_peek(cg_sumcheck* sc, uint32_t mle, const void** dptr, uint64_t* len, uint32_t* is_ext);
+int cg_sumcheck_destroy(cg_sumcheck* sc);
+
+/* Whole loop with the transcript behind a host callback — what the reference does by handing
+ * &mut BasicTranscript to the device crate (gkr_iop/src/gkr/layer/gpu/mod.rs:252-253, 268).
+ * cb receives the round's evaluations and must return the challenge (absorb evals, absorb
+ * b"Internal round", sample).  Outputs on the HOST:
+ *   h_round_evals num_vars*degree ext, h_final_evals n_mles ext, h_challenges num_vars ext. */
+typedef void (*cg_challenge_cb)(void* user, uint32_t round, const uint64_t* round_evals_ext,
+                                uint32_t degree, uint64_t out_r_ext[2]);
+int cg_sumcheck_prove(cg_ctx* ctx, const cg_mle_desc* mles, uint32_t n_mles,
+                      const uint64_t* term_coeff_ext, const uint32_t* term_offsets,
+                      const uint32_t* term_mle_idx, uint32_t n_terms, uint32_t num_vars,
+                      uint32_t degree, uint32_t flags, cg_challenge_cb cb, void* user,
+                      uint64_t* h_round_evals, uint64_t* h_final_evals, uint64_t* h_challenges,
+                      cg_stream s);
+
+/* Same loop with a DEVICE-RESIDENT challenger: no host round trip between rounds; every round's
+ * kernels are enqueued back to back and the messages are read once at the end.  The challenger is
+ * the documented stand-in sponge (splitmix64, `cg_standin_*` below) — the reference's Poseidon2
+ * constants are upstream-only; a Poseidon2 challenger slots in behind the same
+ * device hook once they are available.  h_state_inout: the 8-byte stand-in transcript state. */
+int cg_sumcheck_prove_standin_device(cg_ctx* ctx, const cg_mle_desc* mles, uint32_t n_mles,
+                                     const uint64_t* term_coeff_ext, const uint32_t* term_offsets,
+                                     const uint32_t* term_mle_idx, uint32_t n_terms, uint32_t num_vars,
+                                     uint32_t degree, uint32_t flags, uint64_t* h_state_inout,
+                                     uint64_t* h_round_evals, uint64_t* h_final_evals,
+                                     uint64_t* h_challenges, cg_stream s);
+
+/* Per-round device time (ms) of the last cg_sumcheck_prove* call made with CG_SC_PROFILE on this
+ * context: n receives the round count, up to `cap` values are written.  (The reference wraps the
+ * same phases in tracing spans / NVTX ranges, ceno_zkvm/src/scheme/prover.rs:92-180.) */
+int cg_profile_last(cg_ctx* ctx, float* ms_out, uint32_t cap, uint32_t* n);
+
+/* Stand-in transcript on the host (same algorithm as the device challenger; NOT Poseidon2). */
+void cg_standin_init(uint64_t* state, const uint8_t* label, uint64_t len);
+void cg_standin_append_message(uint64_t* state, const uint8_t* msg, uint64_t len);
+void cg_standin_append_ext(uint64_t* state, const uint64_t* ext, uint64_t n);
+void cg_standin_sample(uint64_t* state, const char* label, uint64_t out_ext[2]);
+/* a ready-made cg_challenge_cb over a stand-in state (user = uint64_t* state) */
+void cg_standin_challenge_cb(void* user, uint32_t round, const uint64_t* evals, uint32_t degree, uint64_t out_r[2]);
+
+/* ---- tower prover: CpuTowerProver::create_proof (ceno_zkvm/src/scheme/cpu/mod.rs:346-554);
+ * replaces cuda_hal.tower.create_proof(hal, TowerInput{prod_specs, logup_specs}, NUM_FANIN,
+ * transcript, stream) (ceno_zkvm/src/scheme/gpu/mod.rs:336-353) and the tower builders
+ * build_prod_tower_from_virtual_ext_batch / build_logup_tower_from_virtual_ext_batch (:2365-2402).
+ *
+ * A spec is described by its LAST layer (the leaves); the library builds all upper layers on the
+ * device (infer_tower_product_witness / infer_tower_logup_witness,
+ * ceno_zkvm/src/scheme/utils.rs:488-659).
+ *   product spec: leaves[0..2) = two ext MLEs of 2^(num_vars-1) elements (low half, high half).
+ *   logup spec  : leaves[0..4) = p1, p2, q1, q2 of 2^num_vars ext; p1 = p2 = NULL means
+ *                 numerators are all one (utils.rs:556-577). */
+typedef struct cg_tower_spec {
+    const uint64_t* leaves[4]; /* device pointers */
+    uint32_t num_vars;         /* product: layers = num_vars; logup: layers = num_vars + 1 */
+    uint32_t is_logup;
+} cg_tower_spec;
+typedef struct cg_tower cg_tower;
+int cg_tower_build(cg_ctx* ctx, const cg_tower_spec* specs, uint32_t n_specs, cg_stream s, cg_tower** out);
+/* get_output_evals (ceno_zkvm/src/scheme/gpu/mod.rs:369-420): layer-0 values of spec i:
+ * 2 ext for a product spec, 4 for a logup spec. */
+int cg_tower_output_evals(cg_tower* tw, uint32_t spec, uint64_t* h_out_ext);
+/* Transcript hooks for the tower (SURVEY §A2 order).  sample(label) must absorb the label and
+ * return one ext challenge; append_exts absorbs final evaluations; sumcheck_begin absorbs
+ * (num_vars, degree) exactly as IOPProverState::prove does before its first round. */
+typedef struct cg_transcript_vt {
+    void* user;
+    void (*sample)(void* user, const char* label, uint64_t out_ext[2]);
+    void (*append_exts)(void* user, const uint64_t* ext, uint64_t n);
+    void (*sumcheck_begin)(void* user, uint64_t num_vars, uint64_t degree);
+    cg_challenge_cb round_challenge;
+} cg_transcript_vt;
+/* Returns the proof flattened the way TowerProofs stores it per round (round = 1..max):
+ *   round*3 ext sumcheck messages, then 2 ext per live product spec, 4 ext per live logup spec.
+ * h_proof must hold cg_tower_proof_len() u64; h_point receives the final point (max_round+1 ext). */
+uint64_t cg_tower_proof_len(const cg_tower* tw);
+uint32_t cg_tower_point_len(const cg_tower* tw);
+int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, uint64_t* h_proof, uint64_t* h_point);
+int cg_tower_destroy(cg_tower* tw);
+/* ready-made vtable functions over a stand-in state (user = uint64_t* state) */
+void cg_standin_vt(uint64_t* state, cg_transcript_vt* out);
+
+/* ---- point-wise layer-output inference: wit_infer_by_monomial_expr
+ * (gkr_iop/src/gpu/mod.rs:599-609; CPU gkr_iop/src/cpu/mod.rs:119-176):
+ * out[b] = sum_t coeff_t prod_{i in t} mle_i[b], ext output of 2^num_vars elements. */
+int cg_wit_infer_by_monomial_expr(cg_ctx* ctx, const cg_mle_desc* mles, uint32_t n_mles,
+                                  const uint64_t* term_coeff_ext, const uint32_t* term_offsets,
+                                  const uint32_t* term_mle_idx, uint32_t n_terms, uint32_t num_vars,
+                                  uint64_t* d_out_ext, cg_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CENO_B200_H */

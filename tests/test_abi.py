@@ -1,0 +1,73 @@
+"""CPU-side checks of the drop-in boundary: the library loads, exports every symbol the header
+declares, and fails loudly (no fallback) without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from ceno_b200 import _lib
+from ceno_b200 import build as cbuild
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    cbuild.build()
+    return _lib.load()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "ceno_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cg_[a-z0-9_]+)\s*\(", src)) - {"cg_challenge_cb"})
+
+
+def test_header_and_loader_agree(lib):
+    assert header_symbols() == sorted(_lib.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    raw = C.CDLL(_lib.SO)
+    for name in header_symbols():
+        assert hasattr(raw, name), name
+
+
+def test_version_and_no_torch_types_in_abi(lib):
+    assert b"sm_100a" in lib.cg_version()
+    hdr = open(os.path.join(ROOT, "include", "ceno_b200.h")).read()
+    assert "torch" not in hdr and "at::" not in hdr
+
+
+def test_product_does_not_import_oracle():
+    # the oracle is test infrastructure; the product path must never reach it
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ceno_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("oracle is test infrastructure", ""), os.path.join(dirpath, f)
+
+
+def test_fails_loudly_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ctx = C.c_void_p()
+    assert lib.cg_init(0, C.byref(ctx)) == 5  # CG_ERR_NO_DEVICE
+    from ceno_b200 import CenoB200Error, Device
+    with pytest.raises(CenoB200Error):
+        Device(0)
+
+
+def test_standin_transcript_host_matches_oracle():
+    # the stand-in sponge is restated independently in the library (host+device) and in the oracle
+    import numpy as np
+    from ceno_b200 import StandInTranscript
+    from oracle import oracle as orc
+    a, b = StandInTranscript(b"abc"), orc.Transcript(b"abc")
+    a.append_message(b"hello world!!"); b.append_message(b"hello world!!")
+    e = np.array([1, 2, 3, 4], dtype=np.uint64)
+    a.append_field_element_exts(e); b.append_ext(e)
+    assert tuple(a.sample_and_append_challenge(b"Internal round")) == tuple(b.sample(b"Internal round"))
+    assert int(a.state[0]) == b.state

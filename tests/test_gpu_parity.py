@@ -1,0 +1,342 @@
+"""Parity tests proper: every kernel of the hot path, called through the C ABI, against the CPU
+oracle on the same seeded inputs — bit-exact (integer work).  Needs a B200: `pytest -m gpu`."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+P = 0xFFFFFFFF00000001
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import ceno_b200 as cb
+    d = cb.Device(0)
+    yield d
+    d.close()
+
+
+def rnd_point(seed, k):
+    return orc.fill_ext(0xE9 ^ (seed << 8), k)
+
+
+def eq_np(a, b):
+    return np.array_equal(np.asarray(a, dtype=np.uint64).reshape(-1), np.asarray(b, dtype=np.uint64).reshape(-1))
+
+
+# ------------------------------------------------------------------ eq-build / selectors
+@pytest.mark.parametrize("k", [0, 1, 2, 5, 11, 12, 13, 16, 20])
+def test_build_eq_x_r_vec(dev, k):
+    import ceno_b200 as cb
+    r = rnd_point(k, k)
+    got = cb.build_eq_x_r_vec(dev, r)
+    assert eq_np(got.evaluations(), orc.build_eq_x_r_vec(r))
+    got.free()
+
+
+@pytest.mark.parametrize("k,offset,ninst", [(4, 3, 7), (12, 0, 1000), (14, 100, 9000), (14, 0, 0), (13, 8191, 1), (16, 12345, 40000)])
+def test_selector_prefix(dev, k, offset, ninst):
+    import ceno_b200 as cb
+    r = rnd_point(100 + k, k)
+    got = cb.SelectorType.compute(dev, cb.SelectorType.PREFIX, r, offset=offset, num_instances=ninst)
+    assert eq_np(got.evaluations(), orc.selector_compute(orc.SEL_PREFIX, r, offset=offset, num_instances=ninst))
+    got.free()
+
+
+def test_selector_ordered_sparse_and_quark(dev):
+    import ceno_b200 as cb
+    r = rnd_point(7, 9)
+    for ninst in [1, 5, 16]:
+        got = cb.SelectorType.compute(dev, cb.SelectorType.ORDERED_SPARSE, r, num_instances=ninst, indices=[0, 3, 17, 31], inner_vars=5)
+        assert eq_np(got.evaluations(), orc.selector_compute(orc.SEL_ORDERED_SPARSE, r, num_instances=ninst, indices=[0, 3, 17, 31], inner_vars=5))
+        got.free()
+    for nv, ninst in [(3, 5), (1, 2), (6, 33), (9, 512), (9, 300), (13, 5000)]:
+        r = rnd_point(nv + ninst, nv)
+        got = cb.SelectorType.compute(dev, cb.SelectorType.QUARK_LT, r, num_instances=ninst)
+        assert eq_np(got.evaluations(), orc.selector_compute(orc.SEL_QUARK_LT, r, num_instances=ninst))
+        got.free()
+
+
+# --------------------------------------------------------------------------- fold / evaluate
+@pytest.mark.parametrize("k,is_ext", [(1, True), (1, False), (2, True), (7, False), (12, True), (18, True), (18, False)])
+def test_fix_variable_and_evaluate(dev, k, is_ext):
+    import ceno_b200 as cb
+    n = 1 << k
+    data = orc.fill_ext(11 + k, n) if is_ext else orc.fill_base(11 + k, n)
+    mle = (cb.MultilinearExtension.from_evaluations_ext_vec if is_ext else cb.MultilinearExtension.from_evaluations_vec)(dev, k, data)
+    r = rnd_point(5, 1)
+    folded = mle.fix_variable(r)
+    assert eq_np(folded.evaluations(), orc.fix_variable(data, is_ext, r))
+    pt = rnd_point(6, k)
+    assert eq_np(mle.evaluate(pt), orc.mle_evaluate(data, is_ext, pt))
+    folded.free(); mle.free()
+
+
+def test_non_canonical_inputs_are_reduced(dev):
+    import ceno_b200 as cb
+    k = 6
+    n = 1 << k
+    canon = orc.fill_ext(99, n)
+    raw = canon.copy()
+    small = raw < np.uint64(0xFFFFFFFF)      # x + p still fits in u64
+    raw[small] = raw[small] + np.uint64(P)   # non-canonical representative of the same element
+    assert small.sum() == 0 or (raw[small] >= np.uint64(P)).all()
+    raw[0] = np.uint64(P)                    # p itself == 0
+    canon[0] = 0
+    raw[3] = np.uint64(2**64 - 1)
+    canon[3] = np.uint64(2**64 - 1 - P)
+    a = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, raw)
+    b = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, orc.fill_ext(98, n))
+    c = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, orc.fill_ext(97, n))
+    terms = [([1, 0], [0, 1, 2])]
+    for flags in (0, cb.IOPProverState.FORCE_GENERIC):
+        got = cb.IOPProverState.prove(dev, [a, b, c], terms, k, 3, transcript=cb.StandInTranscript(b"nc"), flags=flags)
+        want = orc.sumcheck_prove([(canon, True, k), (orc.fill_ext(98, n), True, k), (orc.fill_ext(97, n), True, k)], terms, k, 3,
+                                  transcript=orc.Transcript(b"nc"))
+        for g, w in zip(got, want):
+            assert eq_np(g, w)
+
+
+# ------------------------------------------------------------------------------- sumcheck
+def t3_inputs(k, seed=0):
+    n = 1 << k
+    w = orc.fill_ext(0xE9 + seed, k)
+    eq = orc.build_eq_x_r_vec(w)
+    a = orc.fill_ext(0xC0FFEE ^ (1 + 16 * seed), n)
+    b = orc.fill_ext(0xC0FFEE ^ (2 + 16 * seed), n)
+    return eq, a, b
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 7, 10, 13, 16, 20])
+@pytest.mark.parametrize("mode", ["fused", "nofuse", "generic", "device"])
+def test_t3_sumcheck_bit_exact(dev, k, mode):
+    """BASELINE config #2 shape (eq*A*B, degree 3, all ext) — every kernel variant."""
+    import ceno_b200 as cb
+    if mode != "fused" and k == 20:
+        pytest.skip("large size covered by the fused path")
+    eq, a, b = t3_inputs(k)
+    terms = [([1, 0], [0, 1, 2])]
+    want = orc.sumcheck_prove([(eq, True, k), (a, True, k), (b, True, k)], terms, k, 3, transcript=orc.Transcript(b"t3"))
+    mles = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, x) for x in (eq, a, b)]
+    flags = {"fused": 0, "device": 0, "nofuse": cb.IOPProverState.NO_FUSE, "generic": cb.IOPProverState.FORCE_GENERIC}[mode]
+    tr = cb.StandInTranscript(b"t3")
+    got = cb.IOPProverState.prove(dev, mles, terms, k, 3, transcript=tr, flags=flags, device_challenger=(mode == "device"))
+    for g, w in zip(got, want):
+        assert eq_np(g, w)
+    # inputs are shared (Arc) in the reference: the prover must not have modified them
+    assert eq_np(mles[1].evaluations(), a)
+    for m in mles:
+        m.free()
+
+
+def test_t3_with_coefficient_and_python_transcript(dev):
+    import ceno_b200 as cb
+    k = 9
+    eq, a, b = t3_inputs(k, seed=3)
+    coeff = [12345678901234567, 76543210987654321]
+    terms = [(coeff, [2, 0, 1])]
+
+    def cb_fn(j, evals):
+        t = orc.Transcript(b"py")
+        t.append_message(int(j).to_bytes(8, "little"))
+        t.append_ext(evals)
+        return t.sample(b"x")
+    want = orc.sumcheck_prove([(eq, True, k), (a, True, k), (b, True, k)], terms, k, 3, challenge_fn=cb_fn)
+    mles = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, x) for x in (eq, a, b)]
+    got = cb.IOPProverState.prove(dev, mles, terms, k, 3, challenge_fn=cb_fn)
+    for g, w in zip(got, want):
+        assert eq_np(g, w)
+
+
+@pytest.mark.parametrize("degree", [1, 2, 3, 4, 5, 8])
+def test_generic_terms_mixed_base_ext(dev, degree):
+    """Zerocheck-like instance: base-field witness columns, ext selectors, many monomial terms of
+    degree <= d, lower-degree terms included (gkr_iop/src/gkr/layer/zerocheck_layer.rs:86-207)."""
+    import ceno_b200 as cb
+    rng = random.Random(degree)
+    k, m = 8, 7
+    n = 1 << k
+    host, mles = [], []
+    for i in range(m):
+        is_ext = i >= 4
+        d = orc.fill_ext(500 + i, n) if is_ext else orc.fill_base(500 + i, n)
+        host.append((d, is_ext, k))
+        mles.append((cb.MultilinearExtension.from_evaluations_ext_vec if is_ext else cb.MultilinearExtension.from_evaluations_vec)(dev, k, d))
+    terms = []
+    for _ in range(12):
+        nf = rng.randint(0, degree)
+        terms.append(([rng.randrange(P), rng.randrange(P)], [rng.randrange(m) for _ in range(nf)]))
+    terms.append(([rng.randrange(P), 0], list(range(min(degree, m)))))
+    want = orc.sumcheck_prove(host, terms, k, degree, transcript=orc.Transcript(b"gen"))
+    for dc in (False, True):
+        got = cb.IOPProverState.prove(dev, mles, terms, k, degree, transcript=cb.StandInTranscript(b"gen"), device_challenger=dc)
+        for g, w in zip(got, want):
+            assert eq_np(g, w)
+
+
+def test_step_api_and_peek(dev):
+    import ceno_b200 as cb
+    k = 6
+    eq, a, b = t3_inputs(k, seed=5)
+    mles = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, x) for x in (eq, a, b)]
+    st = cb.IOPProverState(dev, mles, [([1, 0], [0, 1, 2])], k, 3)
+    cur = [eq, a, b]
+    for j in range(k):
+        msg = st.round_eval()
+        want, _, _ = orc.sumcheck_prove([(c, True, k - j) for c in cur], [([1, 0], [0, 1, 2])], k - j, 3, challenge_fn=lambda *_: np.array([1, 2], dtype=np.uint64))
+        assert eq_np(msg, want[0])
+        r = rnd_point(40 + j, 1)
+        st.bind(r)
+        cur = [orc.fix_variable(c, True, r) for c in cur]
+        if j < k - 1:
+            assert eq_np(st.peek(1), cur[1])
+    assert eq_np(st.get_mle_flatten_final_evaluations(), np.concatenate(cur))
+    st.close()
+
+
+def test_occupied_prefix_shorter_than_hypercube(dev):
+    """evaluations_len() < 2^num_vars: implicit zero tail."""
+    import ceno_b200 as cb
+    k = 7
+    n = 1 << k
+    occ = 77
+    a_full = np.zeros(n, np.uint64)
+    a_full[:occ] = orc.fill_base(1, occ)
+    e = orc.fill_ext(2, n)
+    a = cb.MultilinearExtension.from_evaluations_vec(dev, k, a_full[:occ])
+    em = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, e)
+    terms = [([5, 0], [0, 1])]
+    want = orc.sumcheck_prove([(a_full, False, k), (e, True, k)], terms, k, 2, transcript=orc.Transcript(b"occ"))
+    got = cb.IOPProverState.prove(dev, [a, em], terms, k, 2, transcript=cb.StandInTranscript(b"occ"))
+    for g, w in zip(got, want):
+        assert eq_np(g, w)
+
+
+def test_errors_mirror_reference_behaviour(dev):
+    import ceno_b200 as cb
+    a = cb.MultilinearExtension.from_evaluations_ext_vec(dev, 3, orc.fill_ext(1, 8))
+    b = cb.MultilinearExtension.from_evaluations_ext_vec(dev, 2, orc.fill_ext(2, 4))
+    with pytest.raises(cb.CenoB200Error) as ei:      # mixed num_vars: frontload semantics are upstream-only
+        cb.IOPProverState(dev, [a, b], [([1, 0], [0, 1])], 3, 2)
+    assert ei.value.code == 3
+    with pytest.raises(cb.CenoB200Error) as ei:      # term with more factors than the stated degree
+        cb.IOPProverState(dev, [a], [([1, 0], [0, 0, 0])], 3, 2)
+    assert ei.value.code == 2
+    st = cb.IOPProverState(dev, [a], [([1, 0], [0])], 3, 1)
+    with pytest.raises(cb.CenoB200Error) as ei:      # final evals before all variables are bound
+        st.get_mle_flatten_final_evaluations()
+    assert ei.value.code == 6
+    st.close()
+    with pytest.raises(cb.CenoB200Error):            # Prefix selector: end > 2^num_vars (selector.rs:144-150)
+        cb.SelectorType.compute(dev, cb.SelectorType.PREFIX, rnd_point(1, 3), offset=5, num_instances=4)
+
+
+def test_zero_variable_sumcheck_is_noop(dev):
+    import ceno_b200 as cb
+    a = cb.MultilinearExtension.from_evaluations_ext_vec(dev, 0, np.array([5, 6], dtype=np.uint64))
+    rounds, fin, chal = cb.IOPProverState.prove(dev, [a], [([1, 0], [0])], 0, 1, transcript=cb.StandInTranscript(b"z"))
+    assert rounds.size == 0 and chal.size == 0 and eq_np(fin, [5, 6])
+
+
+# ------------------------------------------------------------------------- wit_infer / tower
+def test_wit_infer_by_monomial_expr(dev):
+    import ceno_b200 as cb
+    from oracle import pyref as pr
+    k, n = 6, 64
+    b0 = orc.fill_base(1, n)
+    e1 = orc.fill_ext(2, n)
+    e2 = orc.fill_ext(3, n)
+    mles = [cb.MultilinearExtension.from_evaluations_vec(dev, k, b0), cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, e1),
+            cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, e2)]
+    terms = [([3, 4], [0, 1]), ([5, 0], [1, 2, 2]), ([7, 1], [])]
+    got = pr.to_pairs(cb.wit_infer_by_monomial_expr(dev, mles, terms, k).evaluations())
+    hp = [[(int(x), 0) for x in b0], pr.to_pairs(e1), pr.to_pairs(e2)]
+    for b in range(n):
+        assert got[b] == pr.poly_eval(hp, [(tuple(c), ids) for c, ids in terms], b)
+
+
+def _tower_case(dev, prod_nvs, logup_nvs, with_p, seed):
+    import ceno_b200 as cb
+    specs, o_prod, o_lk = [], [], []
+    s = seed
+    for nv in prod_nvs:
+        f1, f2 = orc.fill_ext(s, 1 << (nv - 1)), orc.fill_ext(s + 1, 1 << (nv - 1))
+        s += 2
+        pw, layers = orc.infer_tower_product_witness(nv, f1, f2)
+        o_prod.append((pw, nv, layers))
+        specs.append(cb.TowerProverSpec([cb.MultilinearExtension.from_evaluations_ext_vec(dev, nv - 1, f1),
+                                         cb.MultilinearExtension.from_evaluations_ext_vec(dev, nv - 1, f2)], nv, False))
+    for nv in logup_nvs:
+        q1, q2 = orc.fill_ext(s, 1 << nv), orc.fill_ext(s + 1, 1 << nv)
+        p1 = orc.fill_ext(s + 2, 1 << nv) if with_p else None
+        p2 = orc.fill_ext(s + 3, 1 << nv) if with_p else None
+        s += 4
+        lw, layers = orc.infer_tower_logup_witness(nv, p1, p2, q1, q2)
+        o_lk.append((lw, nv + 1, layers))
+        mk = lambda x: cb.MultilinearExtension.from_evaluations_ext_vec(dev, nv, x) if x is not None else None
+        specs.append(cb.TowerProverSpec([mk(p1), mk(p2), mk(q1), mk(q2)], nv, True))
+    tw = cb.TowerProver(dev, specs)
+    # output layer values (get_output_evals)
+    for i, (_, _, layers) in enumerate(o_prod):
+        assert eq_np(tw.output_evals(i)[:4], np.concatenate(layers[0]))
+    for i, (_, _, layers) in enumerate(o_lk):
+        assert eq_np(tw.output_evals(len(o_prod) + i), np.concatenate(layers[0]))
+    t_o, t_d = orc.Transcript(b"tower"), cb.StandInTranscript(b"tower")
+    want_proof, want_point = orc.tower_create_proof([(w, l) for w, l, _ in o_prod], [(w, l) for w, l, _ in o_lk], t_o)
+    got_proof, got_point = tw.create_proof(t_d)
+    assert eq_np(got_proof, want_proof)
+    assert eq_np(got_point, want_point)
+    assert int(t_d.state[0]) == t_o.state
+    tw.close()
+
+
+@pytest.mark.parametrize("prod_nvs,logup_nvs,with_p", [
+    ([4], [], False),                 # test_tower_proof_various_prod_size style (scheme/tests.rs:447-500)
+    ([2], [], False), ([10], [], False),
+    ([], [3], False), ([], [6], True),
+    ([6, 6], [5], False),             # read + write + lookup towers of one chip
+    ([9, 5], [8, 3], True),           # specs of different depth drop out of the early rounds
+    ([3] * 9, [2] * 5, False),        # more specs than the specialised kernel's table -> generic kernel
+])
+def test_tower_proof_bit_exact(dev, prod_nvs, logup_nvs, with_p):
+    _tower_case(dev, prod_nvs, logup_nvs, with_p, seed=1000 + 7 * len(prod_nvs) + len(logup_nvs))
+
+
+def test_tower_large(dev):
+    _tower_case(dev, [17, 17], [16], False, seed=77)
+
+
+# ------------------------------------------------ full-size, size-independent properties
+def test_t3_k24_verifier_relations(dev):
+    """BASELINE headline size (2^24 variables... points): too large for the oracle in seconds, so check
+    the verifier's relations (ceno_recursion_v2/src/main/mod.rs:3513-3526): claim chaining through
+    every round and the final product check with independently evaluated MLEs."""
+    import ceno_b200 as cb
+    from oracle import pyref as pr
+    k = 24
+    n = 1 << k
+    w = orc.fill_ext(0xE9, k)
+    eq = cb.build_eq_x_r_vec(dev, w)
+    a_h, b_h = orc.fill_ext(0xC0FFEE ^ 1, n), orc.fill_ext(0xC0FFEE ^ 2, n)
+    a = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, a_h)
+    b = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, b_h)
+    rounds, fin, chal = cb.IOPProverState.prove(dev, [eq, a, b], [([1, 0], [0, 1, 2])], k, 3, transcript=cb.StandInTranscript(b"k24"))
+    rounds2, fin2, chal2 = cb.IOPProverState.prove(dev, [eq, a, b], [([1, 0], [0, 1, 2])], k, 3, transcript=cb.StandInTranscript(b"k24"),
+                                                   device_challenger=True)
+    assert eq_np(rounds, rounds2) and eq_np(fin, fin2) and eq_np(chal, chal2)
+    # claim = sum_b eq(w,b) a(b) b(b) = (a*b)~(w): evaluate the pointwise product MLE at w on the device
+    ab = cb.wit_infer_by_monomial_expr(dev, [a, b], [([1, 0], [0, 1])], k)
+    claim = tuple(int(x) for x in ab.evaluate(w))
+    for j in range(k):
+        msg = [tuple(int(x) for x in e) for e in rounds[j]]
+        e0 = pr.esub(claim, msg[0])
+        claim = pr.lagrange_eval([e0] + msg, tuple(int(x) for x in chal[j]))
+    pt = chal.reshape(-1)
+    fe = [tuple(int(x) for x in f) for f in fin]
+    assert pr.emul(fe[0], pr.emul(fe[1], fe[2])) == claim
+    assert tuple(int(x) for x in orc.eq_eval(w, pt)) == fe[0]
+    assert tuple(int(x) for x in a.evaluate(pt)) == fe[1]
+    assert tuple(int(x) for x in orc.mle_evaluate(b_h, True, pt)) == fe[2]   # CPU check of one MLE (single fold chain)
