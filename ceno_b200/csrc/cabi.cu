@@ -652,13 +652,16 @@ static int launch_tower(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& 
     a.out = ro;
     const unsigned grid = grid_for(c, a.n_pairs);
     const bool canon = (src == 0);   // reading caller-provided buffers
+    const bool simple = a.n_prod == 1 && a.n_logup == 0 && a.alpha_one;
+#define CG_TOWER_LAUNCH(F, CN, SI) tower_round_kernel<F, CN, SI><<<grid, CG_THREADS, 0, sc->stream>>>(a)
     if (fold) {
-        if (canon) tower_round_kernel<true, true><<<grid, CG_THREADS, 0, sc->stream>>>(a);
-        else tower_round_kernel<true, false><<<grid, CG_THREADS, 0, sc->stream>>>(a);
+        if (canon) { if (simple) CG_TOWER_LAUNCH(true, true, true); else CG_TOWER_LAUNCH(true, true, false); }
+        else { if (simple) CG_TOWER_LAUNCH(true, false, true); else CG_TOWER_LAUNCH(true, false, false); }
     } else {
-        if (canon) tower_round_kernel<false, true><<<grid, CG_THREADS, 0, sc->stream>>>(a);
-        else tower_round_kernel<false, false><<<grid, CG_THREADS, 0, sc->stream>>>(a);
+        if (canon) { if (simple) CG_TOWER_LAUNCH(false, true, true); else CG_TOWER_LAUNCH(false, true, false); }
+        else { if (simple) CG_TOWER_LAUNCH(false, false, true); else CG_TOWER_LAUNCH(false, false, false); }
     }
+#undef CG_TOWER_LAUNCH
     LAUNCHED(c);
     CU(c, cudaGetLastError());
     return CG_OK;

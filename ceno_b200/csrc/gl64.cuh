@@ -2,75 +2,222 @@
 // F_p[X]/(X^2 - 7) in registers, for sm_100a.
 //
 // Restates the field of p3-goldilocks =0.4.3 / ff_ext::GoldilocksExt2 (reference Cargo.toml:34,
-// W = 7).  Representation: canonical u64 at every function boundary that leaves
-// the device; inside product chains values may be any u64 (the wide product + reduction is
-// correct for non-canonical operands).
+// W = 7).
 //
-// Identities used:  2^64 = 2^32 - 1 =: EPS,  2^96 = -1,  2^128 = -2^32   (mod p).
+// Design (the kernels are integer-issue bound, so instruction count is the budget):
+//  * products are accumulated UNREDUCED in a 160-bit accumulator (acc160: two u64 + a carry word);
+//    one reduction per dot product instead of one per multiply;
+//  * the reduction uses 2^64 = EPS, 2^96 = -1, 2^128 = -2^32 (mod p) and is written as PTX
+//    carry chains on 32-bit limbs (11 instructions, no compares/selects);
+//  * "weak" results are any u64 congruent to the value (fine as a multiplicand); "canonical" results
+//    are < p (required by gl_sub/gl_add operands and for everything that leaves the device);
+//  * round evaluation points use subtraction only: with nd = lo - hi,  f(1) = hi, f(2) = hi - nd,
+//    f(3) = f(2) - nd  (gl_sub is 5 instructions, a canonical gl_add 9).
+//
+// The same header compiles on the host (g++) with portable carry emulation so tests/test_field_host.py
+// can check the algebra of every sequence against big-int arithmetic without a GPU; the device path
+// is the PTX one.
 #pragma once
 #include <cstdint>
+
+#if defined(__CUDACC__)
 #include <cuda_runtime.h>
+#define GL_DEV __device__ __forceinline__
+#define GL_HD __host__ __device__ inline
+#else
+#define GL_DEV inline
+#define GL_HD inline
+#define __align__(x) __attribute__((aligned(x)))
+#endif
 
 #define GL_P 0xFFFFFFFF00000001ULL
 #define GL_EPS 0xFFFFFFFFULL
-
-#define GL_DEV __device__ __forceinline__
 
 struct __align__(16) ext_t {
     uint64_t c0, c1;
 };
 
-// ---------------------------------------------------------------- base field
-GL_DEV uint64_t gl_canon(uint64_t x) { return x >= GL_P ? x - GL_P : x; }
-
-// a, b canonical -> canonical
-GL_DEV uint64_t gl_add(uint64_t a, uint64_t b) {
-    uint64_t s = a + b;
-    // overflow past 2^64, or landing in [p, 2^64): both are fixed by adding EPS (== subtracting p mod 2^64)
-    return ((s < a) | (s >= GL_P)) ? s + GL_EPS : s;
+// ---------------------------------------------------------------- 64x64 -> 128 product
+GL_DEV void gl_mulwide(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umul64hi(a, b);   // nvcc fuses the pair into 4 IMAD.WIDE.U32 + 2 IADD3
+#else
+    unsigned __int128 x = (unsigned __int128)a * b;
+    lo = (uint64_t)x;
+    hi = (uint64_t)(x >> 64);
+#endif
 }
+
+// ---------------------------------------------------------------- 160-bit lazy accumulator
+struct acc160 {
+    uint64_t s0, s1;
+    uint32_t s2;   // carries out of bit 128 (< 2^31)
+};
+GL_DEV void acc_zero(acc160& A) { A.s0 = 0; A.s1 = 0; A.s2 = 0; }
+GL_DEV void acc_set_mul(acc160& A, uint64_t a, uint64_t b) { gl_mulwide(a, b, A.s0, A.s1); A.s2 = 0; }
+GL_DEV void acc_set64(acc160& A, uint64_t x) { A.s0 = x; A.s1 = 0; A.s2 = 0; }
+// A += a*b
+GL_DEV void acc_mac(acc160& A, uint64_t a, uint64_t b) {
+    uint64_t lo, hi;
+    gl_mulwide(a, b, lo, hi);
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+        : "+l"(A.s0), "+l"(A.s1), "+r"(A.s2) : "l"(lo), "l"(hi));
+#else
+    unsigned __int128 t = (unsigned __int128)A.s0 + lo;
+    A.s0 = (uint64_t)t;
+    t = (unsigned __int128)A.s1 + hi + (uint64_t)(t >> 64);
+    A.s1 = (uint64_t)t;
+    A.s2 += (uint32_t)(t >> 64);
+#endif
+}
+// A += x (64-bit)
+GL_DEV void acc_add64(acc160& A, uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, 0;\n\taddc.u32 %2, %2, 0;"
+        : "+l"(A.s0), "+l"(A.s1), "+r"(A.s2) : "l"(x));
+#else
+    unsigned __int128 t = (unsigned __int128)A.s0 + x;
+    A.s0 = (uint64_t)t;
+    t = (unsigned __int128)A.s1 + (uint64_t)(t >> 64);
+    A.s1 = (uint64_t)t;
+    A.s2 += (uint32_t)(t >> 64);
+#endif
+}
+// A += B
+GL_DEV void acc_add(acc160& A, const acc160& B) {
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, %5;"
+        : "+l"(A.s0), "+l"(A.s1), "+r"(A.s2) : "l"(B.s0), "l"(B.s1), "r"(B.s2));
+#else
+    unsigned __int128 t = (unsigned __int128)A.s0 + B.s0;
+    A.s0 = (uint64_t)t;
+    t = (unsigned __int128)A.s1 + B.s1 + (uint64_t)(t >> 64);
+    A.s1 = (uint64_t)t;
+    A.s2 += B.s2 + (uint32_t)(t >> 64);
+#endif
+}
+
+// x = s0 + s1 2^64 + s2 2^128 (s2 < 2^31)  ->  some u64 congruent to x ("weak").
+//   s1 = h1 2^32 + h0:  x = s0 + (h0 << 32) - (h0 + h1 + (s2 << 32))  (mod p)
+//   T = s0 + (h0 << 32) (carry c), U = T - Z (borrow b), result = U + (c - b) EPS  — never wraps twice.
+GL_DEV uint64_t acc_reduce_weak(uint64_t s0, uint64_t s1, uint32_t s2) {
+#if defined(__CUDA_ARCH__)
+    uint64_t r;
+    asm("{\n\t"
+        ".reg .u32 a0, a1, h0, h1, t1, c, z0, z1, u0, u1, d, nd, dh;\n\t"
+        "mov.b64 {a0, a1}, %1;\n\t"
+        "mov.b64 {h0, h1}, %2;\n\t"
+        "add.cc.u32 t1, a1, h0;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "add.cc.u32 z0, h0, h1;\n\t"
+        "addc.u32 z1, %3, 0;\n\t"
+        "sub.cc.u32 u0, a0, z0;\n\t"
+        "subc.cc.u32 u1, t1, z1;\n\t"
+        "subc.u32 d, c, 0;\n\t"
+        "neg.s32 nd, d;\n\t"
+        "shr.s32 dh, d, 31;\n\t"
+        "add.cc.u32 u0, u0, nd;\n\t"
+        "addc.u32 u1, u1, dh;\n\t"
+        "mov.b64 %0, {u0, u1};\n\t"
+        "}"
+        : "=l"(r) : "l"(s0), "l"(s1), "r"(s2));
+    return r;
+#else
+    const uint32_t a0 = (uint32_t)s0, a1 = (uint32_t)(s0 >> 32), h0 = (uint32_t)s1, h1 = (uint32_t)(s1 >> 32);
+    uint64_t t = (uint64_t)a1 + h0;
+    const uint32_t t1 = (uint32_t)t, c = (uint32_t)(t >> 32);
+    t = (uint64_t)h0 + h1;
+    const uint32_t z0 = (uint32_t)t, z1 = s2 + (uint32_t)(t >> 32);
+    int64_t u = (int64_t)a0 - z0;
+    const uint32_t u0 = (uint32_t)u;
+    int64_t bor = u < 0 ? 1 : 0;
+    u = (int64_t)t1 - z1 - bor;
+    const uint32_t u1 = (uint32_t)u;
+    bor = u < 0 ? 1 : 0;
+    const int32_t d = (int32_t)c - (int32_t)bor;
+    const uint32_t nd = (uint32_t)(-d), dh = (uint32_t)(d >> 31);
+    t = (uint64_t)u0 + nd;
+    const uint32_t r0 = (uint32_t)t;
+    const uint32_t r1 = u1 + dh + (uint32_t)(t >> 32);
+    return ((uint64_t)r1 << 32) | r0;
+#endif
+}
+GL_DEV uint64_t acc_weak(const acc160& A) { return acc_reduce_weak(A.s0, A.s1, A.s2); }
+
+// any u64 -> canonical:  x >= p  <=>  hi == 0xFFFFFFFF and lo != 0, and then x - p = lo - 1
+GL_HD uint64_t gl_canon(uint64_t x) {
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    return (hi == 0xFFFFFFFFu && lo != 0) ? (uint64_t)(lo - 1) : x;
+}
+GL_DEV uint64_t acc_canon(const acc160& A) { return gl_canon(acc_weak(A)); }
+
+// ---------------------------------------------------------------- base field
+// a, b canonical -> canonical (5 instructions)
 GL_DEV uint64_t gl_sub(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    uint64_t r;
+    asm("{\n\t"
+        ".reg .u32 a0, a1, b0, b1, m;\n\t"
+        "mov.b64 {a0, a1}, %1;\n\t"
+        "mov.b64 {b0, b1}, %2;\n\t"
+        "sub.cc.u32 a0, a0, b0;\n\t"
+        "subc.cc.u32 a1, a1, b1;\n\t"
+        "subc.u32 m, 0, 0;\n\t"          // m = -borrow
+        "sub.cc.u32 a0, a0, m;\n\t"      // borrow: subtract EPS (== add p)
+        "subc.u32 a1, a1, 0;\n\t"
+        "mov.b64 %0, {a0, a1};\n\t"
+        "}"
+        : "=l"(r) : "l"(a), "l"(b));
+    return r;
+#else
     uint64_t d = a - b;
     return (a < b) ? d - GL_EPS : d;
+#endif
+}
+// a, b canonical -> canonical
+GL_DEV uint64_t gl_add(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    uint64_t r;
+    asm("{\n\t"
+        ".reg .u32 a0, a1, b0, b1, m;\n\t"
+        ".reg .pred q;\n\t"
+        "mov.b64 {a0, a1}, %1;\n\t"
+        "mov.b64 {b0, b1}, %2;\n\t"
+        // nb = p - b  (b = 0 gives p, which the subtraction below handles)
+        "sub.cc.u32 b0, 1, b0;\n\t"
+        "subc.u32 b1, 0xFFFFFFFF, b1;\n\t"
+        // a - nb
+        "sub.cc.u32 a0, a0, b0;\n\t"
+        "subc.cc.u32 a1, a1, b1;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 a0, a0, m;\n\t"
+        "subc.u32 a1, a1, 0;\n\t"
+        "mov.b64 %0, {a0, a1};\n\t"
+        "}"
+        : "=l"(r) : "l"(a), "l"(b));
+    return r;
+#else
+    uint64_t nb = GL_P - b;          // in [1, p]
+    uint64_t d = a - nb;
+    return (a < nb) ? d - GL_EPS : d;
+#endif
 }
 GL_DEV uint64_t gl_neg(uint64_t a) { return a ? GL_P - a : 0; }
 
-// x = lo + hi 2^64 + top 2^128  (top < 2^31)  ->  canonical residue
-GL_DEV uint64_t gl_reduce160(uint64_t lo, uint64_t hi, uint64_t top) {
-    uint64_t hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
-    uint64_t sub = hi_hi + (top << 32);      // hi_hi 2^96 = -hi_hi ; top 2^128 = -top 2^32
-    uint64_t t0 = lo - sub;
-    if (lo < sub) t0 -= GL_EPS;              // wrapped by 2^64 = EPS
-    uint64_t t1 = hi_lo * GL_EPS;            // hi_lo 2^64 = hi_lo EPS  (< 2^64)
-    uint64_t r = t0 + t1;
-    if (r < t1) r += GL_EPS;
-    return gl_canon(r);
+// any u64 operands -> weak / canonical product
+GL_DEV uint64_t gl_mul_weak(uint64_t a, uint64_t b) {
+    uint64_t lo, hi;
+    gl_mulwide(a, b, lo, hi);
+    return acc_reduce_weak(lo, hi, 0);
 }
-GL_DEV uint64_t gl_reduce128(uint64_t lo, uint64_t hi) { return gl_reduce160(lo, hi, 0); }
-
-// any u64 operands -> canonical
-GL_DEV uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_reduce128(a * b, __umul64hi(a, b)); }
-
-// a0*b0 + a1*b1 with ONE reduction (129-bit intermediate)
-GL_DEV uint64_t gl_dot2(uint64_t a0, uint64_t b0, uint64_t a1, uint64_t b1) {
-    uint64_t l0 = a0 * b0, h0 = __umul64hi(a0, b0);
-    uint64_t l1 = a1 * b1, h1 = __umul64hi(a1, b1);
-    uint64_t lo = l0 + l1;
-    uint64_t c = lo < l0;
-    uint64_t hi = h0 + h1;
-    uint64_t top = hi < h0;
-    hi += c;
-    top += (hi < c);
-    return gl_reduce160(lo, hi, top);
-}
-
-// 7 * a  (a canonical) -> canonical.  7a < 2^67: 7a = lo + t 2^64, t < 8 -> lo + t EPS.
-GL_DEV uint64_t gl_mul7(uint64_t a) {
-    uint64_t lo = a * 7ULL, t = __umul64hi(a, 7ULL);
-    uint64_t add = t * GL_EPS;               // < 2^35
-    uint64_t r = lo + add;
-    if (r < add) r += GL_EPS;
-    return gl_canon(r);
+GL_DEV uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_canon(gl_mul_weak(a, b)); }
+// 7 a for any u64 a -> weak   (7a < 2^67)
+GL_DEV uint64_t gl_mul7_weak(uint64_t a) {
+    uint64_t lo, hi;
+    gl_mulwide(a, 7ULL, lo, hi);
+    return acc_reduce_weak(lo, hi, 0);
 }
 
 // ---------------------------------------------------------------- extension
@@ -81,23 +228,60 @@ GL_DEV ext_t ext_add(ext_t a, ext_t b) { return ext_make(gl_add(a.c0, b.c0), gl_
 GL_DEV ext_t ext_sub(ext_t a, ext_t b) { return ext_make(gl_sub(a.c0, b.c0), gl_sub(a.c1, b.c1)); }
 GL_DEV ext_t ext_canon(ext_t a) { return ext_make(gl_canon(a.c0), gl_canon(a.c1)); }
 
-// (a0 + a1 X)(b0 + b1 X) = a0 b0 + 7 a1 b1 + (a0 b1 + a1 b0) X ; 4 wide products, 2 reductions
-GL_DEV ext_t ext_mul(ext_t a, ext_t b) {
-    uint64_t b1_7 = gl_mul7(gl_canon(b.c1));
-    return ext_make(gl_dot2(a.c0, b.c0, a.c1, b1_7), gl_dot2(a.c0, b.c1, a.c1, b.c0));
+// lazy extension accumulator: value = A0 + A1 X, both unreduced
+struct eacc {
+    acc160 A0, A1;
+};
+GL_DEV void eacc_zero(eacc& E) { acc_zero(E.A0); acc_zero(E.A1); }
+// E += a * b with b's 7*c1 supplied:  (a0 + a1 X)(b0 + b1 X) = a0 b0 + a1 (7 b1) + (a0 b1 + a1 b0) X
+GL_DEV void eacc_mac(eacc& E, ext_t a, ext_t b, uint64_t b1_7) {
+    acc_mac(E.A0, a.c0, b.c0);
+    acc_mac(E.A0, a.c1, b1_7);
+    acc_mac(E.A1, a.c0, b.c1);
+    acc_mac(E.A1, a.c1, b.c0);
 }
-// multiplier with 7*c1 precomputed, for a fixed right operand (the fold challenge r)
+GL_DEV void eacc_add_ext(eacc& E, ext_t x) { acc_add64(E.A0, x.c0); acc_add64(E.A1, x.c1); }
+GL_DEV ext_t eacc_weak(const eacc& E) { return ext_make(acc_weak(E.A0), acc_weak(E.A1)); }
+GL_DEV ext_t eacc_canon(const eacc& E) { return ext_make(acc_canon(E.A0), acc_canon(E.A1)); }
+
+// fixed right operand with 7*c1 precomputed (fold challenge r, alphas)
 struct extmul_t {
     uint64_t c0, c1, c1_7;
 };
 GL_DEV extmul_t extmul_prep(ext_t b) {
-    extmul_t m; m.c0 = gl_canon(b.c0); m.c1 = gl_canon(b.c1); m.c1_7 = gl_mul7(m.c1); return m;
+    extmul_t m; m.c0 = gl_canon(b.c0); m.c1 = gl_canon(b.c1); m.c1_7 = gl_canon(gl_mul7_weak(m.c1)); return m;
 }
+GL_DEV void eacc_mac_prep(eacc& E, ext_t a, const extmul_t& b) {
+    acc_mac(E.A0, a.c0, b.c0);
+    acc_mac(E.A0, a.c1, b.c1_7);
+    acc_mac(E.A1, a.c0, b.c1);
+    acc_mac(E.A1, a.c1, b.c0);
+}
+// a * b for any u64 limbs; weak / canonical result
+GL_DEV ext_t ext_mul_weak(ext_t a, ext_t b) {
+    eacc E;
+    const uint64_t b1_7 = gl_mul7_weak(b.c1);
+    acc_set_mul(E.A0, a.c0, b.c0); acc_mac(E.A0, a.c1, b1_7);
+    acc_set_mul(E.A1, a.c0, b.c1); acc_mac(E.A1, a.c1, b.c0);
+    return eacc_weak(E);
+}
+GL_DEV ext_t ext_mul(ext_t a, ext_t b) { return ext_canon(ext_mul_weak(a, b)); }
 GL_DEV ext_t ext_mul_prep(ext_t a, const extmul_t& b) {
-    return ext_make(gl_dot2(a.c0, b.c0, a.c1, b.c1_7), gl_dot2(a.c0, b.c1, a.c1, b.c0));
+    eacc E;
+    acc_set_mul(E.A0, a.c0, b.c0); acc_mac(E.A0, a.c1, b.c1_7);
+    acc_set_mul(E.A1, a.c0, b.c1); acc_mac(E.A1, a.c1, b.c0);
+    return eacc_canon(E);
 }
 GL_DEV ext_t ext_mul_base(ext_t a, uint64_t b) { return ext_make(gl_mul(a.c0, b), gl_mul(a.c1, b)); }
+// x + d * r  (the fold), one reduction per limb; x canonical or not, result canonical
+GL_DEV ext_t ext_fma_prep(ext_t x, ext_t d, const extmul_t& r) {
+    eacc E;
+    acc_set_mul(E.A0, d.c0, r.c0); acc_mac(E.A0, d.c1, r.c1_7); acc_add64(E.A0, x.c0);
+    acc_set_mul(E.A1, d.c0, r.c1); acc_mac(E.A1, d.c1, r.c0); acc_add64(E.A1, x.c1);
+    return eacc_canon(E);
+}
 
+#if defined(__CUDACC__)
 // ---------------------------------------------------------------- memory helpers
 // 16-byte and 32-byte vector accesses (LDG.E.128 / LDG.E.ENL2.256 on sm_100a).
 GL_DEV ext_t ld_ext(const ext_t* p) {
@@ -112,7 +296,7 @@ GL_DEV void st_ext2(ext_t* p, ext_t a, ext_t b) {           // p 32-byte aligned
     asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a.c0), "l"(a.c1), "l"(b.c0), "l"(b.c1) : "memory");
 }
 
-// ---------------------------------------------------------------- warp / block reduction
+// ---------------------------------------------------------------- warp reduction
 GL_DEV uint64_t shfl_down_u64(uint64_t v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 GL_DEV ext_t warp_reduce_ext(ext_t v) {
 #pragma unroll
@@ -122,21 +306,22 @@ GL_DEV ext_t warp_reduce_ext(ext_t v) {
     }
     return v;
 }
+#endif
 
 // ---------------------------------------------------------------- stand-in transcript (device + host)
 // The documented stand-in sponge (NOT Poseidon2): see include/ceno_b200.h cg_standin_*.
-__host__ __device__ inline uint64_t cg_splitmix64(uint64_t x) {
+GL_HD uint64_t cg_splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ULL;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
     return x ^ (x >> 31);
 }
-__host__ __device__ inline void cg_tr_absorb(uint64_t& h, uint64_t x) { h = cg_splitmix64(h ^ cg_splitmix64(x)); }
-__host__ __device__ inline uint64_t cg_tr_squeeze(uint64_t& h) {
+GL_HD void cg_tr_absorb(uint64_t& h, uint64_t x) { h = cg_splitmix64(h ^ cg_splitmix64(x)); }
+GL_HD uint64_t cg_tr_squeeze(uint64_t& h) {
     h = cg_splitmix64(h + 0xD1B54A32D192ED03ULL);
     return h >= GL_P ? h - GL_P : h;
 }
-__host__ __device__ inline void cg_tr_append_message(uint64_t& h, const uint8_t* msg, uint64_t len) {
+GL_HD void cg_tr_append_message(uint64_t& h, const uint8_t* msg, uint64_t len) {
     cg_tr_absorb(h, 0x6D73670000000000ULL ^ len);
     for (uint64_t i = 0; i < len; i += 8) {
         uint64_t w = 0;

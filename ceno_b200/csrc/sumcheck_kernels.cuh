@@ -102,7 +102,8 @@ GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// pair loader: FOLD = read 4 consecutive ext, fold by r, write the pair; else read 2.
+// pair loader: FOLD = read 4 consecutive ext, fold by r (one reduction per limb, x + d*r accumulated
+// unreduced), write the pair; else read 2.  Results are canonical.
 template <bool FOLD, bool CANON>
 GL_DEV void load_pair(const ext_t* __restrict__ in, ext_t* __restrict__ out, uint64_t item,
                       const extmul_t& r, ext_t& lo, ext_t& hi) {
@@ -111,8 +112,8 @@ GL_DEV void load_pair(const ext_t* __restrict__ in, ext_t* __restrict__ out, uin
         ld_ext2(in + 4 * item, x0, x1);
         ld_ext2(in + 4 * item + 2, x2, x3);
         if (CANON) { x0 = ext_canon(x0); x1 = ext_canon(x1); x2 = ext_canon(x2); x3 = ext_canon(x3); }
-        lo = ext_add(x0, ext_mul_prep(ext_sub(x1, x0), r));
-        hi = ext_add(x2, ext_mul_prep(ext_sub(x3, x2), r));
+        lo = ext_fma_prep(x0, ext_sub(x1, x0), r);
+        hi = ext_fma_prep(x2, ext_sub(x3, x2), r);
         st_ext2(out + 2 * item, lo, hi);
     } else {
         ld_ext2(in + 2 * item, lo, hi);
@@ -126,6 +127,10 @@ GL_DEV void load_pair(const ext_t* __restrict__ in, ext_t* __restrict__ out, uin
 //                          + sum_j [ an_j (p1_j q2_j + p2_j q1_j) + ad_j q1_j q2_j ](X,b) )
 // = the expression CpuTowerProver::create_proof builds per layer
 //   (ceno_zkvm/src/scheme/cpu/mod.rs:417-485).  T3 (eq*A*B) is n_prod = 1, n_logup = 0.
+//
+// Evaluation points by subtraction only: nd = lo - hi, f(1) = hi, f(2) = f(1) - nd, f(3) = f(2) - nd.
+// Inner sums and the per-thread round sums are kept as unreduced 160-bit accumulators; each is
+// reduced once (inner: once per item and point; round sums: once per thread).
 struct TowerArgs {
     const ext_t* eq_in;
     ext_t* eq_out;
@@ -137,66 +142,92 @@ struct TowerArgs {
     ext_t alpha_num[CG_TOWER_MAX_LOGUP];
     ext_t alpha_den[CG_TOWER_MAX_LOGUP];
     int n_prod, n_logup;
-    int alpha_one;            // every alpha_prod is 1 and n_logup == 0: skip the alpha multiply
+    int alpha_one;            // every alpha_prod is 1: skip the alpha multiply
     uint64_t n_pairs;         // pairs evaluated this launch (after the fold, if FOLD)
     ext_t r;                  // fold challenge (FOLD only) ...
     const ext_t* r_ptr;       // ... or read it from device memory (device challenger)
     RoundOut out;
 };
 
-template <bool FOLD, bool CANON>
+// H[t] += u * e for the three points; e given as (value at t=1, nd)
+GL_DEV void accumulate_point(eacc& H, ext_t u, ext_t e) { eacc_mac(H, u, e, gl_mul7_weak(e.c1)); }
+
+// SIMPLE = exactly one product spec with alpha = 1 and no logup spec (the T3 shape): no spec loops.
+template <bool FOLD, bool CANON, bool SIMPLE>
 __global__ void __launch_bounds__(CG_THREADS, 2) tower_round_kernel(const __grid_constant__ TowerArgs a) {
     extmul_t rm;
     if (FOLD) rm = extmul_prep(a.r_ptr ? ld_ext(a.r_ptr) : a.r);
-    ext_t acc[3] = {ext_zero(), ext_zero(), ext_zero()};
+    else { rm.c0 = 0; rm.c1 = 0; rm.c1_7 = 0; }
+    eacc H[3];
+    eacc_zero(H[0]); eacc_zero(H[1]); eacc_zero(H[2]);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < a.n_pairs; item += stride) {
-        ext_t in1 = ext_zero(), in2 = ext_zero(), in3 = ext_zero();
-        for (int p = 0; p < a.n_prod; p++) {
-            ext_t alo, ahi, blo, bhi;
-            load_pair<FOLD, CANON>(a.prod_in[p][0], a.prod_out[p][0], item, rm, alo, ahi);
-            load_pair<FOLD, CANON>(a.prod_in[p][1], a.prod_out[p][1], item, rm, blo, bhi);
-            if (!a.alpha_one) {   // fold alpha into a (2 muls) instead of into the 3 products
-                extmul_t al = extmul_prep(a.alpha_prod[p]);
-                alo = ext_mul_prep(alo, al);
-                ahi = ext_mul_prep(ahi, al);
-            }
-            const ext_t ad = ext_sub(ahi, alo), bd = ext_sub(bhi, blo);
-            const ext_t a2 = ext_add(ahi, ad), b2 = ext_add(bhi, bd);
-            const ext_t a3 = ext_add(a2, ad), b3 = ext_add(b2, bd);
-            in1 = ext_add(in1, ext_mul(ahi, bhi));
-            in2 = ext_add(in2, ext_mul(a2, b2));
-            in3 = ext_add(in3, ext_mul(a3, b3));
-        }
-        for (int l = 0; l < a.n_logup; l++) {
-            ext_t p1lo, p1hi, p2lo, p2hi, q1lo, q1hi, q2lo, q2hi;
-            load_pair<FOLD, CANON>(a.lk_in[l][0], a.lk_out[l][0], item, rm, p1lo, p1hi);
-            load_pair<FOLD, CANON>(a.lk_in[l][1], a.lk_out[l][1], item, rm, p2lo, p2hi);
-            load_pair<FOLD, CANON>(a.lk_in[l][2], a.lk_out[l][2], item, rm, q1lo, q1hi);
-            load_pair<FOLD, CANON>(a.lk_in[l][3], a.lk_out[l][3], item, rm, q2lo, q2hi);
-            const extmul_t an = extmul_prep(a.alpha_num[l]), adn = extmul_prep(a.alpha_den[l]);
-            const ext_t p1d = ext_sub(p1hi, p1lo), p2d = ext_sub(p2hi, p2lo);
-            const ext_t q1d = ext_sub(q1hi, q1lo), q2d = ext_sub(q2hi, q2lo);
-            ext_t p1 = p1hi, p2 = p2hi, q1 = q1hi, q2 = q2hi;
+        ext_t u[3];   // inner value at t = 1, 2, 3 (weak)
+        if (SIMPLE) {
+            ext_t alo, av, blo, bv;
+            load_pair<FOLD, CANON>(a.prod_in[0][0], a.prod_out[0][0], item, rm, alo, av);
+            load_pair<FOLD, CANON>(a.prod_in[0][1], a.prod_out[0][1], item, rm, blo, bv);
+            const ext_t and_ = ext_sub(alo, av), bnd = ext_sub(blo, bv);
 #pragma unroll
             for (int t = 0; t < 3; t++) {
-                const ext_t num = ext_add(ext_mul(p1, q2), ext_mul(p2, q1));
-                const ext_t den = ext_mul(q1, q2);
-                const ext_t v = ext_add(ext_mul_prep(num, an), ext_mul_prep(den, adn));
-                if (t == 0) in1 = ext_add(in1, v);
-                if (t == 1) in2 = ext_add(in2, v);
-                if (t == 2) in3 = ext_add(in3, v);
-                p1 = ext_add(p1, p1d); p2 = ext_add(p2, p2d); q1 = ext_add(q1, q1d); q2 = ext_add(q2, q2d);
+                u[t] = ext_mul_weak(av, bv);
+                if (t < 2) { av = ext_sub(av, and_); bv = ext_sub(bv, bnd); }
             }
+        } else {
+            eacc in[3];
+            eacc_zero(in[0]); eacc_zero(in[1]); eacc_zero(in[2]);
+            for (int p = 0; p < a.n_prod; p++) {
+                ext_t alo, av, blo, bv;
+                load_pair<FOLD, CANON>(a.prod_in[p][0], a.prod_out[p][0], item, rm, alo, av);
+                load_pair<FOLD, CANON>(a.prod_in[p][1], a.prod_out[p][1], item, rm, blo, bv);
+                if (!a.alpha_one) {   // fold alpha into a (2 muls) instead of into the 3 products
+                    const extmul_t al = extmul_prep(a.alpha_prod[p]);
+                    alo = ext_mul_prep(alo, al);
+                    av = ext_mul_prep(av, al);
+                }
+                const ext_t and_ = ext_sub(alo, av), bnd = ext_sub(blo, bv);
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    eacc_mac(in[t], av, bv, gl_mul7_weak(bv.c1));
+                    if (t < 2) { av = ext_sub(av, and_); bv = ext_sub(bv, bnd); }
+                }
+            }
+            for (int l = 0; l < a.n_logup; l++) {
+                ext_t p1lo, p1, p2lo, p2, q1lo, q1, q2lo, q2;
+                load_pair<FOLD, CANON>(a.lk_in[l][0], a.lk_out[l][0], item, rm, p1lo, p1);
+                load_pair<FOLD, CANON>(a.lk_in[l][1], a.lk_out[l][1], item, rm, p2lo, p2);
+                load_pair<FOLD, CANON>(a.lk_in[l][2], a.lk_out[l][2], item, rm, q1lo, q1);
+                load_pair<FOLD, CANON>(a.lk_in[l][3], a.lk_out[l][3], item, rm, q2lo, q2);
+                const extmul_t an = extmul_prep(a.alpha_num[l]), adn = extmul_prep(a.alpha_den[l]);
+                const ext_t p1n = ext_sub(p1lo, p1), p2n = ext_sub(p2lo, p2);
+                const ext_t q1n = ext_sub(q1lo, q1), q2n = ext_sub(q2lo, q2);
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    const uint64_t q1_7 = gl_mul7_weak(q1.c1), q2_7 = gl_mul7_weak(q2.c1);
+                    eacc N;   // p1 q2 + p2 q1, one reduction
+                    eacc_zero(N);
+                    eacc_mac(N, p1, q2, q2_7);
+                    eacc_mac(N, p2, q1, q1_7);
+                    eacc D;   // q1 q2
+                    eacc_zero(D);
+                    eacc_mac(D, q1, q2, q2_7);
+                    eacc_mac_prep(in[t], eacc_weak(N), an);
+                    eacc_mac_prep(in[t], eacc_weak(D), adn);
+                    if (t < 2) { p1 = ext_sub(p1, p1n); p2 = ext_sub(p2, p2n); q1 = ext_sub(q1, q1n); q2 = ext_sub(q2, q2n); }
+                }
+            }
+            u[0] = eacc_weak(in[0]); u[1] = eacc_weak(in[1]); u[2] = eacc_weak(in[2]);
         }
-        ext_t elo, ehi;
-        load_pair<FOLD, CANON>(a.eq_in, a.eq_out, item, rm, elo, ehi);
-        const ext_t ed = ext_sub(ehi, elo);
-        const ext_t e2 = ext_add(ehi, ed), e3 = ext_add(e2, ed);
-        acc[0] = ext_add(acc[0], ext_mul(in1, ehi));
-        acc[1] = ext_add(acc[1], ext_mul(in2, e2));
-        acc[2] = ext_add(acc[2], ext_mul(in3, e3));
+        ext_t elo, ev;
+        load_pair<FOLD, CANON>(a.eq_in, a.eq_out, item, rm, elo, ev);
+        const ext_t end_ = ext_sub(elo, ev);
+        accumulate_point(H[0], u[0], ev);
+        ev = ext_sub(ev, end_);
+        accumulate_point(H[1], u[1], ev);
+        ev = ext_sub(ev, end_);
+        accumulate_point(H[2], u[2], ev);
     }
+    ext_t acc[3] = {eacc_canon(H[0]), eacc_canon(H[1]), eacc_canon(H[2])};
     block_finish<3>(acc, a.out);
 }
 
