@@ -650,18 +650,30 @@ static int launch_tower(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& 
     a.r = sc->pending_r;
     a.r_ptr = sc->pending_r_ptr;
     a.out = ro;
-    const unsigned grid = grid_for(c, a.n_pairs);
     const bool canon = (src == 0);   // reading caller-provided buffers
     const bool simple = a.n_prod == 1 && a.n_logup == 0 && a.alpha_one;
-#define CG_TOWER_LAUNCH(F, CN, SI) tower_round_kernel<F, CN, SI><<<grid, CG_THREADS, 0, sc->stream>>>(a)
-    if (fold) {
-        if (canon) { if (simple) CG_TOWER_LAUNCH(true, true, true); else CG_TOWER_LAUNCH(true, true, false); }
-        else { if (simple) CG_TOWER_LAUNCH(true, false, true); else CG_TOWER_LAUNCH(true, false, false); }
-    } else {
-        if (canon) { if (simple) CG_TOWER_LAUNCH(false, true, true); else CG_TOWER_LAUNCH(false, true, false); }
-        else { if (simple) CG_TOWER_LAUNCH(false, false, true); else CG_TOWER_LAUNCH(false, false, false); }
-    }
+    // launch shape: threads x resident blocks per SM (one persistent wave, grid-stride loop)
+    static const int cfg = []() { const char* e = getenv("CG_TOWER_CFG"); return e ? atoi(e) : 0; }();
+    const int threads = simple ? (cfg == 1 || cfg == 2 ? 128 : (cfg == 3 ? 192 : 256)) : 256;
+    const int minb = simple ? (cfg == 1 ? 5 : (cfg == 2 ? 6 : (cfg == 3 ? 3 : 2))) : 2;
+    uint64_t blocks = (a.n_pairs + threads - 1) / threads;
+    const uint64_t cap = (uint64_t)c->sm_count * minb * (simple ? 1 : 2);
+    if (blocks > cap) blocks = cap;
+    if (blocks > CG_MAX_BLOCKS) blocks = CG_MAX_BLOCKS;
+    const unsigned grid = (unsigned)(blocks ? blocks : 1);
+#define CG_TOWER_LAUNCH2(F, CN, SI, TH, MB) tower_round_kernel<F, CN, SI, TH, MB><<<grid, TH, 0, sc->stream>>>(a)
+#define CG_TOWER_LAUNCH(F, CN)                                                   \
+    do {                                                                         \
+        if (!simple) CG_TOWER_LAUNCH2(F, CN, false, 256, 2);                     \
+        else if (cfg == 1) CG_TOWER_LAUNCH2(F, CN, true, 128, 5);                \
+        else if (cfg == 2) CG_TOWER_LAUNCH2(F, CN, true, 128, 6);                \
+        else if (cfg == 3) CG_TOWER_LAUNCH2(F, CN, true, 192, 3);                \
+        else CG_TOWER_LAUNCH2(F, CN, true, 256, 2);                              \
+    } while (0)
+    if (fold) { if (canon) CG_TOWER_LAUNCH(true, true); else CG_TOWER_LAUNCH(true, false); }
+    else { if (canon) CG_TOWER_LAUNCH(false, true); else CG_TOWER_LAUNCH(false, false); }
 #undef CG_TOWER_LAUNCH
+#undef CG_TOWER_LAUNCH2
     LAUNCHED(c);
     CU(c, cudaGetLastError());
     return CG_OK;

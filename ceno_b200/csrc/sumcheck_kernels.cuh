@@ -36,9 +36,9 @@ struct RoundOut {
 
 template <int D>
 GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out) {
-    __shared__ ext_t s_part[CG_THREADS / 32][D];
+    __shared__ ext_t s_part[CG_THREADS / 32][D];   // blockDim.x <= CG_THREADS
     __shared__ bool s_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
 #pragma unroll
     for (int x = 0; x < D; x++) {
         ext_t v = warp_reduce_ext(acc[x]);
@@ -48,7 +48,7 @@ GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out) {
     if (warp == 0) {
 #pragma unroll
         for (int x = 0; x < D; x++) {
-            ext_t v = lane < (CG_THREADS / 32) ? s_part[lane][x] : ext_zero();
+            ext_t v = lane < n_warps ? s_part[lane][x] : ext_zero();
             v = warp_reduce_ext(v);
             if (lane == 0) out.partials[(size_t)blockIdx.x * D + x] = v;
         }
@@ -77,7 +77,7 @@ GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out) {
         ext_t res[D];
 #pragma unroll
         for (int x = 0; x < D; x++) {
-            ext_t v = lane < (CG_THREADS / 32) ? s_part[lane][x] : ext_zero();
+            ext_t v = lane < n_warps ? s_part[lane][x] : ext_zero();
             res[x] = warp_reduce_ext(v);
         }
         if (lane == 0) {
@@ -153,8 +153,9 @@ struct TowerArgs {
 GL_DEV void accumulate_point(eacc& H, ext_t u, ext_t e) { eacc_mac(H, u, e, gl_mul7_weak(e.c1)); }
 
 // SIMPLE = exactly one product spec with alpha = 1 and no logup spec (the T3 shape): no spec loops.
-template <bool FOLD, bool CANON, bool SIMPLE>
-__global__ void __launch_bounds__(CG_THREADS, 2) tower_round_kernel(const __grid_constant__ TowerArgs a) {
+// THREADS x MINB = launch shape (registers per thread are capped at 65536 / (THREADS * MINB)).
+template <bool FOLD, bool CANON, bool SIMPLE, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) tower_round_kernel(const __grid_constant__ TowerArgs a) {
     extmul_t rm;
     if (FOLD) rm = extmul_prep(a.r_ptr ? ld_ext(a.r_ptr) : a.r);
     else { rm.c0 = 0; rm.c1 = 0; rm.c1_7 = 0; }

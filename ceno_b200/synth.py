@@ -1,5 +1,5 @@
 """Deterministic synthetic inputs: element i, limb l <- splitmix64(seed + 2i + l) mod p.
-numpy restatement used by bench.py (the product path may not call the oracle's generator)."""
+numpy generator used by bench.py and tools (the product path shares no code with the test infrastructure)."""
 import numpy as np
 
 P = np.uint64(0xFFFFFFFF00000001)
