@@ -23,6 +23,7 @@
 struct cg_ctx {
     int device = 0;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t max_smem_optin = 0;
     cudaStream_t own_stream = nullptr;
     std::mutex mu;
     std::string err;
@@ -77,6 +78,7 @@ CG_EXPORT int cg_init(int device_id, cg_ctx** out) {
     c->sm_count = p.multiProcessorCount;
     c->cc_major = p.major;
     c->cc_minor = p.minor;
+    c->max_smem_optin = p.sharedMemPerBlockOptin;
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         return CG_ERR_CUDA;
@@ -423,6 +425,7 @@ struct cg_sumcheck {
     uint64_t* d_tr_state = nullptr;
     ext_t* d_chal = nullptr;
     std::vector<void*> owned;
+    int* d_error = nullptr;
     std::vector<cudaEvent_t> ev;   // CG_SC_PROFILE: 2 events per round on the launching stream
 };
 
@@ -494,8 +497,11 @@ static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles,
     if (rc == CG_OK) { rc = sc_alloc(sc, 256, &p); sc->out.ticket = (unsigned*)p; }
     if (rc == CG_OK && cudaMemsetAsync(sc->out.ticket, 0, 256, st) != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "memset failed");
     if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(ext_t) * (size_t)(num_vars + 1) * degree, &p); sc->d_msgs = (ext_t*)p; }
+    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(ext_t) * (num_vars + 1), &p); sc->d_chal = (ext_t*)p; }
+    if (rc == CG_OK) { rc = sc_alloc(sc, 256, &p); sc->d_error = (int*)p; }
+    if (rc == CG_OK && cudaMemsetAsync(sc->d_error, 0, 256, st) != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "memset failed");
     if (rc == CG_OK) {
-        sc->h_pinned_bytes = sizeof(ext_t) * (CG_MAX_DEGREE + 4);
+        sc->h_pinned_bytes = sizeof(ext_t) * (CG_MAX_DEGREE + 4) + sizeof(TailMailbox) + 64;
         sc->h_pinned = (uint64_t*)pinned_get(c, sc->h_pinned_bytes);
         if (!sc->h_pinned) rc = set_err(c, CG_ERR_CUDA, "cudaHostAlloc failed");
     }
@@ -773,6 +779,77 @@ CG_EXPORT int cg_sumcheck_peek(cg_sumcheck* sc, uint32_t i, const void** dptr, u
     return CG_OK;
 }
 
+
+// ---- persistent tail (all remaining rounds in one CTA, arrays in shared memory)
+static TailMailbox* sc_mailbox(cg_sumcheck* sc) {
+    return (TailMailbox*)((char*)sc->h_pinned + ((sizeof(ext_t) * (CG_MAX_DEGREE + 4) + 63) & ~(size_t)63));
+}
+static bool tail_eligible(const cg_sumcheck* sc) {
+    if (!sc->tl.on || (sc->flags & (CG_SC_NO_FUSE | CG_SC_NO_TAIL)) || sc->round >= sc->num_vars) return false;
+    const uint64_t cur = 1ULL << (sc->num_vars - sc->folds);
+    const uint64_t n0 = sc->pending ? cur / 2 : cur;
+    const size_t n_slots = 1 + sc->tl.prod.size() + sc->tl.lk.size();
+    if (n0 < 2 || n0 > CG_TAIL_MAX_N || n_slots > 1 + 2 * CG_TOWER_MAX_PROD + 4 * CG_TOWER_MAX_LOGUP) return false;
+    return n_slots * n0 * sizeof(ext_t) + 4096 <= sc->ctx->max_smem_optin;
+}
+// launches the tail for rounds sc->round .. num_vars-1; d_tr_state == nullptr -> host mailbox
+static int launch_tail(cg_sumcheck* sc, uint64_t* d_tr_state, ext_t* d_msgs, ext_t* d_chal) {
+    cg_ctx* c = sc->ctx;
+    const TowerLayout& tl = sc->tl;
+    TailArgs a;
+    memset(&a, 0, sizeof(a));
+    const uint32_t f = sc->folds;
+    auto in = [&](uint32_t i) { return (const ext_t*)mle_buf(sc, i, f); };
+    a.t.eq_in = in(tl.eq);
+    a.t.n_prod = (int)tl.prod_alpha.size();
+    a.t.n_logup = (int)tl.lk_an.size();
+    int slot = 0;
+    a.final_idx[slot++] = (uint16_t)tl.eq;
+    for (int p = 0; p < a.t.n_prod; p++) {
+        for (int z = 0; z < 2; z++) { a.t.prod_in[p][z] = in(tl.prod[2 * p + z]); a.final_idx[slot++] = (uint16_t)tl.prod[2 * p + z]; }
+        a.t.alpha_prod[p] = tl.prod_alpha[p];
+    }
+    for (int l = 0; l < a.t.n_logup; l++) {
+        for (int z = 0; z < 4; z++) { a.t.lk_in[l][z] = in(tl.lk[4 * l + z]); a.final_idx[slot++] = (uint16_t)tl.lk[4 * l + z]; }
+        a.t.alpha_num[l] = tl.lk_an[l];
+        a.t.alpha_den[l] = tl.lk_ad[l];
+    }
+    a.t.alpha_one = tl.alpha_one ? 1 : 0;
+    a.t.r = sc->pending_r;
+    a.t.r_ptr = sc->pending_r_ptr;
+    a.entry_fold = sc->pending ? 1 : 0;
+    a.canon = (f == 0) ? 1 : 0;
+    const uint64_t cur = 1ULL << (sc->num_vars - f);
+    a.n0 = (uint32_t)(sc->pending ? cur / 2 : cur);
+    a.first_round = sc->round;
+    a.num_rounds = sc->num_vars;
+    a.d_msgs = d_msgs;
+    a.d_chal = d_chal;
+    a.d_final = sc->d_final;
+    a.d_tr_state = d_tr_state;
+    a.mail = d_tr_state ? nullptr : sc_mailbox(sc);
+    a.d_error = sc->d_error;
+    a.timeout_cycles = 8000000000ULL;   // ~4 s: a dead host must not hang the GPU
+    const size_t smem = (size_t)slot * a.n0 * sizeof(ext_t);
+    const bool simple = a.t.n_prod == 1 && a.t.n_logup == 0 && a.t.alpha_one;
+    if (simple) {
+        CU(c, cudaFuncSetAttribute(tower_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->max_smem_optin));
+        tower_tail_kernel<true><<<1, CG_TAIL_THREADS, smem, sc->stream>>>(a);
+    } else {
+        CU(c, cudaFuncSetAttribute(tower_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->max_smem_optin));
+        tower_tail_kernel<false><<<1, CG_TAIL_THREADS, smem, sc->stream>>>(a);
+    }
+    LAUNCHED(c);
+    CU(c, cudaGetLastError());
+    return CG_OK;
+}
+static void sc_mark_done(cg_sumcheck* sc) {
+    sc->round = sc->num_vars;
+    sc->folds = sc->num_vars;
+    sc->pending = false;
+    sc->evaluated = false;
+}
+
 static void prof_begin(cg_sumcheck* sc) {
     if (!(sc->flags & CG_SC_PROFILE)) return;
     sc->ev.resize(2 * (size_t)sc->num_vars);
@@ -803,6 +880,42 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
     for (uint32_t j = 0; j < sc->num_vars; j++) {
         uint64_t* msg = h_rounds + (size_t)j * sc->degree * 2;
         prof_mark(sc, j, 0);
+        if (tail_eligible(sc)) {
+            // one persistent launch for rounds j..; the transcript stays on the host behind a mailbox
+            cg_ctx* c = sc->ctx;
+            TailMailbox* mb = sc_mailbox(sc);
+            mb->seq_msg = 0; mb->seq_r = 0; mb->abort = 0;
+            __sync_synchronize();
+            CHK(launch_tail(sc, nullptr, sc->d_msgs, sc->d_chal));
+            int rc = CG_OK;
+            for (uint32_t jj = j; jj < sc->num_vars && rc == CG_OK; jj++) {
+                uint64_t spins = 0;
+                while (mb->seq_msg != (uint64_t)jj + 1) {
+                    if ((++spins & 0xFFFFF) == 0 && cudaStreamQuery(sc->stream) != cudaErrorNotReady) {
+                        if (mb->seq_msg == (uint64_t)jj + 1) break;
+                        rc = set_err(c, CG_ERR_CUDA, "tail kernel ended before posting its round message");
+                        break;
+                    }
+                }
+                if (rc != CG_OK) break;
+                __sync_synchronize();
+                uint64_t* m = h_rounds + (size_t)jj * sc->degree * 2;
+                for (uint32_t x = 0; x < 2 * sc->degree; x++) m[x] = mb->msg[x];
+                uint64_t r[2] = {0, 0};
+                cb(user, jj, m, sc->degree, r);
+                if (h_chal) { h_chal[2 * jj] = r[0]; h_chal[2 * jj + 1] = r[1]; }
+                mb->r[0] = r[0]; mb->r[1] = r[1];
+                __sync_synchronize();
+                mb->seq_r = (uint64_t)jj + 1;
+            }
+            if (rc != CG_OK) { mb->abort = 1; __sync_synchronize(); }
+            prof_mark(sc, j, 1);
+            for (uint32_t jj = j + 1; jj < sc->num_vars; jj++) { prof_mark(sc, jj, 0); prof_mark(sc, jj, 1); }
+            CU(c, cudaStreamSynchronize(sc->stream));
+            CHK(rc);
+            sc_mark_done(sc);
+            break;
+        }
         {   // round_eval with the end-of-kernels mark placed before the D2H copy
             cg_ctx* c = sc->ctx;
             RoundOut ro = sc->out;
@@ -843,8 +956,6 @@ static int sc_run_device(cg_sumcheck* sc, uint64_t* h_state, uint64_t* h_rounds,
     void* p = nullptr;
     CHK(sc_alloc(sc, 256, &p));
     sc->d_tr_state = (uint64_t*)p;
-    CHK(sc_alloc(sc, sizeof(ext_t) * (sc->num_vars + 1), &p));
-    sc->d_chal = (ext_t*)p;
     CU(c, cudaMemcpyAsync(sc->d_tr_state, h_state, 8, cudaMemcpyHostToDevice, sc->stream));
     prof_begin(sc);
     for (uint32_t j = 0; j < sc->num_vars; j++) {
@@ -853,6 +964,13 @@ static int sc_run_device(cg_sumcheck* sc, uint64_t* h_state, uint64_t* h_rounds,
         ro.d_tr_state = sc->d_tr_state;
         ro.d_r_out = sc->d_chal + j;
         prof_mark(sc, j, 0);
+        if (tail_eligible(sc)) {   // one persistent launch for every remaining round
+            CHK(launch_tail(sc, sc->d_tr_state, sc->d_msgs, sc->d_chal));
+            prof_mark(sc, j, 1);
+            for (uint32_t jj = j + 1; jj < sc->num_vars; jj++) { prof_mark(sc, jj, 0); prof_mark(sc, jj, 1); }
+            sc_mark_done(sc);
+            break;
+        }
         CHK(sc_enqueue_round(sc, ro));
         prof_mark(sc, j, 1);
         CHK(sc_apply_pending_fold_only(sc));

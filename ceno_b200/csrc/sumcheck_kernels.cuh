@@ -152,86 +152,262 @@ struct TowerArgs {
 // H[t] += u * e for the three points; e given as (value at t=1, nd)
 GL_DEV void accumulate_point(eacc& H, ext_t u, ext_t e) { eacc_mac(H, u, e, gl_mul7_weak(e.c1)); }
 
+// One hypercube pair of the tower-layer polynomial: H[t] += eq(t) * inner(t), t = 1, 2, 3.
+// L supplies the (lo, hi) pair of every MLE: from global memory with the fused fold (GlobalLoader) or
+// from shared memory (SmemLoader, tail kernel).
 // SIMPLE = exactly one product spec with alpha = 1 and no logup spec (the T3 shape): no spec loops.
-// THREADS x MINB = launch shape (registers per thread are capped at 65536 / (THREADS * MINB)).
-template <bool FOLD, bool CANON, bool SIMPLE, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) tower_round_kernel(const __grid_constant__ TowerArgs a) {
-    extmul_t rm;
-    if (FOLD) rm = extmul_prep(a.r_ptr ? ld_ext(a.r_ptr) : a.r);
-    else { rm.c0 = 0; rm.c1 = 0; rm.c1_7 = 0; }
-    eacc H[3];
-    eacc_zero(H[0]); eacc_zero(H[1]); eacc_zero(H[2]);
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < a.n_pairs; item += stride) {
-        ext_t u[3];   // inner value at t = 1, 2, 3 (weak)
-        if (SIMPLE) {
+template <bool SIMPLE, class L>
+GL_DEV void tower_item(const TowerArgs& a, L& ld, uint64_t item, eacc (&H)[3]) {
+    ext_t u[3];   // inner value at t = 1, 2, 3 (weak)
+    if (SIMPLE) {
+        ext_t alo, av, blo, bv;
+        ld.prod(0, 0, item, alo, av);
+        ld.prod(0, 1, item, blo, bv);
+        const ext_t and_ = ext_sub(alo, av), bnd = ext_sub(blo, bv);
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            u[t] = ext_mul_weak(av, bv);
+            if (t < 2) { av = ext_sub(av, and_); bv = ext_sub(bv, bnd); }
+        }
+    } else {
+        eacc in[3];
+        eacc_zero(in[0]); eacc_zero(in[1]); eacc_zero(in[2]);
+        for (int p = 0; p < a.n_prod; p++) {
             ext_t alo, av, blo, bv;
-            load_pair<FOLD, CANON>(a.prod_in[0][0], a.prod_out[0][0], item, rm, alo, av);
-            load_pair<FOLD, CANON>(a.prod_in[0][1], a.prod_out[0][1], item, rm, blo, bv);
+            ld.prod(p, 0, item, alo, av);
+            ld.prod(p, 1, item, blo, bv);
+            if (!a.alpha_one) {   // fold alpha into a (2 muls) instead of into the 3 products
+                const extmul_t al = extmul_prep(a.alpha_prod[p]);
+                alo = ext_mul_prep(alo, al);
+                av = ext_mul_prep(av, al);
+            }
             const ext_t and_ = ext_sub(alo, av), bnd = ext_sub(blo, bv);
 #pragma unroll
             for (int t = 0; t < 3; t++) {
-                u[t] = ext_mul_weak(av, bv);
+                eacc_mac(in[t], av, bv, gl_mul7_weak(bv.c1));
                 if (t < 2) { av = ext_sub(av, and_); bv = ext_sub(bv, bnd); }
             }
-        } else {
-            eacc in[3];
-            eacc_zero(in[0]); eacc_zero(in[1]); eacc_zero(in[2]);
-            for (int p = 0; p < a.n_prod; p++) {
-                ext_t alo, av, blo, bv;
-                load_pair<FOLD, CANON>(a.prod_in[p][0], a.prod_out[p][0], item, rm, alo, av);
-                load_pair<FOLD, CANON>(a.prod_in[p][1], a.prod_out[p][1], item, rm, blo, bv);
-                if (!a.alpha_one) {   // fold alpha into a (2 muls) instead of into the 3 products
-                    const extmul_t al = extmul_prep(a.alpha_prod[p]);
-                    alo = ext_mul_prep(alo, al);
-                    av = ext_mul_prep(av, al);
-                }
-                const ext_t and_ = ext_sub(alo, av), bnd = ext_sub(blo, bv);
-#pragma unroll
-                for (int t = 0; t < 3; t++) {
-                    eacc_mac(in[t], av, bv, gl_mul7_weak(bv.c1));
-                    if (t < 2) { av = ext_sub(av, and_); bv = ext_sub(bv, bnd); }
-                }
-            }
-            for (int l = 0; l < a.n_logup; l++) {
-                ext_t p1lo, p1, p2lo, p2, q1lo, q1, q2lo, q2;
-                load_pair<FOLD, CANON>(a.lk_in[l][0], a.lk_out[l][0], item, rm, p1lo, p1);
-                load_pair<FOLD, CANON>(a.lk_in[l][1], a.lk_out[l][1], item, rm, p2lo, p2);
-                load_pair<FOLD, CANON>(a.lk_in[l][2], a.lk_out[l][2], item, rm, q1lo, q1);
-                load_pair<FOLD, CANON>(a.lk_in[l][3], a.lk_out[l][3], item, rm, q2lo, q2);
-                const extmul_t an = extmul_prep(a.alpha_num[l]), adn = extmul_prep(a.alpha_den[l]);
-                const ext_t p1n = ext_sub(p1lo, p1), p2n = ext_sub(p2lo, p2);
-                const ext_t q1n = ext_sub(q1lo, q1), q2n = ext_sub(q2lo, q2);
-#pragma unroll
-                for (int t = 0; t < 3; t++) {
-                    const uint64_t q1_7 = gl_mul7_weak(q1.c1), q2_7 = gl_mul7_weak(q2.c1);
-                    eacc N;   // p1 q2 + p2 q1, one reduction
-                    eacc_zero(N);
-                    eacc_mac(N, p1, q2, q2_7);
-                    eacc_mac(N, p2, q1, q1_7);
-                    eacc D;   // q1 q2
-                    eacc_zero(D);
-                    eacc_mac(D, q1, q2, q2_7);
-                    eacc_mac_prep(in[t], eacc_weak(N), an);
-                    eacc_mac_prep(in[t], eacc_weak(D), adn);
-                    if (t < 2) { p1 = ext_sub(p1, p1n); p2 = ext_sub(p2, p2n); q1 = ext_sub(q1, q1n); q2 = ext_sub(q2, q2n); }
-                }
-            }
-            u[0] = eacc_weak(in[0]); u[1] = eacc_weak(in[1]); u[2] = eacc_weak(in[2]);
         }
-        ext_t elo, ev;
-        load_pair<FOLD, CANON>(a.eq_in, a.eq_out, item, rm, elo, ev);
-        const ext_t end_ = ext_sub(elo, ev);
-        accumulate_point(H[0], u[0], ev);
-        ev = ext_sub(ev, end_);
-        accumulate_point(H[1], u[1], ev);
-        ev = ext_sub(ev, end_);
-        accumulate_point(H[2], u[2], ev);
+        for (int l = 0; l < a.n_logup; l++) {
+            ext_t p1lo, p1, p2lo, p2, q1lo, q1, q2lo, q2;
+            ld.lk(l, 0, item, p1lo, p1);
+            ld.lk(l, 1, item, p2lo, p2);
+            ld.lk(l, 2, item, q1lo, q1);
+            ld.lk(l, 3, item, q2lo, q2);
+            const extmul_t an = extmul_prep(a.alpha_num[l]), adn = extmul_prep(a.alpha_den[l]);
+            const ext_t p1n = ext_sub(p1lo, p1), p2n = ext_sub(p2lo, p2);
+            const ext_t q1n = ext_sub(q1lo, q1), q2n = ext_sub(q2lo, q2);
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                const uint64_t q1_7 = gl_mul7_weak(q1.c1), q2_7 = gl_mul7_weak(q2.c1);
+                eacc N;   // p1 q2 + p2 q1, one reduction
+                eacc_zero(N);
+                eacc_mac(N, p1, q2, q2_7);
+                eacc_mac(N, p2, q1, q1_7);
+                eacc D;   // q1 q2
+                eacc_zero(D);
+                eacc_mac(D, q1, q2, q2_7);
+                eacc_mac_prep(in[t], eacc_weak(N), an);
+                eacc_mac_prep(in[t], eacc_weak(D), adn);
+                if (t < 2) { p1 = ext_sub(p1, p1n); p2 = ext_sub(p2, p2n); q1 = ext_sub(q1, q1n); q2 = ext_sub(q2, q2n); }
+            }
+        }
+        u[0] = eacc_weak(in[0]); u[1] = eacc_weak(in[1]); u[2] = eacc_weak(in[2]);
     }
+    ext_t elo, ev;
+    ld.eq(item, elo, ev);
+    const ext_t end_ = ext_sub(elo, ev);
+    accumulate_point(H[0], u[0], ev);
+    ev = ext_sub(ev, end_);
+    accumulate_point(H[1], u[1], ev);
+    ev = ext_sub(ev, end_);
+    accumulate_point(H[2], u[2], ev);
+}
+
+template <bool FOLD, bool CANON>
+struct GlobalLoader {
+    const TowerArgs& a;
+    extmul_t rm;
+    GL_DEV void eq(uint64_t item, ext_t& lo, ext_t& hi) { load_pair<FOLD, CANON>(a.eq_in, a.eq_out, item, rm, lo, hi); }
+    GL_DEV void prod(int p, int z, uint64_t item, ext_t& lo, ext_t& hi) { load_pair<FOLD, CANON>(a.prod_in[p][z], a.prod_out[p][z], item, rm, lo, hi); }
+    GL_DEV void lk(int l, int z, uint64_t item, ext_t& lo, ext_t& hi) { load_pair<FOLD, CANON>(a.lk_in[l][z], a.lk_out[l][z], item, rm, lo, hi); }
+};
+
+// THREADS x MINB = launch shape (registers per thread are capped at 65536 / (THREADS * MINB)).
+template <bool FOLD, bool CANON, bool SIMPLE, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) tower_round_kernel(const __grid_constant__ TowerArgs a) {
+    GlobalLoader<FOLD, CANON> ld{a, {0, 0, 0}};
+    if (FOLD) ld.rm = extmul_prep(a.r_ptr ? ld_ext(a.r_ptr) : a.r);
+    eacc H[3];
+    eacc_zero(H[0]); eacc_zero(H[1]); eacc_zero(H[2]);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < a.n_pairs; item += stride)
+        tower_item<SIMPLE>(a, ld, item, H);
     ext_t acc[3] = {eacc_canon(H[0]), eacc_canon(H[1]), eacc_canon(H[2])};
     block_finish<3>(acc, a.out);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tail kernel: once every MLE of the layer fits in one CTA's shared memory, ALL remaining rounds
+// (evaluate, challenge, fold ... final evaluations) run in a single persistent launch: no per-round
+// launch or host synchronisation.  The challenge comes from the device-resident challenger or, for
+// the reference's host-side transcript, from a host mailbox in mapped pinned memory (the kernel posts
+// the round message, the host answers with the challenge; ~one PCIe round trip per round).
+struct TailMailbox {            // mapped pinned host memory
+    volatile uint64_t seq_msg;  // device -> host: round index + 1 when msg[] is valid
+    uint64_t msg[2 * 3];
+    volatile uint64_t seq_r;    // host -> device: round index + 1 when r[] is valid
+    uint64_t r[2];
+    volatile uint64_t abort;    // host -> device: give up (callback failed)
+};
+struct TailArgs {
+    TowerArgs t;                // *_in = state to load; *_out unused; r / r_ptr = entry fold challenge
+    int entry_fold;             // 1: arrays hold 2*n0 elements, fold by r while loading
+    int canon;                  // caller-provided buffers: canonicalise on load
+    uint32_t n0;                // elements per MLE once loaded (power of two)
+    uint32_t first_round, num_rounds;   // rounds first_round .. num_rounds-1 are run here
+    ext_t* d_msgs;              // [num_rounds * 3]
+    ext_t* d_chal;              // [num_rounds]
+    ext_t* d_final;             // one ext per MLE, in the caller's MLE order
+    uint16_t final_idx[1 + 2 * CG_TOWER_MAX_PROD + 4 * CG_TOWER_MAX_LOGUP];   // slot -> MLE index
+    uint64_t* d_tr_state;       // device challenger state, or nullptr -> mailbox
+    TailMailbox* mail;
+    int* d_error;               // set to 1 on mailbox timeout/abort
+    unsigned long long timeout_cycles;
+};
+struct SmemLoader {
+    const ext_t* sm;
+    uint32_t n0;
+    int n_prod;
+    GL_DEV void get(int slot, uint64_t item, ext_t& lo, ext_t& hi) {
+        const ext_t* p = sm + (size_t)slot * n0 + 2 * item;
+        lo = p[0];
+        hi = p[1];
+    }
+    GL_DEV void eq(uint64_t item, ext_t& lo, ext_t& hi) { get(0, item, lo, hi); }
+    GL_DEV void prod(int p, int z, uint64_t item, ext_t& lo, ext_t& hi) { get(1 + 2 * p + z, item, lo, hi); }
+    GL_DEV void lk(int l, int z, uint64_t item, ext_t& lo, ext_t& hi) { get(1 + 2 * n_prod + 4 * l + z, item, lo, hi); }
+};
+#define CG_TAIL_THREADS 512
+#define CG_TAIL_MAX_N 4096
+GL_DEV const ext_t* tail_slot_ptr(const TowerArgs& t, int slot) {
+    if (slot == 0) return t.eq_in;
+    slot -= 1;
+    if (slot < 2 * t.n_prod) return t.prod_in[slot >> 1][slot & 1];
+    slot -= 2 * t.n_prod;
+    return t.lk_in[slot >> 2][slot & 3];
+}
+template <bool SIMPLE>
+__global__ void __launch_bounds__(CG_TAIL_THREADS, 1) tower_tail_kernel(const __grid_constant__ TailArgs a) {
+    extern __shared__ ext_t sm[];
+    __shared__ ext_t s_red[CG_TAIL_THREADS / 32][3];
+    __shared__ ext_t s_r;
+    __shared__ int s_abort;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_slots = 1 + 2 * a.t.n_prod + 4 * a.t.n_logup;
+    uint32_t n = a.n0;
+    if (tid == 0) s_abort = 0;
+    // ---- load (with the entry fold)
+    {
+        extmul_t rm = extmul_prep(a.entry_fold ? (a.t.r_ptr ? ld_ext(a.t.r_ptr) : a.t.r) : ext_zero());
+        for (int slot = 0; slot < n_slots; slot++) {
+            const ext_t* src = tail_slot_ptr(a.t, slot);
+            for (uint32_t b = tid; b < n; b += blockDim.x) {
+                ext_t v;
+                if (a.entry_fold) {
+                    ext_t lo = ld_ext(src + 2 * b), hi = ld_ext(src + 2 * b + 1);
+                    if (a.canon) { lo = ext_canon(lo); hi = ext_canon(hi); }
+                    v = ext_fma_prep(lo, ext_sub(hi, lo), rm);
+                } else {
+                    v = ld_ext(src + b);
+                    if (a.canon) v = ext_canon(v);
+                }
+                sm[(size_t)slot * a.n0 + b] = v;
+            }
+        }
+    }
+    __syncthreads();
+    SmemLoader ld{sm, a.n0, a.t.n_prod};
+    for (uint32_t j = a.first_round; j < a.num_rounds; j++) {
+        const uint32_t pairs = n >> 1;
+        eacc H[3];
+        eacc_zero(H[0]); eacc_zero(H[1]); eacc_zero(H[2]);
+        for (uint32_t item = tid; item < pairs; item += blockDim.x) tower_item<SIMPLE>(a.t, ld, item, H);
+        ext_t acc[3] = {eacc_canon(H[0]), eacc_canon(H[1]), eacc_canon(H[2])};
+#pragma unroll
+        for (int x = 0; x < 3; x++) {
+            const ext_t v = warp_reduce_ext(acc[x]);
+            if (lane == 0) s_red[warp][x] = v;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            ext_t res[3];
+#pragma unroll
+            for (int x = 0; x < 3; x++) res[x] = warp_reduce_ext(lane < (CG_TAIL_THREADS / 32) ? s_red[lane][x] : ext_zero());
+            if (lane == 0) {
+                ext_t r;
+#pragma unroll
+                for (int x = 0; x < 3; x++) a.d_msgs[(size_t)j * 3 + x] = res[x];
+                if (a.d_tr_state) {
+                    uint64_t h = *a.d_tr_state;
+#pragma unroll
+                    for (int x = 0; x < 3; x++) { cg_tr_absorb(h, res[x].c0); cg_tr_absorb(h, res[x].c1); }
+                    const uint8_t label[14] = {'I','n','t','e','r','n','a','l',' ','r','o','u','n','d'};
+                    cg_tr_append_message(h, label, 14);
+                    r.c0 = cg_tr_squeeze(h);
+                    r.c1 = cg_tr_squeeze(h);
+                    *a.d_tr_state = h;
+                } else {
+                    TailMailbox* mb = a.mail;
+#pragma unroll
+                    for (int x = 0; x < 3; x++) { mb->msg[2 * x] = res[x].c0; mb->msg[2 * x + 1] = res[x].c1; }
+                    __threadfence_system();
+                    mb->seq_msg = (uint64_t)j + 1;
+                    __threadfence_system();
+                    const long long t0 = clock64();
+                    r = ext_zero();
+                    while (true) {
+                        if (mb->seq_r == (uint64_t)j + 1) {
+                            __threadfence_system();
+                            r.c0 = gl_canon(((volatile uint64_t*)mb->r)[0]);
+                            r.c1 = gl_canon(((volatile uint64_t*)mb->r)[1]);
+                            break;
+                        }
+                        if (mb->abort || (unsigned long long)(clock64() - t0) > a.timeout_cycles) { s_abort = 1; *a.d_error = 1; break; }
+                    }
+                }
+                a.d_chal[j] = r;
+                s_r = r;
+            }
+        }
+        __syncthreads();
+        if (s_abort) return;
+        // ---- fold every MLE in shared memory: read the pairs, barrier, write the halves
+        const extmul_t rm = extmul_prep(s_r);
+        for (int slot = 0; slot < n_slots; slot++) {
+            ext_t* base = sm + (size_t)slot * a.n0;
+            constexpr int PER = (CG_TAIL_MAX_N / 2 + CG_TAIL_THREADS - 1) / CG_TAIL_THREADS;
+            ext_t v[PER];
+#pragma unroll
+            for (int c = 0; c < PER; c++) {
+                const uint32_t b = tid + c * CG_TAIL_THREADS;
+                if (b < pairs) {
+                    const ext_t lo = base[2 * b], hi = base[2 * b + 1];
+                    v[c] = ext_fma_prep(lo, ext_sub(hi, lo), rm);
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < PER; c++) {
+                const uint32_t b = tid + c * CG_TAIL_THREADS;
+                if (b < pairs) base[b] = v[c];
+            }
+        }
+        __syncthreads();
+        n = pairs;
+    }
+    for (int slot = tid; slot < n_slots; slot += blockDim.x) a.d_final[a.final_idx[slot]] = sm[(size_t)slot * a.n0];
+}
 // ---------------------------------------------------------------------------------------------
 // Generic monomial-term round evaluation: P = sum_t c_t prod_{i in S_t} f_i, base or ext MLEs
 // (the table extract_mle_relationships_from_monomial_terms hands to prove_generic_sumcheck_gpu,

@@ -111,19 +111,20 @@ def t3_inputs(k, seed=0):
 
 
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 7, 10, 13, 16, 20])
-@pytest.mark.parametrize("mode", ["fused", "nofuse", "generic", "device"])
+@pytest.mark.parametrize("mode", ["fused", "nofuse", "generic", "device", "notail", "device_notail"])
 def test_t3_sumcheck_bit_exact(dev, k, mode):
     """BASELINE config #2 shape (eq*A*B, degree 3, all ext) — every kernel variant."""
     import ceno_b200 as cb
-    if mode != "fused" and k == 20:
+    if mode not in ("fused", "device") and k == 20:
         pytest.skip("large size covered by the fused path")
     eq, a, b = t3_inputs(k)
     terms = [([1, 0], [0, 1, 2])]
     want = orc.sumcheck_prove([(eq, True, k), (a, True, k), (b, True, k)], terms, k, 3, transcript=orc.Transcript(b"t3"))
     mles = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, x) for x in (eq, a, b)]
-    flags = {"fused": 0, "device": 0, "nofuse": cb.IOPProverState.NO_FUSE, "generic": cb.IOPProverState.FORCE_GENERIC}[mode]
+    flags = {"fused": 0, "device": 0, "nofuse": cb.IOPProverState.NO_FUSE, "generic": cb.IOPProverState.FORCE_GENERIC,
+             "notail": cb.IOPProverState.NO_TAIL, "device_notail": cb.IOPProverState.NO_TAIL}[mode]
     tr = cb.StandInTranscript(b"t3")
-    got = cb.IOPProverState.prove(dev, mles, terms, k, 3, transcript=tr, flags=flags, device_challenger=(mode == "device"))
+    got = cb.IOPProverState.prove(dev, mles, terms, k, 3, transcript=tr, flags=flags, device_challenger=mode.startswith("device"))
     for g, w in zip(got, want):
         assert eq_np(g, w)
     # inputs are shared (Arc) in the reference: the prover must not have modified them
