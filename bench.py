@@ -43,52 +43,52 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    FIELDS = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    """SM clock and throttle reasons sampled through NVML DURING the GPU work of the bench."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
-
-    def _query(self):
-        # the reasons are called clocks_event_reasons.* on new drivers and clocks_throttle_reasons.* on older ones
-        for prefix in ("clocks_event_reasons", "clocks_throttle_reasons"):
-            q = "clocks.sm,clocks.max.sm," + ",".join(f"{prefix}.{f}" for f in self.FIELDS)
-            try:
-                r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                   capture_output=True, text=True, timeout=20)
-                if r.returncode == 0 and r.stdout.strip():
-                    return q
-            except Exception:
-                pass
-        return "clocks.sm,clocks.max.sm"
+        self.index, self.samples, self.reasons, self.stop_flag, self.t, self.max_mhz = index, [], set(), False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self._query()}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.nv = None
+            self.err = repr(e)
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # older bindings
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(mhz), int(util)))
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")], "samples": 0}
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        sm = [m for m, _ in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(sm), "sm_mhz_min": min(sm) if sm else None}
 
 
 # ----------------------------------------------------------------------------------- CPU arm
@@ -193,18 +193,17 @@ def gpu_arm(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps, out
 
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(args.warmup):
         ref_out = step()
         step(True)
-    clocks = ClockSampler(local)
-    clocks.start()
     l0 = dev.launch_count()
     ms, out = timed(step, args.steps)
     launches = dev.launch_count() - l0
     ms_dev, out_dev = timed(lambda: step(True), args.steps)
     # EQ-k (build_eq_x_r alone), timed separately
     ms_eq, _ = timed(lambda: cb.build_eq_x_r_vec(dev, w, stream=sh, out=eq_d), max(args.steps, 5))
-    clk = clocks.stop()
     for g, d in zip(out, out_dev):
         assert np.array_equal(g, d), "host-transcript and device-challenger runs disagree"
 
@@ -238,6 +237,7 @@ def gpu_arm(args):
     ms_e2e, out_e2e = timed(e2e_step, max(1, min(args.steps, 5)))
     for g, d in zip(out, out_e2e):
         assert np.array_equal(g, d)
+    clk = clocks.stop()
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     from oracle import oracle as orc

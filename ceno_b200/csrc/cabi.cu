@@ -789,7 +789,7 @@ static bool tail_eligible(const cg_sumcheck* sc) {
     const uint64_t cur = 1ULL << (sc->num_vars - sc->folds);
     const uint64_t n0 = sc->pending ? cur / 2 : cur;
     const size_t n_slots = 1 + sc->tl.prod.size() + sc->tl.lk.size();
-    if (n0 < 2 || n0 > CG_TAIL_MAX_N || n_slots > 1 + 2 * CG_TOWER_MAX_PROD + 4 * CG_TOWER_MAX_LOGUP) return false;
+    if (n0 < 2 || n0 > CG_TAIL_START_N || n_slots > 1 + 2 * CG_TOWER_MAX_PROD + 4 * CG_TOWER_MAX_LOGUP) return false;
     return n_slots * n0 * sizeof(ext_t) + 4096 <= sc->ctx->max_smem_optin;
 }
 // launches the tail for rounds sc->round .. num_vars-1; d_tr_state == nullptr -> host mailbox
@@ -833,10 +833,10 @@ static int launch_tail(cg_sumcheck* sc, uint64_t* d_tr_state, ext_t* d_msgs, ext
     const size_t smem = (size_t)slot * a.n0 * sizeof(ext_t);
     const bool simple = a.t.n_prod == 1 && a.t.n_logup == 0 && a.t.alpha_one;
     if (simple) {
-        CU(c, cudaFuncSetAttribute(tower_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->max_smem_optin));
+        if (smem > 32 * 1024) CU(c, cudaFuncSetAttribute(tower_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tower_tail_kernel<true><<<1, CG_TAIL_THREADS, smem, sc->stream>>>(a);
     } else {
-        CU(c, cudaFuncSetAttribute(tower_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->max_smem_optin));
+        if (smem > 32 * 1024) CU(c, cudaFuncSetAttribute(tower_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tower_tail_kernel<false><<<1, CG_TAIL_THREADS, smem, sc->stream>>>(a);
     }
     LAUNCHED(c);

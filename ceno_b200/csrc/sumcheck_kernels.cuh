@@ -289,7 +289,8 @@ struct SmemLoader {
     GL_DEV void lk(int l, int z, uint64_t item, ext_t& lo, ext_t& hi) { get(1 + 2 * n_prod + 4 * l + z, item, lo, hi); }
 };
 #define CG_TAIL_THREADS 512
-#define CG_TAIL_MAX_N 4096
+#define CG_TAIL_MAX_N 4096      // register staging of the in-place fold is sized for this
+#define CG_TAIL_START_N 2048    // enter the tail once each MLE has <= this many elements (one SM: ~2 items/thread)
 GL_DEV const ext_t* tail_slot_ptr(const TowerArgs& t, int slot) {
     if (slot == 0) return t.eq_in;
     slot -= 1;

@@ -1,0 +1,190 @@
+"""Multi-GPU sumcheck: the boolean hypercube sharded across the GPUs of one box.
+
+Layout: with LSB-first binding the top g = log2(N) index bits are bound last, so rank q
+owns the contiguous slice [q 2^(k-g), (q+1) 2^(k-g)) of every MLE.  Rounds 0 .. k-g-1 fold locally;
+the only exchange per round is the d extension-field partial sums (48 B for d = 3), combined by
+modular addition — NCCL has no F_p reduction, so the partials are all-gathered and summed (identical
+on every rank, which then run the transcript redundantly; no broadcast).  After k-g rounds every rank
+holds one element per MLE; those N*m elements are all-gathered and the last g rounds run replicated.
+
+Two exchange engines:
+  * host-orchestrated (this file): `exchange` = torch.distributed all_gather (NCCL on GPUs, gloo in
+    the CPU tests).  The protocol logic is independent of the local prover, which is pluggable.
+  * in-kernel over NVLink peer memory (cg_comm_* in the C ABI): the round kernel's last block stores
+    its partial into every peer's mailbox and combines — no host round trip.
+"""
+import numpy as np
+
+P = 0xFFFFFFFF00000001
+
+
+def modsum_ext(parts):
+    """Sum of ext-element arrays (u64 limbs) mod p, limb-wise."""
+    acc = [0] * parts[0].size
+    for p in parts:
+        for i, v in enumerate(p.reshape(-1)):
+            acc[i] = (acc[i] + int(v)) % P
+    return np.array(acc, dtype=np.uint64)
+
+
+def ext_mul_host(a, b):
+    return ((a[0] * b[0] + 7 * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+def eq_slice_scalar(w_high, q):
+    """prod_i (q_i w_i + (1 - q_i)(1 - w_i)) over the top variables: the factor of eq on rank q's slice."""
+    acc = (1, 0)
+    for i in range(len(w_high) // 2):
+        wi = (int(w_high[2 * i]), int(w_high[2 * i + 1]))
+        f = wi if (q >> i) & 1 else ((1 - wi[0]) % P, (-wi[1]) % P)
+        acc = ext_mul_host(acc, f)
+    return acc
+
+
+class TorchExchange:
+    """all_gather of a small u64 array through torch.distributed (NCCL -> CUDA staging, gloo -> CPU)."""
+
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.device = torch, dist, device
+        self.world = dist.get_world_size()
+
+    def __call__(self, arr):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr).view(np.int64).copy())
+        if self.device is not None:
+            t = t.to(self.device)
+        outs = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(outs, t)
+        return [o.cpu().numpy().view(np.uint64) for o in outs]
+
+
+def sharded_prove(local, k_local, g, degree, transcript, exchange, make_tail):
+    """Run the sharded protocol on this rank.
+
+    local     : local prover over this rank's slice: round_eval() -> 2d u64, bind(r), final_evals() -> [m, 2]
+    transcript: host transcript with sumcheck_begin/round (replicated on every rank)
+    exchange  : arr -> list of every rank's arr (rank order)
+    make_tail : arrays [m][2N u64] -> local-prover-like object over the gathered N-element MLEs
+    Returns (round_evals [k, d, 2], final_evals [m, 2], challenges [k, 2]) — identical on every rank and
+    identical to the single-device proof."""
+    k = k_local + g
+    transcript.append_message(int(k).to_bytes(8, "little"))
+    transcript.append_message(int(degree).to_bytes(8, "little"))
+    msgs, chals = [], []
+
+    def one_round(prover, combine):
+        part = prover.round_eval()
+        msg = modsum_ext(exchange(part)) if combine else part
+        transcript.append_field_element_exts(msg)
+        r = transcript.sample_and_append_challenge(b"Internal round")
+        prover.bind(r)
+        msgs.append(msg.copy())
+        chals.append(np.array(r, dtype=np.uint64))
+
+    for _ in range(k_local):
+        one_round(local, True)
+    fin = np.ascontiguousarray(local.final_evals(), dtype=np.uint64)           # [m, 2]
+    if g == 0:
+        final = fin
+    else:
+        allfin = exchange(fin.reshape(-1))                                        # N x (m*2)
+        m = fin.shape[0]
+        arrays = [np.concatenate([allfin[q][2 * i:2 * i + 2] for q in range(len(allfin))]) for i in range(m)]
+        tail = make_tail(arrays)
+        for _ in range(g):
+            one_round(tail, False)
+        final = np.ascontiguousarray(tail.final_evals(), dtype=np.uint64)
+    return (np.array(msgs, dtype=np.uint64).reshape(k, degree, 2), final.reshape(-1, 2), np.array(chals, dtype=np.uint64).reshape(k, 2))
+
+
+class GpuLocalProver:
+    """Local prover on this rank's GPU (IOPProverState step API over the C ABI)."""
+
+    def __init__(self, dev, mles, terms, num_vars, degree):
+        from .api import IOPProverState
+        self.st = IOPProverState(dev, mles, terms, num_vars, degree)
+
+    def round_eval(self):
+        return self.st.round_eval()
+
+    def bind(self, r):
+        self.st.bind(r)
+
+    def final_evals(self):
+        return self.st.get_mle_flatten_final_evaluations()
+
+    def close(self):
+        self.st.close()
+
+
+def bench_sharded(args, rank, world, local_rank):
+    """bench.py's N>1 arm: T3-k strong scaling — each rank owns a 1/N slice of the same 2^k instance."""
+    import json
+    import torch
+    import torch.distributed as dist
+    from . import api as cb
+    from . import synth
+
+    k, deg = args.k, 3
+    g = world.bit_length() - 1
+    assert 1 << g == world, "number of GPUs must be a power of two"
+    k_local = k - g
+    n_local = 1 << k_local
+    dev = cb.Device(local_rank)
+    seed_a, seed_b, seed_w = 0xC0FFEE ^ 1, 0xC0FFEE ^ 2, 0xE9
+    w = synth.fill_ext(seed_w, k)
+    A = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k_local, synth.fill_ext(seed_a, n_local, start=rank * n_local))
+    B = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k_local, synth.fill_ext(seed_b, n_local, start=rank * n_local))
+    eq_lo = cb.build_eq_x_r_vec(dev, w[:2 * k_local])
+    s = eq_slice_scalar(w[2 * k_local:], rank)
+    EQ = cb.wit_infer_by_monomial_expr(dev, [eq_lo], [(list(s), [0])], k_local)      # eq slice = scalar * eq(w_low, .)
+    eq_lo.free()
+    terms = [([1, 0], [0, 1, 2])]
+    exch = TorchExchange(torch.device("cuda", local_rank))
+
+    def make_tail(arrays):
+        gl = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, g, a) for a in arrays]
+        return GpuLocalProver(dev, gl, terms, g, deg)
+
+    def step():
+        lp = GpuLocalProver(dev, [EQ, A, B], terms, k_local, deg)
+        out = sharded_prove(lp, k_local, g, deg, cb.StandInTranscript(b"bench"), exch, make_tail)
+        lp.close()
+        return out
+
+    for _ in range(args.warmup):
+        out = step()
+    l0 = dev.launch_count()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    launches = dev.launch_count() - l0
+    if rank == 0:
+        ms = float(ms.item())
+        n = 1 << k
+        ops = 99 * n
+        line = {
+            "metric": "sumcheck Gfield-ops/s", "value": ops / (ms * 1e-3) / 1e9, "unit": "Gfield-ops/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64 (Goldilocks, ext2)", "data": "synthetic",
+            "config": {"workload": f"T3-{k}: eq(w,x)*A(x)*B(x), 2^{k}-point hypercube, degree 3, GoldilocksExt2, sliced 1/{world} per GPU",
+                       "k": k, "degree": deg, "n_mles": 3, "parallelism": f"hypercube slices x{world}",
+                       "exchange": "per-round all_gather of 3 ext partials (torch.distributed/NCCL), modular sum on every rank",
+                       "l2": f"per-GPU inputs {3 * 16 * n_local >> 20} MiB"},
+            "points_per_s": n / (ms * 1e-3), "rounds_per_s": k / (ms * 1e-3),
+            "e2e": {"value": ops / (ms * 1e-3) / 1e9, "unit": "Gfield-ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16 * deg * k,
+                    "note": "N>1: inputs resident; see the N=1 line for the host-buffer path"},
+            "gpu_launches": int(launches),
+        }
+        print(json.dumps(line))
+    dev.close()
+    dist.destroy_process_group()

@@ -13,13 +13,13 @@ def _splitmix64(x):
         return x ^ (x >> np.uint64(31))
 
 
-def fill_ext(seed, n, out=None, chunk=1 << 22):
-    """2n u64 limbs of n extension elements."""
+def fill_ext(seed, n, out=None, chunk=1 << 22, start=0):
+    """2n u64 limbs of extension elements start .. start+n-1 of the stream `seed`."""
     out = np.empty(2 * n, np.uint64) if out is None else out
     for s in range(0, 2 * n, chunk):
         e = min(2 * n, s + chunk)
         with np.errstate(over="ignore"):
-            v = _splitmix64(np.arange(s, e, dtype=np.uint64) + np.uint64(seed))
+            v = _splitmix64(np.arange(s, e, dtype=np.uint64) + np.uint64((seed + 2 * start) & 0xFFFFFFFFFFFFFFFF))
         out[s:e] = np.where(v >= P, v - P, v)
     return out
 

@@ -341,3 +341,51 @@ def test_t3_k24_verifier_relations(dev):
     assert tuple(int(x) for x in orc.eq_eval(w, pt)) == fe[0]
     assert tuple(int(x) for x in a.evaluate(pt)) == fe[1]
     assert tuple(int(x) for x in orc.mle_evaluate(b_h, True, pt)) == fe[2]   # CPU check of one MLE (single fold chain)
+
+
+# ------------------------------------------------------------------------------ multi-GPU
+def _dist_gpu_worker(rank, world, k, port, q):
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import ceno_b200 as cb
+    from ceno_b200 import dist as cdist
+    g = world.bit_length() - 1
+    kl, nl = k - g, 1 << (k - g)
+    dev = cb.Device(rank)
+    w = orc.fill_ext(0xE9, k)
+    eq, a, b = orc.build_eq_x_r_vec(w), orc.fill_ext(1, 1 << k), orc.fill_ext(2, 1 << k)
+    sl = slice(2 * rank * nl, 2 * (rank + 1) * nl)
+    mles = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, kl, x[sl]) for x in (eq, a, b)]
+    terms = [([1, 0], [0, 1, 2])]
+    lp = cdist.GpuLocalProver(dev, mles, terms, kl, 3)
+    out = cdist.sharded_prove(lp, kl, g, 3, cb.StandInTranscript(b"dist"), cdist.TorchExchange(torch.device("cuda", rank)),
+                              lambda arrays: cdist.GpuLocalProver(dev, [cb.MultilinearExtension.from_evaluations_ext_vec(dev, g, x) for x in arrays], terms, g, 3))
+    want = orc.sumcheck_prove([(eq, True, k), (a, True, k), (b, True, k)], terms, k, 3, transcript=orc.Transcript(b"dist"))
+    q.put((rank, all(np.array_equal(x, y) for x, y in zip(out, want))))
+    dist.destroy_process_group()
+
+
+def test_sharded_sumcheck_multi_gpu_bit_exact():
+    import torch
+    import torch.multiprocessing as mp
+    world = 1
+    while world * 2 <= min(torch.cuda.device_count(), 8):
+        world *= 2
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dist_gpu_worker, args=(r, world, 14, 29641, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, True) for r in range(world)]
