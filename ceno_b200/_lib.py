@@ -39,6 +39,7 @@ SYMBOLS = [
     "cg_standin_append_message", "cg_standin_append_ext", "cg_standin_sample", "cg_standin_challenge_cb", "cg_tower_build",
     "cg_tower_output_evals", "cg_tower_proof_len", "cg_tower_point_len", "cg_tower_create_proof", "cg_tower_destroy",
     "cg_standin_vt", "cg_wit_infer_by_monomial_expr", "cg_profile_last",
+    "cg_comm_create", "cg_comm_connect", "cg_comm_destroy", "cg_sumcheck_attach_comm", "cg_sumcheck_prove_sharded",
 ]
 
 _lib = None
@@ -99,6 +100,11 @@ def load():
         "cg_standin_vt": (None, [vp, P(CgTranscriptVt)]),
         "cg_wit_infer_by_monomial_expr": (i32, [vp, P(CgMleDesc), u32, vp, vp, vp, u32, u32, vp, vp]),
         "cg_profile_last": (i32, [vp, vp, u32, P(u32)]),
+        "cg_comm_create": (i32, [vp, i32, i32, P(vp), vp]),
+        "cg_comm_connect": (i32, [vp, vp]),
+        "cg_comm_destroy": (i32, [vp]),
+        "cg_sumcheck_attach_comm": (i32, [vp, vp]),
+        "cg_sumcheck_prove_sharded": (i32, [vp, vp, P(CgMleDesc), u32, vp, vp, vp, u32, u32, u32, u32, CHALLENGE_CB, vp, vp, vp, vp, vp, vp]),
     }
     for name in SYMBOLS:
         fn = getattr(lib, name)  # AttributeError if the library does not export it

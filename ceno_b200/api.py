@@ -313,6 +313,50 @@ class IOPProverState:
                 chal[:2 * num_vars].reshape(num_vars, 2))
 
 
+class Comm:
+    """NVLink mailbox of one rank (cg_comm).  `exchange_handles` is any all-gather of 64-byte blobs
+    (e.g. torch.distributed.all_gather_object); the library itself never calls a collective."""
+
+    def __init__(self, dev, rank, nranks, exchange_handles, barrier=None):
+        self.dev, self.rank, self.nranks, self.barrier = dev, rank, nranks, barrier
+        self.h = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        dev.check(dev.lib.cg_comm_create(dev.ctx, rank, nranks, C.byref(self.h), handle))
+        blobs = exchange_handles(bytes(handle))
+        assert len(blobs) == nranks and all(len(b) == 64 for b in blobs)
+        allh = (C.c_uint8 * (64 * nranks)).from_buffer_copy(b"".join(blobs))
+        dev.check(dev.lib.cg_comm_connect(self.h, allh))
+        if barrier:
+            barrier()
+
+    def close(self):
+        if self.h:
+            if self.barrier:
+                self.barrier()
+            self.dev.lib.cg_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def prove_sharded(dev, comm, mles, terms, num_vars_global, degree, transcript, flags=0, device_challenger=False, stream=None):
+    """IOPProverState::prove over MLEs sharded across the ranks of `comm` (this rank passes its slices).
+    Returns the global (round_evals, final_evals, challenges), identical on every rank."""
+    lib = dev.lib
+    descs = (_lib.CgMleDesc * max(len(mles), 1))(*[m.desc() for m in mles])
+    coeff, off, idx = _terms(terms)
+    k = num_vars_global
+    rounds = np.zeros(2 * degree * max(k, 1), np.uint64)
+    fin = np.zeros(2 * max(len(mles), 1), np.uint64)
+    chal = np.zeros(2 * max(k, 1), np.uint64)
+    transcript.append_message(int(k).to_bytes(8, "little"))
+    transcript.append_message(int(degree).to_bytes(8, "little"))
+    st = C.c_void_p(stream) if stream else None
+    cb = C.cast(lib.cg_standin_challenge_cb, _lib.CHALLENGE_CB)
+    dev.check(lib.cg_sumcheck_prove_sharded(dev.ctx, comm.h, descs, len(mles), _vp(coeff), _vp(off), _vp(idx), len(terms), k, degree, flags,
+                                            cb, _vp(transcript.state), _vp(transcript.state) if device_challenger else None,
+                                            _vp(rounds), _vp(fin), _vp(chal), st))
+    return rounds[:2 * degree * k].reshape(k, degree, 2), fin[:2 * len(mles)].reshape(-1, 2), chal[:2 * k].reshape(k, 2)
+
+
 def wit_infer_by_monomial_expr(dev, mles, terms, num_vars):
     descs = (_lib.CgMleDesc * max(len(mles), 1))(*[m.desc() for m in mles])
     coeff, off, idx = _terms(terms)

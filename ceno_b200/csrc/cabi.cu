@@ -383,6 +383,95 @@ CG_EXPORT int cg_selector_compute(cg_ctx* c, int kind, const uint64_t* h_point, 
     }
 }
 
+
+// ------------------------------------------------------------------------------------- comm
+// Multi-GPU mailbox (the reference has no multi-GPU path — docs/src/optimizations.md:3-5
+// lists distributed sumcheck as TODO).  One cudaMalloc'd CommBuf per rank, exported through CUDA IPC;
+// the host framework (torch.distributed, MPI, ...) only moves the 64-byte handles once at start-up.
+struct cg_comm {
+    cg_ctx* ctx = nullptr;
+    int rank = 0, nranks = 1;
+    CommBuf* mine = nullptr;
+    CommBuf* peers[CG_MAX_RANKS] = {nullptr};
+    uint64_t seq = 1;        // next exchange sequence number (identical on every rank)
+    uint64_t gather_calls = 0;
+    int* d_error = nullptr;
+};
+CG_EXPORT int cg_comm_create(cg_ctx* c, int rank, int nranks, cg_comm** out, uint8_t handle_out[64]) {
+    if (!c || !out || !handle_out || nranks < 1 || nranks > CG_MAX_RANKS || rank < 0 || rank >= nranks || (nranks & (nranks - 1)))
+        return set_err(c, CG_ERR_INVALID, "cg_comm_create: nranks must be a power of two <= 8 and 0 <= rank < nranks");
+    CU(c, cudaSetDevice(c->device));
+    cg_comm* cm = new cg_comm();
+    cm->ctx = c;
+    cm->rank = rank;
+    cm->nranks = nranks;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    if (cudaMalloc(&p, sizeof(CommBuf)) != cudaSuccess || cudaMemset(p, 0, sizeof(CommBuf)) != cudaSuccess ||
+        cudaMalloc((void**)&cm->d_error, 256) != cudaSuccess || cudaMemset(cm->d_error, 0, 256) != cudaSuccess) {
+        delete cm;
+        return set_err(c, CG_ERR_CUDA, "cg_comm_create: cudaMalloc failed");
+    }
+    cm->mine = (CommBuf*)p;
+    cm->peers[rank] = cm->mine;
+    cudaIpcMemHandle_t h;
+    memset(&h, 0, sizeof(h));
+    if (nranks > 1 && cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(p);
+        delete cm;
+        return set_err(c, CG_ERR_CUDA, "cg_comm_create: cudaIpcGetMemHandle failed");
+    }
+    memcpy(handle_out, &h, 64);
+    CU(c, cudaDeviceSynchronize());
+    *out = cm;
+    return CG_OK;
+}
+CG_EXPORT int cg_comm_connect(cg_comm* cm, const uint8_t* all_handles) {
+    if (!cm || !all_handles) return CG_ERR_INVALID;
+    cg_ctx* c = cm->ctx;
+    CU(c, cudaSetDevice(c->device));
+    for (int p = 0; p < cm->nranks; p++) {
+        if (p == cm->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all_handles + 64 * (size_t)p, 64);
+        void* ptr = nullptr;
+        CU(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        cm->peers[p] = (CommBuf*)ptr;
+    }
+    return CG_OK;
+}
+CG_EXPORT int cg_comm_destroy(cg_comm* cm) {
+    if (!cm) return CG_ERR_INVALID;
+    cudaSetDevice(cm->ctx->device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < cm->nranks; p++)
+        if (p != cm->rank && cm->peers[p]) cudaIpcCloseMemHandle(cm->peers[p]);
+    cudaFree(cm->mine);
+    cudaFree(cm->d_error);
+    delete cm;
+    return CG_OK;
+}
+static void comm_dev(cg_comm* cm, CommDev& d, uint64_t n_exchanges) {
+    memset(&d, 0, sizeof(d));
+    if (!cm || cm->nranks <= 1) return;
+    d.rank = cm->rank;
+    d.nranks = cm->nranks;
+    d.seq = cm->seq;
+    cm->seq += n_exchanges;
+    for (int p = 0; p < cm->nranks; p++) d.peers[p] = cm->peers[p];
+    d.d_error = cm->d_error;
+    d.timeout_cycles = 8000000000ULL;
+}
+static int comm_check(cg_comm* cm, cudaStream_t st) {
+    if (!cm || cm->nranks <= 1) return CG_OK;
+    int e = 0;
+    if (cudaMemcpyAsync(&e, cm->d_error, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+        return set_err(cm->ctx, CG_ERR_CUDA, "comm error flag read failed");
+    if (e) return set_err(cm->ctx, CG_ERR_CUDA, "multi-GPU exchange timed out waiting for a peer rank");
+    return CG_OK;
+}
+
 // --------------------------------------------------------------------------------- sumcheck
 struct MleState {
     const void* orig = nullptr;
@@ -426,6 +515,7 @@ struct cg_sumcheck {
     ext_t* d_chal = nullptr;
     std::vector<void*> owned;
     int* d_error = nullptr;
+    cg_comm* comm = nullptr;       // multi-GPU: partial sums are combined in-kernel over NVLink
     std::vector<cudaEvent_t> ev;   // CG_SC_PROFILE: 2 events per round on the launching stream
 };
 
@@ -707,11 +797,22 @@ static int sc_enqueue_round(cg_sumcheck* sc, const RoundOut& ro) {
     return CG_OK;
 }
 
+static RoundOut make_ro(cg_sumcheck* sc) {
+    RoundOut ro = sc->out;
+    comm_dev(sc->comm, ro.comm, 1);   // one exchange per round-evaluation launch
+    return ro;
+}
+CG_EXPORT int cg_sumcheck_attach_comm(cg_sumcheck* sc, cg_comm* cm) {
+    if (!sc) return CG_ERR_INVALID;
+    if (sc->round != 0 || sc->evaluated) return set_err(sc->ctx, CG_ERR_STATE, "attach_comm: must be called before the first round");
+    sc->comm = cm;
+    return CG_OK;
+}
 CG_EXPORT int cg_sumcheck_round_eval(cg_sumcheck* sc, uint64_t* h_out) {
     if (!sc || !h_out) return CG_ERR_INVALID;
     cg_ctx* c = sc->ctx;
     CU(c, cudaSetDevice(c->device));
-    RoundOut ro = sc->out;
+    RoundOut ro = make_ro(sc);
     ro.d_out = sc->d_msgs;
     ro.d_tr_state = nullptr;
     ro.d_r_out = nullptr;
@@ -830,6 +931,7 @@ static int launch_tail(cg_sumcheck* sc, uint64_t* d_tr_state, ext_t* d_msgs, ext
     a.mail = d_tr_state ? nullptr : sc_mailbox(sc);
     a.d_error = sc->d_error;
     a.timeout_cycles = 8000000000ULL;   // ~4 s: a dead host must not hang the GPU
+    comm_dev(sc->comm, a.comm, a.num_rounds - a.first_round);
     const size_t smem = (size_t)slot * a.n0 * sizeof(ext_t);
     const bool simple = a.t.n_prod == 1 && a.t.n_logup == 0 && a.t.alpha_one;
     if (simple) {
@@ -918,7 +1020,7 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
         }
         {   // round_eval with the end-of-kernels mark placed before the D2H copy
             cg_ctx* c = sc->ctx;
-            RoundOut ro = sc->out;
+            RoundOut ro = make_ro(sc);
             ro.d_out = sc->d_msgs;
             ro.d_tr_state = nullptr;
             ro.d_r_out = nullptr;
@@ -959,10 +1061,6 @@ static int sc_run_device(cg_sumcheck* sc, uint64_t* h_state, uint64_t* h_rounds,
     CU(c, cudaMemcpyAsync(sc->d_tr_state, h_state, 8, cudaMemcpyHostToDevice, sc->stream));
     prof_begin(sc);
     for (uint32_t j = 0; j < sc->num_vars; j++) {
-        RoundOut ro = sc->out;
-        ro.d_out = sc->d_msgs + (size_t)j * sc->degree;
-        ro.d_tr_state = sc->d_tr_state;
-        ro.d_r_out = sc->d_chal + j;
         prof_mark(sc, j, 0);
         if (tail_eligible(sc)) {   // one persistent launch for every remaining round
             CHK(launch_tail(sc, sc->d_tr_state, sc->d_msgs, sc->d_chal));
@@ -971,6 +1069,10 @@ static int sc_run_device(cg_sumcheck* sc, uint64_t* h_state, uint64_t* h_rounds,
             sc_mark_done(sc);
             break;
         }
+        RoundOut ro = make_ro(sc);
+        ro.d_out = sc->d_msgs + (size_t)j * sc->degree;
+        ro.d_tr_state = sc->d_tr_state;
+        ro.d_r_out = sc->d_chal + j;
         CHK(sc_enqueue_round(sc, ro));
         prof_mark(sc, j, 1);
         CHK(sc_apply_pending_fold_only(sc));
@@ -996,6 +1098,63 @@ CG_EXPORT int cg_sumcheck_prove_standin_device(cg_ctx* c, const cg_mle_desc* mle
     cg_sumcheck* sc = nullptr;
     CHK(cg_sumcheck_create(c, mles, n_mles, coeff, off, idx, n_terms, num_vars, degree, flags, s, &sc));
     int rc = sc_run_device(sc, h_state, h_rounds, h_final, h_chal);
+    cg_sumcheck_destroy(sc);
+    return rc;
+}
+
+
+// Sharded prove: this rank holds the slice [rank 2^(k-g), (rank+1) 2^(k-g)) of every MLE
+// (descs carry num_vars = k - g).  Rounds 0..k-g-1 run locally with the in-kernel NVLink exchange of
+// the partial sums; the final local evaluations are all-gathered into every rank's mailbox and the
+// last g rounds run replicated on the N gathered elements.  Outputs are identical on every rank and
+// identical to the single-device proof.  h_standin_state != NULL selects the device challenger.
+CG_EXPORT int cg_sumcheck_prove_sharded(cg_ctx* c, cg_comm* cm, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t* coeff,
+                                        const uint32_t* off, const uint32_t* idx, uint32_t n_terms, uint32_t num_vars_global,
+                                        uint32_t degree, uint32_t flags, cg_challenge_cb cb, void* user, uint64_t* h_standin_state,
+                                        uint64_t* h_rounds, uint64_t* h_final, uint64_t* h_chal, cg_stream s) {
+    if (!c || !cm || (!cb && !h_standin_state) || !h_rounds) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_prove_sharded: null argument");
+    int g = 0;
+    while ((1 << g) < cm->nranks) g++;
+    if (num_vars_global < (uint32_t)g) return set_err(c, CG_ERR_INVALID, "fewer variables than log2(ranks)");
+    if (n_mles > CG_COMM_GATHER_MLES) return set_err(c, CG_ERR_UNSUPPORTED, "sharded prove supports at most 64 MLEs");
+    const uint32_t k_local = num_vars_global - g;
+    cudaStream_t st = S(c, s);
+    cg_sumcheck* sc = nullptr;
+    CHK(cg_sumcheck_create(c, mles, n_mles, coeff, off, idx, n_terms, k_local, degree, flags, s, &sc));
+    sc->comm = cm;
+    std::vector<uint64_t> fin_local(2 * (size_t)(n_mles ? n_mles : 1));
+    int rc = h_standin_state ? sc_run_device(sc, h_standin_state, h_rounds, fin_local.data(), h_chal)
+                             : sc_run_host(sc, cb, user, h_rounds, fin_local.data(), h_chal);
+    if (rc == CG_OK) rc = comm_check(cm, st);
+    if (rc != CG_OK || g == 0) {
+        if (rc == CG_OK && h_final) memcpy(h_final, fin_local.data(), sizeof(uint64_t) * 2 * n_mles);
+        cg_sumcheck_destroy(sc);
+        return rc;
+    }
+    // all-gather the m final local evaluations (they sit in sc->d_final) into every mailbox
+    const int par = (int)(cm->gather_calls++ & 1);
+    CommDev cd;
+    comm_dev(cm, cd, 1);
+    comm_allgather_kernel<<<1, 64, 0, st>>>(sc->d_final, (int)n_mles, cd, par);
+    LAUNCHED(c);
+    if (cudaGetLastError() != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "comm_allgather_kernel launch failed");
+    if (k_local == 0 && rc == CG_OK) {
+        // zero local rounds: d_final was never written by a fold; the single local values are the inputs
+        rc = set_err(c, CG_ERR_UNSUPPORTED, "sharded prove needs at least one local variable per rank");
+    }
+    cg_sumcheck* sc2 = nullptr;
+    if (rc == CG_OK) {
+        std::vector<cg_mle_desc> gd(n_mles);
+        for (uint32_t i = 0; i < n_mles; i++) gd[i] = cg_mle_desc{&cm->mine->gather.v[par][i][0], (uint64_t)cm->nranks, (uint32_t)g, 1u};
+        rc = cg_sumcheck_create(c, gd.data(), n_mles, coeff, off, idx, n_terms, (uint32_t)g, degree, flags, s, &sc2);
+    }
+    if (rc == CG_OK) {
+        uint64_t* r2 = h_rounds + (size_t)k_local * degree * 2;
+        uint64_t* c2 = h_chal ? h_chal + (size_t)k_local * 2 : nullptr;
+        rc = h_standin_state ? sc_run_device(sc2, h_standin_state, r2, h_final, c2) : sc_run_host(sc2, cb, user, r2, h_final, c2);
+    }
+    if (rc == CG_OK) rc = comm_check(cm, st);
+    if (sc2) cg_sumcheck_destroy(sc2);
     cg_sumcheck_destroy(sc);
     return rc;
 }

@@ -24,6 +24,88 @@
 #define CG_TOWER_MAX_LOGUP 4
 
 // ---------------------------------------------------------------------------------------------
+// Multi-GPU exchange over NVLink peer memory: every rank owns a mailbox buffer that its
+// peers map through CUDA IPC.  The last block of a round kernel stores its partial round sums into
+// slot [ring][my_rank] of EVERY peer's mailbox (plain P2P stores + system fence + sequence flag),
+// waits for the N flags in its own mailbox and adds the N partials mod p.  All ranks obtain the same
+// message, so the transcript runs replicated and nothing is broadcast.  A fast rank can be at most one
+// exchange ahead of a slow one (it needs the slow rank's next partial to finish), so a ring of 4 is safe.
+#define CG_MAX_RANKS 8
+#define CG_COMM_RING 4
+#define CG_COMM_GATHER_MLES 64
+struct CommSlot {
+    uint64_t v[2 * CG_MAX_DEGREE];
+    uint64_t seq;
+    uint64_t pad[7];
+};
+struct CommGather {                 // final local evaluations, all-gathered for the replicated tail
+    ext_t v[2][CG_COMM_GATHER_MLES][CG_MAX_RANKS];
+    uint64_t seq[2][CG_MAX_RANKS];
+};
+struct CommBuf {
+    CommSlot slots[CG_COMM_RING][CG_MAX_RANKS];
+    CommGather gather;
+};
+struct CommDev {
+    int rank, nranks;               // nranks <= 1: no exchange
+    uint64_t seq;                   // sequence number of this launch's (first) exchange
+    CommBuf* peers[CG_MAX_RANKS];   // peers[rank] is the local buffer
+    int* d_error;
+    unsigned long long timeout_cycles;
+};
+// executed by a whole converged warp; the local partial is in lane 0, the combined sum returns in lane 0
+template <int D>
+GL_DEV void comm_exchange(ext_t (&res)[D], const CommDev& cm, uint64_t seq) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int x = 0; x < D; x++) {
+        res[x].c0 = __shfl_sync(0xffffffffu, res[x].c0, 0);
+        res[x].c1 = __shfl_sync(0xffffffffu, res[x].c1, 0);
+    }
+    const int ring = (int)(seq % CG_COMM_RING);
+    ext_t got[D];
+#pragma unroll
+    for (int x = 0; x < D; x++) got[x] = ext_zero();
+    if (lane < cm.nranks) {
+        CommSlot* dst = &cm.peers[lane]->slots[ring][cm.rank];
+#pragma unroll
+        for (int x = 0; x < D; x++) { dst->v[2 * x] = res[x].c0; dst->v[2 * x + 1] = res[x].c1; }
+        __threadfence_system();
+        *(volatile uint64_t*)&dst->seq = seq;
+        volatile CommSlot* src = &cm.peers[cm.rank]->slots[ring][lane];
+        const long long t0 = clock64();
+        bool ok = true;
+        while (src->seq != seq) {
+            if ((unsigned long long)(clock64() - t0) > cm.timeout_cycles) { *cm.d_error = 2; ok = false; break; }
+        }
+        __threadfence_system();
+        if (ok) {
+#pragma unroll
+            for (int x = 0; x < D; x++) got[x] = ext_make(gl_canon(src->v[2 * x]), gl_canon(src->v[2 * x + 1]));
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < D; x++) res[x] = warp_reduce_ext(got[x]);
+}
+// all-gather of the m final local evaluations into every rank's gather area [par][mle][rank]
+__global__ void comm_allgather_kernel(const ext_t* __restrict__ d_final, int m, const __grid_constant__ CommDev cm, int par) {
+    const int tid = threadIdx.x;
+    for (int p = 0; p < cm.nranks; p++)
+        for (int i = tid; i < m; i += blockDim.x) cm.peers[p]->gather.v[par][i][cm.rank] = d_final[i];
+    __threadfence_system();
+    __syncthreads();
+    if (tid < cm.nranks) {
+        *(volatile uint64_t*)&cm.peers[tid]->gather.seq[par][cm.rank] = cm.seq;
+        volatile uint64_t* f = &cm.peers[cm.rank]->gather.seq[par][tid];
+        const long long t0 = clock64();
+        while (*f != cm.seq) {
+            if ((unsigned long long)(clock64() - t0) > cm.timeout_cycles) { *cm.d_error = 2; break; }
+        }
+        __threadfence_system();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // round output / finish
 struct RoundOut {
     ext_t* partials;          // [CG_MAX_BLOCKS * CG_MAX_DEGREE]
@@ -32,6 +114,7 @@ struct RoundOut {
     // device-resident stand-in challenger (optional): absorbs the message, squeezes r
     uint64_t* d_tr_state;     // nullptr -> host transcript
     ext_t* d_r_out;           // where to put the challenge for the next launch
+    CommDev comm;             // multi-GPU: combine the partial sums of all ranks (nranks <= 1: off)
 };
 
 template <int D>
@@ -80,6 +163,7 @@ GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out) {
             ext_t v = lane < n_warps ? s_part[lane][x] : ext_zero();
             res[x] = warp_reduce_ext(v);
         }
+        if (out.comm.nranks > 1) comm_exchange<D>(res, out.comm, out.comm.seq);
         if (lane == 0) {
 #pragma unroll
             for (int x = 0; x < D; x++) out.d_out[x] = res[x];
@@ -274,6 +358,7 @@ struct TailArgs {
     TailMailbox* mail;
     int* d_error;               // set to 1 on mailbox timeout/abort
     unsigned long long timeout_cycles;
+    CommDev comm;               // multi-GPU: exchange j uses sequence comm.seq + (j - first_round)
 };
 struct SmemLoader {
     const ext_t* sm;
@@ -345,6 +430,7 @@ __global__ void __launch_bounds__(CG_TAIL_THREADS, 1) tower_tail_kernel(const __
             ext_t res[3];
 #pragma unroll
             for (int x = 0; x < 3; x++) res[x] = warp_reduce_ext(lane < (CG_TAIL_THREADS / 32) ? s_red[lane][x] : ext_zero());
+            if (a.comm.nranks > 1) comm_exchange<3>(res, a.comm, a.comm.seq + (j - a.first_round));
             if (lane == 0) {
                 ext_t r;
 #pragma unroll

@@ -141,35 +141,42 @@ def bench_sharded(args, rank, world, local_rank):
     EQ = cb.wit_infer_by_monomial_expr(dev, [eq_lo], [(list(s), [0])], k_local)      # eq slice = scalar * eq(w_low, .)
     eq_lo.free()
     terms = [([1, 0], [0, 1, 2])]
-    exch = TorchExchange(torch.device("cuda", local_rank))
 
-    def make_tail(arrays):
-        gl = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, g, a) for a in arrays]
-        return GpuLocalProver(dev, gl, terms, g, deg)
+    def xchg(blob):
+        outs = [None] * world
+        dist.all_gather_object(outs, blob)
+        return outs
+    comm = cb.Comm(dev, rank, world, xchg, barrier=dist.barrier)
+    stream = torch.cuda.Stream()
+    sh = stream.cuda_stream
 
-    def step():
-        lp = GpuLocalProver(dev, [EQ, A, B], terms, k_local, deg)
-        out = sharded_prove(lp, k_local, g, deg, cb.StandInTranscript(b"bench"), exch, make_tail)
-        lp.close()
-        return out
+    def step(device_challenger=False):
+        return cb.prove_sharded(dev, comm, [EQ, A, B], terms, k, deg, cb.StandInTranscript(b"bench"),
+                                device_challenger=device_challenger, stream=sh)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            o = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)     # max over ranks
+        dist.barrier()
+        return float(t.item()), o
 
     for _ in range(args.warmup):
         out = step()
+        step(True)
     l0 = dev.launch_count()
-    torch.cuda.synchronize()
-    dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    dist.barrier()
+    ms, out = timed(step, args.steps)
     launches = dev.launch_count() - l0
+    ms_dev, out_dev = timed(lambda: step(True), args.steps)
+    assert all(np.array_equal(x, y) for x, y in zip(out, out_dev))
     if rank == 0:
-        ms = float(ms.item())
         n = 1 << k
         ops = 99 * n
         line = {
@@ -178,13 +185,15 @@ def bench_sharded(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "u64 (Goldilocks, ext2)", "data": "synthetic",
             "config": {"workload": f"T3-{k}: eq(w,x)*A(x)*B(x), 2^{k}-point hypercube, degree 3, GoldilocksExt2, sliced 1/{world} per GPU",
                        "k": k, "degree": deg, "n_mles": 3, "parallelism": f"hypercube slices x{world}",
-                       "exchange": "per-round all_gather of 3 ext partials (torch.distributed/NCCL), modular sum on every rank",
+                       "exchange": "in-kernel: last block stores its 3 ext partials into every peer's NVLink-mapped mailbox, waits for the N flags, sums mod p; replicated host transcript; all-gather of the final local elements + replicated tail",
                        "l2": f"per-GPU inputs {3 * 16 * n_local >> 20} MiB"},
             "points_per_s": n / (ms * 1e-3), "rounds_per_s": k / (ms * 1e-3),
+            "device_challenger": {"ms_per_step": ms_dev, "value": ops / (ms_dev * 1e-3) / 1e9, "unit": "Gfield-ops/s"},
             "e2e": {"value": ops / (ms * 1e-3) / 1e9, "unit": "Gfield-ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16 * deg * k,
                     "note": "N>1: inputs resident; see the N=1 line for the host-buffer path"},
             "gpu_launches": int(launches),
         }
         print(json.dumps(line))
+    comm.close()
     dev.close()
     dist.destroy_process_group()

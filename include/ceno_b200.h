@@ -176,6 +176,29 @@ int cg_sumcheck_prove_standin_device(cg_ctx* ctx, const cg_mle_desc* mles, uint3
                                      uint64_t* h_round_evals, uint64_t* h_final_evals,
                                      uint64_t* h_challenges, cg_stream s);
 
+/* ---- multi-GPU (one process per GPU).  The reference has no multi-GPU path ("Distributed Sumcheck —
+ * TODO", docs/src/optimizations.md:3-5; single device id gkr_iop/src/gpu/mod.rs:55-56); this is the
+ * hypercube slicing of SURVEY §8e.  Each rank creates a mailbox and publishes its 64-byte CUDA-IPC
+ * handle; the host framework all-gathers the handles once (torch.distributed, MPI, a file ...) and
+ * every rank connects.  After that the ranks exchange per-round partial sums directly over NVLink
+ * peer memory from inside the round kernels — no host or NCCL call per round.  The caller must
+ * barrier between connect and first use, and before destroy. */
+typedef struct cg_comm cg_comm;
+int cg_comm_create(cg_ctx* ctx, int rank, int nranks, cg_comm** out, uint8_t handle_out[64]);
+int cg_comm_connect(cg_comm* comm, const uint8_t* all_handles /* nranks * 64 bytes, rank order */);
+int cg_comm_destroy(cg_comm* comm);
+/* step API: combine this sumcheck's round messages across the ranks of `comm` (call before round 0) */
+int cg_sumcheck_attach_comm(cg_sumcheck* sc, cg_comm* comm);
+/* Whole sharded proof: `mles` are this rank's slices (num_vars = num_vars_global - log2 nranks),
+ * outputs are the GLOBAL proof (num_vars_global rounds), identical on every rank.  Exactly one of
+ * (cb, h_standin_state) selects the host transcript or the device-resident challenger. */
+int cg_sumcheck_prove_sharded(cg_ctx* ctx, cg_comm* comm, const cg_mle_desc* mles, uint32_t n_mles,
+                              const uint64_t* term_coeff_ext, const uint32_t* term_offsets,
+                              const uint32_t* term_mle_idx, uint32_t n_terms, uint32_t num_vars_global,
+                              uint32_t degree, uint32_t flags, cg_challenge_cb cb, void* user,
+                              uint64_t* h_standin_state, uint64_t* h_round_evals, uint64_t* h_final_evals,
+                              uint64_t* h_challenges, cg_stream s);
+
 /* Per-round device time (ms) of the last cg_sumcheck_prove* call made with CG_SC_PROFILE on this
  * context: n receives the round count, up to `cap` values are written.  (The reference wraps the
  * same phases in tracing spans / NVTX ranges, ceno_zkvm/src/scheme/prover.rs:92-180.) */

@@ -368,7 +368,19 @@ def _dist_gpu_worker(rank, world, k, port, q):
     out = cdist.sharded_prove(lp, kl, g, 3, cb.StandInTranscript(b"dist"), cdist.TorchExchange(torch.device("cuda", rank)),
                               lambda arrays: cdist.GpuLocalProver(dev, [cb.MultilinearExtension.from_evaluations_ext_vec(dev, g, x) for x in arrays], terms, g, 3))
     want = orc.sumcheck_prove([(eq, True, k), (a, True, k), (b, True, k)], terms, k, 3, transcript=orc.Transcript(b"dist"))
-    q.put((rank, all(np.array_equal(x, y) for x, y in zip(out, want))))
+    ok = all(np.array_equal(x, y) for x, y in zip(out, want))
+    # in-kernel NVLink mailbox exchange (cg_comm): host transcript, device challenger, and a generic-kernel run
+
+    def xchg(blob):
+        outs = [None] * world
+        dist.all_gather_object(outs, blob)
+        return outs
+    comm = cb.Comm(dev, rank, world, xchg, barrier=dist.barrier)
+    for dc, flags in ((False, 0), (True, 0), (False, cb.IOPProverState.FORCE_GENERIC), (True, cb.IOPProverState.NO_TAIL)):
+        got = cb.prove_sharded(dev, comm, mles, terms, k, 3, cb.StandInTranscript(b"dist"), flags=flags, device_challenger=dc)
+        ok = ok and all(np.array_equal(x, y) for x, y in zip(got, want))
+    comm.close()
+    q.put((rank, ok))
     dist.destroy_process_group()
 
 
