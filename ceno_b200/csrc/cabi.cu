@@ -515,6 +515,9 @@ struct cg_sumcheck {
     ext_t* d_chal = nullptr;
     std::vector<void*> owned;
     int* d_error = nullptr;
+    uint32_t extra_rounds = 0;     // sharded prove: replicated rounds the tail kernel runs after the all-gather
+    bool extra_done = false;
+    bool profile_append = false;   // sharded prove: the replicated tail appends to the local rounds' profile
     cg_comm* comm = nullptr;       // multi-GPU: partial sums are combined in-kernel over NVLink
     std::vector<cudaEvent_t> ev;   // CG_SC_PROFILE: 2 events per round on the launching stream
 };
@@ -586,8 +589,8 @@ static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles,
     if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(ext_t) * CG_MAX_BLOCKS * CG_MAX_DEGREE, &p); sc->out.partials = (ext_t*)p; }
     if (rc == CG_OK) { rc = sc_alloc(sc, 256, &p); sc->out.ticket = (unsigned*)p; }
     if (rc == CG_OK && cudaMemsetAsync(sc->out.ticket, 0, 256, st) != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "memset failed");
-    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(ext_t) * (size_t)(num_vars + 1) * degree, &p); sc->d_msgs = (ext_t*)p; }
-    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(ext_t) * (num_vars + 1), &p); sc->d_chal = (ext_t*)p; }
+    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(ext_t) * (size_t)(num_vars + 4) * degree, &p); sc->d_msgs = (ext_t*)p; }
+    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(ext_t) * (num_vars + 4), &p); sc->d_chal = (ext_t*)p; }
     if (rc == CG_OK) { rc = sc_alloc(sc, 256, &p); sc->d_error = (int*)p; }
     if (rc == CG_OK && cudaMemsetAsync(sc->d_error, 0, 256, st) != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "memset failed");
     if (rc == CG_OK) {
@@ -891,6 +894,7 @@ static bool tail_eligible(const cg_sumcheck* sc) {
     const uint64_t n0 = sc->pending ? cur / 2 : cur;
     const size_t n_slots = 1 + sc->tl.prod.size() + sc->tl.lk.size();
     if (n0 < 2 || n0 > CG_TAIL_START_N || n_slots > 1 + 2 * CG_TOWER_MAX_PROD + 4 * CG_TOWER_MAX_LOGUP) return false;
+    if (sc->extra_rounds && (n0 < (uint64_t)(1u << sc->extra_rounds) || n_slots > CG_COMM_GATHER_MLES)) return false;
     return n_slots * n0 * sizeof(ext_t) + 4096 <= sc->ctx->max_smem_optin;
 }
 // launches the tail for rounds sc->round .. num_vars-1; d_tr_state == nullptr -> host mailbox
@@ -923,7 +927,8 @@ static int launch_tail(cg_sumcheck* sc, uint64_t* d_tr_state, ext_t* d_msgs, ext
     const uint64_t cur = 1ULL << (sc->num_vars - f);
     a.n0 = (uint32_t)(sc->pending ? cur / 2 : cur);
     a.first_round = sc->round;
-    a.num_rounds = sc->num_vars;
+    a.num_rounds = sc->num_vars + sc->extra_rounds;
+    a.local_end = sc->num_vars;
     a.d_msgs = d_msgs;
     a.d_chal = d_chal;
     a.d_final = sc->d_final;
@@ -931,7 +936,12 @@ static int launch_tail(cg_sumcheck* sc, uint64_t* d_tr_state, ext_t* d_msgs, ext
     a.mail = d_tr_state ? nullptr : sc_mailbox(sc);
     a.d_error = sc->d_error;
     a.timeout_cycles = 8000000000ULL;   // ~4 s: a dead host must not hang the GPU
-    comm_dev(sc->comm, a.comm, a.num_rounds - a.first_round);
+    comm_dev(sc->comm, a.comm, a.local_end - a.first_round);
+    if (sc->comm && sc->extra_rounds) {
+        a.gather_par = (int)(sc->comm->gather_calls++ & 1);
+        a.gather_seq = sc->comm->seq++;
+        sc->extra_done = true;
+    }
     const size_t smem = (size_t)slot * a.n0 * sizeof(ext_t);
     const bool simple = a.t.n_prod == 1 && a.t.n_logup == 0 && a.t.alpha_one;
     if (simple) {
@@ -964,8 +974,12 @@ static void prof_end(cg_sumcheck* sc) {
     if (!(sc->flags & CG_SC_PROFILE)) return;
     cudaStreamSynchronize(sc->stream);
     std::lock_guard<std::mutex> g(sc->ctx->mu);
-    sc->ctx->profile_ms.assign(sc->num_vars, 0.f);
-    for (uint32_t j = 0; j < sc->num_vars; j++) cudaEventElapsedTime(&sc->ctx->profile_ms[j], sc->ev[2 * j], sc->ev[2 * j + 1]);
+    if (!sc->profile_append) sc->ctx->profile_ms.clear();
+    for (uint32_t j = 0; j < sc->num_vars; j++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, sc->ev[2 * j], sc->ev[2 * j + 1]);
+        sc->ctx->profile_ms.push_back(ms);
+    }
     for (auto& e : sc->ev) cudaEventDestroy(e);
     sc->ev.clear();
 }
@@ -990,7 +1004,7 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
             __sync_synchronize();
             CHK(launch_tail(sc, nullptr, sc->d_msgs, sc->d_chal));
             int rc = CG_OK;
-            for (uint32_t jj = j; jj < sc->num_vars && rc == CG_OK; jj++) {
+            for (uint32_t jj = j; jj < sc->num_vars + sc->extra_rounds && rc == CG_OK; jj++) {
                 uint64_t spins = 0;
                 while (mb->seq_msg != (uint64_t)jj + 1) {
                     if ((++spins & 0xFFFFF) == 0 && cudaStreamQuery(sc->stream) != cudaErrorNotReady) {
@@ -1081,8 +1095,9 @@ static int sc_run_device(cg_sumcheck* sc, uint64_t* h_state, uint64_t* h_rounds,
         CHK(sc_bind_common(sc));
     }
     if (sc->num_vars) {
-        CU(c, cudaMemcpyAsync(h_rounds, sc->d_msgs, sizeof(ext_t) * sc->num_vars * sc->degree, cudaMemcpyDeviceToHost, sc->stream));
-        if (h_chal) CU(c, cudaMemcpyAsync(h_chal, sc->d_chal, sizeof(ext_t) * sc->num_vars, cudaMemcpyDeviceToHost, sc->stream));
+        const uint32_t nr = sc->num_vars + (sc->extra_done ? sc->extra_rounds : 0);
+        CU(c, cudaMemcpyAsync(h_rounds, sc->d_msgs, sizeof(ext_t) * nr * sc->degree, cudaMemcpyDeviceToHost, sc->stream));
+        if (h_chal) CU(c, cudaMemcpyAsync(h_chal, sc->d_chal, sizeof(ext_t) * nr, cudaMemcpyDeviceToHost, sc->stream));
     }
     CU(c, cudaMemcpyAsync(h_state, sc->d_tr_state, 8, cudaMemcpyDeviceToHost, sc->stream));
     CU(c, cudaStreamSynchronize(sc->stream));
@@ -1122,11 +1137,12 @@ CG_EXPORT int cg_sumcheck_prove_sharded(cg_ctx* c, cg_comm* cm, const cg_mle_des
     cg_sumcheck* sc = nullptr;
     CHK(cg_sumcheck_create(c, mles, n_mles, coeff, off, idx, n_terms, k_local, degree, flags, s, &sc));
     sc->comm = cm;
+    sc->extra_rounds = (uint32_t)g;   // the persistent tail kernel continues through the replicated rounds when it can
     std::vector<uint64_t> fin_local(2 * (size_t)(n_mles ? n_mles : 1));
     int rc = h_standin_state ? sc_run_device(sc, h_standin_state, h_rounds, fin_local.data(), h_chal)
                              : sc_run_host(sc, cb, user, h_rounds, fin_local.data(), h_chal);
     if (rc == CG_OK) rc = comm_check(cm, st);
-    if (rc != CG_OK || g == 0) {
+    if (rc != CG_OK || g == 0 || sc->extra_done) {
         if (rc == CG_OK && h_final) memcpy(h_final, fin_local.data(), sizeof(uint64_t) * 2 * n_mles);
         cg_sumcheck_destroy(sc);
         return rc;
@@ -1147,6 +1163,7 @@ CG_EXPORT int cg_sumcheck_prove_sharded(cg_ctx* c, cg_comm* cm, const cg_mle_des
         std::vector<cg_mle_desc> gd(n_mles);
         for (uint32_t i = 0; i < n_mles; i++) gd[i] = cg_mle_desc{&cm->mine->gather.v[par][i][0], (uint64_t)cm->nranks, (uint32_t)g, 1u};
         rc = cg_sumcheck_create(c, gd.data(), n_mles, coeff, off, idx, n_terms, (uint32_t)g, degree, flags, s, &sc2);
+        if (rc == CG_OK) sc2->profile_append = true;
     }
     if (rc == CG_OK) {
         uint64_t* r2 = h_rounds + (size_t)k_local * degree * 2;

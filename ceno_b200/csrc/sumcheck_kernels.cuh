@@ -53,6 +53,13 @@ struct CommDev {
     int* d_error;
     unsigned long long timeout_cycles;
 };
+// Slot validation without a writer-side fence: the flag word is seq mixed with a checksum of the
+// payload, so a reader that sees the flag before (part of) the payload simply keeps polling.
+GL_DEV uint64_t comm_checksum(uint64_t seq, const uint64_t* v, int n) {
+    uint64_t h = seq * 0x9E3779B97F4A7C15ULL + 0x632BE59BD9B4E019ULL;
+    for (int i = 0; i < n; i++) h = (h ^ v[i]) * 0xD6E8FEB86659FD93ULL + (uint64_t)i;
+    return h ^ (h >> 29);
+}
 // executed by a whole converged warp; the local partial is in lane 0, the combined sum returns in lane 0
 template <int D>
 GL_DEV void comm_exchange(ext_t (&res)[D], const CommDev& cm, uint64_t seq) {
@@ -67,21 +74,25 @@ GL_DEV void comm_exchange(ext_t (&res)[D], const CommDev& cm, uint64_t seq) {
 #pragma unroll
     for (int x = 0; x < D; x++) got[x] = ext_zero();
     if (lane < cm.nranks) {
-        CommSlot* dst = &cm.peers[lane]->slots[ring][cm.rank];
+        uint64_t v[2 * D];
 #pragma unroll
-        for (int x = 0; x < D; x++) { dst->v[2 * x] = res[x].c0; dst->v[2 * x + 1] = res[x].c1; }
-        __threadfence_system();
-        *(volatile uint64_t*)&dst->seq = seq;
+        for (int x = 0; x < D; x++) { v[2 * x] = res[x].c0; v[2 * x + 1] = res[x].c1; }
+        volatile CommSlot* dst = &cm.peers[lane]->slots[ring][cm.rank];
+#pragma unroll
+        for (int i = 0; i < 2 * D; i++) dst->v[i] = v[i];
+        dst->seq = comm_checksum(seq, v, 2 * D);           // no fence: the reader validates
         volatile CommSlot* src = &cm.peers[cm.rank]->slots[ring][lane];
         const long long t0 = clock64();
-        bool ok = true;
-        while (src->seq != seq) {
-            if ((unsigned long long)(clock64() - t0) > cm.timeout_cycles) { *cm.d_error = 2; ok = false; break; }
-        }
-        __threadfence_system();
-        if (ok) {
+        while (true) {
+            const uint64_t flag = src->seq;
 #pragma unroll
-            for (int x = 0; x < D; x++) got[x] = ext_make(gl_canon(src->v[2 * x]), gl_canon(src->v[2 * x + 1]));
+            for (int i = 0; i < 2 * D; i++) v[i] = src->v[i];
+            if (flag == comm_checksum(seq, v, 2 * D)) {
+#pragma unroll
+                for (int x = 0; x < D; x++) got[x] = ext_make(gl_canon(v[2 * x]), gl_canon(v[2 * x + 1]));
+                break;
+            }
+            if ((unsigned long long)(clock64() - t0) > cm.timeout_cycles) { *cm.d_error = 2; break; }
         }
     }
 #pragma unroll
@@ -359,6 +370,9 @@ struct TailArgs {
     int* d_error;               // set to 1 on mailbox timeout/abort
     unsigned long long timeout_cycles;
     CommDev comm;               // multi-GPU: exchange j uses sequence comm.seq + (j - first_round)
+    uint32_t local_end;         // rounds < local_end are sharded (exchange); after round local_end-1 the
+    int gather_par;             // final local elements are all-gathered and the rest runs replicated
+    uint64_t gather_seq;
 };
 struct SmemLoader {
     const ext_t* sm;
@@ -430,7 +444,7 @@ __global__ void __launch_bounds__(CG_TAIL_THREADS, 1) tower_tail_kernel(const __
             ext_t res[3];
 #pragma unroll
             for (int x = 0; x < 3; x++) res[x] = warp_reduce_ext(lane < (CG_TAIL_THREADS / 32) ? s_red[lane][x] : ext_zero());
-            if (a.comm.nranks > 1) comm_exchange<3>(res, a.comm, a.comm.seq + (j - a.first_round));
+            if (a.comm.nranks > 1 && j < a.local_end) comm_exchange<3>(res, a.comm, a.comm.seq + (j - a.first_round));
             if (lane == 0) {
                 ext_t r;
 #pragma unroll
@@ -492,6 +506,34 @@ __global__ void __launch_bounds__(CG_TAIL_THREADS, 1) tower_tail_kernel(const __
         }
         __syncthreads();
         n = pairs;
+        if (a.comm.nranks > 1 && j + 1 == a.local_end && a.local_end < a.num_rounds) {
+            // every rank now holds one element per MLE: all-gather them through the mailboxes and run the
+            // last log2(N) rounds replicated on the N gathered elements (rank = top index bits)
+            const CommDev& cm = a.comm;
+            for (int slot = tid; slot < n_slots; slot += blockDim.x) {
+                const ext_t v = sm[(size_t)slot * a.n0];
+                for (int p = 0; p < cm.nranks; p++) cm.peers[p]->gather.v[a.gather_par][slot][cm.rank] = v;
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid < cm.nranks) {
+                *(volatile uint64_t*)&cm.peers[tid]->gather.seq[a.gather_par][cm.rank] = a.gather_seq;
+                volatile uint64_t* f = &cm.peers[cm.rank]->gather.seq[a.gather_par][tid];
+                const long long t0 = clock64();
+                while (*f != a.gather_seq) {
+                    if ((unsigned long long)(clock64() - t0) > cm.timeout_cycles) { *cm.d_error = 2; break; }
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+            for (int i = tid; i < n_slots * cm.nranks; i += blockDim.x) {
+                const int slot = i / cm.nranks, q = i % cm.nranks;
+                const volatile uint64_t* src = (const volatile uint64_t*)&cm.peers[cm.rank]->gather.v[a.gather_par][slot][q];
+                sm[(size_t)slot * a.n0 + q] = ext_make(gl_canon(src[0]), gl_canon(src[1]));
+            }
+            __syncthreads();
+            n = (uint32_t)cm.nranks;
+        }
     }
     for (int slot = tid; slot < n_slots; slot += blockDim.x) a.d_final[a.final_idx[slot]] = sm[(size_t)slot * a.n0];
 }
