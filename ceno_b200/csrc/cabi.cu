@@ -396,6 +396,7 @@ struct cg_comm {
     uint64_t seq = 1;        // next exchange sequence number (identical on every rank)
     uint64_t gather_calls = 0;
     int* d_error = nullptr;
+    unsigned long long* d_dbg = nullptr;
 };
 CG_EXPORT int cg_comm_create(cg_ctx* c, int rank, int nranks, cg_comm** out, uint8_t handle_out[64]) {
     if (!c || !out || !handle_out || nranks < 1 || nranks > CG_MAX_RANKS || rank < 0 || rank >= nranks || (nranks & (nranks - 1)))
@@ -414,6 +415,7 @@ CG_EXPORT int cg_comm_create(cg_ctx* c, int rank, int nranks, cg_comm** out, uin
     }
     cm->mine = (CommBuf*)p;
     cm->peers[rank] = cm->mine;
+    if (getenv("CG_COMM_DEBUG")) { cudaMalloc((void**)&cm->d_dbg, 1024 * 4 * 8); cudaMemset(cm->d_dbg, 0, 1024 * 4 * 8); }
     cudaIpcMemHandle_t h;
     memset(&h, 0, sizeof(h));
     if (nranks > 1 && cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
@@ -445,6 +447,15 @@ CG_EXPORT int cg_comm_destroy(cg_comm* cm) {
     if (!cm) return CG_ERR_INVALID;
     cudaSetDevice(cm->ctx->device);
     cudaDeviceSynchronize();
+    if (cm->d_dbg) {   // CG_COMM_DEBUG: dump the last exchanges' wait times
+        std::vector<unsigned long long> h(1024 * 4);
+        cudaMemcpy(h.data(), cm->d_dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+        const uint64_t last = cm->seq - 1;
+        for (uint64_t q = last > 40 ? last - 40 : 1; q <= last; q++)
+            fprintf(stderr, "[comm rank %d] seq %llu wait_self %llu ns wait_peer %llu ns polls %llu start %llu\n", cm->rank, (unsigned long long)q,
+                    h[(q % 1024) * 4], h[(q % 1024) * 4 + 1], h[(q % 1024) * 4 + 2], h[(q % 1024) * 4 + 3]);
+        cudaFree(cm->d_dbg);
+    }
     for (int p = 0; p < cm->nranks; p++)
         if (p != cm->rank && cm->peers[p]) cudaIpcCloseMemHandle(cm->peers[p]);
     cudaFree(cm->mine);
@@ -462,6 +473,7 @@ static void comm_dev(cg_comm* cm, CommDev& d, uint64_t n_exchanges) {
     for (int p = 0; p < cm->nranks; p++) d.peers[p] = cm->peers[p];
     d.d_error = cm->d_error;
     d.timeout_cycles = 8000000000ULL;
+    d.dbg = cm->d_dbg;
 }
 static int comm_check(cg_comm* cm, cudaStream_t st) {
     if (!cm || cm->nranks <= 1) return CG_OK;
@@ -891,10 +903,11 @@ static TailMailbox* sc_mailbox(cg_sumcheck* sc) {
 static bool tail_eligible(const cg_sumcheck* sc) {
     if (!sc->tl.on || (sc->flags & (CG_SC_NO_FUSE | CG_SC_NO_TAIL)) || sc->round >= sc->num_vars) return false;
     const uint64_t cur = 1ULL << (sc->num_vars - sc->folds);
-    const uint64_t n0 = sc->pending ? cur / 2 : cur;
+    const uint64_t n_loc = sc->pending ? cur / 2 : cur;
+    const uint64_t n0 = n_loc << sc->extra_rounds;       // sharded: the gathered (global) array
     const size_t n_slots = 1 + sc->tl.prod.size() + sc->tl.lk.size();
-    if (n0 < 2 || n0 > CG_TAIL_START_N || n_slots > 1 + 2 * CG_TOWER_MAX_PROD + 4 * CG_TOWER_MAX_LOGUP) return false;
-    if (sc->extra_rounds && (n0 < (uint64_t)(1u << sc->extra_rounds) || n_slots > CG_COMM_GATHER_MLES)) return false;
+    if (n_loc < 2 || n0 > CG_TAIL_START_N || n_slots > CG_COMM_GATHER_SLOTS) return false;
+    if (sc->comm && sc->comm->nranks > 1 && !sc->extra_rounds) return false;   // step API with a comm: per-round exchange only
     return n_slots * n0 * sizeof(ext_t) + 4096 <= sc->ctx->max_smem_optin;
 }
 // launches the tail for rounds sc->round .. num_vars-1; d_tr_state == nullptr -> host mailbox
@@ -925,10 +938,9 @@ static int launch_tail(cg_sumcheck* sc, uint64_t* d_tr_state, ext_t* d_msgs, ext
     a.entry_fold = sc->pending ? 1 : 0;
     a.canon = (f == 0) ? 1 : 0;
     const uint64_t cur = 1ULL << (sc->num_vars - f);
-    a.n0 = (uint32_t)(sc->pending ? cur / 2 : cur);
+    a.n0 = (uint32_t)((sc->pending ? cur / 2 : cur) << sc->extra_rounds);   // sharded: size after the entry all-gather
     a.first_round = sc->round;
     a.num_rounds = sc->num_vars + sc->extra_rounds;
-    a.local_end = sc->num_vars;
     a.d_msgs = d_msgs;
     a.d_chal = d_chal;
     a.d_final = sc->d_final;
@@ -936,10 +948,10 @@ static int launch_tail(cg_sumcheck* sc, uint64_t* d_tr_state, ext_t* d_msgs, ext
     a.mail = d_tr_state ? nullptr : sc_mailbox(sc);
     a.d_error = sc->d_error;
     a.timeout_cycles = 8000000000ULL;   // ~4 s: a dead host must not hang the GPU
-    comm_dev(sc->comm, a.comm, a.local_end - a.first_round);
-    if (sc->comm && sc->extra_rounds) {
+    if (sc->comm && sc->extra_rounds) {   // sharded prove: all-gather on entry, then everything replicated
+        comm_dev(sc->comm, a.comm, 1);
         a.gather_par = (int)(sc->comm->gather_calls++ & 1);
-        a.gather_seq = sc->comm->seq++;
+        a.gather_seq = a.comm.seq;
         sc->extra_done = true;
     }
     const size_t smem = (size_t)slot * a.n0 * sizeof(ext_t);

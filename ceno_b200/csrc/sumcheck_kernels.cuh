@@ -33,14 +33,17 @@
 #define CG_MAX_RANKS 8
 #define CG_COMM_RING 4
 #define CG_COMM_GATHER_MLES 64
-struct CommSlot {
-    uint64_t v[2 * CG_MAX_DEGREE];
-    uint64_t seq;
-    uint64_t pad[7];
+struct __align__(32) CommSlot {       // payload words w[0 .. 2D), validation flag at w[2D]; 32-byte chunks
+    uint64_t w[2 * CG_MAX_DEGREE + 8];
 };
-struct CommGather {                 // final local evaluations, all-gathered for the replicated tail
-    ext_t v[2][CG_COMM_GATHER_MLES][CG_MAX_RANKS];
+#define CG_TAIL_MAX_N 4096      // register staging of the in-place fold is sized for this
+#define CG_TAIL_START_N 2048    // enter the tail once each (global) MLE has <= this many elements (one SM: ~2 items/thread)
+#define CG_COMM_GATHER_SLOTS 33 // 1 + 2*8 + 4*4 MLE slots of the tower layout
+struct CommGather {
+    ext_t v[2][CG_COMM_GATHER_MLES][CG_MAX_RANKS];                 // fallback path: final local evaluations
     uint64_t seq[2][CG_MAX_RANKS];
+    ext_t big[2][CG_COMM_GATHER_SLOTS][CG_TAIL_START_N];           // tail entry: every rank's folded slice, rank-major
+    uint64_t big_seq[2][CG_MAX_RANKS];
 };
 struct CommBuf {
     CommSlot slots[CG_COMM_RING][CG_MAX_RANKS];
@@ -52,6 +55,7 @@ struct CommDev {
     CommBuf* peers[CG_MAX_RANKS];   // peers[rank] is the local buffer
     int* d_error;
     unsigned long long timeout_cycles;
+    unsigned long long* dbg;        // optional: [seq % 1024][4] = {wait_ns(lane 0), wait_ns(lane 1), polls(lane 1), rank}
 };
 // Slot validation without a writer-side fence: the flag word is seq mixed with a checksum of the
 // payload, so a reader that sees the flag before (part of) the payload simply keeps polling.
@@ -60,36 +64,54 @@ GL_DEV uint64_t comm_checksum(uint64_t seq, const uint64_t* v, int n) {
     for (int i = 0; i < n; i++) h = (h ^ v[i]) * 0xD6E8FEB86659FD93ULL + (uint64_t)i;
     return h ^ (h >> 29);
 }
-// executed by a whole converged warp; the local partial is in lane 0, the combined sum returns in lane 0
+// executed by a whole converged warp; the local partial is in lane 0, the combined sum returns in lane 0.
+// The message (payload + flag) is staged in shared memory and leaves as ONE warp-wide instruction of
+// 32-byte stores (lane = peer x chunk): peer stores cost ~2 us of issue stall each, so the number of
+// store instructions — not bytes — is what matters.
 template <int D>
-GL_DEV void comm_exchange(ext_t (&res)[D], const CommDev& cm, uint64_t seq) {
+GL_DEV void comm_exchange(ext_t (&res)[D], const CommDev& cm, uint64_t seq, uint64_t* s_msg /* >= 2D+4 words, 32-B aligned */) {
     const int lane = threadIdx.x & 31;
+    constexpr int CHUNKS = (2 * D + 1 + 3) / 4;
+    if (lane == 0) {
+        uint64_t v[2 * D];
 #pragma unroll
-    for (int x = 0; x < D; x++) {
-        res[x].c0 = __shfl_sync(0xffffffffu, res[x].c0, 0);
-        res[x].c1 = __shfl_sync(0xffffffffu, res[x].c1, 0);
+        for (int x = 0; x < D; x++) { v[2 * x] = res[x].c0; v[2 * x + 1] = res[x].c1; s_msg[2 * x] = res[x].c0; s_msg[2 * x + 1] = res[x].c1; }
+        s_msg[2 * D] = comm_checksum(seq, v, 2 * D);
+#pragma unroll
+        for (int i = 2 * D + 1; i < 4 * CHUNKS; i++) s_msg[i] = 0;
     }
+    __syncwarp();
     const int ring = (int)(seq % CG_COMM_RING);
+    for (int item = lane; item < cm.nranks * CHUNKS; item += 32) {
+        const int p = item / CHUNKS, ch = item % CHUNKS;
+        const uint64_t* src = s_msg + 4 * ch;
+        uint64_t* dst = &cm.peers[p]->slots[ring][cm.rank].w[4 * ch];
+        asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(src[0]), "l"(src[1]), "l"(src[2]), "l"(src[3]) : "memory");
+    }
     ext_t got[D];
 #pragma unroll
     for (int x = 0; x < D; x++) got[x] = ext_zero();
     if (lane < cm.nranks) {
-        uint64_t v[2 * D];
-#pragma unroll
-        for (int x = 0; x < D; x++) { v[2 * x] = res[x].c0; v[2 * x + 1] = res[x].c1; }
-        volatile CommSlot* dst = &cm.peers[lane]->slots[ring][cm.rank];
-#pragma unroll
-        for (int i = 0; i < 2 * D; i++) dst->v[i] = v[i];
-        dst->seq = comm_checksum(seq, v, 2 * D);           // no fence: the reader validates
-        volatile CommSlot* src = &cm.peers[cm.rank]->slots[ring][lane];
+        const CommSlot* src = &cm.peers[cm.rank]->slots[ring][lane];
         const long long t0 = clock64();
+        unsigned long long g0 = 0, polls = 0;
+        if (cm.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+        uint64_t w[4 * CHUNKS];
         while (true) {
-            const uint64_t flag = src->seq;
 #pragma unroll
-            for (int i = 0; i < 2 * D; i++) v[i] = src->v[i];
-            if (flag == comm_checksum(seq, v, 2 * D)) {
+            for (int ch = 0; ch < CHUNKS; ch++)
+                asm volatile("ld.volatile.global.v4.u64 {%0, %1, %2, %3}, [%4];"
+                             : "=l"(w[4 * ch]), "=l"(w[4 * ch + 1]), "=l"(w[4 * ch + 2]), "=l"(w[4 * ch + 3]) : "l"(&src->w[4 * ch]) : "memory");
+            polls++;
+            if (w[2 * D] == comm_checksum(seq, w, 2 * D)) {   // stale or torn contents fail and are re-read
 #pragma unroll
-                for (int x = 0; x < D; x++) got[x] = ext_make(gl_canon(v[2 * x]), gl_canon(v[2 * x + 1]));
+                for (int x = 0; x < D; x++) got[x] = ext_make(gl_canon(w[2 * x]), gl_canon(w[2 * x + 1]));
+                if (cm.dbg && lane < 2) {
+                    unsigned long long g1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+                    cm.dbg[(seq % 1024) * 4 + lane] = g1 - g0;
+                    if (lane == 1) { cm.dbg[(seq % 1024) * 4 + 2] = polls; cm.dbg[(seq % 1024) * 4 + 3] = g0; }
+                }
                 break;
             }
             if ((unsigned long long)(clock64() - t0) > cm.timeout_cycles) { *cm.d_error = 2; break; }
@@ -131,6 +153,7 @@ struct RoundOut {
 template <int D>
 GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out) {
     __shared__ ext_t s_part[CG_THREADS / 32][D];   // blockDim.x <= CG_THREADS
+    __shared__ __align__(32) uint64_t s_msg[2 * D + 8];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
 #pragma unroll
@@ -174,7 +197,7 @@ GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out) {
             ext_t v = lane < n_warps ? s_part[lane][x] : ext_zero();
             res[x] = warp_reduce_ext(v);
         }
-        if (out.comm.nranks > 1) comm_exchange<D>(res, out.comm, out.comm.seq);
+        if (out.comm.nranks > 1) comm_exchange<D>(res, out.comm, out.comm.seq, s_msg);
         if (lane == 0) {
 #pragma unroll
             for (int x = 0; x < D; x++) out.d_out[x] = res[x];
@@ -369,10 +392,9 @@ struct TailArgs {
     TailMailbox* mail;
     int* d_error;               // set to 1 on mailbox timeout/abort
     unsigned long long timeout_cycles;
-    CommDev comm;               // multi-GPU: exchange j uses sequence comm.seq + (j - first_round)
-    uint32_t local_end;         // rounds < local_end are sharded (exchange); after round local_end-1 the
-    int gather_par;             // final local elements are all-gathered and the rest runs replicated
-    uint64_t gather_seq;
+    CommDev comm;               // multi-GPU: this rank loads n_loc = n0 / nranks elements per MLE (its slice of
+    int gather_par;             // the global folded array) and all-gathers the other slices over NVLink on
+    uint64_t gather_seq;        // entry; every later round runs replicated, with no further exchange
 };
 struct SmemLoader {
     const ext_t* sm;
@@ -388,8 +410,6 @@ struct SmemLoader {
     GL_DEV void lk(int l, int z, uint64_t item, ext_t& lo, ext_t& hi) { get(1 + 2 * n_prod + 4 * l + z, item, lo, hi); }
 };
 #define CG_TAIL_THREADS 512
-#define CG_TAIL_MAX_N 4096      // register staging of the in-place fold is sized for this
-#define CG_TAIL_START_N 2048    // enter the tail once each MLE has <= this many elements (one SM: ~2 items/thread)
 GL_DEV const ext_t* tail_slot_ptr(const TowerArgs& t, int slot) {
     if (slot == 0) return t.eq_in;
     slot -= 1;
@@ -407,12 +427,16 @@ __global__ void __launch_bounds__(CG_TAIL_THREADS, 1) tower_tail_kernel(const __
     const int n_slots = 1 + 2 * a.t.n_prod + 4 * a.t.n_logup;
     uint32_t n = a.n0;
     if (tid == 0) s_abort = 0;
-    // ---- load (with the entry fold)
+    // ---- load (with the entry fold); sharded: my slice goes to smem AND to every peer's gather area
     {
+        const CommDev& cm = a.comm;
+        const bool sharded = cm.nranks > 1;
+        const uint32_t n_loc = sharded ? a.n0 / (uint32_t)cm.nranks : a.n0;
+        const uint32_t base = sharded ? (uint32_t)cm.rank * n_loc : 0;
         extmul_t rm = extmul_prep(a.entry_fold ? (a.t.r_ptr ? ld_ext(a.t.r_ptr) : a.t.r) : ext_zero());
         for (int slot = 0; slot < n_slots; slot++) {
             const ext_t* src = tail_slot_ptr(a.t, slot);
-            for (uint32_t b = tid; b < n; b += blockDim.x) {
+            for (uint32_t b = tid; b < n_loc; b += blockDim.x) {
                 ext_t v;
                 if (a.entry_fold) {
                     ext_t lo = ld_ext(src + 2 * b), hi = ld_ext(src + 2 * b + 1);
@@ -422,8 +446,31 @@ __global__ void __launch_bounds__(CG_TAIL_THREADS, 1) tower_tail_kernel(const __
                     v = ld_ext(src + b);
                     if (a.canon) v = ext_canon(v);
                 }
-                sm[(size_t)slot * a.n0 + b] = v;
+                sm[(size_t)slot * a.n0 + base + b] = v;
+                if (sharded)
+                    for (int p = 0; p < cm.nranks; p++)
+                        if (p != cm.rank) st_ext(&cm.peers[p]->gather.big[a.gather_par][slot][base + b], v);
             }
+        }
+        if (sharded) {
+            __threadfence_system();
+            __syncthreads();
+            if (tid < cm.nranks) {
+                *(volatile uint64_t*)&cm.peers[tid]->gather.big_seq[a.gather_par][cm.rank] = a.gather_seq;
+                volatile uint64_t* f = &cm.peers[cm.rank]->gather.big_seq[a.gather_par][tid];
+                const long long t0 = clock64();
+                while (*f != a.gather_seq) {
+                    if ((unsigned long long)(clock64() - t0) > cm.timeout_cycles) { *cm.d_error = 2; break; }
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+            for (int slot = 0; slot < n_slots; slot++)
+                for (uint32_t b = tid; b < a.n0; b += blockDim.x) {
+                    if (b >= base && b < base + n_loc) continue;
+                    const volatile uint64_t* src = (const volatile uint64_t*)&cm.peers[cm.rank]->gather.big[a.gather_par][slot][b];
+                    sm[(size_t)slot * a.n0 + b] = ext_make(src[0], src[1]);
+                }
         }
     }
     __syncthreads();
@@ -444,7 +491,6 @@ __global__ void __launch_bounds__(CG_TAIL_THREADS, 1) tower_tail_kernel(const __
             ext_t res[3];
 #pragma unroll
             for (int x = 0; x < 3; x++) res[x] = warp_reduce_ext(lane < (CG_TAIL_THREADS / 32) ? s_red[lane][x] : ext_zero());
-            if (a.comm.nranks > 1 && j < a.local_end) comm_exchange<3>(res, a.comm, a.comm.seq + (j - a.first_round));
             if (lane == 0) {
                 ext_t r;
 #pragma unroll
@@ -506,34 +552,6 @@ __global__ void __launch_bounds__(CG_TAIL_THREADS, 1) tower_tail_kernel(const __
         }
         __syncthreads();
         n = pairs;
-        if (a.comm.nranks > 1 && j + 1 == a.local_end && a.local_end < a.num_rounds) {
-            // every rank now holds one element per MLE: all-gather them through the mailboxes and run the
-            // last log2(N) rounds replicated on the N gathered elements (rank = top index bits)
-            const CommDev& cm = a.comm;
-            for (int slot = tid; slot < n_slots; slot += blockDim.x) {
-                const ext_t v = sm[(size_t)slot * a.n0];
-                for (int p = 0; p < cm.nranks; p++) cm.peers[p]->gather.v[a.gather_par][slot][cm.rank] = v;
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (tid < cm.nranks) {
-                *(volatile uint64_t*)&cm.peers[tid]->gather.seq[a.gather_par][cm.rank] = a.gather_seq;
-                volatile uint64_t* f = &cm.peers[cm.rank]->gather.seq[a.gather_par][tid];
-                const long long t0 = clock64();
-                while (*f != a.gather_seq) {
-                    if ((unsigned long long)(clock64() - t0) > cm.timeout_cycles) { *cm.d_error = 2; break; }
-                }
-                __threadfence_system();
-            }
-            __syncthreads();
-            for (int i = tid; i < n_slots * cm.nranks; i += blockDim.x) {
-                const int slot = i / cm.nranks, q = i % cm.nranks;
-                const volatile uint64_t* src = (const volatile uint64_t*)&cm.peers[cm.rank]->gather.v[a.gather_par][slot][q];
-                sm[(size_t)slot * a.n0 + q] = ext_make(gl_canon(src[0]), gl_canon(src[1]));
-            }
-            __syncthreads();
-            n = (uint32_t)cm.nranks;
-        }
     }
     for (int slot = tid; slot < n_slots; slot += blockDim.x) a.d_final[a.final_idx[slot]] = sm[(size_t)slot * a.n0];
 }
