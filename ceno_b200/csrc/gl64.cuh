@@ -49,88 +49,77 @@ GL_DEV void gl_mulwide(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
 #endif
 }
 
-// ---------------------------------------------------------------- 160-bit lazy accumulator
-struct acc160 {
-    uint64_t s0, s1;
-    uint32_t s2;   // carries out of bit 128 (< 2^31)
+// ---------------------------------------------------------------- lazy accumulators (32-bit limbs)
+// acc_t holds a sum of 64x64 products WITHOUT carry propagation between the product columns:
+//   value = E + M 2^32,  E = e0 + e1 2^32 + e2 2^64 + e3 2^96 + e4 2^128,  M = m0 + m1 2^32 + m2 2^64.
+// a*b adds a0 b0 into (e1:e0), a1 b1 into (e3:e2) [one carry chain, tail in e4] and a0 b1, a1 b0 into
+// (m1:m0) [carry in m2].  Every window is an aligned register pair, so ptxas fuses each mad.lo.cc /
+// madc.hi pair into one IMAD.WIDE.U32: a multiply-accumulate is 4 IMAD.WIDE + 3 carry adds.
+struct acc_t {
+    uint32_t e0, e1, e2, e3, e4, m0, m1, m2;
 };
-GL_DEV void acc_zero(acc160& A) { A.s0 = 0; A.s1 = 0; A.s2 = 0; }
-GL_DEV void acc_set_mul(acc160& A, uint64_t a, uint64_t b) { gl_mulwide(a, b, A.s0, A.s1); A.s2 = 0; }
-GL_DEV void acc_set64(acc160& A, uint64_t x) { A.s0 = x; A.s1 = 0; A.s2 = 0; }
-// A += a*b
-GL_DEV void acc_mac(acc160& A, uint64_t a, uint64_t b) {
-    uint64_t lo, hi;
-    gl_mulwide(a, b, lo, hi);
+GL_DEV void acc_zero(acc_t& A) { A.e0 = A.e1 = A.e2 = A.e3 = A.e4 = A.m0 = A.m1 = A.m2 = 0; }
+GL_DEV void acc_set64(acc_t& A, uint64_t x) { acc_zero(A); A.e0 = (uint32_t)x; A.e1 = (uint32_t)(x >> 32); }
+// A += a*b   (any u64 operands; up to 2^31 accumulations)
+GL_DEV void acc_mac(acc_t& A, uint64_t a, uint64_t b) {
+    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
 #if defined(__CUDA_ARCH__)
-    asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
-        : "+l"(A.s0), "+l"(A.s1), "+r"(A.s2) : "l"(lo), "l"(hi));
+    asm("mad.lo.cc.u32 %0, %8, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %11, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %11, %3;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 %5, %8, %11, %5;\n\t"
+        "madc.hi.cc.u32 %6, %8, %11, %6;\n\t"
+        "addc.u32 %7, %7, 0;\n\t"
+        "mad.lo.cc.u32 %5, %9, %10, %5;\n\t"
+        "madc.hi.cc.u32 %6, %9, %10, %6;\n\t"
+        "addc.u32 %7, %7, 0;"
+        : "+r"(A.e0), "+r"(A.e1), "+r"(A.e2), "+r"(A.e3), "+r"(A.e4), "+r"(A.m0), "+r"(A.m1), "+r"(A.m2)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
 #else
-    unsigned __int128 t = (unsigned __int128)A.s0 + lo;
-    A.s0 = (uint64_t)t;
-    t = (unsigned __int128)A.s1 + hi + (uint64_t)(t >> 64);
-    A.s1 = (uint64_t)t;
-    A.s2 += (uint32_t)(t >> 64);
+    unsigned __int128 E = ((unsigned __int128)A.e3 << 96) | ((unsigned __int128)A.e2 << 64) | ((unsigned __int128)A.e1 << 32) | A.e0;
+    unsigned __int128 add = (unsigned __int128)((uint64_t)a0 * b0) + ((unsigned __int128)((uint64_t)a1 * b1) << 64);
+    unsigned __int128 Es = E + add;
+    A.e4 += (Es < E) ? 1u : 0u;
+    A.e0 = (uint32_t)Es; A.e1 = (uint32_t)(Es >> 32); A.e2 = (uint32_t)(Es >> 64); A.e3 = (uint32_t)(Es >> 96);
+    unsigned __int128 M = ((unsigned __int128)A.m2 << 64) | ((unsigned __int128)A.m1 << 32) | A.m0;
+    M += (uint64_t)a0 * b1;
+    M += (uint64_t)a1 * b0;
+    A.m0 = (uint32_t)M; A.m1 = (uint32_t)(M >> 32); A.m2 = (uint32_t)(M >> 64);
 #endif
 }
-// A += x (64-bit)
-GL_DEV void acc_add64(acc160& A, uint64_t x) {
-#if defined(__CUDA_ARCH__)
-    asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, 0;\n\taddc.u32 %2, %2, 0;"
-        : "+l"(A.s0), "+l"(A.s1), "+r"(A.s2) : "l"(x));
-#else
-    unsigned __int128 t = (unsigned __int128)A.s0 + x;
-    A.s0 = (uint64_t)t;
-    t = (unsigned __int128)A.s1 + (uint64_t)(t >> 64);
-    A.s1 = (uint64_t)t;
-    A.s2 += (uint32_t)(t >> 64);
-#endif
-}
-// A += B
-GL_DEV void acc_add(acc160& A, const acc160& B) {
-#if defined(__CUDA_ARCH__)
-    asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, %5;"
-        : "+l"(A.s0), "+l"(A.s1), "+r"(A.s2) : "l"(B.s0), "l"(B.s1), "r"(B.s2));
-#else
-    unsigned __int128 t = (unsigned __int128)A.s0 + B.s0;
-    A.s0 = (uint64_t)t;
-    t = (unsigned __int128)A.s1 + B.s1 + (uint64_t)(t >> 64);
-    A.s1 = (uint64_t)t;
-    A.s2 += B.s2 + (uint32_t)(t >> 64);
-#endif
-}
-
-// x = s0 + s1 2^64 + s2 2^128 (s2 < 2^31)  ->  some u64 congruent to x ("weak").
-//   s1 = h1 2^32 + h0:  x = s0 + (h0 << 32) - (h0 + h1 + (s2 << 32))  (mod p)
-//   T = s0 + (h0 << 32) (carry c), U = T - Z (borrow b), result = U + (c - b) EPS  — never wraps twice.
-GL_DEV uint64_t acc_reduce_weak(uint64_t s0, uint64_t s1, uint32_t s2) {
+// x = l0 + l1 2^32 + l2 2^64 + l3 2^96 + l4 2^128 (l4 < 2^31) -> some u64 congruent to x ("weak"):
+//   x = (l1:l0) + (l2 << 32) - (l2 + l3 + (l4 << 32))   (2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32)
+//   T = (l1:l0) + (l2 << 32) (carry c), U = T - Z (borrow b), result = U + (c - b) EPS  — never wraps twice.
+GL_DEV uint64_t gl_reduce_limbs(uint32_t l0, uint32_t l1, uint32_t l2, uint32_t l3, uint32_t l4) {
 #if defined(__CUDA_ARCH__)
     uint64_t r;
     asm("{\n\t"
-        ".reg .u32 a0, a1, h0, h1, t1, c, z0, z1, u0, u1, d, nd, dh;\n\t"
-        "mov.b64 {a0, a1}, %1;\n\t"
-        "mov.b64 {h0, h1}, %2;\n\t"
-        "add.cc.u32 t1, a1, h0;\n\t"
+        ".reg .u32 t1, c, z0, z1, u0, u1, d;\n\t"
+        ".reg .b64 uu;\n\t"
+        "add.cc.u32 t1, %2, %3;\n\t"
         "addc.u32 c, 0, 0;\n\t"
-        "add.cc.u32 z0, h0, h1;\n\t"
-        "addc.u32 z1, %3, 0;\n\t"
-        "sub.cc.u32 u0, a0, z0;\n\t"
+        "add.cc.u32 z0, %3, %4;\n\t"
+        "addc.u32 z1, %5, 0;\n\t"
+        "sub.cc.u32 u0, %1, z0;\n\t"
         "subc.cc.u32 u1, t1, z1;\n\t"
         "subc.u32 d, c, 0;\n\t"
-        "neg.s32 nd, d;\n\t"
-        "shr.s32 dh, d, 31;\n\t"
-        "add.cc.u32 u0, u0, nd;\n\t"
-        "addc.u32 u1, u1, dh;\n\t"
+        // result = U + d EPS = (U - d) + (d << 32), d in {-1,0,1}: both steps on the FMA pipe
+        "mov.b64 uu, {u0, u1};\n\t"
+        "mad.wide.s32 uu, d, -1, uu;\n\t"
+        "mov.b64 {u0, u1}, uu;\n\t"
+        "mad.lo.s32 u1, d, 1, u1;\n\t"
         "mov.b64 %0, {u0, u1};\n\t"
         "}"
-        : "=l"(r) : "l"(s0), "l"(s1), "r"(s2));
+        : "=l"(r) : "r"(l0), "r"(l1), "r"(l2), "r"(l3), "r"(l4));
     return r;
 #else
-    const uint32_t a0 = (uint32_t)s0, a1 = (uint32_t)(s0 >> 32), h0 = (uint32_t)s1, h1 = (uint32_t)(s1 >> 32);
-    uint64_t t = (uint64_t)a1 + h0;
+    uint64_t t = (uint64_t)l1 + l2;
     const uint32_t t1 = (uint32_t)t, c = (uint32_t)(t >> 32);
-    t = (uint64_t)h0 + h1;
-    const uint32_t z0 = (uint32_t)t, z1 = s2 + (uint32_t)(t >> 32);
-    int64_t u = (int64_t)a0 - z0;
+    t = (uint64_t)l2 + l3;
+    const uint32_t z0 = (uint32_t)t, z1 = l4 + (uint32_t)(t >> 32);
+    int64_t u = (int64_t)l0 - z0;
     const uint32_t u0 = (uint32_t)u;
     int64_t bor = u < 0 ? 1 : 0;
     u = (int64_t)t1 - z1 - bor;
@@ -144,17 +133,68 @@ GL_DEV uint64_t acc_reduce_weak(uint64_t s0, uint64_t s1, uint32_t s2) {
     return ((uint64_t)r1 << 32) | r0;
 #endif
 }
-GL_DEV uint64_t acc_weak(const acc160& A) { return acc_reduce_weak(A.s0, A.s1, A.s2); }
+GL_DEV uint64_t acc_reduce_weak(uint64_t s0, uint64_t s1, uint32_t s2) {
+    return gl_reduce_limbs((uint32_t)s0, (uint32_t)(s0 >> 32), (uint32_t)s1, (uint32_t)(s1 >> 32), s2);
+}
+// fold M into E (one carry chain), then reduce
+GL_DEV uint64_t acc_weak(const acc_t& A) {
+    uint32_t l1, l2, l3, l4;
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %4, %8;\n\t"
+        "addc.cc.u32 %1, %5, %9;\n\t"
+        "addc.cc.u32 %2, %6, %10;\n\t"
+        "addc.u32 %3, %7, 0;"
+        : "=r"(l1), "=r"(l2), "=r"(l3), "=r"(l4) : "r"(A.e1), "r"(A.e2), "r"(A.e3), "r"(A.e4), "r"(A.m0), "r"(A.m1), "r"(A.m2));
+#else
+    uint64_t t = (uint64_t)A.e1 + A.m0; l1 = (uint32_t)t;
+    t = (uint64_t)A.e2 + A.m1 + (t >> 32); l2 = (uint32_t)t;
+    t = (uint64_t)A.e3 + A.m2 + (t >> 32); l3 = (uint32_t)t;
+    l4 = A.e4 + (uint32_t)(t >> 32);
+#endif
+    return gl_reduce_limbs(A.e0, l1, l2, l3, l4);
+}
+// compact accumulator (5 limbs) for long-lived sums: adding an acc_t costs 9 carry adds
+struct cacc_t {
+    uint32_t l0, l1, l2, l3, l4;
+};
+GL_DEV void cacc_zero(cacc_t& C) { C.l0 = C.l1 = C.l2 = C.l3 = C.l4 = 0; }
+GL_DEV void cacc_add(cacc_t& C, const acc_t& A) {
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %0, %5;\n\t"
+        "addc.cc.u32 %1, %1, %6;\n\t"
+        "addc.cc.u32 %2, %2, %7;\n\t"
+        "addc.cc.u32 %3, %3, %8;\n\t"
+        "addc.u32 %4, %4, %9;\n\t"
+        "add.cc.u32 %1, %1, %10;\n\t"
+        "addc.cc.u32 %2, %2, %11;\n\t"
+        "addc.cc.u32 %3, %3, %12;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(C.l0), "+r"(C.l1), "+r"(C.l2), "+r"(C.l3), "+r"(C.l4)
+        : "r"(A.e0), "r"(A.e1), "r"(A.e2), "r"(A.e3), "r"(A.e4), "r"(A.m0), "r"(A.m1), "r"(A.m2));
+#else
+    uint64_t t = (uint64_t)C.l0 + A.e0; C.l0 = (uint32_t)t;
+    t = (uint64_t)C.l1 + A.e1 + (t >> 32); C.l1 = (uint32_t)t;
+    t = (uint64_t)C.l2 + A.e2 + (t >> 32); C.l2 = (uint32_t)t;
+    t = (uint64_t)C.l3 + A.e3 + (t >> 32); C.l3 = (uint32_t)t;
+    C.l4 += A.e4 + (uint32_t)(t >> 32);
+    t = (uint64_t)C.l1 + A.m0; C.l1 = (uint32_t)t;
+    t = (uint64_t)C.l2 + A.m1 + (t >> 32); C.l2 = (uint32_t)t;
+    t = (uint64_t)C.l3 + A.m2 + (t >> 32); C.l3 = (uint32_t)t;
+    C.l4 += (uint32_t)(t >> 32);
+#endif
+}
+GL_DEV uint64_t cacc_weak(const cacc_t& C) { return gl_reduce_limbs(C.l0, C.l1, C.l2, C.l3, C.l4); }
 
 // any u64 -> canonical:  x >= p  <=>  hi == 0xFFFFFFFF and lo != 0, and then x - p = lo - 1
 GL_HD uint64_t gl_canon(uint64_t x) {
     const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
     return (hi == 0xFFFFFFFFu && lo != 0) ? (uint64_t)(lo - 1) : x;
 }
-GL_DEV uint64_t acc_canon(const acc160& A) { return gl_canon(acc_weak(A)); }
+GL_DEV uint64_t acc_canon(const acc_t& A) { return gl_canon(acc_weak(A)); }
+GL_DEV uint64_t cacc_canon(const cacc_t& C) { return gl_canon(cacc_weak(C)); }
 
 // ---------------------------------------------------------------- base field
-// a, b canonical -> canonical (5 instructions)
+// a, b canonical -> canonical (5 instructions, ALU pipe)
 GL_DEV uint64_t gl_sub(uint64_t a, uint64_t b) {
 #if defined(__CUDA_ARCH__)
     uint64_t r;
@@ -230,8 +270,12 @@ GL_DEV ext_t ext_canon(ext_t a) { return ext_make(gl_canon(a.c0), gl_canon(a.c1)
 
 // lazy extension accumulator: value = A0 + A1 X, both unreduced
 struct eacc {
-    acc160 A0, A1;
+    acc_t A0, A1;
 };
+struct ecacc {       // compact, for the per-thread round sums
+    cacc_t A0, A1;
+};
+GL_DEV void ecacc_zero(ecacc& E) { cacc_zero(E.A0); cacc_zero(E.A1); }
 GL_DEV void eacc_zero(eacc& E) { acc_zero(E.A0); acc_zero(E.A1); }
 // E += a * b with b's 7*c1 supplied:  (a0 + a1 X)(b0 + b1 X) = a0 b0 + a1 (7 b1) + (a0 b1 + a1 b0) X
 GL_DEV void eacc_mac(eacc& E, ext_t a, ext_t b, uint64_t b1_7) {
@@ -240,7 +284,8 @@ GL_DEV void eacc_mac(eacc& E, ext_t a, ext_t b, uint64_t b1_7) {
     acc_mac(E.A1, a.c0, b.c1);
     acc_mac(E.A1, a.c1, b.c0);
 }
-GL_DEV void eacc_add_ext(eacc& E, ext_t x) { acc_add64(E.A0, x.c0); acc_add64(E.A1, x.c1); }
+GL_DEV void ecacc_add(ecacc& C, const eacc& E) { cacc_add(C.A0, E.A0); cacc_add(C.A1, E.A1); }
+GL_DEV ext_t ecacc_canon(const ecacc& C) { return ext_make(cacc_canon(C.A0), cacc_canon(C.A1)); }
 GL_DEV ext_t eacc_weak(const eacc& E) { return ext_make(acc_weak(E.A0), acc_weak(E.A1)); }
 GL_DEV ext_t eacc_canon(const eacc& E) { return ext_make(acc_canon(E.A0), acc_canon(E.A1)); }
 
@@ -260,24 +305,24 @@ GL_DEV void eacc_mac_prep(eacc& E, ext_t a, const extmul_t& b) {
 // a * b for any u64 limbs; weak / canonical result
 GL_DEV ext_t ext_mul_weak(ext_t a, ext_t b) {
     eacc E;
-    const uint64_t b1_7 = gl_mul7_weak(b.c1);
-    acc_set_mul(E.A0, a.c0, b.c0); acc_mac(E.A0, a.c1, b1_7);
-    acc_set_mul(E.A1, a.c0, b.c1); acc_mac(E.A1, a.c1, b.c0);
+    eacc_zero(E);
+    eacc_mac(E, a, b, gl_mul7_weak(b.c1));
     return eacc_weak(E);
 }
 GL_DEV ext_t ext_mul(ext_t a, ext_t b) { return ext_canon(ext_mul_weak(a, b)); }
 GL_DEV ext_t ext_mul_prep(ext_t a, const extmul_t& b) {
     eacc E;
-    acc_set_mul(E.A0, a.c0, b.c0); acc_mac(E.A0, a.c1, b.c1_7);
-    acc_set_mul(E.A1, a.c0, b.c1); acc_mac(E.A1, a.c1, b.c0);
+    eacc_zero(E);
+    eacc_mac_prep(E, a, b);
     return eacc_canon(E);
 }
 GL_DEV ext_t ext_mul_base(ext_t a, uint64_t b) { return ext_make(gl_mul(a.c0, b), gl_mul(a.c1, b)); }
 // x + d * r  (the fold), one reduction per limb; x canonical or not, result canonical
 GL_DEV ext_t ext_fma_prep(ext_t x, ext_t d, const extmul_t& r) {
     eacc E;
-    acc_set_mul(E.A0, d.c0, r.c0); acc_mac(E.A0, d.c1, r.c1_7); acc_add64(E.A0, x.c0);
-    acc_set_mul(E.A1, d.c0, r.c1); acc_mac(E.A1, d.c1, r.c0); acc_add64(E.A1, x.c1);
+    acc_set64(E.A0, x.c0);        // x rides in the accumulator: no separate modular add
+    acc_set64(E.A1, x.c1);
+    eacc_mac_prep(E, d, r);
     return eacc_canon(E);
 }
 

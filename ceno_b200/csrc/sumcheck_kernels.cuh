@@ -268,14 +268,19 @@ struct TowerArgs {
 };
 
 // H[t] += u * e for the three points; e given as (value at t=1, nd)
-GL_DEV void accumulate_point(eacc& H, ext_t u, ext_t e) { eacc_mac(H, u, e, gl_mul7_weak(e.c1)); }
+GL_DEV void accumulate_point(ecacc& H, ext_t u, ext_t e) {
+    eacc T;
+    eacc_zero(T);
+    eacc_mac(T, u, e, gl_mul7_weak(e.c1));
+    ecacc_add(H, T);   // long-lived sums stay compact (5 limbs); the 4 products accumulate in aligned limb pairs
+}
 
 // One hypercube pair of the tower-layer polynomial: H[t] += eq(t) * inner(t), t = 1, 2, 3.
 // L supplies the (lo, hi) pair of every MLE: from global memory with the fused fold (GlobalLoader) or
 // from shared memory (SmemLoader, tail kernel).
 // SIMPLE = exactly one product spec with alpha = 1 and no logup spec (the T3 shape): no spec loops.
 template <bool SIMPLE, class L>
-GL_DEV void tower_item(const TowerArgs& a, L& ld, uint64_t item, eacc (&H)[3]) {
+GL_DEV void tower_item(const TowerArgs& a, L& ld, uint64_t item, ecacc (&H)[3]) {
     ext_t u[3];   // inner value at t = 1, 2, 3 (weak)
     if (SIMPLE) {
         ext_t alo, av, blo, bv;
@@ -288,8 +293,8 @@ GL_DEV void tower_item(const TowerArgs& a, L& ld, uint64_t item, eacc (&H)[3]) {
             if (t < 2) { av = ext_sub(av, and_); bv = ext_sub(bv, bnd); }
         }
     } else {
-        eacc in[3];
-        eacc_zero(in[0]); eacc_zero(in[1]); eacc_zero(in[2]);
+        ecacc in[3];
+        ecacc_zero(in[0]); ecacc_zero(in[1]); ecacc_zero(in[2]);
         for (int p = 0; p < a.n_prod; p++) {
             ext_t alo, av, blo, bv;
             ld.prod(p, 0, item, alo, av);
@@ -302,7 +307,10 @@ GL_DEV void tower_item(const TowerArgs& a, L& ld, uint64_t item, eacc (&H)[3]) {
             const ext_t and_ = ext_sub(alo, av), bnd = ext_sub(blo, bv);
 #pragma unroll
             for (int t = 0; t < 3; t++) {
-                eacc_mac(in[t], av, bv, gl_mul7_weak(bv.c1));
+                eacc T;
+                eacc_zero(T);
+                eacc_mac(T, av, bv, gl_mul7_weak(bv.c1));
+                ecacc_add(in[t], T);
                 if (t < 2) { av = ext_sub(av, and_); bv = ext_sub(bv, bnd); }
             }
         }
@@ -325,12 +333,17 @@ GL_DEV void tower_item(const TowerArgs& a, L& ld, uint64_t item, eacc (&H)[3]) {
                 eacc D;   // q1 q2
                 eacc_zero(D);
                 eacc_mac(D, q1, q2, q2_7);
-                eacc_mac_prep(in[t], eacc_weak(N), an);
-                eacc_mac_prep(in[t], eacc_weak(D), adn);
+                eacc T;
+                eacc_zero(T);
+                eacc_mac_prep(T, eacc_weak(N), an);
+                eacc_mac_prep(T, eacc_weak(D), adn);
+                ecacc_add(in[t], T);
                 if (t < 2) { p1 = ext_sub(p1, p1n); p2 = ext_sub(p2, p2n); q1 = ext_sub(q1, q1n); q2 = ext_sub(q2, q2n); }
             }
         }
-        u[0] = eacc_weak(in[0]); u[1] = eacc_weak(in[1]); u[2] = eacc_weak(in[2]);
+        u[0] = ext_make(cacc_weak(in[0].A0), cacc_weak(in[0].A1));
+        u[1] = ext_make(cacc_weak(in[1].A0), cacc_weak(in[1].A1));
+        u[2] = ext_make(cacc_weak(in[2].A0), cacc_weak(in[2].A1));
     }
     ext_t elo, ev;
     ld.eq(item, elo, ev);
@@ -356,12 +369,12 @@ template <bool FOLD, bool CANON, bool SIMPLE, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) tower_round_kernel(const __grid_constant__ TowerArgs a) {
     GlobalLoader<FOLD, CANON> ld{a, {0, 0, 0}};
     if (FOLD) ld.rm = extmul_prep(a.r_ptr ? ld_ext(a.r_ptr) : a.r);
-    eacc H[3];
-    eacc_zero(H[0]); eacc_zero(H[1]); eacc_zero(H[2]);
+    ecacc H[3];
+    ecacc_zero(H[0]); ecacc_zero(H[1]); ecacc_zero(H[2]);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < a.n_pairs; item += stride)
         tower_item<SIMPLE>(a, ld, item, H);
-    ext_t acc[3] = {eacc_canon(H[0]), eacc_canon(H[1]), eacc_canon(H[2])};
+    ext_t acc[3] = {ecacc_canon(H[0]), ecacc_canon(H[1]), ecacc_canon(H[2])};
     block_finish<3>(acc, a.out);
 }
 
@@ -477,10 +490,10 @@ __global__ void __launch_bounds__(CG_TAIL_THREADS, 1) tower_tail_kernel(const __
     SmemLoader ld{sm, a.n0, a.t.n_prod};
     for (uint32_t j = a.first_round; j < a.num_rounds; j++) {
         const uint32_t pairs = n >> 1;
-        eacc H[3];
-        eacc_zero(H[0]); eacc_zero(H[1]); eacc_zero(H[2]);
+        ecacc H[3];
+        ecacc_zero(H[0]); ecacc_zero(H[1]); ecacc_zero(H[2]);
         for (uint32_t item = tid; item < pairs; item += blockDim.x) tower_item<SIMPLE>(a.t, ld, item, H);
-        ext_t acc[3] = {eacc_canon(H[0]), eacc_canon(H[1]), eacc_canon(H[2])};
+        ext_t acc[3] = {ecacc_canon(H[0]), ecacc_canon(H[1]), ecacc_canon(H[2])};
 #pragma unroll
         for (int x = 0; x < 3; x++) {
             const ext_t v = warp_reduce_ext(acc[x]);

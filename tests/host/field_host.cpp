@@ -4,6 +4,16 @@
 #include "../../ceno_b200/csrc/gl64.cuh"
 extern "C" {
 uint64_t h_reduce_weak(uint64_t s0, uint64_t s1, uint32_t s2) { return acc_reduce_weak(s0, s1, s2); }
+// compact accumulation of n products a_i*b_i through the aligned-limb accumulator
+uint64_t h_cacc_dot(const uint64_t* a, const uint64_t* b, uint32_t n, uint32_t per) {
+    cacc_t C; cacc_zero(C);
+    for (uint32_t i = 0; i < n; i += per) {
+        acc_t A; acc_zero(A);
+        for (uint32_t j = i; j < n && j < i + per; j++) acc_mac(A, a[j], b[j]);
+        cacc_add(C, A);
+    }
+    return cacc_canon(C);
+}
 uint64_t h_canon(uint64_t x) { return gl_canon(x); }
 uint64_t h_sub(uint64_t a, uint64_t b) { return gl_sub(a, b); }
 uint64_t h_add(uint64_t a, uint64_t b) { return gl_add(a, b); }

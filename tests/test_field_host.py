@@ -58,6 +58,25 @@ def test_sub_add_mul_canonical(lib):
         assert lib.h_mul7_weak(a) % P == 7 * a % P
 
 
+def test_aligned_limb_accumulators(lib):
+    """acc_t (E/M limb columns) + cacc_t (compact) against big-int dot products, worst-case carries included."""
+    lib.h_cacc_dot.restype = C.c_uint64
+    rng = random.Random(7)
+    for n, per in [(1, 1), (2, 2), (5, 2), (64, 4), (1000, 7), (4096, 4096)]:
+        for mode in ("max", "rand", "edge"):
+            if mode == "max":
+                a = [M64] * n
+                b = [M64] * n
+            elif mode == "rand":
+                a = [rng.randrange(1 << 64) for _ in range(n)]
+                b = [rng.randrange(1 << 64) for _ in range(n)]
+            else:
+                a = [rng.choice(EDGE) for _ in range(n)]
+                b = [rng.choice(EDGE) for _ in range(n)]
+            got = lib.h_cacc_dot((C.c_uint64 * n)(*a), (C.c_uint64 * n)(*b), n, per)
+            assert got == sum(x * y for x, y in zip(a, b)) % P, (n, per, mode)
+
+
 def emul(a, b):
     return ((a[0] * b[0] + 7 * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
 
