@@ -1012,7 +1012,7 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
             // one persistent launch for rounds j..; the transcript stays on the host behind a mailbox
             cg_ctx* c = sc->ctx;
             TailMailbox* mb = sc_mailbox(sc);
-            mb->seq_msg = 0; mb->seq_r = 0; mb->abort = 0;
+            if (j == 0) { mb->seq_msg = 0; mb->seq_r = 0; mb->abort = 0; }
             __sync_synchronize();
             CHK(launch_tail(sc, nullptr, sc->d_msgs, sc->d_chal));
             int rc = CG_OK;
@@ -1044,17 +1044,28 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
             sc_mark_done(sc);
             break;
         }
-        {   // round_eval with the end-of-kernels mark placed before the D2H copy
+        {   // one launch; its last block posts the message into the host mailbox (no D2H copy + stream sync)
             cg_ctx* c = sc->ctx;
+            TailMailbox* mb = sc_mailbox(sc);
+            if (j == 0) { mb->seq_msg = 0; mb->seq_r = 0; mb->abort = 0; __sync_synchronize(); }
             RoundOut ro = make_ro(sc);
             ro.d_out = sc->d_msgs;
             ro.d_tr_state = nullptr;
             ro.d_r_out = nullptr;
+            ro.mail = mb;
+            ro.mail_seq = (uint64_t)j + 1;
             CHK(sc_enqueue_round(sc, ro));
             prof_mark(sc, j, 1);
-            CU(c, cudaMemcpyAsync(sc->h_pinned, sc->d_msgs, sizeof(ext_t) * sc->degree, cudaMemcpyDeviceToHost, sc->stream));
-            CU(c, cudaStreamSynchronize(sc->stream));
-            memcpy(msg, sc->h_pinned, sizeof(ext_t) * sc->degree);
+            uint64_t spins = 0;
+            while (mb->seq_msg != (uint64_t)j + 1) {
+                if ((++spins & 0xFFFFF) == 0) {
+                    cudaError_t q = cudaStreamQuery(sc->stream);
+                    if (q != cudaErrorNotReady && mb->seq_msg != (uint64_t)j + 1)
+                        return set_err(c, CG_ERR_CUDA, std::string("round kernel ended without posting its message: ") + cudaGetErrorString(q));
+                }
+            }
+            __sync_synchronize();
+            for (uint32_t x = 0; x < 2 * sc->degree; x++) msg[x] = mb->msg[x];
         }
         uint64_t r[2] = {0, 0};
         cb(user, j, msg, sc->degree, r);

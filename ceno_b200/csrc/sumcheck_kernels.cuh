@@ -138,6 +138,16 @@ __global__ void comm_allgather_kernel(const ext_t* __restrict__ d_final, int m, 
     }
 }
 
+// Host mailbox in mapped pinned memory: the device posts a round message, the host answers with the
+// challenge (tail kernel) or simply launches the next round (per-round kernels) — no D2H copy + stream sync.
+struct TailMailbox {
+    volatile uint64_t seq_msg;  // device -> host: round index + 1 when msg[] is valid
+    uint64_t msg[2 * 8];
+    volatile uint64_t seq_r;    // host -> device: round index + 1 when r[] is valid
+    uint64_t r[2];
+    volatile uint64_t abort;    // host -> device: give up (callback failed)
+};
+
 // ---------------------------------------------------------------------------------------------
 // round output / finish
 struct RoundOut {
@@ -148,6 +158,8 @@ struct RoundOut {
     uint64_t* d_tr_state;     // nullptr -> host transcript
     ext_t* d_r_out;           // where to put the challenge for the next launch
     CommDev comm;             // multi-GPU: combine the partial sums of all ranks (nranks <= 1: off)
+    TailMailbox* mail;        // host transcript: also post the message to the host mailbox with sequence mail_seq
+    uint64_t mail_seq;
 };
 
 template <int D>
@@ -201,6 +213,12 @@ GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out) {
         if (lane == 0) {
 #pragma unroll
             for (int x = 0; x < D; x++) out.d_out[x] = res[x];
+            if (out.mail) {
+#pragma unroll
+                for (int x = 0; x < D; x++) { out.mail->msg[2 * x] = res[x].c0; out.mail->msg[2 * x + 1] = res[x].c1; }
+                __threadfence_system();
+                out.mail->seq_msg = out.mail_seq;
+            }
             if (out.d_tr_state) {   // stand-in challenger: absorb evals, label "Internal round", squeeze
                 uint64_t h = *out.d_tr_state;
 #pragma unroll
@@ -384,13 +402,6 @@ __global__ void __launch_bounds__(THREADS, MINB) tower_round_kernel(const __grid
 // launch or host synchronisation.  The challenge comes from the device-resident challenger or, for
 // the reference's host-side transcript, from a host mailbox in mapped pinned memory (the kernel posts
 // the round message, the host answers with the challenge; ~one PCIe round trip per round).
-struct TailMailbox {            // mapped pinned host memory
-    volatile uint64_t seq_msg;  // device -> host: round index + 1 when msg[] is valid
-    uint64_t msg[2 * 3];
-    volatile uint64_t seq_r;    // host -> device: round index + 1 when r[] is valid
-    uint64_t r[2];
-    volatile uint64_t abort;    // host -> device: give up (callback failed)
-};
 struct TailArgs {
     TowerArgs t;                // *_in = state to load; *_out unused; r / r_ptr = entry fold challenge
     int entry_fold;             // 1: arrays hold 2*n0 elements, fold by r while loading

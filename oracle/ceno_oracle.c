@@ -410,6 +410,166 @@ OR_API int or_sumcheck_prove(const or_mle* mles, uint32_t n_mles, const uint64_t
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * CPU-baseline variant: the reference's parallel decomposition.
+ * `num_threads = optimal_sumcheck_threads(k)` contiguous hypercube chunks, one per thread; each thread
+ * evaluates and folds its own chunk IN PLACE (sequential within the chunk, so the LSB fold is safe) and
+ * owns a shrinking prefix of it; partial round sums are merged on the main thread; once every chunk is
+ * one element the T survivors are compacted and a single thread finishes (the tail).  Ext MLEs given
+ * with consume != 0 are folded inside the caller's buffers, like Either::Right(&mut mle) in the
+ * reference (ceno_zkvm/src/scheme/cpu/mod.rs:417-418, gkr_iop/src/gkr/layer/cpu/mod.rs:186-200) — no
+ * allocation or copy on the timed path.  The inner loop is specialised for one product of three ext
+ * MLEs (the tower layer / T3 shape), everything else takes the generic term loop.
+ * Bit-identical to or_sumcheck_prove (tests/test_oracle_kat.py). */
+static inline gl gl_add_fast(gl a, gl b) { gl s = a + b; return (s < a || s >= GL_P) ? s - GL_P : s; }
+static inline ext ext_add_f(ext a, ext b) { return E(gl_add_fast(a.c0, b.c0), gl_add_fast(a.c1, b.c1)); }
+static inline ext ext_sub_f(ext a, ext b) { return E(gl_sub(a.c0, b.c0), gl_sub(a.c1, b.c1)); }
+static inline gl gl_mul7(gl a) { u128 x = (u128)a * 7; uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64); uint64_t t = hi * GL_EPS; uint64_t r = lo + t; if (r < t) r += GL_EPS; return r >= GL_P ? r - GL_P : r; }
+static inline ext ext_mul_f(ext a, ext b) {
+    /* a0 b0 + 7 a1 b1 and a0 b1 + a1 b0 with one reduction each (129-bit sums) */
+    u128 p0 = (u128)a.c0 * b.c0, p1 = (u128)a.c1 * gl_mul7(b.c1);
+    u128 s = p0 + p1; uint64_t top = s < p0;
+    u128 q0 = (u128)a.c0 * b.c1, q1 = (u128)a.c1 * b.c0;
+    u128 t = q0 + q1; uint64_t top2 = t < q0;
+    ext r;
+    {   uint64_t lo = (uint64_t)s, hi = (uint64_t)(s >> 64), hh = hi >> 32, hl = hi & GL_EPS;
+        uint64_t sub = hh + (top << 32); uint64_t t0 = lo - sub; if (lo < sub) t0 -= GL_EPS;
+        uint64_t t1 = hl * GL_EPS; uint64_t x = t0 + t1; if (x < t1) x += GL_EPS; r.c0 = x >= GL_P ? x - GL_P : x; }
+    {   uint64_t lo = (uint64_t)t, hi = (uint64_t)(t >> 64), hh = hi >> 32, hl = hi & GL_EPS;
+        uint64_t sub = hh + (top2 << 32); uint64_t t0 = lo - sub; if (lo < sub) t0 -= GL_EPS;
+        uint64_t t1 = hl * GL_EPS; uint64_t x = t0 + t1; if (x < t1) x += GL_EPS; r.c1 = x >= GL_P ? x - GL_P : x; }
+    return r;
+}
+OR_API int or_sumcheck_prove_chunked(const or_mle* mles, uint32_t n_mles, const uint64_t* term_coeff,
+                                     const uint32_t* term_off, const uint32_t* term_idx, uint32_t n_terms,
+                                     uint32_t num_vars, uint32_t degree, or_challenge_fn cb, void* user,
+                                     uint64_t* round_evals, uint64_t* final_evals, uint64_t* challenges, int consume) {
+    if (degree > OR_MAX_DEG || degree == 0) return -1;
+    for (uint32_t i = 0; i < n_mles; i++) if (mles[i].num_vars != num_vars) return -2;
+    const uint64_t n = 1ULL << num_vars;
+    int maxthr = 1;
+#ifdef _OPENMP
+    maxthr = omp_get_max_threads();
+#endif
+    uint32_t lt = 0;
+    while ((2u << lt) <= (uint32_t)maxthr && lt + 1 < num_vars) lt++;   /* T = 2^lt chunks, each >= 2 elements */
+    if (num_vars == 0) lt = 0;
+    const uint32_t T = 1u << lt;
+    const uint64_t chunk = n >> lt;
+    ext** f = (ext**)malloc(sizeof(ext*) * (n_mles ? n_mles : 1));
+    int* owned = (int*)calloc(n_mles ? n_mles : 1, sizeof(int));
+    for (uint32_t i = 0; i < n_mles; i++) {
+        if (mles[i].is_ext && consume) { f[i] = (ext*)mles[i].data; continue; }
+        f[i] = (ext*)malloc(sizeof(ext) * n); owned[i] = 1;
+        const uint64_t* d = mles[i].data;
+#pragma omp parallel for schedule(static)
+        for (uint64_t b = 0; b < n; b++) f[i][b] = mles[i].is_ext ? E(d[2 * b], d[2 * b + 1]) : ext_from(d[b]);
+    }
+    const ext* coeff = (const ext*)term_coeff;
+    const int t3 = (n_terms == 1 && degree == 3 && term_off[1] - term_off[0] == 3);
+    ext* part = (ext*)malloc(sizeof(ext) * OR_MAX_DEG * T);
+    uint64_t live = chunk;          /* live elements per chunk */
+    uint32_t j = 0;
+    for (; j < num_vars && live >= 2; j++) {
+        const uint64_t half = live >> 1;
+#pragma omp parallel for schedule(static) num_threads(T)
+        for (uint32_t t = 0; t < T; t++) {
+            ext acc[OR_MAX_DEG];
+            for (uint32_t x = 0; x < degree; x++) acc[x] = EXT_ZERO;
+            const uint64_t base = (uint64_t)t * chunk;
+            if (t3) {
+                const ext* A = f[term_idx[term_off[0]]] + base; const ext* B = f[term_idx[term_off[0] + 1]] + base;
+                const ext* Cc = f[term_idx[term_off[0] + 2]] + base;
+                const ext c = coeff[0];
+                const int c_one = (c.c0 == 1 && c.c1 == 0);
+                ext h1 = EXT_ZERO, h2 = EXT_ZERO, h3 = EXT_ZERO;
+                for (uint64_t b = 0; b < half; b++) {
+                    ext a1 = A[2 * b + 1], ad = ext_sub_f(a1, A[2 * b]);
+                    ext b1 = B[2 * b + 1], bd = ext_sub_f(b1, B[2 * b]);
+                    ext c1 = Cc[2 * b + 1], cd = ext_sub_f(c1, Cc[2 * b]);
+                    ext a2 = ext_add_f(a1, ad), b2 = ext_add_f(b1, bd), c2 = ext_add_f(c1, cd);
+                    ext a3 = ext_add_f(a2, ad), b3 = ext_add_f(b2, bd), c3 = ext_add_f(c2, cd);
+                    h1 = ext_add_f(h1, ext_mul_f(ext_mul_f(a1, b1), c1));
+                    h2 = ext_add_f(h2, ext_mul_f(ext_mul_f(a2, b2), c2));
+                    h3 = ext_add_f(h3, ext_mul_f(ext_mul_f(a3, b3), c3));
+                }
+                if (!c_one) { h1 = ext_mul_f(h1, c); h2 = ext_mul_f(h2, c); h3 = ext_mul_f(h3, c); }
+                acc[0] = h1; acc[1] = h2; acc[2] = h3;
+            } else {
+                for (uint64_t b = 0; b < half; b++)
+                    for (uint32_t q = 0; q < n_terms; q++) {
+                        ext prod[OR_MAX_DEG];
+                        for (uint32_t x = 0; x < degree; x++) prod[x] = coeff[q];
+                        for (uint32_t z = term_off[q]; z < term_off[q + 1]; z++) {
+                            const ext* fi = f[term_idx[z]] + base;
+                            ext hi = fi[2 * b + 1], dl = ext_sub_f(hi, fi[2 * b]), v = hi;
+                            for (uint32_t x = 0; x < degree; x++) { prod[x] = ext_mul_f(prod[x], v); v = ext_add_f(v, dl); }
+                        }
+                        for (uint32_t x = 0; x < degree; x++) acc[x] = ext_add_f(acc[x], prod[x]);
+                    }
+            }
+            for (uint32_t x = 0; x < degree; x++) part[t * OR_MAX_DEG + x] = acc[x];
+        }
+        ext* msg = (ext*)(round_evals + (uint64_t)j * degree * 2);
+        for (uint32_t x = 0; x < degree; x++) {
+            ext sacc = EXT_ZERO;
+            for (uint32_t t = 0; t < T; t++) sacc = ext_add_f(sacc, part[t * OR_MAX_DEG + x]);
+            msg[x] = sacc;
+        }
+        uint64_t r_[2];
+        cb(user, j, (const uint64_t*)msg, degree, r_);
+        challenges[2 * j] = r_[0]; challenges[2 * j + 1] = r_[1];
+        const ext r = E(r_[0], r_[1]);
+#pragma omp parallel for schedule(static) num_threads(T) collapse(2)
+        for (uint32_t i = 0; i < n_mles; i++)
+            for (uint32_t t = 0; t < T; t++) {
+                ext* c = f[i] + (uint64_t)t * chunk;
+                for (uint64_t b = 0; b < half; b++) c[b] = ext_add_f(c[2 * b], ext_mul_f(ext_sub_f(c[2 * b + 1], c[2 * b]), r));
+            }
+        live = half;
+    }
+    /* tail: one survivor per chunk -> compact, finish single-threaded */
+    uint64_t m = T;
+    ext** g = (ext**)malloc(sizeof(ext*) * (n_mles ? n_mles : 1));
+    for (uint32_t i = 0; i < n_mles; i++) {
+        g[i] = (ext*)malloc(sizeof(ext) * m);
+        for (uint64_t t = 0; t < m; t++) g[i][t] = f[i][t * chunk];
+    }
+    for (; j < num_vars; j++) {
+        const uint64_t half = m >> 1;
+        ext acc[OR_MAX_DEG];
+        for (uint32_t x = 0; x < degree; x++) acc[x] = EXT_ZERO;
+        for (uint64_t b = 0; b < half; b++)
+            for (uint32_t q = 0; q < n_terms; q++) {
+                ext prod[OR_MAX_DEG];
+                for (uint32_t x = 0; x < degree; x++) prod[x] = coeff[q];
+                for (uint32_t z = term_off[q]; z < term_off[q + 1]; z++) {
+                    const ext* fi = g[term_idx[z]];
+                    ext hi = fi[2 * b + 1], dl = ext_sub_f(hi, fi[2 * b]), v = hi;
+                    for (uint32_t x = 0; x < degree; x++) { prod[x] = ext_mul_f(prod[x], v); v = ext_add_f(v, dl); }
+                }
+                for (uint32_t x = 0; x < degree; x++) acc[x] = ext_add_f(acc[x], prod[x]);
+            }
+        ext* msg = (ext*)(round_evals + (uint64_t)j * degree * 2);
+        for (uint32_t x = 0; x < degree; x++) msg[x] = acc[x];
+        uint64_t r_[2];
+        cb(user, j, (const uint64_t*)msg, degree, r_);
+        challenges[2 * j] = r_[0]; challenges[2 * j + 1] = r_[1];
+        const ext r = E(r_[0], r_[1]);
+        for (uint32_t i = 0; i < n_mles; i++)
+            for (uint64_t b = 0; b < half; b++) g[i][b] = ext_add_f(g[i][2 * b], ext_mul_f(ext_sub_f(g[i][2 * b + 1], g[i][2 * b]), r));
+        m = half;
+    }
+    for (uint32_t i = 0; i < n_mles; i++) { final_evals[2 * i] = g[i][0].c0; final_evals[2 * i + 1] = g[i][0].c1; }
+    for (uint32_t i = 0; i < n_mles; i++) { free(g[i]); if (owned[i]) free(f[i]); }
+    free(f); free(g); free(owned); free(part);
+    return 0;
+}
+OR_API int or_sumcheck_prove_chunked_standin(const or_mle* mles, uint32_t n_mles, const uint64_t* term_coeff,
+                                             const uint32_t* term_off, const uint32_t* term_idx, uint32_t n_terms,
+                                             uint32_t num_vars, uint32_t degree, or_transcript* tr,
+                                             uint64_t* round_evals, uint64_t* final_evals, uint64_t* challenges, int consume);
+
 /* Stand-in transcript driven sumcheck (SURVEY §A2 order):
  *   append_message(num_vars LE u64), append_message(degree LE u64);
  *   per round: absorb d ext evals, label "Internal round", sample challenge. */
@@ -428,6 +588,17 @@ OR_API int or_sumcheck_prove_standin(const or_mle* mles, uint32_t n_mles, const 
     or_tr_append_message(tr, (const uint8_t*)&dg, 8);
     return or_sumcheck_prove(mles, n_mles, term_coeff, term_off, term_idx, n_terms, num_vars, degree,
                              standin_cb, tr, round_evals, final_evals, challenges);
+}
+
+OR_API int or_sumcheck_prove_chunked_standin(const or_mle* mles, uint32_t n_mles, const uint64_t* term_coeff,
+                                             const uint32_t* term_off, const uint32_t* term_idx, uint32_t n_terms,
+                                             uint32_t num_vars, uint32_t degree, or_transcript* tr,
+                                             uint64_t* round_evals, uint64_t* final_evals, uint64_t* challenges, int consume) {
+    uint64_t nv = num_vars, dg = degree;
+    or_tr_append_message(tr, (const uint8_t*)&nv, 8);
+    or_tr_append_message(tr, (const uint8_t*)&dg, 8);
+    return or_sumcheck_prove_chunked(mles, n_mles, term_coeff, term_off, term_idx, n_terms, num_vars, degree,
+                                     standin_cb, tr, round_evals, final_evals, challenges, consume);
 }
 
 /* verifier-side helpers (ceno_recursion_v2/src/main/mod.rs:3513-3526):

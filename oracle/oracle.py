@@ -235,6 +235,22 @@ def _mk_terms(terms):
     return coeff, off, np.array(idx, dtype=np.uint32)
 
 
+def sumcheck_prove_chunked(mles, terms, num_vars, degree, transcript, consume=False):
+    """CPU-baseline variant (reference decomposition: per-thread chunks folded in place + single-thread tail).
+    With consume=True the ext input arrays are overwritten (Either::Right semantics)."""
+    arr, keep = _mk_mles(mles)
+    coeff, off, idx = _mk_terms(terms)
+    rounds = np.zeros(max(num_vars, 1) * degree * 2, np.uint64)
+    fin = np.zeros(len(mles) * 2, np.uint64)
+    chal = np.zeros(max(num_vars, 1) * 2, np.uint64)
+    rc = lib().or_sumcheck_prove_chunked_standin(arr, C.c_uint32(len(mles)), _p(coeff), _p(off), _p(idx), C.c_uint32(len(terms)),
+                                                 C.c_uint32(num_vars), C.c_uint32(degree), C.byref(transcript.t), _p(rounds), _p(fin),
+                                                 _p(chal), C.c_int(1 if consume else 0))
+    if rc:
+        raise ValueError(f"or_sumcheck_prove_chunked rc={rc}")
+    return (rounds[:num_vars * degree * 2].reshape(num_vars, degree, 2), fin.reshape(-1, 2), chal[:num_vars * 2].reshape(num_vars, 2))
+
+
 def sumcheck_prove(mles, terms, num_vars, degree, transcript=None, challenge_fn=None):
     """Returns (round_evals[num_vars, degree, 2], final_evals[n_mles, 2], challenges[num_vars, 2]).
 

@@ -353,3 +353,24 @@ def test_tower_proof_verifies():
     full = [x for x in f1] + [x for x in f2]  # top variable selects the half
     assert pr.mle_evaluate(full, rt) == prod_claim
     assert pr.mle_evaluate(q1 + q2, rt) == q_claim
+
+
+@pytest.mark.parametrize("k,shape", [(0, "t3"), (1, "t3"), (2, "t3"), (5, "t3"), (9, "t3"), (12, "t3"), (7, "generic"), (11, "generic")])
+def test_chunked_cpu_baseline_variant_is_bit_identical(k, shape):
+    """The timed CPU arm (reference decomposition, in-place chunk folds) against the simple restatement."""
+    rng = random.Random(k)
+    n = 1 << k
+    if shape == "t3":
+        mles = [(orc.fill_ext(10 + i, n), True, k) for i in range(3)]
+        terms = [([1, 0] if k % 2 else [rng.randrange(P), rng.randrange(P)], [0, 1, 2])]
+        degree = 3
+    else:
+        mles = [(orc.fill_base(20, n), False, k), (orc.fill_ext(21, n), True, k), (orc.fill_ext(22, n), True, k), (orc.fill_ext(23, n), True, k)]
+        terms = [([rng.randrange(P), rng.randrange(P)], [0, 1, 2, 3]), ([3, 0], [1]), ([5, 7], [])]
+        degree = 4
+    want = orc.sumcheck_prove(mles, terms, k, degree, transcript=orc.Transcript(b"chunk"))
+    for consume in (False, True):
+        copies = [(m[0].copy(), m[1], m[2]) for m in mles]
+        got = orc.sumcheck_prove_chunked(copies, terms, k, degree, orc.Transcript(b"chunk"), consume=consume)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
