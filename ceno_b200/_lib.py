@@ -14,6 +14,11 @@ class CgMleDesc(C.Structure):
     _fields_ = [("dptr", C.c_void_p), ("len", C.c_uint64), ("num_vars", C.c_uint32), ("is_ext", C.c_uint32)]
 
 
+class CgPoseidon2Params(C.Structure):
+    _fields_ = [("ext_rc", (C.c_uint64 * 8) * 8), ("int_rc", C.c_uint64 * 22), ("diag", C.c_uint64 * 8),
+                ("mds_variant", C.c_uint32), ("pad", C.c_uint32)]
+
+
 class CgTowerSpec(C.Structure):
     _fields_ = [("leaves", C.c_void_p * 4), ("num_vars", C.c_uint32), ("is_logup", C.c_uint32)]
 
@@ -40,6 +45,7 @@ SYMBOLS = [
     "cg_tower_output_evals", "cg_tower_proof_len", "cg_tower_point_len", "cg_tower_create_proof", "cg_tower_destroy",
     "cg_standin_vt", "cg_wit_infer_by_monomial_expr", "cg_profile_last",
     "cg_comm_create", "cg_comm_connect", "cg_comm_destroy", "cg_sumcheck_attach_comm", "cg_sumcheck_prove_sharded",
+    "cg_poseidon2_set_params", "cg_poseidon2_permute", "cg_merkle_commit",
 ]
 
 _lib = None
@@ -104,6 +110,9 @@ def load():
         "cg_comm_connect": (i32, [vp, vp]),
         "cg_comm_destroy": (i32, [vp]),
         "cg_sumcheck_attach_comm": (i32, [vp, vp]),
+        "cg_poseidon2_set_params": (i32, [vp, vp]),
+        "cg_poseidon2_permute": (i32, [vp, vp, u64, vp]),
+        "cg_merkle_commit": (i32, [vp, vp, u64, u64, i32, vp, vp, vp]),
         "cg_sumcheck_prove_sharded": (i32, [vp, vp, P(CgMleDesc), u32, vp, vp, vp, u32, u32, u32, u32, CHALLENGE_CB, vp, vp, vp, vp, vp, vp]),
     }
     for name in SYMBOLS:

@@ -407,3 +407,34 @@ class TowerProver:
         if self.h:
             self.dev.lib.cg_tower_destroy(self.h)
             self.h = C.c_void_p()
+
+
+# ------------------------------------------------------------------- Poseidon2 / Merkle (a9; constants supplied by the caller)
+def poseidon2_set_params(dev, ext_rc, int_rc, diag, mds_variant=0):
+    p = _lib.CgPoseidon2Params()
+    for r in range(8):
+        for i in range(8):
+            p.ext_rc[r][i] = int(ext_rc[r][i])
+    for r in range(22):
+        p.int_rc[r] = int(int_rc[r])
+    for i in range(8):
+        p.diag[i] = int(diag[i])
+    p.mds_variant = mds_variant
+    dev.check(dev.lib.cg_poseidon2_set_params(dev.ctx, C.byref(p)))
+
+
+def poseidon2_permute(dev, states):
+    states = _u64(states)
+    buf = dev.to_device(states)
+    dev.check(dev.lib.cg_poseidon2_permute(dev.ctx, C.c_void_p(buf.ptr), states.size // 8, None))
+    out = buf.to_host()
+    buf.free()
+    return out
+
+
+def merkle_commit(dev, matrix_buf, width, height, col_major=True):
+    """matrix_buf: DeviceBuffer of height*width base elements.  Returns (tree DeviceBuffer, root[4])."""
+    tree = dev.alloc(32 * (2 * height - 1))
+    root = np.zeros(4, np.uint64)
+    dev.check(dev.lib.cg_merkle_commit(dev.ctx, C.c_void_p(matrix_buf.ptr), width, height, 1 if col_major else 0, C.c_void_p(tree.ptr), _vp(root), None))
+    return tree, root

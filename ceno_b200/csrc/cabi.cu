@@ -16,6 +16,7 @@
 
 #include "../../include/ceno_b200.h"
 #include "sumcheck_kernels.cuh"
+#include "poseidon2.cuh"
 
 #define CG_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -32,6 +33,7 @@ struct cg_ctx {
     size_t used = 0, reserved = 0;
     uint64_t launches = 0;
     std::vector<std::pair<size_t, void*>> pinned_cache;   // reusable pinned staging buffers
+    P2Params* d_p2 = nullptr;                             // Poseidon2 constants (caller-supplied, cg_poseidon2_set_params)
     std::vector<float> profile_ms;                        // per-round device time of the last CG_SC_PROFILE run
 };
 
@@ -137,6 +139,7 @@ CG_EXPORT int cg_destroy(cg_ctx* c) {
     cg_pool_trim(c);
     for (auto& kv : c->live) cudaFree(kv.first);
     for (auto& pc : c->pinned_cache) cudaFreeHost(pc.second);
+    if (c->d_p2) cudaFree(c->d_p2);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return CG_OK;
@@ -1495,5 +1498,52 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
         alpha_pows(tr, n_alpha, alpha);
     }
     memcpy(h_point, rt.data(), sizeof(uint64_t) * 2 * rt_len);
+    return CG_OK;
+}
+
+// --------------------------------------------------------------------- Poseidon2 / Merkle (a9)
+static_assert(sizeof(P2Params) == sizeof(cg_poseidon2_params), "params layout");
+CG_EXPORT int cg_poseidon2_set_params(cg_ctx* c, const cg_poseidon2_params* p) {
+    if (!c || !p) return CG_ERR_INVALID;
+    if (p->mds_variant > 1) return set_err(c, CG_ERR_INVALID, "cg_poseidon2_set_params: mds_variant must be 0 or 1");
+    CU(c, cudaSetDevice(c->device));
+    if (!c->d_p2) CU(c, cudaMalloc((void**)&c->d_p2, sizeof(P2Params)));
+    P2Params h;
+    memcpy(&h, p, sizeof(h));
+    uint64_t* w = reinterpret_cast<uint64_t*>(&h);
+    for (size_t i = 0; i < (8 * 8 + 22 + 8); i++) w[i] = w[i] >= GL_P ? w[i] - GL_P : w[i];
+    CU(c, cudaMemcpy(c->d_p2, &h, sizeof(h), cudaMemcpyHostToDevice));
+    return CG_OK;
+}
+CG_EXPORT int cg_poseidon2_permute(cg_ctx* c, uint64_t* d_states, uint64_t n, cg_stream s) {
+    if (!c || !d_states) return CG_ERR_INVALID;
+    if (!c->d_p2) return set_err(c, CG_ERR_STATE, "cg_poseidon2_set_params has not been called (constants are upstream-only: the caller supplies them)");
+    if (n == 0) return CG_OK;
+    p2_permute_kernel<<<(unsigned)((n + 127) / 128), 128, 0, S(c, s)>>>(c->d_p2, d_states, n);
+    LAUNCHED(c);
+    CU(c, cudaGetLastError());
+    return CG_OK;
+}
+CG_EXPORT int cg_merkle_commit(cg_ctx* c, const uint64_t* d_matrix, uint64_t width, uint64_t height, int col_major,
+                               uint64_t* d_tree, uint64_t h_root[4], cg_stream s) {
+    if (!c || !d_matrix || !d_tree || width == 0) return CG_ERR_INVALID;
+    if (!c->d_p2) return set_err(c, CG_ERR_STATE, "cg_poseidon2_set_params has not been called (constants are upstream-only: the caller supplies them)");
+    if (height == 0 || (height & (height - 1))) return set_err(c, CG_ERR_INVALID, "cg_merkle_commit: height must be a power of two");
+    cudaStream_t st = S(c, s);
+    CU(c, cudaSetDevice(c->device));
+    p2_leaf_kernel<<<(unsigned)((height + 127) / 128), 128, 0, st>>>(c->d_p2, d_matrix, width, height, col_major, d_tree);
+    LAUNCHED(c);
+    uint64_t off = 0, n = height;
+    while (n > 1) {
+        p2_compress_kernel<<<(unsigned)((n / 2 + 127) / 128), 128, 0, st>>>(c->d_p2, d_tree + 4 * off, n / 2, d_tree + 4 * (off + n));
+        LAUNCHED(c);
+        off += n;
+        n /= 2;
+    }
+    CU(c, cudaGetLastError());
+    if (h_root) {
+        CU(c, cudaMemcpyAsync(h_root, d_tree + 4 * off, 32, cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+    }
     return CG_OK;
 }

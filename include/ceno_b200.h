@@ -261,6 +261,28 @@ int cg_wit_infer_by_monomial_expr(cg_ctx* ctx, const cg_mle_desc* mles, uint32_t
                                   const uint32_t* term_mle_idx, uint32_t n_terms, uint32_t num_vars,
                                   uint64_t* d_out_ext, cg_stream s);
 
+/* ---- kernel (iii-commit): Merkle commitment over Poseidon2-Goldilocks (TraceCommitter::commit_traces ->
+ * PCS::batch_commit, ceno_zkvm/src/scheme/cpu/mod.rs:559-584; GPU basefold.batch_commit_*,
+ * ceno_zkvm/src/scheme/gpu/mod.rs:1062-1509).  PARITY UNPINNED: Poseidon2 round constants, the internal diagonal
+ * and Basefold's code/leaf arrangement are defined only in un-vendored crates, so the
+ * constants are supplied by the caller (the Rust side has them) and the layout offered is the plain
+ * Plonky3 one: leaf = PaddingFreeSponge<8, rate 4, out 4> over one matrix row, node = TruncatedPermutation.
+ * RS-encoding of the columns is not included. */
+typedef struct cg_poseidon2_params {
+    uint64_t ext_rc[8][8];   /* external round constants: rounds 0-3 initial, 4-7 terminal */
+    uint64_t int_rc[22];     /* internal round constants (lane 0) */
+    uint64_t diag[8];        /* internal layer: state[i] = state[i] * diag[i] + sum(state) */
+    uint32_t mds_variant;    /* 0: circ(2,3,1,1)  1: Horizen-Labs M4 */
+    uint32_t pad;
+} cg_poseidon2_params;
+int cg_poseidon2_set_params(cg_ctx* ctx, const cg_poseidon2_params* params);
+int cg_poseidon2_permute(cg_ctx* ctx, uint64_t* d_states /* n x 8 */, uint64_t n, cg_stream s);
+/* d_matrix: height x width base elements (height a power of two), column-major (col_major != 0, what the
+ * reference keeps on the device after matrix_transpose) or row-major.  d_tree receives 2*height-1 digests of
+ * 4 u64 (leaf level first, root last); h_root (optional) the root. */
+int cg_merkle_commit(cg_ctx* ctx, const uint64_t* d_matrix, uint64_t width, uint64_t height, int col_major,
+                     uint64_t* d_tree, uint64_t h_root[4], cg_stream s);
+
 #ifdef __cplusplus
 }
 #endif

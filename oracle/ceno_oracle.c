@@ -822,3 +822,92 @@ OR_API int or_num_threads(void) {
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Poseidon2 over Goldilocks, width 8, and the Merkle commitment built on it.
+ * PARITY UNPINNED: round constants, the internal diagonal and the Basefold leaf arrangement live in
+ * the un-vendored crates (p3-goldilocks 0.4.3 / gkr-backend `poseidon`, `mpcs`), so the
+ * constants are PARAMETERS here.  Structure restated from the published Poseidon2 construction as
+ * Plonky3 instantiates it for Goldilocks: S-box x^7, 8 external + 22 internal rounds;
+ *   external layer: M4 on each 4-chunk, then every lane += the sum of the lanes at the same offset;
+ *   internal layer: s = sum(state); state[i] = state[i] * diag[i] + s;
+ *   order: external layer, 4 x (rc, sbox all, external), 22 x (rc0, sbox lane 0, internal), 4 x (...).
+ * Hashing (p3-symmetric): PaddingFreeSponge<8, rate 4, out 4> for a leaf row (inputs OVERWRITE the
+ * rate lanes, permute per chunk), TruncatedPermutation<2, 4, 8> for an inner node. */
+#define P2_W 8
+#define P2_RF 8
+#define P2_RP 22
+typedef struct {
+    uint64_t ext_rc[P2_RF][P2_W];
+    uint64_t int_rc[P2_RP];
+    uint64_t diag[P2_W];
+    uint32_t mds_variant;   /* 0: circ(2,3,1,1)   1: Horizen-Labs M4 [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]] */
+    uint32_t pad;
+} or_p2_params;
+static inline gl p2_sbox(gl x) { gl x2 = gl_mul(x, x), x3 = gl_mul(x2, x), x4 = gl_mul(x2, x2); return gl_mul(x4, x3); }
+static void p2_m4(gl* x, uint32_t variant) {
+    static const uint64_t M0[4][4] = {{2, 3, 1, 1}, {1, 2, 3, 1}, {1, 1, 2, 3}, {3, 1, 1, 2}};
+    static const uint64_t M1[4][4] = {{5, 7, 1, 3}, {4, 6, 1, 1}, {1, 3, 5, 7}, {1, 1, 4, 6}};
+    gl o[4];
+    for (int i = 0; i < 4; i++) {
+        gl acc = 0;
+        for (int j = 0; j < 4; j++) acc = gl_add(acc, gl_mul((variant ? M1 : M0)[i][j], x[j]));
+        o[i] = acc;
+    }
+    for (int i = 0; i < 4; i++) x[i] = o[i];
+}
+static void p2_external(gl* s, uint32_t variant) {
+    p2_m4(s, variant); p2_m4(s + 4, variant);
+    for (int i = 0; i < 4; i++) { gl t = gl_add(s[i], s[4 + i]); s[i] = gl_add(s[i], t); s[4 + i] = gl_add(s[4 + i], t); }
+}
+OR_API void or_poseidon2_permute(const or_p2_params* p, uint64_t* state) {
+    gl s[P2_W];
+    for (int i = 0; i < P2_W; i++) s[i] = to_canon(state[i]);
+    p2_external(s, p->mds_variant);
+    for (int r = 0; r < P2_RF / 2; r++) {
+        for (int i = 0; i < P2_W; i++) s[i] = p2_sbox(gl_add(s[i], to_canon(p->ext_rc[r][i])));
+        p2_external(s, p->mds_variant);
+    }
+    for (int r = 0; r < P2_RP; r++) {
+        s[0] = p2_sbox(gl_add(s[0], to_canon(p->int_rc[r])));
+        gl sum = 0;
+        for (int i = 0; i < P2_W; i++) sum = gl_add(sum, s[i]);
+        for (int i = 0; i < P2_W; i++) s[i] = gl_add(gl_mul(s[i], to_canon(p->diag[i])), sum);
+    }
+    for (int r = P2_RF / 2; r < P2_RF; r++) {
+        for (int i = 0; i < P2_W; i++) s[i] = p2_sbox(gl_add(s[i], to_canon(p->ext_rc[r][i])));
+        p2_external(s, p->mds_variant);
+    }
+    for (int i = 0; i < P2_W; i++) state[i] = s[i];
+}
+static void p2_hash_row(const or_p2_params* p, const uint64_t* row, uint64_t width, uint64_t* out4) {
+    uint64_t st[P2_W] = {0};
+    for (uint64_t c = 0; c < width; c += 4) {
+        for (uint64_t i = 0; i < 4 && c + i < width; i++) st[i] = to_canon(row[c + i]);
+        or_poseidon2_permute(p, st);
+    }
+    for (int i = 0; i < 4; i++) out4[i] = st[i];
+}
+static void p2_compress(const or_p2_params* p, const uint64_t* l, const uint64_t* r, uint64_t* out4) {
+    uint64_t st[P2_W];
+    for (int i = 0; i < 4; i++) { st[i] = l[i]; st[4 + i] = r[i]; }
+    or_poseidon2_permute(p, st);
+    for (int i = 0; i < 4; i++) out4[i] = st[i];
+}
+/* matrix: height rows (power of two) x width base elements, row-major.  tree: (2*height - 1) digests of 4 u64,
+ * leaves first (level 0 = leaf digests), root last.  Returns the root in root4. */
+OR_API int or_merkle_commit(const or_p2_params* p, const uint64_t* matrix, uint64_t width, uint64_t height,
+                            uint64_t* tree, uint64_t* root4) {
+    if (height == 0 || (height & (height - 1))) return -1;
+#pragma omp parallel for schedule(static)
+    for (uint64_t i = 0; i < height; i++) p2_hash_row(p, matrix + i * width, width, tree + 4 * i);
+    uint64_t off = 0, n = height;
+    while (n > 1) {
+        uint64_t* dst = tree + 4 * (off + n);
+#pragma omp parallel for schedule(static)
+        for (uint64_t i = 0; i < n / 2; i++) p2_compress(p, tree + 4 * (off + 2 * i), tree + 4 * (off + 2 * i + 1), dst + 4 * i);
+        off += n; n /= 2;
+    }
+    for (int i = 0; i < 4; i++) root4[i] = tree[4 * off + i];
+    return 0;
+}

@@ -351,3 +351,41 @@ def tower_create_proof(prod_wits, logup_wits, transcript):
     if w < 0:
         raise ValueError(f"or_tower_create_proof rc={w}")
     return proof[:w].copy(), point[:2 * plen.value].copy()
+
+
+# -------------------------------------------------------------- Poseidon2 / Merkle (a9, parity unpinned)
+class P2Params(C.Structure):
+    _fields_ = [("ext_rc", (C.c_uint64 * 8) * 8), ("int_rc", C.c_uint64 * 22), ("diag", C.c_uint64 * 8),
+                ("mds_variant", C.c_uint32), ("pad", C.c_uint32)]
+
+
+def p2_params(seed=1, mds_variant=0):
+    """Deterministic PLACEHOLDER constants (the real ones are upstream-only)."""
+    p = P2Params()
+    vals = fill_base(0x9052 + seed, 8 * 8 + 22 + 8)
+    k = 0
+    for r in range(8):
+        for i in range(8):
+            p.ext_rc[r][i] = int(vals[k]); k += 1
+    for r in range(22):
+        p.int_rc[r] = int(vals[k]); k += 1
+    for i in range(8):
+        p.diag[i] = int(vals[k]); k += 1
+    p.mds_variant = mds_variant
+    return p
+
+
+def poseidon2_permute(params, state):
+    st = _u64(state).copy()
+    lib().or_poseidon2_permute(C.byref(params), _p(st))
+    return st
+
+
+def merkle_commit(params, matrix, width, height):
+    matrix = _u64(matrix)
+    tree = np.zeros(4 * (2 * height - 1), np.uint64)
+    root = np.zeros(4, np.uint64)
+    rc = lib().or_merkle_commit(C.byref(params), _p(matrix), C.c_uint64(width), C.c_uint64(height), _p(tree), _p(root))
+    if rc:
+        raise ValueError(f"or_merkle_commit rc={rc}")
+    return tree, root

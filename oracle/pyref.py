@@ -128,3 +128,43 @@ def from_pairs(pairs):
         out[2 * i] = a
         out[2 * i + 1] = b
     return out
+
+
+# ---------------------------------------------------------------- Poseidon2 width 8 (structure only; constants are parameters)
+M4 = {0: [[2, 3, 1, 1], [1, 2, 3, 1], [1, 1, 2, 3], [3, 1, 1, 2]], 1: [[5, 7, 1, 3], [4, 6, 1, 1], [1, 3, 5, 7], [1, 1, 4, 6]]}
+
+
+def _p2_external(s, variant):
+    m = M4[variant]
+    s = [sum(m[i][j] * s[4 * c + j] for j in range(4)) % P for c in range(2) for i in range(4)]
+    sums = [(s[i] + s[4 + i]) % P for i in range(4)]
+    return [(s[4 * c + i] + sums[i]) % P for c in range(2) for i in range(4)]
+
+
+def poseidon2_permute(ext_rc, int_rc, diag, variant, state):
+    s = _p2_external([x % P for x in state], variant)
+    for r in range(4):
+        s = _p2_external([pow((s[i] + ext_rc[r][i]) % P, 7, P) for i in range(8)], variant)
+    for r in range(22):
+        s[0] = pow((s[0] + int_rc[r]) % P, 7, P)
+        tot = sum(s) % P
+        s = [(s[i] * diag[i] + tot) % P for i in range(8)]
+    for r in range(4, 8):
+        s = _p2_external([pow((s[i] + ext_rc[r][i]) % P, 7, P) for i in range(8)], variant)
+    return s
+
+
+def hash_row(perm, row):
+    st = [0] * 8
+    for c in range(0, len(row), 4):
+        chunk = row[c:c + 4]
+        st[:len(chunk)] = [x % P for x in chunk]
+        st = perm(st)
+    return st[:4]
+
+
+def merkle_root(perm, rows):
+    level = [hash_row(perm, r) for r in rows]
+    while len(level) > 1:
+        level = [perm(level[2 * i] + level[2 * i + 1])[:4] for i in range(len(level) // 2)]
+    return level[0]

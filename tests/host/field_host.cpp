@@ -2,7 +2,9 @@
 // sequences (weak reduction, lazy accumulation, subtraction-only evaluation points) can be checked
 // against big-int arithmetic without a GPU.  The PTX transcription itself is covered by the -m gpu tests.
 #include "../../ceno_b200/csrc/gl64.cuh"
+#include "../../ceno_b200/csrc/poseidon2.cuh"
 extern "C" {
+void h_p2_permute(const P2Params* p, uint64_t* st) { uint64_t s[8]; for (int i = 0; i < 8; i++) s[i] = gl_canon(st[i]); p2_permute(*p, s); for (int i = 0; i < 8; i++) st[i] = s[i]; }
 uint64_t h_reduce_weak(uint64_t s0, uint64_t s1, uint32_t s2) { return acc_reduce_weak(s0, s1, s2); }
 // compact accumulation of n products a_i*b_i through the aligned-limb accumulator
 uint64_t h_cacc_dot(const uint64_t* a, const uint64_t* b, uint32_t n, uint32_t per) {

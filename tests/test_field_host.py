@@ -17,7 +17,8 @@ def lib():
     so = os.path.join(HERE, "host", "libfield_host.so")
     src = os.path.join(HERE, "host", "field_host.cpp")
     hdr = os.path.join(HERE, "..", "ceno_b200", "csrc", "gl64.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdr2 = os.path.join(HERE, "..", "ceno_b200", "csrc", "poseidon2.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2)):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-o", so, src])
     L = C.CDLL(so)
     for f in ("h_reduce_weak", "h_canon", "h_sub", "h_add", "h_mul", "h_mul7_weak"):
@@ -108,3 +109,16 @@ def test_ext_mul_fma_and_lazy_dot(lib):
             m = emul((a[2 * i], a[2 * i + 1]), (b[2 * i], b[2 * i + 1]))
             acc = ((acc[0] + m[0]) % P, (acc[1] + m[1]) % P)
         assert (o[0], o[1]) == acc
+
+
+def test_poseidon2_device_code_on_host_matches_oracle(lib):
+    """ceno_b200/csrc/poseidon2.cuh compiled for the host vs the oracle's restatement (same placeholder constants)."""
+    import numpy as np
+    from oracle import oracle as orc
+    for variant in (0, 1):
+        prm = orc.p2_params(seed=9, mds_variant=variant)
+        rng = random.Random(variant)
+        for st in ([0] * 8, [P - 1] * 8, [rng.randrange(P) for _ in range(8)], [rng.randrange(P) for _ in range(8)]):
+            arr = (C.c_uint64 * 8)(*st)
+            lib.h_p2_permute(C.byref(prm), arr)
+            assert list(arr) == [int(x) for x in orc.poseidon2_permute(prm, np.array(st, dtype=np.uint64))]

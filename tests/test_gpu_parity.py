@@ -401,3 +401,32 @@ def test_sharded_sumcheck_multi_gpu_bit_exact():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, True) for r in range(world)]
+
+
+# ------------------------------------------------------------------- Poseidon2 / Merkle (a9)
+@pytest.mark.parametrize("variant", [0, 1])
+def test_poseidon2_and_merkle_commit(dev, variant):
+    """Constants are caller-supplied placeholders (parity unpinned upstream); the kernels must match
+    the oracle bit for bit on the same constants."""
+    import ceno_b200 as cb
+    from ceno_b200 import api
+    prm = orc.p2_params(seed=5, mds_variant=variant)
+    api.poseidon2_set_params(dev, [[int(prm.ext_rc[r][i]) for i in range(8)] for r in range(8)], [int(x) for x in prm.int_rc],
+                             [int(x) for x in prm.diag], variant)
+    st = orc.fill_base(31, 8 * 300)
+    st[:8] = 0
+    st[8:16] = np.uint64(P - 1)
+    st[16:24] = np.uint64(2**64 - 1)     # non-canonical input lanes
+    want = np.concatenate([orc.poseidon2_permute(prm, st[8 * i:8 * i + 8]) for i in range(300)])
+    assert eq_np(api.poseidon2_permute(dev, st), want)
+    for width, height in [(1, 1), (3, 2), (8, 64), (13, 1024), (64, 4096)]:
+        m = orc.fill_base(500 + width, width * height)                   # row-major host matrix
+        tree_w, root_w = orc.merkle_commit(prm, m, width, height)
+        rm = dev.to_device(m)
+        cm = dev.to_device(np.ascontiguousarray(m.reshape(height, width).T).reshape(-1))
+        for buf, col_major in ((rm, False), (cm, True)):
+            tree, root = api.merkle_commit(dev, buf, width, height, col_major=col_major)
+            assert eq_np(root, root_w)
+            assert eq_np(tree.to_host(), tree_w)
+            tree.free()
+        rm.free(); cm.free()

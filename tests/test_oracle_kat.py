@@ -374,3 +374,22 @@ def test_chunked_cpu_baseline_variant_is_bit_identical(k, shape):
         got = orc.sumcheck_prove_chunked(copies, terms, k, degree, orc.Transcript(b"chunk"), consume=consume)
         for g, w in zip(got, want):
             assert np.array_equal(g, w)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_poseidon2_and_merkle_vs_bigint_restatement(variant):
+    """a9 building blocks, constants supplied by the caller (parity unpinned: SURVEY §C-2/3)."""
+    prm = orc.p2_params(seed=3, mds_variant=variant)
+    ext_rc = [[int(prm.ext_rc[r][i]) for i in range(8)] for r in range(8)]
+    int_rc = [int(prm.int_rc[r]) for r in range(22)]
+    diag = [int(prm.diag[i]) for i in range(8)]
+    perm = lambda st: pr.poseidon2_permute(ext_rc, int_rc, diag, variant, st)
+    rng = random.Random(variant)
+    for st in ([0] * 8, list(range(8)), [P - 1] * 8, [rng.randrange(P) for _ in range(8)]):
+        assert [int(x) for x in orc.poseidon2_permute(prm, np.array(st, dtype=np.uint64))] == perm(st)
+    for width, height in [(1, 1), (3, 2), (4, 4), (9, 8), (17, 16)]:
+        m = orc.fill_base(77 + width, width * height)
+        tree, root = orc.merkle_commit(prm, m, width, height)
+        rows = [[int(x) for x in m[i * width:(i + 1) * width]] for i in range(height)]
+        assert [int(x) for x in root] == pr.merkle_root(perm, rows)
+        assert [int(x) for x in tree[:4]] == pr.hash_row(perm, rows[0])
