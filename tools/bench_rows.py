@@ -1,0 +1,117 @@
+"""Secondary measurements for the other SURVEY §8 rows (not the headline bench):
+  Z     : zerocheck-shaped generic sumcheck (SURVEY §8d instance "Z": 64 base witness MLEs + 4 ext selectors,
+          200 monomial terms of degree <= 4, k = 20)  — a5 / the uniform-size part of a7
+  TOWER : CpuTowerProver::create_proof shape: 2 product specs + 1 logup spec, 2^21-point leaves (a6 + a8)
+  EQ    : build_eq_x_r, k = 24 (a3)
+  C-26  : Merkle commit of 64 columns x 2^20 rows = 2^26 base elements, placeholder Poseidon2 constants (a9)
+usage: python tools/bench_rows.py [--cpu]   (--cpu also times the oracle on the host for Z and TOWER)"""
+import json
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ceno_b200 as cb
+from ceno_b200 import api, synth
+
+P = 0xFFFFFFFF00000001
+dev = cb.Device(0)
+out = {}
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    dev.sync()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    dev.sync()
+    return (time.perf_counter() - t0) / reps * 1e3
+
+
+# ---------------------------------------------------------------- Z
+k, nb, ne, nt, deg = 20, 64, 4, 200, 4
+n = 1 << k
+rng = random.Random(1234)
+mles = [cb.MultilinearExtension.from_evaluations_vec(dev, k, synth.fill_base(100 + i, n)) for i in range(nb)]
+mles += [cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, synth.fill_ext(900 + i, n)) for i in range(ne)]
+terms = []
+for t in range(nt):
+    sel = nb + rng.randrange(ne)                       # one ext selector ...
+    wit = [rng.randrange(nb) for _ in range(rng.randint(1, deg - 1))]   # ... times 1..3 base witnesses
+    terms.append(([rng.randrange(P), rng.randrange(P)], [sel] + wit))
+z_ms = timeit(lambda: cb.IOPProverState.prove(dev, mles, terms, k, deg, transcript=cb.StandInTranscript(b"z")), reps=3, warm=1)
+factors = sum(len(t[1]) for t in terms)
+out["Z"] = {"k": k, "base_mles": nb, "ext_mles": ne, "terms": nt, "degree": deg, "ms": z_ms, "points_per_s": n / (z_ms * 1e-3),
+            "term_factor_evals_per_s": factors * n / (z_ms * 1e-3)}
+if "--cpu" in sys.argv:
+    from oracle import oracle as orc
+    host = [(synth.fill_base(100 + i, n), False, k) for i in range(nb)] + [(synth.fill_ext(900 + i, n), True, k) for i in range(ne)]
+    t0 = time.perf_counter()
+    orc.sumcheck_prove_chunked(host, terms, k, deg, orc.Transcript(b"z"))
+    out["Z"]["cpu_ms"] = (time.perf_counter() - t0) * 1e3
+    out["Z"]["cpu_threads"] = orc.num_threads()
+for m in mles:
+    m.free()
+
+# ---------------------------------------------------------------- TOWER
+nvp, nvl = 22, 21
+specs = []
+for s in range(2):
+    specs.append(cb.TowerProverSpec([cb.MultilinearExtension.from_evaluations_ext_vec(dev, nvp - 1, synth.fill_ext(50 + 2 * s + z, 1 << (nvp - 1))) for z in range(2)], nvp, False))
+specs.append(cb.TowerProverSpec([None, None] + [cb.MultilinearExtension.from_evaluations_ext_vec(dev, nvl, synth.fill_ext(60 + z, 1 << nvl)) for z in range(2)], nvl, True))
+
+
+def tower():
+    tw = cb.TowerProver(dev, specs)
+    tw.create_proof(cb.StandInTranscript(b"tower"))
+    tw.close()
+
+
+def tower_build_only():
+    tw = cb.TowerProver(dev, specs)
+    dev.sync()
+    tw.close()
+
+
+t_all, t_build = timeit(tower, reps=3, warm=1), timeit(tower_build_only, reps=3, warm=1)
+leaf_elems = 2 * (1 << nvp) + 4 * (1 << nvl)
+out["TOWER"] = {"specs": "2 product (2^21-point halves) + 1 logup (2^21 points)", "leaf_ext_elements": leaf_elems, "build_ms": t_build,
+                "build_plus_prove_ms": t_all, "layers": nvp - 1}
+for sp in specs:
+    for m in sp.leaves:
+        if m is not None:
+            m.free()
+
+# ---------------------------------------------------------------- EQ
+w = synth.fill_ext(0xE9, 24)
+eqb = dev.alloc(16 << 24)
+eq_ms = timeit(lambda: cb.build_eq_x_r_vec(dev, w, out=eqb), reps=10)
+out["EQ"] = {"k": 24, "ms": eq_ms, "GBps_written": (16 << 24) / (eq_ms * 1e-3) / 1e9}
+eqb.free()
+
+# ---------------------------------------------------------------- C-26
+width, height = 64, 1 << 20
+vals = synth.fill_base(0x9052, 8 * 8 + 22 + 8)
+api.poseidon2_set_params(dev, vals[:64].reshape(8, 8), vals[64:86], vals[86:94], 0)
+mat = dev.to_device(synth.fill_base(4242, width * height))       # column-major: column c at [c*height, (c+1)*height)
+tree = dev.alloc(32 * (2 * height - 1))
+import ctypes as C
+
+
+def commit():
+    root = np.zeros(4, np.uint64)
+    dev.check(dev.lib.cg_merkle_commit(dev.ctx, C.c_void_p(mat.ptr), width, height, 1, C.c_void_p(tree.ptr), root.ctypes.data_as(C.c_void_p), None))
+
+
+c_ms = timeit(commit, reps=5)
+perms = height * (width // 4) + height - 1
+out["C-26"] = {"width": width, "height": height, "elements": width * height, "ms": c_ms, "permutations": perms,
+               "Mperm_per_s": perms / (c_ms * 1e-3) / 1e6, "GBps_read": 8 * width * height / (c_ms * 1e-3) / 1e9,
+               "note": "placeholder constants; leaf hash + Merkle only (no RS encode)"}
+print(json.dumps(out))
+dev.close()
