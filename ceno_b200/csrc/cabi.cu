@@ -530,6 +530,9 @@ struct cg_sumcheck {
     ext_t* d_chal = nullptr;
     std::vector<void*> owned;
     int* d_error = nullptr;
+    std::vector<uint64_t> h_coeff;   // term tables stay on the host until a generic kernel needs them
+    std::vector<uint32_t> h_off, h_idx;
+    bool tables_ready = false;
     uint32_t extra_rounds = 0;     // sharded prove: replicated rounds the tail kernel runs after the all-gather
     bool extra_done = false;
     bool profile_append = false;   // sharded prove: the replicated tail appends to the local rounds' profile
@@ -599,15 +602,25 @@ static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles,
         }
     }
     if (rc == CG_OK && num_vars >= 1) rc = sc_alloc(sc, (size_t)n_mles * ws_per(n) * sizeof(ext_t), &sc->ws);
-    void* p = nullptr;
-    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(ext_t) * (n_mles + 1), &p); sc->d_final = (ext_t*)p; }
-    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(ext_t) * CG_MAX_BLOCKS * CG_MAX_DEGREE, &p); sc->out.partials = (ext_t*)p; }
-    if (rc == CG_OK) { rc = sc_alloc(sc, 256, &p); sc->out.ticket = (unsigned*)p; }
-    if (rc == CG_OK && cudaMemsetAsync(sc->out.ticket, 0, 256, st) != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "memset failed");
-    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(ext_t) * (size_t)(num_vars + 4) * degree, &p); sc->d_msgs = (ext_t*)p; }
-    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(ext_t) * (num_vars + 4), &p); sc->d_chal = (ext_t*)p; }
-    if (rc == CG_OK) { rc = sc_alloc(sc, 256, &p); sc->d_error = (int*)p; }
-    if (rc == CG_OK && cudaMemsetAsync(sc->d_error, 0, 256, st) != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "memset failed");
+    if (rc == CG_OK) {
+        // one slab for the small per-sumcheck state: [ticket | error | final | msgs | chal | partials]
+        auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        const size_t o_ticket = 0, o_err = 256, o_final = 512;
+        const size_t o_msgs = o_final + up(sizeof(ext_t) * (n_mles + 1));
+        const size_t o_chal = o_msgs + up(sizeof(ext_t) * (size_t)(num_vars + 4) * degree);
+        const size_t o_part = o_chal + up(sizeof(ext_t) * (num_vars + 4));
+        const size_t total = o_part + sizeof(ext_t) * CG_MAX_BLOCKS * CG_MAX_DEGREE;
+        void* slab = nullptr;
+        rc = sc_alloc(sc, total, &slab);
+        if (rc == CG_OK && cudaMemsetAsync(slab, 0, 512, st) != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "memset failed");
+        char* b = (char*)slab;
+        sc->out.ticket = (unsigned*)(b + o_ticket);
+        sc->d_error = (int*)(b + o_err);
+        sc->d_final = (ext_t*)(b + o_final);
+        sc->d_msgs = (ext_t*)(b + o_msgs);
+        sc->d_chal = (ext_t*)(b + o_chal);
+        sc->out.partials = (ext_t*)(b + o_part);
+    }
     if (rc == CG_OK) {
         sc->h_pinned_bytes = sizeof(ext_t) * (CG_MAX_DEGREE + 4) + sizeof(TailMailbox) + 64;
         sc->h_pinned = (uint64_t*)pinned_get(c, sc->h_pinned_bytes);
@@ -619,7 +632,8 @@ static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles,
 }
 
 // upload per-round slot tables for the generic kernels
-static int sc_upload_tables(cg_sumcheck* sc) {
+static int sc_ensure_tables(cg_sumcheck* sc) {
+    if (sc->tables_ready) return CG_OK;
     cg_ctx* c = sc->ctx;
     const uint32_t m = sc->n_mles, nv = sc->num_vars;
     std::vector<MleSlot> slots((size_t)(nv + 1) * m);
@@ -641,7 +655,15 @@ static int sc_upload_tables(cg_sumcheck* sc) {
     CHK(sc_alloc(sc, sizeof(FoldSlot) * folds.size() + 16, &p));
     sc->d_fold = (FoldSlot*)p;
     CU(c, cudaMemcpyAsync(p, folds.data(), sizeof(FoldSlot) * folds.size(), cudaMemcpyHostToDevice, sc->stream));
-    CU(c, cudaStreamSynchronize(sc->stream));   // host vectors go out of scope
+    // term tables (generic kernels only)
+    CHK(sc_alloc(sc, sizeof(ext_t) * (sc->n_terms + 1), &p)); sc->d_coeff = (ext_t*)p;
+    CHK(sc_alloc(sc, sizeof(uint32_t) * (sc->n_terms + 2), &p)); sc->d_off = (uint32_t*)p;
+    CHK(sc_alloc(sc, sizeof(uint32_t) * (sc->h_idx.size() + 1), &p)); sc->d_idx = (uint32_t*)p;
+    if (sc->n_terms) CU(c, cudaMemcpyAsync(sc->d_coeff, sc->h_coeff.data(), sizeof(ext_t) * sc->n_terms, cudaMemcpyHostToDevice, sc->stream));
+    CU(c, cudaMemcpyAsync(sc->d_off, sc->h_off.data(), sizeof(uint32_t) * (sc->n_terms + 1), cudaMemcpyHostToDevice, sc->stream));
+    if (!sc->h_idx.empty()) CU(c, cudaMemcpyAsync(sc->d_idx, sc->h_idx.data(), sizeof(uint32_t) * sc->h_idx.size(), cudaMemcpyHostToDevice, sc->stream));
+    CU(c, cudaStreamSynchronize(sc->stream));   // the local slot vectors go out of scope
+    sc->tables_ready = true;
     return CG_OK;
 }
 
@@ -660,25 +682,13 @@ CG_EXPORT int cg_sumcheck_create(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_
     CHK(sc_create_common(c, mles, n_mles, num_vars, degree, flags, st, &sc));
     sc->n_terms = n_terms;
     int rc = CG_OK;
-    void* p = nullptr;
     const uint32_t n_idx = n_terms ? off[n_terms] : 0;
-    rc = sc_alloc(sc, sizeof(ext_t) * (n_terms + 1), &p); sc->d_coeff = (ext_t*)p;
-    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(uint32_t) * (n_terms + 2), &p); sc->d_off = (uint32_t*)p; }
-    if (rc == CG_OK) { rc = sc_alloc(sc, sizeof(uint32_t) * (n_idx + 1), &p); sc->d_idx = (uint32_t*)p; }
-    if (rc == CG_OK && n_terms) {
-        // canonicalise coefficients on the host (inputs may be any u64)
-        std::vector<uint64_t> cc(2 * (size_t)n_terms);
-        for (size_t i = 0; i < cc.size(); i++) cc[i] = coeff[i] >= GL_P ? coeff[i] - GL_P : coeff[i];
-        if (cudaMemcpyAsync(sc->d_coeff, cc.data(), sizeof(ext_t) * n_terms, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-            cudaMemcpyAsync(sc->d_off, off, sizeof(uint32_t) * (n_terms + 1), cudaMemcpyHostToDevice, st) != cudaSuccess ||
-            (n_idx && cudaMemcpyAsync(sc->d_idx, idx, sizeof(uint32_t) * n_idx, cudaMemcpyHostToDevice, st) != cudaSuccess) ||
-            cudaStreamSynchronize(st) != cudaSuccess)
-            rc = set_err(c, CG_ERR_CUDA, "term table upload failed");
-    } else if (rc == CG_OK) {
-        uint32_t z = 0;
-        if (cudaMemcpyAsync(sc->d_off, &z, 4, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "upload failed");
-    }
-    if (rc == CG_OK) rc = sc_upload_tables(sc);
+    sc->h_coeff.resize(2 * (size_t)n_terms);   // canonicalised on the host (inputs may be any u64)
+    for (size_t i = 0; i < sc->h_coeff.size(); i++) sc->h_coeff[i] = coeff[i] >= GL_P ? coeff[i] - GL_P : coeff[i];
+    sc->h_off.assign(n_terms + 1, 0);
+    if (n_terms) memcpy(sc->h_off.data(), off, sizeof(uint32_t) * (n_terms + 1));
+    sc->h_idx.assign(n_idx, 0);
+    if (n_idx) memcpy(sc->h_idx.data(), idx, sizeof(uint32_t) * n_idx);
     // shape detection: one degree-3 product of three distinct ext MLEs -> tower kernel (T3)
     if (rc == CG_OK && !(flags & CG_SC_FORCE_GENERIC) && n_terms == 1 && degree == 3 && off[1] - off[0] == 3 && num_vars >= 1) {
         const uint32_t a = idx[off[0]], b = idx[off[0] + 1], d = idx[off[0] + 2];
@@ -700,6 +710,7 @@ CG_EXPORT uint32_t cg_sumcheck_round(const cg_sumcheck* sc) { return sc ? sc->ro
 
 static int launch_fold(cg_sumcheck* sc, uint32_t f) {   // fold state f -> f+1
     cg_ctx* c = sc->ctx;
+    CHK(sc_ensure_tables(sc));
     const uint64_t n_out = 1ULL << (sc->num_vars - f - 1);
     dim3 grid(grid_for(c, n_out), sc->n_mles);
     if (sc->n_mles == 0) return CG_OK;
@@ -714,6 +725,7 @@ static void launch_generic_d(cg_sumcheck* sc, const GenericArgs& a, unsigned gri
 }
 static int launch_generic_eval(cg_sumcheck* sc, uint32_t f, const RoundOut& ro) {   // evaluate state f
     cg_ctx* c = sc->ctx;
+    CHK(sc_ensure_tables(sc));
     GenericArgs a;
     a.mles = sc->d_slots + (size_t)f * sc->n_mles;
     a.coeff = sc->d_coeff;
