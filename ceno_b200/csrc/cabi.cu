@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -533,6 +534,12 @@ struct cg_sumcheck {
     std::vector<uint64_t> h_coeff;   // term tables stay on the host until a generic kernel needs them
     std::vector<uint32_t> h_off, h_idx;
     bool tables_ready = false;
+    // grouped plan (terms grouped by their round-0 ext factors), host side and device side
+    bool plan_on = false;
+    std::vector<uint32_t> p_g_term_off, p_g_ext_off, p_g_ext_idx, p_t_off, p_t_idx;
+    std::vector<uint64_t> p_t_coeff;
+    uint32_t *d_g_term_off = nullptr, *d_g_ext_off = nullptr, *d_g_ext_idx = nullptr, *d_pt_off = nullptr, *d_pt_idx = nullptr;
+    uint64_t* d_pt_coeff = nullptr;
     uint32_t extra_rounds = 0;     // sharded prove: replicated rounds the tail kernel runs after the all-gather
     bool extra_done = false;
     bool profile_append = false;   // sharded prove: the replicated tail appends to the local rounds' profile
@@ -662,6 +669,23 @@ static int sc_ensure_tables(cg_sumcheck* sc) {
     if (sc->n_terms) CU(c, cudaMemcpyAsync(sc->d_coeff, sc->h_coeff.data(), sizeof(ext_t) * sc->n_terms, cudaMemcpyHostToDevice, sc->stream));
     CU(c, cudaMemcpyAsync(sc->d_off, sc->h_off.data(), sizeof(uint32_t) * (sc->n_terms + 1), cudaMemcpyHostToDevice, sc->stream));
     if (!sc->h_idx.empty()) CU(c, cudaMemcpyAsync(sc->d_idx, sc->h_idx.data(), sizeof(uint32_t) * sc->h_idx.size(), cudaMemcpyHostToDevice, sc->stream));
+    if (sc->plan_on) {
+        auto up32 = [&](const std::vector<uint32_t>& v, uint32_t** d) -> int {
+            void* q = nullptr;
+            CHK(sc_alloc(sc, sizeof(uint32_t) * (v.size() + 1), &q));
+            *d = (uint32_t*)q;
+            if (!v.empty()) CU(c, cudaMemcpyAsync(q, v.data(), sizeof(uint32_t) * v.size(), cudaMemcpyHostToDevice, sc->stream));
+            return CG_OK;
+        };
+        CHK(up32(sc->p_g_term_off, &sc->d_g_term_off));
+        CHK(up32(sc->p_g_ext_off, &sc->d_g_ext_off));
+        CHK(up32(sc->p_g_ext_idx, &sc->d_g_ext_idx));
+        CHK(up32(sc->p_t_off, &sc->d_pt_off));
+        CHK(up32(sc->p_t_idx, &sc->d_pt_idx));
+        CHK(sc_alloc(sc, sizeof(uint64_t) * (sc->p_t_coeff.size() + 1), &p));
+        sc->d_pt_coeff = (uint64_t*)p;
+        if (!sc->p_t_coeff.empty()) CU(c, cudaMemcpyAsync(p, sc->p_t_coeff.data(), sizeof(uint64_t) * sc->p_t_coeff.size(), cudaMemcpyHostToDevice, sc->stream));
+    }
     CU(c, cudaStreamSynchronize(sc->stream));   // the local slot vectors go out of scope
     sc->tables_ready = true;
     return CG_OK;
@@ -689,6 +713,33 @@ CG_EXPORT int cg_sumcheck_create(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_
     if (n_terms) memcpy(sc->h_off.data(), off, sizeof(uint32_t) * (n_terms + 1));
     sc->h_idx.assign(n_idx, 0);
     if (n_idx) memcpy(sc->h_idx.data(), idx, sizeof(uint32_t) * n_idx);
+    // grouped plan: terms that share the same set of round-0 ext factors (selectors / eq) are summed first
+    if (rc == CG_OK && n_terms && degree <= 4) {
+        std::map<std::vector<uint32_t>, std::vector<uint32_t>> groups;   // ext-factor multiset -> term ids
+        for (uint32_t tm = 0; tm < n_terms; tm++) {
+            std::vector<uint32_t> key;
+            for (uint32_t q = off[tm]; q < off[tm + 1]; q++) if (mles[idx[q]].is_ext) key.push_back(idx[q]);
+            std::sort(key.begin(), key.end());
+            groups[key].push_back(tm);
+        }
+        sc->p_g_term_off.push_back(0);
+        sc->p_g_ext_off.push_back(0);
+        sc->p_t_off.push_back(0);
+        for (auto& kv : groups) {
+            for (uint32_t e : kv.first) sc->p_g_ext_idx.push_back(e);
+            sc->p_g_ext_off.push_back((uint32_t)sc->p_g_ext_idx.size());
+            for (uint32_t tm : kv.second) {
+                const uint64_t c0 = sc->h_coeff[2 * tm], c1 = sc->h_coeff[2 * tm + 1];
+                sc->p_t_coeff.push_back(c0);
+                sc->p_t_coeff.push_back(c1);
+                sc->p_t_coeff.push_back((uint64_t)(((unsigned __int128)c1 * 7) % GL_P));
+                for (uint32_t q = off[tm]; q < off[tm + 1]; q++) if (!mles[idx[q]].is_ext) sc->p_t_idx.push_back(idx[q]);
+                sc->p_t_off.push_back((uint32_t)sc->p_t_idx.size());
+            }
+            sc->p_g_term_off.push_back((uint32_t)sc->p_t_off.size() - 1);
+        }
+        sc->plan_on = true;
+    }
     // shape detection: one degree-3 product of three distinct ext MLEs -> tower kernel (T3)
     if (rc == CG_OK && !(flags & CG_SC_FORCE_GENERIC) && n_terms == 1 && degree == 3 && off[1] - off[0] == 3 && num_vars >= 1) {
         const uint32_t a = idx[off[0]], b = idx[off[0] + 1], d = idx[off[0] + 2];
@@ -735,6 +786,35 @@ static int launch_generic_eval(cg_sumcheck* sc, uint32_t f, const RoundOut& ro) 
     a.n_pairs = 1ULL << (sc->num_vars - f - 1);
     a.out = ro;
     const unsigned grid = grid_for(c, a.n_pairs);
+    if (sc->plan_on && !(sc->flags & CG_SC_NO_PLAN)) {
+        GroupedArgs ga;
+        ga.mles = a.mles;
+        ga.g_term_off = sc->d_g_term_off;
+        ga.g_ext_off = sc->d_g_ext_off;
+        ga.g_ext_idx = sc->d_g_ext_idx;
+        ga.t_coeff = sc->d_pt_coeff;
+        ga.t_off = sc->d_pt_off;
+        ga.t_idx = sc->d_pt_idx;
+        ga.n_groups = (uint32_t)sc->p_g_term_off.size() - 1;
+        ga.n_pairs = a.n_pairs;
+        ga.out = ro;
+        const unsigned ggrid = grid_for(c, ga.n_pairs, 2);
+#define CG_GROUPED(DD)                                                                                              \
+    do {                                                                                                            \
+        if (f == 0) grouped_round_kernel<DD, true><<<ggrid, CG_THREADS, 0, sc->stream>>>(ga);                      \
+        else grouped_round_kernel<DD, false><<<ggrid, CG_THREADS, 0, sc->stream>>>(ga);                            \
+    } while (0)
+        switch (sc->degree) {
+            case 1: CG_GROUPED(1); break;
+            case 2: CG_GROUPED(2); break;
+            case 3: CG_GROUPED(3); break;
+            default: CG_GROUPED(4); break;
+        }
+#undef CG_GROUPED
+        LAUNCHED(c);
+        CU(c, cudaGetLastError());
+        return CG_OK;
+    }
     switch (sc->degree) {
         case 1: launch_generic_d<1>(sc, a, grid); break;
         case 2: launch_generic_d<2>(sc, a, grid); break;

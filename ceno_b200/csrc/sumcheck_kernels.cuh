@@ -640,6 +640,130 @@ __global__ void __launch_bounds__(CG_THREADS) generic_round_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Grouped monomial-term evaluation (the zerocheck shape, gkr_iop/src/gkr/layer/zerocheck_layer.rs:86-207):
+//   P = sum_g [ prod_{e in E_g} e(x) ] * [ sum_{t in g} c_t prod_{w in W_t} w(x) ]
+// Terms are grouped on the host by their factors that are ext-field MLEs in round 0 (selectors / eq) — the
+// factoring the reference's CommonTermPlan performs (gkr_iop/src/gkr/layer/gpu/mod.rs:186-230).  The inner sum
+// is accumulated UNREDUCED (one reduction per group and point); in round 0 the witness products W_t are
+// base-field products (1 multiply per factor and point instead of 4); the group's last ext factor is
+// multiplied straight into the thread's compact round-sum accumulators.
+struct GroupedArgs {
+    const MleSlot* mles;          // state of every MLE this round
+    const uint32_t* g_term_off;   // [G+1] term range of group g
+    const uint32_t* g_ext_off;    // [G+1] range into g_ext_idx
+    const uint32_t* g_ext_idx;    // shared ext factors
+    const uint64_t* t_coeff;      // [T][3] = c0, c1, 7*c1 (canonical)
+    const uint32_t* t_off;        // [T+1] range into t_idx
+    const uint32_t* t_idx;        // residual (witness) factors
+    uint32_t n_groups;
+    uint64_t n_pairs;
+    RoundOut out;
+};
+template <int D, bool PHASE0>
+__global__ void __launch_bounds__(CG_THREADS, 2) grouped_round_kernel(const __grid_constant__ GroupedArgs a) {
+    ecacc H[D];
+#pragma unroll
+    for (int x = 0; x < D; x++) ecacc_zero(H[x]);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < a.n_pairs; item += stride) {
+        for (uint32_t g = 0; g < a.n_groups; g++) {
+            ecacc inner[D];
+#pragma unroll
+            for (int x = 0; x < D; x++) ecacc_zero(inner[x]);
+            const uint32_t t0 = a.g_term_off[g], t1 = a.g_term_off[g + 1];
+            for (uint32_t t = t0; t < t1; t++) {
+                const uint64_t c0 = a.t_coeff[3 * t], c1 = a.t_coeff[3 * t + 1], c1_7 = a.t_coeff[3 * t + 2];
+                const uint32_t q0 = a.t_off[t], q1 = a.t_off[t + 1];
+                if (q0 == q1) {   // constant residual: W = 1
+#pragma unroll
+                    for (int x = 0; x < D; x++) { acc_t T; acc_set64(T, c0); cacc_add(inner[x].A0, T); acc_set64(T, c1); cacc_add(inner[x].A1, T); }
+                    continue;
+                }
+                if (PHASE0) {     // witnesses are base-field: the product stays in the base field
+                    uint64_t w[D];
+                    for (uint32_t q = q0; q < q1; q++) {
+                        const MleSlot sl = a.mles[a.t_idx[q]];
+                        const ulonglong2 pr = *(reinterpret_cast<const ulonglong2*>(sl.ptr) + item);
+                        const uint64_t lo = gl_canon(pr.x);
+                        uint64_t v = gl_canon(pr.y);
+                        const uint64_t nd = gl_sub(lo, v);
+#pragma unroll
+                        for (int x = 0; x < D; x++) {
+                            w[x] = (q == q0) ? v : gl_mul_weak(w[x], v);
+                            if (x + 1 < D) v = gl_sub(v, nd);
+                        }
+                    }
+#pragma unroll
+                    for (int x = 0; x < D; x++) {
+                        acc_t T;
+                        acc_zero(T); acc_mac(T, c0, w[x]); cacc_add(inner[x].A0, T);
+                        acc_zero(T); acc_mac(T, c1, w[x]); cacc_add(inner[x].A1, T);
+                    }
+                } else {
+                    ext_t w[D];
+                    for (uint32_t q = q0; q < q1; q++) {
+                        const MleSlot sl = a.mles[a.t_idx[q]];
+                        ext_t lo, v;
+                        ld_ext2(reinterpret_cast<const ext_t*>(sl.ptr) + 2 * item, lo, v);
+                        const ext_t nd = ext_sub(lo, v);
+#pragma unroll
+                        for (int x = 0; x < D; x++) {
+                            w[x] = (q == q0) ? v : ext_mul_weak(w[x], v);
+                            if (x + 1 < D) v = ext_sub(v, nd);
+                        }
+                    }
+                    extmul_t cm; cm.c0 = c0; cm.c1 = c1; cm.c1_7 = c1_7;
+#pragma unroll
+                    for (int x = 0; x < D; x++) {
+                        eacc T;
+                        eacc_zero(T);
+                        eacc_mac_prep(T, w[x], cm);
+                        ecacc_add(inner[x], T);
+                    }
+                }
+            }
+            const uint32_t e0 = a.g_ext_off[g], e1 = a.g_ext_off[g + 1];
+            if (e0 == e1) {   // no shared ext factor: the inner sums go straight into the round sums
+#pragma unroll
+                for (int x = 0; x < D; x++) {
+                    acc_t T;
+                    acc_set64(T, cacc_weak(inner[x].A0)); cacc_add(H[x].A0, T);
+                    acc_set64(T, cacc_weak(inner[x].A1)); cacc_add(H[x].A1, T);
+                }
+                continue;
+            }
+            ext_t u[D];
+#pragma unroll
+            for (int x = 0; x < D; x++) u[x] = ext_make(cacc_weak(inner[x].A0), cacc_weak(inner[x].A1));
+            for (uint32_t q = e0; q < e1; q++) {
+                const MleSlot sl = a.mles[a.g_ext_idx[q]];
+                ext_t lo, v;
+                ld_ext2(reinterpret_cast<const ext_t*>(sl.ptr) + 2 * item, lo, v);
+                if (PHASE0) { lo = ext_canon(lo); v = ext_canon(v); }
+                const ext_t nd = ext_sub(lo, v);
+                const bool last = (q + 1 == e1);
+#pragma unroll
+                for (int x = 0; x < D; x++) {
+                    if (last) {
+                        eacc T;
+                        eacc_zero(T);
+                        eacc_mac(T, u[x], v, gl_mul7_weak(v.c1));
+                        ecacc_add(H[x], T);
+                    } else {
+                        u[x] = ext_mul_weak(u[x], v);
+                    }
+                    if (x + 1 < D) v = ext_sub(v, nd);
+                }
+            }
+        }
+    }
+    ext_t acc[D];
+#pragma unroll
+    for (int x = 0; x < D; x++) acc[x] = ecacc_canon(H[x]);
+    block_finish<D>(acc, a.out);
+}
+
+// ---------------------------------------------------------------------------------------------
 // fold of many MLEs in one launch: grid.y = MLE.  Output always ext.
 struct FoldSlot {
     const void* in;

@@ -172,8 +172,38 @@ def test_generic_terms_mixed_base_ext(dev, degree):
         terms.append(([rng.randrange(P), rng.randrange(P)], [rng.randrange(m) for _ in range(nf)]))
     terms.append(([rng.randrange(P), 0], list(range(min(degree, m)))))
     want = orc.sumcheck_prove(host, terms, k, degree, transcript=orc.Transcript(b"gen"))
-    for dc in (False, True):
-        got = cb.IOPProverState.prove(dev, mles, terms, k, degree, transcript=cb.StandInTranscript(b"gen"), device_challenger=dc)
+    for dc, flags in ((False, 0), (True, 0), (False, cb.IOPProverState.NO_PLAN)):     # grouped plan and term-by-term kernel
+        got = cb.IOPProverState.prove(dev, mles, terms, k, degree, transcript=cb.StandInTranscript(b"gen"), device_challenger=dc, flags=flags)
+        for g, w in zip(got, want):
+            assert eq_np(g, w)
+
+
+def test_zerocheck_layer_shape(dev):
+    """ZerocheckLayerProver::prove shape (gkr_iop/src/gkr/layer/cpu/mod.rs:99-239): selector eq MLEs from
+    SelectorType::compute, base-field witness columns, alpha-weighted monomial terms sel_g * prod(witness)."""
+    import ceno_b200 as cb
+    rng = random.Random(42)
+    k, n_wit = 10, 12
+    n = 1 << k
+    pt = rnd_point(77, k)
+    sel_specs = [(cb.SelectorType.WHOLE, orc.SEL_WHOLE, {}), (cb.SelectorType.PREFIX, orc.SEL_PREFIX, dict(offset=3, num_instances=700)),
+                 (cb.SelectorType.PREFIX, orc.SEL_PREFIX, dict(offset=0, num_instances=1000))]
+    wit_h = [orc.fill_base(600 + i, n) for i in range(n_wit)]
+    mles = [cb.MultilinearExtension.from_evaluations_vec(dev, k, w) for w in wit_h]
+    host = [(w, False, k) for w in wit_h]
+    for kind_d, kind_o, kw in sel_specs:
+        mles.append(cb.SelectorType.compute(dev, kind_d, pt, **kw))
+        host.append((orc.selector_compute(kind_o, pt, **kw), True, k))
+    alpha = [rng.randrange(P), rng.randrange(P)]
+    terms, apow = [], (1, 0)
+    for e in range(30):                      # alpha^e * sel_g * w_a * w_b (* w_c)
+        g = n_wit + rng.randrange(len(sel_specs))
+        ws = [rng.randrange(n_wit) for _ in range(rng.randint(1, 3))]
+        terms.append(([apow[0], apow[1]], sorted([g] + ws, reverse=True)))     # product sorted by descending witness id
+        apow = ((apow[0] * alpha[0] + 7 * apow[1] * alpha[1]) % P, (apow[0] * alpha[1] + apow[1] * alpha[0]) % P)
+    want = orc.sumcheck_prove(host, terms, k, 4, transcript=orc.Transcript(b"zc"))
+    for flags in (0, cb.IOPProverState.NO_PLAN):
+        got = cb.IOPProverState.prove(dev, mles, terms, k, 4, transcript=cb.StandInTranscript(b"zc"), flags=flags)
         for g, w in zip(got, want):
             assert eq_np(g, w)
 
