@@ -537,6 +537,8 @@ struct cg_sumcheck {
     // grouped plan (terms grouped by their round-0 ext factors), host side and device side
     bool plan_on = false;
     std::vector<uint32_t> p_g_term_off, p_g_ext_off, p_g_ext_idx, p_t_off, p_t_idx;
+    std::vector<uint32_t> pf_g_term_off, pf_g_ext_off, pf_g_ext_idx;   // fine plan: groups split into 8-term chunks
+    uint32_t *d_fg_term_off = nullptr, *d_fg_ext_off = nullptr, *d_fg_ext_idx = nullptr;
     std::vector<uint64_t> p_t_coeff;
     uint32_t *d_g_term_off = nullptr, *d_g_ext_off = nullptr, *d_g_ext_idx = nullptr, *d_pt_off = nullptr, *d_pt_idx = nullptr;
     uint64_t* d_pt_coeff = nullptr;
@@ -680,6 +682,9 @@ static int sc_ensure_tables(cg_sumcheck* sc) {
         CHK(up32(sc->p_g_term_off, &sc->d_g_term_off));
         CHK(up32(sc->p_g_ext_off, &sc->d_g_ext_off));
         CHK(up32(sc->p_g_ext_idx, &sc->d_g_ext_idx));
+        CHK(up32(sc->pf_g_term_off, &sc->d_fg_term_off));
+        CHK(up32(sc->pf_g_ext_off, &sc->d_fg_ext_off));
+        CHK(up32(sc->pf_g_ext_idx, &sc->d_fg_ext_idx));
         CHK(up32(sc->p_t_off, &sc->d_pt_off));
         CHK(up32(sc->p_t_idx, &sc->d_pt_idx));
         CHK(sc_alloc(sc, sizeof(uint64_t) * (sc->p_t_coeff.size() + 1), &p));
@@ -722,12 +727,15 @@ CG_EXPORT int cg_sumcheck_create(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_
             std::sort(key.begin(), key.end());
             groups[key].push_back(tm);
         }
+        // two plans over the same term order: whole groups (large rounds: one selector multiply per group) and
+        // groups split into chunks of 8 terms (small rounds: the chunks are spread over blockIdx.y)
         sc->p_g_term_off.push_back(0);
         sc->p_g_ext_off.push_back(0);
         sc->p_t_off.push_back(0);
+        sc->pf_g_term_off.push_back(0);
+        sc->pf_g_ext_off.push_back(0);
         for (auto& kv : groups) {
-            for (uint32_t e : kv.first) sc->p_g_ext_idx.push_back(e);
-            sc->p_g_ext_off.push_back((uint32_t)sc->p_g_ext_idx.size());
+            const uint32_t first_term = (uint32_t)sc->p_t_off.size() - 1;
             for (uint32_t tm : kv.second) {
                 const uint64_t c0 = sc->h_coeff[2 * tm], c1 = sc->h_coeff[2 * tm + 1];
                 sc->p_t_coeff.push_back(c0);
@@ -736,7 +744,15 @@ CG_EXPORT int cg_sumcheck_create(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_
                 for (uint32_t q = off[tm]; q < off[tm + 1]; q++) if (!mles[idx[q]].is_ext) sc->p_t_idx.push_back(idx[q]);
                 sc->p_t_off.push_back((uint32_t)sc->p_t_idx.size());
             }
-            sc->p_g_term_off.push_back((uint32_t)sc->p_t_off.size() - 1);
+            const uint32_t last_term = (uint32_t)sc->p_t_off.size() - 1;
+            for (uint32_t e : kv.first) sc->p_g_ext_idx.push_back(e);
+            sc->p_g_ext_off.push_back((uint32_t)sc->p_g_ext_idx.size());
+            sc->p_g_term_off.push_back(last_term);
+            for (uint32_t b = first_term; b < last_term; b += 8) {
+                for (uint32_t e : kv.first) sc->pf_g_ext_idx.push_back(e);
+                sc->pf_g_ext_off.push_back((uint32_t)sc->pf_g_ext_idx.size());
+                sc->pf_g_term_off.push_back(std::min(b + 8, last_term));
+            }
         }
         sc->plan_on = true;
     }
@@ -798,7 +814,16 @@ static int launch_generic_eval(cg_sumcheck* sc, uint32_t f, const RoundOut& ro) 
         ga.n_groups = (uint32_t)sc->p_g_term_off.size() - 1;
         ga.n_pairs = a.n_pairs;
         ga.out = ro;
-        const unsigned ggrid = grid_for(c, ga.n_pairs, 2);
+        unsigned gx = grid_for(c, ga.n_pairs, 2), gy = 1;
+        if (gx < (unsigned)c->sm_count) {   // too few items to fill the chip: spread 8-term chunks over blockIdx.y
+            ga.g_term_off = sc->d_fg_term_off;
+            ga.g_ext_off = sc->d_fg_ext_off;
+            ga.g_ext_idx = sc->d_fg_ext_idx;
+            ga.n_groups = (uint32_t)sc->pf_g_term_off.size() - 1;
+            gy = std::min<unsigned>(ga.n_groups, std::max(1u, 2u * (unsigned)c->sm_count / gx));
+            if ((uint64_t)gx * gy > CG_MAX_BLOCKS) gy = CG_MAX_BLOCKS / gx;
+        }
+        const dim3 ggrid(gx, gy);
 #define CG_GROUPED(DD)                                                                                              \
     do {                                                                                                            \
         if (f == 0) grouped_round_kernel<DD, true><<<ggrid, CG_THREADS, 0, sc->stream>>>(ga);                      \

@@ -179,12 +179,12 @@ GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out) {
         for (int x = 0; x < D; x++) {
             ext_t v = lane < n_warps ? s_part[lane][x] : ext_zero();
             v = warp_reduce_ext(v);
-            if (lane == 0) out.partials[(size_t)blockIdx.x * D + x] = v;
+            if (lane == 0) out.partials[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * D + x] = v;
         }
         if (lane == 0) {
             __threadfence();
             unsigned t = atomicAdd(out.ticket, 1u);
-            s_last = (t == gridDim.x - 1);
+            s_last = (t == gridDim.x * gridDim.y - 1);
         }
     }
     __syncthreads();
@@ -194,7 +194,7 @@ GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out) {
 #pragma unroll
     for (int x = 0; x < D; x++) {
         ext_t v = ext_zero();
-        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        for (unsigned b = threadIdx.x; b < gridDim.x * gridDim.y; b += blockDim.x) {
             const ulonglong2 p = __ldcg(reinterpret_cast<const ulonglong2*>(&out.partials[(size_t)b * D + x]));
             v = ext_add(v, ext_make(p.x, p.y));
         }
@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) grouped_round_kernel(const __gr
     for (int x = 0; x < D; x++) ecacc_zero(H[x]);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < a.n_pairs; item += stride) {
-        for (uint32_t g = 0; g < a.n_groups; g++) {
+        for (uint32_t g = blockIdx.y; g < a.n_groups; g += gridDim.y) {   // small rounds: groups spread over blockIdx.y
             ecacc inner[D];
 #pragma unroll
             for (int x = 0; x < D; x++) ecacc_zero(inner[x]);
