@@ -241,7 +241,7 @@ class IOPProverState:
     `prove(...)` mirrors IOPProverState::prove(virtual_polys, transcript) -> (proof, state);
     the step API (round_eval / bind) is what a multi-GPU or Rust-transcript host drives."""
 
-    FORCE_GENERIC, NO_FUSE, PROFILE, NO_TAIL, NO_PLAN = 1, 2, 4, 8, 16
+    FORCE_GENERIC, NO_FUSE, PROFILE, NO_TAIL, NO_PLAN, NO_MID = 1, 2, 4, 8, 16, 32
 
     def __init__(self, dev, mles, terms, num_vars, degree, flags=0):
         self.dev, self.mles, self.num_vars, self.degree = dev, mles, num_vars, degree

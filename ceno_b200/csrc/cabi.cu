@@ -531,6 +531,8 @@ struct cg_sumcheck {
     ext_t* d_chal = nullptr;
     std::vector<void*> owned;
     int* d_error = nullptr;
+    unsigned *d_mid_ticket = nullptr, *d_mid_flag = nullptr;
+    bool mid_used = false;
     std::vector<uint64_t> h_coeff;   // term tables stay on the host until a generic kernel needs them
     std::vector<uint32_t> h_off, h_idx;
     bool tables_ready = false;
@@ -625,6 +627,8 @@ static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles,
         char* b = (char*)slab;
         sc->out.ticket = (unsigned*)(b + o_ticket);
         sc->d_error = (int*)(b + o_err);
+        sc->d_mid_ticket = (unsigned*)(b + 128);
+        sc->d_mid_flag = (unsigned*)(b + 192);
         sc->d_final = (ext_t*)(b + o_final);
         sc->d_msgs = (ext_t*)(b + o_msgs);
         sc->d_chal = (ext_t*)(b + o_chal);
@@ -1094,6 +1098,82 @@ static void sc_mark_done(cg_sumcheck* sc) {
     sc->evaluated = false;
 }
 
+// ---- cooperative mid kernel (rounds between the streaming rounds and the tail)
+#define CG_MID_MAX_LOG_PAIRS 17
+// first round the tail kernel can take over, given the state at round sc->round
+static uint32_t tail_entry_round(const cg_sumcheck* sc) {
+    const uint32_t left = sc->num_vars - sc->folds;                  // log2(elements) of the current state
+    const uint32_t lim = 12 - (sc->extra_rounds < 12 ? sc->extra_rounds : 12);   // entry needs elements <= 4096 >> extra
+    const uint32_t skip = left > lim ? left - lim : 0;
+    const uint32_t jt = sc->round + skip;
+    return jt < sc->num_vars ? jt : sc->num_vars;
+}
+static bool mid_eligible(const cg_sumcheck* sc) {
+    if (!sc->tl.on || sc->mid_used || (sc->flags & (CG_SC_NO_FUSE | CG_SC_NO_TAIL | CG_SC_NO_MID))) return false;
+    if (!sc->pending || sc->folds < 1 || sc->round >= sc->num_vars) return false;
+    const uint32_t left = sc->num_vars - sc->folds;
+    if (left < 3 || left - 2 > CG_MID_MAX_LOG_PAIRS) return false;    // fused round: 2^left elements -> 2^(left-2) pairs
+    const size_t n_slots = 1 + sc->tl.prod.size() + sc->tl.lk.size();
+    if (n_slots > CG_COMM_GATHER_SLOTS) return false;
+    return tail_entry_round(sc) > sc->round;
+}
+static int launch_mid(cg_sumcheck* sc, uint64_t* d_tr_state, uint32_t* jt_out) {
+    cg_ctx* c = sc->ctx;
+    const TowerLayout& tl = sc->tl;
+    MidArgs a;
+    memset(&a, 0, sizeof(a));
+    a.t.n_prod = (int)tl.prod_alpha.size();
+    a.t.n_logup = (int)tl.lk_an.size();
+    int slot = 0;
+    auto put = [&](uint32_t mle) { a.buf_odd[slot] = (const ext_t*)mle_buf(sc, mle, 1); a.buf_even[slot] = (const ext_t*)mle_buf(sc, mle, 2); slot++; };
+    put(tl.eq);
+    for (int p = 0; p < a.t.n_prod; p++) { put(tl.prod[2 * p]); put(tl.prod[2 * p + 1]); a.t.alpha_prod[p] = tl.prod_alpha[p]; }
+    for (int l = 0; l < a.t.n_logup; l++) {
+        for (int z = 0; z < 4; z++) put(tl.lk[4 * l + z]);
+        a.t.alpha_num[l] = tl.lk_an[l];
+        a.t.alpha_den[l] = tl.lk_ad[l];
+    }
+    a.t.alpha_one = tl.alpha_one ? 1 : 0;
+    a.t.r = sc->pending_r;
+    a.t.r_ptr = sc->pending_r_ptr;
+    a.f0 = sc->folds;
+    a.log_n_in = sc->num_vars - sc->folds;
+    a.first_round = sc->round;
+    a.end_round = tail_entry_round(sc);
+    a.d_msgs = sc->d_msgs;
+    a.d_chal = sc->d_chal;
+    a.d_tr_state = d_tr_state;
+    a.mail = d_tr_state ? nullptr : sc_mailbox(sc);
+    a.d_error = sc->d_error;
+    a.timeout_cycles = 8000000000ULL;
+    comm_dev(sc->comm, a.comm, a.end_round - a.first_round);
+    a.partials = sc->out.partials;
+    a.ticket = sc->d_mid_ticket;
+    a.round_flag = sc->d_mid_flag;
+    const bool simple = a.t.n_prod == 1 && a.t.n_logup == 0 && a.t.alpha_one;
+    const void* fn = simple ? (const void*)tower_mid_kernel<true> : (const void*)tower_mid_kernel<false>;
+    int occ = 0;
+    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, CG_THREADS, 0));
+    if (occ < 1) return set_err(c, CG_ERR_CUDA, "mid kernel does not fit on an SM");
+    const uint64_t first_pairs = 1ULL << (a.log_n_in - 2);
+    uint64_t blocks = (first_pairs + CG_THREADS - 1) / CG_THREADS;
+    const uint64_t cap = (uint64_t)c->sm_count * (occ > 2 ? 2 : occ);
+    if (blocks > cap) blocks = cap;
+    void* args[] = {&a};
+    CU(c, cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(CG_THREADS), args, 0, sc->stream));
+    LAUNCHED(c);
+    // bookkeeping: the device now owns rounds [first_round, end_round); the last challenge sits in d_chal
+    const uint32_t steps = a.end_round - a.first_round;
+    sc->folds += steps;
+    sc->round = a.end_round;
+    sc->pending = true;
+    sc->pending_r_ptr = sc->d_chal + (a.end_round - 1);
+    sc->evaluated = false;
+    sc->mid_used = true;
+    *jt_out = a.end_round;
+    return CG_OK;
+}
+
 static void prof_begin(cg_sumcheck* sc) {
     if (!(sc->flags & CG_SC_PROFILE)) return;
     sc->ev.resize(2 * (size_t)sc->num_vars);
@@ -1128,20 +1208,28 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
     for (uint32_t j = 0; j < sc->num_vars; j++) {
         uint64_t* msg = h_rounds + (size_t)j * sc->degree * 2;
         prof_mark(sc, j, 0);
-        if (tail_eligible(sc)) {
-            // one persistent launch for rounds j..; the transcript stays on the host behind a mailbox
+        if (mid_eligible(sc) || tail_eligible(sc)) {
+            // the device runs every remaining round on its own (cooperative mid kernel, then the shared-memory tail
+            // kernel, both enqueued now); the transcript stays on the host and answers through the mailbox
             cg_ctx* c = sc->ctx;
             TailMailbox* mb = sc_mailbox(sc);
             if (j == 0) { mb->seq_msg = 0; mb->seq_r = 0; mb->abort = 0; }
             __sync_synchronize();
-            CHK(launch_tail(sc, nullptr, sc->d_msgs, sc->d_chal));
+            uint32_t upto = j;   // rounds [j, upto) are owned by enqueued kernels
+            bool done = false;
+            if (mid_eligible(sc)) CHK(launch_mid(sc, nullptr, &upto));
+            if (tail_eligible(sc)) {
+                CHK(launch_tail(sc, nullptr, sc->d_msgs, sc->d_chal));
+                upto = sc->num_vars + sc->extra_rounds;
+                done = true;
+            }
             int rc = CG_OK;
-            for (uint32_t jj = j; jj < sc->num_vars + sc->extra_rounds && rc == CG_OK; jj++) {
+            for (uint32_t jj = j; jj < upto && rc == CG_OK; jj++) {
                 uint64_t spins = 0;
                 while (mb->seq_msg != (uint64_t)jj + 1) {
                     if ((++spins & 0xFFFFF) == 0 && cudaStreamQuery(sc->stream) != cudaErrorNotReady) {
                         if (mb->seq_msg == (uint64_t)jj + 1) break;
-                        rc = set_err(c, CG_ERR_CUDA, "tail kernel ended before posting its round message");
+                        rc = set_err(c, CG_ERR_CUDA, "persistent kernel ended before posting its round message");
                         break;
                     }
                 }
@@ -1158,11 +1246,15 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
             }
             if (rc != CG_OK) { mb->abort = 1; __sync_synchronize(); }
             prof_mark(sc, j, 1);
-            for (uint32_t jj = j + 1; jj < sc->num_vars; jj++) { prof_mark(sc, jj, 0); prof_mark(sc, jj, 1); }
-            CU(c, cudaStreamSynchronize(sc->stream));
-            CHK(rc);
-            sc_mark_done(sc);
-            break;
+            for (uint32_t jj = j + 1; jj < sc->num_vars && jj < upto; jj++) { prof_mark(sc, jj, 0); prof_mark(sc, jj, 1); }
+            if (done || rc != CG_OK) {
+                CU(c, cudaStreamSynchronize(sc->stream));
+                CHK(rc);
+                sc_mark_done(sc);
+                break;
+            }
+            j = upto - 1;   // tail not possible (flags / shape): continue with per-round launches from round `upto`
+            continue;
         }
         {   // one launch; its last block posts the message into the host mailbox (no D2H copy + stream sync)
             cg_ctx* c = sc->ctx;
@@ -1219,6 +1311,14 @@ static int sc_run_device(cg_sumcheck* sc, uint64_t* h_state, uint64_t* h_rounds,
     prof_begin(sc);
     for (uint32_t j = 0; j < sc->num_vars; j++) {
         prof_mark(sc, j, 0);
+        if (mid_eligible(sc)) {    // one cooperative launch for the latency-bound rounds before the tail
+            uint32_t upto = j;
+            CHK(launch_mid(sc, sc->d_tr_state, &upto));
+            prof_mark(sc, j, 1);
+            for (uint32_t jj = j + 1; jj < upto; jj++) { prof_mark(sc, jj, 0); prof_mark(sc, jj, 1); }
+            j = upto - 1;
+            continue;
+        }
         if (tail_eligible(sc)) {   // one persistent launch for every remaining round
             CHK(launch_tail(sc, sc->d_tr_state, sc->d_msgs, sc->d_chal));
             prof_mark(sc, j, 1);

@@ -640,6 +640,155 @@ __global__ void __launch_bounds__(CG_THREADS) generic_round_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Mid kernel: the latency-bound rounds between the big streaming rounds and the shared-memory tail
+// (2^17 .. 2^12 pairs) run in ONE cooperative persistent launch.  Every block evaluates (and folds) its
+// grid-stride share of the round, publishes a partial, and takes a ticket; the block that draws the last
+// ticket of the round combines the partials, does the multi-GPU exchange, obtains the challenge (device
+// challenger or host mailbox), stores it and releases the round flag the other blocks spin on.  One
+// grid-wide hand-off per round replaces launch + finish + host round trip.
+struct MidArgs {
+    TowerArgs t;                    // spec counts and alphas; r / r_ptr = challenge of the pending entry fold
+    const ext_t* buf_odd[CG_COMM_GATHER_SLOTS];    // workspace of each slot: states f odd ...
+    const ext_t* buf_even[CG_COMM_GATHER_SLOTS];   // ... and f even (f >= 1; the kernel never touches caller data)
+    uint32_t f0;                    // state read by the first round (it is folded into state f0+1)
+    uint32_t log_n_in;              // log2(elements per MLE) of state f0
+    uint32_t first_round, end_round;
+    ext_t* d_msgs;                  // [round * 3]
+    ext_t* d_chal;                  // [round]
+    uint64_t* d_tr_state;           // device challenger, or nullptr -> host mailbox
+    TailMailbox* mail;
+    int* d_error;
+    unsigned long long timeout_cycles;
+    CommDev comm;                   // exchange of round j uses sequence comm.seq + (j - first_round)
+    ext_t* partials;                // [gridDim.x * 3]
+    unsigned int* ticket;           // monotonically increasing across rounds (zero on entry, reset on exit)
+    volatile unsigned int* round_flag;   // = index of the last finished round + 1
+};
+struct MidLoader {
+    const MidArgs& a;
+    uint32_t f_in;
+    extmul_t rm;
+    GL_DEV const ext_t* in(int slot) const { return (f_in & 1) ? a.buf_odd[slot] : a.buf_even[slot]; }
+    GL_DEV ext_t* out(int slot) const { return const_cast<ext_t*>((f_in & 1) ? a.buf_even[slot] : a.buf_odd[slot]); }
+    GL_DEV void eq(uint64_t item, ext_t& lo, ext_t& hi) { load_pair<true, false>(in(0), out(0), item, rm, lo, hi); }
+    GL_DEV void prod(int p, int z, uint64_t item, ext_t& lo, ext_t& hi) { const int s = 1 + 2 * p + z; load_pair<true, false>(in(s), out(s), item, rm, lo, hi); }
+    GL_DEV void lk(int l, int z, uint64_t item, ext_t& lo, ext_t& hi) { const int s = 1 + 2 * a.t.n_prod + 4 * l + z; load_pair<true, false>(in(s), out(s), item, rm, lo, hi); }
+};
+template <bool SIMPLE>
+__global__ void __launch_bounds__(CG_THREADS, 2) tower_mid_kernel(const __grid_constant__ MidArgs a) {
+    __shared__ ext_t s_part[CG_THREADS / 32][3];
+    __shared__ __align__(32) uint64_t s_msg[2 * 3 + 8];
+    __shared__ ext_t s_r;
+    __shared__ int s_flag;   // 1: this block drew the last ticket, 2: abort
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ext_t r = a.t.r_ptr ? ext_canon(ld_ext(a.t.r_ptr)) : a.t.r;
+    for (uint32_t j = a.first_round; j < a.end_round; j++) {
+        const uint32_t step = j - a.first_round;
+        MidLoader ld{a, a.f0 + step, extmul_prep(r)};
+        const uint64_t n_pairs = 1ULL << (a.log_n_in - step - 2);
+        ecacc H[3];
+        ecacc_zero(H[0]); ecacc_zero(H[1]); ecacc_zero(H[2]);
+        const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+        for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < n_pairs; item += stride)
+            tower_item<SIMPLE>(a.t, ld, item, H);
+        ext_t acc[3] = {ecacc_canon(H[0]), ecacc_canon(H[1]), ecacc_canon(H[2])};
+#pragma unroll
+        for (int x = 0; x < 3; x++) {
+            const ext_t v = warp_reduce_ext(acc[x]);
+            if (lane == 0) s_part[warp][x] = v;
+        }
+        if (threadIdx.x == 0) s_flag = 0;
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int x = 0; x < 3; x++) {
+                const ext_t v = warp_reduce_ext(lane < (CG_THREADS / 32) ? s_part[lane][x] : ext_zero());
+                if (lane == 0) a.partials[(size_t)blockIdx.x * 3 + x] = v;
+            }
+            if (lane == 0) {
+                __threadfence();   // partial + this block's folded outputs are visible before the ticket
+                const unsigned tk = atomicAdd(a.ticket, 1u);
+                if (tk == gridDim.x * (step + 1) - 1) s_flag = 1;
+            }
+        }
+        __syncthreads();
+        if (s_flag == 1) {   // last block of the round: combine, exchange, challenge, release
+            __threadfence();
+            ext_t res[3];
+#pragma unroll
+            for (int x = 0; x < 3; x++) {
+                ext_t v = ext_zero();
+                for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+                    const ulonglong2 p = __ldcg(reinterpret_cast<const ulonglong2*>(&a.partials[(size_t)b * 3 + x]));
+                    v = ext_add(v, ext_make(p.x, p.y));
+                }
+                v = warp_reduce_ext(v);
+                if (lane == 0) s_part[warp][x] = v;
+            }
+            __syncthreads();
+            if (warp == 0) {
+#pragma unroll
+                for (int x = 0; x < 3; x++) res[x] = warp_reduce_ext(lane < (CG_THREADS / 32) ? s_part[lane][x] : ext_zero());
+                if (a.comm.nranks > 1) comm_exchange<3>(res, a.comm, a.comm.seq + step, s_msg);
+                if (lane == 0) {
+                    ext_t rn = ext_zero();
+#pragma unroll
+                    for (int x = 0; x < 3; x++) a.d_msgs[(size_t)j * 3 + x] = res[x];
+                    bool abort = false;
+                    if (a.d_tr_state) {
+                        uint64_t h = *a.d_tr_state;
+#pragma unroll
+                        for (int x = 0; x < 3; x++) { cg_tr_absorb(h, res[x].c0); cg_tr_absorb(h, res[x].c1); }
+                        const uint8_t label[14] = {'I','n','t','e','r','n','a','l',' ','r','o','u','n','d'};
+                        cg_tr_append_message(h, label, 14);
+                        rn.c0 = cg_tr_squeeze(h);
+                        rn.c1 = cg_tr_squeeze(h);
+                        *a.d_tr_state = h;
+                    } else {
+                        TailMailbox* mb = a.mail;
+#pragma unroll
+                        for (int x = 0; x < 3; x++) { mb->msg[2 * x] = res[x].c0; mb->msg[2 * x + 1] = res[x].c1; }
+                        __threadfence_system();
+                        mb->seq_msg = (uint64_t)j + 1;
+                        __threadfence_system();
+                        const long long t0 = clock64();
+                        while (true) {
+                            if (mb->seq_r == (uint64_t)j + 1) {
+                                __threadfence_system();
+                                rn.c0 = gl_canon(((volatile uint64_t*)mb->r)[0]);
+                                rn.c1 = gl_canon(((volatile uint64_t*)mb->r)[1]);
+                                break;
+                            }
+                            if (mb->abort || (unsigned long long)(clock64() - t0) > a.timeout_cycles) { abort = true; *a.d_error = 1; break; }
+                        }
+                    }
+                    a.d_chal[j] = rn;
+                    __threadfence();
+                    *a.round_flag = abort ? 0xFFFFFFFFu : (j + 1);   // release
+                }
+            }
+        }
+        // every block: wait for the round to be released, pick up the challenge
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            unsigned fl;
+            while ((fl = *a.round_flag) < j + 1) {
+                if ((unsigned long long)(clock64() - t0) > 2 * a.timeout_cycles) { fl = 0xFFFFFFFFu; break; }
+            }
+            if (fl == 0xFFFFFFFFu) s_flag = 2;
+            else {
+                const ulonglong2 p = __ldcg(reinterpret_cast<const ulonglong2*>(&a.d_chal[j]));
+                s_r = ext_make(p.x, p.y);
+            }
+        }
+        __syncthreads();
+        if (s_flag == 2) return;
+        __threadfence();   // acquire: the other blocks' folded outputs (gpu-scope fence also invalidates L1)
+        r = s_r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Grouped monomial-term evaluation (the zerocheck shape, gkr_iop/src/gkr/layer/zerocheck_layer.rs:86-207):
 //   P = sum_g [ prod_{e in E_g} e(x) ] * [ sum_{t in g} c_t prod_{w in W_t} w(x) ]
 // Terms are grouped on the host by their factors that are ext-field MLEs in round 0 (selectors / eq) — the

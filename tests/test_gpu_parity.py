@@ -111,7 +111,7 @@ def t3_inputs(k, seed=0):
 
 
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 7, 10, 13, 16, 20])
-@pytest.mark.parametrize("mode", ["fused", "nofuse", "generic", "device", "notail", "device_notail"])
+@pytest.mark.parametrize("mode", ["fused", "nofuse", "generic", "device", "notail", "device_notail", "nomid", "device_nomid"])
 def test_t3_sumcheck_bit_exact(dev, k, mode):
     """BASELINE config #2 shape (eq*A*B, degree 3, all ext) — every kernel variant."""
     import ceno_b200 as cb
@@ -122,7 +122,8 @@ def test_t3_sumcheck_bit_exact(dev, k, mode):
     want = orc.sumcheck_prove([(eq, True, k), (a, True, k), (b, True, k)], terms, k, 3, transcript=orc.Transcript(b"t3"))
     mles = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, x) for x in (eq, a, b)]
     flags = {"fused": 0, "device": 0, "nofuse": cb.IOPProverState.NO_FUSE, "generic": cb.IOPProverState.FORCE_GENERIC,
-             "notail": cb.IOPProverState.NO_TAIL, "device_notail": cb.IOPProverState.NO_TAIL}[mode]
+             "notail": cb.IOPProverState.NO_TAIL, "device_notail": cb.IOPProverState.NO_TAIL,
+             "nomid": cb.IOPProverState.NO_MID, "device_nomid": cb.IOPProverState.NO_MID}[mode]
     tr = cb.StandInTranscript(b"t3")
     got = cb.IOPProverState.prove(dev, mles, terms, k, 3, transcript=tr, flags=flags, device_challenger=mode.startswith("device"))
     for g, w in zip(got, want):
