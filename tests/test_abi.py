@@ -72,3 +72,36 @@ def test_standin_transcript_host_matches_oracle():
     a.append_field_element_exts(e); b.append_ext(e)
     assert tuple(a.sample_and_append_challenge(b"Internal round")) == tuple(b.sample(b"Internal round"))
     assert int(a.state[0]) == b.state
+
+
+def _build_c_smoke():
+    import subprocess
+    from oracle import oracle as orc
+    orc.build()
+    exe = os.path.join(ROOT, "tests", "c", "abi_smoke")
+    src = os.path.join(ROOT, "tests", "c", "abi_smoke.c")
+    libdir, odir = os.path.join(ROOT, "ceno_b200", "lib"), os.path.join(ROOT, "oracle")
+    subprocess.check_call(["/usr/bin/gcc", "-O2", "-o", exe, src, "-L" + libdir, "-lceno_b200", "-L" + odir, "-lceno_oracle",
+                           "-Wl,-rpath," + libdir, "-Wl,-rpath," + odir])
+    return exe
+
+
+def test_c_consumer_links_against_the_abi(lib):
+    """A plain-C program (what a Rust extern "C" block sees) compiles and links against the header + .so.
+    Without a GPU it must report that cg_init refuses (exit 77) — no CPU fallback."""
+    import subprocess
+    import torch
+    exe = _build_c_smoke()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 77, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_c_consumer_bit_exact_on_gpu(lib):
+    import subprocess
+    exe = _build_c_smoke()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "bit-exact" in r.stdout, r.stdout + r.stderr
