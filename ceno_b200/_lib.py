@@ -46,6 +46,7 @@ SYMBOLS = [
     "cg_standin_vt", "cg_wit_infer_by_monomial_expr", "cg_profile_last",
     "cg_comm_create", "cg_comm_connect", "cg_comm_destroy", "cg_sumcheck_attach_comm", "cg_sumcheck_prove_sharded",
     "cg_poseidon2_set_params", "cg_poseidon2_permute", "cg_merkle_commit",
+    "cg_rotation_next_base_mle", "cg_rotation_selector",
 ]
 
 _lib = None
@@ -113,6 +114,8 @@ def load():
         "cg_poseidon2_set_params": (i32, [vp, vp]),
         "cg_poseidon2_permute": (i32, [vp, vp, u64, vp]),
         "cg_merkle_commit": (i32, [vp, vp, u64, u64, i32, vp, vp, vp]),
+        "cg_rotation_next_base_mle": (i32, [vp, P(CgMleDesc), u32, vp, vp]),
+        "cg_rotation_selector": (i32, [vp, vp, u64, u32, u32, vp, vp]),
         "cg_sumcheck_prove_sharded": (i32, [vp, vp, P(CgMleDesc), u32, vp, vp, vp, u32, u32, u32, u32, CHALLENGE_CB, vp, vp, vp, vp, vp, vp]),
     }
     for name in SYMBOLS:

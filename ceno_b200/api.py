@@ -438,3 +438,20 @@ def merkle_commit(dev, matrix_buf, width, height, col_major=True):
     root = np.zeros(4, np.uint64)
     dev.check(dev.lib.cg_merkle_commit(dev.ctx, C.c_void_p(matrix_buf.ptr), width, height, 1 if col_major else 0, C.c_void_p(tree.ptr), _vp(root), None))
     return tree, root
+
+
+# ------------------------------------------------------------------- rotation pre-passes (gkr_iop/src/utils.rs:19-76)
+def rotation_next_base_mle(dev, mle, cyclic_group_log2_size):
+    out = dev.alloc(8 * mle.len)
+    d = mle.desc()
+    dev.check(dev.lib.cg_rotation_next_base_mle(dev.ctx, C.byref(d), cyclic_group_log2_size, C.c_void_p(out.ptr), None))
+    dev.sync()
+    return MultilinearExtension(dev, out, mle.num_vars, False, mle.len)
+
+
+def rotation_selector(dev, eq, cyclic_subgroup_size, cyclic_group_log2_size):
+    out = dev.alloc(16 * eq.len)
+    dev.check(dev.lib.cg_rotation_selector(dev.ctx, C.c_void_p(eq.buf.ptr), eq.len, cyclic_subgroup_size, cyclic_group_log2_size,
+                                           C.c_void_p(out.ptr), None))
+    dev.sync()
+    return MultilinearExtension(dev, out, eq.num_vars, True)

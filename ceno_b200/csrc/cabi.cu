@@ -1764,3 +1764,35 @@ CG_EXPORT int cg_merkle_commit(cg_ctx* c, const uint64_t* d_matrix, uint64_t wid
     }
     return CG_OK;
 }
+
+// --------------------------------------------------------------------- rotation pre-passes (f-3)
+CG_EXPORT int cg_rotation_next_base_mle(cg_ctx* c, const cg_mle_desc* mle, uint32_t cyclic_group_log2, uint64_t* d_out, cg_stream s) {
+    if (!c || !mle || !d_out) return CG_ERR_INVALID;
+    if (cyclic_group_log2 != 5 && cyclic_group_log2 != 6) return set_err(c, CG_ERR_UNSUPPORTED, "BooleanHypercube supports 5 or 6 variables (booleanhypercube.rs:119-121)");
+    if (mle->is_ext) return set_err(c, CG_ERR_INVALID, "rotation_next_base_mle takes a base-field MLE (get_base_field_vec, utils.rs:35)");
+    const uint64_t n = mle->len;
+    if (n % (1ULL << cyclic_group_log2)) return set_err(c, CG_ERR_INVALID, "rotation: length must be a multiple of the cyclic group size");
+    CU(c, cudaSetDevice(c->device));
+    rotation_next_base_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, S(c, s)>>>((const uint64_t*)mle->dptr, d_out, n, cyclic_group_log2);
+    LAUNCHED(c);
+    CU(c, cudaGetLastError());
+    return CG_OK;
+}
+CG_EXPORT int cg_rotation_selector(cg_ctx* c, const uint64_t* d_eq_ext, uint64_t total_len, uint32_t cyclic_subgroup_size,
+                                   uint32_t cyclic_group_log2, uint64_t* d_out_ext, cg_stream s) {
+    if (!c || !d_eq_ext || !d_out_ext) return CG_ERR_INVALID;
+    if (cyclic_group_log2 != 5 && cyclic_group_log2 != 6) return set_err(c, CG_ERR_UNSUPPORTED, "BooleanHypercube supports 5 or 6 variables (booleanhypercube.rs:119-121)");
+    if (cyclic_subgroup_size > (1u << cyclic_group_log2)) return set_err(c, CG_ERR_INVALID, "cyclic_subgroup_size > cyclic_group_size (utils.rs:62)");
+    if (total_len % (1ULL << cyclic_group_log2)) return set_err(c, CG_ERR_INVALID, "rotation: length must be a multiple of the cyclic group size");
+    uint64_t keep = 0, cur = 1;
+    for (uint32_t i = 0; i < cyclic_subgroup_size; i++) {
+        keep |= 1ULL << cur;
+        cur <<= 1;
+        if (cur >> cyclic_group_log2) cur ^= (cyclic_group_log2 == 5 ? 0x25u : 0x43u);
+    }
+    CU(c, cudaSetDevice(c->device));
+    rotation_selector_kernel<<<grid_for(c, total_len, 8), CG_THREADS, 0, S(c, s)>>>((const ext_t*)d_eq_ext, (ext_t*)d_out_ext, total_len, cyclic_group_log2, keep);
+    LAUNCHED(c);
+    CU(c, cudaGetLastError());
+    return CG_OK;
+}

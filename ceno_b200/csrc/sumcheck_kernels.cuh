@@ -1048,6 +1048,29 @@ __global__ void __launch_bounds__(CG_THREADS) tower_logup_layer_kernel(const ext
         st_ext(q_out + x, ext_mul(a1, a2));
     }
 }
+// ---------------------------------------------------------------------------------------------
+// Rotation pre-passes (gkr_iop/src/utils.rs:19-76; GPU call sites rotation_next_base_mle_gpu / rotation_selector_gpu,
+// gkr_iop/src/gkr/layer/gpu/utils.rs:231-336).  The BooleanHypercube order is x -> x*X mod (X^5+X^2+1) resp.
+// (X^6+X+1) (gkr_iop/src/gkr/booleanhypercube.rs:10-118): a one-step shift register, no table needed.
+GL_DEV uint32_t bh_next(uint32_t x, uint32_t log2) {
+    x <<= 1;
+    if (x >> log2) x ^= (log2 == 5 ? 0x25u : 0x43u);
+    return x;
+}
+// out[chunk + x] = in[chunk + next(x)] for x != 0, out[chunk] = in[chunk]   (base field)
+__global__ void rotation_next_base_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, uint64_t n, uint32_t log2) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, mask = (1ULL << log2) - 1;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride) {
+        const uint32_t x = (uint32_t)(b & mask);
+        out[b] = gl_canon(in[(b & ~mask) | (x ? bh_next(x, log2) : 0u)]);
+    }
+}
+// keep[x] bit set for the first `subgroup` elements of the group
+__global__ void rotation_selector_kernel(const ext_t* __restrict__ eq, ext_t* __restrict__ out, uint64_t n, uint32_t log2, uint64_t keep) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, mask = (1ULL << log2) - 1;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride)
+        st_ext(out + b, ((keep >> (b & mask)) & 1) ? ext_canon(ld_ext(eq + b)) : ext_zero());
+}
 __global__ void fill_ext_kernel(ext_t* __restrict__ v, uint64_t n, ext_t val) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride) v[b] = val;

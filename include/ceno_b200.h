@@ -263,6 +263,14 @@ int cg_wit_infer_by_monomial_expr(cg_ctx* ctx, const cg_mle_desc* mles, uint32_t
                                   const uint32_t* term_mle_idx, uint32_t n_terms, uint32_t num_vars,
                                   uint64_t* d_out_ext, cg_stream s);
 
+/* ---- rotation pre-passes: rotation_next_base_mle / rotation_selector
+ * (gkr_iop/src/utils.rs:19-76); replace rotation_next_base_mle_gpu / rotation_selector_gpu
+ * (gkr_iop/src/gkr/layer/gpu/utils.rs:231-336).  The BooleanHypercube cyclic order (5 or 6 variables,
+ * gkr_iop/src/gkr/booleanhypercube.rs) is applied inside every chunk of 2^cyclic_group_log2 elements. */
+int cg_rotation_next_base_mle(cg_ctx* ctx, const cg_mle_desc* base_mle, uint32_t cyclic_group_log2, uint64_t* d_out_base, cg_stream s);
+int cg_rotation_selector(cg_ctx* ctx, const uint64_t* d_eq_ext, uint64_t total_len, uint32_t cyclic_subgroup_size,
+                         uint32_t cyclic_group_log2, uint64_t* d_out_ext, cg_stream s);
+
 /* ---- kernel (iii-commit): Merkle commitment over Poseidon2-Goldilocks (TraceCommitter::commit_traces ->
  * PCS::batch_commit, ceno_zkvm/src/scheme/cpu/mod.rs:559-584; GPU basefold.batch_commit_*,
  * ceno_zkvm/src/scheme/gpu/mod.rs:1062-1509).  PARITY UNPINNED: Poseidon2 round constants, the internal diagonal

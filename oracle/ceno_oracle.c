@@ -911,3 +911,46 @@ OR_API int or_merkle_commit(const or_p2_params* p, const uint64_t* matrix, uint6
     for (int i = 0; i < 4; i++) root4[i] = tree[4 * off + i];
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Rotation pre-passes: BooleanHypercube cyclic group (gkr_iop/src/gkr/booleanhypercube.rs:10-193),
+ * rotation_next_base_mle / rotation_selector (gkr_iop/src/utils.rs:19-76).  The group table is the sequence
+ * X^i mod (X^5 + X^2 + 1) resp. (X^6 + X + 1), generated here by the shift register instead of a literal table. */
+static void bh_table(uint32_t nv, uint64_t* tab) {   /* 2^nv entries: 1, X, X^2, ..., back to 1 */
+    const uint64_t modulus = nv == 5 ? 0x25 : 0x43;
+    uint64_t cur = 1;
+    for (uint64_t i = 0; i < (1ULL << nv); i++) {
+        tab[i] = cur;
+        cur <<= 1;
+        if (cur >> nv) cur ^= modulus;
+    }
+}
+OR_API int or_bh_table(uint32_t nv, uint64_t* tab) { if (nv != 5 && nv != 6) return -1; bh_table(nv, tab); return 0; }
+/* literal restatement of the reference loop (including its overwrite order) */
+OR_API int or_rotation_next_base_mle(const uint64_t* evals, uint64_t len, uint32_t log2, uint64_t* out) {
+    if (log2 != 5 && log2 != 6) return -1;
+    const uint64_t size = 1ULL << log2;
+    uint64_t idx[64];
+    bh_table(log2, idx);
+    memset(out, 0, sizeof(uint64_t) * len);
+    for (uint64_t c = 0; c + size <= len; c += size) {
+        const uint64_t* o = evals + c; uint64_t* r = out + c;
+        const uint64_t first = idx[0], last = idx[size - 1];
+        if (first == last) r[last] = o[first];
+        r[0] = o[0];
+        for (int64_t i = (int64_t)size - 2; i >= 0; i--) r[idx[i]] = o[idx[i + 1]];
+    }
+    return 0;
+}
+OR_API int or_rotation_selector(const uint64_t* eq, uint64_t total_len, uint32_t subgroup_size, uint32_t log2, uint64_t* out) {
+    if ((log2 != 5 && log2 != 6) || subgroup_size > (1u << log2)) return -1;
+    const uint64_t size = 1ULL << log2;
+    uint64_t idx[64];
+    bh_table(log2, idx);
+    memset(out, 0, sizeof(ext) * total_len);
+    for (uint64_t c = 0; c + size <= total_len; c += size)
+        for (int64_t i = (int64_t)subgroup_size - 1; i >= 0; i--) {
+            ((ext*)out)[c + idx[i]] = ((const ext*)eq)[c + idx[i]];
+        }
+    return 0;
+}

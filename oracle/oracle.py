@@ -389,3 +389,27 @@ def merkle_commit(params, matrix, width, height):
     if rc:
         raise ValueError(f"or_merkle_commit rc={rc}")
     return tree, root
+
+
+# ------------------------------------------------------------------------------- rotation (f-3)
+def bh_table(nv):
+    tab = np.zeros(1 << nv, np.uint64)
+    if lib().or_bh_table(C.c_uint32(nv), _p(tab)):
+        raise ValueError("BooleanHypercube supports 5 or 6 variables")
+    return tab
+
+
+def rotation_next_base_mle(evals, log2):
+    evals = _u64(evals)
+    out = np.zeros_like(evals)
+    if lib().or_rotation_next_base_mle(_p(evals), C.c_uint64(evals.size), C.c_uint32(log2), _p(out)):
+        raise ValueError("rotation_next_base_mle: bad group size")
+    return out
+
+
+def rotation_selector(eq, subgroup_size, log2):
+    eq = _u64(eq)
+    out = np.zeros_like(eq)
+    if lib().or_rotation_selector(_p(eq), C.c_uint64(eq.size // 2), C.c_uint32(subgroup_size), C.c_uint32(log2), _p(out)):
+        raise ValueError("rotation_selector: bad arguments")
+    return out

@@ -461,3 +461,20 @@ def test_poseidon2_and_merkle_commit(dev, variant):
             assert eq_np(tree.to_host(), tree_w)
             tree.free()
         rm.free(); cm.free()
+
+
+# ------------------------------------------------------------------- rotation pre-passes (f-3)
+@pytest.mark.parametrize("log2", [5, 6])
+def test_rotation_prepasses(dev, log2):
+    import ceno_b200 as cb
+    from ceno_b200 import api
+    k = 12
+    base = orc.fill_base(3 + log2, 1 << k)
+    m = cb.MultilinearExtension.from_evaluations_vec(dev, k, base)
+    assert eq_np(api.rotation_next_base_mle(dev, m, log2).evaluations(), orc.rotation_next_base_mle(base, log2))
+    pt = rnd_point(9, k)
+    eq = cb.build_eq_x_r_vec(dev, pt)
+    for sub in (1, 23, (1 << log2) - 1, 1 << log2):
+        assert eq_np(api.rotation_selector(dev, eq, sub, log2).evaluations(), orc.rotation_selector(orc.build_eq_x_r_vec(pt), sub, log2))
+    with pytest.raises(cb.CenoB200Error):
+        api.rotation_next_base_mle(dev, m, 4)      # BooleanHypercube::new asserts 5 or 6

@@ -393,3 +393,35 @@ def test_poseidon2_and_merkle_vs_bigint_restatement(variant):
         rows = [[int(x) for x in m[i * width:(i + 1) * width]] for i in range(height)]
         assert [int(x) for x in root] == pr.merkle_root(perm, rows)
         assert [int(x) for x in tree[:4]] == pr.hash_row(perm, rows[0])
+
+
+@pytest.mark.parametrize("nv", [5, 6])
+def test_kat_rotation_next_base_mle_eval(nv):
+    """gkr_iop/src/utils.rs:343-365 (test_rotation_next_base_mle_eval) + get_rotation_points
+    (gkr_iop/src/gkr/booleanhypercube.rs:124-163): rotated(point) = (1 - r_top) poly(left) + r_top poly(right)."""
+    rng = random.Random(nv)
+    total_vars = nv + 2
+    poly = np.arange(1 << total_vars, dtype=np.uint64)
+    rotated = orc.rotation_next_base_mle(poly, nv)
+    tab = [int(x) for x in orc.bh_table(nv)]
+    assert len(set(tab[:-1])) == (1 << nv) - 1 and tab[0] == tab[-1] == 1       # booleanhypercube.rs:196-242
+    pt = [rnd_ext(rng) for _ in range(total_vars)]
+    one_minus = lambda e: ((1 - e[0]) % P, (-e[1]) % P)
+    if nv == 5:
+        left = [pr.ZERO] + pt[:4] + pt[5:]
+        right = [pr.ONE, pt[0], one_minus(pt[1])] + pt[2:4] + pt[5:]
+    else:
+        left = [pr.ZERO] + pt[:5] + pt[6:]
+        right = [pr.ONE, one_minus(pt[0]), pt[1]] + pt[2:5] + pt[6:]
+    left, right = left[:total_vars], right[:total_vars]
+    ev = lambda arr, p: tuple(int(x) for x in orc.mle_evaluate(arr, False, ext_arr(p)))
+    top = pt[nv - 1]
+    want = pr.eadd(pr.emul(one_minus(top), ev(poly, left)), pr.emul(top, ev(poly, right)))
+    assert ev(rotated, pt) == want
+    # rotation_selector keeps exactly the first `subgroup` group elements of every chunk (utils.rs:54-76)
+    eq = orc.build_eq_x_r_vec(ext_arr(pt))
+    sel = pr.to_pairs(orc.rotation_selector(eq, 23, nv))
+    eqp = pr.to_pairs(eq)
+    keep = set(tab[:23])
+    for b in range(1 << total_vars):
+        assert sel[b] == (eqp[b] if (b & ((1 << nv) - 1)) in keep else pr.ZERO)
