@@ -166,6 +166,26 @@ class MultilinearExtension:
         self.buf.free()
 
 
+class EqPolynomial:
+    """Virtual eq(w, .) MLE (cg_mle_desc kind CG_MLE_EQ): the prover receives the point instead of the
+    2^k table build_eq_x_r_vec(w) would produce, with identical round messages and final evaluation.
+    The role of the reference's virtual device MLEs (ceno_zkvm/src/scheme/gpu/mod.rs:2195-2268)."""
+
+    is_ext = True
+
+    def __init__(self, dev, w):
+        self.dev = dev
+        self.w = _u64(w).copy()
+        self.num_vars = self.w.size // 2
+        self.len = 1 << self.num_vars
+
+    def desc(self):
+        return _lib.CgMleDesc(self.w.ctypes.data, 0, self.num_vars, 2)
+
+    def free(self):
+        pass
+
+
 def build_eq_x_r_vec(dev, r, offset=0, num_instances=None, stream=None, out=None):
     """eq table of point r (k ext) as a device ext MLE; optional prefix mask (build_mle_as_ceno).
     With `stream` (a cudaStream_t handle) the call is asynchronous on that stream."""

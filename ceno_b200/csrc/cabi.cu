@@ -503,6 +503,17 @@ struct TowerLayout {           // MLE indices of the specialised (tower-shaped) 
     std::vector<ext_t> lk_an, lk_ad;
     bool alpha_one = false;
 };
+struct VeqState {               // a virtual eq MLE (CG_MLE_EQ) handled by the split-eq kernels
+    bool split = false;         // split rounds active: the eq state is not materialised yet
+    bool have = false;          // a virtual eq was declared (point recorded)
+    uint32_t idx = 0;           // its MLE index
+    uint32_t J = 0;             // rounds 0 .. J-1 are split rounds
+    std::vector<uint64_t> h_point;
+    ext_t* d_w = nullptr;       // the point on the device
+    ext_t* d_prefix = nullptr;  // P_folds = prod_{i < folds} eq(w_i, r_i)
+    ulonglong4 *d_L = nullptr, *d_H = nullptr;
+    uint64_t h_off[CG_VEQ_MAX_ROUNDS + 1] = {0};
+};
 struct cg_sumcheck {
     cg_ctx* ctx = nullptr;
     cudaStream_t stream = nullptr;
@@ -515,6 +526,7 @@ struct cg_sumcheck {
     const ext_t* pending_r_ptr = nullptr;   // device challenger: challenge lives on the device
     std::vector<MleState> mles;
     TowerLayout tl;
+    VeqState veq;
     // device state
     void* ws = nullptr;        // workspace: per MLE [n/2 | n/4] ext
     ext_t* d_final = nullptr;  // n_mles ext
@@ -577,6 +589,71 @@ CG_EXPORT int cg_sumcheck_destroy(cg_sumcheck* sc) {
     return CG_OK;
 }
 
+// virtual eq -> ordinary table (shapes / flags the split-eq kernels do not cover)
+static int veq_build_full(cg_sumcheck* sc, uint32_t i, const uint64_t* h_point) {
+    void* buf = nullptr;
+    CHK(sc_alloc(sc, sizeof(ext_t) << sc->num_vars, &buf));
+    CHK(cg_build_eq(sc->ctx, h_point, sc->num_vars, (uint64_t*)buf, 0, 1ULL << sc->num_vars, (cg_stream)sc->stream));
+    sc->mles[i].orig = buf;
+    sc->mles[i].orig_is_ext = 1;
+    return CG_OK;
+}
+// split mode: upload the point, build every round's L/H tables in one launch
+static int veq_setup_split(cg_sumcheck* sc) {
+    cg_ctx* c = sc->ctx;
+    VeqState& v = sc->veq;
+    const uint32_t k = sc->num_vars;
+    v.J = k - 18;   // rounds with >= 2^17 pairs; the cooperative mid kernel takes over after them
+    if (v.J > CG_VEQ_MAX_ROUNDS) v.J = CG_VEQ_MAX_ROUNDS;
+    v.h_off[0] = 0;
+    for (uint32_t j = 0; j < v.J; j++) v.h_off[j + 1] = v.h_off[j] + (1ULL << (k - j - 1 - CG_VEQ_LO_BITS));
+    void* p = nullptr;
+    CHK(sc_alloc(sc, sizeof(ext_t) * k + 256, &p));
+    v.d_w = (ext_t*)p;
+    v.d_prefix = (ext_t*)((char*)p + ((sizeof(ext_t) * k + 63) & ~(size_t)63));
+    CU(c, cudaMemcpyAsync(v.d_w, v.h_point.data(), sizeof(ext_t) * k, cudaMemcpyHostToDevice, sc->stream));
+    static const uint64_t one[2] = {1, 0};
+    CU(c, cudaMemcpyAsync(v.d_prefix, one, sizeof(one), cudaMemcpyHostToDevice, sc->stream));
+    CHK(sc_alloc(sc, sizeof(ulonglong4) * ((size_t)v.J << CG_VEQ_LO_BITS), &p));
+    v.d_L = (ulonglong4*)p;
+    CHK(sc_alloc(sc, sizeof(ulonglong4) * v.h_off[v.J], &p));
+    v.d_H = (ulonglong4*)p;
+    VeqTabArgs a;
+    memset(&a, 0, sizeof(a));
+    a.w = v.d_w; a.k = k; a.J = v.J; a.L = v.d_L; a.H = v.d_H;
+    for (uint32_t j = 0; j <= v.J; j++) a.h_off[j] = v.h_off[j];
+    veq_tables_kernel<<<grid_for(c, ((uint64_t)v.J << CG_VEQ_LO_BITS) + v.h_off[v.J], 8), CG_THREADS, 0, sc->stream>>>(a);
+    LAUNCHED(c);
+    CU(c, cudaGetLastError());
+    v.split = true;
+    return CG_OK;
+}
+static const void* mle_buf(const cg_sumcheck* sc, uint32_t i, uint32_t f);
+// leave split mode: write the eq state of fold level sc->folds where a materialised table would be now
+static int veq_leave_split(cg_sumcheck* sc) {
+    cg_ctx* c = sc->ctx;
+    VeqState& v = sc->veq;
+    if (!v.split) return CG_OK;
+    const uint32_t f = sc->folds;
+    const uint64_t n = 1ULL << (sc->num_vars - f);
+    if (f == 0) {   // nothing bound yet: the plain table
+        CHK(veq_build_full(sc, v.idx, v.h_point.data()));
+    } else {
+        if (f > v.J) return set_err(c, CG_ERR_STATE, "split-eq: no tables for this fold level");
+        const uint32_t j = f - 1;   // tables of round j cover variables [j+1, k) = [f, k)
+        veq_materialise_kernel<<<grid_for(c, n / 2, 8), CG_THREADS, 0, sc->stream>>>(v.d_L + ((size_t)j << CG_VEQ_LO_BITS), v.d_H + v.h_off[j],
+                                                                                  v.d_prefix, n, (ext_t*)mle_buf(sc, v.idx, f));
+        LAUNCHED(c);
+        CU(c, cudaGetLastError());
+    }
+    v.split = false;
+    return CG_OK;
+}
+static int veq_prepare(cg_sumcheck* sc) {   // before evaluating round sc->round
+    if (sc->veq.split && sc->round >= sc->veq.J) return veq_leave_split(sc);
+    return CG_OK;
+}
+
 static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, uint32_t num_vars, uint32_t degree,
                             uint32_t flags, cudaStream_t st, cg_sumcheck** out) {
     if (!c || !out || (n_mles && !mles)) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: null argument");
@@ -586,6 +663,11 @@ static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles,
         if (mles[i].num_vars != num_vars)
             return set_err(c, CG_ERR_UNSUPPORTED,
                            "mixed num_vars (frontloaded batched sumcheck) is defined only in the un-vendored upstream crate (SURVEY §C-1)");
+        if (mles[i].is_ext == CG_MLE_EQ) {   // virtual eq: dptr is the HOST point
+            if (!mles[i].dptr && num_vars) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: virtual eq MLE without a point");
+            continue;
+        }
+        if (mles[i].is_ext > CG_MLE_EQ) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: unknown MLE kind");
         if (!mles[i].dptr || mles[i].len > (1ULL << num_vars) || ((uintptr_t)mles[i].dptr & 15))
             return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: MLE pointer null/unaligned or len > 2^num_vars");
     }
@@ -601,6 +683,20 @@ static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles,
     const uint64_t n = 1ULL << num_vars;
     int rc = CG_OK;
     for (uint32_t i = 0; i < n_mles && rc == CG_OK; i++) {
+        if (mles[i].is_ext == CG_MLE_EQ) {
+            sc->mles[i].orig = nullptr;
+            sc->mles[i].orig_is_ext = 1;
+            const uint64_t* pt = (const uint64_t*)mles[i].dptr;
+            if (!sc->veq.have) {   // the first one may run split-eq rounds (decided once the term shape is known)
+                sc->veq.have = true;
+                sc->veq.idx = i;
+                sc->veq.h_point.resize(2 * (size_t)num_vars);
+                for (size_t q = 0; q < sc->veq.h_point.size(); q++) sc->veq.h_point[q] = pt[q] >= GL_P ? pt[q] - GL_P : pt[q];
+            } else {
+                rc = veq_build_full(sc, i, pt);
+            }
+            continue;
+        }
         sc->mles[i].orig = mles[i].dptr;
         sc->mles[i].orig_is_ext = mles[i].is_ext ? 1 : 0;
         const size_t es = mles[i].is_ext ? 16 : 8;
@@ -767,10 +863,17 @@ CG_EXPORT int cg_sumcheck_create(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_
             sc->tl.on = true;
             sc->tl.eq = a;
             sc->tl.prod = {b, d};
+            if (sc->veq.have && sc->veq.idx == b) { sc->tl.eq = b; sc->tl.prod = {a, d}; }   // the factors commute:
+            if (sc->veq.have && sc->veq.idx == d) { sc->tl.eq = d; sc->tl.prod = {a, b}; }   // the virtual eq takes the eq slot
             ext_t al = ext_t{coeff[0] >= GL_P ? coeff[0] - GL_P : coeff[0], coeff[1] >= GL_P ? coeff[1] - GL_P : coeff[1]};
             sc->tl.prod_alpha = {al};
             sc->tl.alpha_one = (al.c0 == 1 && al.c1 == 0);
         }
+    }
+    if (rc == CG_OK && sc->veq.have) {
+        const bool split_ok = sc->tl.on && sc->tl.eq == sc->veq.idx && sc->tl.alpha_one && sc->tl.prod.size() == 2 && sc->tl.lk.empty() &&
+                              !(flags & (CG_SC_NO_FUSE | CG_SC_FORCE_GENERIC)) && num_vars >= 20 && num_vars <= 32;
+        rc = split_ok ? veq_setup_split(sc) : veq_build_full(sc, sc->veq.idx, sc->veq.h_point.data());
     }
     if (rc != CG_OK) { cg_sumcheck_destroy(sc); return rc; }
     *out = sc;
@@ -858,8 +961,49 @@ static int launch_generic_eval(cg_sumcheck* sc, uint32_t f, const RoundOut& ro) 
     CU(c, cudaGetLastError());
     return CG_OK;
 }
+// split-eq round (virtual eq): evaluate state f, folding f-1 -> f first when `fold`
+static int launch_veq(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro) {
+    cg_ctx* c = sc->ctx;
+    const VeqState& v = sc->veq;
+    VeqArgs a;
+    memset(&a, 0, sizeof(a));
+    const uint32_t src = fold ? f - 1 : f;
+    for (int z = 0; z < 2; z++) {
+        a.in[z] = (const ext_t*)mle_buf(sc, sc->tl.prod[z], src);
+        a.out[z] = fold ? (ext_t*)mle_buf(sc, sc->tl.prod[z], f) : nullptr;
+    }
+    a.L = v.d_L + ((size_t)f << CG_VEQ_LO_BITS);
+    a.H = v.d_H + v.h_off[f];
+    a.n_rows = 1ULL << (sc->num_vars - f - 1 - CG_VEQ_LO_BITS);
+    a.r = sc->pending_r;
+    a.r_ptr = sc->pending_r_ptr;
+    a.fin.w = v.d_w;
+    a.fin.prefix = v.d_prefix;
+    a.fin.round = f;
+    a.fin.fold = fold ? 1 : 0;
+    a.fin.r = sc->pending_r;
+    a.fin.r_ptr = sc->pending_r_ptr;
+    a.out_ = ro;
+    static const int minb = []() { const char* e = getenv("CG_VEQ_MINB"); const int x = e ? atoi(e) : 2; return x == 1 || x == 3 ? x : 2; }();
+    uint64_t blocks = (uint64_t)c->sm_count * minb;
+    if (blocks > a.n_rows) blocks = a.n_rows;
+    const unsigned grid = (unsigned)blocks;
+    const bool canon = (src == 0);
+#define CG_VEQ_LAUNCH(MB)                                                                        \
+    do {                                                                                         \
+        if (!fold) veq_round_kernel<false, false, MB><<<grid, 256, 0, sc->stream>>>(a);          \
+        else if (canon) veq_round_kernel<true, true, MB><<<grid, 256, 0, sc->stream>>>(a);       \
+        else veq_round_kernel<true, false, MB><<<grid, 256, 0, sc->stream>>>(a);                 \
+    } while (0)
+    if (minb == 1) CG_VEQ_LAUNCH(1); else if (minb == 3) CG_VEQ_LAUNCH(3); else CG_VEQ_LAUNCH(2);
+#undef CG_VEQ_LAUNCH
+    LAUNCHED(c);
+    CU(c, cudaGetLastError());
+    return CG_OK;
+}
 // tower-shaped kernel: evaluate state f (fold==false) or fold f-1 -> f and evaluate (fold==true)
 static int launch_tower(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro) {
+    if (sc->veq.split) return launch_veq(sc, f, fold, ro);
     cg_ctx* c = sc->ctx;
     const TowerLayout& tl = sc->tl;
     TowerArgs a;
@@ -917,6 +1061,7 @@ static int launch_tower(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& 
 // enqueue the kernels of the current round's evaluation (applying a pending fold first)
 static int sc_enqueue_round(cg_sumcheck* sc, const RoundOut& ro) {
     if (sc->round >= sc->num_vars) return set_err(sc->ctx, CG_ERR_STATE, "round_eval: all variables are already bound");
+    CHK(veq_prepare(sc));
     if (sc->pending) {
         const uint32_t f = sc->folds;   // fold f -> f+1, then evaluate state f+1
         if (sc->tl.on && !(sc->flags & CG_SC_NO_FUSE)) {
@@ -944,6 +1089,7 @@ static RoundOut make_ro(cg_sumcheck* sc) {
 CG_EXPORT int cg_sumcheck_attach_comm(cg_sumcheck* sc, cg_comm* cm) {
     if (!sc) return CG_ERR_INVALID;
     if (sc->round != 0 || sc->evaluated) return set_err(sc->ctx, CG_ERR_STATE, "attach_comm: must be called before the first round");
+    if (sc->veq.have && cm) return set_err(sc->ctx, CG_ERR_UNSUPPORTED, "attach_comm: virtual eq MLEs are not supported with a comm yet");
     sc->comm = cm;
     return CG_OK;
 }
@@ -964,6 +1110,7 @@ CG_EXPORT int cg_sumcheck_round_eval(cg_sumcheck* sc, uint64_t* h_out) {
 
 static int sc_apply_pending_fold_only(cg_sumcheck* sc) {
     if (!sc->pending) return CG_OK;
+    CHK(veq_leave_split(sc));   // a fold without an evaluation cannot advance the split-eq prefix
     CHK(launch_fold(sc, sc->folds));
     sc->folds++;
     sc->pending = false;
@@ -1011,6 +1158,7 @@ CG_EXPORT int cg_sumcheck_final_evals(cg_sumcheck* sc, uint64_t* h_out) {
 CG_EXPORT int cg_sumcheck_peek(cg_sumcheck* sc, uint32_t i, const void** dptr, uint64_t* len, uint32_t* is_ext) {
     if (!sc || i >= sc->n_mles) return CG_ERR_INVALID;
     CHK(sc_apply_pending_fold_only(sc));
+    CHK(veq_leave_split(sc));
     CU(sc->ctx, cudaStreamSynchronize(sc->stream));
     const uint32_t f = sc->folds;
     if (dptr) *dptr = (f == sc->num_vars && f > 0) ? (const void*)(sc->d_final + i) : mle_buf(sc, i, f);
@@ -1025,6 +1173,7 @@ static TailMailbox* sc_mailbox(cg_sumcheck* sc) {
     return (TailMailbox*)((char*)sc->h_pinned + ((sizeof(ext_t) * (CG_MAX_DEGREE + 4) + 63) & ~(size_t)63));
 }
 static bool tail_eligible(const cg_sumcheck* sc) {
+    if (sc->veq.split) return false;
     if (!sc->tl.on || (sc->flags & (CG_SC_NO_FUSE | CG_SC_NO_TAIL)) || sc->round >= sc->num_vars) return false;
     const uint64_t cur = 1ULL << (sc->num_vars - sc->folds);
     const uint64_t n_loc = sc->pending ? cur / 2 : cur;
@@ -1109,6 +1258,7 @@ static uint32_t tail_entry_round(const cg_sumcheck* sc) {
     return jt < sc->num_vars ? jt : sc->num_vars;
 }
 static bool mid_eligible(const cg_sumcheck* sc) {
+    if (sc->veq.split) return false;
     if (!sc->tl.on || sc->mid_used || (sc->flags & (CG_SC_NO_FUSE | CG_SC_NO_TAIL | CG_SC_NO_MID))) return false;
     if (!sc->pending || sc->folds < 1 || sc->round >= sc->num_vars) return false;
     const uint32_t left = sc->num_vars - sc->folds;
@@ -1208,6 +1358,7 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
     for (uint32_t j = 0; j < sc->num_vars; j++) {
         uint64_t* msg = h_rounds + (size_t)j * sc->degree * 2;
         prof_mark(sc, j, 0);
+        CHK(veq_prepare(sc));
         if (mid_eligible(sc) || tail_eligible(sc)) {
             // the device runs every remaining round on its own (cooperative mid kernel, then the shared-memory tail
             // kernel, both enqueued now); the transcript stays on the host and answers through the mailbox
@@ -1311,6 +1462,7 @@ static int sc_run_device(cg_sumcheck* sc, uint64_t* h_state, uint64_t* h_rounds,
     prof_begin(sc);
     for (uint32_t j = 0; j < sc->num_vars; j++) {
         prof_mark(sc, j, 0);
+        CHK(veq_prepare(sc));
         if (mid_eligible(sc)) {    // one cooperative launch for the latency-bound rounds before the tail
             uint32_t upto = j;
             CHK(launch_mid(sc, sc->d_tr_state, &upto));
@@ -1375,6 +1527,8 @@ CG_EXPORT int cg_sumcheck_prove_sharded(cg_ctx* c, cg_comm* cm, const cg_mle_des
     while ((1 << g) < cm->nranks) g++;
     if (num_vars_global < (uint32_t)g) return set_err(c, CG_ERR_INVALID, "fewer variables than log2(ranks)");
     if (n_mles > CG_COMM_GATHER_MLES) return set_err(c, CG_ERR_UNSUPPORTED, "sharded prove supports at most 64 MLEs");
+    for (uint32_t i = 0; i < n_mles; i++)
+        if (mles && mles[i].is_ext == CG_MLE_EQ) return set_err(c, CG_ERR_UNSUPPORTED, "sharded prove: virtual eq MLEs are not supported yet (pass the slice of the table)");
     const uint32_t k_local = num_vars_global - g;
     cudaStream_t st = S(c, s);
     cg_sumcheck* sc = nullptr;
@@ -1430,6 +1584,7 @@ CG_EXPORT int cg_fix_variable(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mle
     if (nv == 0) return set_err(c, CG_ERR_INVALID, "cg_fix_variable: MLE has no variables");
     std::vector<FoldSlot> slots(n_mles);
     for (uint32_t i = 0; i < n_mles; i++) {
+        if (mles[i].is_ext > CG_MLE_EXT) return set_err(c, CG_ERR_INVALID, "cg_fix_variable: dense MLEs only");
         if (mles[i].num_vars != nv) return set_err(c, CG_ERR_INVALID, "cg_fix_variable: all MLEs must have the same num_vars");
         if (mles[i].len != (1ULL << nv)) return set_err(c, CG_ERR_UNSUPPORTED, "cg_fix_variable: len must equal 2^num_vars");
         if (((uintptr_t)mles[i].dptr & 31) || ((uintptr_t)d_out[i] & 15)) return set_err(c, CG_ERR_INVALID, "cg_fix_variable: pointers must be 32-byte (in) / 16-byte (out) aligned");
@@ -1466,6 +1621,7 @@ CG_EXPORT int cg_wit_infer_by_monomial_expr(cg_ctx* c, const cg_mle_desc* mles, 
     const uint64_t n = 1ULL << num_vars;
     std::vector<MleSlot> slots(n_mles ? n_mles : 1);
     for (uint32_t i = 0; i < n_mles; i++) {
+        if (mles[i].is_ext > CG_MLE_EXT) return set_err(c, CG_ERR_INVALID, "wit_infer: dense MLEs only");
         if (mles[i].num_vars != num_vars || mles[i].len != n) return set_err(c, CG_ERR_UNSUPPORTED, "wit_infer: every MLE must be full length 2^num_vars");
         slots[i] = MleSlot{mles[i].dptr, mles[i].is_ext ? 1u : 0u, 1u};
     }

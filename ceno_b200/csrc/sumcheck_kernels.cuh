@@ -162,8 +162,14 @@ struct RoundOut {
     uint64_t mail_seq;
 };
 
-template <int D>
-GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out) {
+struct NoXf {
+    template <int D>
+    GL_DEV void operator()(ext_t (&)[D]) const {}
+};
+// xf: transform applied by lane 0 of the last block to the combined local sums before the multi-GPU
+// exchange and the output (the split-eq kernels turn their three bilinear sums into the round message).
+template <int D, class XF = NoXf>
+GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out, const XF xf = XF()) {
     __shared__ ext_t s_part[CG_THREADS / 32][D];   // blockDim.x <= CG_THREADS
     __shared__ __align__(32) uint64_t s_msg[2 * D + 8];
     __shared__ bool s_last;
@@ -209,6 +215,7 @@ GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out) {
             ext_t v = lane < n_warps ? s_part[lane][x] : ext_zero();
             res[x] = warp_reduce_ext(v);
         }
+        if (lane == 0) xf(res);
         if (out.comm.nranks > 1) comm_exchange<D>(res, out.comm, out.comm.seq, s_msg);
         if (lane == 0) {
 #pragma unroll
@@ -394,6 +401,155 @@ __global__ void __launch_bounds__(THREADS, MINB) tower_round_kernel(const __grid
         tower_item<SIMPLE>(a, ld, item, H);
     ext_t acc[3] = {ecacc_canon(H[0]), ecacc_canon(H[1]), ecacc_canon(H[2])};
     block_finish<3>(acc, a.out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split-eq rounds for a VIRTUAL eq MLE (cg_mle_desc kind CG_MLE_EQ: the caller hands over the point w
+// instead of the 2^k table).  With  eq(w, (r_0..r_{j-1}, X, x)) = P_j * eq(w_j, X) * E_j(x),
+//   P_j = prod_{i<j} eq(w_i, r_i),   E_j(x) = eq(w_{j+1..k-1}, x) = L_j[x & 255] * H_j[x >> 8],
+// the round polynomial is  p_j(X) = P_j eq(w_j, X) q_j(X),  q_j(X) = sum_x E_j(x) A(X, x) B(X, x)  (degree 2).
+// The kernel never streams or folds an eq table: per pair it weights A by the row weight H_j[x >> 8]
+// (uniform over the block), accumulates the three bilinear sums
+//   S00 = sum A'lo Blo,  S11 = sum A'hi Bhi,  Sx = sum (A'lo Bhi + A'hi Blo)
+// UNREDUCED and without a single modular subtraction, applies the thread's fixed L_j[tid] once at the
+// end, and the last block turns (S00, S11, Sx) into [p_j(1), p_j(2), p_j(3)]:
+//   q(0) = S00, q(1) = S11, X^2 coefficient c2 = S00 + S11 - Sx.
+// Field arithmetic is exact, so the message is bit-identical to the one computed from a materialised
+// eq table (IOPProverState semantics); this is the eq handling of the reference's
+// tower/zerocheck sumchecks (ceno_zkvm/src/scheme/cpu/mod.rs:417-485) without the eq stream.
+#define CG_VEQ_MAX_ROUNDS 16
+#define CG_VEQ_LO_BITS 8
+struct VeqFin {
+    const ext_t* w;        // device: the point (num_vars ext)
+    ext_t* prefix;         // device scalar: P_{j-1} on entry when `fold`, P_j otherwise (includes a rank factor when sharded)
+    uint32_t round;        // j
+    int fold;              // this launch folds by r_{j-1}: P_j = P_{j-1} eq(w_{j-1}, r_{j-1}) is stored back
+    ext_t r;
+    const ext_t* r_ptr;
+    GL_DEV void operator()(ext_t (&res)[3]) const {
+        ext_t P = ext_canon(*prefix);
+        const ext_t one = ext_one();
+        if (fold) {
+            const ext_t rr = ext_canon(r_ptr ? ld_ext(r_ptr) : r), wp = ext_canon(w[round - 1]);
+            P = ext_mul(P, ext_add(ext_mul(ext_sub(one, wp), ext_sub(one, rr)), ext_mul(wp, rr)));
+            *prefix = P;
+        }
+        const ext_t wj = ext_canon(w[round]);
+        const ext_t q0 = res[0], q1 = res[1];
+        const ext_t c2 = ext_sub(ext_add(q0, q1), res[2]);
+        const ext_t c1 = ext_sub(ext_sub(q1, q0), c2);
+        const ext_t q2 = ext_add(ext_add(q0, ext_mul_base(c1, 2)), ext_mul_base(c2, 4));
+        const ext_t q3 = ext_add(ext_add(q0, ext_mul_base(c1, 3)), ext_mul_base(c2, 9));
+        // eq(w_j, t) = 1 - w_j + t (2 w_j - 1):  t=1: w_j,  t=2: 3 w_j - 1,  t=3: 5 w_j - 2
+        const ext_t e2 = ext_sub(ext_mul_base(wj, 3), one);
+        const ext_t e3 = ext_sub(ext_mul_base(wj, 5), ext_make(2, 0));
+        res[0] = ext_mul(ext_mul(P, wj), q1);
+        res[1] = ext_mul(ext_mul(P, e2), q2);
+        res[2] = ext_mul(ext_mul(P, e3), q3);
+    }
+};
+struct VeqArgs {
+    const ext_t* in[2];       // A, B: the state this launch reads
+    ext_t* out[2];            // FOLD: where the folded state goes
+    const ulonglong4* L;      // 256 entries {c0, c1, 7 c1, 0}: eq over variables [j+1, j+9)
+    const ulonglong4* H;      // n_rows entries, same format: eq over variables [j+9, k)
+    uint64_t n_rows;          // pairs / 256
+    ext_t r;                  // fold challenge (FOLD) ...
+    const ext_t* r_ptr;       // ... or its device location
+    VeqFin fin;
+    RoundOut out_;
+};
+GL_DEV ulonglong4 ld_tab(const ulonglong4* p) {   // read-only table entry, one 256-bit load
+    ulonglong4 v;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v.x), "=l"(v.y), "=l"(v.z), "=l"(v.w) : "l"(p));
+    return v;
+}
+GL_DEV ext_t ext_mul_prep_weak(ext_t a, const extmul_t& b) {
+    eacc E;
+    eacc_zero(E);
+    eacc_mac_prep(E, a, b);
+    return eacc_weak(E);
+}
+// one pair: weight A by W, accumulate the three bilinear sums (operands may be any u64 — no canonical form needed)
+GL_DEV void veq_item(ext_t alo, ext_t ahi, ext_t blo, ext_t bhi, const extmul_t& W, eacc& S00, eacc& S11, eacc& Sx) {
+    const ext_t wl = ext_mul_prep_weak(alo, W), wh = ext_mul_prep_weak(ahi, W);
+    const uint64_t b7l = gl_mul7_weak(blo.c1), b7h = gl_mul7_weak(bhi.c1);
+    eacc_mac(S00, wl, blo, b7l);
+    eacc_mac(S11, wh, bhi, b7h);
+    eacc_mac(Sx, wl, bhi, b7h);
+    eacc_mac(Sx, wh, blo, b7l);
+}
+template <bool FOLD, bool CANON, int MINB>
+__global__ void __launch_bounds__(256, MINB) veq_round_kernel(const __grid_constant__ VeqArgs a) {
+    extmul_t rm = {0, 0, 0};
+    if (FOLD) rm = extmul_prep(a.r_ptr ? ld_ext(a.r_ptr) : a.r);
+    // balanced contiguous row range of this block; a row is 256 consecutive pairs (one per thread)
+    const uint64_t r0 = a.n_rows * blockIdx.x / gridDim.x, r1 = a.n_rows * (blockIdx.x + 1) / gridDim.x;
+    eacc S00, S11, Sx;
+    eacc_zero(S00); eacc_zero(S11); eacc_zero(Sx);
+    for (uint64_t row = r0; row < r1; row++) {
+        const ulonglong4 hv = ld_tab(a.H + row);   // uniform across the block
+        extmul_t W; W.c0 = hv.x; W.c1 = hv.y; W.c1_7 = hv.z;
+        const uint64_t item = row * 256 + threadIdx.x;
+        ext_t alo, ahi, blo, bhi;
+        load_pair<FOLD, CANON && FOLD>(a.in[0], a.out[0], item, rm, alo, ahi);
+        load_pair<FOLD, CANON && FOLD>(a.in[1], a.out[1], item, rm, blo, bhi);
+        veq_item(alo, ahi, blo, bhi, W, S00, S11, Sx);
+    }
+    const ulonglong4 lv = ld_tab(a.L + threadIdx.x);   // this thread's fixed low-variable weight, applied once
+    extmul_t Lm; Lm.c0 = lv.x; Lm.c1 = lv.y; Lm.c1_7 = lv.z;
+    ext_t acc[3] = {ext_mul_prep(eacc_weak(S00), Lm), ext_mul_prep(eacc_weak(S11), Lm), ext_mul_prep(eacc_weak(Sx), Lm)};
+    block_finish<3, VeqFin>(acc, a.out_, a.fin);
+}
+// all tables of the split rounds in one launch: entry = direct product over its variables
+struct VeqTabArgs {
+    const ext_t* w;
+    uint32_t k, J;
+    ulonglong4* L;                              // [J][256]
+    ulonglong4* H;                              // concatenated, H_j at h_off[j]
+    uint64_t h_off[CG_VEQ_MAX_ROUNDS + 1];
+};
+__global__ void __launch_bounds__(CG_THREADS) veq_tables_kernel(const __grid_constant__ VeqTabArgs a) {
+    const uint64_t n_lo = (uint64_t)a.J << CG_VEQ_LO_BITS, total = n_lo + a.h_off[a.J];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        uint32_t v0, nb;
+        uint64_t x;
+        ulonglong4* dst;
+        if (e < n_lo) {
+            const uint32_t j = (uint32_t)(e >> CG_VEQ_LO_BITS);
+            x = e & ((1u << CG_VEQ_LO_BITS) - 1);
+            v0 = j + 1; nb = CG_VEQ_LO_BITS;
+            dst = a.L + e;
+        } else {
+            const uint64_t y = e - n_lo;
+            uint32_t j = 0;
+            while (y >= a.h_off[j + 1]) j++;
+            x = y - a.h_off[j];
+            v0 = j + 1 + CG_VEQ_LO_BITS; nb = a.k - v0;
+            dst = a.H + y;
+        }
+        ext_t v = ext_one();
+        for (uint32_t i = 0; i < nb; i++) {
+            const ext_t wi = ext_canon(a.w[v0 + i]);
+            v = ext_mul(v, ((x >> i) & 1) ? wi : ext_sub(ext_one(), wi));
+        }
+        *dst = make_ulonglong4(v.c0, v.c1, gl_canon(gl_mul7_weak(v.c1)), 0ULL);
+    }
+}
+// leave split mode: out[x] = P * L[x & 255] * H[x >> 8]  =  the eq state a materialised table would hold
+// after the same folds (variables [f, k), prefix P = prod_{i<f} eq(w_i, r_i))
+__global__ void __launch_bounds__(CG_THREADS) veq_materialise_kernel(const ulonglong4* __restrict__ L, const ulonglong4* __restrict__ H,
+                                                                      const ext_t* __restrict__ prefix, uint64_t n, ext_t* __restrict__ out) {
+    const extmul_t P = extmul_prep(ld_ext(prefix));
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t pair = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; pair < n / 2; pair += stride) {
+        const uint64_t b = 2 * pair;
+        const ulonglong4 hv = ld_tab(H + (b >> CG_VEQ_LO_BITS));
+        const extmul_t ph = extmul_prep(ext_mul_prep(ext_make(hv.x, hv.y), P));
+        const ulonglong4 l0 = ld_tab(L + (b & 255)), l1 = ld_tab(L + (b & 255) + 1);
+        st_ext2(out + b, ext_mul_prep(ext_make(l0.x, l0.y), ph), ext_mul_prep(ext_make(l1.x, l1.y), ph));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

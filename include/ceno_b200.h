@@ -58,8 +58,18 @@ typedef struct cg_mle_desc {
     const void* dptr;
     uint64_t len;
     uint32_t num_vars;
-    uint32_t is_ext;
+    uint32_t is_ext; /* CG_MLE_BASE, CG_MLE_EXT or CG_MLE_EQ */
 } cg_mle_desc;
+#define CG_MLE_BASE 0u
+#define CG_MLE_EXT 1u
+/* Virtual eq MLE, accepted by the cg_sumcheck_* entry points: the polynomial is eq(w, .) for the point w
+ * and no table exists.  dptr = HOST pointer to w (num_vars ext = 2*num_vars u64, read during the call),
+ * len is ignored.  It behaves exactly like the table cg_build_eq(w) would produce (same round messages,
+ * same final evaluation eq(w, r)); for the shape eq*A*B (one degree-3 product, coefficient 1) the large
+ * rounds then run the split-eq kernel, which never streams or folds an eq table.  This is what the
+ * reference's virtual device MLEs are for (GpuVirtualInterleavedExt, ceno_zkvm/src/scheme/gpu/mod.rs:2195-2268):
+ * hand the device a description instead of 2^k elements.  Not accepted by cg_sumcheck_prove_sharded yet. */
+#define CG_MLE_EQ 2u
 
 /* ---- lifecycle / memory: replaces cuda_hal context + mem_pool
  * (gkr_iop/src/gpu/mod.rs:53-66 get_cuda_hal; alloc_*_on_device / alloc_*_from_host / to_cpu_vec,

@@ -134,6 +134,76 @@ def test_t3_sumcheck_bit_exact(dev, k, mode):
         m.free()
 
 
+@pytest.mark.parametrize("k,mode,pos", [(20, "host", 0), (21, "device", 0), (22, "host", 1), (21, "host", 2), (20, "device_nomid", 0),
+                                        (21, "notail", 0), (12, "host", 0), (19, "device", 0), (20, "nofuse", 0), (20, "generic", 1)])
+def test_t3_virtual_eq_bit_exact(dev, k, mode, pos):
+    """eq handed over as its point (CG_MLE_EQ): the split-eq rounds (k >= 20) and every fallback must
+    give the proof of the materialised table, bit for bit."""
+    import ceno_b200 as cb
+    n = 1 << k
+    w = orc.fill_ext(0xE9 + k, k)
+    a = orc.fill_ext(0xC0FFEE ^ (1 + 16 * k), n)
+    b = orc.fill_ext(0xC0FFEE ^ (2 + 16 * k), n)
+    host = [(a, True, k), (b, True, k)]
+    host.insert(pos, (orc.build_eq_x_r_vec(w), True, k))
+    terms = [([1, 0], [0, 1, 2])]
+    want = orc.sumcheck_prove(host, terms, k, 3, transcript=orc.Transcript(b"veq"))
+    mles = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, x) for x in (a, b)]
+    mles.insert(pos, cb.EqPolynomial(dev, w))
+    flags = {"host": 0, "device": 0, "device_nomid": cb.IOPProverState.NO_MID, "notail": cb.IOPProverState.NO_TAIL,
+             "nofuse": cb.IOPProverState.NO_FUSE, "generic": cb.IOPProverState.FORCE_GENERIC}[mode]
+    got = cb.IOPProverState.prove(dev, mles, terms, k, 3, transcript=cb.StandInTranscript(b"veq"), flags=flags,
+                                  device_challenger=mode.startswith("device"))
+    for g, x in zip(got, want):
+        assert eq_np(g, x)
+    for m in mles:
+        m.free()
+
+
+def test_virtual_eq_step_api_other_shapes(dev):
+    """Virtual eq through the step API (round_eval / bind / peek, bind without an evaluation), with a
+    coefficient != 1 and inside a two-term expression: all fall back to exact table semantics."""
+    import ceno_b200 as cb
+    k = 20
+    n = 1 << k
+    w = orc.fill_ext(0x51, k)
+    eq = orc.build_eq_x_r_vec(w)
+    a, b = orc.fill_ext(0xAB1, n), orc.fill_ext(0xAB2, n)
+    terms = [([1, 0], [0, 1, 2])]
+    mles = [cb.EqPolynomial(dev, w)] + [cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, x) for x in (a, b)]
+    st = cb.IOPProverState(dev, mles, terms, k, 3)
+    cur = [eq, a, b]
+    for j in range(4):     # two split rounds, then the switch to the materialised state inside the step API
+        msg = st.round_eval()
+        want, _, _ = orc.sumcheck_prove([(c, True, k - j) for c in cur], terms, k - j, 3, challenge_fn=lambda *_: np.array([1, 2], dtype=np.uint64))
+        assert eq_np(msg, want[0])
+        r = rnd_point(70 + j, 1)
+        st.bind(r)
+        cur = [orc.fix_variable(c, True, r) for c in cur]
+    assert eq_np(st.peek(0), cur[0]) and eq_np(st.peek(2), cur[2])
+    st.close()
+    # peek / bind-without-eval while still in split mode
+    st = cb.IOPProverState(dev, mles, terms, k, 3)
+    cur = [eq, a, b]
+    st.round_eval()
+    r = rnd_point(90, 1)
+    st.bind(r)
+    cur = [orc.fix_variable(c, True, r) for c in cur]
+    assert eq_np(st.peek(0), cur[0])
+    msg = st.round_eval()
+    want, _, _ = orc.sumcheck_prove([(c, True, k - 1) for c in cur], terms, k - 1, 3, challenge_fn=lambda *_: np.array([1, 2], dtype=np.uint64))
+    assert eq_np(msg, want[0])
+    st.close()
+    # coefficient != 1 and a two-term expression
+    for tms, deg in (([([5, 9], [0, 1, 2])], 3), ([([1, 0], [0, 1, 2]), ([3, 4], [0, 1])], 3)):
+        want = orc.sumcheck_prove([(eq, True, k), (a, True, k), (b, True, k)], tms, k, deg, transcript=orc.Transcript(b"v2"))
+        got = cb.IOPProverState.prove(dev, mles, tms, k, deg, transcript=cb.StandInTranscript(b"v2"))
+        for g, x in zip(got, want):
+            assert eq_np(g, x)
+    for m in mles:
+        m.free()
+
+
 def test_t3_with_coefficient_and_python_transcript(dev):
     import ceno_b200 as cb
     k = 9
