@@ -11,8 +11,12 @@ with CUDA events, and a CPU baseline (the oracle port of the reference algorithm
 A "step" is one full sumcheck (k rounds of evaluate+fold) over the resident instance.
 `value`  : inputs resident in HBM, transcript on the host behind the C-ABI callback (the
            reference's flow: it hands &mut BasicTranscript to the device crate).
-`e2e`    : same call with HOST buffers — H2D of A and B from pinned memory, eq-build, prove, results
-           back on the host — inside the timed region.
+`e2e`    : same call with HOST buffers — H2D of A and B from pinned memory, prove, results back on
+           the host — inside the timed region.
+--eq virtual (default): eq(w, .) is handed over as its point (cg_mle_desc kind CG_MLE_EQ) and the large
+           rounds run the split-eq kernel (no eq stream, no eq fold); --eq table: eq is a resident
+           2^k table built by cg_build_eq (the `table_eq` sub-object always reports that variant too).
+           Both produce the same proof bit for bit.
 """
 import argparse
 import ctypes as C
@@ -172,16 +176,20 @@ def gpu_arm(args):
     B = cb.MultilinearExtension(dev, b_d, k, True)
     EQ = cb.build_eq_x_r_vec(dev, w, stream=sh, out=eq_d)
     stream.synchronize()
-    mles, terms = [EQ, A, B], [([1, 0], [0, 1, 2])]
+    virt = args.eq == "virtual"
+    EQV = cb.EqPolynomial(dev, w)
+    terms = [([1, 0], [0, 1, 2])]
+    mles_table, mles = [EQ, A, B], ([EQV, A, B] if virt else [EQ, A, B])
 
-    def step(device_challenger=False, flags=0):
-        return cb.IOPProverState.prove(dev, mles, terms, k, deg, transcript=cb.StandInTranscript(b"bench"), flags=flags,
-                                       device_challenger=device_challenger, stream=sh)
+    def step(device_challenger=False, flags=0, which=None):
+        return cb.IOPProverState.prove(dev, mles if which is None else which, terms, k, deg, transcript=cb.StandInTranscript(b"bench"),
+                                       flags=flags, device_challenger=device_challenger, stream=sh)
 
     def e2e_step():
         dev.h2d(a_d.ptr, a_hp, nbytes, sh)
         dev.h2d(b_d.ptr, b_hp, nbytes, sh)
-        cb.build_eq_x_r_vec(dev, w, stream=sh, out=eq_d)
+        if not virt:
+            cb.build_eq_x_r_vec(dev, w, stream=sh, out=eq_d)
         return step()
 
     def timed(fn, steps):
@@ -203,6 +211,10 @@ def gpu_arm(args):
     ms, out = timed(step, args.steps)
     launches = dev.launch_count() - l0
     ms_dev, out_dev = timed(lambda: step(True), args.steps)
+    ms_tab, out_tab = timed(lambda: step(which=mles_table), args.steps)          # resident eq table, streamed and folded
+    ms_tab_dev, _ = timed(lambda: step(True, which=mles_table), args.steps)
+    for g, d in zip(out, out_tab):
+        assert np.array_equal(g, d), "virtual-eq and table-eq proofs disagree"
     # EQ-k (build_eq_x_r alone), timed separately
     ms_eq, _ = timed(lambda: cb.build_eq_x_r_vec(dev, w, stream=sh, out=eq_d), max(args.steps, 5))
     for g, d in zip(out, out_dev):
@@ -214,23 +226,45 @@ def gpu_arm(args):
         step(True, flags=4)
         prof.append(dev.profile_last())
     prof = np.mean(np.array(prof), axis=0)       # ms per round
-    m, s = 3, 16
-    fused_bytes = [1.5 * m * s * (1 << (k - j + 1)) for j in range(1, k)]     # round j>=1: read 2^(k-j+1), write half
-    fused_ms = [float(prof[j]) for j in range(1, k)]
+    # Dominant kernel: the fused fix_variable + next-round evaluation of the streaming rounds.
+    #   virtual eq: veq_tma_kernel<FOLD=1>, rounds 1 .. J-1 (J = k - 18), streams m = 2 MLEs (A, B);
+    #   table eq  : tower_round_kernel<FOLD=1>, rounds 1 .. 5, streams m = 3 MLEs.
+    # Algorithmic bytes of a fused launch over inputs of n_in elements: read m*16*n_in, write half.
+    s = 16
+    m = 2 if virt else 3
+    last = (k - 18) if virt else min(6, k)          # first round NOT run by the dominant kernel
+    rounds = list(range(1, max(last, 2)))
+    fused_bytes = [1.5 * m * s * (1 << (k - j + 1)) for j in rounds]
+    fused_ms = [float(prof[j]) for j in rounds]
     peak, peak_src = read_peaks()
     ach_all = sum(fused_bytes) / (sum(fused_ms) * 1e-3) / 1e9
     ach_top = fused_bytes[0] / (fused_ms[0] * 1e-3) / 1e9
     r0_bytes = m * s * n
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the same launches from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        tk = tj.get("veq_tma_kernel<FOLD=1>" if virt else "tower_round_kernel<FOLD=1>")
+        if tk and tk.get("k") == k:
+            traffic = float(np.mean(tk["bytes_per_launch"]))
+    except Exception:
+        pass
     roofline = {
-        "bound": "hbm", "kernel": "tower_round_kernel<FOLD=1> (fused fix_variable + next-round evaluation)",
+        "bound": "hbm",
+        "kernel": ("veq_tma_kernel<FOLD=1> (split-eq: fused fix_variable + next-round evaluation, TMA-staged; streams A and B only)" if virt
+                   else "tower_round_kernel<FOLD=1> (fused fix_variable + next-round evaluation; streams eq, A, B)"),
         "achieved": ach_all, "peak": peak, "unit": "GB/s", "frac": ach_all / peak, "peak_source": peak_src,
-        "traffic": None,
-        "launches_per_step": k - 1, "algorithmic_bytes_per_step": sum(fused_bytes), "ms_per_step_in_kernel": sum(fused_ms),
+        "traffic": traffic,
+        "bytes_definition": f"per launch 1.5*m*16*n_in with m = {m} streamed MLEs (SURVEY §8d); achieved/traffic are averages over the {len(rounds)} launches of this kernel per step",
+        "achieved_per_launch_avg_bytes": float(np.mean(fused_bytes)),
+        "launches_per_step": len(rounds), "algorithmic_bytes_per_step": sum(fused_bytes), "ms_per_step_in_kernel": sum(fused_ms),
         "top_launch": {"round": 1, "bytes": fused_bytes[0], "ms": fused_ms[0], "achieved": ach_top, "frac": ach_top / peak},
         "round0_eval": {"bytes": r0_bytes, "ms": float(prof[0]), "achieved": r0_bytes / (float(prof[0]) * 1e-3) / 1e9},
         "eq_build": {"bytes": 16 * n, "ms": ms_eq, "achieved": 16 * n / (ms_eq * 1e-3) / 1e9},
         "round_ms": [round(float(x), 5) for x in prof],
     }
+    if virt:   # what SURVEY §8d's 3-MLE table formulation would have to move in the same time (the eq stream this kernel avoids)
+        roofline["table_formulation_equiv"] = {"bytes_per_step": 1.5 * sum(fused_bytes), "achieved": 1.5 * ach_all, "frac": 1.5 * ach_all / peak,
+                                               "note": "SURVEY §8d counts m = 3 (eq materialised); the split-eq kernel never reads or writes it"}
 
     # ---- e2e: host buffers, copies inside the timed region
     for _ in range(min(args.warmup, 2)):
@@ -255,14 +289,17 @@ def gpu_arm(args):
         "dtype": "u64 (Goldilocks, ext2)", "data": "synthetic",
         "config": {"workload": f"T3-{k}: eq(w,x)*A(x)*B(x), 2^{k}-point hypercube, degree 3, GoldilocksExt2 (3 ext MLEs x {nbytes >> 20} MiB)",
                    "k": k, "degree": deg, "n_mles": 3, "parallelism": "1 GPU",
+                   "eq": ("virtual: eq(w,.) passed as its point (CG_MLE_EQ), split-eq kernels" if virt else "table: resident 2^k ext table"),
                    "l2": f"inputs {3 * nbytes >> 20} MiB > L2 126 MB (no flush needed)",
                    "transcript": "stand-in sponge on the host behind cg_challenge_cb (reference flow); Poseidon2 constants are upstream-only"},
         "points_per_s": n / (ms * 1e-3), "rounds_per_s": k / (ms * 1e-3),
         "device_challenger": {"ms_per_step": ms_dev, "value": ops / (ms_dev * 1e-3) / 1e9, "unit": "Gfield-ops/s",
                               "note": "same kernels, stand-in challenger on the device: no host round trip per round"},
+        "table_eq": {"ms_per_step": ms_tab, "value": ops / (ms_tab * 1e-3) / 1e9, "unit": "Gfield-ops/s", "device_challenger_ms": ms_tab_dev,
+                     "note": "same instance with eq as a resident 2^k table (cg_build_eq) streamed and folded like A and B; identical proof"},
         "e2e": {"value": ops / (ms_e2e * 1e-3) / 1e9, "unit": "Gfield-ops/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": 2 * nbytes + 16 * k, "d2h_bytes_per_step": 16 * (k * deg + 3 + k),
-                "note": "H2D of A,B from pinned host memory + eq-build + prove through cg_sumcheck_prove, results on the host"},
+                "note": "H2D of A,B from pinned host memory" + ("" if virt else " + eq-build") + " + prove through cg_sumcheck_prove, results on the host"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_val, "unit": "Gfield-ops/s", "cores": cores, "kind": "port", "ms": t_cpu * 1e3,
@@ -301,6 +338,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--k", type=int, default=24, help="log2 hypercube size of the T3 instance")
+    ap.add_argument("--eq", default="virtual", choices=["virtual", "table"], help="how eq(w,.) is given to the prover (see the module docstring)")
     ap.add_argument("--cpu-k", type=int, default=24, help="log2 size of the bounded CPU sample")
     args = ap.parse_args()
     if args.impl == "reference":

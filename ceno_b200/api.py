@@ -173,10 +173,11 @@ class EqPolynomial:
 
     is_ext = True
 
-    def __init__(self, dev, w):
+    def __init__(self, dev, w, num_vars=None):
+        """num_vars < len(w): this rank's slice in prove_sharded (w stays the GLOBAL point)."""
         self.dev = dev
         self.w = _u64(w).copy()
-        self.num_vars = self.w.size // 2
+        self.num_vars = self.w.size // 2 if num_vars is None else num_vars
         self.len = 1 << self.num_vars
 
     def desc(self):

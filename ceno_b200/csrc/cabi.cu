@@ -510,7 +510,8 @@ struct VeqState {               // a virtual eq MLE (CG_MLE_EQ) handled by the s
     uint32_t J = 0;             // rounds 0 .. J-1 are split rounds
     std::vector<uint64_t> h_point;
     ext_t* d_w = nullptr;       // the point on the device
-    ext_t* d_prefix = nullptr;  // P_folds = prod_{i < folds} eq(w_i, r_i)
+    ext_t* d_prefix = nullptr;  // scale * P_folds,  P_folds = prod_{i < folds} eq(w_i, r_i)
+    ext_t scale{1, 0};          // sharded prove: eq(w_top, rank) — the constant factor of eq on this rank's slice
     ulonglong4 *d_L = nullptr, *d_H = nullptr;
     uint64_t h_off[CG_VEQ_MAX_ROUNDS + 1] = {0};
 };
@@ -594,6 +595,12 @@ static int veq_build_full(cg_sumcheck* sc, uint32_t i, const uint64_t* h_point) 
     void* buf = nullptr;
     CHK(sc_alloc(sc, sizeof(ext_t) << sc->num_vars, &buf));
     CHK(cg_build_eq(sc->ctx, h_point, sc->num_vars, (uint64_t*)buf, 0, 1ULL << sc->num_vars, (cg_stream)sc->stream));
+    if (i == sc->veq.idx && sc->veq.have && !(sc->veq.scale.c0 == 1 && sc->veq.scale.c1 == 0)) {
+        const uint64_t n = 1ULL << sc->num_vars;
+        scale_ext_kernel<<<grid_for(sc->ctx, n, 8), CG_THREADS, 0, sc->stream>>>((ext_t*)buf, n, sc->veq.scale);
+        LAUNCHED(sc->ctx);
+        CU(sc->ctx, cudaGetLastError());
+    }
     sc->mles[i].orig = buf;
     sc->mles[i].orig_is_ext = 1;
     return CG_OK;
@@ -612,8 +619,7 @@ static int veq_setup_split(cg_sumcheck* sc) {
     v.d_w = (ext_t*)p;
     v.d_prefix = (ext_t*)((char*)p + ((sizeof(ext_t) * k + 63) & ~(size_t)63));
     CU(c, cudaMemcpyAsync(v.d_w, v.h_point.data(), sizeof(ext_t) * k, cudaMemcpyHostToDevice, sc->stream));
-    static const uint64_t one[2] = {1, 0};
-    CU(c, cudaMemcpyAsync(v.d_prefix, one, sizeof(one), cudaMemcpyHostToDevice, sc->stream));
+    CU(c, cudaMemcpyAsync(v.d_prefix, &v.scale, sizeof(ext_t), cudaMemcpyHostToDevice, sc->stream));   // v lives as long as sc
     CHK(sc_alloc(sc, sizeof(ulonglong4) * ((size_t)v.J << CG_VEQ_LO_BITS), &p));
     v.d_L = (ulonglong4*)p;
     CHK(sc_alloc(sc, sizeof(ulonglong4) * v.h_off[v.J], &p));
@@ -796,9 +802,17 @@ static int sc_ensure_tables(cg_sumcheck* sc) {
     return CG_OK;
 }
 
+static int sc_create_terms(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t* coeff,
+                           const uint32_t* off, const uint32_t* idx, uint32_t n_terms, uint32_t num_vars,
+                           uint32_t degree, uint32_t flags, cg_stream s, const ext_t* veq_scale, cg_sumcheck** out);
 CG_EXPORT int cg_sumcheck_create(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t* coeff,
                                  const uint32_t* off, const uint32_t* idx, uint32_t n_terms, uint32_t num_vars,
                                  uint32_t degree, uint32_t flags, cg_stream s, cg_sumcheck** out) {
+    return sc_create_terms(c, mles, n_mles, coeff, off, idx, n_terms, num_vars, degree, flags, s, nullptr, out);
+}
+static int sc_create_terms(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t* coeff,
+                           const uint32_t* off, const uint32_t* idx, uint32_t n_terms, uint32_t num_vars,
+                           uint32_t degree, uint32_t flags, cg_stream s, const ext_t* veq_scale, cg_sumcheck** out) {
     if (!c) return CG_ERR_INVALID;
     if (n_terms && (!coeff || !off || !idx)) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: null term table");
     for (uint32_t t = 0; t < n_terms; t++) {
@@ -871,6 +885,7 @@ CG_EXPORT int cg_sumcheck_create(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_
         }
     }
     if (rc == CG_OK && sc->veq.have) {
+        if (veq_scale) sc->veq.scale = *veq_scale;
         const bool split_ok = sc->tl.on && sc->tl.eq == sc->veq.idx && sc->tl.alpha_one && sc->tl.prod.size() == 2 && sc->tl.lk.empty() &&
                               !(flags & (CG_SC_NO_FUSE | CG_SC_FORCE_GENERIC)) && num_vars >= 20 && num_vars <= 32;
         rc = split_ok ? veq_setup_split(sc) : veq_build_full(sc, sc->veq.idx, sc->veq.h_point.data());
@@ -995,7 +1010,21 @@ static int launch_veq(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro
         else if (canon) veq_round_kernel<true, true, MB><<<grid, 256, 0, sc->stream>>>(a);       \
         else veq_round_kernel<true, false, MB><<<grid, 256, 0, sc->stream>>>(a);                 \
     } while (0)
-    if (minb == 1) CG_VEQ_LAUNCH(1); else if (minb == 3) CG_VEQ_LAUNCH(3); else CG_VEQ_LAUNCH(2);
+    static const int use_tma = []() { const char* e = getenv("CG_VEQ_TMA"); return e ? atoi(e) : 1; }();
+    if (use_tma) {   // rows staged through shared memory by cp.async.bulk (default)
+        static bool attr_done = false;
+        if (!attr_done) {
+            CU(c, cudaFuncSetAttribute(veq_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VeqTmaCfg<false>::SMEM));
+            CU(c, cudaFuncSetAttribute(veq_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VeqTmaCfg<true>::SMEM));
+            CU(c, cudaFuncSetAttribute(veq_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VeqTmaCfg<true>::SMEM));
+            attr_done = true;
+        }
+        uint64_t tb = (uint64_t)c->sm_count * 2;
+        if (tb > a.n_rows) tb = a.n_rows;
+        if (!fold) veq_tma_kernel<false, false><<<(unsigned)tb, 256, VeqTmaCfg<false>::SMEM, sc->stream>>>(a);
+        else if (canon) veq_tma_kernel<true, true><<<(unsigned)tb, 256, VeqTmaCfg<true>::SMEM, sc->stream>>>(a);
+        else veq_tma_kernel<true, false><<<(unsigned)tb, 256, VeqTmaCfg<true>::SMEM, sc->stream>>>(a);
+    } else if (minb == 1) CG_VEQ_LAUNCH(1); else if (minb == 3) CG_VEQ_LAUNCH(3); else CG_VEQ_LAUNCH(2);
 #undef CG_VEQ_LAUNCH
     LAUNCHED(c);
     CU(c, cudaGetLastError());
@@ -1527,12 +1556,31 @@ CG_EXPORT int cg_sumcheck_prove_sharded(cg_ctx* c, cg_comm* cm, const cg_mle_des
     while ((1 << g) < cm->nranks) g++;
     if (num_vars_global < (uint32_t)g) return set_err(c, CG_ERR_INVALID, "fewer variables than log2(ranks)");
     if (n_mles > CG_COMM_GATHER_MLES) return set_err(c, CG_ERR_UNSUPPORTED, "sharded prove supports at most 64 MLEs");
-    for (uint32_t i = 0; i < n_mles; i++)
-        if (mles && mles[i].is_ext == CG_MLE_EQ) return set_err(c, CG_ERR_UNSUPPORTED, "sharded prove: virtual eq MLEs are not supported yet (pass the slice of the table)");
+
     const uint32_t k_local = num_vars_global - g;
     cudaStream_t st = S(c, s);
+    // a virtual eq MLE carries the GLOBAL point (num_vars_global ext): on this rank's slice eq(w, .) is
+    // eq(w_top, rank) * eq(w_low, .), so the local prover gets w_low and the constant factor as its initial prefix
+    ext_t veq_scale{1, 0};
+    uint32_t n_veq = 0;
+    for (uint32_t i = 0; i < n_mles; i++) {
+        if (!mles || mles[i].is_ext != CG_MLE_EQ) continue;
+        if (++n_veq > 1) return set_err(c, CG_ERR_UNSUPPORTED, "sharded prove: at most one virtual eq MLE");
+        if (!mles[i].dptr) return set_err(c, CG_ERR_INVALID, "sharded prove: virtual eq MLE without a point");
+        const uint64_t* pt = (const uint64_t*)mles[i].dptr;
+        unsigned __int128 P = GL_P;
+        uint64_t a0 = 1, a1 = 0;
+        for (int b = 0; b < g; b++) {
+            uint64_t w0 = pt[2 * (k_local + b)] % GL_P, w1 = pt[2 * (k_local + b) + 1] % GL_P;
+            if (!((cm->rank >> b) & 1)) { w0 = (uint64_t)(((unsigned __int128)1 + P - w0) % P); w1 = (uint64_t)((P - w1) % P); }
+            const uint64_t n0 = (uint64_t)((((unsigned __int128)a0 * w0) % P + ((((unsigned __int128)a1 * w1) % P) * 7) % P) % P);
+            const uint64_t n1 = (uint64_t)((((unsigned __int128)a0 * w1) % P + ((unsigned __int128)a1 * w0) % P) % P);
+            a0 = n0; a1 = n1;
+        }
+        veq_scale = ext_t{a0, a1};
+    }
     cg_sumcheck* sc = nullptr;
-    CHK(cg_sumcheck_create(c, mles, n_mles, coeff, off, idx, n_terms, k_local, degree, flags, s, &sc));
+    CHK(sc_create_terms(c, mles, n_mles, coeff, off, idx, n_terms, k_local, degree, flags, s, n_veq ? &veq_scale : nullptr, &sc));
     sc->comm = cm;
     sc->extra_rounds = (uint32_t)g;   // the persistent tail kernel continues through the replicated rounds when it can
     std::vector<uint64_t> fin_local(2 * (size_t)(n_mles ? n_mles : 1));

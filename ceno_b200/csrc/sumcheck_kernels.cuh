@@ -501,6 +501,137 @@ __global__ void __launch_bounds__(256, MINB) veq_round_kernel(const __grid_const
     ext_t acc[3] = {ext_mul_prep(eacc_weak(S00), Lm), ext_mul_prep(eacc_weak(S11), Lm), ext_mul_prep(eacc_weak(Sx), Lm)};
     block_finish<3, VeqFin>(acc, a.out_, a.fin);
 }
+// ---- the same round with TMA staging: rows (256 pairs = 16 KB per MLE when folding, 8 KB in round 0) are
+// brought into a shared-memory ring by 1-D bulk copies (cp.async.bulk, mbarrier complete_tx), so DRAM latency is
+// hidden by the ring depth instead of by resident warps (the register-heavy lazy accumulators allow only 16
+// warps per SM; ncu showed long-scoreboard stalls as the top issue-slot loss of the LDG version).
+// Bank conflicts: a thread owns 64 contiguous bytes (4 ext), so a plain read order would be 4-way conflicted.
+// Thread t reads its 16-byte chunks in the order i ^ s, s = (t >> 1) & 3 — conflict-free — and the permutation
+// costs nothing per pair: s & 1 swaps (x0, x1) and (x2, x3), absorbed by folding with 1 - r
+// (x1 + (1-r)(x0 - x1) = x0 + r (x1 - x0)); s & 2 swaps the lo/hi pair, absorbed by swapping S00 and S11
+// once at the end (Sx is symmetric) and by the store address.
+GL_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+GL_DEV void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+GL_DEV void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+GL_DEV void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+GL_DEV bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+GL_DEV void mbar_wait(uint32_t bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) {} }
+GL_DEV void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+GL_DEV ext_t lds_ext(uint32_t addr) {
+    ext_t v;
+    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(v.c0), "=l"(v.c1) : "r"(addr));
+    return v;
+}
+template <bool FOLD>
+struct VeqTmaCfg {
+    static constexpr uint32_t ROWB = FOLD ? 16384u : 8192u;   // bytes per MLE per row
+    static constexpr uint32_t STAGEB = 2 * ROWB + 128;        // A row | B row | H entry (32 B) + pad
+    static constexpr int STAGES = FOLD ? 3 : 4;
+    static constexpr uint32_t SMEM = STAGES * STAGEB + 2 * STAGES * 8;
+};
+template <bool FOLD, bool CANON>
+__global__ void __launch_bounds__(256, 2) veq_tma_kernel(const __grid_constant__ VeqArgs a) {
+    using Cfg = VeqTmaCfg<FOLD>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr uint32_t ROWB = Cfg::ROWB, STAGEB = Cfg::STAGEB;
+    extern __shared__ __align__(128) unsigned char veq_smem[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t sbase = smem_u32(veq_smem);
+    const uint32_t bar_full = sbase + STAGES * STAGEB, bar_empty = bar_full + STAGES * 8;
+    const uint64_t r0 = a.n_rows * blockIdx.x / gridDim.x, r1 = a.n_rows * (blockIdx.x + 1) / gridDim.x;
+    const uint32_t nrows = (uint32_t)(r1 - r0);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](uint32_t i) {   // thread 0: bring row r0 + i into stage i % STAGES
+        const uint32_t s = i % STAGES;
+        const uint64_t row = r0 + i;
+        const uint32_t dst = sbase + s * STAGEB, bar = bar_full + 8 * s;
+        mbar_expect_tx(bar, 2 * ROWB + 32);
+        tma_load_1d(dst, reinterpret_cast<const unsigned char*>(a.in[0]) + row * ROWB, ROWB, bar);
+        tma_load_1d(dst + ROWB, reinterpret_cast<const unsigned char*>(a.in[1]) + row * ROWB, ROWB, bar);
+        tma_load_1d(dst + 2 * ROWB, a.H + row, 32, bar);
+    };
+    if (tid == 0)
+        for (uint32_t i = 0; i < (uint32_t)STAGES && i < nrows; i++) issue(i);
+    // per-thread chunk permutation (see above)
+    const uint32_t sx = FOLD ? ((tid >> 1) & 3) : ((tid >> 2) & 1);
+    const uint32_t hs = FOLD ? (sx >> 1) : sx;            // lo/hi pair swapped for this thread
+    const uint32_t toff = FOLD ? tid * 64 : tid * 32;
+    extmul_t rm = {0, 0, 0};
+    if (FOLD) {
+        ext_t r = ext_canon(a.r_ptr ? ld_ext(a.r_ptr) : a.r);
+        if (sx & 1) r = ext_sub(ext_one(), r);
+        rm = extmul_prep(r);
+    }
+    eacc Sf, Ss, Sx;   // first*first, second*second, cross
+    eacc_zero(Sf); eacc_zero(Ss); eacc_zero(Sx);
+    uint32_t s = 0, ph = 0;
+    for (uint32_t i = 0; i < nrows; i++) {
+        if (tid == 0 && i >= 1 && i - 1 + STAGES < nrows) {   // refill the stage released one row ago
+            const uint32_t ps = (i - 1) % STAGES, pph = ((i - 1) / STAGES) & 1;
+            mbar_wait(bar_empty + 8 * ps, pph);
+            issue(i - 1 + STAGES);
+        }
+        mbar_wait(bar_full + 8 * s, ph);
+        const uint32_t st = sbase + s * STAGEB;
+        ext_t af, as_, bf, bs;
+        const uint64_t item = (r0 + i) * 256 + tid;
+        if (FOLD) {
+            ext_t y0 = lds_ext(st + toff + ((0 ^ sx) << 4)), y1 = lds_ext(st + toff + ((1 ^ sx) << 4));
+            ext_t y2 = lds_ext(st + toff + ((2 ^ sx) << 4)), y3 = lds_ext(st + toff + ((3 ^ sx) << 4));
+            ext_t z0 = lds_ext(st + ROWB + toff + ((0 ^ sx) << 4)), z1 = lds_ext(st + ROWB + toff + ((1 ^ sx) << 4));
+            ext_t z2 = lds_ext(st + ROWB + toff + ((2 ^ sx) << 4)), z3 = lds_ext(st + ROWB + toff + ((3 ^ sx) << 4));
+            const ext_t hw0 = lds_ext(st + 2 * ROWB), hw1 = lds_ext(st + 2 * ROWB + 16);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+            if (CANON) {
+                y0 = ext_canon(y0); y1 = ext_canon(y1); y2 = ext_canon(y2); y3 = ext_canon(y3);
+                z0 = ext_canon(z0); z1 = ext_canon(z1); z2 = ext_canon(z2); z3 = ext_canon(z3);
+            }
+            af = ext_fma_prep(y0, ext_sub(y1, y0), rm);
+            as_ = ext_fma_prep(y2, ext_sub(y3, y2), rm);
+            bf = ext_fma_prep(z0, ext_sub(z1, z0), rm);
+            bs = ext_fma_prep(z2, ext_sub(z3, z2), rm);
+            st_ext(a.out[0] + 2 * item + hs, af);
+            st_ext(a.out[0] + 2 * item + (1 - hs), as_);
+            st_ext(a.out[1] + 2 * item + hs, bf);
+            st_ext(a.out[1] + 2 * item + (1 - hs), bs);
+            extmul_t W; W.c0 = hw0.c0; W.c1 = hw0.c1; W.c1_7 = hw1.c0;
+            veq_item(af, as_, bf, bs, W, Sf, Ss, Sx);
+        } else {
+            af = lds_ext(st + toff + ((0 ^ sx) << 4));
+            as_ = lds_ext(st + toff + ((1 ^ sx) << 4));
+            bf = lds_ext(st + ROWB + toff + ((0 ^ sx) << 4));
+            bs = lds_ext(st + ROWB + toff + ((1 ^ sx) << 4));
+            const ext_t hw0 = lds_ext(st + 2 * ROWB), hw1 = lds_ext(st + 2 * ROWB + 16);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+            extmul_t W; W.c0 = hw0.c0; W.c1 = hw0.c1; W.c1_7 = hw1.c0;
+            veq_item(af, as_, bf, bs, W, Sf, Ss, Sx);
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
+    const ulonglong4 lv = ld_tab(a.L + tid);
+    extmul_t Lm; Lm.c0 = lv.x; Lm.c1 = lv.y; Lm.c1_7 = lv.z;
+    const ext_t vf = ext_mul_prep(eacc_weak(Sf), Lm), vs = ext_mul_prep(eacc_weak(Ss), Lm);
+    ext_t acc[3] = {hs ? vs : vf, hs ? vf : vs, ext_mul_prep(eacc_weak(Sx), Lm)};
+    block_finish<3, VeqFin>(acc, a.out_, a.fin);
+}
+
 // all tables of the split rounds in one launch: entry = direct product over its variables
 struct VeqTabArgs {
     const ext_t* w;
@@ -1226,6 +1357,11 @@ __global__ void rotation_selector_kernel(const ext_t* __restrict__ eq, ext_t* __
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, mask = (1ULL << log2) - 1;
     for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride)
         st_ext(out + b, ((keep >> (b & mask)) & 1) ? ext_canon(ld_ext(eq + b)) : ext_zero());
+}
+__global__ void __launch_bounds__(CG_THREADS) scale_ext_kernel(ext_t* __restrict__ v, uint64_t n, ext_t c) {
+    const extmul_t cm = extmul_prep(c);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride) st_ext(v + b, ext_mul_prep(ext_canon(ld_ext(v + b)), cm));
 }
 __global__ void fill_ext_kernel(ext_t* __restrict__ v, uint64_t n, ext_t val) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;

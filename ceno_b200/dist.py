@@ -136,10 +136,13 @@ def bench_sharded(args, rank, world, local_rank):
     w = synth.fill_ext(seed_w, k)
     A = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k_local, synth.fill_ext(seed_a, n_local, start=rank * n_local))
     B = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k_local, synth.fill_ext(seed_b, n_local, start=rank * n_local))
-    eq_lo = cb.build_eq_x_r_vec(dev, w[:2 * k_local])
-    s = eq_slice_scalar(w[2 * k_local:], rank)
-    EQ = cb.wit_infer_by_monomial_expr(dev, [eq_lo], [(list(s), [0])], k_local)      # eq slice = scalar * eq(w_low, .)
-    eq_lo.free()
+    if getattr(args, "eq", "virtual") == "table":
+        eq_lo = cb.build_eq_x_r_vec(dev, w[:2 * k_local])
+        s = eq_slice_scalar(w[2 * k_local:], rank)
+        EQ = cb.wit_infer_by_monomial_expr(dev, [eq_lo], [(list(s), [0])], k_local)      # eq slice = scalar * eq(w_low, .)
+        eq_lo.free()
+    else:   # eq handed over as its (global) point: split-eq rounds, no eq stream; the rank factor is derived by the library
+        EQ = cb.EqPolynomial(dev, w, num_vars=k_local)
     terms = [([1, 0], [0, 1, 2])]
 
     def xchg(blob):
@@ -184,7 +187,7 @@ def bench_sharded(args, rank, world, local_rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64 (Goldilocks, ext2)", "data": "synthetic",
             "config": {"workload": f"T3-{k}: eq(w,x)*A(x)*B(x), 2^{k}-point hypercube, degree 3, GoldilocksExt2, sliced 1/{world} per GPU",
-                       "k": k, "degree": deg, "n_mles": 3, "parallelism": f"hypercube slices x{world}",
+                       "k": k, "degree": deg, "n_mles": 3, "parallelism": f"hypercube slices x{world}", "eq": getattr(args, "eq", "virtual"),
                        "exchange": "in-kernel: last block stores its 3 ext partials into every peer's NVLink-mapped mailbox, waits for the N flags, sums mod p; replicated host transcript; all-gather of the final local elements + replicated tail",
                        "l2": f"per-GPU inputs {3 * 16 * n_local >> 20} MiB"},
             "points_per_s": n / (ms * 1e-3), "rounds_per_s": k / (ms * 1e-3),

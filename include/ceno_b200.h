@@ -68,7 +68,9 @@ typedef struct cg_mle_desc {
  * same final evaluation eq(w, r)); for the shape eq*A*B (one degree-3 product, coefficient 1) the large
  * rounds then run the split-eq kernel, which never streams or folds an eq table.  This is what the
  * reference's virtual device MLEs are for (GpuVirtualInterleavedExt, ceno_zkvm/src/scheme/gpu/mod.rs:2195-2268):
- * hand the device a description instead of 2^k elements.  Not accepted by cg_sumcheck_prove_sharded yet. */
+ * hand the device a description instead of 2^k elements.  In cg_sumcheck_prove_sharded the point is the GLOBAL one
+ * (num_vars_global ext) although num_vars is the local count: the rank's constant factor eq(w_top, rank) is derived
+ * by the library.  Not accepted together with cg_sumcheck_attach_comm (step API). */
 #define CG_MLE_EQ 2u
 
 /* ---- lifecycle / memory: replaces cuda_hal context + mem_pool

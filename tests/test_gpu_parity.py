@@ -485,6 +485,62 @@ def _dist_gpu_worker(rank, world, k, port, q):
     dist.destroy_process_group()
 
 
+def _dist_gpu_worker_veq(rank, world, k, port, q):
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import ceno_b200 as cb
+    g = world.bit_length() - 1
+    kl, nl = k - g, 1 << (k - g)
+    dev = cb.Device(rank)
+    w = orc.fill_ext(0xE9, k)
+    a, b = orc.fill_ext(1, 1 << k), orc.fill_ext(2, 1 << k)
+    sl = slice(2 * rank * nl, 2 * (rank + 1) * nl)
+    mles = [cb.EqPolynomial(dev, w, num_vars=kl)] + [cb.MultilinearExtension.from_evaluations_ext_vec(dev, kl, x[sl]) for x in (a, b)]
+    terms = [([1, 0], [0, 1, 2])]
+    want = orc.sumcheck_prove([(orc.build_eq_x_r_vec(w), True, k), (a, True, k), (b, True, k)], terms, k, 3, transcript=orc.Transcript(b"dv"))
+
+    def xchg(blob):
+        outs = [None] * world
+        dist.all_gather_object(outs, blob)
+        return outs
+    comm = cb.Comm(dev, rank, world, xchg, barrier=dist.barrier)
+    ok = True
+    for dc, flags in ((False, 0), (True, 0), (True, cb.IOPProverState.NO_MID), (False, cb.IOPProverState.FORCE_GENERIC)):
+        got = cb.prove_sharded(dev, comm, mles, terms, k, 3, cb.StandInTranscript(b"dv"), flags=flags, device_challenger=dc)
+        ok = ok and all(np.array_equal(x, y) for x, y in zip(got, want))
+    comm.close()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_sharded_virtual_eq_multi_gpu_bit_exact():
+    """The virtual eq under hypercube sharding: every rank passes the GLOBAL point, the library derives the
+    rank factor eq(w_top, rank); split-eq rounds when the local slice has >= 20 variables, scaled table otherwise."""
+    import torch
+    import torch.multiprocessing as mp
+    world = 1
+    while world * 2 <= min(torch.cuda.device_count(), 8):
+        world *= 2
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dist_gpu_worker_veq, args=(r, world, 22, 29653, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, True) for r in range(world)]
+
+
 def test_sharded_sumcheck_multi_gpu_bit_exact():
     import torch
     import torch.multiprocessing as mp

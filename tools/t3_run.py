@@ -1,5 +1,5 @@
 """Minimal T3-k driver for ncu captures: a few sumcheck steps with resident inputs, nothing else.
-usage: python tools/t3_run.py [k] [steps] [host|device]"""
+usage: python tools/t3_run.py [k] [steps] [host|device] [table|virtual]"""
 import os
 import sys
 
@@ -14,7 +14,8 @@ dev = cb.Device(0)
 n = 1 << k
 a = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, synth.fill_ext(0xC0FFEE ^ 1, n))
 b = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, synth.fill_ext(0xC0FFEE ^ 2, n))
-eq = cb.build_eq_x_r_vec(dev, synth.fill_ext(0xE9, k))
+virt = len(sys.argv) > 4 and sys.argv[4] == "virtual"
+eq = cb.EqPolynomial(dev, synth.fill_ext(0xE9, k)) if virt else cb.build_eq_x_r_vec(dev, synth.fill_ext(0xE9, k))
 for _ in range(steps):
     out = cb.IOPProverState.prove(dev, [eq, a, b], [([1, 0], [0, 1, 2])], k, 3, transcript=cb.StandInTranscript(b"bench"),
                                   device_challenger=(mode == "device"))
