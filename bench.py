@@ -325,13 +325,18 @@ def _physical_cores():
 def _cpu_env():
     """The CPU arm runs one thread per physical core, spread and pinned (measured on the 2x32-core host: 128 SMT
     threads are ~10x slower than 64 pinned cores for this memory-bound integer loop).  Must run before libgomp loads."""
+    if "--impl" in sys.argv and os.environ.get("TORCHELASTIC_RUN_ID"):
+        os.environ["OMP_NUM_THREADS"] = str(_physical_cores())   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core
     os.environ.setdefault("OMP_NUM_THREADS", str(_physical_cores()))
     os.environ.setdefault("OMP_PROC_BIND", "spread")
     os.environ.setdefault("OMP_PLACES", "cores")
 
 
 def main():
-    _cpu_env()
+    # N>1 ranks must NOT bind: every rank would pin its main thread to the same first core, and the ranks' host
+    # transcript loops (which answer each other's in-kernel exchange) would time-slice one core (measured: 52 ms/step)
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1 or "--impl" in sys.argv:
+        _cpu_env()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
