@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "lib", "libceno_b200.so")
+SO = os.environ.get("CENO_B200_LIB") or os.path.join(HERE, "lib", "libceno_b200.so")   # override: kernel A/B experiments only
 
 CG_OK = 0
 ERR_NAMES = {1: "CG_ERR_CUDA", 2: "CG_ERR_INVALID", 3: "CG_ERR_UNSUPPORTED", 4: "CG_ERR_OOM", 5: "CG_ERR_NO_DEVICE", 6: "CG_ERR_STATE"}

@@ -999,8 +999,7 @@ static int launch_veq(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro
     a.fin.r = sc->pending_r;
     a.fin.r_ptr = sc->pending_r_ptr;
     a.out_ = ro;
-    static const int minb = []() { const char* e = getenv("CG_VEQ_MINB"); const int x = e ? atoi(e) : 2; return x == 1 || x == 3 ? x : 2; }();
-    uint64_t blocks = (uint64_t)c->sm_count * minb;
+    uint64_t blocks = (uint64_t)c->sm_count * 2;
     if (blocks > a.n_rows) blocks = a.n_rows;
     const unsigned grid = (unsigned)blocks;
     const bool canon = (src == 0);
@@ -1024,7 +1023,9 @@ static int launch_veq(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro
         if (!fold) veq_tma_kernel<false, false><<<(unsigned)tb, 256, VeqTmaCfg<false>::SMEM, sc->stream>>>(a);
         else if (canon) veq_tma_kernel<true, true><<<(unsigned)tb, 256, VeqTmaCfg<true>::SMEM, sc->stream>>>(a);
         else veq_tma_kernel<true, false><<<(unsigned)tb, 256, VeqTmaCfg<true>::SMEM, sc->stream>>>(a);
-    } else if (minb == 1) CG_VEQ_LAUNCH(1); else if (minb == 3) CG_VEQ_LAUNCH(3); else CG_VEQ_LAUNCH(2);
+    } else {         // CG_VEQ_TMA=0: the same round with plain 256-bit loads (A/B comparison)
+        CG_VEQ_LAUNCH(2);
+    }
 #undef CG_VEQ_LAUNCH
     LAUNCHED(c);
     CU(c, cudaGetLastError());

@@ -89,6 +89,57 @@ GL_DEV void acc_mac(acc_t& A, uint64_t a, uint64_t b) {
     A.m0 = (uint32_t)M; A.m1 = (uint32_t)(M >> 32); A.m2 = (uint32_t)(M >> 64);
 #endif
 }
+// A = a*b into a FRESH accumulator: no zero-fill, the only possible carry is the second cross product's
+// (4 IMAD.WIDE + 1 carry add instead of 8 register clears + 4 IMAD.WIDE + 3 carry adds)
+GL_DEV void acc_mul(acc_t& A, uint64_t a, uint64_t b) {
+    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t"
+        ".reg .b64 t;\n\t"
+        "mul.wide.u32 t, %8, %10;\n\t"
+        "mov.b64 {%0, %1}, t;\n\t"
+        "mul.wide.u32 t, %9, %11;\n\t"
+        "mov.b64 {%2, %3}, t;\n\t"
+        "mul.wide.u32 t, %8, %11;\n\t"
+        "mov.b64 {%5, %6}, t;\n\t"
+        "mad.lo.cc.u32 %5, %9, %10, %5;\n\t"
+        "madc.hi.cc.u32 %6, %9, %10, %6;\n\t"
+        "addc.u32 %7, 0, 0;\n\t"
+        "mov.u32 %4, 0;\n\t"
+        "}"
+        : "=&r"(A.e0), "=&r"(A.e1), "=&r"(A.e2), "=&r"(A.e3), "=&r"(A.e4), "=&r"(A.m0), "=&r"(A.m1), "=&r"(A.m2)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+#else
+    acc_zero(A);
+    acc_mac(A, a, b);
+#endif
+}
+// A = x + a*b into a FRESH accumulator (the fold's x + r d): x rides in the low product's addend, the carry
+// runs through the high product and cannot leave it (a1 b1 + 1 < 2^64)
+GL_DEV void acc_fma_first(acc_t& A, uint64_t x, uint64_t a, uint64_t b) {
+    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+#if defined(__CUDA_ARCH__)
+    const uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32);
+    asm("{\n\t"
+        ".reg .b64 t;\n\t"
+        "mad.lo.cc.u32 %0, %8, %10, %12;\n\t"
+        "madc.hi.cc.u32 %1, %8, %10, %13;\n\t"
+        "madc.lo.cc.u32 %2, %9, %11, 0;\n\t"
+        "madc.hi.u32 %3, %9, %11, 0;\n\t"
+        "mul.wide.u32 t, %8, %11;\n\t"
+        "mov.b64 {%5, %6}, t;\n\t"
+        "mad.lo.cc.u32 %5, %9, %10, %5;\n\t"
+        "madc.hi.cc.u32 %6, %9, %10, %6;\n\t"
+        "addc.u32 %7, 0, 0;\n\t"
+        "mov.u32 %4, 0;\n\t"
+        "}"
+        : "=&r"(A.e0), "=&r"(A.e1), "=&r"(A.e2), "=&r"(A.e3), "=&r"(A.e4), "=&r"(A.m0), "=&r"(A.m1), "=&r"(A.m2)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(x0), "r"(x1));
+#else
+    acc_set64(A, x);
+    acc_mac(A, a, b);
+#endif
+}
 // x = l0 + l1 2^32 + l2 2^64 + l3 2^96 + l4 2^128 (l4 < 2^31) -> some u64 congruent to x ("weak"):
 //   x = (l1:l0) + (l2 << 32) - (l2 + l3 + (l4 << 32))   (2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32)
 //   T = (l1:l0) + (l2 << 32) (carry c), U = T - Z (borrow b), result = U + (c - b) EPS  — never wraps twice.
@@ -255,9 +306,33 @@ GL_DEV uint64_t gl_mul_weak(uint64_t a, uint64_t b) {
 GL_DEV uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_canon(gl_mul_weak(a, b)); }
 // 7 a for any u64 a -> weak   (7a < 2^67)
 GL_DEV uint64_t gl_mul7_weak(uint64_t a) {
-    uint64_t lo, hi;
-    gl_mulwide(a, 7ULL, lo, hi);
-    return acc_reduce_weak(lo, hi, 0);
+#if defined(__CUDA_ARCH__)
+    // 7a = (u0:t0) + u1 2^64 with u1 <= 6, and 2^64 = EPS: two wrap-free corrections (5 instructions)
+    uint64_t r;
+    asm("{\n\t"
+        ".reg .u32 x0, x1, t0, t1, u0, u1, v0, v1, c;\n\t"
+        ".reg .b64 t, u, v;\n\t"
+        "mov.b64 {x0, x1}, %1;\n\t"
+        "mul.wide.u32 t, x0, 7;\n\t"
+        "mov.b64 {t0, t1}, t;\n\t"
+        "mov.b64 u, {t1, 0};\n\t"
+        "mad.wide.u32 u, x1, 7, u;\n\t"
+        "mov.b64 {u0, u1}, u;\n\t"
+        "mad.lo.cc.u32 v0, u1, 0xFFFFFFFF, t0;\n\t"
+        "madc.hi.cc.u32 v1, u1, 0xFFFFFFFF, u0;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "mov.b64 v, {v0, v1};\n\t"
+        "mad.wide.u32 %0, c, 0xFFFFFFFF, v;\n\t"
+        "}"
+        : "=l"(r) : "l"(a));
+    return r;
+#else
+    unsigned __int128 x = (unsigned __int128)a * 7;
+    unsigned __int128 v = (unsigned __int128)(uint64_t)x + (unsigned __int128)(uint64_t)(x >> 64) * GL_EPS;
+    uint64_t lo = (uint64_t)v;
+    if ((uint64_t)(v >> 64)) lo += GL_EPS;   // cannot wrap again
+    return lo;
+#endif
 }
 
 // ---------------------------------------------------------------- extension
@@ -284,6 +359,13 @@ GL_DEV void eacc_mac(eacc& E, ext_t a, ext_t b, uint64_t b1_7) {
     acc_mac(E.A1, a.c0, b.c1);
     acc_mac(E.A1, a.c1, b.c0);
 }
+// E = a * b (fresh accumulators)
+GL_DEV void eacc_mul(eacc& E, ext_t a, ext_t b, uint64_t b1_7) {
+    acc_mul(E.A0, a.c0, b.c0);
+    acc_mac(E.A0, a.c1, b1_7);
+    acc_mul(E.A1, a.c0, b.c1);
+    acc_mac(E.A1, a.c1, b.c0);
+}
 GL_DEV void ecacc_add(ecacc& C, const eacc& E) { cacc_add(C.A0, E.A0); cacc_add(C.A1, E.A1); }
 GL_DEV ext_t ecacc_canon(const ecacc& C) { return ext_make(cacc_canon(C.A0), cacc_canon(C.A1)); }
 GL_DEV ext_t eacc_weak(const eacc& E) { return ext_make(acc_weak(E.A0), acc_weak(E.A1)); }
@@ -305,24 +387,34 @@ GL_DEV void eacc_mac_prep(eacc& E, ext_t a, const extmul_t& b) {
 // a * b for any u64 limbs; weak / canonical result
 GL_DEV ext_t ext_mul_weak(ext_t a, ext_t b) {
     eacc E;
-    eacc_zero(E);
-    eacc_mac(E, a, b, gl_mul7_weak(b.c1));
+    eacc_mul(E, a, b, gl_mul7_weak(b.c1));
     return eacc_weak(E);
 }
 GL_DEV ext_t ext_mul(ext_t a, ext_t b) { return ext_canon(ext_mul_weak(a, b)); }
+GL_DEV void eacc_mul_prep(eacc& E, ext_t a, const extmul_t& b) {
+    acc_mul(E.A0, a.c0, b.c0);
+    acc_mac(E.A0, a.c1, b.c1_7);
+    acc_mul(E.A1, a.c0, b.c1);
+    acc_mac(E.A1, a.c1, b.c0);
+}
 GL_DEV ext_t ext_mul_prep(ext_t a, const extmul_t& b) {
     eacc E;
-    eacc_zero(E);
-    eacc_mac_prep(E, a, b);
+    eacc_mul_prep(E, a, b);
     return eacc_canon(E);
+}
+GL_DEV ext_t ext_mul_prep_weak(ext_t a, const extmul_t& b) {
+    eacc E;
+    eacc_mul_prep(E, a, b);
+    return eacc_weak(E);
 }
 GL_DEV ext_t ext_mul_base(ext_t a, uint64_t b) { return ext_make(gl_mul(a.c0, b), gl_mul(a.c1, b)); }
 // x + d * r  (the fold), one reduction per limb; x canonical or not, result canonical
 GL_DEV ext_t ext_fma_prep(ext_t x, ext_t d, const extmul_t& r) {
-    eacc E;
-    acc_set64(E.A0, x.c0);        // x rides in the accumulator: no separate modular add
-    acc_set64(E.A1, x.c1);
-    eacc_mac_prep(E, d, r);
+    eacc E;                       // x rides in the accumulator: no separate modular add
+    acc_fma_first(E.A0, x.c0, d.c0, r.c0);
+    acc_mac(E.A0, d.c1, r.c1_7);
+    acc_fma_first(E.A1, x.c1, d.c0, r.c1);
+    acc_mac(E.A1, d.c1, r.c0);
     return eacc_canon(E);
 }
 

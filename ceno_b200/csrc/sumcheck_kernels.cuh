@@ -295,8 +295,7 @@ struct TowerArgs {
 // H[t] += u * e for the three points; e given as (value at t=1, nd)
 GL_DEV void accumulate_point(ecacc& H, ext_t u, ext_t e) {
     eacc T;
-    eacc_zero(T);
-    eacc_mac(T, u, e, gl_mul7_weak(e.c1));
+    eacc_mul(T, u, e, gl_mul7_weak(e.c1));
     ecacc_add(H, T);   // long-lived sums stay compact (5 limbs); the 4 products accumulate in aligned limb pairs
 }
 
@@ -333,8 +332,7 @@ GL_DEV void tower_item(const TowerArgs& a, L& ld, uint64_t item, ecacc (&H)[3]) 
 #pragma unroll
             for (int t = 0; t < 3; t++) {
                 eacc T;
-                eacc_zero(T);
-                eacc_mac(T, av, bv, gl_mul7_weak(bv.c1));
+                eacc_mul(T, av, bv, gl_mul7_weak(bv.c1));
                 ecacc_add(in[t], T);
                 if (t < 2) { av = ext_sub(av, and_); bv = ext_sub(bv, bnd); }
             }
@@ -464,12 +462,6 @@ GL_DEV ulonglong4 ld_tab(const ulonglong4* p) {   // read-only table entry, one 
     asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v.x), "=l"(v.y), "=l"(v.z), "=l"(v.w) : "l"(p));
     return v;
 }
-GL_DEV ext_t ext_mul_prep_weak(ext_t a, const extmul_t& b) {
-    eacc E;
-    eacc_zero(E);
-    eacc_mac_prep(E, a, b);
-    return eacc_weak(E);
-}
 // one pair: weight A by W, accumulate the three bilinear sums (operands may be any u64 — no canonical form needed)
 GL_DEV void veq_item(ext_t alo, ext_t ahi, ext_t blo, ext_t bhi, const extmul_t& W, eacc& S00, eacc& S11, eacc& Sx) {
     const ext_t wl = ext_mul_prep_weak(alo, W), wh = ext_mul_prep_weak(ahi, W);
@@ -580,6 +572,7 @@ __global__ void __launch_bounds__(256, 2) veq_tma_kernel(const __grid_constant__
     eacc Sf, Ss, Sx;   // first*first, second*second, cross
     eacc_zero(Sf); eacc_zero(Ss); eacc_zero(Sx);
     uint32_t s = 0, ph = 0;
+#pragma unroll 1   // measured: unrolling by 2 costs registers (spills) and 8 % of the round time
     for (uint32_t i = 0; i < nrows; i++) {
         if (tid == 0 && i >= 1 && i - 1 + STAGES < nrows) {   // refill the stage released one row ago
             const uint32_t ps = (i - 1) % STAGES, pph = ((i - 1) / STAGES) & 1;

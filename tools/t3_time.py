@@ -23,5 +23,5 @@ for i in range(reps + 3):
     if i >= 3:
         prof.append(dev.profile_last())
 p = np.mean(np.array(prof), axis=0)
-print("virtual" if virt else "table", "minb", os.environ.get("CG_VEQ_MINB", "2"), "cfg", os.environ.get("CG_TOWER_CFG", "0"), "total_ms %.4f" % p.sum(), "r0 %.4f r1 %.4f r2 %.4f r3 %.4f" % tuple(p[:4]), "tail(sum r10..) %.4f" % p[10:].sum(), "rounds", np.round(p[:8], 4).tolist())
+print("virtual" if virt else "table", "tma", os.environ.get("CG_VEQ_TMA", "1"), "cfg", os.environ.get("CG_TOWER_CFG", "0"), "total_ms %.4f" % p.sum(), "r0 %.4f r1 %.4f r2 %.4f r3 %.4f" % tuple(p[:4]), "tail(sum r10..) %.4f" % p[10:].sum(), "rounds", np.round(p[:8], 4).tolist())
 dev.close()
