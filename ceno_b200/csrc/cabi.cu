@@ -668,7 +668,7 @@ static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles,
     for (uint32_t i = 0; i < n_mles; i++) {
         if (mles[i].num_vars != num_vars)
             return set_err(c, CG_ERR_UNSUPPORTED,
-                           "mixed num_vars (frontloaded batched sumcheck) is defined only in the un-vendored upstream crate (SURVEY §C-1)");
+                           "mixed num_vars (the frontloaded batched main sumcheck) is served by cg_sumcheck_prove, not by the step API");
         if (mles[i].is_ext == CG_MLE_EQ) {   // virtual eq: dptr is the HOST point
             if (!mles[i].dptr && num_vars) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: virtual eq MLE without a point");
             continue;
@@ -1470,11 +1470,138 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
     return CG_OK;
 }
 
+// ---- mixed sizes: the cross-chip batched main sumcheck (prove_batched_main_constraints,
+// ceno_zkvm/src/scheme/cpu/mod.rs:1052-1390; GPU call site ceno_zkvm/src/scheme/gpu/mod.rs:2968-2981).
+// An MLE f with k' < k variables stands for F(x) = f(x_0..x_{k'-1}) * prod_{j>=k'} x_j ("frontload"): pinned by the
+// verifier's final claim (ceno_zkvm/src/scheme/verifier.rs:180-238) as restated in
+// ceno_recursion_v2/src/main/mod.rs:3414-3448.  Every term lives in one chip, i.e. its factors share one k'.  So
+//   rounds j <  k': the term's round polynomial is the chip's own sumcheck round over its 2^(k'-j-1) pairs;
+//   rounds j >= k': it is  scalar * prod_i c_i * X^(#factors),  c_i = f_i(r_<k') * prod_{k'<=l<j} r_l.
+// The library runs one uniform sub-sumcheck per size class in lockstep (all device kernels as usual) and adds the
+// closed-form contributions of the collapsed classes on the host (a handful of field multiplications per round,
+// next to the transcript).  Reported final evaluations are the raw f_i(r_<k') (cpu/mod.rs:1346-1358).
+static inline uint64_t hx_mulmod(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) % GL_P); }
+static inline uint64_t hx_addmod(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a + b) % GL_P); }
+static inline ext_t hx_mul(ext_t a, ext_t b) {
+    return ext_t{hx_addmod(hx_mulmod(a.c0, b.c0), hx_mulmod(7, hx_mulmod(a.c1, b.c1))), hx_addmod(hx_mulmod(a.c0, b.c1), hx_mulmod(a.c1, b.c0))};
+}
+static inline ext_t hx_add(ext_t a, ext_t b) { return ext_t{hx_addmod(a.c0, b.c0), hx_addmod(a.c1, b.c1)}; }
+static bool mles_mixed(const cg_mle_desc* mles, uint32_t n_mles, uint32_t num_vars) {
+    for (uint32_t i = 0; i < n_mles; i++) if (mles && mles[i].num_vars != num_vars) return true;
+    return false;
+}
+static int sc_prove_mixed(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t* coeff, const uint32_t* off,
+                          const uint32_t* idx, uint32_t n_terms, uint32_t num_vars, uint32_t degree, uint32_t flags,
+                          cg_challenge_cb cb, void* user, uint64_t* h_rounds, uint64_t* h_final, uint64_t* h_chal, cg_stream s) {
+    if (degree == 0 || degree > CG_MAX_DEGREE) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_prove: degree must be in 1..8");
+    struct Class {
+        uint32_t kv = 0;
+        std::vector<uint32_t> mle_ids;                  // global MLE index of local MLE l
+        std::vector<cg_mle_desc> descs;
+        std::vector<uint64_t> t_coeff;
+        std::vector<uint32_t> t_off{0}, t_idx;          // local term tables
+        cg_sumcheck* sc = nullptr;
+        std::vector<ext_t> cval;                        // collapsed: c_i per local MLE
+        bool collapsed = false;
+    };
+    std::map<uint32_t, Class> classes;
+    std::vector<uint32_t> local_of(n_mles, 0);
+    for (uint32_t i = 0; i < n_mles; i++) {
+        if (mles[i].num_vars > num_vars) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_prove: an MLE has more variables than the sumcheck");
+        if (mles[i].is_ext == CG_MLE_EQ) return set_err(c, CG_ERR_UNSUPPORTED, "mixed-size sumcheck: virtual eq MLEs are not supported");
+        Class& cl = classes[mles[i].num_vars];
+        cl.kv = mles[i].num_vars;
+        local_of[i] = (uint32_t)cl.mle_ids.size();
+        cl.mle_ids.push_back(i);
+        cl.descs.push_back(mles[i]);
+    }
+    for (uint32_t t = 0; t < n_terms; t++) {
+        if (off[t + 1] <= off[t]) return set_err(c, CG_ERR_UNSUPPORTED, "mixed-size sumcheck: constant terms are not supported");
+        if (off[t + 1] - off[t] > degree) return set_err(c, CG_ERR_INVALID, "term has more factors than `degree`");
+        for (uint32_t q = off[t]; q < off[t + 1]; q++)
+            if (idx[q] >= n_mles) return set_err(c, CG_ERR_INVALID, "term references an MLE index out of range");
+        const uint32_t kv = mles[idx[off[t]]].num_vars;
+        for (uint32_t q = off[t]; q < off[t + 1]; q++)
+            if (mles[idx[q]].num_vars != kv)
+                return set_err(c, CG_ERR_UNSUPPORTED, "mixed-size sumcheck: the factors of a term must share one num_vars (one chip)");
+        Class& cl = classes[kv];
+        cl.t_coeff.push_back(coeff[2 * t] % GL_P);
+        cl.t_coeff.push_back(coeff[2 * t + 1] % GL_P);
+        for (uint32_t q = off[t]; q < off[t + 1]; q++) cl.t_idx.push_back(local_of[idx[q]]);
+        cl.t_off.push_back((uint32_t)cl.t_idx.size());
+    }
+    int rc = CG_OK;
+    auto cleanup = [&]() { for (auto& kv : classes) if (kv.second.sc) cg_sumcheck_destroy(kv.second.sc); };
+    for (auto& kv : classes) {
+        Class& cl = kv.second;
+        const uint32_t nt = (uint32_t)cl.t_off.size() - 1;
+        rc = sc_create_terms(c, cl.descs.data(), (uint32_t)cl.descs.size(), nt ? cl.t_coeff.data() : nullptr, nt ? cl.t_off.data() : nullptr,
+                             nt ? cl.t_idx.data() : nullptr, nt, cl.kv, degree, flags & ~CG_SC_PROFILE, s, nullptr, &cl.sc);
+        if (rc != CG_OK) { cleanup(); return rc; }
+    }
+    std::vector<uint64_t> tmp(2 * (size_t)degree), fin(2 * (size_t)(n_mles ? n_mles : 1));
+    auto collapse = [&](Class& cl) -> int {   // all of the class's variables are bound: fetch the raw evaluations
+        std::vector<uint64_t> f(2 * cl.descs.size());
+        CHK(cg_sumcheck_final_evals(cl.sc, f.data()));
+        cl.cval.resize(cl.descs.size());
+        for (size_t l = 0; l < cl.descs.size(); l++) {
+            cl.cval[l] = ext_t{f[2 * l], f[2 * l + 1]};
+            fin[2 * cl.mle_ids[l]] = f[2 * l];
+            fin[2 * cl.mle_ids[l] + 1] = f[2 * l + 1];
+        }
+        cl.collapsed = true;
+        return CG_OK;
+    };
+    for (auto& kv : classes) if (kv.second.kv == 0 && rc == CG_OK) rc = collapse(kv.second);
+    for (uint32_t j = 0; j < num_vars && rc == CG_OK; j++) {
+        std::vector<ext_t> msg(degree, ext_t{0, 0});
+        for (auto& kv : classes) {
+            Class& cl = kv.second;
+            if (!cl.collapsed) {
+                rc = cg_sumcheck_round_eval(cl.sc, tmp.data());
+                if (rc != CG_OK) break;
+                for (uint32_t x = 0; x < degree; x++) msg[x] = hx_add(msg[x], ext_t{tmp[2 * x], tmp[2 * x + 1]});
+            } else {
+                const uint32_t nt = (uint32_t)cl.t_off.size() - 1;
+                for (uint32_t t = 0; t < nt; t++) {
+                    ext_t v{cl.t_coeff[2 * t], cl.t_coeff[2 * t + 1]};
+                    const uint32_t d = cl.t_off[t + 1] - cl.t_off[t];
+                    for (uint32_t q = cl.t_off[t]; q < cl.t_off[t + 1]; q++) v = hx_mul(v, cl.cval[cl.t_idx[q]]);
+                    for (uint32_t x = 0; x < degree; x++) {
+                        uint64_t pw = 1;
+                        for (uint32_t e = 0; e < d; e++) pw = hx_mulmod(pw, x + 1);
+                        msg[x] = hx_add(msg[x], ext_t{hx_mulmod(v.c0, pw), hx_mulmod(v.c1, pw)});
+                    }
+                }
+            }
+        }
+        if (rc != CG_OK) break;
+        uint64_t* m = h_rounds + (size_t)j * degree * 2;
+        for (uint32_t x = 0; x < degree; x++) { m[2 * x] = msg[x].c0; m[2 * x + 1] = msg[x].c1; }
+        uint64_t r[2] = {0, 0};
+        cb(user, j, m, degree, r);
+        if (h_chal) { h_chal[2 * j] = r[0]; h_chal[2 * j + 1] = r[1]; }
+        const ext_t re{r[0] % GL_P, r[1] % GL_P};
+        for (auto& kv : classes) {
+            Class& cl = kv.second;
+            if (cl.collapsed) { for (auto& cv : cl.cval) cv = hx_mul(cv, re); continue; }
+            rc = cg_sumcheck_bind(cl.sc, r);
+            if (rc == CG_OK && cl.kv == j + 1) rc = collapse(cl);
+            if (rc != CG_OK) break;
+        }
+    }
+    if (rc == CG_OK && h_final) memcpy(h_final, fin.data(), sizeof(uint64_t) * 2 * n_mles);
+    cleanup();
+    return rc;
+}
+
 CG_EXPORT int cg_sumcheck_prove(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t* coeff,
                                 const uint32_t* off, const uint32_t* idx, uint32_t n_terms, uint32_t num_vars,
                                 uint32_t degree, uint32_t flags, cg_challenge_cb cb, void* user, uint64_t* h_rounds,
                                 uint64_t* h_final, uint64_t* h_chal, cg_stream s) {
     if (!cb || (!h_rounds && num_vars)) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_prove: null callback/output");
+    if (c && mles_mixed(mles, n_mles, num_vars))
+        return sc_prove_mixed(c, mles, n_mles, coeff, off, idx, n_terms, num_vars, degree, flags, cb, user, h_rounds, h_final, h_chal, s);
     cg_sumcheck* sc = nullptr;
     CHK(cg_sumcheck_create(c, mles, n_mles, coeff, off, idx, n_terms, num_vars, degree, flags, s, &sc));
     int rc = sc_run_host(sc, cb, user, h_rounds, h_final, h_chal);
@@ -1535,6 +1662,9 @@ CG_EXPORT int cg_sumcheck_prove_standin_device(cg_ctx* c, const cg_mle_desc* mle
                                                uint32_t degree, uint32_t flags, uint64_t* h_state, uint64_t* h_rounds,
                                                uint64_t* h_final, uint64_t* h_chal, cg_stream s) {
     if (!h_state || (!h_rounds && num_vars)) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_prove_standin_device: null output");
+    if (c && mles_mixed(mles, n_mles, num_vars))   // mixed sizes: the class lockstep runs on the host; same stand-in sponge, same proof
+        return sc_prove_mixed(c, mles, n_mles, coeff, off, idx, n_terms, num_vars, degree, flags, cg_standin_challenge_cb, h_state,
+                              h_rounds, h_final, h_chal, s);
     cg_sumcheck* sc = nullptr;
     CHK(cg_sumcheck_create(c, mles, n_mles, coeff, off, idx, n_terms, num_vars, degree, flags, s, &sc));
     int rc = sc_run_device(sc, h_state, h_rounds, h_final, h_chal);

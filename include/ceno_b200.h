@@ -137,8 +137,13 @@ int cg_mle_evaluate(cg_ctx* ctx, const cg_mle_desc* mle, const uint64_t* h_point
  *   term_offsets   : n_terms+1 u32 (HOST), CSR offsets into term_mle_idx
  *   term_mle_idx   : indices into `mles`
  * Round message = [p(1) .. p(degree)] (p(0) is not sent).
- * All MLEs must have num_vars variables; mixed sizes ("frontload") return CG_ERR_UNSUPPORTED
- * because that embedding is defined only in the un-vendored upstream crate. */
+ * Mixed sizes — the cross-chip batched main sumcheck, prove_batched_main_constraints
+ * (ceno_zkvm/src/scheme/cpu/mod.rs:1052-1390, GPU call ceno_zkvm/src/scheme/gpu/mod.rs:2968-2981): an MLE with
+ * k' < num_vars variables stands for F(x) = f(x_0..x_{k'-1}) * prod_{j>=k'} x_j ("frontload"; verifier.rs:180-238,
+ * restated in ceno_recursion_v2/src/main/mod.rs:3414-3448).  cg_sumcheck_prove / _standin_device accept such lists
+ * when the factors of every term share one num_vars (one chip) and no term is a bare constant; the final evaluation
+ * reported for a small MLE is the raw f(r_0..r_{k'-1}).  The step API (cg_sumcheck_create ...) and the sharded
+ * prove take uniform sizes only. */
 #define CG_SC_DEFAULT 0u
 #define CG_SC_FORCE_GENERIC 1u /* disable shape-specialised kernels (testing) */
 #define CG_SC_NO_FUSE 2u       /* separate fold and eval launches (testing / profiling) */

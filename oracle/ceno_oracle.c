@@ -339,19 +339,30 @@ OR_API int or_sumcheck_prove(const or_mle* mles, uint32_t n_mles, const uint64_t
                              uint32_t num_vars, uint32_t degree, or_challenge_fn cb, void* user,
                              uint64_t* round_evals, uint64_t* final_evals, uint64_t* challenges) {
     if (degree > OR_MAX_DEG || degree == 0) return -1;
-    for (uint32_t i = 0; i < n_mles; i++) if (mles[i].num_vars != num_vars) return -2; /* frontload: upstream-only */
+    for (uint32_t i = 0; i < n_mles; i++) if (mles[i].num_vars > num_vars) return -2;
+    /* Mixed sizes ("frontload", the cross-chip batched main sumcheck, ceno_zkvm/src/scheme/cpu/mod.rs:1332-1360):
+     * an MLE f with k' < k variables stands for  F(x) = f(x_0..x_{k'-1}) * prod_{j >= k'} x_j , i.e. the dense
+     * table that holds f in its LAST 2^k' entries and zero elsewhere.  Pinned in-tree by the verifier's final
+     * claim, restated in ceno_recursion_v2/src/main/mod.rs:3414-3448 (every factor's evaluation is multiplied by
+     * every tail challenge) and by ceno_zkvm/src/scheme/verifier.rs:233-237.  The final evaluation reported for
+     * such an MLE is the raw f(r_0..r_{k'-1}) (the callers multiply the tail themselves, cpu/mod.rs:1346-1358).
+     * This restatement simply runs the uniform prover on the dense embedding. */
     uint64_t n = 1ULL << num_vars;
     ext** f = (ext**)malloc(sizeof(ext*) * n_mles);
     ext** g = (ext**)malloc(sizeof(ext*) * n_mles);
+    ext** raw = (ext**)calloc(n_mles, sizeof(ext*));
     for (uint32_t i = 0; i < n_mles; i++) {
         f[i] = (ext*)malloc(sizeof(ext) * n);
         g[i] = (ext*)malloc(sizeof(ext) * (n / 2 ? n / 2 : 1));
         const uint64_t* d = mles[i].data;
-        if (mles[i].is_ext) memcpy(f[i], d, sizeof(ext) * n);
+        const uint64_t ni = 1ULL << mles[i].num_vars, off = n - ni;
+        if (off) memset(f[i], 0, sizeof(ext) * off);
+        if (mles[i].is_ext) memcpy(f[i] + off, d, sizeof(ext) * ni);
         else {
 #pragma omp parallel for schedule(static)
-            for (uint64_t b = 0; b < n; b++) f[i][b] = ext_from(d[b]);
+            for (uint64_t b = 0; b < ni; b++) f[i][off + b] = ext_from(d[b]);
         }
+        if (off) { raw[i] = (ext*)malloc(sizeof(ext) * ni); memcpy(raw[i], f[i] + off, sizeof(ext) * ni); }
     }
     const ext* coeff = (const ext*)term_coeff;
     int nthr = 1;
@@ -401,12 +412,19 @@ OR_API int or_sumcheck_prove(const or_mle* mles, uint32_t n_mles, const uint64_t
 #pragma omp parallel for schedule(static)
             for (uint64_t b = 0; b < half; b++) dst[b] = ext_add(src[2 * b], ext_mul(r, ext_sub(src[2 * b + 1], src[2 * b])));
             f[i] = dst; g[i] = src;
+            if (raw[i] && j < mles[i].num_vars) {   /* the raw small MLE follows its own first k' challenges */
+                const uint64_t h2 = 1ULL << (mles[i].num_vars - j - 1);
+                for (uint64_t b = 0; b < h2; b++) raw[i][b] = ext_add(raw[i][2 * b], ext_mul(r, ext_sub(raw[i][2 * b + 1], raw[i][2 * b])));
+            }
         }
         n = half;
     }
-    for (uint32_t i = 0; i < n_mles; i++) { final_evals[2 * i] = f[i][0].c0; final_evals[2 * i + 1] = f[i][0].c1; }
-    for (uint32_t i = 0; i < n_mles; i++) { free(f[i]); free(g[i]); }
-    free(f); free(g); free(part);
+    for (uint32_t i = 0; i < n_mles; i++) {
+        const ext v = raw[i] ? raw[i][0] : f[i][0];
+        final_evals[2 * i] = v.c0; final_evals[2 * i + 1] = v.c1;
+    }
+    for (uint32_t i = 0; i < n_mles; i++) { free(f[i]); free(g[i]); free(raw[i]); }
+    free(f); free(g); free(raw); free(part);
     return 0;
 }
 

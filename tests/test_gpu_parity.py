@@ -279,6 +279,36 @@ def test_zerocheck_layer_shape(dev):
             assert eq_np(g, w)
 
 
+@pytest.mark.parametrize("chip_vars", [[14, 11, 11, 7, 3, 0], [17, 17, 13], [5, 9]])
+def test_batched_main_constraints_mixed_sizes(dev, chip_vars):
+    """prove_batched_main_constraints shape (ceno_zkvm/src/scheme/cpu/mod.rs:1052-1390): one sumcheck over the
+    union of all chips' monomial terms, chips of different num_vars ("frontload" embedding, pinned by
+    tests/test_oracle_kat.py::test_mixed_size_frontload_sumcheck_verifies)."""
+    import ceno_b200 as cb
+    k = max(chip_vars)
+    host, mles, terms = [], [], []
+    rng = random.Random(sum(chip_vars))
+    for c, kv in enumerate(chip_vars):
+        n = 1 << kv
+        base = len(host)
+        sel = orc.build_eq_x_r_vec(rnd_point(300 + c, kv)) if kv else np.array([3, 4], dtype=np.uint64)
+        host.append((sel, True, kv))
+        for wi in range(3):
+            host.append((orc.fill_base(1000 * c + wi, n), False, kv))
+        al = lambda: [rng.randrange(P), rng.randrange(P)]
+        terms += [(al(), [base, base + 1, base + 2]), (al(), [base, base + 3]), (al(), [base, base + 1, base + 2, base + 3]),
+                  (al(), [base + 1])]
+    want = orc.sumcheck_prove(host, terms, k, 4, transcript=orc.Transcript(b"bm"))
+    for d, is_ext, kv in host:
+        mles.append((cb.MultilinearExtension.from_evaluations_ext_vec if is_ext else cb.MultilinearExtension.from_evaluations_vec)(dev, kv, d))
+    for dc in (False, True):
+        got = cb.IOPProverState.prove(dev, mles, terms, k, 4, transcript=cb.StandInTranscript(b"bm"), device_challenger=dc)
+        for g, w in zip(got, want):
+            assert eq_np(g, w)
+    for m in mles:
+        m.free()
+
+
 def test_step_api_and_peek(dev):
     import ceno_b200 as cb
     k = 6
@@ -321,7 +351,7 @@ def test_errors_mirror_reference_behaviour(dev):
     import ceno_b200 as cb
     a = cb.MultilinearExtension.from_evaluations_ext_vec(dev, 3, orc.fill_ext(1, 8))
     b = cb.MultilinearExtension.from_evaluations_ext_vec(dev, 2, orc.fill_ext(2, 4))
-    with pytest.raises(cb.CenoB200Error) as ei:      # mixed num_vars: frontload semantics are upstream-only
+    with pytest.raises(cb.CenoB200Error) as ei:      # mixed num_vars: served by prove(), not by the step API
         cb.IOPProverState(dev, [a, b], [([1, 0], [0, 1])], 3, 2)
     assert ei.value.code == 3
     with pytest.raises(cb.CenoB200Error) as ei:      # term with more factors than the stated degree

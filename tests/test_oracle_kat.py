@@ -264,6 +264,54 @@ def test_sumcheck_matches_pyref_and_verifier_relations(k, degree):
     assert acc == claim
 
 
+@pytest.mark.parametrize("k,sizes,degree", [(5, [5, 3, 3, 0], 3), (6, [2, 2, 6, 6, 4], 4), (4, [4, 1], 2)])
+def test_mixed_size_frontload_sumcheck_verifies(k, sizes, degree):
+    """The cross-chip batched main sumcheck (ceno_zkvm/src/scheme/cpu/mod.rs:1332-1360): MLEs with k' < k variables.
+    Pinned by the verifier's final claim as restated in ceno_recursion_v2/src/main/mod.rs:3414-3448:
+    sum_t scalar_t prod_i (f_i(r_0..r_{k'-1}) * prod_{j>=k'} r_j), with the raw f_i(r_<k') as reported evaluations,
+    and by the claimed sum being the sum of every chip's own hypercube sum."""
+    rng = random.Random(7 * k + degree)
+    mles_p = [[rnd_ext(rng) for _ in range(1 << kv)] for kv in sizes]
+    by_size = {}
+    for i, kv in enumerate(sizes):
+        by_size.setdefault(kv, []).append(i)
+    terms = []
+    for kv, ids in by_size.items():     # every term stays inside one size class (one chip)
+        terms.append((rnd_ext(rng), ids[:degree]))
+        terms.append((rnd_ext(rng), [ids[0]]))
+        if len(ids) >= 2:
+            terms.append((rnd_ext(rng), [ids[-1], ids[0]]))
+    cb = _standin_cb(k)
+    rounds, fin, chal = orc.sumcheck_prove([(ext_arr(x), True, kv) for x, kv in zip(mles_p, sizes)],
+                                           [(list(c), ids) for c, ids in terms], k, degree, challenge_fn=cb)
+    pchal = [tuple(int(x) for x in e) for e in chal]
+    pfin = [tuple(int(x) for x in e) for e in fin]
+    # claimed sum = sum over chips of their own hypercube sums (the padding region contributes nothing)
+    claim = pr.ZERO
+    for c, ids in terms:
+        kv = sizes[ids[0]]
+        for b in range(1 << kv):
+            p_ = c
+            for i in ids:
+                p_ = pr.emul(p_, mles_p[i][b])
+            claim = pr.eadd(claim, p_)
+    for j in range(k):
+        msg = [tuple(int(x) for x in e) for e in rounds[j]]
+        e0 = pr.esub(claim, msg[0])
+        claim = pr.lagrange_eval([e0] + msg, pchal[j])
+    # reported evaluations are the raw small-MLE evaluations at the first k' challenges
+    assert pfin == [pr.mle_evaluate(m_, pchal[:kv]) for m_, kv in zip(mles_p, sizes)]
+    acc = pr.ZERO
+    for c, ids in terms:
+        value = c
+        for i in ids:
+            value = pr.emul(value, pfin[i])
+            for tail in pchal[sizes[i]:]:
+                value = pr.emul(value, tail)
+        acc = pr.eadd(acc, value)
+    assert acc == claim
+
+
 def test_sumcheck_base_field_mles_and_transcript_order():
     rng = random.Random(77)
     k = 5
