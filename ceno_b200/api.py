@@ -388,6 +388,18 @@ def wit_infer_by_monomial_expr(dev, mles, terms, num_vars):
     return MultilinearExtension(dev, out, num_vars, True)
 
 
+def interleaving_mles_to_mles(dev, mles, num_instances, num_limbs, default):
+    """ceno_zkvm/src/scheme/utils.rs:402-462 on the device: returns `num_limbs` ext MLEs (tower leaves)."""
+    descs = (_lib.CgMleDesc * len(mles))(*[m.desc() for m in mles])
+    out_len = int(dev.lib.cg_tower_interleave_out_len(len(mles), num_instances, num_limbs))
+    out = dev.alloc(16 * out_len * num_limbs)
+    d = _u64(default)
+    dev.check(dev.lib.cg_tower_interleave(dev.ctx, descs, len(mles), num_instances, num_limbs, _vp(d), C.c_void_p(out.ptr), None))
+    dev.sync()
+    nv = out_len.bit_length() - 1
+    return [MultilinearExtension(dev, DeviceBuffer(dev, out.ptr + 16 * out_len * i, 16 * out_len, owner=(i == 0)), nv, True) for i in range(num_limbs)], out
+
+
 class TowerProverSpec:
     """Leaves of one tower: product (a, b of 2^(num_vars-1)) or logup (p1, p2, q1, q2 of 2^num_vars;
     p1 = p2 = None -> numerators are ones)."""

@@ -1922,6 +1922,63 @@ CG_EXPORT int cg_tower_build(cg_ctx* c, const cg_tower_spec* specs, uint32_t n_s
     *out = tw;
     return CG_OK;
 }
+static uint32_t ceil_log2_u64(uint64_t x) { uint32_t l = 0; while ((1ULL << l) < x) l++; return l; }
+CG_EXPORT uint64_t cg_tower_interleave_out_len(uint32_t n_mles, uint64_t num_instances, uint32_t num_limbs) {
+    uint64_t np2 = 1;
+    while (np2 < num_instances) np2 <<= 1;
+    if (np2 < 2) np2 = 2;   // next_pow2_instance_padding: minimum 2
+    const uint32_t l2i = ceil_log2_u64(np2), l2m = ceil_log2_u64(n_mles), l2l = ceil_log2_u64(num_limbs);
+    return 1ULL << (l2m + (l2i > l2l ? l2i - l2l : 0));
+}
+CG_EXPORT int cg_tower_interleave(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, uint64_t num_instances, uint32_t num_limbs,
+                                  const uint64_t default_ext[2], uint64_t* d_out, cg_stream s) {
+    if (!c || !mles || !n_mles || !default_ext || !d_out) return set_err(c, CG_ERR_INVALID, "cg_tower_interleave: null argument");
+    if (!num_limbs || (num_limbs & (num_limbs - 1))) return set_err(c, CG_ERR_INVALID, "cg_tower_interleave: num_limbs must be a power of two (utils.rs:408)");
+    uint64_t np2 = 1;
+    while (np2 < num_instances) np2 <<= 1;
+    if (np2 < 2) np2 = 2;
+    const uint64_t mle_len = mles[0].len;
+    std::vector<const void*> ptrs(n_mles);
+    std::vector<uint32_t> ext(n_mles);
+    for (uint32_t i = 0; i < n_mles; i++) {
+        if (mles[i].is_ext > CG_MLE_EXT || !mles[i].dptr) return set_err(c, CG_ERR_INVALID, "cg_tower_interleave: dense MLEs only");
+        if (mles[i].len != mle_len) return set_err(c, CG_ERR_INVALID, "cg_tower_interleave: every MLE must have the same length");
+        if (mles[i].len > np2) return set_err(c, CG_ERR_INVALID, "cg_tower_interleave: MLE longer than the padded instance count (utils.rs:411-414)");
+        if ((uintptr_t)mles[i].dptr & (mles[i].is_ext ? 15 : 7)) return set_err(c, CG_ERR_INVALID, "cg_tower_interleave: misaligned MLE pointer");
+        ptrs[i] = mles[i].dptr;
+        ext[i] = mles[i].is_ext;
+    }
+    cudaStream_t st = S(c, s);
+    CU(c, cudaSetDevice(c->device));
+    void *d_ptrs = nullptr, *d_ext = nullptr;
+    CHK(upload_small(c, ptrs.data(), sizeof(void*) * n_mles, &d_ptrs, st));
+    int rc = upload_small(c, ext.data(), sizeof(uint32_t) * n_mles, &d_ext, st);
+    if (rc == CG_OK) {
+        InterleaveArgs a;
+        memset(&a, 0, sizeof(a));
+        a.ptrs = (const void* const*)d_ptrs;
+        a.is_ext = (const uint32_t*)d_ext;
+        a.n_mles = n_mles;
+        a.l2m = ceil_log2_u64(n_mles);
+        a.out_len = cg_tower_interleave_out_len(n_mles, num_instances, num_limbs);
+        a.per_fanin_len = mle_len / num_limbs ? mle_len / num_limbs : 1;
+        a.num_instances = num_instances;
+        a.mle_len = mle_len;
+        a.def = ext_t{default_ext[0] % GL_P, default_ext[1] % GL_P};
+        a.out = (ext_t*)d_out;
+        const uint64_t n_inst_out = a.out_len >> a.l2m, per_instance = 1ULL << a.l2m;
+        const dim3 grid((unsigned)((n_inst_out + 31) / 32), (unsigned)((per_instance + 31) / 32), num_limbs);
+        if (grid.y > 65535 || grid.z > 65535) rc = set_err(c, CG_ERR_UNSUPPORTED, "cg_tower_interleave: too many records / limbs for one launch");
+        else {
+            tower_interleave_kernel<<<grid, dim3(32, 8), 0, st>>>(a);
+            LAUNCHED(c);
+            if (cudaGetLastError() != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "tower_interleave_kernel launch failed");
+        }
+    }
+    tmp_free(d_ptrs, st);
+    tmp_free(d_ext, st);
+    return rc;
+}
 CG_EXPORT int cg_tower_output_evals(cg_tower* tw, uint32_t spec, uint64_t* h_out) {
     if (!tw || spec >= tw->specs.size() || !h_out) return CG_ERR_INVALID;
     const TowerSpecState& sp = tw->specs[spec];

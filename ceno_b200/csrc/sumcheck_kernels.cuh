@@ -1295,6 +1295,49 @@ __global__ void quark_mask_kernel(ext_t* __restrict__ v, uint64_t n, const __gri
 }
 
 // ---------------------------------------------------------------------------------------------
+// interleaving_mles_to_mles (ceno_zkvm/src/scheme/utils.rs:402-462): R record MLEs (one value per instance)
+// become `num_limbs` tower leaves, out[limb][s * 2^ceil_log2(R) + i] = mle_i[limb * per_fanin_len + s], padded with
+// `def`.  A 32 x 32 shared-memory tile transpose: reads run along the instances of one MLE, writes along the
+// records of one instance, both coalesced.
+struct InterleaveArgs {
+    const void* const* ptrs;     // device array of n_mles pointers
+    const uint32_t* is_ext;      // device array
+    uint32_t n_mles, l2m;        // per_instance = 2^l2m
+    uint64_t out_len, per_fanin_len, num_instances, mle_len;
+    ext_t def;
+    ext_t* out;                  // [num_limbs][out_len]
+};
+__global__ void __launch_bounds__(256) tower_interleave_kernel(const __grid_constant__ InterleaveArgs a) {
+    __shared__ ext_t tile[32][33];
+    const uint32_t tx = threadIdx.x, ty = threadIdx.y;
+    const uint64_t fi = blockIdx.z;
+    const uint64_t per_instance = 1ULL << a.l2m, n_inst_out = a.out_len >> a.l2m;
+    const uint64_t start = a.per_fanin_len * fi;
+    const uint64_t valid = start < a.num_instances ? (a.per_fanin_len < a.num_instances - start ? a.per_fanin_len : a.num_instances - start) : 0;
+    const uint64_t s0 = (uint64_t)blockIdx.x * 32, i0 = (uint64_t)blockIdx.y * 32;
+    for (uint32_t ii = ty; ii < 32; ii += 8) {
+        const uint64_t i = i0 + ii, sidx = s0 + tx;
+        ext_t v = a.def;
+        if (i < a.n_mles && start < a.num_instances) {
+            const uint32_t e = a.is_ext[i];
+            uint64_t cnt = e ? valid : a.per_fanin_len;     // Ext arm: valid_instances_len, Base arm: per_fanin_len (utils.rs:433-456)
+            if (start + cnt > a.mle_len) cnt = 0;           // `.get(range)` out of range -> empty
+            if (cnt > n_inst_out) cnt = n_inst_out;
+            if (sidx < cnt) {
+                if (e) v = ext_canon(ld_ext(reinterpret_cast<const ext_t*>(a.ptrs[i]) + start + sidx));
+                else v = ext_make(gl_canon(reinterpret_cast<const uint64_t*>(a.ptrs[i])[start + sidx]), 0);
+            }
+        }
+        tile[ii][tx] = v;
+    }
+    __syncthreads();
+    for (uint32_t ss = ty; ss < 32; ss += 8) {
+        const uint64_t sidx = s0 + ss, i = i0 + tx;
+        if (sidx < n_inst_out && i < per_instance) st_ext(a.out + fi * a.out_len + sidx * per_instance + i, tile[tx][ss]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // tower witness layers (infer_tower_product_witness / infer_tower_logup_witness,
 // ceno_zkvm/src/scheme/utils.rs:488-659).  Layer l buffer = [a | b] (product) or [p1|p2|q1|q2]
 // (logup), each 2^l ext; layer l = pointwise combination of layer l+1's arrays over 2^(l+1) points.

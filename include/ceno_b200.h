@@ -247,6 +247,15 @@ typedef struct cg_tower_spec {
     uint32_t num_vars;         /* product: layers = num_vars; logup: layers = num_vars + 1 */
     uint32_t is_logup;
 } cg_tower_spec;
+/* interleaving_mles_to_mles (ceno_zkvm/src/scheme/utils.rs:402-462; the reference GPU path keeps this virtual,
+ * GpuVirtualInterleavedExt, ceno_zkvm/src/scheme/gpu/mod.rs:2195-2268): the chip's R record MLEs (one value per
+ * instance, base or ext, all of length mles[0].len <= next_pow2(num_instances)) become `num_limbs` (= fan-in, 2)
+ * tower leaves of cg_tower_interleave_out_len() ext each, written consecutively to d_out_ext:
+ *   out[limb][s * 2^ceil_log2(R) + i] = mle_i[limb * per_fanin_len + s],  everything else = default
+ * (1 for read/write records, the challenge alpha for lookup records). */
+uint64_t cg_tower_interleave_out_len(uint32_t n_mles, uint64_t num_instances, uint32_t num_limbs);
+int cg_tower_interleave(cg_ctx* ctx, const cg_mle_desc* mles, uint32_t n_mles, uint64_t num_instances, uint32_t num_limbs,
+                        const uint64_t default_ext[2], uint64_t* d_out_ext, cg_stream s);
 typedef struct cg_tower cg_tower;
 int cg_tower_build(cg_ctx* ctx, const cg_tower_spec* specs, uint32_t n_specs, cg_stream s, cg_tower** out);
 /* get_output_evals (ceno_zkvm/src/scheme/gpu/mod.rs:369-420): layer-0 values of spec i:

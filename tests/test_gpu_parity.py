@@ -425,6 +425,82 @@ def _tower_case(dev, prod_nvs, logup_nvs, with_p, seed):
     tw.close()
 
 
+def test_interleaving_mles_to_mles(dev):
+    """ceno_zkvm/src/scheme/utils.rs:402-462 on the device: the reference's literal vectors (utils.rs:968-1065) and
+    seeded cases against the oracle (base and ext records, instance counts off the powers of two, R up to 70)."""
+    import ceno_b200 as cb
+    from ceno_b200 import api
+    from oracle import pyref as pr
+
+    def run(cols, is_ext, num_instances, num_limbs, default):
+        host = [(c, e) for c, e in zip(cols, is_ext)]
+        want = orc.interleaving_mles_to_mles(host, num_instances, num_limbs, default)
+        mles = []
+        for c, e in host:
+            nv = max((c.size // (2 if e else 1)) - 1, 0).bit_length()
+            mles.append((cb.MultilinearExtension.from_evaluations_ext_vec if e else cb.MultilinearExtension.from_evaluations_vec)(dev, nv, c))
+        got, buf = api.interleaving_mles_to_mles(dev, mles, num_instances, num_limbs, default)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert eq_np(g.evaluations(), w)
+        buf.free()
+        for m in mles:
+            m.free()
+        return want
+
+    E = lambda *xs: np.array([v for x in xs for v in (x, 0)], dtype=np.uint64)
+    w = run([E(1, 2), E(3, 4), E(5, 6), E(7, 8)], [True] * 4, 2, 2, [1, 0])
+    assert pr.to_pairs(w[0]) == [(1, 0), (3, 0), (5, 0), (7, 0)] and pr.to_pairs(w[1]) == [(2, 0), (4, 0), (6, 0), (8, 0)]
+    run([E(1, 2), E(3, 4), E(5, 6)], [True] * 3, 2, 2, [0, 0])
+    run([E(1, 0), E(3, 0), E(5, 0)], [True] * 3, 1, 2, [1, 0])
+    run([E(2), E(3)], [True] * 2, 1, 2, [1, 0])
+    rng = random.Random(77)
+    for R, log_n, ninst, limbs in [(1, 6, 64, 2), (2, 7, 100, 2), (5, 10, 1000, 2), (17, 12, 4096, 2), (33, 9, 300, 2), (70, 8, 255, 2), (3, 11, 2048, 4),
+                                   (9, 5, 17, 1)]:
+        n = 1 << log_n
+        ext_flags = [rng.random() < 0.5 for _ in range(R)]
+        cols = [orc.fill_ext(5000 + 97 * R + i, n) if e else orc.fill_base(5000 + 97 * R + i, n) for i, e in enumerate(ext_flags)]
+        run(cols, ext_flags, ninst, limbs, [rng.randrange(P), rng.randrange(P)])
+
+
+def test_chip_tower_flow_records_to_proof(dev):
+    """The tower half of create_chip_proof (ceno_zkvm/src/scheme/prover.rs:717, cpu/mod.rs:586-700): record MLEs ->
+    interleaving_mles_to_mles (pad 1 for read/write, alpha for lookups) -> tower build -> tower proof, all on the
+    device, against the same chain in the oracle."""
+    import ceno_b200 as cb
+    from ceno_b200 import api
+    log_n, ninst = 10, 1000
+    n = 1 << log_n
+    alpha = [12345, 678]
+    r_recs = [orc.fill_ext(9100 + i, n) for i in range(3)]        # read records  (R = 3 -> padded to 4 per instance)
+    w_recs = [orc.fill_ext(9200 + i, n) for i in range(2)]        # write records
+    lk_recs = [orc.fill_ext(9300 + i, n) for i in range(5)]       # lookup denominators
+    specs_dev, o_prod, o_lk, keep = [], [], [], []
+    for recs in (r_recs, w_recs):
+        want = orc.interleaving_mles_to_mles([(c, True) for c in recs], ninst, 2, [1, 0])
+        nv = (want[0].size // 2).bit_length()      # leaves of 2^(nv-1)
+        pw, layers = orc.infer_tower_product_witness(nv, want[0], want[1])
+        o_prod.append((pw, nv))
+        mles = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, log_n, c) for c in recs]
+        got, buf = api.interleaving_mles_to_mles(dev, mles, ninst, 2, [1, 0])
+        keep.append(buf)
+        specs_dev.append(cb.TowerProverSpec(got, nv, False))
+    want = orc.interleaving_mles_to_mles([(c, True) for c in lk_recs], ninst, 2, alpha)
+    nv = (want[0].size // 2).bit_length() - 1
+    lw, layers = orc.infer_tower_logup_witness(nv, None, None, want[0], want[1])
+    o_lk.append((lw, nv + 1))
+    mles = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, log_n, c) for c in lk_recs]
+    got, buf = api.interleaving_mles_to_mles(dev, mles, ninst, 2, alpha)
+    keep.append(buf)
+    specs_dev.append(cb.TowerProverSpec([None, None, got[0], got[1]], nv, True))
+    tw = cb.TowerProver(dev, specs_dev)
+    t_o, t_d = orc.Transcript(b"chip"), cb.StandInTranscript(b"chip")
+    want_proof, want_point = orc.tower_create_proof(o_prod, o_lk, t_o)
+    got_proof, got_point = tw.create_proof(t_d)
+    assert eq_np(got_proof, want_proof) and eq_np(got_point, want_point)
+    tw.close()
+
+
 @pytest.mark.parametrize("prod_nvs,logup_nvs,with_p", [
     ([4], [], False),                 # test_tower_proof_various_prod_size style (scheme/tests.rs:447-500)
     ([2], [], False), ([10], [], False),
