@@ -19,6 +19,19 @@ class CgPoseidon2Params(C.Structure):
                 ("mds_variant", C.c_uint32), ("pad", C.c_uint32)]
 
 
+class CgSchedTask(C.Structure):
+    _fields_ = [("task_id", C.c_uint32), ("reserved", C.c_uint32), ("estimated_memory_bytes", C.c_uint64), ("booked_memory_bytes", C.c_uint64)]
+
+
+class CgSchedResult(C.Structure):
+    _fields_ = [("task_id", C.c_uint32), ("lane_id", C.c_uint32), ("status", C.c_int32), ("launch_seq", C.c_uint32),
+                ("booked_total_at_launch", C.c_uint64), ("queue_delay_ms", C.c_double), ("host_execution_ms", C.c_double),
+                ("event_wait_ms", C.c_double)]
+
+
+SCHED_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p)
+
+
 class CgTowerSpec(C.Structure):
     _fields_ = [("leaves", C.c_void_p * 4), ("num_vars", C.c_uint32), ("is_logup", C.c_uint32)]
 
@@ -47,6 +60,7 @@ SYMBOLS = [
     "cg_comm_create", "cg_comm_connect", "cg_comm_destroy", "cg_sumcheck_attach_comm", "cg_sumcheck_prove_sharded",
     "cg_poseidon2_set_params", "cg_poseidon2_permute", "cg_merkle_commit",
     "cg_rotation_next_base_mle", "cg_rotation_selector",
+    "cg_sched_execute", "cg_stream_create", "cg_stream_destroy",
 ]
 
 _lib = None
@@ -118,6 +132,9 @@ def load():
         "cg_merkle_commit": (i32, [vp, vp, u64, u64, i32, vp, vp, vp]),
         "cg_rotation_next_base_mle": (i32, [vp, P(CgMleDesc), u32, vp, vp]),
         "cg_rotation_selector": (i32, [vp, vp, u64, u32, u32, vp, vp]),
+        "cg_sched_execute": (i32, [vp, P(CgSchedTask), u32, u32, u64, SCHED_FN, vp, P(CgSchedResult)]),
+        "cg_stream_create": (i32, [vp, P(vp)]),
+        "cg_stream_destroy": (i32, [vp, vp]),
         "cg_sumcheck_prove_sharded": (i32, [vp, vp, P(CgMleDesc), u32, vp, vp, vp, u32, u32, u32, u32, CHALLENGE_CB, vp, vp, vp, vp, vp, vp]),
     }
     for name in SYMBOLS:

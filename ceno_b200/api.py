@@ -488,3 +488,77 @@ def rotation_selector(dev, eq, cyclic_subgroup_size, cyclic_group_log2_size):
                                            C.c_void_p(out.ptr), None))
     dev.sync()
     return MultilinearExtension(dev, out, eq.num_vars, True)
+
+
+class ChipTask:
+    """One chip proof for the lane scheduler (ChipTask, ceno_zkvm/src/scheme/scheduler.rs:113-145): `payload` is
+    whatever the execute callback needs; `booked_memory_bytes` defaults to the estimate."""
+
+    def __init__(self, task_id, estimated_memory_bytes, payload=None, booked_memory_bytes=0, circuit_name=""):
+        self.task_id, self.estimated_memory_bytes, self.booked_memory_bytes = task_id, estimated_memory_bytes, booked_memory_bytes
+        self.payload, self.circuit_name = payload, circuit_name
+
+
+class ChipScheduler:
+    """ChipScheduler::execute (ceno_zkvm/src/scheme/scheduler.rs:205-250): run `execute_task(task, lane_id, stream)` for
+    every task on up to `lanes` (1..8, default 4) concurrent lanes with greedy memory backfilling.  Returns
+    (outputs ordered by task_id, telemetry ordered by task_id).  `dev=None` schedules host-only work (no streams).
+    Exceptions raised by a task are re-raised after the in-flight tasks have drained, like the reference returns
+    the first task error."""
+
+    DEFAULT_LANES = 4
+
+    def __init__(self, dev=None):
+        self.dev = dev
+        self.lib = dev.lib if dev is not None else _lib.load()
+
+    def execute(self, tasks, execute_task, lanes=0, mem_budget_bytes=0):
+        n = len(tasks)
+        arr = (_lib.CgSchedTask * max(n, 1))()
+        for i, t in enumerate(tasks):
+            arr[i].task_id, arr[i].estimated_memory_bytes, arr[i].booked_memory_bytes = t.task_id, t.estimated_memory_bytes, t.booked_memory_bytes
+        res = (_lib.CgSchedResult * max(n, 1))()
+        outputs, errors = {}, {}
+
+        def tramp(_user, index, task_id, lane_id, stream):
+            try:
+                outputs[task_id] = execute_task(tasks[index], lane_id, stream)
+                return _lib.CG_OK
+            except CenoB200Error as e:
+                errors[task_id] = e
+                return e.code
+            except Exception as e:   # noqa: BLE001 — a task failure must not unwind through the C frames
+                errors[task_id] = e
+                return 6
+
+        cb = _lib.SCHED_FN(tramp)
+        ctx = self.dev.ctx if self.dev is not None else None
+        rc = self.lib.cg_sched_execute(ctx, arr, n, lanes, mem_budget_bytes, cb, None, res)
+        telemetry = [{"task_id": r.task_id, "lane_id": r.lane_id, "status": r.status, "launch_seq": r.launch_seq,
+                      "booked_total_at_launch": r.booked_total_at_launch, "queue_delay_ms": r.queue_delay_ms,
+                      "host_execution_ms": r.host_execution_ms, "event_wait_ms": r.event_wait_ms} for r in res[:n]]
+        if errors:
+            first = min(errors, key=lambda tid: next(t["launch_seq"] for t in telemetry if t["task_id"] == tid))
+            raise errors[first]
+        if rc != _lib.CG_OK:
+            msg = self.lib.cg_last_error(ctx).decode() if ctx else "cg_sched_execute failed (deadlock: remaining tasks are too big for the memory pool, or bad arguments)"
+            raise CenoB200Error(rc, msg)
+        return [outputs[t["task_id"]] for t in telemetry], telemetry
+
+
+class Stream:
+    """A lane stream (one non-blocking CUDA stream per OS thread, gkr_iop/src/gpu/mod.rs:79-154)."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        h = C.c_void_p()
+        dev.check(dev.lib.cg_stream_create(dev.ctx, C.byref(h)))
+        self.handle = h.value
+
+    def sync(self):
+        self.dev.check(self.dev.lib.cg_stream_sync(self.dev.ctx, C.c_void_p(self.handle)))
+
+    def close(self):
+        if self.handle:
+            self.dev.lib.cg_stream_destroy(self.dev.ctx, C.c_void_p(self.handle))
+            self.handle = None

@@ -976,6 +976,9 @@ static int launch_generic_eval(cg_sumcheck* sc, uint32_t f, const RoundOut& ro) 
     CU(c, cudaGetLastError());
     return CG_OK;
 }
+#ifndef CG_VEQ_MINB_DEFAULT
+#define CG_VEQ_MINB_DEFAULT 2
+#endif
 // split-eq round (virtual eq): evaluate state f, folding f-1 -> f first when `fold`
 static int launch_veq(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro) {
     cg_ctx* c = sc->ctx;
@@ -1011,18 +1014,26 @@ static int launch_veq(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro
     } while (0)
     static const int use_tma = []() { const char* e = getenv("CG_VEQ_TMA"); return e ? atoi(e) : 1; }();
     if (use_tma) {   // rows staged through shared memory by cp.async.bulk (default)
+        // CG_VEQ_MINB = 2 | 3 resident blocks per SM (A/B switch; see VeqTmaCfg)
+        static const int minb = []() { const char* e = getenv("CG_VEQ_MINB"); return e ? atoi(e) : CG_VEQ_MINB_DEFAULT; }();
         static bool attr_done = false;
         if (!attr_done) {
-            CU(c, cudaFuncSetAttribute(veq_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VeqTmaCfg<false>::SMEM));
-            CU(c, cudaFuncSetAttribute(veq_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VeqTmaCfg<true>::SMEM));
-            CU(c, cudaFuncSetAttribute(veq_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VeqTmaCfg<true>::SMEM));
+#define CG_VEQ_ATTR(F, C, MB) CU(c, cudaFuncSetAttribute(veq_tma_kernel<F, C, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VeqTmaCfg<F, MB>::SMEM))
+            CG_VEQ_ATTR(false, false, 2); CG_VEQ_ATTR(true, true, 2); CG_VEQ_ATTR(true, false, 2);
+            CG_VEQ_ATTR(false, false, 3); CG_VEQ_ATTR(true, true, 3); CG_VEQ_ATTR(true, false, 3);
+#undef CG_VEQ_ATTR
             attr_done = true;
         }
-        uint64_t tb = (uint64_t)c->sm_count * 2;
+        uint64_t tb = (uint64_t)c->sm_count * (minb == 3 ? 3 : 2);
         if (tb > a.n_rows) tb = a.n_rows;
-        if (!fold) veq_tma_kernel<false, false><<<(unsigned)tb, 256, VeqTmaCfg<false>::SMEM, sc->stream>>>(a);
-        else if (canon) veq_tma_kernel<true, true><<<(unsigned)tb, 256, VeqTmaCfg<true>::SMEM, sc->stream>>>(a);
-        else veq_tma_kernel<true, false><<<(unsigned)tb, 256, VeqTmaCfg<true>::SMEM, sc->stream>>>(a);
+#define CG_VEQ_TMA_LAUNCH(MB)                                                                                                   \
+    do {                                                                                                                        \
+        if (!fold) veq_tma_kernel<false, false, MB><<<(unsigned)tb, 256, VeqTmaCfg<false, MB>::SMEM, sc->stream>>>(a);          \
+        else if (canon) veq_tma_kernel<true, true, MB><<<(unsigned)tb, 256, VeqTmaCfg<true, MB>::SMEM, sc->stream>>>(a);        \
+        else veq_tma_kernel<true, false, MB><<<(unsigned)tb, 256, VeqTmaCfg<true, MB>::SMEM, sc->stream>>>(a);                  \
+    } while (0)
+        if (minb == 3) CG_VEQ_TMA_LAUNCH(3); else CG_VEQ_TMA_LAUNCH(2);
+#undef CG_VEQ_TMA_LAUNCH
     } else {         // CG_VEQ_TMA=0: the same round with plain 256-bit loads (A/B comparison)
         CG_VEQ_LAUNCH(2);
     }
@@ -2188,3 +2199,5 @@ CG_EXPORT int cg_rotation_selector(cg_ctx* c, const uint64_t* d_eq_ext, uint64_t
     CU(c, cudaGetLastError());
     return CG_OK;
 }
+
+#include "sched.cuh"

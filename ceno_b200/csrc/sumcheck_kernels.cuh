@@ -524,16 +524,18 @@ GL_DEV ext_t lds_ext(uint32_t addr) {
     asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(v.c0), "=l"(v.c1) : "r"(addr));
     return v;
 }
-template <bool FOLD>
+// MINB = resident blocks per SM (2: 128 registers per thread; 3: 80 registers, a few spills, 24 warps per SM);
+// the ring depth follows from the shared memory left per block.
+template <bool FOLD, int MINB = 2>
 struct VeqTmaCfg {
     static constexpr uint32_t ROWB = FOLD ? 16384u : 8192u;   // bytes per MLE per row
     static constexpr uint32_t STAGEB = 2 * ROWB + 128;        // A row | B row | H entry (32 B) + pad
-    static constexpr int STAGES = FOLD ? 3 : 4;
+    static constexpr int STAGES = MINB == 2 ? (FOLD ? 3 : 4) : (FOLD ? 2 : 4);
     static constexpr uint32_t SMEM = STAGES * STAGEB + 2 * STAGES * 8;
 };
-template <bool FOLD, bool CANON>
-__global__ void __launch_bounds__(256, 2) veq_tma_kernel(const __grid_constant__ VeqArgs a) {
-    using Cfg = VeqTmaCfg<FOLD>;
+template <bool FOLD, bool CANON, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB) veq_tma_kernel(const __grid_constant__ VeqArgs a) {
+    using Cfg = VeqTmaCfg<FOLD, MINB>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr uint32_t ROWB = Cfg::ROWB, STAGEB = Cfg::STAGEB;
     extern __shared__ __align__(128) unsigned char veq_smem[];

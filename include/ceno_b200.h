@@ -319,6 +319,40 @@ int cg_poseidon2_permute(cg_ctx* ctx, uint64_t* d_states /* n x 8 */, uint64_t n
 int cg_merkle_commit(cg_ctx* ctx, const uint64_t* d_matrix, uint64_t width, uint64_t height, int col_major,
                      uint64_t* d_tree, uint64_t h_root[4], cg_stream s);
 
+/* ---- f-4: chip-level concurrency — ChipScheduler::execute (ceno_zkvm/src/scheme/scheduler.rs:109-400,
+ * docs/src/concurrent-chip-proving.md).  Greedy backfilling over 1..8 lanes (0 = the reference's default, 4), one OS
+ * thread + one non-default stream per lane: tasks are sorted by estimated memory (descending), the first pending task
+ * whose booking fits the remaining budget is launched while a lane is free, the scheduler blocks on completions when
+ * nothing fits, and reports "Deadlock: Remaining tasks are too big for the memory pool" (CG_ERR_OOM) when nothing
+ * fits and nothing runs.  A lane (and its booking) is released only after the lane's stream has drained.  The
+ * callback does the chip's work (transcript fork + cg_tower_* / cg_sumcheck_* calls) on the stream it is given and
+ * returns a CG_* status; the first failure is returned after in-flight tasks have finished, tasks never started get
+ * status CG_ERR_STATE.  results[] (n_tasks entries) comes back ordered by task_id.  ctx may be NULL for host-only
+ * use (then stream is NULL in the callback and mem_budget_bytes is required); mem_budget_bytes = 0 means the
+ * device memory free now plus the pool's idle blocks. */
+#define CG_SCHED_DEFAULT_LANES 4u
+#define CG_SCHED_MAX_LANES 8u
+typedef struct cg_sched_task {
+    uint32_t task_id;                /* result ordering */
+    uint32_t reserved;
+    uint64_t estimated_memory_bytes; /* sort key */
+    uint64_t booked_memory_bytes;    /* what the scheduler reserves (0 = estimated_memory_bytes) */
+} cg_sched_task;
+typedef struct cg_sched_result {
+    uint32_t task_id;
+    uint32_t lane_id;
+    int32_t status;
+    uint32_t launch_seq;             /* order in which the scheduler admitted the task */
+    uint64_t booked_total_at_launch; /* bytes booked right after admission (never above the budget) */
+    double queue_delay_ms, host_execution_ms, event_wait_ms;
+} cg_sched_result;
+typedef int (*cg_sched_fn)(void* user, uint32_t task_index, uint32_t task_id, uint32_t lane_id, cg_stream stream);
+int cg_sched_execute(cg_ctx* ctx, const cg_sched_task* tasks, uint32_t n_tasks, uint32_t lanes, uint64_t mem_budget_bytes,
+                     cg_sched_fn fn, void* user, cg_sched_result* results);
+/* a non-blocking stream for a caller-owned lane thread (get_pool_stream / bind_thread_stream, gkr_iop/src/gpu/mod.rs:79-154) */
+int cg_stream_create(cg_ctx* ctx, cg_stream* out);
+int cg_stream_destroy(cg_ctx* ctx, cg_stream s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -710,3 +710,42 @@ def test_rotation_prepasses(dev, log2):
         assert eq_np(api.rotation_selector(dev, eq, sub, log2).evaluations(), orc.rotation_selector(orc.build_eq_x_r_vec(pt), sub, log2))
     with pytest.raises(cb.CenoB200Error):
         api.rotation_next_base_mle(dev, m, 4)      # BooleanHypercube::new asserts 5 or 6
+
+
+# ------------------------------------------------------------------ f-4: concurrent chip proving on lanes
+def test_chip_scheduler_concurrent_lanes_bit_exact(dev):
+    """ChipScheduler::execute shape (ceno_zkvm/src/scheme/scheduler.rs:205-250): several chip-sized sumchecks of
+    different sizes proved concurrently on 4 lanes (one stream + one OS thread each), every proof bit-exact and the
+    library re-entrant per (ctx, stream)."""
+    import ceno_b200 as cb
+    ks = [16, 12, 18, 14, 17, 13, 15, 11]
+    terms = [([1, 0], [0, 1, 2])]
+    inputs = {i: t3_inputs(k, seed=40 + i) for i, k in enumerate(ks)}
+    want = {i: orc.sumcheck_prove([(x, True, ks[i]) for x in inputs[i]], terms, ks[i], 3, transcript=orc.Transcript(b"chip%d" % i))
+            for i in range(len(ks))}
+    tasks = [cb.ChipTask(i, 3 * 16 * (1 << k) * 2, payload=i, circuit_name="chip%d" % i) for i, k in enumerate(ks)]
+
+    def prove(task, lane, stream):
+        i = task.payload
+        assert stream                                               # a real, non-default lane stream
+        mles = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, ks[i], x) for x in inputs[i]]
+        got = cb.IOPProverState.prove(dev, mles, terms, ks[i], 3, transcript=cb.StandInTranscript(b"chip%d" % i), stream=stream)
+        for m in mles:
+            m.free()
+        return got
+
+    for lanes in (1, 4, 8):
+        out, tel = cb.ChipScheduler(dev).execute(tasks, prove, lanes=lanes)
+        for i in range(len(ks)):
+            for g, w in zip(out[i], want[i]):
+                assert eq_np(g, w), (lanes, i)
+        assert {t["lane_id"] for t in tel} <= set(range(lanes))
+        assert [t["task_id"] for t in tel] == list(range(len(ks)))
+    # caller-owned lane stream (cg_stream_create): same result
+    st = cb.Stream(dev)
+    mles = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, ks[0], x) for x in inputs[0]]
+    got = cb.IOPProverState.prove(dev, mles, terms, ks[0], 3, transcript=cb.StandInTranscript(b"chip0"), stream=st.handle)
+    st.sync()
+    for g, w in zip(got, want[0]):
+        assert eq_np(g, w)
+    st.close()
