@@ -60,7 +60,7 @@ SYMBOLS = [
     "cg_comm_create", "cg_comm_connect", "cg_comm_destroy", "cg_sumcheck_attach_comm", "cg_sumcheck_prove_sharded",
     "cg_poseidon2_set_params", "cg_poseidon2_permute", "cg_merkle_commit",
     "cg_rotation_next_base_mle", "cg_rotation_selector",
-    "cg_sched_execute", "cg_stream_create", "cg_stream_destroy",
+    "cg_sched_execute", "cg_stream_create", "cg_stream_destroy", "cg_ntt", "cg_rs_encode",
 ]
 
 _lib = None
@@ -133,6 +133,8 @@ def load():
         "cg_rotation_next_base_mle": (i32, [vp, P(CgMleDesc), u32, vp, vp]),
         "cg_rotation_selector": (i32, [vp, vp, u64, u32, u32, vp, vp]),
         "cg_sched_execute": (i32, [vp, P(CgSchedTask), u32, u32, u64, SCHED_FN, vp, P(CgSchedResult)]),
+        "cg_ntt": (i32, [vp, vp, u32, u64, u64, u32, vp]),
+        "cg_rs_encode": (i32, [vp, vp, u64, u32, u32, vp, u32, vp]),
         "cg_stream_create": (i32, [vp, P(vp)]),
         "cg_stream_destroy": (i32, [vp, vp]),
         "cg_sumcheck_prove_sharded": (i32, [vp, vp, P(CgMleDesc), u32, vp, vp, vp, u32, u32, u32, u32, CHALLENGE_CB, vp, vp, vp, vp, vp, vp]),

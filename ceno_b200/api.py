@@ -562,3 +562,36 @@ class Stream:
         if self.handle:
             self.dev.lib.cg_stream_destroy(self.dev.ctx, C.c_void_p(self.handle))
             self.handle = None
+
+
+# ------------------------------------------------------------------- NTT / RS-encode (a9, f-2)
+NTT_INVERSE, NTT_BITREV, NTT_EXT = 1, 2, 4
+
+
+def ntt(dev, buf, log_n, n_cols=1, col_stride=None, inverse=False, bitrev=False, ext=False, stream=None):
+    """In-place batched NTT of `n_cols` columns held in DeviceBuffer `buf` (p3 Radix2 semantics, see cg_ntt)."""
+    flags = (NTT_INVERSE if inverse else 0) | (NTT_BITREV if bitrev else 0) | (NTT_EXT if ext else 0)
+    dev.check(dev.lib.cg_ntt(dev.ctx, C.c_void_p(buf.ptr), log_n, n_cols, col_stride if col_stride is not None else (1 << log_n), flags,
+                             C.c_void_p(stream) if stream else None))
+    if not stream:
+        dev.sync()
+
+
+def rs_encode(dev, msg_buf, width, log_n, rate_log, bitrev=True, stream=None):
+    """Reed-Solomon encode every column of a column-major message matrix; returns the code matrix DeviceBuffer
+    (width x 2^(log_n+rate_log), column-major)."""
+    code = dev.alloc(8 * (width << (log_n + rate_log)))
+    dev.check(dev.lib.cg_rs_encode(dev.ctx, C.c_void_p(msg_buf.ptr), width, log_n, rate_log, C.c_void_p(code.ptr), NTT_BITREV if bitrev else 0,
+                                   C.c_void_p(stream) if stream else None))
+    if not stream:
+        dev.sync()
+    return code
+
+
+def basefold_style_commit(dev, msg_buf, width, log_n, rate_log=1):
+    """TraceCommitter::commit_traces shape (ceno_zkvm/src/scheme/cpu/mod.rs:559-584): RS-encode the witness columns,
+    Merkle-hash the codeword matrix row-wise.  Returns (code DeviceBuffer, tree DeviceBuffer, root[4]).  Arrangement
+    parity is unpinned: bit-reversed codeword rows, one leaf per row across all columns."""
+    code = rs_encode(dev, msg_buf, width, log_n, rate_log, bitrev=True)
+    tree, root = merkle_commit(dev, code, width, 1 << (log_n + rate_log), col_major=True)
+    return code, tree, root

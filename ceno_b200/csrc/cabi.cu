@@ -18,6 +18,7 @@
 #include "../../include/ceno_b200.h"
 #include "sumcheck_kernels.cuh"
 #include "poseidon2.cuh"
+#include "ntt_kernels.cuh"
 
 #define CG_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -36,6 +37,7 @@ struct cg_ctx {
     std::vector<std::pair<size_t, void*>> pinned_cache;   // reusable pinned staging buffers
     P2Params* d_p2 = nullptr;                             // Poseidon2 constants (caller-supplied, cg_poseidon2_set_params)
     std::vector<float> profile_ms;                        // per-round device time of the last CG_SC_PROFILE run
+    uint64_t* d_ntt_tab = nullptr;                        // NTT twiddle tables A | B | W12 (lazy, cg_ntt)
 };
 
 static int set_err(cg_ctx* c, int code, const std::string& msg) {
@@ -141,6 +143,7 @@ CG_EXPORT int cg_destroy(cg_ctx* c) {
     for (auto& kv : c->live) cudaFree(kv.first);
     for (auto& pc : c->pinned_cache) cudaFreeHost(pc.second);
     if (c->d_p2) cudaFree(c->d_p2);
+    if (c->d_ntt_tab) cudaFree(c->d_ntt_tab);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return CG_OK;
@@ -2201,3 +2204,4 @@ CG_EXPORT int cg_rotation_selector(cg_ctx* c, const uint64_t* d_eq_ext, uint64_t
 }
 
 #include "sched.cuh"
+#include "ntt_host.cuh"

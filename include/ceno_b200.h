@@ -319,6 +319,27 @@ int cg_poseidon2_permute(cg_ctx* ctx, uint64_t* d_states /* n x 8 */, uint64_t n
 int cg_merkle_commit(cg_ctx* ctx, const uint64_t* d_matrix, uint64_t width, uint64_t height, int col_major,
                      uint64_t* d_tree, uint64_t h_root[4], cg_stream s);
 
+/* ---- a9 / f-2: Reed-Solomon encoding of witness columns = batched radix-2 NTT over Goldilocks (the encode step of
+ * PCS::batch_commit, EXTERNAL mpcs::Basefold over p3-dft; call site ceno_zkvm/src/scheme/cpu/mod.rs:559-584, GPU
+ * basefold.batch_commit_*, ceno_zkvm/src/scheme/gpu/mod.rs:1062-1509).  The transform is p3's:
+ * X[k] = sum_j x[j] w^(jk), w = two_adic_generator(log_n) = g^(2^(32-log_n)), g = 7^((p-1)/2^32).
+ * PARITY UNPINNED for Basefold's arrangement (rate, basecode size, leaf order live in un-vendored mpcs):
+ * rate_log and the output order are parameters.  log_n (+ rate_log) <= 27.
+ * cg_ntt: in place, n_cols columns of 2^log_n elements, column c at d_data + c*col_stride (elements).
+ *   CG_NTT_INVERSE: inverse transform (includes 1/n).
+ *   CG_NTT_BITREV : forward writes / inverse reads bit-reversed order (the fast path: no permutation pass; it is the
+ *                   order in which a folding prover pairs adjacent entries).
+ *   CG_NTT_EXT    : elements are ext ([c0,c1]); both limb arrays are transformed.
+ * cg_rs_encode: every column of the column-major message matrix (width x 2^log_n base elements, an MLE's evaluation
+ *   vector taken as coefficients) is zero-padded to 2^(log_n+rate_log) and transformed into d_code (width x 2^(log_n+rate_log),
+ *   column-major: directly what cg_merkle_commit hashes row-wise). */
+#define CG_NTT_INVERSE 1u
+#define CG_NTT_BITREV 2u
+#define CG_NTT_EXT 4u
+int cg_ntt(cg_ctx* ctx, uint64_t* d_data, uint32_t log_n, uint64_t n_cols, uint64_t col_stride, uint32_t flags, cg_stream s);
+int cg_rs_encode(cg_ctx* ctx, const uint64_t* d_msg, uint64_t width, uint32_t log_n, uint32_t rate_log, uint64_t* d_code,
+                 uint32_t flags, cg_stream s);
+
 /* ---- f-4: chip-level concurrency — ChipScheduler::execute (ceno_zkvm/src/scheme/scheduler.rs:109-400,
  * docs/src/concurrent-chip-proving.md).  Greedy backfilling over 1..8 lanes (0 = the reference's default, 4), one OS
  * thread + one non-default stream per lane: tasks are sorted by estimated memory (descending), the first pending task

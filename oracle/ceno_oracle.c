@@ -972,3 +972,72 @@ OR_API int or_rotation_selector(const uint64_t* eq, uint64_t total_len, uint32_t
         }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Radix-2 NTT over Goldilocks and Reed-Solomon encoding of witness columns (the RS-encode
+ * step of PCS::batch_commit, EXTERNAL mpcs::Basefold over p3-dft; call site ceno_zkvm/src/scheme/cpu/mod.rs:559-584).
+ * PARITY UNPINNED for the arrangement (rate, coset, leaf order are upstream-only); what IS fixed is the
+ * transform itself: X[k] = sum_j x[j] w^(jk) with w = two_adic_generator(log_n) = g^(2^(32 - log_n)),
+ * g = 7^((p-1)/2^32) = 1753635133440165772 (p3-goldilocks TWO_ADIC_GENERATOR; checked in tests against 7^((p-1)/2^32)).
+ * Textbook decimation-in-time: bit-reversal permutation, then log_n butterfly stages — deliberately a different
+ * formulation from the device's multi-pass decimation-in-frequency kernels. */
+#define GL_TWO_ADIC_GEN 1753635133440165772ULL
+static uint64_t bitrev64(uint64_t x, uint32_t bits) {
+    uint64_t r = 0;
+    for (uint32_t i = 0; i < bits; i++) r |= ((x >> i) & 1ULL) << (bits - 1 - i);
+    return r;
+}
+OR_API uint64_t or_two_adic_generator(uint32_t bits) { return bits > 32 ? 0 : gl_pow(GL_TWO_ADIC_GEN, 1ULL << (32 - bits)); }
+static void ntt_one(gl* a, uint32_t log_n, int inverse) {
+    const uint64_t n = 1ULL << log_n;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t j = bitrev64(i, log_n);
+        if (i < j) { gl t = a[i]; a[i] = a[j]; a[j] = t; }
+    }
+    for (uint32_t s = 1; s <= log_n; s++) {
+        const uint64_t m = 1ULL << s, h = m >> 1;
+        gl wm = or_two_adic_generator(s);
+        if (inverse) wm = gl_inv(wm);
+        for (uint64_t k = 0; k < n; k += m) {
+            gl w = 1;
+            for (uint64_t j = 0; j < h; j++) {
+                const gl t = gl_mul(w, a[k + j + h]), u = a[k + j];
+                a[k + j] = gl_add(u, t);
+                a[k + j + h] = gl_sub(u, t);
+                w = gl_mul(w, wm);
+            }
+        }
+    }
+    if (inverse) {
+        const gl ninv = gl_inv(to_canon(n));
+        for (uint64_t i = 0; i < n; i++) a[i] = gl_mul(a[i], ninv);
+    }
+}
+/* data: n_cols columns of 2^log_n base elements, column c at data + c * 2^log_n (column-major), natural order in
+ * and out; bitrev != 0: forward writes bit-reversed order / inverse reads bit-reversed order. */
+OR_API int or_ntt(uint64_t* data, uint32_t log_n, uint64_t n_cols, int inverse, int bitrev) {
+    if (log_n > 32) return -1;
+    const uint64_t n = 1ULL << log_n;
+#pragma omp parallel for schedule(dynamic)
+    for (uint64_t c = 0; c < n_cols; c++) {
+        gl* a = data + c * n;
+        for (uint64_t i = 0; i < n; i++) a[i] = to_canon(a[i]);
+        if (inverse && bitrev)
+            for (uint64_t i = 0; i < n; i++) { const uint64_t j = bitrev64(i, log_n); if (i < j) { gl t = a[i]; a[i] = a[j]; a[j] = t; } }
+        ntt_one(a, log_n, inverse);
+        if (!inverse && bitrev)
+            for (uint64_t i = 0; i < n; i++) { const uint64_t j = bitrev64(i, log_n); if (i < j) { gl t = a[i]; a[i] = a[j]; a[j] = t; } }
+    }
+    return 0;
+}
+/* Reed-Solomon encode: every column (2^log_n message symbols = the MLE's evaluation vector taken as coefficients)
+ * is zero-padded to 2^(log_n + rate_log) and transformed; code column c at out + c * 2^(log_n + rate_log). */
+OR_API int or_rs_encode(const uint64_t* msg, uint64_t width, uint32_t log_n, uint32_t rate_log, uint64_t* out, int bitrev) {
+    if (log_n + rate_log > 32) return -1;
+    const uint64_t n = 1ULL << log_n, m = 1ULL << (log_n + rate_log);
+    for (uint64_t c = 0; c < width; c++) {
+        memcpy(out + c * m, msg + c * n, n * sizeof(uint64_t));
+        memset(out + c * m + n, 0, (m - n) * sizeof(uint64_t));
+    }
+    return or_ntt(out, log_n + rate_log, width, 0, bitrev);
+}

@@ -58,6 +58,7 @@ def lib():
         _lib.or_interleave_out_len.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32]
         _lib.or_tower_create_proof.restype = C.c_int64
         _lib.or_num_threads.restype = C.c_int
+        _lib.or_two_adic_generator.restype = C.c_uint64
     return _lib
 
 
@@ -412,4 +413,27 @@ def rotation_selector(eq, subgroup_size, log2):
     out = np.zeros_like(eq)
     if lib().or_rotation_selector(_p(eq), C.c_uint64(eq.size // 2), C.c_uint32(subgroup_size), C.c_uint32(log2), _p(out)):
         raise ValueError("rotation_selector: bad arguments")
+    return out
+
+
+# ------------------------------------------------------------------------------- NTT / RS-encode (a9, f-2)
+def two_adic_generator(bits):
+    return int(lib().or_two_adic_generator(C.c_uint32(bits)))
+
+
+def ntt(data, log_n, n_cols=1, inverse=False, bitrev=False):
+    """data: n_cols columns of 2^log_n base elements (column-major).  Forward: X[k] = sum_j x[j] w^(jk),
+    w = two_adic_generator(log_n); bitrev: forward output / inverse input in bit-reversed order."""
+    a = _u64(data).copy()
+    assert a.size == n_cols << log_n
+    if lib().or_ntt(_p(a), C.c_uint32(log_n), C.c_uint64(n_cols), C.c_int(int(inverse)), C.c_int(int(bitrev))):
+        raise ValueError("or_ntt: bad size")
+    return a
+
+
+def rs_encode(msg, width, log_n, rate_log, bitrev=True):
+    msg = _u64(msg)
+    out = np.zeros(width << (log_n + rate_log), np.uint64)
+    if lib().or_rs_encode(_p(msg), C.c_uint64(width), C.c_uint32(log_n), C.c_uint32(rate_log), _p(out), C.c_int(int(bitrev))):
+        raise ValueError("or_rs_encode: bad size")
     return out

@@ -473,3 +473,49 @@ def test_kat_rotation_next_base_mle_eval(nv):
     keep = set(tab[:23])
     for b in range(1 << total_vars):
         assert sel[b] == (eqp[b] if (b & ((1 << nv) - 1)) in keep else pr.ZERO)
+
+
+# ------------------------------------------------------------------ NTT / RS-encode (a9, f-2)
+def test_two_adic_generator_is_the_p3_goldilocks_constant():
+    """p3-goldilocks: GENERATOR = 7, TWO_ADICITY = 32, two_adic_generator(32) = 7^((p-1)/2^32) = 1753635133440165772."""
+    g = orc.two_adic_generator(32)
+    assert g == pow(7, (P - 1) >> 32, P) == 1753635133440165772
+    assert pow(g, 1 << 31, P) == P - 1                     # primitive 2^32-th root of unity
+    for bits in (0, 1, 5, 12, 27):
+        assert orc.two_adic_generator(bits) == pow(g, 1 << (32 - bits), P)
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 6])
+def test_ntt_matches_the_dft_definition(log_n):
+    n = 1 << log_n
+    x = [int(v) for v in orc.fill_base(77 + log_n, n)]
+    w = orc.two_adic_generator(log_n)
+    want = [sum(x[j] * pow(w, j * k, P) for j in range(n)) % P for k in range(n)]
+    got = orc.ntt(np.array(x, dtype=np.uint64), log_n)
+    assert [int(v) for v in got] == want
+    rev = [int(format(i, "0%db" % log_n)[::-1], 2) if log_n else 0 for i in range(n)]
+    br = orc.ntt(np.array(x, dtype=np.uint64), log_n, bitrev=True)
+    assert all(int(br[rev[k]]) == want[k] for k in range(n))
+    assert [int(v) for v in orc.ntt(got, log_n, inverse=True)] == x
+    assert [int(v) for v in orc.ntt(br, log_n, inverse=True, bitrev=True)] == x
+
+
+def test_rs_encode_is_polynomial_evaluation_and_linear():
+    """codeword[k] = f(w^k) for f = the message as coefficients; systematic properties: linearity, and the
+    rate-1/2 code of a constant message is constant."""
+    log_n, rate_log, width = 4, 1, 3
+    n, m = 1 << log_n, 1 << (log_n + rate_log)
+    msg = orc.fill_base(91, width * n)
+    code = orc.rs_encode(msg, width, log_n, rate_log, bitrev=False)
+    w = orc.two_adic_generator(log_n + rate_log)
+    for c in range(width):
+        coeffs = [int(v) for v in msg[c * n:(c + 1) * n]]
+        for k in (0, 1, 7, m - 1):
+            x = pow(w, k, P)
+            assert int(code[c * m + k]) == sum(a * pow(x, j, P) for j, a in enumerate(coeffs)) % P
+    a, b = orc.fill_base(92, n), orc.fill_base(93, n)
+    s = np.array([(int(u) + int(v)) % P for u, v in zip(a, b)], dtype=np.uint64)
+    ca, cb_, cs = (orc.rs_encode(v, 1, log_n, rate_log) for v in (a, b, s))
+    assert [int(v) for v in cs] == [(int(u) + int(v)) % P for u, v in zip(ca, cb_)]
+    const = np.zeros(n, np.uint64); const[0] = 5
+    assert set(int(v) for v in orc.rs_encode(const, 1, log_n, rate_log)) == {5}
