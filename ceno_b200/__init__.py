@@ -3,5 +3,5 @@
 The product is the C ABI in include/ceno_b200.h implemented by ceno_b200/csrc (hand-written CUDA);
 this package is the thin host-side mirror of the reference's interface used by tests and bench.py.
 """
-from .api import (CenoB200Error, ChipScheduler, ChipTask, Comm, Device, DeviceBuffer, EqPolynomial, IOPProverState, MultilinearExtension, SelectorType,  # noqa: F401
+from .api import (CenoB200Error, ChipScheduler, EccQuarkProver, ChipTask, Comm, Device, DeviceBuffer, EqPolynomial, IOPProverState, MultilinearExtension, SelectorType,  # noqa: F401
                   StandInTranscript, Stream, TowerProver, TowerProverSpec, build_eq_x_r_vec, prove_sharded, wit_infer_by_monomial_expr)

@@ -238,6 +238,21 @@ class StandInTranscript:
         self.lib.cg_standin_sample(_vp(self.state), C.c_char_p(label), _vp(out))
         return out
 
+    def sample_and_append_vec(self, label: bytes, n):
+        """n challenges under one label (Transcript::sample_and_append_vec); stand-in semantics: n successive samples."""
+        return np.concatenate([self.sample_and_append_challenge(label) for _ in range(n)]) if n else np.zeros(0, np.uint64)
+
+    def sample_and_append_challenge_pows(self, size, label: bytes):
+        """[1, a, a^2, ...] for ONE sampled a (Transcript::sample_and_append_challenge_pows, SURVEY §A2)."""
+        from .expr import ext_mul
+        a = self.sample_and_append_challenge(label)
+        a = (int(a[0]), int(a[1]))
+        out, cur = [], (1, 0)
+        for _ in range(size):
+            out.append(cur)
+            cur = ext_mul(cur, a)
+        return np.array(out, dtype=np.uint64)
+
     def vtable(self):
         vt = _lib.CgTranscriptVt()
         self.lib.cg_standin_vt(_vp(self.state), C.byref(vt))
@@ -595,3 +610,79 @@ def basefold_style_commit(dev, msg_buf, width, log_n, rate_log=1):
     code = rs_encode(dev, msg_buf, width, log_n, rate_log, bitrev=True)
     tree, root = merkle_commit(dev, code, width, 1 << (log_n + rate_log), col_major=True)
     return code, tree, root
+
+
+# ------------------------------------------------------------------- f-3: EC-sum Quark prover (cpu/mod.rs:72-316)
+SEPTIC_EXTENSION_DEGREE = 7
+
+
+def ecc_quark_selectors(dev, out_rt, num_instances):
+    """(sel_add, sel_bypass, sel_export) as device ext MLEs (cg_ecc_quark_selectors)."""
+    out_rt = _u64(out_rt)
+    n = out_rt.size // 2
+    bufs = [dev.alloc(16 << n) for _ in range(3)]
+    dev.check(dev.lib.cg_ecc_quark_selectors(dev.ctx, _vp(out_rt), n, num_instances, *[C.c_void_p(b.ptr) for b in bufs], None))
+    dev.sync()
+    return [MultilinearExtension(dev, b, n, True) for b in bufs]
+
+
+def split_even_odd(dev, mles):
+    """filter_bj: ([v[2b]], [v[2b+1]]) for base MLEs (cg_split_even_odd)."""
+    nv = mles[0].num_vars
+    ev = [dev.alloc(8 << (nv - 1)) for _ in mles]
+    od = [dev.alloc(8 << (nv - 1)) for _ in mles]
+    descs = (_lib.CgMleDesc * len(mles))(*[m.desc() for m in mles])
+    pe = (C.c_void_p * len(mles))(*[b.ptr for b in ev])
+    po = (C.c_void_p * len(mles))(*[b.ptr for b in od])
+    dev.check(dev.lib.cg_split_even_odd(dev.ctx, descs, len(mles), pe, po, None))
+    dev.sync()
+    return ([MultilinearExtension(dev, b, nv - 1, False) for b in ev], [MultilinearExtension(dev, b, nv - 1, False) for b in od])
+
+
+class EccQuarkProver:
+    """CpuEccProver::create_ecc_proof (ceno_zkvm/src/scheme/cpu/mod.rs:72-316; trait EccQuarkProver, hal.rs:164-171):
+    accumulate 2^n EC points (affine, septic extension coordinates) in one Quark-style layer.  xs / ys / invs are 7
+    base-field device MLEs each with n+1 variables.  Returns the EccQuarkProof fields as a dict."""
+
+    @staticmethod
+    def build_terms(alpha_pows, final_sum_x, final_sum_y):
+        """The zerocheck expression in monomial form over the MLE order
+        [sel_add, sel_bypass, sel_export, s(7), x0(7), y0(7), x1(7), y1(7), x3(7), y3(7)]  (:153-262)."""
+        from .expr import Poly, SymbolicSepticExtension as Sep, ext
+        D = SEPTIC_EXTENSION_DEGREE
+        sel_add, sel_bypass, sel_export = Poly.var(0), Poly.var(1), Poly.var(2)
+        grp = lambda g: Sep([Poly.var(3 + D * g + i) for i in range(D)])
+        s, x0, y0, x1, y1, x3, y3 = (grp(g) for g in range(7))
+        al = iter([ext(int(a[0]), int(a[1])) for a in alpha_pows])
+        comb = lambda exprs: sum((e * next(al) for e in exprs), Poly())
+        add = Poly()
+        add = add + comb((s * (x0 - x1) - (y0 - y1)).to_exprs())            # slope
+        add = add + comb(((s * s) - x0 - x1 - x3).to_exprs())               # x3 = s^2 - x0 - x1
+        add = add + comb((s * (x0 - x3) - (y0 + y3)).to_exprs())            # y3 = s (x0 - x3) - y0
+        byp = comb((x3 - x0).to_exprs()) + comb((y3 - y0).to_exprs())
+        exp = comb([x - Poly.const(int(f)) for x, f in zip(x3.to_exprs() + y3.to_exprs(), list(final_sum_x) + list(final_sum_y))])
+        return (add * sel_add + byp * sel_bypass + exp * sel_export).terms()
+
+    @staticmethod
+    def create_ecc_proof(dev, num_instances, xs, ys, invs, transcript, flags=0):
+        D = SEPTIC_EXTENSION_DEGREE
+        assert len(xs) == D and len(ys) == D and len(invs) == D
+        n = xs[0].num_vars - 1
+        out_rt = transcript.sample_and_append_vec(b"ecc", n)
+        alpha_pows = transcript.sample_and_append_challenge_pows(D * 3 + D * 2 + D * 2, b"ecc_alpha")
+        sels = ecc_quark_selectors(dev, out_rt, num_instances)
+        x0, x1 = split_even_odd(dev, xs)
+        y0, y1 = split_even_odd(dev, ys)
+        half = 8 << n
+        view = lambda m: MultilinearExtension(dev, DeviceBuffer(dev, m.buf.ptr + half, half, owner=False), n, False)   # as_view_slice(2, 1)
+        x3, y3, s = [view(m) for m in xs], [view(m) for m in ys], [view(m) for m in invs]
+        last = (1 << n) - 2                                            # the final sum sits at [1,..,1,0]
+        fx = [int(m.buf.to_host(8, 8 * last)[0]) for m in x3]
+        fy = [int(m.buf.to_host(8, 8 * last)[0]) for m in y3]
+        terms = EccQuarkProver.build_terms(alpha_pows, fx, fy)
+        mles = sels + s + x0 + y0 + x1 + y1 + x3 + y3
+        rounds, evals, rt = IOPProverState.prove(dev, mles, terms, n, 3, transcript=transcript, flags=flags)
+        for m in sels + x0 + x1 + y0 + y1:
+            m.free()
+        assert evals.shape[0] == 3 + D * 7
+        return {"zerocheck_proof": rounds, "num_instances": num_instances, "evals": evals, "rt": rt, "sum": (fx, fy)}

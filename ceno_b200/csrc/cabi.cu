@@ -390,6 +390,51 @@ CG_EXPORT int cg_selector_compute(cg_ctx* c, int kind, const uint64_t* h_point, 
     }
 }
 
+// EC-sum Quark pre-passes (f-3): the three selector MLEs of CpuEccProver::create_ecc_proof and the even/odd split
+CG_EXPORT int cg_ecc_quark_selectors(cg_ctx* c, const uint64_t* h_out_rt, uint32_t n_vars, uint64_t num_instances, uint64_t* d_sel_add,
+                                     uint64_t* d_sel_bypass, uint64_t* d_sel_export, cg_stream s) {
+    if (!c || !d_sel_add || !d_sel_bypass || !d_sel_export) return CG_ERR_INVALID;
+    if (n_vars == 0 || n_vars > 40) return set_err(c, CG_ERR_INVALID, "cg_ecc_quark_selectors: num_vars out of range");
+    const uint64_t n = 1ULL << n_vars;
+    if (num_instances > n) return set_err(c, CG_ERR_INVALID, "cg_ecc_quark_selectors: num_instances > 2^num_vars");
+    cudaStream_t st = S(c, s);
+    CHK(cg_selector_compute(c, CG_SEL_QUARK_LT, h_out_rt, n_vars, 0, num_instances, nullptr, 0, 0, d_sel_add, s));
+    CHK(cg_build_eq(c, h_out_rt, n_vars, d_sel_bypass, 0, n, s));
+    ecc_selectors_kernel<<<grid_for(c, n), CG_THREADS, 0, st>>>((const ext_t*)d_sel_add, (ext_t*)d_sel_bypass, (ext_t*)d_sel_export, n);
+    LAUNCHED(c);
+    CU(c, cudaGetLastError());
+    return CG_OK;
+}
+CG_EXPORT int cg_split_even_odd(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, uint64_t* const* d_even, uint64_t* const* d_odd, cg_stream s) {
+    if (!c || (n_mles && (!mles || !d_even || !d_odd))) return CG_ERR_INVALID;
+    if (n_mles == 0) return CG_OK;
+    const uint32_t nv = mles[0].num_vars;
+    if (nv == 0) return set_err(c, CG_ERR_INVALID, "cg_split_even_odd: MLE has no variables");
+    std::vector<const void*> ptrs(3 * (size_t)n_mles);
+    for (uint32_t i = 0; i < n_mles; i++) {
+        if (mles[i].is_ext != CG_MLE_BASE) return set_err(c, CG_ERR_INVALID, "cg_split_even_odd: base-field MLEs only (get_base_field_vec, cpu/mod.rs:141)");
+        if (mles[i].num_vars != nv || mles[i].len != (1ULL << nv)) return set_err(c, CG_ERR_INVALID, "cg_split_even_odd: all MLEs must be full and of one size");
+        if ((uintptr_t)mles[i].dptr & 15) return set_err(c, CG_ERR_INVALID, "cg_split_even_odd: input must be 16-byte aligned");
+        ptrs[i] = mles[i].dptr;
+        ptrs[n_mles + i] = d_even[i];
+        ptrs[2 * (size_t)n_mles + i] = d_odd[i];
+    }
+    cudaStream_t st = S(c, s);
+    CU(c, cudaSetDevice(c->device));
+    void* d_ptrs = nullptr;
+    CHK(upload_small(c, ptrs.data(), sizeof(void*) * ptrs.size(), &d_ptrs, st));
+    SplitArgs a;
+    a.in = (const uint64_t* const*)d_ptrs;
+    a.even = (uint64_t* const*)d_ptrs + n_mles;
+    a.odd = (uint64_t* const*)d_ptrs + 2 * (size_t)n_mles;
+    a.n_out = 1ULL << (nv - 1);
+    split_even_odd_kernel<<<dim3(grid_for(c, a.n_out), n_mles), 256, 0, st>>>(a);
+    LAUNCHED(c);
+    tmp_free(d_ptrs, st);
+    CU(c, cudaGetLastError());
+    return CG_OK;
+}
+
 
 // ------------------------------------------------------------------------------------- comm
 // Multi-GPU mailbox (the reference has no multi-GPU path — docs/src/optimizations.md:3-5

@@ -1296,6 +1296,38 @@ __global__ void quark_mask_kernel(ext_t* __restrict__ v, uint64_t n, const __gri
     }
 }
 
+// EC-sum Quark pre-passes (CpuEccProver::create_ecc_proof, ceno_zkvm/src/scheme/cpu/mod.rs:100-133, 138-162).
+// On entry sel_add = the QuarkBinaryTreeLessThan selector (masked eq), sel_bypass = the unmasked eq(out_rt, .) table.
+//   sel_bypass[b] = 0 where sel_add[b] != 0 and at the last index;  sel_export = one-hot at n - 2 carrying
+//   eq_eval(out_rt, (0,1,...,1)), which IS the eq table entry at n - 2 (index bit i = variable i).
+__global__ void ecc_selectors_kernel(const ext_t* __restrict__ sel_add, ext_t* __restrict__ sel_bypass, ext_t* __restrict__ sel_export, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride) {
+        const ext_t a = ld_ext(sel_add + b), e = ld_ext(sel_bypass + b);
+        const bool add_on = (a.c0 | a.c1) != 0;
+        st_ext(sel_export + b, (n >= 2 && b == n - 2) ? e : ext_zero());
+        if (add_on || b == n - 1) st_ext(sel_bypass + b, ext_zero());
+    }
+}
+// filter_bj (cpu/mod.rs:138-152): even[b] = v[2b], odd[b] = v[2b+1] for base-field vectors; one 16-byte load per pair
+struct SplitArgs {
+    const uint64_t* const* in;     // device array of n_mles pointers
+    uint64_t* const* even;
+    uint64_t* const* odd;
+    uint64_t n_out;                // pairs per MLE
+};
+__global__ void __launch_bounds__(256) split_even_odd_kernel(const __grid_constant__ SplitArgs a) {
+    const uint64_t* __restrict__ in = a.in[blockIdx.y];
+    uint64_t* __restrict__ ev = a.even[blockIdx.y];
+    uint64_t* __restrict__ od = a.odd[blockIdx.y];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < a.n_out; b += stride) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(in + 2 * b);
+        ev[b] = gl_canon(v.x);
+        od[b] = gl_canon(v.y);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // interleaving_mles_to_mles (ceno_zkvm/src/scheme/utils.rs:402-462): R record MLEs (one value per instance)
 // become `num_limbs` tower leaves, out[limb][s * 2^ceil_log2(R) + i] = mle_i[limb * per_fanin_len + s], padded with

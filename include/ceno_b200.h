@@ -297,6 +297,18 @@ int cg_rotation_next_base_mle(cg_ctx* ctx, const cg_mle_desc* base_mle, uint32_t
 int cg_rotation_selector(cg_ctx* ctx, const uint64_t* d_eq_ext, uint64_t total_len, uint32_t cyclic_subgroup_size,
                          uint32_t cyclic_group_log2, uint64_t* d_out_ext, cg_stream s);
 
+/* ---- f-3: EC-sum Quark pre-passes (CpuEccProver::create_ecc_proof, ceno_zkvm/src/scheme/cpu/mod.rs:72-316; the
+ * zerocheck itself is a degree-3 cg_sumcheck_prove over the monomial terms of the septic-extension constraints).
+ * cg_ecc_quark_selectors: for out_rt (n ext, host) writes three ext MLEs of 2^n entries:
+ *   sel_add    = SelectorType::QuarkBinaryTreeLessThan.compute(out_rt, {offset 0, num_instances, n})   (:100-107)
+ *   sel_export = one-hot at index 2^n - 2 with value eq_eval(out_rt, (0,1,..,1))                       (:109-117)
+ *   sel_bypass = eq(out_rt, .) zeroed wherever sel_add != 0 and at the last index                      (:119-133)
+ * cg_split_even_odd: filter_bj (:138-152): even[i][b] = mle_i[2b], odd[i][b] = mle_i[2b+1] (base MLEs; x[b,0] / x[b,1]).
+ * x[1,b] = as_view_slice(2, 1) is the second half of the same buffer: a pointer offset, no call needed. */
+int cg_ecc_quark_selectors(cg_ctx* ctx, const uint64_t* h_out_rt_ext, uint32_t num_vars, uint64_t num_instances,
+                           uint64_t* d_sel_add_ext, uint64_t* d_sel_bypass_ext, uint64_t* d_sel_export_ext, cg_stream s);
+int cg_split_even_odd(cg_ctx* ctx, const cg_mle_desc* mles, uint32_t n_mles, uint64_t* const* d_even, uint64_t* const* d_odd, cg_stream s);
+
 /* ---- kernel (iii-commit): Merkle commitment over Poseidon2-Goldilocks (TraceCommitter::commit_traces ->
  * PCS::batch_commit, ceno_zkvm/src/scheme/cpu/mod.rs:559-584; GPU basefold.batch_commit_*,
  * ceno_zkvm/src/scheme/gpu/mod.rs:1062-1509).  PARITY UNPINNED: Poseidon2 round constants, the internal diagonal

@@ -437,3 +437,179 @@ def rs_encode(msg, width, log_n, rate_log, bitrev=True):
     if lib().or_rs_encode(_p(msg), C.c_uint64(width), C.c_uint32(log_n), C.c_uint32(rate_log), _p(out), C.c_int(int(bitrev))):
         raise ValueError("or_rs_encode: bad size")
     return out
+
+
+# ------------------------------------------------------------------------------- EC-sum Quark (f-3)
+# CpuEccProver::create_ecc_proof (ceno_zkvm/src/scheme/cpu/mod.rs:72-316) restated: selectors, even/odd split,
+# the septic-extension constraints expanded to monomials, then the generic sumcheck.  Written independently of
+# ceno_b200/expr.py (explicit multiplication table instead of a symbolic polynomial class).
+SEPTIC_D = 7
+
+
+def _septic_table():
+    """z^i * z^j = sum c z^k with z^7 = 2z + 5 (ceno_zkvm/src/scheme/septic_curve.rs:689-701)."""
+    return [[([(i + j, 1)] if i + j < 7 else [(i + j - 7, 5), (i + j - 6, 2)]) for j in range(7)] for i in range(7)]
+
+
+def septic_mul(a, b):
+    out = [0] * 7
+    tab = _septic_table()
+    for i in range(7):
+        for j in range(7):
+            for k, c in tab[i][j]:
+                out[k] = (out[k] + c * a[i] * b[j]) % P
+    return out
+
+
+def septic_inv(a):
+    """Inverse in F_p[z]/(z^7 - 2z - 5) by solving (mult-by-a) u = 1 (Gaussian elimination mod p; test-size only)."""
+    cols = []
+    for j in range(7):
+        e = [0] * 7
+        e[j] = 1
+        cols.append(septic_mul(a, e))
+    m = [[cols[j][i] for j in range(7)] + [1 if i == 0 else 0] for i in range(7)]
+    for c in range(7):
+        piv = next(r for r in range(c, 7) if m[r][c])
+        m[c], m[piv] = m[piv], m[c]
+        inv = pow(m[c][c], P - 2, P)
+        m[c] = [v * inv % P for v in m[c]]
+        for r in range(7):
+            if r != c and m[r][c]:
+                f = m[r][c]
+                m[r] = [(v - f * w) % P for v, w in zip(m[r], m[c])]
+    return [m[i][7] for i in range(7)]
+
+
+def ecc_quark_make_witness(seed, n, num_instances):
+    """xs, ys, invs: 7 base arrays of 2^(n+1) each laid out like the reference's EC-sum chip: leaves in the first half,
+    node (1,b) at 2^n + b = children 2b (+) 2b+1 where the Quark selector is on, a copy of child 2b elsewhere; the slope
+    s[1,b] in invs.  The affine-addition identities hold for ANY pairs with x0 != x1, so random 'points' give a witness on
+    which all seven constraint families vanish."""
+    N = 1 << n
+    rnd = fill_base(seed, 14 * num_instances).reshape(num_instances, 14)
+    X = [[0] * 7 for _ in range(2 * N)]
+    Y = [[0] * 7 for _ in range(2 * N)]
+    S = [[0] * 7 for _ in range(2 * N)]
+    for i in range(num_instances):
+        X[i] = [int(v) for v in rnd[i, :7]]
+        Y[i] = [int(v) for v in rnd[i, 7:]]
+    on = selector_compute(3, fill_ext(seed + 1, n), 0, num_instances).reshape(-1, 2)
+    sub = lambda a, b: [(u - v) % P for u, v in zip(a, b)]
+    for b in range(N - 1):
+        l, r = 2 * b, 2 * b + 1
+        if on[b].any():
+            s = septic_mul(sub(Y[l], Y[r]), septic_inv(sub(X[l], X[r])))
+            x3 = sub(sub(septic_mul(s, s), X[l]), X[r])
+            y3 = sub(septic_mul(s, sub(X[l], x3)), Y[l])
+            X[N + b], Y[N + b], S[N + b] = x3, y3, s
+        else:
+            X[N + b], Y[N + b] = list(X[l]), list(Y[l])
+    col = lambda M, i: np.array([row[i] for row in M], dtype=np.uint64)
+    return [col(X, i) for i in range(7)], [col(Y, i) for i in range(7)], [col(S, i) for i in range(7)]
+
+
+def ecc_quark_selectors(out_rt, num_instances):
+    n = _u64(out_rt).size // 2
+    sel_add = selector_compute(3, out_rt, 0, num_instances).reshape(-1, 2)
+    eq = build_eq_x_r_vec(out_rt).reshape(-1, 2)
+    sel_export = np.zeros_like(eq)
+    sel_export[(1 << n) - 2] = eq_eval(out_rt, np.array([0, 0] + [1, 0] * (n - 1), dtype=np.uint64))
+    sel_bypass = eq.copy()
+    sel_bypass[sel_add.any(axis=1)] = 0
+    sel_bypass[-1] = 0
+    return sel_add.reshape(-1), sel_bypass.reshape(-1), sel_export.reshape(-1)
+
+
+def ecc_quark_terms(alpha_pows, fx, fy):
+    """MLE order [sel_add, sel_bypass, sel_export, s, x0, y0, x1, y1, x3, y3] (7 each after the selectors)."""
+    tab = _septic_table()
+    V = lambda g, i: 3 + 7 * g + i
+    Sg, X0, Y0, X1, Y1, X3, Y3 = range(7)
+    acc = {}
+
+    def add_term(coef, factors):
+        key = tuple(sorted(factors))
+        c = acc.get(key, (0, 0))
+        acc[key] = ((c[0] + coef[0]) % P, (c[1] + coef[1]) % P)
+
+    def scale(a, c):
+        return (a[0] * c % P, a[1] * c % P)
+
+    al = [(int(a[0]), int(a[1])) for a in np.asarray(alpha_pows, dtype=np.uint64).reshape(-1, 2)]
+    ai = 0
+    SEL_ADD, SEL_BYP, SEL_EXP = 0, 1, 2
+    # 1) s (x0 - x1) - (y0 - y1)
+    for k in range(7):
+        a = al[ai + k]
+        for i in range(7):
+            for j in range(7):
+                for kk, c in tab[i][j]:
+                    if kk == k:
+                        add_term(scale(a, c), [SEL_ADD, V(Sg, i), V(X0, j)])
+                        add_term(scale(a, P - c), [SEL_ADD, V(Sg, i), V(X1, j)])
+        add_term(scale(a, P - 1), [SEL_ADD, V(Y0, k)])
+        add_term(a, [SEL_ADD, V(Y1, k)])
+    ai += 7
+    # 2) s^2 - x0 - x1 - x3
+    for k in range(7):
+        a = al[ai + k]
+        for i in range(7):
+            for j in range(7):
+                for kk, c in tab[i][j]:
+                    if kk == k:
+                        add_term(scale(a, c), [SEL_ADD, V(Sg, i), V(Sg, j)])
+        for g in (X0, X1, X3):
+            add_term(scale(a, P - 1), [SEL_ADD, V(g, k)])
+    ai += 7
+    # 3) s (x0 - x3) - (y0 + y3)
+    for k in range(7):
+        a = al[ai + k]
+        for i in range(7):
+            for j in range(7):
+                for kk, c in tab[i][j]:
+                    if kk == k:
+                        add_term(scale(a, c), [SEL_ADD, V(Sg, i), V(X0, j)])
+                        add_term(scale(a, P - c), [SEL_ADD, V(Sg, i), V(X3, j)])
+        add_term(scale(a, P - 1), [SEL_ADD, V(Y0, k)])
+        add_term(scale(a, P - 1), [SEL_ADD, V(Y3, k)])
+    ai += 7
+    # bypass: x3 - x0, y3 - y0
+    for g3, g0 in ((X3, X0), (Y3, Y0)):
+        for k in range(7):
+            a = al[ai + k]
+            add_term(a, [SEL_BYP, V(g3, k)])
+            add_term(scale(a, P - 1), [SEL_BYP, V(g0, k)])
+        ai += 7
+    # export: x3 - final_x, y3 - final_y
+    for g3, fin in ((X3, fx), (Y3, fy)):
+        for k in range(7):
+            a = al[ai + k]
+            add_term(a, [SEL_EXP, V(g3, k)])
+            add_term(scale(a, (P - int(fin[k])) % P), [SEL_EXP])
+        ai += 7
+    return [([c[0], c[1]], list(k)) for k, c in sorted(acc.items()) if c != (0, 0)]
+
+
+def ecc_quark_create_proof(num_instances, xs, ys, invs, transcript):
+    n = int(np.log2(xs[0].size)) - 1
+    N = 1 << n
+    out_rt = np.concatenate([transcript.sample(b"ecc") for _ in range(n)])
+    a = transcript.sample(b"ecc_alpha")
+    alpha, cur, one = (int(a[0]), int(a[1])), (1, 0), None
+    pows = []
+    for _ in range(49):
+        pows.append(cur)
+        cur = ((cur[0] * alpha[0] + 7 * cur[1] * alpha[1]) % P, (cur[0] * alpha[1] + cur[1] * alpha[0]) % P)
+    sel = ecc_quark_selectors(out_rt, num_instances)
+    ev = lambda v: [np.ascontiguousarray(a[0::2]) for a in v]
+    od = lambda v: [np.ascontiguousarray(a[1::2]) for a in v]
+    hi = lambda v: [np.ascontiguousarray(a[N:]) for a in v]
+    last = N - 2
+    fx, fy = [int(a[N + last]) for a in xs], [int(a[N + last]) for a in ys]
+    terms = ecc_quark_terms(np.array(pows, dtype=np.uint64), fx, fy)
+    groups = hi(invs) + ev(xs) + ev(ys) + od(xs) + od(ys) + hi(xs) + hi(ys)
+    mles = [(s, True, n) for s in sel] + [(g, False, n) for g in groups]
+    rounds, evals, rt = sumcheck_prove(mles, terms, n, 3, transcript=transcript)
+    return {"zerocheck_proof": rounds, "num_instances": num_instances, "evals": evals, "rt": rt, "sum": (fx, fy),
+            "out_rt": out_rt, "mles": mles, "terms": terms}

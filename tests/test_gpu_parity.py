@@ -831,3 +831,53 @@ def test_ntt_large_roundtrip_and_linearity(dev):
     api.ntt(dev, buf, log_n, n_cols, inverse=True, bitrev=True)
     assert eq_np(buf.to_host(), x)
     buf.free()
+
+
+# ------------------------------------------------------------------ f-3: EC-sum Quark prover
+@pytest.mark.parametrize("n,num_instances", [(1, 2), (3, 5), (6, 64), (10, 777), (14, 1 << 14)])
+def test_ecc_quark_prover_bit_exact(dev, n, num_instances):
+    """EccQuarkProver::prove_ec_sum_quark shape (cpu/mod.rs:72-316): device pre-passes (selectors, even/odd split, views)
+    + the degree-3 zerocheck over 260 monomial terms, against the oracle restatement; host term expansion against the
+    oracle's independent one."""
+    import ceno_b200 as cb
+    from ceno_b200 import api
+    if n <= 6:
+        xs, ys, invs = orc.ecc_quark_make_witness(800 + n, n, num_instances)
+    else:                                                   # parity does not need a satisfying witness
+        xs, ys, invs = ([orc.fill_base(900 + 10 * g + i, 2 << n) for i in range(7)] for g in range(3))
+    want = orc.ecc_quark_create_proof(num_instances, xs, ys, invs, orc.Transcript(b"ecc"))
+    # pre-passes on their own
+    sels = api.ecc_quark_selectors(dev, want["out_rt"], num_instances)
+    for m, w in zip(sels, orc.ecc_quark_selectors(want["out_rt"], num_instances)):
+        assert eq_np(m.evaluations(), w)
+        m.free()
+    dx = [cb.MultilinearExtension.from_evaluations_vec(dev, n + 1, v) for v in xs]
+    dy = [cb.MultilinearExtension.from_evaluations_vec(dev, n + 1, v) for v in ys]
+    di = [cb.MultilinearExtension.from_evaluations_vec(dev, n + 1, v) for v in invs]
+    ev, od = api.split_even_odd(dev, dx)
+    for i in range(7):
+        assert eq_np(ev[i].evaluations(), xs[i][0::2]) and eq_np(od[i].evaluations(), xs[i][1::2])
+    for m in ev + od:
+        m.free()
+    got = cb.EccQuarkProver.create_ecc_proof(dev, num_instances, dx, dy, di, cb.StandInTranscript(b"ecc"))
+    assert sorted((tuple(c), tuple(i)) for c, i in api.EccQuarkProver.build_terms(
+        orc_alpha_pows(b"ecc", n), want["sum"][0], want["sum"][1])) == sorted((tuple(c), tuple(i)) for c, i in want["terms"])
+    for key in ("zerocheck_proof", "evals", "rt"):
+        assert eq_np(got[key], want[key]), key
+    assert got["sum"] == want["sum"]
+    if n <= 6:                                              # a zerocheck: first-round claim p(0) + p(1) = 0
+        assert eq_np(got["zerocheck_proof"], want["zerocheck_proof"])
+    for m in dx + dy + di:
+        m.free()
+
+
+def orc_alpha_pows(label, n):
+    t = orc.Transcript(label)
+    for _ in range(n):
+        t.sample(b"ecc")
+    a = t.sample(b"ecc_alpha")
+    a, cur, out = (int(a[0]), int(a[1])), (1, 0), []
+    for _ in range(49):
+        out.append(cur)
+        cur = ((cur[0] * a[0] + 7 * cur[1] * a[1]) % P, (cur[0] * a[1] + cur[1] * a[0]) % P)
+    return np.array(out, dtype=np.uint64)

@@ -519,3 +519,63 @@ def test_rs_encode_is_polynomial_evaluation_and_linear():
     assert [int(v) for v in cs] == [(int(u) + int(v)) % P for u, v in zip(ca, cb_)]
     const = np.zeros(n, np.uint64); const[0] = 5
     assert set(int(v) for v in orc.rs_encode(const, 1, log_n, rate_log)) == {5}
+
+
+# ------------------------------------------------------------------ EC-sum Quark (f-3)
+def test_septic_extension_arithmetic():
+    """F[z]/(z^7 - 2z - 5) (ceno_zkvm/src/scheme/septic_curve.rs:30-39): z^7 = 2z + 5, inverses, associativity."""
+    z = [0, 1, 0, 0, 0, 0, 0]
+    acc = [1, 0, 0, 0, 0, 0, 0]
+    for _ in range(7):
+        acc = orc.septic_mul(acc, z)
+    assert acc == [5, 2, 0, 0, 0, 0, 0]
+    a, b, c = ([int(v) for v in orc.fill_base(s, 7)] for s in (1, 2, 3))
+    assert orc.septic_mul(a, orc.septic_inv(a)) == [1, 0, 0, 0, 0, 0, 0]
+    assert orc.septic_mul(orc.septic_mul(a, b), c) == orc.septic_mul(a, orc.septic_mul(b, c))
+
+
+@pytest.mark.parametrize("n,num_instances", [(1, 2), (3, 8), (3, 5), (4, 11), (5, 32)])
+def test_ecc_quark_zerocheck_vanishes_on_a_valid_witness_and_verifies(n, num_instances):
+    """create_ecc_proof (ceno_zkvm/src/scheme/cpu/mod.rs:72-316) on a witness built with the affine-addition formulas:
+    the claimed sum is 0 (it is a zerocheck), every round satisfies p(0) + p(1) = claim with p(0) derived by the
+    verifier, and the final claim equals the expression at the returned evaluations (its sanity-check block :268-290)."""
+    xs, ys, invs = orc.ecc_quark_make_witness(700 + n, n, num_instances)
+    proof = orc.ecc_quark_create_proof(num_instances, xs, ys, invs, orc.Transcript(b"ecc-kat"))
+    rounds, evals, rt, terms = proof["zerocheck_proof"], proof["evals"], proof["rt"], proof["terms"]
+    assert evals.shape[0] == 3 + 7 * 7
+    mles_p = [[(int(a), int(b)) for a, b in m.reshape(-1, 2)] if is_ext else [(int(a), 0) for a in m] for m, is_ext, _ in proof["mles"]]
+    tl = [((int(c[0]), int(c[1])), ids) for c, ids in terms]
+    # the polynomial vanishes at every hypercube point, not only in sum (zero constraints under their selectors)
+    for b in range(1 << n):
+        assert pr.poly_eval(mles_p, tl, b) == pr.ZERO
+    claim = pr.ZERO
+    for j in range(n):
+        msg = [tuple(int(x) for x in e) for e in rounds[j]]
+        e0 = pr.esub(claim, msg[0])
+        claim = pr.lagrange_eval([e0] + msg, tuple(int(x) for x in rt[j]))
+    fin = [tuple(int(x) for x in e) for e in evals]
+    assert fin == [pr.mle_evaluate(m_, [tuple(int(x) for x in r) for r in rt]) for m_ in mles_p]
+    acc = pr.ZERO
+    for c, ids in tl:
+        p = c
+        for i in ids:
+            p = pr.emul(p, fin[i])
+        acc = pr.eadd(acc, p)
+    assert acc == claim
+    # sel_export(rt) = eq(out_rt, lsi) * eq(rt, lsi), lsi = (0,1,..,1)   (cpu/mod.rs:274-275)
+    lsi = np.array([0, 0] + [1, 0] * (n - 1), dtype=np.uint64)
+    want = orc.ext_mul(orc.eq_eval(proof["out_rt"], lsi), orc.eq_eval(rt.reshape(-1), lsi))
+    assert tuple(int(x) for x in want) == fin[2]
+
+
+def test_ecc_quark_detects_a_broken_witness():
+    n, ni = 3, 8
+    xs, ys, invs = orc.ecc_quark_make_witness(9, n, ni)
+    xs[2][(1 << n) + 1] ^= np.uint64(1)                  # corrupt one coordinate limb of node (1,1)
+    proof = orc.ecc_quark_create_proof(ni, xs, ys, invs, orc.Transcript(b"ecc-kat"))
+    mles_p = [[(int(a), int(b)) for a, b in m.reshape(-1, 2)] if is_ext else [(int(a), 0) for a in m] for m, is_ext, _ in proof["mles"]]
+    tl = [((int(c[0]), int(c[1])), ids) for c, ids in proof["terms"]]
+    total = pr.ZERO
+    for b in range(1 << n):
+        total = pr.eadd(total, pr.poly_eval(mles_p, tl, b))
+    assert total != pr.ZERO

@@ -15,7 +15,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ceno_b200 as cb
-from ceno_b200 import api, synth
+from ceno_b200 import _lib, api, synth
 
 P = 0xFFFFFFFF00000001
 dev = cb.Device(0)
@@ -113,5 +113,52 @@ perms = height * (width // 4) + height - 1
 out["C-26"] = {"width": width, "height": height, "elements": width * height, "ms": c_ms, "permutations": perms,
                "Mperm_per_s": perms / (c_ms * 1e-3) / 1e6, "GBps_read": 8 * width * height / (c_ms * 1e-3) / 1e9,
                "note": "placeholder constants; leaf hash + Merkle only (no RS encode)"}
+tree.free()
+
+# ---------------------------------------------------------------- RS-26 / COMMIT-26 (BASELINE config #5: 2^26-element batch, eq-build + fold + commit)
+log_n, rate_log = 20, 1
+code = dev.alloc(8 * (width << (log_n + rate_log)))
+
+
+def encode():
+    dev.check(dev.lib.cg_rs_encode(dev.ctx, C.c_void_p(mat.ptr), width, log_n, rate_log, C.c_void_p(code.ptr), api.NTT_BITREV, None))
+
+
+e_ms = timeit(encode, reps=5)
+n_code = width << (log_n + rate_log)
+# algorithmic bytes: pass 1 reads the message (zero padding is implicit) and writes the code, pass 2 reads + writes the code
+alg = 8 * (width << log_n) + 3 * 8 * n_code
+out["RS-26"] = {"width": width, "log_n": log_n, "rate_log": rate_log, "ms": e_ms, "passes": 2, "algorithmic_bytes": alg,
+                "GBps": alg / (e_ms * 1e-3) / 1e9, "butterflies_per_s": (n_code // 2) * (log_n + rate_log) / (e_ms * 1e-3)}
+tree2 = dev.alloc(32 * (2 * (height << rate_log) - 1))
+
+
+def full_commit():
+    encode()
+    root = np.zeros(4, np.uint64)
+    dev.check(dev.lib.cg_merkle_commit(dev.ctx, C.c_void_p(code.ptr), width, height << rate_log, 1, C.c_void_p(tree2.ptr), root.ctypes.data_as(C.c_void_p), None))
+
+
+fc_ms = timeit(full_commit, reps=3)
+out["COMMIT-26"] = {"ms": fc_ms, "note": "RS-encode (rate 1/2, bit-reversed rows) + Poseidon2 leaf hash + Merkle over the 64 x 2^21 codeword matrix; placeholder constants"}
+# the other two legs of config #5 on the same 64 x 2^20 batch: eq-build (k = 20) and one fix_variable of all 64 columns
+w20 = synth.fill_ext(0xE9, log_n)
+eq20 = dev.alloc(16 << log_n)
+eq20_ms = timeit(lambda: cb.build_eq_x_r_vec(dev, w20, out=eq20), reps=10)
+descs = (_lib.CgMleDesc * width)(*[_lib.CgMleDesc(mat.ptr + 8 * height * cidx, height, log_n, 0) for cidx in range(width)])
+fold_out = dev.alloc(16 * (height // 2) * width)
+outs = (C.c_void_p * width)(*[fold_out.ptr + 16 * (height // 2) * cidx for cidx in range(width)])
+r_fold = synth.fill_ext(0xF01D, 1)
+
+
+def fold_all():
+    dev.check(dev.lib.cg_fix_variable(dev.ctx, descs, width, r_fold.ctypes.data_as(C.c_void_p), outs, None))
+
+
+f_ms = timeit(fold_all, reps=10)
+fold_bytes = width * (8 * height + 16 * (height // 2))
+out["BATCH-26"] = {"config": "BASELINE #5: 2^26-element MLE batch = 64 base columns x 2^20 rows", "eq_build_ms": eq20_ms,
+                   "fold_ms": f_ms, "fold_GBps": fold_bytes / (f_ms * 1e-3) / 1e9, "rs_encode_ms": e_ms, "commit_total_ms": fc_ms,
+                   "total_ms": eq20_ms + f_ms + fc_ms}
 print(json.dumps(out))
 dev.close()
