@@ -393,24 +393,27 @@ def prove_sharded(dev, comm, mles, terms, num_vars_global, degree, transcript, f
     return rounds[:2 * degree * k].reshape(k, degree, 2), fin[:2 * len(mles)].reshape(-1, 2), chal[:2 * k].reshape(k, 2)
 
 
-def wit_infer_by_monomial_expr(dev, mles, terms, num_vars):
+def wit_infer_by_monomial_expr(dev, mles, terms, num_vars, stream=None):
     descs = (_lib.CgMleDesc * max(len(mles), 1))(*[m.desc() for m in mles])
     coeff, off, idx = _terms(terms)
     out = dev.alloc(16 << num_vars)
     dev.check(dev.lib.cg_wit_infer_by_monomial_expr(dev.ctx, descs, len(mles), _vp(coeff), _vp(off), _vp(idx), len(terms), num_vars,
-                                                    C.c_void_p(out.ptr), None))
-    dev.sync()
+                                                    C.c_void_p(out.ptr), C.c_void_p(stream) if stream else None))
+    if not stream:
+        dev.sync()
     return MultilinearExtension(dev, out, num_vars, True)
 
 
-def interleaving_mles_to_mles(dev, mles, num_instances, num_limbs, default):
+def interleaving_mles_to_mles(dev, mles, num_instances, num_limbs, default, stream=None):
     """ceno_zkvm/src/scheme/utils.rs:402-462 on the device: returns `num_limbs` ext MLEs (tower leaves)."""
     descs = (_lib.CgMleDesc * len(mles))(*[m.desc() for m in mles])
     out_len = int(dev.lib.cg_tower_interleave_out_len(len(mles), num_instances, num_limbs))
     out = dev.alloc(16 * out_len * num_limbs)
     d = _u64(default)
-    dev.check(dev.lib.cg_tower_interleave(dev.ctx, descs, len(mles), num_instances, num_limbs, _vp(d), C.c_void_p(out.ptr), None))
-    dev.sync()
+    dev.check(dev.lib.cg_tower_interleave(dev.ctx, descs, len(mles), num_instances, num_limbs, _vp(d), C.c_void_p(out.ptr),
+                                          C.c_void_p(stream) if stream else None))
+    if not stream:
+        dev.sync()
     nv = out_len.bit_length() - 1
     return [MultilinearExtension(dev, DeviceBuffer(dev, out.ptr + 16 * out_len * i, 16 * out_len, owner=(i == 0)), nv, True) for i in range(num_limbs)], out
 
@@ -424,7 +427,7 @@ class TowerProverSpec:
 
 
 class TowerProver:
-    def __init__(self, dev, specs):
+    def __init__(self, dev, specs, stream=None):
         self.dev = dev
         arr = (_lib.CgTowerSpec * len(specs))()
         for i, s in enumerate(specs):
@@ -434,7 +437,7 @@ class TowerProver:
             arr[i].num_vars = s.num_vars
             arr[i].is_logup = 1 if s.is_logup else 0
         self.h = C.c_void_p()
-        dev.check(dev.lib.cg_tower_build(dev.ctx, arr, len(specs), None, C.byref(self.h)))
+        dev.check(dev.lib.cg_tower_build(dev.ctx, arr, len(specs), C.c_void_p(stream) if stream else None, C.byref(self.h)))
         self.specs = specs
 
     def output_evals(self, i):
@@ -480,11 +483,12 @@ def poseidon2_permute(dev, states):
     return out
 
 
-def merkle_commit(dev, matrix_buf, width, height, col_major=True):
+def merkle_commit(dev, matrix_buf, width, height, col_major=True, stream=None):
     """matrix_buf: DeviceBuffer of height*width base elements.  Returns (tree DeviceBuffer, root[4])."""
     tree = dev.alloc(32 * (2 * height - 1))
     root = np.zeros(4, np.uint64)
-    dev.check(dev.lib.cg_merkle_commit(dev.ctx, C.c_void_p(matrix_buf.ptr), width, height, 1 if col_major else 0, C.c_void_p(tree.ptr), _vp(root), None))
+    dev.check(dev.lib.cg_merkle_commit(dev.ctx, C.c_void_p(matrix_buf.ptr), width, height, 1 if col_major else 0, C.c_void_p(tree.ptr), _vp(root),
+                                       C.c_void_p(stream) if stream else None))
     return tree, root
 
 
@@ -603,12 +607,12 @@ def rs_encode(dev, msg_buf, width, log_n, rate_log, bitrev=True, stream=None):
     return code
 
 
-def basefold_style_commit(dev, msg_buf, width, log_n, rate_log=1):
+def basefold_style_commit(dev, msg_buf, width, log_n, rate_log=1, stream=None):
     """TraceCommitter::commit_traces shape (ceno_zkvm/src/scheme/cpu/mod.rs:559-584): RS-encode the witness columns,
     Merkle-hash the codeword matrix row-wise.  Returns (code DeviceBuffer, tree DeviceBuffer, root[4]).  Arrangement
     parity is unpinned: bit-reversed codeword rows, one leaf per row across all columns."""
-    code = rs_encode(dev, msg_buf, width, log_n, rate_log, bitrev=True)
-    tree, root = merkle_commit(dev, code, width, 1 << (log_n + rate_log), col_major=True)
+    code = rs_encode(dev, msg_buf, width, log_n, rate_log, bitrev=True, stream=stream)
+    tree, root = merkle_commit(dev, code, width, 1 << (log_n + rate_log), col_major=True, stream=stream)
     return code, tree, root
 
 

@@ -1467,9 +1467,17 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
             for (uint32_t jj = j; jj < upto && rc == CG_OK; jj++) {
                 uint64_t spins = 0;
                 while (mb->seq_msg != (uint64_t)jj + 1) {
-                    if ((++spins & 0xFFFFF) == 0 && cudaStreamQuery(sc->stream) != cudaErrorNotReady) {
-                        if (mb->seq_msg == (uint64_t)jj + 1) break;
-                        rc = set_err(c, CG_ERR_CUDA, "persistent kernel ended before posting its round message");
+                    if ((++spins & 0xFFFFF) == 0) {
+                        const cudaError_t q = cudaStreamQuery(sc->stream);
+                        if (q == cudaErrorNotReady) continue;
+                        // the stream has drained: the message must be there; re-read for a short grace period before giving up
+                        bool seen = false;
+                        for (int grace = 0; grace < 2000000 && !seen; grace++) { __sync_synchronize(); seen = (mb->seq_msg == (uint64_t)jj + 1); }
+                        if (seen) break;
+                        rc = set_err(c, CG_ERR_CUDA, std::string("persistent kernel ended before posting its round message (round ") + std::to_string(jj) +
+                                                         " of " + std::to_string(sc->num_vars) + ", owned up to " + std::to_string(upto) + ", mailbox seq_msg=" +
+                                                         std::to_string((unsigned long long)mb->seq_msg) + " seq_r=" + std::to_string((unsigned long long)mb->seq_r) +
+                                                         " abort=" + std::to_string((int)mb->abort) + ", stream: " + cudaGetErrorString(q) + ")");
                         break;
                     }
                 }

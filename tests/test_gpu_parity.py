@@ -881,3 +881,87 @@ def orc_alpha_pows(label, n):
         out.append(cur)
         cur = ((cur[0] * a[0] + 7 * cur[1] * a[1]) % P, (cur[0] * a[1] + cur[1] * a[0]) % P)
     return np.array(out, dtype=np.uint64)
+
+
+# ------------------------------------------------------------------ chip flow (create_chip_proof shape) on scheduler lanes
+def _chip_oracle(chip, alpha=(12345, 678)):
+    """The same composition on the CPU oracle (records by direct evaluation, towers, main zerocheck)."""
+    k, ninst, n = chip.num_vars, chip.num_instances, 1 << chip.num_vars
+    wit = chip.witness().reshape(chip.n_wit, n)
+    mles = [(np.ascontiguousarray(wit[c]), False, k) for c in range(chip.n_wit)]
+    from oracle import pyref as pr
+
+    def record(e):   # ext vector of the monomial expression, row by row (vectorised big-int is too slow: use the oracle's generic evaluator)
+        out = np.zeros((n, 2), np.uint64)
+        for row in range(n):
+            acc = (0, 0)
+            for c, ids in e:
+                t = (int(c[0]), int(c[1]))
+                for i in ids:
+                    w = int(wit[i, row])
+                    t = (t[0] * w % P, t[1] * w % P)
+                acc = ((acc[0] + t[0]) % P, (acc[1] + t[1]) % P)
+            out[row] = acc
+        return out.reshape(-1)
+
+    groups = [[record(e) for e in ex] for ex in (chip.read_exprs, chip.write_exprs, chip.lk_exprs)]
+    o_prod, o_lk = [], []
+    for recs in groups[:2]:
+        leaves = orc.interleaving_mles_to_mles([(c, True) for c in recs], ninst, 2, [1, 0])
+        nv = (leaves[0].size // 2).bit_length()
+        o_prod.append((orc.infer_tower_product_witness(nv, leaves[0], leaves[1])[0], nv))
+    leaves = orc.interleaving_mles_to_mles([(c, True) for c in groups[2]], ninst, 2, list(alpha))
+    nv = (leaves[0].size // 2).bit_length() - 1
+    o_lk.append((orc.infer_tower_logup_witness(nv, None, None, leaves[0], leaves[1])[0], nv + 1))
+    t = orc.Transcript(chip.name.encode())
+    proof, point = orc.tower_create_proof(o_prod, o_lk, t)
+    rt = point[:2 * k]
+    sel = orc.selector_compute(1, rt, 0, ninst)
+    a = t.sample(b"combine subset evals")
+    a, cur, pows = (int(a[0]), int(a[1])), (1, 0), []
+    for _ in range(sum(len(g) for g in groups)):
+        pows.append(cur)
+        cur = ((cur[0] * a[0] + 7 * cur[1] * a[1]) % P, (cur[0] * a[1] + cur[1] * a[0]) % P)
+    acc, ai = {}, 0
+    for ex in (chip.read_exprs, chip.write_exprs, chip.lk_exprs):
+        for e in ex:
+            for c, ids in e:
+                key = tuple(sorted([0] + [1 + i for i in ids]))
+                cc = ((int(c[0]) * pows[ai][0] + 7 * int(c[1]) * pows[ai][1]) % P, (int(c[0]) * pows[ai][1] + int(c[1]) * pows[ai][0]) % P)
+                v = acc.get(key, (0, 0))
+                acc[key] = ((v[0] + cc[0]) % P, (v[1] + cc[1]) % P)
+            ai += 1
+    terms = [([c[0], c[1]], list(kk)) for kk, c in sorted(acc.items()) if c != (0, 0)]
+    rounds, evals, pt = orc.sumcheck_prove([(sel, True, k)] + mles, terms, k, 3, transcript=t)
+    return {"tower_proof": proof, "tower_point": point, "main_proof": rounds, "main_evals": evals, "main_point": pt}
+
+
+def test_chip_proof_flow_on_lanes_bit_exact(dev):
+    """Six synthetic chips proved through ChipScheduler lanes (records -> towers -> tower proof -> main zerocheck ->
+    commitment): lane execution equals sequential execution, and the small chips equal the CPU oracle composition."""
+    import ceno_b200 as cb
+    from ceno_b200 import api, chip as chipmod
+    prm = orc.p2_params(seed=3)
+    api.poseidon2_set_params(dev, [[int(prm.ext_rc[r][i]) for i in range(8)] for r in range(8)], [int(x) for x in prm.int_rc],
+                             [int(x) for x in prm.diag], 0)
+    chips = [chipmod.SyntheticChip(s, k, ni, n_wit=8) for s, (k, ni) in enumerate([(9, 500), (7, 128), (12, 4000), (8, 200), (11, 2048), (6, 33)])]
+    wits = [chipmod.upload_witness(dev, c) for c in chips]
+    tasks = [cb.ChipTask(i, c.estimated_memory_bytes(), payload=i, circuit_name=c.name) for i, c in enumerate(chips)]
+
+    def prove(task, lane, stream):
+        i = task.payload
+        return chipmod.create_chip_proof(dev, chips[i], wits[i][1], cb.StandInTranscript(chips[i].name.encode()), stream=stream, commit_matrix=wits[i][0])
+
+    seq, _ = cb.ChipScheduler(dev).execute(tasks, prove, lanes=1)
+    par, tel = cb.ChipScheduler(dev).execute(tasks, prove, lanes=4)
+    assert len({t["lane_id"] for t in tel}) > 1
+    for a, b in zip(seq, par):
+        assert a.keys() == b.keys()
+        for key in a:
+            assert eq_np(a[key], b[key]), key
+    for i in (1, 3, 5):                                   # small chips against the oracle composition
+        want = _chip_oracle(chips[i])
+        for key, w in want.items():
+            assert eq_np(par[i][key], w), (i, key)
+    for buf, _ in wits:
+        buf.free()
