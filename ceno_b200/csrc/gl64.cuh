@@ -236,6 +236,38 @@ GL_DEV void cacc_add(cacc_t& C, const acc_t& A) {
 }
 GL_DEV uint64_t cacc_weak(const cacc_t& C) { return gl_reduce_limbs(C.l0, C.l1, C.l2, C.l3, C.l4); }
 
+// 96-bit lazy SUM of u64 values (linear layers without products: Poseidon2's MDS / internal sums): 3 carry adds per
+// term, one reduction per linear combination.  Up to 2^32 terms.
+struct wsum_t {
+    uint32_t l0, l1, l2;
+};
+GL_DEV void wsum_set(wsum_t& W, uint64_t x) { W.l0 = (uint32_t)x; W.l1 = (uint32_t)(x >> 32); W.l2 = 0; }
+GL_DEV void wsum_add(wsum_t& W, uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %0, %3;\n\t"
+        "addc.cc.u32 %1, %1, %4;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(W.l0), "+r"(W.l1), "+r"(W.l2) : "r"((uint32_t)x), "r"((uint32_t)(x >> 32)));
+#else
+    uint64_t t = (uint64_t)W.l0 + (uint32_t)x; W.l0 = (uint32_t)t;
+    t = (uint64_t)W.l1 + (uint32_t)(x >> 32) + (t >> 32); W.l1 = (uint32_t)t;
+    W.l2 += (uint32_t)(t >> 32);
+#endif
+}
+GL_DEV void wsum_addw(wsum_t& W, const wsum_t& V) {
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %0, %3;\n\t"
+        "addc.cc.u32 %1, %1, %4;\n\t"
+        "addc.u32 %2, %2, %5;"
+        : "+r"(W.l0), "+r"(W.l1), "+r"(W.l2) : "r"(V.l0), "r"(V.l1), "r"(V.l2));
+#else
+    uint64_t t = (uint64_t)W.l0 + V.l0; W.l0 = (uint32_t)t;
+    t = (uint64_t)W.l1 + V.l1 + (t >> 32); W.l1 = (uint32_t)t;
+    W.l2 += V.l2 + (uint32_t)(t >> 32);
+#endif
+}
+GL_DEV uint64_t wsum_weak(const wsum_t& W) { return gl_reduce_limbs(W.l0, W.l1, W.l2, 0, 0); }
+
 // any u64 -> canonical:  x >= p  <=>  hi == 0xFFFFFFFF and lo != 0, and then x - p = lo - 1
 GL_HD uint64_t gl_canon(uint64_t x) {
     const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);

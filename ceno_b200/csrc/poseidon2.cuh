@@ -27,63 +27,99 @@ struct P2Params {
     uint32_t pad;
 };
 
+// Values between the steps are "weak" (any u64 congruent to the field element): multiplicands and summands need no
+// canonical form; the permutation canonicalises its 8 outputs once at the end.
 GL_DEV uint64_t p2_sbox(uint64_t x) {
     const uint64_t x2 = gl_mul_weak(x, x), x3 = gl_mul_weak(x2, x), x4 = gl_mul_weak(x2, x2);
-    return gl_mul(x4, x3);
+    return gl_mul_weak(x4, x3);
 }
-GL_DEV void p2_m4(uint64_t* x, uint32_t variant) {
-    const uint32_t M0[4][4] = {{2, 3, 1, 1}, {1, 2, 3, 1}, {1, 1, 2, 3}, {3, 1, 1, 2}};
-    const uint32_t M1[4][4] = {{5, 7, 1, 3}, {4, 6, 1, 1}, {1, 3, 5, 7}, {1, 1, 4, 6}};
-    uint64_t o[4];
+// one 4-chunk of the external layer as unreduced 96-bit sums
+//   variant 0, circ(2,3,1,1):  o_i = S + x_i + 2 x_{i+1},  S = x0+x1+x2+x3           (additions only)
+//   variant 1, Horizen-Labs M4 [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]]: small-constant multiples by repeated addition
+GL_DEV void p2_m4_wide(const uint64_t* x, uint32_t variant, wsum_t* o) {
+    if (variant == 0) {
+        wsum_t S;
+        wsum_set(S, x[0]); wsum_add(S, x[1]); wsum_add(S, x[2]); wsum_add(S, x[3]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            o[i] = S;
+            wsum_add(o[i], x[i]);
+            wsum_add(o[i], x[(i + 1) & 3]);
+            wsum_add(o[i], x[(i + 1) & 3]);
+        }
+    } else {
+        const uint32_t M1[4][4] = {{5, 7, 1, 3}, {4, 6, 1, 1}, {1, 3, 5, 7}, {1, 1, 4, 6}};
+        wsum_t m[4][3];   // x_j, 2 x_j, 4 x_j
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            wsum_set(m[j][0], x[j]);
+            m[j][1] = m[j][0]; wsum_addw(m[j][1], m[j][0]);
+            m[j][2] = m[j][1]; wsum_addw(m[j][2], m[j][1]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            wsum_set(o[i], 0);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int b = 0; b < 3; b++)
+                    if ((M1[i][j] >> b) & 1) wsum_addw(o[i], m[j][b]);
+        }
+    }
+}
+// external layer: M4 on each 4-chunk, then lane i of chunk c += o[0][i] + o[1][i]; `rc` (optional) = the NEXT round's
+// constants, added inside the same sums (one reduction per lane for linear layer + constant)
+GL_DEV void p2_external(uint64_t* s, uint32_t variant, const uint64_t* rc) {
+    wsum_t o0[4], o1[4];
+    p2_m4_wide(s, variant, o0);
+    p2_m4_wide(s + 4, variant, o1);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        acc_t A;
-        acc_zero(A);
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc_mac(A, variant ? M1[i][j] : M0[i][j], x[j]);
-        o[i] = acc_canon(A);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) x[i] = o[i];
-}
-GL_DEV void p2_external(uint64_t* s, uint32_t variant) {
-    p2_m4(s, variant);
-    p2_m4(s + 4, variant);
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint64_t t = gl_add(s[i], s[4 + i]);
-        s[i] = gl_add(s[i], t);
-        s[4 + i] = gl_add(s[4 + i], t);
+        wsum_t a = o0[i], b = o1[i];
+        wsum_addw(a, o0[i]); wsum_addw(a, o1[i]);     // 2 o0 + o1
+        wsum_addw(b, o1[i]); wsum_addw(b, o0[i]);     // o0 + 2 o1
+        if (rc) { wsum_add(a, rc[i]); wsum_add(b, rc[4 + i]); }
+        s[i] = wsum_weak(a);
+        s[4 + i] = wsum_weak(b);
     }
 }
-// state canonical in, canonical out
+// any u64 in, canonical out
 GL_DEV void p2_permute(const P2Params& p, uint64_t* s) {
-    p2_external(s, p.mds_variant);
+    p2_external(s, p.mds_variant, p.ext_rc[0]);
     for (int r = 0; r < 4; r++) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = p2_sbox(gl_add(s[i], p.ext_rc[r][i]));
-        p2_external(s, p.mds_variant);
+        for (int i = 0; i < 8; i++) s[i] = p2_sbox(s[i]);
+        p2_external(s, p.mds_variant, r < 3 ? p.ext_rc[r + 1] : nullptr);
     }
     for (int r = 0; r < 22; r++) {
-        s[0] = p2_sbox(gl_add(s[0], p.int_rc[r]));
-        acc_t S;
-        acc_zero(S);
+        wsum_t t;
+        wsum_set(t, s[0]);
+        wsum_add(t, p.int_rc[r]);
+        s[0] = p2_sbox(wsum_weak(t));
+        wsum_t S;
+        wsum_set(S, s[0]);
 #pragma unroll
-        for (int i = 0; i < 8; i++) acc_mac(S, 1ULL, s[i]);
-        const uint64_t sum = acc_canon(S);
+        for (int i = 1; i < 8; i++) wsum_add(S, s[i]);
+        const uint64_t sum = wsum_weak(S);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             acc_t A;
-            acc_set64(A, sum);
-            acc_mac(A, s[i], p.diag[i]);
-            s[i] = acc_canon(A);
+            acc_fma_first(A, sum, s[i], p.diag[i]);
+            s[i] = acc_weak(A);
         }
     }
     for (int r = 4; r < 8; r++) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = p2_sbox(gl_add(s[i], p.ext_rc[r][i]));
-        p2_external(s, p.mds_variant);
+        for (int i = 0; i < 8; i++) {
+            wsum_t t;
+            wsum_set(t, s[i]);
+            wsum_add(t, p.ext_rc[r][i]);
+            s[i] = p2_sbox(wsum_weak(t));
+        }
+        p2_external(s, p.mds_variant, nullptr);
     }
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = gl_canon(s[i]);
 }
 
 #if defined(__CUDACC__)
