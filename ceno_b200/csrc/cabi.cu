@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -33,7 +34,7 @@ struct cg_ctx {
     std::multimap<size_t, void*> free_blocks;
     std::unordered_map<void*, size_t> live;
     size_t used = 0, reserved = 0;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
     std::vector<std::pair<size_t, void*>> pinned_cache;   // reusable pinned staging buffers
     P2Params* d_p2 = nullptr;                             // Poseidon2 constants (caller-supplied, cg_poseidon2_set_params)
     std::vector<float> profile_ms;                        // per-round device time of the last CG_SC_PROFILE run
@@ -70,6 +71,45 @@ static inline unsigned grid_for(cg_ctx* c, uint64_t items, unsigned per_sm = 4) 
 
 CG_EXPORT const char* cg_version(void) { return "ceno_b200 0.1 (sm_100a)"; }
 
+// Per-context kernel preparation.  (1) Dynamic shared-memory opt-ins are function attributes, i.e. process-global state:
+// they are raised ONCE here to the device maximum instead of per launch (two lanes setting different sizes for the same
+// kernel would race).  (2) cudaFuncGetAttributes forces the load of the persistent kernels now: with lazy module loading
+// the first launch of a function can otherwise happen while another persistent kernel is resident and waiting for the host.
+template <typename K>
+static cudaError_t optin_smem(K kernel, size_t max_optin) {
+    cudaFuncAttributes at;
+    cudaError_t e = cudaFuncGetAttributes(&at, kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(max_optin - at.sharedSizeBytes));
+}
+template <typename K>
+static cudaError_t preload(K kernel) {
+    cudaFuncAttributes at;
+    return cudaFuncGetAttributes(&at, kernel);
+}
+static cudaError_t prepare_kernels(size_t max_optin) {
+    cudaError_t e;
+#define CG_PREP(call) if ((e = (call)) != cudaSuccess) return e
+    CG_PREP(optin_smem(tower_tail_kernel<true>, max_optin));
+    CG_PREP(optin_smem(tower_tail_kernel<false>, max_optin));
+    CG_PREP(optin_smem(eq_small_kernel, max_optin));
+    CG_PREP(optin_smem(veq_tma_kernel<false, false, 2>, max_optin));
+    CG_PREP(optin_smem(veq_tma_kernel<true, true, 2>, max_optin));
+    CG_PREP(optin_smem(veq_tma_kernel<true, false, 2>, max_optin));
+    CG_PREP(optin_smem(veq_tma_kernel<false, false, 3>, max_optin));
+    CG_PREP(optin_smem(veq_tma_kernel<true, true, 3>, max_optin));
+    CG_PREP(optin_smem(veq_tma_kernel<true, false, 3>, max_optin));
+    CG_PREP(preload(tower_mid_kernel<true>));
+    CG_PREP(preload(tower_mid_kernel<false>));
+    CG_PREP(preload(fold_kernel));
+    CG_PREP(preload(veq_materialise_kernel));
+    CG_PREP(preload(veq_tables_kernel));
+#undef CG_PREP
+    return cudaSuccess;
+}
+// ask for eager module loading when the CUDA runtime has not been initialised yet in this process (no effect otherwise)
+__attribute__((constructor)) static void cg_module_loading_eager() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
+
 CG_EXPORT int cg_init(int device_id, cg_ctx** out) {
     if (!out) return CG_ERR_INVALID;
     *out = nullptr;
@@ -85,6 +125,12 @@ CG_EXPORT int cg_init(int device_id, cg_ctx** out) {
     c->cc_minor = p.minor;
     c->max_smem_optin = p.sharedMemPerBlockOptin;
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return CG_ERR_CUDA;
+    }
+    if (prepare_kernels(c->max_smem_optin) != cudaSuccess) {
+        cudaGetLastError();
+        cudaStreamDestroy(c->own_stream);
         delete c;
         return CG_ERR_CUDA;
     }
@@ -149,7 +195,7 @@ CG_EXPORT int cg_destroy(cg_ctx* c) {
     return CG_OK;
 }
 CG_EXPORT const char* cg_last_error(cg_ctx* c) { return c ? c->err.c_str() : "null context"; }
-CG_EXPORT uint64_t cg_launch_count(cg_ctx* c) { return c ? c->launches : 0; }
+CG_EXPORT uint64_t cg_launch_count(cg_ctx* c) { return c ? c->launches.load() : 0ULL; }
 CG_EXPORT int cg_device_info(cg_ctx* c, int* sm, int* maj, int* min, size_t* fr, size_t* tot) {
     if (!c) return CG_ERR_INVALID;
     CU(c, cudaSetDevice(c->device));
@@ -296,7 +342,7 @@ static int upload_small(cg_ctx* c, const void* h, size_t bytes, void** d, cudaSt
 }
 static int eq_small(cg_ctx* c, const ext_t* d_point, uint32_t k, ext_t* d_out, cudaStream_t st) {
     const size_t smem = sizeof(ext_t) << k;
-    if (smem > 48 * 1024) CU(c, cudaFuncSetAttribute(eq_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // (dynamic shared-memory opt-in raised once per context in prepare_kernels)
     unsigned threads = k >= 10 ? 1024 : (k >= 5 ? (1u << k) : 32);
     eq_small_kernel<<<1, threads, smem, st>>>(d_point, k, d_out);
     LAUNCHED(c);
@@ -1064,14 +1110,6 @@ static int launch_veq(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro
     if (use_tma) {   // rows staged through shared memory by cp.async.bulk (default)
         // CG_VEQ_MINB = 2 | 3 resident blocks per SM (A/B switch; see VeqTmaCfg)
         static const int minb = []() { const char* e = getenv("CG_VEQ_MINB"); return e ? atoi(e) : CG_VEQ_MINB_DEFAULT; }();
-        static bool attr_done = false;
-        if (!attr_done) {
-#define CG_VEQ_ATTR(F, C, MB) CU(c, cudaFuncSetAttribute(veq_tma_kernel<F, C, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VeqTmaCfg<F, MB>::SMEM))
-            CG_VEQ_ATTR(false, false, 2); CG_VEQ_ATTR(true, true, 2); CG_VEQ_ATTR(true, false, 2);
-            CG_VEQ_ATTR(false, false, 3); CG_VEQ_ATTR(true, true, 3); CG_VEQ_ATTR(true, false, 3);
-#undef CG_VEQ_ATTR
-            attr_done = true;
-        }
         uint64_t tb = (uint64_t)c->sm_count * (minb == 3 ? 3 : 2);
         if (tb > a.n_rows) tb = a.n_rows;
 #define CG_VEQ_TMA_LAUNCH(MB)                                                                                                   \
@@ -1318,13 +1356,10 @@ static int launch_tail(cg_sumcheck* sc, uint64_t* d_tr_state, ext_t* d_msgs, ext
     }
     const size_t smem = (size_t)slot * a.n0 * sizeof(ext_t);
     const bool simple = a.t.n_prod == 1 && a.t.n_logup == 0 && a.t.alpha_one;
-    if (simple) {
-        if (smem > 32 * 1024) CU(c, cudaFuncSetAttribute(tower_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tower_tail_kernel<true><<<1, CG_TAIL_THREADS, smem, sc->stream>>>(a);
-    } else {
-        if (smem > 32 * 1024) CU(c, cudaFuncSetAttribute(tower_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tower_tail_kernel<false><<<1, CG_TAIL_THREADS, smem, sc->stream>>>(a);
-    }
+    // the dynamic shared-memory opt-in of both instantiations is raised once per context (prepare_kernels): a per-launch
+    // cudaFuncSetAttribute is process-global state and races between lanes
+    if (simple) tower_tail_kernel<true><<<1, CG_TAIL_THREADS, smem, sc->stream>>>(a);
+    else tower_tail_kernel<false><<<1, CG_TAIL_THREADS, smem, sc->stream>>>(a);
     LAUNCHED(c);
     CU(c, cudaGetLastError());
     return CG_OK;
