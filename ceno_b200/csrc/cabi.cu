@@ -10,6 +10,7 @@
 #include <cstring>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
@@ -1299,6 +1300,32 @@ CG_EXPORT int cg_sumcheck_peek(cg_sumcheck* sc, uint32_t i, const void** dptr, u
 static TailMailbox* sc_mailbox(cg_sumcheck* sc) {
     return (TailMailbox*)((char*)sc->h_pinned + ((sizeof(ext_t) * (CG_MAX_DEGREE + 4) + 63) & ~(size_t)63));
 }
+// host side of the mailbox protocol (see TailMailbox)
+static void mailbox_reset(TailMailbox* mb) {
+    for (int i = 0; i < 16; i++) mb->msg[i] = 0;
+    uint64_t z[16] = {0};
+    mb->seq_msg = ~0ULL ^ cg_mb_mix(z, 16);   // validates for no (round, word count): a stale buffer can never be accepted
+    mb->r[0] = mb->r[1] = 0;
+    mb->seq_r = 0;
+    mb->abort = 0;
+    __sync_synchronize();
+}
+// true when the message of sequence `seq` (n words) is complete; the words are copied to `out`
+static bool mailbox_take(TailMailbox* mb, uint32_t n, uint64_t seq, uint64_t* out) {
+    const uint64_t flag = mb->seq_msg;
+    uint64_t w[16];
+    const volatile uint64_t* m = mb->msg;
+    for (uint32_t i = 0; i < n; i++) w[i] = m[i];
+    if ((flag ^ cg_mb_mix(w, n)) != seq) return false;
+    for (uint32_t i = 0; i < n; i++) out[i] = w[i];
+    return true;
+}
+static void mailbox_reply(TailMailbox* mb, const uint64_t r[2], uint64_t seq) {
+    ((volatile uint64_t*)mb->r)[0] = r[0];
+    ((volatile uint64_t*)mb->r)[1] = r[1];
+    __sync_synchronize();
+    mb->seq_r = seq;
+}
 static bool tail_eligible(const cg_sumcheck* sc) {
     if (sc->veq.split) return false;
     if (!sc->tl.on || (sc->flags & (CG_SC_NO_FUSE | CG_SC_NO_TAIL)) || sc->round >= sc->num_vars) return false;
@@ -1488,8 +1515,7 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
             // kernel, both enqueued now); the transcript stays on the host and answers through the mailbox
             cg_ctx* c = sc->ctx;
             TailMailbox* mb = sc_mailbox(sc);
-            if (j == 0) { mb->seq_msg = 0; mb->seq_r = 0; mb->abort = 0; }
-            __sync_synchronize();
+            if (j == 0) mailbox_reset(mb);
             uint32_t upto = j;   // rounds [j, upto) are owned by enqueued kernels
             bool done = false;
             if (mid_eligible(sc)) CHK(launch_mid(sc, nullptr, &upto));
@@ -1501,31 +1527,27 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
             int rc = CG_OK;
             for (uint32_t jj = j; jj < upto && rc == CG_OK; jj++) {
                 uint64_t spins = 0;
-                while (mb->seq_msg != (uint64_t)jj + 1) {
+                uint64_t* m = h_rounds + (size_t)jj * sc->degree * 2;
+                while (!mailbox_take(mb, 2 * sc->degree, (uint64_t)jj + 1, m)) {
                     if ((++spins & 0xFFFFF) == 0) {
                         const cudaError_t q = cudaStreamQuery(sc->stream);
                         if (q == cudaErrorNotReady) continue;
                         // the stream has drained: the message must be there; re-read for a short grace period before giving up
                         bool seen = false;
-                        for (int grace = 0; grace < 2000000 && !seen; grace++) { __sync_synchronize(); seen = (mb->seq_msg == (uint64_t)jj + 1); }
+                        for (int grace = 0; grace < 2000000 && !seen; grace++) { __sync_synchronize(); seen = mailbox_take(mb, 2 * sc->degree, (uint64_t)jj + 1, m); }
                         if (seen) break;
                         rc = set_err(c, CG_ERR_CUDA, std::string("persistent kernel ended before posting its round message (round ") + std::to_string(jj) +
-                                                         " of " + std::to_string(sc->num_vars) + ", owned up to " + std::to_string(upto) + ", mailbox seq_msg=" +
-                                                         std::to_string((unsigned long long)mb->seq_msg) + " seq_r=" + std::to_string((unsigned long long)mb->seq_r) +
-                                                         " abort=" + std::to_string((int)mb->abort) + ", stream: " + cudaGetErrorString(q) + ")");
+                                                         " of " + std::to_string(sc->num_vars) + ", owned up to " + std::to_string(upto) + ", seq_r=" +
+                                                         std::to_string((unsigned long long)mb->seq_r) + " abort=" + std::to_string((int)mb->abort) +
+                                                         ", stream: " + cudaGetErrorString(q) + ")");
                         break;
                     }
                 }
                 if (rc != CG_OK) break;
-                __sync_synchronize();
-                uint64_t* m = h_rounds + (size_t)jj * sc->degree * 2;
-                for (uint32_t x = 0; x < 2 * sc->degree; x++) m[x] = mb->msg[x];
                 uint64_t r[2] = {0, 0};
                 cb(user, jj, m, sc->degree, r);
                 if (h_chal) { h_chal[2 * jj] = r[0]; h_chal[2 * jj + 1] = r[1]; }
-                mb->r[0] = r[0]; mb->r[1] = r[1];
-                __sync_synchronize();
-                mb->seq_r = (uint64_t)jj + 1;
+                mailbox_reply(mb, r, (uint64_t)jj + 1);
             }
             if (rc != CG_OK) { mb->abort = 1; __sync_synchronize(); }
             prof_mark(sc, j, 1);
@@ -1542,7 +1564,7 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
         {   // one launch; its last block posts the message into the host mailbox (no D2H copy + stream sync)
             cg_ctx* c = sc->ctx;
             TailMailbox* mb = sc_mailbox(sc);
-            if (j == 0) { mb->seq_msg = 0; mb->seq_r = 0; mb->abort = 0; __sync_synchronize(); }
+            if (j == 0) mailbox_reset(mb);
             RoundOut ro = make_ro(sc);
             ro.d_out = sc->d_msgs;
             ro.d_tr_state = nullptr;
@@ -1552,15 +1574,17 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
             CHK(sc_enqueue_round(sc, ro));
             prof_mark(sc, j, 1);
             uint64_t spins = 0;
-            while (mb->seq_msg != (uint64_t)j + 1) {
+            while (!mailbox_take(mb, 2 * sc->degree, (uint64_t)j + 1, msg)) {
                 if ((++spins & 0xFFFFF) == 0) {
                     cudaError_t q = cudaStreamQuery(sc->stream);
-                    if (q != cudaErrorNotReady && mb->seq_msg != (uint64_t)j + 1)
-                        return set_err(c, CG_ERR_CUDA, std::string("round kernel ended without posting its message: ") + cudaGetErrorString(q));
+                    if (q != cudaErrorNotReady) {
+                        bool seen = false;
+                        for (int grace = 0; grace < 2000000 && !seen; grace++) { __sync_synchronize(); seen = mailbox_take(mb, 2 * sc->degree, (uint64_t)j + 1, msg); }
+                        if (!seen) return set_err(c, CG_ERR_CUDA, std::string("round kernel ended without posting its message: ") + cudaGetErrorString(q));
+                        break;
+                    }
                 }
             }
-            __sync_synchronize();
-            for (uint32_t x = 0; x < 2 * sc->degree; x++) msg[x] = mb->msg[x];
         }
         uint64_t r[2] = {0, 0};
         cb(user, j, msg, sc->degree, r);
@@ -2130,12 +2154,17 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
     uint32_t rt_len = 1;
     tr->sample(tr->user, "product_sum", rt.data());
     uint64_t w = 0;
+    static const bool trace = getenv("CG_TOWER_TRACE") != nullptr;   // host-side time per phase, summed over the layers
+    double t_eq = 0, t_create = 0, t_run = 0, t_fin = 0;
+    auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     for (uint32_t round = 1; round <= tw->max_round; round++) {
         const uint32_t nv = rt_len;
         const uint64_t n = 1ULL << nv;
         void* d_eq = nullptr;
+        const double t0 = now();
         CHK(tmp_alloc(c, sizeof(ext_t) * n, &d_eq, tw->stream));
         int rc = cg_build_eq(c, rt.data(), nv, (uint64_t*)d_eq, 0, n, tw->stream);
+        const double t1 = now();
         // MLE list in the reference's lift order: eq, then live product specs, then live logup specs
         std::vector<cg_mle_desc> mles;
         mles.push_back(cg_mle_desc{d_eq, n, nv, 1});
@@ -2182,14 +2211,20 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
                                     (uint32_t)off.size() - 1, nv, 3, CG_SC_FORCE_GENERIC, tw->stream, &sc);
         }
         std::vector<uint64_t> fin(2 * mles.size()), chal(2 * (size_t)nv);
+        const double t2 = now();
         if (rc == CG_OK) {
             if (fits) sc->tl = tl;
             tr->sumcheck_begin(tr->user, nv, 3);
             rc = sc_run_host(sc, tr->round_challenge, tr->user, h_proof + w, fin.data(), chal.data());
         }
+        const double t3 = now();
         if (sc) cg_sumcheck_destroy(sc);
         tmp_free(d_eq, tw->stream);
         if (rc != CG_OK) return rc;
+        if (trace) {
+            t_eq += t1 - t0; t_create += t2 - t1; t_run += t3 - t2; t_fin += now() - t3;
+            fprintf(stderr, "[tower] layer %2u nv=%2u eq %.0f create %.0f run %.0f destroy %.0f us\n", round, nv, t1 - t0, t2 - t1, t3 - t2, now() - t3);
+        }
         w += (uint64_t)nv * 3 * 2;
         for (int pass = 0; pass < 2; pass++)
             for (size_t si = 0; si < tw->specs.size(); si++) {
@@ -2209,6 +2244,7 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
         alpha_pows(tr, n_alpha, alpha);
     }
     memcpy(h_point, rt.data(), sizeof(uint64_t) * 2 * rt_len);
+    if (trace) fprintf(stderr, "[tower] total: eq %.0f create %.0f run %.0f destroy %.0f us\n", t_eq, t_create, t_run, t_fin);
     return CG_OK;
 }
 

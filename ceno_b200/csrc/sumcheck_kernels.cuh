@@ -139,14 +139,42 @@ __global__ void comm_allgather_kernel(const ext_t* __restrict__ d_final, int m, 
 }
 
 // Host mailbox in mapped pinned memory: the device posts a round message, the host answers with the
-// challenge (tail kernel) or simply launches the next round (per-round kernels) — no D2H copy + stream sync.
-struct TailMailbox {
-    volatile uint64_t seq_msg;  // device -> host: round index + 1 when msg[] is valid
-    uint64_t msg[2 * 8];
-    volatile uint64_t seq_r;    // host -> device: round index + 1 when r[] is valid
-    uint64_t r[2];
-    volatile uint64_t abort;    // host -> device: give up (callback failed)
+// challenge (tail / mid kernels) or simply launches the next round (per-round kernels) — no D2H copy + stream sync.
+// Latency protocol (one PCIe round trip per round, no system fences on the critical path):
+//   device -> host: the message words, then flag = (round + 1) ^ mix(words).  The host accepts the message when the flag
+//                   matches the words it read, so payload and flag need no ordering fence between them;
+//   host -> device: {r0, r1, seq_r, abort} is ONE 32-byte line the device polls with a single 256-bit load: when seq_r
+//                   matches, the challenge arrived in the same load (the host writes r before seq_r, x86 store order).
+struct __align__(64) TailMailbox {
+    uint64_t msg[2 * 8];        // device -> host
+    volatile uint64_t seq_msg;  // (round index + 1) ^ cg_mb_mix(msg words)
+    uint64_t pad0[7];
+    uint64_t r[2];              // host -> device: the reply line (32-byte aligned)
+    volatile uint64_t seq_r;    // round index + 1 when r[] is valid
+    volatile uint64_t abort;    // give up (callback failed)
 };
+GL_HD uint64_t cg_mb_mix(const uint64_t* m, uint32_t n) {
+    uint64_t h = 0x9E3779B97F4A7C15ULL;
+    for (uint32_t i = 0; i < n; i++) { h = (h ^ m[i]) * 0xBF58476D1CE4E5B9ULL; h ^= h >> 31; }
+    return h;
+}
+template <int D>
+GL_DEV void mailbox_post(TailMailbox* mb, const ext_t (&res)[D], uint64_t seq) {
+    uint64_t w[2 * D];
+#pragma unroll
+    for (int x = 0; x < D; x++) { w[2 * x] = res[x].c0; w[2 * x + 1] = res[x].c1; }
+    volatile uint64_t* m = mb->msg;
+#pragma unroll
+    for (int x = 0; x < 2 * D; x++) m[x] = w[x];
+    mb->seq_msg = seq ^ cg_mb_mix(w, 2 * D);
+}
+// 1: challenge ready (r set, canonical), -1: host asked to abort, 0: not yet
+GL_DEV int mailbox_poll(const TailMailbox* mb, uint64_t seq, ext_t& r) {
+    unsigned long long r0, r1, sq, ab;
+    asm volatile("ld.volatile.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r0), "=l"(r1), "=l"(sq), "=l"(ab) : "l"(mb->r) : "memory");
+    if (sq == seq) { r.c0 = gl_canon(r0); r.c1 = gl_canon(r1); return 1; }
+    return ab ? -1 : 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // round output / finish
@@ -220,12 +248,7 @@ GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out, const XF xf = XF(
         if (lane == 0) {
 #pragma unroll
             for (int x = 0; x < D; x++) out.d_out[x] = res[x];
-            if (out.mail) {
-#pragma unroll
-                for (int x = 0; x < D; x++) { out.mail->msg[2 * x] = res[x].c0; out.mail->msg[2 * x + 1] = res[x].c1; }
-                __threadfence_system();
-                out.mail->seq_msg = out.mail_seq;
-            }
+            if (out.mail) mailbox_post<D>(out.mail, res, out.mail_seq);
             if (out.d_tr_state) {   // stand-in challenger: absorb evals, label "Internal round", squeeze
                 uint64_t h = *out.d_tr_state;
 #pragma unroll
@@ -812,21 +835,13 @@ __global__ void __launch_bounds__(CG_TAIL_THREADS, 1) tower_tail_kernel(const __
                     *a.d_tr_state = h;
                 } else {
                     TailMailbox* mb = a.mail;
-#pragma unroll
-                    for (int x = 0; x < 3; x++) { mb->msg[2 * x] = res[x].c0; mb->msg[2 * x + 1] = res[x].c1; }
-                    __threadfence_system();
-                    mb->seq_msg = (uint64_t)j + 1;
-                    __threadfence_system();
+                    mailbox_post<3>(mb, res, (uint64_t)j + 1);
                     const long long t0 = clock64();
                     r = ext_zero();
                     while (true) {
-                        if (mb->seq_r == (uint64_t)j + 1) {
-                            __threadfence_system();
-                            r.c0 = gl_canon(((volatile uint64_t*)mb->r)[0]);
-                            r.c1 = gl_canon(((volatile uint64_t*)mb->r)[1]);
-                            break;
-                        }
-                        if (mb->abort || (unsigned long long)(clock64() - t0) > a.timeout_cycles) { s_abort = 1; *a.d_error = 1; break; }
+                        const int st = mailbox_poll(mb, (uint64_t)j + 1, r);
+                        if (st == 1) break;
+                        if (st < 0 || (unsigned long long)(clock64() - t0) > a.timeout_cycles) { s_abort = 1; *a.d_error = 1; break; }
                     }
                 }
                 a.d_chal[j] = r;
@@ -1028,20 +1043,12 @@ __global__ void __launch_bounds__(CG_THREADS, 2) tower_mid_kernel(const __grid_c
                         *a.d_tr_state = h;
                     } else {
                         TailMailbox* mb = a.mail;
-#pragma unroll
-                        for (int x = 0; x < 3; x++) { mb->msg[2 * x] = res[x].c0; mb->msg[2 * x + 1] = res[x].c1; }
-                        __threadfence_system();
-                        mb->seq_msg = (uint64_t)j + 1;
-                        __threadfence_system();
+                        mailbox_post<3>(mb, res, (uint64_t)j + 1);
                         const long long t0 = clock64();
                         while (true) {
-                            if (mb->seq_r == (uint64_t)j + 1) {
-                                __threadfence_system();
-                                rn.c0 = gl_canon(((volatile uint64_t*)mb->r)[0]);
-                                rn.c1 = gl_canon(((volatile uint64_t*)mb->r)[1]);
-                                break;
-                            }
-                            if (mb->abort || (unsigned long long)(clock64() - t0) > a.timeout_cycles) { abort = true; *a.d_error = 1; break; }
+                            const int st = mailbox_poll(mb, (uint64_t)j + 1, rn);
+                            if (st == 1) break;
+                            if (st < 0 || (unsigned long long)(clock64() - t0) > a.timeout_cycles) { abort = true; *a.d_error = 1; break; }
                         }
                     }
                     a.d_chal[j] = rn;
