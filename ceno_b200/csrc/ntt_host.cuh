@@ -25,6 +25,22 @@ static int ntt_tables(cg_ctx* c, cudaStream_t st) {
     return CG_OK;
 }
 
+// the instantiated digit geometries: last digit (C = 0, T = 1..12) and leading digits (T = 1..9, C = 12 - T)
+template <int T, int C>
+static void ntt_launch_tc(const NttPassArgs& a, unsigned tiles, cudaStream_t st) {
+    if (a.inverse) ntt_pass_kernel<T, C, false><<<tiles, 256, 0, st>>>(a);
+    else ntt_pass_kernel<T, C, true><<<tiles, 256, 0, st>>>(a);
+}
+static bool ntt_launch(const NttPassArgs& a, unsigned tiles, cudaStream_t st) {
+#define CG_NTT_CASE(T_, C_) if (a.T == T_ && a.C == C_) { ntt_launch_tc<T_, C_>(a, tiles, st); return true; }
+    CG_NTT_CASE(1, 0) CG_NTT_CASE(2, 0) CG_NTT_CASE(3, 0) CG_NTT_CASE(4, 0) CG_NTT_CASE(5, 0) CG_NTT_CASE(6, 0)
+    CG_NTT_CASE(7, 0) CG_NTT_CASE(8, 0) CG_NTT_CASE(9, 0) CG_NTT_CASE(10, 0) CG_NTT_CASE(11, 0) CG_NTT_CASE(12, 0)
+    CG_NTT_CASE(1, 11) CG_NTT_CASE(2, 10) CG_NTT_CASE(3, 9) CG_NTT_CASE(4, 8) CG_NTT_CASE(5, 7) CG_NTT_CASE(6, 6)
+    CG_NTT_CASE(7, 5) CG_NTT_CASE(8, 4) CG_NTT_CASE(9, 3)
+#undef CG_NTT_CASE
+    return false;
+}
+
 // digits of log_n, top digit first: the last (lowest) digit takes up to 12 bits, the rest is split evenly (<= 8 each)
 static int ntt_plan(uint32_t log_n, uint32_t digits[4]) {
     if (log_n <= CG_NTT_TILE_LOG) { digits[0] = log_n; return 1; }
@@ -67,7 +83,7 @@ static int ntt_run(cg_ctx* c, const uint64_t* in, uint64_t in_col_stride, uint64
         a.scale = (inverse && step == np - 1) ? 1 : 0;
         const uint64_t tiles = n_cols << (log_n - a.T - a.C);
         if (tiles > 0x7FFFFFFFULL) return set_err(c, CG_ERR_INVALID, "cg_ntt: too many tiles for one launch");
-        ntt_pass_kernel<<<(unsigned)tiles, 256, 0, st>>>(a);
+        if (!ntt_launch(a, (unsigned)tiles, st)) return set_err(c, CG_ERR_STATE, "cg_ntt: no kernel for this digit geometry");
         LAUNCHED(c);
     }
     CU(c, cudaGetLastError());

@@ -41,11 +41,18 @@ GL_DEV uint64_t ntt_tw(const NttPassArgs& a, uint32_t E) {   // w_{2^27}^E, E < 
     return gl_mul(__ldg(a.A + (E & ((1u << CG_NTT_A_BITS) - 1))), __ldg(a.B + (E >> CG_NTT_A_BITS)));
 }
 
+// Digit geometry (T, C) is a template parameter: every index computation is a shift by a constant and every loop has a
+// compile-time trip count (the run-time version spent most of its instructions on index arithmetic: 436 per element per pass).
+// FORWARD = decimation in frequency (natural in, bit-reversed out), else decimation in time (bit-reversed in, natural out).
+// When C == 0 the last two DIF stages (first two DIT stages) run in registers on 4 consecutive elements per thread
+// (two 128-bit shared-memory accesses, conflict-free) instead of two more shared-memory round trips.
+template <int T, int C, bool FORWARD>
 __global__ void __launch_bounds__(256) ntt_pass_kernel(const __grid_constant__ NttPassArgs a) {
-    __shared__ uint64_t tile[1 << CG_NTT_TILE_LOG];
-    __shared__ uint64_t tws[1 << (CG_NTT_TILE_LOG - 1)];
-    const uint32_t T = a.T, C = a.C, lo = a.lo;
-    const uint32_t E_t = 1u << (T + C), cmask = (1u << C) - 1;
+    constexpr uint32_t E_t = 1u << (T + C), cmask = (1u << C) - 1, NP = E_t >> 1;
+    constexpr int REG2 = (C == 0 && T >= 2) ? 2 : 0;       // stages handled in registers
+    __shared__ __align__(16) uint64_t tile[E_t];
+    __shared__ uint64_t tws[(1u << T) / 2];
+    const uint32_t lo = a.lo;
     const uint32_t tiles_per_col_log = a.log_n - T - C;
     const uint64_t tile_id = blockIdx.x;
     const uint64_t col = tile_id >> tiles_per_col_log;
@@ -55,64 +62,113 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(const __grid_constant__ N
     const uint64_t base = (outer << (lo + T)) | (ig << C);
     const uint32_t jr0 = (uint32_t)(ig << C);             // j_rest of column c = jr0 + c  (< 2^lo)
     const uint32_t sub_shift = CG_NTT_MAX_LOG - (lo + T);  // w_{2^(lo+T)}^e = w_{2^27}^(e << sub_shift)
-    const uint32_t emask = (1u << CG_NTT_MAX_LOG) - 1;
+    constexpr uint32_t emask = (1u << CG_NTT_MAX_LOG) - 1;
     // digit twiddles w_{2^T}^(+-i), i < 2^(T-1)
-    for (uint32_t i = threadIdx.x; i < (1u << T) / 2; i += blockDim.x) {
+    for (uint32_t i = threadIdx.x; i < (1u << T) / 2; i += 256) {
         uint32_t e = i << (CG_NTT_TILE_LOG - T);
-        if (a.inverse) e = (4096u - e) & 4095u;
+        if (!FORWARD) e = (4096u - e) & 4095u;
         tws[i] = __ldg(a.W12 + e);
     }
     const uint64_t* src = a.in + col * a.in_col_stride * a.estride;
-    for (uint32_t e = threadIdx.x; e < E_t; e += blockDim.x) {
-        const uint32_t t = e >> C, c = e & cmask;
-        const uint64_t idx = base + ((uint64_t)t << lo) + c;
-        uint64_t v = idx < a.in_len ? gl_canon(src[idx * a.estride]) : 0ULL;
-        if (a.inverse && lo) {
-            const uint32_t k = __brev(t) >> (32 - T);
-            const uint32_t ex = (uint32_t)(((uint64_t)k * (jr0 + c)) << sub_shift) & emask;
-            v = gl_mul(v, ntt_tw(a, ((1u << CG_NTT_MAX_LOG) - ex) & emask));
+#pragma unroll 4
+    for (uint32_t e0 = 0; e0 < E_t; e0 += 256) {
+        const uint32_t e = e0 + threadIdx.x;
+        if (E_t >= 256 || e < E_t) {
+            const uint32_t t = e >> C, c = e & cmask;
+            const uint64_t idx = base + ((uint64_t)t << lo) + c;
+            uint64_t v = idx < a.in_len ? gl_canon(src[idx * a.estride]) : 0ULL;
+            if (!FORWARD && lo) {
+                const uint32_t k = __brev(t) >> (32 - T);
+                const uint32_t ex = (uint32_t)(((uint64_t)k * (jr0 + c)) << sub_shift) & emask;
+                v = gl_mul(v, ntt_tw(a, ((1u << CG_NTT_MAX_LOG) - ex) & emask));
+            }
+            tile[e] = v;
         }
-        tile[e] = v;
     }
     __syncthreads();
-    const uint32_t npairs = E_t >> 1;
-    if (!a.inverse) {
-        for (int s = (int)T - 1; s >= 0; s--) {
-            for (uint32_t q = threadIdx.x; q < npairs; q += blockDim.x) {
-                const uint32_t c = q & cmask, pt = q >> C;
-                const uint32_t low = pt & ((1u << s) - 1), high = pt >> s;
-                const uint32_t i0 = ((((high << 1) << s) | low) << C) | c, i1 = i0 + (1u << (s + C));
-                const uint64_t x = tile[i0], y = tile[i1];
-                tile[i0] = gl_add(x, y);
-                tile[i1] = gl_mul(gl_sub(x, y), tws[low << (T - 1 - s)]);
+    if (FORWARD) {
+#pragma unroll
+        for (int s = T - 1; s >= REG2; s--) {
+#pragma unroll 2
+            for (uint32_t q0 = 0; q0 < NP; q0 += 256) {
+                const uint32_t q = q0 + threadIdx.x;
+                if (NP >= 256 || q < NP) {
+                    const uint32_t c = q & cmask, pt = q >> C;
+                    const uint32_t low = pt & ((1u << s) - 1), high = pt >> s;
+                    const uint32_t i0 = ((((high << 1) << s) | low) << C) | c, i1 = i0 + (1u << (s + C));
+                    const uint64_t x = tile[i0], y = tile[i1];
+                    tile[i0] = gl_add(x, y);
+                    tile[i1] = gl_mul(gl_sub(x, y), tws[low << (T - 1 - s)]);
+                }
+            }
+            __syncthreads();
+        }
+        if (REG2) {   // stages 1 and 0 on elements 4q .. 4q+3:  stage 1 pairs (0,2),(1,3) with w^(low << (T-2)), stage 0 pairs (0,1),(2,3)
+            const uint64_t w1 = tws[1u << (T - 2)];   // w_4^1 for T >= 2 (low = 1 at stage 1)
+#pragma unroll 2
+            for (uint32_t q0 = 0; q0 < E_t / 4; q0 += 256) {
+                const uint32_t q = q0 + threadIdx.x;
+                if (E_t / 4 >= 256 || q < E_t / 4) {
+                    ulonglong2* p = reinterpret_cast<ulonglong2*>(tile + 4 * q);
+                    const ulonglong2 u = p[0], v = p[1];
+                    const uint64_t a0 = gl_add(u.x, v.x), a2 = gl_sub(u.x, v.x);
+                    const uint64_t a1 = gl_add(u.y, v.y), a3 = gl_mul(gl_sub(u.y, v.y), w1);
+                    p[0] = make_ulonglong2(gl_add(a0, a1), gl_sub(a0, a1));
+                    p[1] = make_ulonglong2(gl_add(a2, a3), gl_sub(a2, a3));
+                }
             }
             __syncthreads();
         }
     } else {
-        for (uint32_t s = 0; s < T; s++) {
-            for (uint32_t q = threadIdx.x; q < npairs; q += blockDim.x) {
-                const uint32_t c = q & cmask, pt = q >> C;
-                const uint32_t low = pt & ((1u << s) - 1), high = pt >> s;
-                const uint32_t i0 = ((((high << 1) << s) | low) << C) | c, i1 = i0 + (1u << (s + C));
-                const uint64_t x = tile[i0], y = gl_mul(tile[i1], tws[low << (T - 1 - s)]);
-                tile[i0] = gl_add(x, y);
-                tile[i1] = gl_sub(x, y);
+        if (REG2) {   // DIT stages 0 and 1 on elements 4q .. 4q+3 with the inverse twiddles
+            const uint64_t w1 = tws[1u << (T - 2)];
+#pragma unroll 2
+            for (uint32_t q0 = 0; q0 < E_t / 4; q0 += 256) {
+                const uint32_t q = q0 + threadIdx.x;
+                if (E_t / 4 >= 256 || q < E_t / 4) {
+                    ulonglong2* p = reinterpret_cast<ulonglong2*>(tile + 4 * q);
+                    const ulonglong2 u = p[0], v = p[1];
+                    const uint64_t a0 = gl_add(u.x, u.y), a1 = gl_sub(u.x, u.y);
+                    const uint64_t a2 = gl_add(v.x, v.y), a3 = gl_mul(gl_sub(v.x, v.y), w1);
+                    p[0] = make_ulonglong2(gl_add(a0, a2), gl_add(a1, a3));
+                    p[1] = make_ulonglong2(gl_sub(a0, a2), gl_sub(a1, a3));
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int s = REG2; s < T; s++) {
+#pragma unroll 2
+            for (uint32_t q0 = 0; q0 < NP; q0 += 256) {
+                const uint32_t q = q0 + threadIdx.x;
+                if (NP >= 256 || q < NP) {
+                    const uint32_t c = q & cmask, pt = q >> C;
+                    const uint32_t low = pt & ((1u << s) - 1), high = pt >> s;
+                    const uint32_t i0 = ((((high << 1) << s) | low) << C) | c, i1 = i0 + (1u << (s + C));
+                    const uint64_t x = tile[i0], y = gl_mul(tile[i1], tws[low << (T - 1 - s)]);
+                    tile[i0] = gl_add(x, y);
+                    tile[i1] = gl_sub(x, y);
+                }
             }
             __syncthreads();
         }
     }
     uint64_t* dst = a.out + col * a.out_col_stride * a.estride;
-    for (uint32_t e = threadIdx.x; e < E_t; e += blockDim.x) {
-        const uint32_t t = e >> C, c = e & cmask;
-        const uint64_t idx = base + ((uint64_t)t << lo) + c;
-        uint64_t v = tile[e];
-        if (!a.inverse && lo) {
-            const uint32_t k = __brev(t) >> (32 - T);
-            const uint32_t ex = (uint32_t)(((uint64_t)k * (jr0 + c)) << sub_shift) & emask;
-            v = gl_mul(v, ntt_tw(a, ex));
+#pragma unroll 4
+    for (uint32_t e0 = 0; e0 < E_t; e0 += 256) {
+        const uint32_t e = e0 + threadIdx.x;
+        if (E_t >= 256 || e < E_t) {
+            const uint32_t t = e >> C, c = e & cmask;
+            const uint64_t idx = base + ((uint64_t)t << lo) + c;
+            uint64_t v = tile[e];
+            if (FORWARD && lo) {
+                const uint32_t k = __brev(t) >> (32 - T);
+                const uint32_t ex = (uint32_t)(((uint64_t)k * (jr0 + c)) << sub_shift) & emask;
+                v = gl_mul(v, ntt_tw(a, ex));
+            }
+            if (a.scale) v = gl_mul(v, a.n_inv);
+            dst[idx * a.estride] = v;
         }
-        if (a.scale) v = gl_mul(v, a.n_inv);
-        dst[idx * a.estride] = v;
     }
 }
 
