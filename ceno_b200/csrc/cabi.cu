@@ -195,7 +195,15 @@ CG_EXPORT int cg_destroy(cg_ctx* c) {
     delete c;
     return CG_OK;
 }
-CG_EXPORT const char* cg_last_error(cg_ctx* c) { return c ? c->err.c_str() : "null context"; }
+CG_EXPORT const char* cg_last_error(cg_ctx* c) {   // a per-thread copy: other lanes may set a new message concurrently
+    static thread_local std::string tl;
+    if (!c) return "null context";
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        tl = c->err;
+    }
+    return tl.c_str();
+}
 CG_EXPORT uint64_t cg_launch_count(cg_ctx* c) { return c ? c->launches.load() : 0ULL; }
 CG_EXPORT int cg_device_info(cg_ctx* c, int* sm, int* maj, int* min, size_t* fr, size_t* tot) {
     if (!c) return CG_ERR_INVALID;

@@ -965,3 +965,35 @@ def test_chip_proof_flow_on_lanes_bit_exact(dev):
             assert eq_np(par[i][key], w), (i, key)
     for buf, _ in wits:
         buf.free()
+
+
+def test_concurrent_towers_of_different_sizes_on_lanes(dev):
+    """Regression for a lane race: tower proofs whose persistent tail kernels need DIFFERENT amounts of dynamic shared
+    memory, proved concurrently on 8 lanes several times over, must equal the sequential proofs (the shared-memory opt-in
+    is process-global function state and is now raised once per context)."""
+    import ceno_b200 as cb
+    shapes = [([4], [3]), ([9, 9], [8]), ([6], []), ([11, 10], [10]), ([], [7]), ([12], [11]), ([8, 3], [5]), ([10], [9])]
+    towers = []
+    for i, (pn, ln) in enumerate(shapes):
+        specs, s = [], 5000 + 50 * i
+        for nv in pn:
+            specs.append(cb.TowerProverSpec([cb.MultilinearExtension.from_evaluations_ext_vec(dev, nv - 1, orc.fill_ext(s + z, 1 << (nv - 1))) for z in range(2)], nv, False))
+            s += 2
+        for nv in ln:
+            specs.append(cb.TowerProverSpec([None, None] + [cb.MultilinearExtension.from_evaluations_ext_vec(dev, nv, orc.fill_ext(s + z, 1 << nv)) for z in range(2)], nv, True))
+            s += 2
+        towers.append(specs)
+    tasks = [cb.ChipTask(i, 1 << 20, payload=i) for i in range(len(shapes))]
+
+    def prove(task, lane, stream):
+        tw = cb.TowerProver(dev, towers[task.payload], stream=stream)
+        out = tw.create_proof(cb.StandInTranscript(b"tw%d" % task.payload))
+        tw.close()
+        return out
+
+    want, _ = cb.ChipScheduler(dev).execute(tasks, prove, lanes=1)
+    for rep in range(4):
+        got, tel = cb.ChipScheduler(dev).execute(tasks, prove, lanes=8)
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert eq_np(g[0], w[0]) and eq_np(g[1], w[1]), (rep, i)
+    assert len({t["lane_id"] for t in tel}) > 1
