@@ -997,3 +997,68 @@ def test_concurrent_towers_of_different_sizes_on_lanes(dev):
         for i, (g, w) in enumerate(zip(got, want)):
             assert eq_np(g[0], w[0]) and eq_np(g[1], w[1]), (rep, i)
     assert len({t["lane_id"] for t in tel}) > 1
+
+
+# ------------------------------------------------------------------ gkr_iop layer / circuit API mirror (a5, a10)
+def test_gkr_circuit_two_layers_bit_exact(dev):
+    """GKRCircuit::prove (gkr_iop/src/gkr.rs:70-117) over a zerocheck layer with two selector groups (Prefix + Whole,
+    ZerocheckLayerProver::prove cpu/mod.rs:99-239) followed by a linear layer (cpu/mod.rs:44-67): the device mirror
+    against the same call / transcript order composed from the oracle's primitives."""
+    import ceno_b200 as cb
+    from ceno_b200 import gkr
+    from ceno_b200.expr import Poly
+    from oracle import pyref as pr
+    k, ninst = 8, 200
+    n = 1 << k
+    W = [orc.fill_base(7000 + i, n) for i in range(3)]
+    F0 = orc.fill_base(7010, n)
+    V = [orc.fill_ext(7020 + i, n) for i in range(2)]
+    w0, w1, w2, f0 = (Poly.var(i) for i in range(4))
+    exprs = [w0 * w1 + f0, w2 * w2 * w0, w1 - w2, w0 + w1 * 3]
+    groups = [gkr.OutGroup(cb.SelectorType.PREFIX, 0, [0, 1, 2]), gkr.OutGroup(cb.SelectorType.WHOLE, 1, [3])]
+    l0 = gkr.Layer("out", gkr.ZEROCHECK, 3, 1, 2, exprs, groups, in_eval_positions=[4, 5, 6, 7, 8, 9])
+    l1 = gkr.Layer("inner", gkr.LINEAR, 2, 0, 0, [], [gkr.OutGroup(None, 0, [4])], in_eval_positions=[10, 11])
+    circuit = gkr.GKRCircuit([l0, l1], 12, [10, 11, 7])
+    p0, p1 = rnd_point(71, k), rnd_point(72, k)
+    zero = np.zeros(2, np.uint64)
+    out_evals = [(p0, zero), (p0, zero), (p0, zero), (p1, zero)]
+    challenges = orc.fill_ext(7030, 2)
+    ctxs = [gkr.SelectorContext(0, ninst, k), gkr.SelectorContext(0, ninst, k)]
+    mk_b = lambda v: cb.MultilinearExtension.from_evaluations_vec(dev, k, v)
+    wit0 = [mk_b(v) for v in W] + [mk_b(F0), None, None]
+    wit1 = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, v) for v in V]
+    got = circuit.prove(dev, [wit0, wit1], out_evals, [], challenges, cb.StandInTranscript(b"gkr"), ctxs)
+
+    # ---- the same flow from the oracle's primitives
+    t = orc.Transcript(b"gkr")
+    a = t.sample(b"combine subset evals")
+    a, cur, al = (int(a[0]), int(a[1])), (1, 0), []
+    for _ in range(len(exprs)):
+        al.append(cur)
+        cur = ((cur[0] * a[0] + 7 * cur[1] * a[1]) % P, (cur[0] * a[1] + cur[1] * a[0]) % P)
+    sel0 = orc.selector_compute(1, p0, 0, ninst)
+    sel1 = orc.selector_compute(0, p1)
+    terms = l0.main_sumcheck_terms(np.array(al, dtype=np.uint64))
+    mles = [(v, False, k) for v in W] + [(F0, False, k), (sel0, True, k), (sel1, True, k)]
+    # the monomial table equals the layer polynomial sum_g sel_g * sum_j alpha_j expr_j at sampled points (direct evaluation)
+    mp = [[(int(x), 0) for x in v] for v in W + [F0]] + [[(int(x), int(y)) for x, y in s.reshape(-1, 2)] for s in (sel0, sel1)]
+    tl = [((int(c[0]), int(c[1])), ids) for c, ids in terms]
+    for x in (0, 1, 57, ninst - 1, ninst, n - 1):
+        v = [m[x][0] for m in mp[:4]]
+        ev = [(v[0] * v[1] + v[3]) % P, v[2] * v[2] * v[0] % P, (v[1] - v[2]) % P, (v[0] + 3 * v[1]) % P]
+        g0 = pr.ZERO
+        for j in range(3):
+            g0 = pr.eadd(g0, pr.emul(al[j], (ev[j], 0)))
+        want_x = pr.eadd(pr.emul(mp[4][x], g0), pr.emul(mp[5][x], pr.emul(al[3], (ev[3], 0))))
+        assert pr.poly_eval(mp, tl, x) == want_x
+    rounds, evals, point = orc.sumcheck_prove(mles, terms, k, 4, transcript=t)
+    t.append_ext(evals.reshape(-1))
+    lin = np.array([orc.mle_evaluate(v, True, point.reshape(-1)) for v in V], dtype=np.uint64)
+    t.append_ext(lin.reshape(-1))
+    assert eq_np(got["gkr_proof"][0].proof, rounds) and eq_np(got["gkr_proof"][0].evals, evals)
+    assert eq_np(got["rt"][0], point) and eq_np(got["rt"][1], point)          # the linear layer opens at the zerocheck's point
+    assert got["gkr_proof"][1].proof.size == 0 and eq_np(got["gkr_proof"][1].evals, lin)
+    vals = [o[0] for o in got["opening_evaluations"]]
+    assert eq_np(vals[0], lin[0]) and eq_np(vals[1], lin[1]) and eq_np(vals[2], evals[3])
+    for m in wit0[:4] + wit1:
+        m.free()
