@@ -138,6 +138,28 @@ class MultilinearExtension:
         assert evals.size % 2 == 0 and evals.size // 2 <= (1 << num_vars)
         return cls(dev, dev.to_device(evals), num_vars, True, evals.size // 2)
 
+    @classmethod
+    def from_evaluation_vec_smart(cls, dev, num_vars, evals, is_ext=False):
+        """MultilinearExtension::from_evaluation_vec_smart: base or ext evaluations, chosen by the element type."""
+        return cls.from_evaluations_ext_vec(dev, num_vars, evals) if is_ext else cls.from_evaluations_vec(dev, num_vars, evals)
+
+    def as_view_slice(self, num_chunks, chunk_index):
+        """Zero-copy view of chunk `chunk_index` of `num_chunks` equal contiguous chunks (as_view_slice; the device form is
+        owned_subrange, ceno_zkvm/src/scheme/gpu/mod.rs:2088-2113): log2(num_chunks) fewer variables, the TOP index bits fixed."""
+        assert num_chunks & (num_chunks - 1) == 0 and self.len == (1 << self.num_vars) and 0 <= chunk_index < num_chunks
+        sub = self.num_vars - (num_chunks.bit_length() - 1)
+        nbytes = (16 if self.is_ext else 8) << sub
+        view = DeviceBuffer(self.dev, self.buf.ptr + nbytes * chunk_index, nbytes, owner=False)
+        return MultilinearExtension(self.dev, view, sub, self.is_ext)
+
+    def get_base_field_vec(self):
+        assert not self.is_ext
+        return self.evaluations()
+
+    def get_ext_field_vec(self):
+        assert self.is_ext
+        return self.evaluations()
+
     def desc(self):
         return _lib.CgMleDesc(self.buf.ptr, self.len, self.num_vars, 1 if self.is_ext else 0)
 
@@ -677,9 +699,7 @@ class EccQuarkProver:
         sels = ecc_quark_selectors(dev, out_rt, num_instances)
         x0, x1 = split_even_odd(dev, xs)
         y0, y1 = split_even_odd(dev, ys)
-        half = 8 << n
-        view = lambda m: MultilinearExtension(dev, DeviceBuffer(dev, m.buf.ptr + half, half, owner=False), n, False)   # as_view_slice(2, 1)
-        x3, y3, s = [view(m) for m in xs], [view(m) for m in ys], [view(m) for m in invs]
+        x3, y3, s = ([m.as_view_slice(2, 1) for m in grp] for grp in (xs, ys, invs))   # x[1,b], y[1,b], s[1,b]
         last = (1 << n) - 2                                            # the final sum sits at [1,..,1,0]
         fx = [int(m.buf.to_host(8, 8 * last)[0]) for m in x3]
         fy = [int(m.buf.to_host(8, 8 * last)[0]) for m in y3]
