@@ -1,8 +1,12 @@
 // Integer-pipe microbenchmark for sm_100a: issue rate of the instructions the field kernels are made of.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipes pipes.cu && ./pipes
 // Each test runs ITER iterations of a body with CH independent dependency chains per thread (one block per SM) and
-// reports warp-instructions per cycle per SM sub-partition (SMSP) at 1, 2, 4, 8 warps per SMSP.  The SASS of every
-// body was checked with cuobjdump (loop = exactly the CH listed instructions + 3 loop-control instructions).
+// reports warp-instructions per cycle per SM sub-partition (SMSP) at 1, 2, 4, 8 warps per SMSP.
+// CAVEAT (read before quoting a number): ptxas rewrites these bodies — the IMAD.WIDE loop below compiles to 7 IMAD.WIDE +
+// 7 carry adds + 2 moves per iteration, not 8 bare IMAD.WIDE — so the printed rates are LOWER BOUNDS of the per-instruction
+// issue rate (measured on B200: IMAD.WIDE >= 0.175, IMAD / IADD3 / LOP3 ~ 0.5 per cycle per SMSP).  The figures DESIGN.md
+// relies on come from ncu's pipe counters on the real kernels instead (sm__pipe_fmaheavy_cycles_active: IMAD.WIDE occupies
+// the heavy FMA pipe for ~4 cycles per warp, the other IMAD forms for 2).
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
