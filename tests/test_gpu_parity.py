@@ -1062,3 +1062,42 @@ def test_gkr_circuit_two_layers_bit_exact(dev):
     assert eq_np(vals[0], lin[0]) and eq_np(vals[1], lin[1]) and eq_np(vals[2], evals[3])
     for m in wit0[:4] + wit1:
         m.free()
+
+
+# ------------------------------------------------------------------ randomized sweep over term tables / shapes / code paths
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_random_sumcheck_instances_bit_exact(dev, seed):
+    """Random monomial term tables (repeated factors, constants, lower-degree terms), base / ext / occupied-prefix MLEs,
+    1..11 variables, degree 1..5, every kernel family (grouped plan, term-by-term, unfused, tower-shaped when it applies,
+    host transcript or device challenger): bit-exact against the oracle."""
+    import ceno_b200 as cb
+    rng = random.Random(9000 + seed)
+    for _ in range(4):
+        k = rng.randint(1, 11)
+        n = 1 << k
+        degree = rng.randint(1, 5)
+        m = rng.randint(1, 6)
+        host, mles = [], []
+        for i in range(m):
+            is_ext = rng.random() < 0.5
+            ln = n if rng.random() < 0.7 else rng.randint(1, n)                    # occupied prefix (SURVEY §A9)
+            d = orc.fill_ext(rng.randrange(1 << 30), ln) if is_ext else orc.fill_base(rng.randrange(1 << 30), ln)
+            full = np.zeros((2 if is_ext else 1) * n, np.uint64)
+            full[:d.size] = d
+            host.append((full, is_ext, k))
+            mles.append((cb.MultilinearExtension.from_evaluations_ext_vec if is_ext else cb.MultilinearExtension.from_evaluations_vec)(dev, k, d))
+        terms = []
+        for _t in range(rng.randint(1, 9)):
+            nf = rng.randint(0 if len(terms) else 1, degree)
+            coeff = [rng.randrange(P), rng.choice([0, rng.randrange(P)])]
+            terms.append((coeff, [rng.randrange(m) for _ in range(nf)]))
+        label = b"rnd%d" % seed
+        want = orc.sumcheck_prove(host, terms, k, degree, transcript=orc.Transcript(label))
+        flags = rng.choice([0, 0, cb.IOPProverState.NO_PLAN, cb.IOPProverState.NO_FUSE, cb.IOPProverState.FORCE_GENERIC,
+                            cb.IOPProverState.NO_TAIL, cb.IOPProverState.NO_MID])
+        dc = rng.random() < 0.5
+        got = cb.IOPProverState.prove(dev, mles, terms, k, degree, transcript=cb.StandInTranscript(label), device_challenger=dc, flags=flags)
+        for g, w in zip(got, want):
+            assert eq_np(g, w), (seed, k, degree, m, terms, flags, dc)
+        for mm in mles:
+            mm.free()
