@@ -1316,6 +1316,8 @@ static void mailbox_reset(TailMailbox* mb) {
     mb->r[0] = mb->r[1] = 0;
     mb->seq_r = 0;
     mb->abort = 0;
+    mb->fin_flag = 0;   // a valid flag is (rounds + 1) ^ checksum: zero words + zero flag never validate for seq >= 1
+    for (int i = 0; i < 2 * CG_COMM_GATHER_SLOTS; i++) mb->fin[i] = 0;
     __sync_synchronize();
 }
 // true when the message of sequence `seq` (n words) is complete; the words are copied to `out`
@@ -1326,6 +1328,16 @@ static bool mailbox_take(TailMailbox* mb, uint32_t n, uint64_t seq, uint64_t* ou
     for (uint32_t i = 0; i < n; i++) w[i] = m[i];
     if ((flag ^ cg_mb_mix(w, n)) != seq) return false;
     for (uint32_t i = 0; i < n; i++) out[i] = w[i];
+    return true;
+}
+// final evaluations posted by the tail kernel (n ext in the caller's MLE order)
+static bool mailbox_take_final(TailMailbox* mb, uint32_t n, uint64_t seq, uint64_t* out) {
+    const uint64_t flag = mb->fin_flag;
+    uint64_t w[2 * CG_COMM_GATHER_SLOTS], h = 0;
+    const volatile uint64_t* f = mb->fin;
+    for (uint32_t i = 0; i < 2 * n; i++) { w[i] = f[i]; h ^= cg_mb_word(w[i], i); }
+    if ((flag ^ h) != seq) return false;
+    if (out) for (uint32_t i = 0; i < 2 * n; i++) out[i] = w[i];
     return true;
 }
 static void mailbox_reply(TailMailbox* mb, const uint64_t r[2], uint64_t seq) {
@@ -1513,6 +1525,7 @@ CG_EXPORT int cg_profile_last(cg_ctx* c, float* ms_out, uint32_t cap, uint32_t* 
 }
 
 static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t* h_rounds, uint64_t* h_final, uint64_t* h_chal) {
+    bool have_final = false;
     prof_begin(sc);
     for (uint32_t j = 0; j < sc->num_vars; j++) {
         uint64_t* msg = h_rounds + (size_t)j * sc->degree * 2;
@@ -1560,6 +1573,26 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
             if (rc != CG_OK) { mb->abort = 1; __sync_synchronize(); }
             prof_mark(sc, j, 1);
             for (uint32_t jj = j + 1; jj < sc->num_vars && jj < upto; jj++) { prof_mark(sc, jj, 0); prof_mark(sc, jj, 1); }
+            if (done && rc == CG_OK && sc->n_mles <= CG_COMM_GATHER_SLOTS && !(sc->flags & CG_SC_PROFILE)) {
+                // the tail kernel posts the final evaluations into the mailbox: no stream synchronisation, no D2H copy
+                // (the sumcheck's buffers are released in stream order, so the kernel may still be exiting)
+                uint64_t fin_tmp[2 * CG_COMM_GATHER_SLOTS];
+                uint64_t spins = 0;
+                bool got = false;
+                const uint64_t fseq = (uint64_t)sc->num_vars + sc->extra_rounds + 1;
+                while (!(got = mailbox_take_final(mb, sc->n_mles, fseq, fin_tmp))) {
+                    if ((++spins & 0xFFFFF) == 0 && cudaStreamQuery(sc->stream) != cudaErrorNotReady) {
+                        for (int grace = 0; grace < 2000000 && !got; grace++) { __sync_synchronize(); got = mailbox_take_final(mb, sc->n_mles, fseq, fin_tmp); }
+                        break;
+                    }
+                }
+                if (got) {
+                    if (h_final) memcpy(h_final, fin_tmp, sizeof(ext_t) * sc->n_mles);
+                    sc_mark_done(sc);
+                    have_final = true;
+                    break;
+                }
+            }
             if (done || rc != CG_OK) {
                 CU(c, cudaStreamSynchronize(sc->stream));
                 CHK(rc);
@@ -1600,7 +1633,7 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
         CHK(cg_sumcheck_bind(sc, r));
     }
     prof_end(sc);
-    if (h_final) CHK(cg_sumcheck_final_evals(sc, h_final));
+    if (h_final && !have_final) CHK(cg_sumcheck_final_evals(sc, h_final));
     return CG_OK;
 }
 

@@ -152,7 +152,15 @@ struct __align__(64) TailMailbox {
     uint64_t r[2];              // host -> device: the reply line (32-byte aligned)
     volatile uint64_t seq_r;    // round index + 1 when r[] is valid
     volatile uint64_t abort;    // give up (callback failed)
+    // device -> host, once, after the last round: the final evaluations in the caller's MLE order, validated by
+    // fin_flag = seq ^ (order-independent checksum) — the host needs neither a D2H copy nor a stream synchronisation
+    uint64_t fin[2 * 33];       // CG_COMM_GATHER_SLOTS ext
+    volatile uint64_t fin_flag;
 };
+GL_HD uint64_t cg_mb_word(uint64_t v, uint32_t pos) {
+    uint64_t h = (v ^ (0x9E3779B97F4A7C15ULL * (pos + 1))) * 0xBF58476D1CE4E5B9ULL;
+    return h ^ (h >> 29);
+}
 GL_HD uint64_t cg_mb_mix(const uint64_t* m, uint32_t n) {
     uint64_t h = 0x9E3779B97F4A7C15ULL;
     for (uint32_t i = 0; i < n; i++) { h = (h ^ m[i]) * 0xBF58476D1CE4E5B9ULL; h ^= h >> 31; }
@@ -875,6 +883,18 @@ __global__ void __launch_bounds__(CG_TAIL_THREADS, 1) tower_tail_kernel(const __
         n = pairs;
     }
     for (int slot = tid; slot < n_slots; slot += blockDim.x) a.d_final[a.final_idx[slot]] = sm[(size_t)slot * a.n0];
+    if (a.mail && tid == 0) {   // host transcript: also post the final evaluations into the mapped mailbox
+        volatile uint64_t* f = a.mail->fin;
+        uint64_t h = 0;
+        for (int slot = 0; slot < n_slots; slot++) {
+            const ext_t v = sm[(size_t)slot * a.n0];
+            const uint32_t w = 2u * a.final_idx[slot];
+            f[w] = v.c0;
+            f[w + 1] = v.c1;
+            h ^= cg_mb_word(v.c0, w) ^ cg_mb_word(v.c1, w + 1);
+        }
+        a.mail->fin_flag = ((uint64_t)a.num_rounds + 1) ^ h;
+    }
 }
 // ---------------------------------------------------------------------------------------------
 // Generic monomial-term round evaluation: P = sum_t c_t prod_{i in S_t} f_i, base or ext MLEs
