@@ -1101,3 +1101,16 @@ def test_random_sumcheck_instances_bit_exact(dev, seed):
             assert eq_np(g, w), (seed, k, degree, m, terms, flags, dc)
         for mm in mles:
             mm.free()
+
+
+@pytest.mark.parametrize("seed", list(range(6)))
+def test_random_tower_shapes_bit_exact(dev, seed):
+    """Random tower shapes: 0..5 product specs and 0..3 logup specs of independent depths 1..11, numerators present or
+    implicit ones — output evaluations, proof and point against the oracle (CpuTowerProver::create_proof semantics)."""
+    rng = random.Random(4000 + seed)
+    while True:
+        prod = [rng.randint(1, 11) for _ in range(rng.randint(0, 5))]
+        lk = [rng.randint(1, 10) for _ in range(rng.randint(0, 3))]
+        if prod or lk:
+            break
+    _tower_case(dev, prod, lk, with_p=rng.random() < 0.5, seed=6000 + 100 * seed)
