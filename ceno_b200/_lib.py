@@ -61,7 +61,7 @@ SYMBOLS = [
     "cg_poseidon2_set_params", "cg_poseidon2_permute", "cg_merkle_commit",
     "cg_rotation_next_base_mle", "cg_rotation_selector",
     "cg_sched_execute", "cg_stream_create", "cg_stream_destroy", "cg_ntt", "cg_rs_encode",
-    "cg_ecc_quark_selectors", "cg_split_even_odd",
+    "cg_ecc_quark_selectors", "cg_split_even_odd", "cg_ecc_quark_terms",
 ]
 
 _lib = None
@@ -138,6 +138,7 @@ def load():
         "cg_rs_encode": (i32, [vp, vp, u64, u32, u32, vp, u32, vp]),
         "cg_ecc_quark_selectors": (i32, [vp, vp, u32, u64, vp, vp, vp, vp]),
         "cg_split_even_odd": (i32, [vp, P(CgMleDesc), u32, P(vp), P(vp), vp]),
+        "cg_ecc_quark_terms": (i32, [vp, vp, vp, vp, vp, vp, u32, u32, P(u32), P(u32)]),
         "cg_stream_create": (i32, [vp, P(vp)]),
         "cg_stream_destroy": (i32, [vp, vp]),
         "cg_sumcheck_prove_sharded": (i32, [vp, vp, P(CgMleDesc), u32, vp, vp, vp, u32, u32, u32, u32, CHALLENGE_CB, vp, vp, vp, vp, vp, vp]),

@@ -673,7 +673,25 @@ class EccQuarkProver:
     @staticmethod
     def build_terms(alpha_pows, final_sum_x, final_sum_y):
         """The zerocheck expression in monomial form over the MLE order
-        [sel_add, sel_bypass, sel_export, s(7), x0(7), y0(7), x1(7), y1(7), x3(7), y3(7)]  (:153-262)."""
+        [sel_add, sel_bypass, sel_export, s(7), x0(7), y0(7), x1(7), y1(7), x3(7), y3(7)]  (:153-262), expanded by the
+        library (cg_ecc_quark_terms, host-side C++)."""
+        lib = _lib.load()
+        al = _u64(np.asarray(alpha_pows, dtype=np.uint64).reshape(-1))
+        fx, fy = _u64(np.array([int(v) for v in final_sum_x], dtype=np.uint64)), _u64(np.array([int(v) for v in final_sum_y], dtype=np.uint64))
+        assert al.size == 2 * 49 and fx.size == 7 and fy.size == 7
+        nt, ni = C.c_uint32(), C.c_uint32()
+        rc = lib.cg_ecc_quark_terms(_vp(al), _vp(fx), _vp(fy), None, None, None, 0, 0, C.byref(nt), C.byref(ni))
+        if rc != _lib.CG_OK:
+            raise CenoB200Error(rc, "cg_ecc_quark_terms failed")
+        coeff, off, idx = np.zeros(2 * nt.value, np.uint64), np.zeros(nt.value + 1, np.uint32), np.zeros(max(ni.value, 1), np.uint32)
+        rc = lib.cg_ecc_quark_terms(_vp(al), _vp(fx), _vp(fy), _vp(coeff), _vp(off), _vp(idx), nt.value, ni.value, C.byref(nt), C.byref(ni))
+        if rc != _lib.CG_OK:
+            raise CenoB200Error(rc, "cg_ecc_quark_terms failed")
+        return [([int(coeff[2 * t]), int(coeff[2 * t + 1])], [int(i) for i in idx[off[t]:off[t + 1]]]) for t in range(nt.value)]
+
+    @staticmethod
+    def build_terms_symbolic(alpha_pows, final_sum_x, final_sum_y):
+        """The same table through the symbolic engine of expr.py (cross-check of the C++ expansion in the host tests)."""
         from .expr import Poly, SymbolicSepticExtension as Sep, ext
         D = SEPTIC_EXTENSION_DEGREE
         sel_add, sel_bypass, sel_export = Poly.var(0), Poly.var(1), Poly.var(2)

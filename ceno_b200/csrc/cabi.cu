@@ -2370,3 +2370,4 @@ CG_EXPORT int cg_rotation_selector(cg_ctx* c, const uint64_t* d_eq_ext, uint64_t
 
 #include "sched.cuh"
 #include "ntt_host.cuh"
+#include "ecc_host.cuh"

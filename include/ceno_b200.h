@@ -308,6 +308,13 @@ int cg_rotation_selector(cg_ctx* ctx, const uint64_t* d_eq_ext, uint64_t total_l
 int cg_ecc_quark_selectors(cg_ctx* ctx, const uint64_t* h_out_rt_ext, uint32_t num_vars, uint64_t num_instances,
                            uint64_t* d_sel_add_ext, uint64_t* d_sel_bypass_ext, uint64_t* d_sel_export_ext, cg_stream s);
 int cg_split_even_odd(cg_ctx* ctx, const cg_mle_desc* mles, uint32_t n_mles, uint64_t* const* d_even, uint64_t* const* d_odd, cg_stream s);
+/* Host-only: the monomial term table of the EC-sum Quark zerocheck (cpu/mod.rs:153-262: add / bypass / export constraint
+ * families under their selectors, septic products expanded by z^7 = 2z + 5) over the MLE order
+ * [sel_add, sel_bypass, sel_export, s(7), x0(7), y0(7), x1(7), y1(7), x3(7), y3(7)], in the layout cg_sumcheck_* take
+ * (coeff: 2 u64 per term, off: n_terms + 1 prefix offsets, idx: factor lists).  alpha_pows: 49 ext; final_x / final_y: the 7 + 7
+ * base limbs of the exported sum.  Call with NULL outputs to get the sizes (260 terms, 717 factors for generic alphas). */
+int cg_ecc_quark_terms(const uint64_t* alpha_pows_ext, const uint64_t* final_x, const uint64_t* final_y, uint64_t* coeff_out,
+                       uint32_t* off_out, uint32_t* idx_out, uint32_t cap_terms, uint32_t cap_idx, uint32_t* n_terms, uint32_t* n_idx);
 
 /* ---- kernel (iii-commit): Merkle commitment over Poseidon2-Goldilocks (TraceCommitter::commit_traces ->
  * PCS::batch_commit, ceno_zkvm/src/scheme/cpu/mod.rs:559-584; GPU basefold.batch_commit_*,

@@ -46,10 +46,16 @@ def test_ecc_quark_terms_match_the_oracle_expansion():
     rng = random.Random(11)
     alpha = np.array([[rng.randrange(P), rng.randrange(P)] for _ in range(49)], dtype=np.uint64)
     fx, fy = [rng.randrange(P) for _ in range(7)], [rng.randrange(P) for _ in range(7)]
-    got = sorted((tuple(c), tuple(i)) for c, i in api.EccQuarkProver.build_terms(alpha, fx, fy))
+    from ceno_b200 import build as cbuild
+    cbuild.build()
+    terms = api.EccQuarkProver.build_terms(alpha, fx, fy)                       # the library's C++ expansion (cg_ecc_quark_terms)
+    got = sorted((tuple(c), tuple(i)) for c, i in terms)
+    sym = sorted((tuple(c), tuple(i)) for c, i in api.EccQuarkProver.build_terms_symbolic(alpha, fx, fy))
     want = sorted((tuple(c), tuple(i)) for c, i in orc.ecc_quark_terms(alpha, fx, fy))
-    assert got == want and len(got) == 260
+    assert got == want == sym and len(got) == 260
     assert max(len(i) for _, i in got) == 3
+    assert [tuple(i) for _, i in terms] == sorted(tuple(i) for _, i in terms)     # deterministic (lexicographic) order
+    assert [(tuple(c), tuple(i)) for c, i in terms] == [(tuple(c), tuple(i)) for c, i in api.EccQuarkProver.build_terms_symbolic(alpha, fx, fy)]
 
 
 def test_zerocheck_layer_polynomial():
