@@ -105,3 +105,18 @@ def test_c_consumer_bit_exact_on_gpu(lib):
     exe = _build_c_smoke()
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "bit-exact" in r.stdout, r.stdout + r.stderr
+
+
+def test_integration_doc_binds_only_declared_symbols():
+    """Every `pub fn cg_*` of the Rust extern block in INTEGRATION.md and every cg_* call named in DESIGN.md is a symbol the
+    header declares (the documents cannot drift from the ABI)."""
+    import re
+    declared = set(header_symbols())
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    integ = open(os.path.join(root, "INTEGRATION.md")).read()
+    rust = set(re.findall(r"pub fn (cg_[a-z0-9_]+)", integ))
+    assert rust and rust <= declared, sorted(rust - declared)
+    design = open(os.path.join(root, "DESIGN.md")).read()
+    named = {n for n in re.findall(r"`(cg_[a-z0-9_]+)`", design) if not n.endswith("_")}
+    structs = {"cg_mle_desc", "cg_challenge_cb", "cg_transcript_vt", "cg_tower_spec", "cg_sched_task", "cg_sched_result", "cg_stream", "cg_ctx"}
+    assert named - structs <= declared, sorted(named - structs - declared)
