@@ -95,6 +95,13 @@ class ClockSampler:
                 "samples": len(sm), "sm_mhz_min": min(sm) if sm else None}
 
 
+def workload_config(k, n_gpus):
+    """`config` of the JSON line: identical in the GPU arm and the `--impl reference` arm (same workload, same sharding request)."""
+    return {"workload": f"T3-{k}: eq(w,x)*A(x)*B(x), 2^{k}-point hypercube, degree 3, GoldilocksExt2 (3 ext MLEs x {(16 << k) >> 20} MiB)",
+            "k": k, "degree": 3, "n_mles": 3, "n_gpus": n_gpus,
+            "l2": f"inputs {(3 * 16 << k) >> 20} MiB per job > L2 126 MB (no flush needed)"}
+
+
 # ----------------------------------------------------------------------------------- CPU arm
 def cpu_run(k, threads=None):
     """One T3-k step on the host cores with the oracle port: eq-build + sumcheck (rounds + folds)."""
@@ -105,8 +112,16 @@ def cpu_run(k, threads=None):
     eq = orc.build_eq_x_r_vec(w)
     t0 = time.perf_counter()
     # reference decomposition: per-thread chunks folded in place (inputs consumed), single-thread tail
-    orc.sumcheck_prove_chunked([(eq, True, k), (a, True, k), (b, True, k)], [([1, 0], [0, 1, 2])], k, 3, orc.Transcript(b"bench"), consume=True)
-    return time.perf_counter() - t0
+    proof = orc.sumcheck_prove_chunked([(eq, True, k), (a, True, k), (b, True, k)], [([1, 0], [0, 1, 2])], k, 3, orc.Transcript(b"bench"), consume=True)
+    return time.perf_counter() - t0, proof
+
+
+def assert_same_proof(got, want, what):
+    """Bit-exact comparison of (round_evals, final_evals, challenges) against the oracle's proof of the same instance."""
+    names = ("round polynomials", "final evaluations", "challenges")
+    for g, x, nm in zip(got, want, names):
+        if not np.array_equal(np.asarray(g, dtype=np.uint64).reshape(-1), np.asarray(x, dtype=np.uint64).reshape(-1)):
+            raise AssertionError(f"PARITY FAILURE ({what}): {nm} differ from the oracle")
 
 
 def reference_arm(args):
@@ -117,7 +132,7 @@ def reference_arm(args):
     k = args.cpu_k
     for _ in range(max(args.warmup, 1) if args.warmup else 0):
         cpu_run(min(k, 18))
-    ts = [cpu_run(k) for _ in range(args.steps)]
+    ts = [cpu_run(k)[0] for _ in range(args.steps)]
     t = float(np.mean(ts))
     val = OPS_PER_PAIR * (1 << k) / t / 1e9
     cores = orc.num_threads()
@@ -125,8 +140,8 @@ def reference_arm(args):
         "impl": "reference", "metric": "sumcheck Gfield-ops/s", "value": val, "unit": "Gfield-ops/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64 (Goldilocks, ext2)", "data": "synthetic",
-        "config": {"workload": f"T3-{args.k}: eq(w,x)*A(x)*B(x), degree 3, GoldilocksExt2; CPU arm times a bounded sample T3-{k}",
-                   "k": args.k, "degree": 3, "n_mles": 3},
+        "config": workload_config(args.k, args.gpus),
+        "config_detail": {"sample": f"CPU arm times T3-{k} per step", "parallelism": f"OpenMP {cores} threads on the host"},
         "points_per_s": (1 << k) / t, "rounds_per_s": k / t,
         "cpu_baseline": {"value": val, "unit": "Gfield-ops/s", "cores": cores, "kind": "port",
                          "sample": f"T3-{k} full sumcheck (2^{k} points, {k} rounds) per step; oracle port with the reference's decomposition, OpenMP {cores} threads; the reference is Rust (Rayon) and cannot be built here"},
@@ -277,7 +292,12 @@ def gpu_arm(args):
     # ---- CPU baseline on this box's host cores (bounded sample)
     from oracle import oracle as orc
     cpu_run(min(args.cpu_k, 16))
-    t_cpu = cpu_run(args.cpu_k)
+    t_cpu, cpu_proof = cpu_run(args.cpu_k)
+    parity_checked = None
+    if args.cpu_k == k:   # the oracle proved the very instance the GPU timed: compare every output bit for bit
+        for nm, o in (("host transcript", out), ("device challenger", out_dev), ("table eq", out_tab), ("e2e from host buffers", out_e2e)):
+            assert_same_proof(o, cpu_proof, f"T3-{k}, {nm}")
+        parity_checked = f"oracle k={k}: round polynomials, final evaluations and challenges bit-exact for the virtual-eq, table-eq, device-challenger and e2e runs"
     cpu_val = OPS_PER_PAIR * (1 << args.cpu_k) / t_cpu / 1e9
     cores = orc.num_threads()
 
@@ -287,11 +307,10 @@ def gpu_arm(args):
         "metric": "sumcheck Gfield-ops/s", "value": value, "unit": "Gfield-ops/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64 (Goldilocks, ext2)", "data": "synthetic",
-        "config": {"workload": f"T3-{k}: eq(w,x)*A(x)*B(x), 2^{k}-point hypercube, degree 3, GoldilocksExt2 (3 ext MLEs x {nbytes >> 20} MiB)",
-                   "k": k, "degree": deg, "n_mles": 3, "parallelism": "1 GPU",
-                   "eq": ("virtual: eq(w,.) passed as its point (CG_MLE_EQ), split-eq kernels" if virt else "table: resident 2^k ext table"),
-                   "l2": f"inputs {3 * nbytes >> 20} MiB > L2 126 MB (no flush needed)",
-                   "transcript": "stand-in sponge on the host behind cg_challenge_cb (reference flow); Poseidon2 constants are upstream-only"},
+        "config": workload_config(k, 1),
+        "config_detail": {"parallelism": "1 GPU",
+                          "eq": ("virtual: eq(w,.) passed as its point (CG_MLE_EQ), split-eq kernels" if virt else "table: resident 2^k ext table"),
+                          "transcript": "stand-in sponge on the host behind cg_challenge_cb (reference flow); Poseidon2 constants are upstream-only"},
         "points_per_s": n / (ms * 1e-3), "rounds_per_s": k / (ms * 1e-3),
         "device_challenger": {"ms_per_step": ms_dev, "value": ops / (ms_dev * 1e-3) / 1e9, "unit": "Gfield-ops/s",
                               "note": "same kernels, stand-in challenger on the device: no host round trip per round"},
@@ -305,6 +324,7 @@ def gpu_arm(args):
         "cpu_baseline": {"value": cpu_val, "unit": "Gfield-ops/s", "cores": cores, "kind": "port", "ms": t_cpu * 1e3,
                          "sample": f"T3-{args.cpu_k} full sumcheck ({'the whole workload' if args.cpu_k == k else f'1/{1 << (k - args.cpu_k)} of its points'}), one run; oracle port with the reference's decomposition (per-thread chunks folded in place, single-thread tail), OpenMP {cores} threads"},
         "clocks": clk,
+        "parity_checked": parity_checked,
     }
     print(json.dumps(line))
     dev.close()

@@ -49,7 +49,7 @@ class CgTranscriptVt(C.Structure):
 
 # every symbol include/ceno_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
-    "cg_init", "cg_destroy", "cg_last_error", "cg_version", "cg_device_info", "cg_alloc", "cg_free", "cg_pool_stats",
+    "cg_init", "cg_destroy", "cg_last_error", "cg_version", "cg_device_info", "cg_alloc", "cg_free", "cg_free_async", "cg_pool_stats",
     "cg_pool_trim", "cg_h2d", "cg_d2h", "cg_d2d", "cg_stream_sync", "cg_host_alloc_pinned", "cg_host_free_pinned",
     "cg_launch_count", "cg_build_eq", "cg_selector_compute", "cg_fix_variable", "cg_mle_evaluate", "cg_sumcheck_create",
     "cg_sumcheck_round_eval", "cg_sumcheck_bind", "cg_sumcheck_final_evals", "cg_sumcheck_round", "cg_sumcheck_peek",
@@ -86,6 +86,7 @@ def load():
         "cg_device_info": (i32, [vp, P(i32), P(i32), P(i32), P(sz), P(sz)]),
         "cg_alloc": (i32, [vp, sz, P(vp)]),
         "cg_free": (i32, [vp, vp]),
+        "cg_free_async": (i32, [vp, vp, vp]),
         "cg_pool_stats": (i32, [vp, P(sz), P(sz)]),
         "cg_pool_trim": (i32, [vp]),
         "cg_h2d": (i32, [vp, vp, vp, sz, vp]),

@@ -113,9 +113,14 @@ class DeviceBuffer:
         self.dev.sync()
         return out
 
-    def free(self):
+    def free(self, stream=None):
+        """Return the block to the pool.  Without `stream` the caller must have synchronised every stream that still uses
+        the buffer (cg_free); with `stream` the release is ordered behind the work enqueued on it (cg_free_async)."""
         if self.owner and self.ptr:
-            self.dev.lib.cg_free(self.dev.ctx, C.c_void_p(self.ptr))
+            if stream is not None:
+                self.dev.check(self.dev.lib.cg_free_async(self.dev.ctx, C.c_void_p(self.ptr), C.c_void_p(stream) if stream else None))
+            else:
+                self.dev.lib.cg_free(self.dev.ctx, C.c_void_p(self.ptr))
             self.ptr = 0
 
 
@@ -184,8 +189,8 @@ class MultilinearExtension:
         self.dev.sync()
         return MultilinearExtension(self.dev, out, self.num_vars - 1, True)
 
-    def free(self):
-        self.buf.free()
+    def free(self, stream=None):
+        self.buf.free(stream)
 
 
 class EqPolynomial:

@@ -33,6 +33,8 @@ struct cg_ctx {
     std::mutex mu;
     std::string err;
     std::multimap<size_t, void*> free_blocks;
+    struct PendingFree { void* p; size_t sz; cudaEvent_t ev; };
+    std::vector<PendingFree> pending_free;               // cg_free_async: blocks whose owning stream may still use them
     std::unordered_map<void*, size_t> live;
     size_t used = 0, reserved = 0;
     std::atomic<uint64_t> launches{0};
@@ -40,6 +42,8 @@ struct cg_ctx {
     P2Params* d_p2 = nullptr;                             // Poseidon2 constants (caller-supplied, cg_poseidon2_set_params)
     std::vector<float> profile_ms;                        // per-round device time of the last CG_SC_PROFILE run
     uint64_t* d_ntt_tab = nullptr;                        // NTT twiddle tables A | B | W12 (lazy, cg_ntt)
+    bool host_wait_ok = true;                             // false: kernel launches block the host (profiler / sanitizer) — no kernel may wait for the host
+    unsigned long long wait_timeout_cycles = 8000000000ULL;   // device-side limit of every wait on the host or a peer (CG_WAIT_TIMEOUT_MS)
 };
 
 static int set_err(cg_ctx* c, int code, const std::string& msg) {
@@ -111,6 +115,35 @@ static cudaError_t prepare_kernels(size_t max_optin) {
 // ask for eager module loading when the CUDA runtime has not been initialised yet in this process (no effect otherwise)
 __attribute__((constructor)) static void cg_module_loading_eager() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
 
+// Can a running kernel be answered by the host?  Under ncu / compute-sanitizer every launch blocks the calling thread until
+// the kernel has finished, so a persistent kernel that waits for the host transcript (tail / mid mailbox protocol) would
+// only ever see its own timeout.  cg_init finds out by experiment: a one-thread kernel waits (<= 50 ms) for a flag in mapped
+// pinned memory that the host sets right after the launch call returns.  When the flag never arrives in time the context
+// runs host-transcript sumchecks with one launch per round (CG_SC_NO_TAIL | CG_SC_NO_MID semantics); the device-challenger
+// path keeps its persistent kernels (they never wait for the host).  CG_NO_HOST_WAIT=1 forces that mode, =0 skips the probe.
+__global__ void host_wait_probe_kernel(const volatile unsigned* flag, unsigned* result, unsigned long long timeout_cycles) {
+    const long long t0 = clock64();
+    while (*flag == 0u) {
+        if ((unsigned long long)(clock64() - t0) > timeout_cycles) { *result = 2u; return; }
+    }
+    *result = 1u;
+}
+static bool probe_host_wait(cudaStream_t st) {
+    if (const char* e = getenv("CG_NO_HOST_WAIT")) return atoi(e) == 0;
+    if (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_SANITIZER_INJECTION_PORT_BASE")) return false;   // ncu / compute-sanitizer announce themselves
+    unsigned* h = nullptr;
+    if (cudaHostAlloc((void**)&h, 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); return true; }
+    h[0] = 0; h[8] = 0;
+    __sync_synchronize();
+    host_wait_probe_kernel<<<1, 1, 0, st>>>(h, h + 8, 100000000ULL);   // ~50 ms
+    ((volatile unsigned*)h)[0] = 1u;
+    __sync_synchronize();
+    const bool ok = cudaStreamSynchronize(st) == cudaSuccess && ((volatile unsigned*)h)[8] == 1u;
+    cudaGetLastError();
+    cudaFreeHost(h);
+    return ok;
+}
+
 CG_EXPORT int cg_init(int device_id, cg_ctx** out) {
     if (!out) return CG_ERR_INVALID;
     *out = nullptr;
@@ -134,6 +167,11 @@ CG_EXPORT int cg_init(int device_id, cg_ctx** out) {
         cudaStreamDestroy(c->own_stream);
         delete c;
         return CG_ERR_CUDA;
+    }
+    c->host_wait_ok = probe_host_wait(c->own_stream);
+    if (const char* e = getenv("CG_WAIT_TIMEOUT_MS")) {   // the device-side wait limit is configurable (default ~4 s)
+        const double ms = atof(e);
+        if (ms > 0) c->wait_timeout_cycles = (unsigned long long)(ms * 2.0e6);
     }
     // internal temporaries are stream-ordered (cudaMallocAsync); keep freed memory cached in the pool
     cudaMemPool_t mp;
@@ -174,10 +212,12 @@ static void pinned_put(cg_ctx* c, void* p, size_t bytes) {
     std::lock_guard<std::mutex> g(c->mu);
     c->pinned_cache.emplace_back(bytes < 4096 ? 4096 : bytes, p);
 }
+static void reap_pending_free(cg_ctx* c, bool wait);
 CG_EXPORT int cg_pool_trim(cg_ctx* c) {
     if (!c) return CG_ERR_INVALID;
     std::lock_guard<std::mutex> g(c->mu);
     cudaSetDevice(c->device);
+    reap_pending_free(c, true);
     for (auto& kv : c->free_blocks) { cudaFree(kv.second); c->reserved -= kv.first; }
     c->free_blocks.clear();
     return CG_OK;
@@ -223,12 +263,26 @@ static size_t round_size(size_t b) {
     const size_t g = b <= (1u << 16) ? 256 : (b <= (1u << 21) ? (1u << 16) : (1u << 21));
     return (b + g - 1) / g * g;
 }
+// blocks released by cg_free_async become reusable once their stream has passed the release point (caller holds c->mu)
+static void reap_pending_free(cg_ctx* c, bool wait) {
+    for (size_t i = 0; i < c->pending_free.size();) {
+        cg_ctx::PendingFree& pf = c->pending_free[i];
+        cudaError_t q = wait ? cudaEventSynchronize(pf.ev) : cudaEventQuery(pf.ev);
+        if (q == cudaErrorNotReady) { i++; continue; }
+        cudaGetLastError();
+        cudaEventDestroy(pf.ev);
+        c->free_blocks.emplace(pf.sz, pf.p);
+        c->pending_free[i] = c->pending_free.back();
+        c->pending_free.pop_back();
+    }
+}
 CG_EXPORT int cg_alloc(cg_ctx* c, size_t bytes, void** dptr) {
     if (!c || !dptr) return CG_ERR_INVALID;
     if (bytes == 0) bytes = 256;
     const size_t sz = round_size(bytes);
     {
         std::lock_guard<std::mutex> g(c->mu);
+        if (!c->pending_free.empty()) reap_pending_free(c, false);
         auto it = c->free_blocks.find(sz);
         if (it != c->free_blocks.end()) {
             *dptr = it->second;
@@ -261,6 +315,23 @@ CG_EXPORT int cg_free(cg_ctx* c, void* p) {
     auto it = c->live.find(p);
     if (it == c->live.end()) { c->err = "cg_free: pointer not owned by this context"; return CG_ERR_INVALID; }
     c->free_blocks.emplace(it->second, p);
+    c->used -= it->second;
+    c->live.erase(it);
+    return CG_OK;
+}
+// stream-ordered release: the block returns to the pool only after everything enqueued on `s` so far has finished, so a
+// lane may release a buffer its own (non-blocking) stream is still using without synchronising first
+CG_EXPORT int cg_free_async(cg_ctx* c, void* p, cg_stream s) {
+    if (!c) return CG_ERR_INVALID;
+    if (!p) return CG_OK;
+    CU(c, cudaSetDevice(c->device));
+    cudaEvent_t ev;
+    CU(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (cudaEventRecord(ev, S(c, s)) != cudaSuccess) { cudaEventDestroy(ev); return set_err(c, CG_ERR_CUDA, "cg_free_async: cudaEventRecord failed"); }
+    std::lock_guard<std::mutex> g(c->mu);
+    auto it = c->live.find(p);
+    if (it == c->live.end()) { cudaEventDestroy(ev); c->err = "cg_free_async: pointer not owned by this context"; return CG_ERR_INVALID; }
+    c->pending_free.push_back(cg_ctx::PendingFree{p, it->second, ev});
     c->used -= it->second;
     c->live.erase(it);
     return CG_OK;
@@ -390,6 +461,7 @@ CG_EXPORT int cg_build_eq(cg_ctx* c, const uint64_t* h_point, uint32_t k, uint64
     if (!c || !d_out || (k && !h_point) || k > 40) return set_err(c, CG_ERR_INVALID, "cg_build_eq: bad argument");
     const uint64_t n = 1ULL << k;
     if (offset > n || num_instances > n - offset) return set_err(c, CG_ERR_INVALID, "cg_build_eq: offset + num_instances > 2^k");
+    if ((uintptr_t)d_out & (k >= 1 ? 31 : 15)) return set_err(c, CG_ERR_INVALID, "cg_build_eq: d_out_ext must be 32-byte aligned (256-bit stores)");
     cudaStream_t st = S(c, s);
     CU(c, cudaSetDevice(c->device));
     void* d_point = nullptr;
@@ -452,6 +524,7 @@ CG_EXPORT int cg_ecc_quark_selectors(cg_ctx* c, const uint64_t* h_out_rt, uint32
     if (n_vars == 0 || n_vars > 40) return set_err(c, CG_ERR_INVALID, "cg_ecc_quark_selectors: num_vars out of range");
     const uint64_t n = 1ULL << n_vars;
     if (num_instances > n) return set_err(c, CG_ERR_INVALID, "cg_ecc_quark_selectors: num_instances > 2^num_vars");
+    if (((uintptr_t)d_sel_add | (uintptr_t)d_sel_bypass | (uintptr_t)d_sel_export) & 31) return set_err(c, CG_ERR_INVALID, "cg_ecc_quark_selectors: outputs must be 32-byte aligned");
     cudaStream_t st = S(c, s);
     CHK(cg_selector_compute(c, CG_SEL_QUARK_LT, h_out_rt, n_vars, 0, num_instances, nullptr, 0, 0, d_sel_add, s));
     CHK(cg_build_eq(c, h_out_rt, n_vars, d_sel_bypass, 0, n, s));
@@ -579,7 +652,7 @@ static void comm_dev(cg_comm* cm, CommDev& d, uint64_t n_exchanges) {
     cm->seq += n_exchanges;
     for (int p = 0; p < cm->nranks; p++) d.peers[p] = cm->peers[p];
     d.d_error = cm->d_error;
-    d.timeout_cycles = 8000000000ULL;
+    d.timeout_cycles = cm->ctx->wait_timeout_cycles;
     d.dbg = cm->d_dbg;
 }
 static int comm_check(cg_comm* cm, cudaStream_t st) {
@@ -973,8 +1046,10 @@ static int sc_create_terms(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, 
         }
         sc->plan_on = true;
     }
-    // shape detection: one degree-3 product of three distinct ext MLEs -> tower kernel (T3)
-    if (rc == CG_OK && !(flags & CG_SC_FORCE_GENERIC) && n_terms == 1 && degree == 3 && off[1] - off[0] == 3 && num_vars >= 1) {
+    // shape detection: one degree-3 product of three distinct ext MLEs -> tower kernel (T3).  Only when the list holds nothing
+    // else (n_mles == 3): the specialised kernels fold the term's MLEs only, and an unreferenced MLE (a zerocheck layer passes
+    // every witin/fixed/structural column) must still be folded for get_mle_flatten_final_evaluations.
+    if (rc == CG_OK && !(flags & CG_SC_FORCE_GENERIC) && n_terms == 1 && n_mles == 3 && degree == 3 && off[1] - off[0] == 3 && num_vars >= 1) {
         const uint32_t a = idx[off[0]], b = idx[off[0] + 1], d = idx[off[0] + 2];
         if (a != b && b != d && a != d && mles[a].is_ext && mles[b].is_ext && mles[d].is_ext) {
             sc->tl.on = true;
@@ -1394,7 +1469,7 @@ static int launch_tail(cg_sumcheck* sc, uint64_t* d_tr_state, ext_t* d_msgs, ext
     a.d_tr_state = d_tr_state;
     a.mail = d_tr_state ? nullptr : sc_mailbox(sc);
     a.d_error = sc->d_error;
-    a.timeout_cycles = 8000000000ULL;   // ~4 s: a dead host must not hang the GPU
+    a.timeout_cycles = c->wait_timeout_cycles;   // default ~4 s: a dead host must not hang the GPU
     if (sc->comm && sc->extra_rounds) {   // sharded prove: all-gather on entry, then everything replicated
         comm_dev(sc->comm, a.comm, 1);
         a.gather_par = (int)(sc->comm->gather_calls++ & 1);
@@ -1466,7 +1541,7 @@ static int launch_mid(cg_sumcheck* sc, uint64_t* d_tr_state, uint32_t* jt_out) {
     a.d_tr_state = d_tr_state;
     a.mail = d_tr_state ? nullptr : sc_mailbox(sc);
     a.d_error = sc->d_error;
-    a.timeout_cycles = 8000000000ULL;
+    a.timeout_cycles = c->wait_timeout_cycles;
     comm_dev(sc->comm, a.comm, a.end_round - a.first_round);
     a.partials = sc->out.partials;
     a.ticket = sc->d_mid_ticket;
@@ -1524,8 +1599,9 @@ CG_EXPORT int cg_profile_last(cg_ctx* c, float* ms_out, uint32_t cap, uint32_t* 
     return CG_OK;
 }
 
-static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t* h_rounds, uint64_t* h_final, uint64_t* h_chal) {
+static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t* h_rounds, uint64_t* h_final, uint64_t* h_chal, uint32_t round_base = 0) {
     bool have_final = false;
+    if (!sc->ctx->host_wait_ok) sc->flags |= CG_SC_NO_TAIL | CG_SC_NO_MID;   // launches block the host (profiler): one launch per round
     prof_begin(sc);
     for (uint32_t j = 0; j < sc->num_vars; j++) {
         uint64_t* msg = h_rounds + (size_t)j * sc->degree * 2;
@@ -1566,7 +1642,7 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
                 }
                 if (rc != CG_OK) break;
                 uint64_t r[2] = {0, 0};
-                cb(user, jj, m, sc->degree, r);
+                cb(user, round_base + jj, m, sc->degree, r);
                 if (h_chal) { h_chal[2 * jj] = r[0]; h_chal[2 * jj + 1] = r[1]; }
                 mailbox_reply(mb, r, (uint64_t)jj + 1);
             }
@@ -1628,7 +1704,7 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
             }
         }
         uint64_t r[2] = {0, 0};
-        cb(user, j, msg, sc->degree, r);
+        cb(user, round_base + j, msg, sc->degree, r);
         if (h_chal) { h_chal[2 * j] = r[0]; h_chal[2 * j + 1] = r[1]; }
         CHK(cg_sumcheck_bind(sc, r));
     }
@@ -1911,7 +1987,7 @@ CG_EXPORT int cg_sumcheck_prove_sharded(cg_ctx* c, cg_comm* cm, const cg_mle_des
     if (rc == CG_OK) {
         uint64_t* r2 = h_rounds + (size_t)k_local * degree * 2;
         uint64_t* c2 = h_chal ? h_chal + (size_t)k_local * 2 : nullptr;
-        rc = h_standin_state ? sc_run_device(sc2, h_standin_state, r2, h_final, c2) : sc_run_host(sc2, cb, user, r2, h_final, c2);
+        rc = h_standin_state ? sc_run_device(sc2, h_standin_state, r2, h_final, c2) : sc_run_host(sc2, cb, user, r2, h_final, c2, k_local);
     }
     if (rc == CG_OK) rc = comm_check(cm, st);
     if (sc2) cg_sumcheck_destroy(sc2);
@@ -2300,6 +2376,7 @@ CG_EXPORT int cg_poseidon2_set_params(cg_ctx* c, const cg_poseidon2_params* p) {
     memcpy(&h, p, sizeof(h));
     uint64_t* w = reinterpret_cast<uint64_t*>(&h);
     for (size_t i = 0; i < (8 * 8 + 22 + 8); i++) w[i] = w[i] >= GL_P ? w[i] - GL_P : w[i];
+    CU(c, cudaDeviceSynchronize());   // hash kernels on the lanes' non-blocking streams read d_p2: replace it only when the device is idle
     CU(c, cudaMemcpy(c->d_p2, &h, sizeof(h), cudaMemcpyHostToDevice));
     return CG_OK;
 }
@@ -2317,6 +2394,7 @@ CG_EXPORT int cg_merkle_commit(cg_ctx* c, const uint64_t* d_matrix, uint64_t wid
     if (!c || !d_matrix || !d_tree || width == 0) return CG_ERR_INVALID;
     if (!c->d_p2) return set_err(c, CG_ERR_STATE, "cg_poseidon2_set_params has not been called (constants are upstream-only: the caller supplies them)");
     if (height == 0 || (height & (height - 1))) return set_err(c, CG_ERR_INVALID, "cg_merkle_commit: height must be a power of two");
+    if (((uintptr_t)d_tree & 31) || ((uintptr_t)d_matrix & 7)) return set_err(c, CG_ERR_INVALID, "cg_merkle_commit: d_tree must be 32-byte aligned (digests are stored as 256-bit words)");
     cudaStream_t st = S(c, s);
     CU(c, cudaSetDevice(c->device));
     p2_leaf_kernel<<<(unsigned)((height + 127) / 128), 128, 0, st>>>(c->d_p2, d_matrix, width, height, col_major, d_tree);

@@ -82,7 +82,12 @@ const char* cg_last_error(cg_ctx* ctx);
 const char* cg_version(void);
 int cg_device_info(cg_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes, size_t* total_bytes);
 int cg_alloc(cg_ctx* ctx, size_t bytes, void** dptr);   /* pooled; 256-byte aligned */
-int cg_free(cg_ctx* ctx, void* dptr);                   /* returns the block to the pool */
+/* cg_free returns the block to the pool IMMEDIATELY: the caller must have synchronised every stream that still reads or
+ * writes it (the library's own calls may return while their kernels run).  cg_free_async is the stream-ordered form:
+ * the block becomes reusable only after the work enqueued on `s` so far has finished (alloc_*_on_device buffers dropped
+ * by a lane thread, gkr_iop/src/gpu/mod.rs:79-154). */
+int cg_free(cg_ctx* ctx, void* dptr);
+int cg_free_async(cg_ctx* ctx, void* dptr, cg_stream s);
 int cg_pool_stats(cg_ctx* ctx, size_t* used_bytes, size_t* reserved_bytes);
 int cg_pool_trim(cg_ctx* ctx);                          /* cudaFree every cached block */
 int cg_h2d(cg_ctx* ctx, void* dst, const void* src, size_t bytes, cg_stream s); /* async on s */
@@ -100,7 +105,9 @@ uint64_t cg_launch_count(cg_ctx* ctx);
  * (gkr_iop/src/selector.rs:140,152; ceno_zkvm/src/scheme/cpu/mod.rs:121,417).
  * out[b] = prod_i (b_i r_i + (1-b_i)(1-r_i)) for offset <= b < offset+num_instances, else 0.
  * Pass offset = 0, num_instances = 2^k for the unmasked table.  h_point_ext: k ext elements on
- * the HOST (k*2 u64).  d_out_ext: 2^k ext elements on the device. */
+ * the HOST (k*2 u64).  d_out_ext: 2^k ext elements on the device, 32-byte aligned (the same holds for the outputs of
+ * cg_selector_compute / cg_ecc_quark_selectors and for cg_merkle_commit's d_tree: they are written with 256-bit stores;
+ * a misaligned pointer is rejected with CG_ERR_INVALID). */
 int cg_build_eq(cg_ctx* ctx, const uint64_t* h_point_ext, uint32_t k, uint64_t* d_out_ext,
                 uint64_t offset, uint64_t num_instances, cg_stream s);
 

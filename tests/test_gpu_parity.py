@@ -550,6 +550,71 @@ def test_t3_k24_verifier_relations(dev):
     assert tuple(int(x) for x in orc.mle_evaluate(b_h, True, pt)) == fe[2]   # CPU check of one MLE (single fold chain)
 
 
+def test_t3_k24_bit_exact_vs_oracle(dev):
+    """The headline instance itself (bench.py's T3-24 seeds), every output bit against the oracle's proof:
+    table eq and virtual eq, host transcript and device challenger."""
+    import ceno_b200 as cb
+    k = 24
+    n = 1 << k
+    w = orc.fill_ext(0xE9, k)
+    a_h, b_h = orc.fill_ext(0xC0FFEE ^ 1, n), orc.fill_ext(0xC0FFEE ^ 2, n)
+    a = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, a_h)
+    b = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, b_h)
+    eq = cb.build_eq_x_r_vec(dev, w)
+    eqv = cb.EqPolynomial(dev, w)
+    terms = [([1, 0], [0, 1, 2])]
+    want = orc.sumcheck_prove_chunked([(orc.build_eq_x_r_vec(w), True, k), (a_h, True, k), (b_h, True, k)], terms, k, 3,
+                                      orc.Transcript(b"k24"), consume=True)
+    for mles in ([eqv, a, b], [eq, a, b]):
+        for devch in (False, True):
+            got = cb.IOPProverState.prove(dev, mles, terms, k, 3, transcript=cb.StandInTranscript(b"k24"), device_challenger=devch)
+            for g, x in zip(got, want):
+                assert eq_np(g, x), ("virtual" if mles[0] is eqv else "table", devch)
+    eq.free(); a.free(); b.free()
+
+
+@pytest.mark.parametrize("k", [3, 12, 16])
+def test_t3_shape_with_an_unreferenced_mle(dev, k):
+    """a zerocheck layer passes every column; an MLE that no term references must still be folded so that
+    get_mle_flatten_final_evaluations returns its value (here: eq*A*B plus an unused ext and an unused base column)."""
+    import ceno_b200 as cb
+    n = 1 << k
+    w = rnd_point(900 + k, k)
+    hs = [orc.build_eq_x_r_vec(w), orc.fill_ext(901 + k, n), orc.fill_ext(902 + k, n), orc.fill_ext(903 + k, n), orc.fill_base(904 + k, n)]
+    ext = [True, True, True, True, False]
+    ms = [(cb.MultilinearExtension.from_evaluations_ext_vec if e else cb.MultilinearExtension.from_evaluations_vec)(dev, k, h) for h, e in zip(hs, ext)]
+    terms = [([1, 0], [0, 1, 2])]
+    want = orc.sumcheck_prove([(h, e, k) for h, e in zip(hs, ext)], terms, k, 3, transcript=orc.Transcript(b"unused"))
+    for devch in (False, True):
+        got = cb.IOPProverState.prove(dev, ms, terms, k, 3, transcript=cb.StandInTranscript(b"unused"), device_challenger=devch)
+        for g, x in zip(got, want):
+            assert eq_np(g, x)
+    for m in ms:
+        m.free()
+
+
+def test_free_async_and_alignment_checks(dev):
+    """cg_free_async defers reuse behind the stream; 256-bit-store outputs reject misaligned pointers."""
+    import ctypes as C
+    import ceno_b200 as cb
+    lib = dev.lib
+    buf = dev.alloc(1 << 20)
+    ptr = buf.ptr
+    assert lib.cg_free_async(dev.ctx, C.c_void_p(ptr), None) == 0
+    buf.ptr = None
+    dev.sync()
+    again = dev.alloc(1 << 20)          # the block is reusable once the stream has drained
+    again.free()
+    out = dev.alloc(16 * 64 + 64)
+    w = np.ascontiguousarray(rnd_point(5, 5))
+    rc = lib.cg_build_eq(dev.ctx, w.ctypes.data_as(C.c_void_p), 5, C.c_void_p(out.ptr + 16), 0, 32, None)
+    assert rc == 2, rc                  # CG_ERR_INVALID, not a sticky misaligned-address fault
+    rc = lib.cg_build_eq(dev.ctx, w.ctypes.data_as(C.c_void_p), 5, C.c_void_p(out.ptr), 0, 32, None)
+    assert rc == 0
+    dev.sync()
+    out.free()
+
+
 # ------------------------------------------------------------------------------ multi-GPU
 def _dist_gpu_worker(rank, world, k, port, q):
     import os
