@@ -42,6 +42,7 @@ struct cg_ctx {
     P2Params* d_p2 = nullptr;                             // Poseidon2 constants (caller-supplied, cg_poseidon2_set_params)
     std::vector<float> profile_ms;                        // per-round device time of the last CG_SC_PROFILE run
     uint64_t* d_ntt_tab = nullptr;                        // NTT twiddle tables A | B | W12 (lazy, cg_ntt)
+    uint32_t tail_max_c = 1;                              // largest cluster the tail kernel can be launched with (16, 8, ... 1)
     bool host_wait_ok = true;                             // false: kernel launches block the host (profiler / sanitizer) — no kernel may wait for the host
     unsigned long long wait_timeout_cycles = 8000000000ULL;   // device-side limit of every wait on the host or a peer (CG_WAIT_TIMEOUT_MS)
 };
@@ -95,8 +96,10 @@ static cudaError_t preload(K kernel) {
 static cudaError_t prepare_kernels(size_t max_optin) {
     cudaError_t e;
 #define CG_PREP(call) if ((e = (call)) != cudaSuccess) return e
-    CG_PREP(optin_smem(tower_tail_kernel<true>, max_optin));
-    CG_PREP(optin_smem(tower_tail_kernel<false>, max_optin));
+    CG_PREP(optin_smem(tower_ctail_kernel<true>, max_optin));
+    CG_PREP(optin_smem(tower_ctail_kernel<false>, max_optin));
+    CG_PREP(cudaFuncSetAttribute(tower_ctail_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));    // clusters of 16 CTAs
+    CG_PREP(cudaFuncSetAttribute(tower_ctail_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     CG_PREP(optin_smem(eq_small_kernel, max_optin));
     CG_PREP(optin_smem(veq_tma_kernel<false, false, 2>, max_optin));
     CG_PREP(optin_smem(veq_tma_kernel<true, true, 2>, max_optin));
@@ -104,6 +107,8 @@ static cudaError_t prepare_kernels(size_t max_optin) {
     CG_PREP(optin_smem(veq_tma_kernel<false, false, 3>, max_optin));
     CG_PREP(optin_smem(veq_tma_kernel<true, true, 3>, max_optin));
     CG_PREP(optin_smem(veq_tma_kernel<true, false, 3>, max_optin));
+    CG_PREP(optin_smem(veq_tma_kernel<true, true, 2, true>, max_optin));
+    CG_PREP(optin_smem(veq_tma_kernel<true, false, 2, true>, max_optin));
     CG_PREP(preload(tower_mid_kernel<true>));
     CG_PREP(preload(tower_mid_kernel<false>));
     CG_PREP(preload(fold_kernel));
@@ -169,6 +174,22 @@ CG_EXPORT int cg_init(int device_id, cg_ctx** out) {
         return CG_ERR_CUDA;
     }
     c->host_wait_ok = probe_host_wait(c->own_stream);
+    // largest thread-block cluster the tail kernel can run with at its full shared-memory footprint (16 is non-portable)
+    for (uint32_t cs = CG_CT_MAX_C; cs >= 2; cs >>= 1) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(cs);
+        cfg.blockDim = dim3(CG_CT_THREADS);
+        cfg.dynamicSmemBytes = c->max_smem_optin - 8192;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, tower_ctail_kernel<false>, &cfg) == cudaSuccess && n_clusters >= 1) { c->tail_max_c = cs; break; }
+        cudaGetLastError();
+    }
     if (const char* e = getenv("CG_WAIT_TIMEOUT_MS")) {   // the device-side wait limit is configurable (default ~4 s)
         const double ms = atof(e);
         if (ms > 0) c->wait_timeout_cycles = (unsigned long long)(ms * 2.0e6);
@@ -664,6 +685,26 @@ static int comm_check(cg_comm* cm, cudaStream_t st) {
     return CG_OK;
 }
 
+// host-side field helpers (transcript-side scalar work: a handful of operations per sumcheck, next to the callbacks)
+static inline uint64_t hx_mulmod(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) % GL_P); }
+static inline uint64_t hx_addmod(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a + b) % GL_P); }
+static inline uint64_t hx_submod(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)(a % GL_P) + GL_P - (b % GL_P)) % GL_P); }
+static inline ext_t hx_mul(ext_t a, ext_t b) {
+    return ext_t{hx_addmod(hx_mulmod(a.c0, b.c0), hx_mulmod(7, hx_mulmod(a.c1, b.c1))), hx_addmod(hx_mulmod(a.c0, b.c1), hx_mulmod(a.c1, b.c0))};
+}
+static inline ext_t hx_add(ext_t a, ext_t b) { return ext_t{hx_addmod(a.c0, b.c0), hx_addmod(a.c1, b.c1)}; }
+static inline uint64_t hx_powmod(uint64_t a, uint64_t e) {
+    uint64_t r = 1;
+    for (; e; e >>= 1, a = hx_mulmod(a, a)) if (e & 1) r = hx_mulmod(r, a);
+    return r;
+}
+// (a0 + a1 X)^-1 = (a0 - a1 X) / (a0^2 - 7 a1^2)   (X^2 = 7; the norm is non-zero for a != 0 because 7 is a non-residue)
+static inline ext_t hx_inv(ext_t a) {
+    const uint64_t norm = hx_submod(hx_mulmod(a.c0, a.c0), hx_mulmod(7, hx_mulmod(a.c1, a.c1)));
+    const uint64_t ni = hx_powmod(norm, GL_P - 2);
+    return ext_t{hx_mulmod(a.c0 % GL_P, ni), hx_mulmod(hx_submod(0, a.c1), ni)};
+}
+
 // --------------------------------------------------------------------------------- sumcheck
 struct MleState {
     const void* orig = nullptr;
@@ -684,9 +725,12 @@ struct VeqState {               // a virtual eq MLE (CG_MLE_EQ) handled by the s
     bool have = false;          // a virtual eq was declared (point recorded)
     uint32_t idx = 0;           // its MLE index
     uint32_t J = 0;             // rounds 0 .. J-1 are split rounds
-    std::vector<uint64_t> h_point;
+    std::vector<uint64_t> h_point, h_up;
     ext_t* d_w = nullptr;       // the point on the device
-    ext_t* d_prefix = nullptr;  // scale * P_folds,  P_folds = prod_{i < folds} eq(w_i, r_i)
+    ext_t* d_prefix = nullptr;  // P_folds = prod_{i < folds} eq(w_i, r_i)   (the rank factor `scale` is kept separate)
+    ext_t* d_inv1mw = nullptr;  // 1 / (1 - w_j), host-computed
+    ext_t* d_qstate = nullptr;  // coefficients of the previous round's q(X): the running claim of the claim-derived rounds
+    bool derive_ok = false;     // every 1 - w_j is invertible (else the rounds accumulate all three sums)
     ext_t scale{1, 0};          // sharded prove: eq(w_top, rank) — the constant factor of eq on this rank's slice
     ulonglong4 *d_L = nullptr, *d_H = nullptr;
     uint64_t h_off[CG_VEQ_MAX_ROUNDS + 1] = {0};
@@ -781,21 +825,42 @@ static int veq_build_full(cg_sumcheck* sc, uint32_t i, const uint64_t* h_point) 
     sc->mles[i].orig_is_ext = 1;
     return CG_OK;
 }
+static uint32_t log2_u64(uint64_t x);
+static uint64_t tail_cap_n0(const cg_ctx* c, size_t n_slots, bool sharded);
 // split mode: upload the point, build every round's L/H tables in one launch
 static int veq_setup_split(cg_sumcheck* sc) {
     cg_ctx* c = sc->ctx;
     VeqState& v = sc->veq;
     const uint32_t k = sc->num_vars;
-    v.J = k - 18;   // rounds with >= 2^17 pairs; the cooperative mid kernel takes over after them
+    // split rounds run until the cluster tail can take the (materialised) state over: it enters at round J with a pending
+    // fold, i.e. with 2^(k - J) elements per MLE (cluster-wide; sharded: times the rank count)
+    const bool sharded = sc->comm && sc->comm->nranks > 1;
+    const uint32_t cap_log = log2_u64(std::max<uint64_t>(2, tail_cap_n0(c, 3, sharded)));
+    const uint32_t loc_log = cap_log > sc->extra_rounds ? cap_log - sc->extra_rounds : 1;
+    v.J = k > loc_log ? k - loc_log : 1;
+    if (v.J > k - 1 - CG_VEQ_LO_BITS) v.J = k - 1 - CG_VEQ_LO_BITS;   // a round needs at least one row of 256 pairs
     if (v.J > CG_VEQ_MAX_ROUNDS) v.J = CG_VEQ_MAX_ROUNDS;
     v.h_off[0] = 0;
     for (uint32_t j = 0; j < v.J; j++) v.h_off[j + 1] = v.h_off[j] + (1ULL << (k - j - 1 - CG_VEQ_LO_BITS));
+    // one upload: [w (k ext) | 1 / (1 - w_j) (k ext) | prefix = 1 | q-state (3 ext)]
     void* p = nullptr;
-    CHK(sc_alloc(sc, sizeof(ext_t) * k + 256, &p));
+    CHK(sc_alloc(sc, sizeof(ext_t) * (2 * (size_t)k + 4) + 256, &p));
     v.d_w = (ext_t*)p;
-    v.d_prefix = (ext_t*)((char*)p + ((sizeof(ext_t) * k + 63) & ~(size_t)63));
-    CU(c, cudaMemcpyAsync(v.d_w, v.h_point.data(), sizeof(ext_t) * k, cudaMemcpyHostToDevice, sc->stream));
-    CU(c, cudaMemcpyAsync(v.d_prefix, &v.scale, sizeof(ext_t), cudaMemcpyHostToDevice, sc->stream));   // v lives as long as sc
+    v.d_inv1mw = v.d_w + k;
+    v.d_prefix = v.d_w + 2 * (size_t)k;
+    v.d_qstate = v.d_prefix + 1;
+    v.h_up.assign(2 * (2 * (size_t)k + 4), 0);
+    memcpy(v.h_up.data(), v.h_point.data(), sizeof(ext_t) * k);
+    v.derive_ok = !(sc->flags & CG_SC_NO_DERIVE);
+    for (uint32_t j = 0; j < k; j++) {
+        const ext_t om{hx_submod(1, v.h_point[2 * j]), hx_submod(0, v.h_point[2 * j + 1])};
+        if (om.c0 == 0 && om.c1 == 0) { if (j >= 1 && j < v.J) v.derive_ok = false; continue; }
+        const ext_t iv = hx_inv(om);
+        v.h_up[2 * (k + j)] = iv.c0;
+        v.h_up[2 * (k + j) + 1] = iv.c1;
+    }
+    v.h_up[2 * (2 * (size_t)k)] = 1;   // prefix = 1
+    CU(c, cudaMemcpyAsync(v.d_w, v.h_up.data(), sizeof(uint64_t) * v.h_up.size(), cudaMemcpyHostToDevice, sc->stream));   // v lives as long as sc
     CHK(sc_alloc(sc, sizeof(ulonglong4) * ((size_t)v.J << CG_VEQ_LO_BITS), &p));
     v.d_L = (ulonglong4*)p;
     CHK(sc_alloc(sc, sizeof(ulonglong4) * v.h_off[v.J], &p));
@@ -824,7 +889,7 @@ static int veq_leave_split(cg_sumcheck* sc) {
         if (f > v.J) return set_err(c, CG_ERR_STATE, "split-eq: no tables for this fold level");
         const uint32_t j = f - 1;   // tables of round j cover variables [j+1, k) = [f, k)
         veq_materialise_kernel<<<grid_for(c, n / 2, 8), CG_THREADS, 0, sc->stream>>>(v.d_L + ((size_t)j << CG_VEQ_LO_BITS), v.d_H + v.h_off[j],
-                                                                                  v.d_prefix, n, (ext_t*)mle_buf(sc, v.idx, f));
+                                                                                  v.d_prefix, v.scale, n, (ext_t*)mle_buf(sc, v.idx, f));
         LAUNCHED(c);
         CU(c, cudaGetLastError());
     }
@@ -980,7 +1045,8 @@ static int sc_ensure_tables(cg_sumcheck* sc) {
 
 static int sc_create_terms(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t* coeff,
                            const uint32_t* off, const uint32_t* idx, uint32_t n_terms, uint32_t num_vars,
-                           uint32_t degree, uint32_t flags, cg_stream s, const ext_t* veq_scale, cg_sumcheck** out);
+                           uint32_t degree, uint32_t flags, cg_stream s, const ext_t* veq_scale, cg_sumcheck** out,
+                           cg_comm* comm = nullptr, uint32_t extra_rounds = 0);
 CG_EXPORT int cg_sumcheck_create(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t* coeff,
                                  const uint32_t* off, const uint32_t* idx, uint32_t n_terms, uint32_t num_vars,
                                  uint32_t degree, uint32_t flags, cg_stream s, cg_sumcheck** out) {
@@ -988,7 +1054,8 @@ CG_EXPORT int cg_sumcheck_create(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_
 }
 static int sc_create_terms(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, const uint64_t* coeff,
                            const uint32_t* off, const uint32_t* idx, uint32_t n_terms, uint32_t num_vars,
-                           uint32_t degree, uint32_t flags, cg_stream s, const ext_t* veq_scale, cg_sumcheck** out) {
+                           uint32_t degree, uint32_t flags, cg_stream s, const ext_t* veq_scale, cg_sumcheck** out,
+                           cg_comm* comm, uint32_t extra_rounds) {
     if (!c) return CG_ERR_INVALID;
     if (n_terms && (!coeff || !off || !idx)) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: null term table");
     for (uint32_t t = 0; t < n_terms; t++) {
@@ -1000,6 +1067,8 @@ static int sc_create_terms(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, 
     cg_sumcheck* sc = nullptr;
     CHK(sc_create_common(c, mles, n_mles, num_vars, degree, flags, st, &sc));
     sc->n_terms = n_terms;
+    sc->comm = comm;                   // sharded prove: known before the split-eq rounds are planned
+    sc->extra_rounds = extra_rounds;
     int rc = CG_OK;
     const uint32_t n_idx = n_terms ? off[n_terms] : 0;
     sc->h_coeff.resize(2 * (size_t)n_terms);   // canonicalised on the host (inputs may be any u64)
@@ -1174,7 +1243,11 @@ static int launch_veq(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro
     a.r = sc->pending_r;
     a.r_ptr = sc->pending_r_ptr;
     a.fin.w = v.d_w;
+    a.fin.inv1mw = v.d_inv1mw;
     a.fin.prefix = v.d_prefix;
+    a.fin.qstate = v.d_qstate;
+    a.fin.scale = v.scale;
+    a.fin.sharded = (sc->comm && sc->comm->nranks > 1) ? 1 : 0;
     a.fin.round = f;
     a.fin.fold = fold ? 1 : 0;
     a.fin.r = sc->pending_r;
@@ -1191,9 +1264,17 @@ static int launch_veq(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro
         else veq_round_kernel<true, false, MB><<<grid, 256, 0, sc->stream>>>(a);                 \
     } while (0)
     static const int use_tma = []() { const char* e = getenv("CG_VEQ_TMA"); return e ? atoi(e) : 1; }();
-    if (use_tma) {   // rows staged through shared memory by cp.async.bulk (default)
+    static const int minb = []() { const char* e = getenv("CG_VEQ_MINB"); return e ? atoi(e) : CG_VEQ_MINB_DEFAULT; }();
+    // claim-derived round (two products per pair): every round after the first, default configuration
+    const bool derive = fold && v.derive_ok && use_tma && minb != 3;
+    a.fin.derive = derive ? 1 : 0;
+    if (derive) {
+        uint64_t tb = (uint64_t)c->sm_count * 2;
+        if (tb > a.n_rows) tb = a.n_rows;
+        if (canon) veq_tma_kernel<true, true, 2, true><<<(unsigned)tb, 256, VeqTmaCfg<true, 2>::SMEM, sc->stream>>>(a);
+        else veq_tma_kernel<true, false, 2, true><<<(unsigned)tb, 256, VeqTmaCfg<true, 2>::SMEM, sc->stream>>>(a);
+    } else if (use_tma) {   // rows staged through shared memory by cp.async.bulk (default)
         // CG_VEQ_MINB = 2 | 3 resident blocks per SM (A/B switch; see VeqTmaCfg)
-        static const int minb = []() { const char* e = getenv("CG_VEQ_MINB"); return e ? atoi(e) : CG_VEQ_MINB_DEFAULT; }();
         uint64_t tb = (uint64_t)c->sm_count * (minb == 3 ? 3 : 2);
         if (tb > a.n_rows) tb = a.n_rows;
 #define CG_VEQ_TMA_LAUNCH(MB)                                                                                                   \
@@ -1421,23 +1502,74 @@ static void mailbox_reply(TailMailbox* mb, const uint64_t r[2], uint64_t seq) {
     __sync_synchronize();
     mb->seq_r = seq;
 }
+// Shape of a cluster-tail launch for a layer with n_slots MLEs entering with n0 elements each (cluster-wide):
+// n_loc0 = elements per MLE per CTA, C = cluster size, nt = size at which the slices are gathered into CTA 0.
+struct TailPlan {
+    bool ok = false;
+    uint32_t C = 1, n_loc0 = 0, nt = 0;
+    size_t smem = 0;
+};
+static uint32_t pow2_floor_u32(uint64_t x) { uint32_t r = 1; while (2ULL * r <= x) r *= 2; return r; }
+// per-CTA capacity (elements per MLE) and cluster-wide capacity for n_slots MLEs
+static uint32_t tail_nloc_cap(const cg_ctx* c, size_t n_slots) {
+    const uint64_t cap = (c->max_smem_optin - 8192) / (n_slots * sizeof(ext_t));
+    return cap < 2 ? 0 : std::min<uint32_t>(CG_CT_MAX_NLOC, pow2_floor_u32(cap));
+}
+static TailPlan tail_plan(const cg_ctx* c, size_t n_slots, uint64_t n0, bool sharded) {
+    TailPlan p;
+    const uint32_t cap = tail_nloc_cap(c, n_slots);
+    if (n0 < 1 || cap < 2 || n_slots > CG_COMM_GATHER_SLOTS) return p;
+    if (sharded && n_slots * n0 > CG_GATHER_EXT) return p;
+    const char* fe = getenv("CG_TAIL_CLUSTER");   // testing: cap the cluster size (read per call so one process can sweep it)
+    const int force_c = fe ? atoi(fe) : 0;
+    const uint32_t max_c = force_c > 0 ? std::min<uint32_t>((uint32_t)force_c, c->tail_max_c) : c->tail_max_c;
+    if (n0 <= std::min<uint32_t>(cap, CG_TAIL_START_N) || max_c == 1) {   // one CTA
+        if (n0 > cap) return p;
+        p.C = 1; p.n_loc0 = (uint32_t)n0; p.nt = (uint32_t)n0;
+    } else {
+        uint64_t C = n0 / cap;
+        if (C < 2) C = 2;
+        if (C > max_c) return p;
+        p.C = (uint32_t)C;
+        p.n_loc0 = (uint32_t)(n0 / C);
+        p.nt = std::min<uint32_t>(p.n_loc0 / 2, CG_CT_GATHER_N);   // stay distributed while a CTA still has work for its warps
+        if (p.nt < p.C || p.n_loc0 < 4) return p;
+    }
+    p.smem = n_slots * (size_t)p.n_loc0 * sizeof(ext_t);
+    p.ok = true;
+    return p;
+}
+// largest entry size (elements per MLE, cluster-wide, after the entry fold) the tail accepts for n_slots MLEs
+static uint64_t tail_cap_n0(const cg_ctx* c, size_t n_slots, bool sharded) {
+    const char* fe = getenv("CG_TAIL_CLUSTER");
+    const uint32_t max_c = fe && atoi(fe) > 0 ? std::min<uint32_t>((uint32_t)atoi(fe), c->tail_max_c) : c->tail_max_c;
+    uint64_t n = (uint64_t)tail_nloc_cap(c, n_slots) * max_c;
+    if (max_c == 1) n = std::min<uint64_t>(n, CG_TAIL_START_N);
+    if (sharded) while (n > 1 && n_slots * n > CG_GATHER_EXT) n >>= 1;
+    return n;
+}
+static uint64_t tail_entry_n0(const cg_sumcheck* sc) {
+    const uint64_t cur = 1ULL << (sc->num_vars - sc->folds);
+    return (sc->pending ? cur / 2 : cur) << sc->extra_rounds;       // sharded: the gathered (global) array
+}
 static bool tail_eligible(const cg_sumcheck* sc) {
     if (sc->veq.split) return false;
     if (!sc->tl.on || (sc->flags & (CG_SC_NO_FUSE | CG_SC_NO_TAIL)) || sc->round >= sc->num_vars) return false;
     const uint64_t cur = 1ULL << (sc->num_vars - sc->folds);
     const uint64_t n_loc = sc->pending ? cur / 2 : cur;
-    const uint64_t n0 = n_loc << sc->extra_rounds;       // sharded: the gathered (global) array
+    if (n_loc < 2) return false;
+    const bool sharded = sc->comm && sc->comm->nranks > 1;
+    if (sharded && !sc->extra_rounds) return false;   // step API with a comm: per-round exchange only
     const size_t n_slots = 1 + sc->tl.prod.size() + sc->tl.lk.size();
-    if (n_loc < 2 || n0 > CG_TAIL_START_N || n_slots > CG_COMM_GATHER_SLOTS) return false;
-    if (sc->comm && sc->comm->nranks > 1 && !sc->extra_rounds) return false;   // step API with a comm: per-round exchange only
-    return n_slots * n0 * sizeof(ext_t) + 4096 <= sc->ctx->max_smem_optin;
+    return tail_plan(sc->ctx, n_slots, tail_entry_n0(sc), sharded).ok;
 }
 // launches the tail for rounds sc->round .. num_vars-1; d_tr_state == nullptr -> host mailbox
 static int launch_tail(cg_sumcheck* sc, uint64_t* d_tr_state, ext_t* d_msgs, ext_t* d_chal) {
     cg_ctx* c = sc->ctx;
     const TowerLayout& tl = sc->tl;
-    TailArgs a;
-    memset(&a, 0, sizeof(a));
+    CTailArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    TailArgs& a = ca.t;
     const uint32_t f = sc->folds;
     auto in = [&](uint32_t i) { return (const ext_t*)mle_buf(sc, i, f); };
     a.t.eq_in = in(tl.eq);
@@ -1459,8 +1591,7 @@ static int launch_tail(cg_sumcheck* sc, uint64_t* d_tr_state, ext_t* d_msgs, ext
     a.t.r_ptr = sc->pending_r_ptr;
     a.entry_fold = sc->pending ? 1 : 0;
     a.canon = (f == 0) ? 1 : 0;
-    const uint64_t cur = 1ULL << (sc->num_vars - f);
-    a.n0 = (uint32_t)((sc->pending ? cur / 2 : cur) << sc->extra_rounds);   // sharded: size after the entry all-gather
+    a.n0 = (uint32_t)tail_entry_n0(sc);   // sharded: size after the entry all-gather
     a.first_round = sc->round;
     a.num_rounds = sc->num_vars + sc->extra_rounds;
     a.d_msgs = d_msgs;
@@ -1470,20 +1601,59 @@ static int launch_tail(cg_sumcheck* sc, uint64_t* d_tr_state, ext_t* d_msgs, ext
     a.mail = d_tr_state ? nullptr : sc_mailbox(sc);
     a.d_error = sc->d_error;
     a.timeout_cycles = c->wait_timeout_cycles;   // default ~4 s: a dead host must not hang the GPU
-    if (sc->comm && sc->extra_rounds) {   // sharded prove: all-gather on entry, then everything replicated
+    const bool sharded = sc->comm && sc->comm->nranks > 1 && sc->extra_rounds;
+    if (sharded) {   // sharded prove: all-gather on entry, then everything replicated
         comm_dev(sc->comm, a.comm, 1);
         a.gather_par = (int)(sc->comm->gather_calls++ & 1);
         a.gather_seq = a.comm.seq;
+        for (int p = 0; p < sc->comm->nranks; p++) {
+            ca.gbuf[p] = &sc->comm->peers[p]->gather.big[a.gather_par][0];
+            ca.gflag[p] = &sc->comm->peers[p]->gather.big_seq[a.gather_par][0];
+        }
         sc->extra_done = true;
     }
-    const size_t smem = (size_t)slot * a.n0 * sizeof(ext_t);
+    const TailPlan tp = tail_plan(c, (size_t)slot, a.n0, sharded);
+    if (!tp.ok) return set_err(c, CG_ERR_STATE, "launch_tail: layer does not fit the tail kernel");
+    ca.n_loc0 = tp.n_loc0;
+    ca.nt = tp.nt;
+    static long long* d_dbg = nullptr;
+    if (getenv("CG_TAIL_DEBUG")) {
+        if (!d_dbg) cudaMalloc((void**)&d_dbg, 64 * 8 * sizeof(long long));
+        cudaMemsetAsync(d_dbg, 0, 64 * 8 * sizeof(long long), sc->stream);
+        ca.dbg = d_dbg;
+    }
     const bool simple = a.t.n_prod == 1 && a.t.n_logup == 0 && a.t.alpha_one;
     // the dynamic shared-memory opt-in of both instantiations is raised once per context (prepare_kernels): a per-launch
     // cudaFuncSetAttribute is process-global state and races between lanes
-    if (simple) tower_tail_kernel<true><<<1, CG_TAIL_THREADS, smem, sc->stream>>>(a);
-    else tower_tail_kernel<false><<<1, CG_TAIL_THREADS, smem, sc->stream>>>(a);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(tp.C);
+    cfg.blockDim = dim3(CG_CT_THREADS);
+    cfg.dynamicSmemBytes = tp.smem;
+    cfg.stream = sc->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = tp.C;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (simple) CU(c, cudaLaunchKernelEx(&cfg, tower_ctail_kernel<true>, ca));
+    else CU(c, cudaLaunchKernelEx(&cfg, tower_ctail_kernel<false>, ca));
     LAUNCHED(c);
     CU(c, cudaGetLastError());
+    if (ca.dbg) {   // CG_TAIL_DEBUG: print the phase breakdown of every round (cycles of CTA 0)
+        cudaStreamSynchronize(sc->stream);
+        std::vector<long long> hdbg(64 * 8);
+        cudaMemcpy(hdbg.data(), d_dbg, hdbg.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        const uint32_t nr = a.num_rounds - a.first_round;
+        fprintf(stderr, "[ctail] C=%u n0=%u n_loc0=%u nt=%u rounds=%u\n", tp.C, a.n0, tp.n_loc0, tp.nt, nr);
+        for (uint32_t q = 0; q < nr && q < 64; q++) {
+            const long long* d = &hdbg[q * 8];
+            fprintf(stderr, "[ctail] round %2u: eval %6lld  exch %6lld  chal %6lld (reduce %lld transcript %lld)  fold %6lld  | gap %6lld cycles\n", q, d[1] - d[0], d[2] - d[1], d[3] - d[2],
+                    d[5] - d[2], d[6] - d[5], d[4] - d[3], q + 1 < nr ? hdbg[(q + 1) * 8] - d[4] : 0LL);
+        }
+    }
     return CG_OK;
 }
 static void sc_mark_done(cg_sumcheck* sc) {
@@ -1496,9 +1666,14 @@ static void sc_mark_done(cg_sumcheck* sc) {
 // ---- cooperative mid kernel (rounds between the streaming rounds and the tail)
 #define CG_MID_MAX_LOG_PAIRS 17
 // first round the tail kernel can take over, given the state at round sc->round
+static uint32_t log2_u64(uint64_t x) { uint32_t l = 0; while ((2ULL << l) <= x) l++; return l; }
 static uint32_t tail_entry_round(const cg_sumcheck* sc) {
     const uint32_t left = sc->num_vars - sc->folds;                  // log2(elements) of the current state
-    const uint32_t lim = 12 - (sc->extra_rounds < 12 ? sc->extra_rounds : 12);   // entry needs elements <= 4096 >> extra
+    const size_t n_slots = 1 + sc->tl.prod.size() + sc->tl.lk.size();
+    const bool sharded = sc->comm && sc->comm->nranks > 1;
+    const uint32_t cap_log = log2_u64(std::max<uint64_t>(1, tail_cap_n0(sc->ctx, n_slots, sharded)));   // global entry size after the entry fold
+    const uint32_t glob = cap_log + 1;                               // ... so the state before it may hold twice that
+    const uint32_t lim = glob > sc->extra_rounds ? glob - sc->extra_rounds : 0;
     const uint32_t skip = left > lim ? left - lim : 0;
     const uint32_t jt = sc->round + skip;
     return jt < sc->num_vars ? jt : sc->num_vars;
@@ -1723,12 +1898,6 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
 // The library runs one uniform sub-sumcheck per size class in lockstep (all device kernels as usual) and adds the
 // closed-form contributions of the collapsed classes on the host (a handful of field multiplications per round,
 // next to the transcript).  Reported final evaluations are the raw f_i(r_<k') (cpu/mod.rs:1346-1358).
-static inline uint64_t hx_mulmod(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) % GL_P); }
-static inline uint64_t hx_addmod(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a + b) % GL_P); }
-static inline ext_t hx_mul(ext_t a, ext_t b) {
-    return ext_t{hx_addmod(hx_mulmod(a.c0, b.c0), hx_mulmod(7, hx_mulmod(a.c1, b.c1))), hx_addmod(hx_mulmod(a.c0, b.c1), hx_mulmod(a.c1, b.c0))};
-}
-static inline ext_t hx_add(ext_t a, ext_t b) { return ext_t{hx_addmod(a.c0, b.c0), hx_addmod(a.c1, b.c1)}; }
 static bool mles_mixed(const cg_mle_desc* mles, uint32_t n_mles, uint32_t num_vars) {
     for (uint32_t i = 0; i < n_mles; i++) if (mles && mles[i].num_vars != num_vars) return true;
     return false;
@@ -1954,9 +2123,8 @@ CG_EXPORT int cg_sumcheck_prove_sharded(cg_ctx* c, cg_comm* cm, const cg_mle_des
         veq_scale = ext_t{a0, a1};
     }
     cg_sumcheck* sc = nullptr;
-    CHK(sc_create_terms(c, mles, n_mles, coeff, off, idx, n_terms, k_local, degree, flags, s, n_veq ? &veq_scale : nullptr, &sc));
-    sc->comm = cm;
-    sc->extra_rounds = (uint32_t)g;   // the persistent tail kernel continues through the replicated rounds when it can
+    // the persistent tail kernel continues through the replicated rounds when it can (extra_rounds = g)
+    CHK(sc_create_terms(c, mles, n_mles, coeff, off, idx, n_terms, k_local, degree, flags, s, n_veq ? &veq_scale : nullptr, &sc, cm, (uint32_t)g));
     std::vector<uint64_t> fin_local(2 * (size_t)(n_mles ? n_mles : 1));
     int rc = h_standin_state ? sc_run_device(sc, h_standin_state, h_rounds, fin_local.data(), h_chal)
                              : sc_run_host(sc, cb, user, h_rounds, fin_local.data(), h_chal);

@@ -466,20 +466,34 @@ GL_DEV void st_ext2(ext_t* p, ext_t a, ext_t b) {           // p 32-byte aligned
 }
 
 // ---------------------------------------------------------------- warp reduction
+// Sum of the 32 lanes' values mod p with the hardware integer warp reduction (REDUX.SUM): the value is cut into four
+// 16-bit limbs, each limb is summed over the warp in ONE instruction (32 * 65535 < 2^21, no overflow), and the four sums are
+// recombined and reduced once.  Four independent REDUX instead of a five-step dependent chain of shuffles + modular adds;
+// the result (canonical) is valid in every lane.  Any u64 input is accepted.
 GL_DEV uint64_t shfl_down_u64(uint64_t v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
-GL_DEV ext_t warp_reduce_ext(ext_t v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        ext_t o = ext_make(shfl_down_u64(v.c0, d), shfl_down_u64(v.c1, d));
-        v = ext_add(v, o);
-    }
-    return v;
+GL_DEV uint64_t warp_sum_gl(uint64_t v) {
+    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    const uint32_t s0 = __reduce_add_sync(0xffffffffu, lo & 0xFFFFu);
+    const uint32_t s1 = __reduce_add_sync(0xffffffffu, lo >> 16);
+    const uint32_t s2 = __reduce_add_sync(0xffffffffu, hi & 0xFFFFu);
+    const uint32_t s3 = __reduce_add_sync(0xffffffffu, hi >> 16);
+    const uint64_t a = (uint64_t)s0 + ((uint64_t)s1 << 16) + ((uint64_t)s2 << 32);   // < 2^54
+    const uint64_t b = (uint64_t)(s3 & 0xFFFFu) << 48;
+    const uint64_t t = a + b;
+    const uint32_t top = (s3 >> 16) + (t < a ? 1u : 0u);                             // value = t + top 2^64, top < 64
+    return gl_canon(gl_reduce_limbs((uint32_t)t, (uint32_t)(t >> 32), top, 0, 0));
 }
+GL_DEV ext_t warp_reduce_ext(ext_t v) { return ext_make(warp_sum_gl(v.c0), warp_sum_gl(v.c1)); }
 #endif
 
 // ---------------------------------------------------------------- stand-in transcript (device + host)
 // The documented stand-in sponge (NOT Poseidon2): see include/ceno_b200.h cg_standin_*.
-GL_HD uint64_t cg_splitmix64(uint64_t x) {
+#if defined(__CUDACC__)
+#define GL_HDC constexpr __host__ __device__ inline
+#else
+#define GL_HDC constexpr inline
+#endif
+GL_HDC uint64_t cg_splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ULL;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
     x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
@@ -497,4 +511,37 @@ GL_HD void cg_tr_append_message(uint64_t& h, const uint8_t* msg, uint64_t len) {
         for (uint64_t j = 0; j < 8 && i + j < len; j++) w |= (uint64_t)msg[i + j] << (8 * j);
         cg_tr_absorb(h, w);
     }
+}
+// One sumcheck round of the stand-in transcript — absorb the D evaluations, absorb the label "Internal round", squeeze the
+// challenge — arranged for a single GPU lane: absorb(h, x) = mix(h ^ mix(x)), and the inner mix(x) of the 2D message words
+// (independent of h, so they overlap) and of the three label words (compile-time constants) leave a serial chain of
+// 2D + 3 + 2 mixes instead of 4D + 6 + 2.  Bit-identical to cg_tr_absorb / cg_tr_append_message / cg_tr_squeeze.
+GL_HDC uint64_t cg_tr_pack8(const char* s, int n) {
+    uint64_t w = 0;
+    for (int j = 0; j < 8 && j < n; j++) w |= (uint64_t)(uint8_t)s[j] << (8 * j);
+    return w;
+}
+template <int D>
+GL_HD ext_t cg_tr_round(uint64_t& h, const ext_t (&res)[D]) {
+    constexpr uint64_t L0 = cg_splitmix64(0x6D73670000000000ULL ^ 14ULL);
+    constexpr uint64_t L1 = cg_splitmix64(cg_tr_pack8("Internal", 8));
+    constexpr uint64_t L2 = cg_splitmix64(cg_tr_pack8(" round", 6));
+    uint64_t sx[2 * D];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int x = 0; x < D; x++) { sx[2 * x] = cg_splitmix64(res[x].c0); sx[2 * x + 1] = cg_splitmix64(res[x].c1); }
+    uint64_t g = h;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 2 * D; i++) g = cg_splitmix64(g ^ sx[i]);
+    g = cg_splitmix64(g ^ L0);
+    g = cg_splitmix64(g ^ L1);
+    g = cg_splitmix64(g ^ L2);
+    ext_t r;
+    r.c0 = cg_tr_squeeze(g);
+    r.c1 = cg_tr_squeeze(g);
+    h = g;
+    return r;
 }

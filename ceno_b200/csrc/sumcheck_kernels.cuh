@@ -42,7 +42,7 @@ struct __align__(32) CommSlot {       // payload words w[0 .. 2D), validation fl
 struct CommGather {
     ext_t v[2][CG_COMM_GATHER_MLES][CG_MAX_RANKS];                 // fallback path: final local evaluations
     uint64_t seq[2][CG_MAX_RANKS];
-    ext_t big[2][CG_COMM_GATHER_SLOTS][CG_TAIL_START_N];           // tail entry: every rank's folded slice, rank-major
+    ext_t big[2][1u << 18];                                        // tail entry (CG_GATHER_EXT): every rank's folded slice, [slot][n0]
     uint64_t big_seq[2][CG_MAX_RANKS];
 };
 struct CommBuf {
@@ -200,10 +200,13 @@ struct RoundOut {
 
 struct NoXf {
     template <int D>
-    GL_DEV void operator()(ext_t (&)[D]) const {}
+    GL_DEV void pre(ext_t (&)[D]) const {}
+    template <int D>
+    GL_DEV void post(ext_t (&)[D]) const {}
 };
-// xf: transform applied by lane 0 of the last block to the combined local sums before the multi-GPU
-// exchange and the output (the split-eq kernels turn their three bilinear sums into the round message).
+// xf: transforms applied by lane 0 of the last block to the combined local sums: pre() before the multi-GPU exchange
+// (must be linear: the ranks' results are added), post() after it (the split-eq kernels turn their bilinear sums and
+// the running claim into the round message there).
 template <int D, class XF = NoXf>
 GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out, const XF xf = XF()) {
     __shared__ ext_t s_part[CG_THREADS / 32][D];   // blockDim.x <= CG_THREADS
@@ -251,21 +254,16 @@ GL_DEV void block_finish(ext_t (&acc)[D], const RoundOut& out, const XF xf = XF(
             ext_t v = lane < n_warps ? s_part[lane][x] : ext_zero();
             res[x] = warp_reduce_ext(v);
         }
-        if (lane == 0) xf(res);
+        if (lane == 0) xf.pre(res);
         if (out.comm.nranks > 1) comm_exchange<D>(res, out.comm, out.comm.seq, s_msg);
         if (lane == 0) {
+            xf.post(res);
 #pragma unroll
             for (int x = 0; x < D; x++) out.d_out[x] = res[x];
             if (out.mail) mailbox_post<D>(out.mail, res, out.mail_seq);
             if (out.d_tr_state) {   // stand-in challenger: absorb evals, label "Internal round", squeeze
                 uint64_t h = *out.d_tr_state;
-#pragma unroll
-                for (int x = 0; x < D; x++) { cg_tr_absorb(h, res[x].c0); cg_tr_absorb(h, res[x].c1); }
-                const uint8_t label[14] = {'I','n','t','e','r','n','a','l',' ','r','o','u','n','d'};
-                cg_tr_append_message(h, label, 14);
-                ext_t r;
-                r.c0 = cg_tr_squeeze(h);
-                r.c1 = cg_tr_squeeze(h);
+                const ext_t r = cg_tr_round<D>(h, res);
                 *out.d_tr_state = h;
                 *out.d_r_out = r;
             }
@@ -409,6 +407,65 @@ GL_DEV void tower_item(const TowerArgs& a, L& ld, uint64_t item, ecacc (&H)[3]) 
     accumulate_point(H[2], u[2], ev);
 }
 
+// The same pair evaluated at ONE point X = t + 1 (t = 0, 1, 2) into a single round sum: the latency-bound small rounds of
+// the tail kernel give every pair to three threads (one per point), which cuts the dependent chain of an item to a third.
+template <bool SIMPLE, class L>
+GL_DEV void tower_item_pt(const TowerArgs& a, L& ld, uint64_t item, int t, ecacc& H) {
+    auto at = [&](ext_t lo, ext_t hi) -> ext_t {   // f(t + 1) = hi - t (lo - hi)
+        const ext_t nd = ext_sub(lo, hi);
+        ext_t v = hi;
+        if (t >= 1) v = ext_sub(v, nd);
+        if (t >= 2) v = ext_sub(v, nd);
+        return v;
+    };
+    ext_t u;
+    if (SIMPLE) {
+        ext_t alo, ahi, blo, bhi;
+        ld.prod(0, 0, item, alo, ahi);
+        ld.prod(0, 1, item, blo, bhi);
+        u = ext_mul_weak(at(alo, ahi), at(blo, bhi));
+    } else {
+        ecacc in;
+        ecacc_zero(in);
+        for (int p = 0; p < a.n_prod; p++) {
+            ext_t alo, ahi, blo, bhi;
+            ld.prod(p, 0, item, alo, ahi);
+            ld.prod(p, 1, item, blo, bhi);
+            ext_t av = at(alo, ahi);
+            const ext_t bv = at(blo, bhi);
+            if (!a.alpha_one) av = ext_mul_prep(av, extmul_prep(a.alpha_prod[p]));
+            eacc T;
+            eacc_mul(T, av, bv, gl_mul7_weak(bv.c1));
+            ecacc_add(in, T);
+        }
+        for (int l = 0; l < a.n_logup; l++) {
+            ext_t lo, hi;
+            ld.lk(l, 0, item, lo, hi); const ext_t p1 = at(lo, hi);
+            ld.lk(l, 1, item, lo, hi); const ext_t p2 = at(lo, hi);
+            ld.lk(l, 2, item, lo, hi); const ext_t q1 = at(lo, hi);
+            ld.lk(l, 3, item, lo, hi); const ext_t q2 = at(lo, hi);
+            const extmul_t an = extmul_prep(a.alpha_num[l]), adn = extmul_prep(a.alpha_den[l]);
+            const uint64_t q1_7 = gl_mul7_weak(q1.c1), q2_7 = gl_mul7_weak(q2.c1);
+            eacc N;
+            eacc_zero(N);
+            eacc_mac(N, p1, q2, q2_7);
+            eacc_mac(N, p2, q1, q1_7);
+            eacc D;
+            eacc_zero(D);
+            eacc_mac(D, q1, q2, q2_7);
+            eacc T;
+            eacc_zero(T);
+            eacc_mac_prep(T, eacc_weak(N), an);
+            eacc_mac_prep(T, eacc_weak(D), adn);
+            ecacc_add(in, T);
+        }
+        u = ext_make(cacc_weak(in.A0), cacc_weak(in.A1));
+    }
+    ext_t elo, ehi;
+    ld.eq(item, elo, ehi);
+    accumulate_point(H, u, at(elo, ehi));
+}
+
 template <bool FOLD, bool CANON>
 struct GlobalLoader {
     const TowerArgs& a;
@@ -449,24 +506,52 @@ __global__ void __launch_bounds__(THREADS, MINB) tower_round_kernel(const __grid
 #define CG_VEQ_MAX_ROUNDS 16
 #define CG_VEQ_LO_BITS 8
 struct VeqFin {
-    const ext_t* w;        // device: the point (num_vars ext)
-    ext_t* prefix;         // device scalar: P_{j-1} on entry when `fold`, P_j otherwise (includes a rank factor when sharded)
+    const ext_t* w;        // device: the point (num_vars ext), followed by ...
+    const ext_t* inv1mw;   // ... 1 / (1 - w_j) for every variable (host-computed; the claim-derived rounds need it)
+    ext_t* prefix;         // device scalar: P_{j-1} on entry when `fold`, P_j otherwise (WITHOUT the rank factor)
+    ext_t* qstate;         // device: q_{j-1}(X) = qstate[0] + qstate[1] X + qstate[2] X^2 of the previous round (written every round)
+    ext_t scale;           // sharded: eq(w_top, rank), the constant factor of eq on this rank's slice (else 1)
     uint32_t round;        // j
     int fold;              // this launch folds by r_{j-1}: P_j = P_{j-1} eq(w_{j-1}, r_{j-1}) is stored back
+    int derive;            // 1: res = (S11, c2, -) and q(0) follows from the running claim; 0: res = (S00, S11, Sx)
+    int sharded;
     ext_t r;
     const ext_t* r_ptr;
-    GL_DEV void operator()(ext_t (&res)[3]) const {
+    // linear part, before the ranks' sums are added: the rank's constant eq factor
+    GL_DEV void pre(ext_t (&res)[3]) const {
+        if (!sharded) return;
+        const extmul_t sm = extmul_prep(scale);
+#pragma unroll
+        for (int x = 0; x < 3; x++) res[x] = ext_mul_prep(res[x], sm);
+    }
+    // Claim-derived rounds (j >= 1): the verifier's relation p_j(0) + p_j(1) = claim_j, divided by P_j, reads
+    //   (1 - w_j) q_j(0) + w_j q_j(1) = q_{j-1}(r_{j-1}),
+    // so the kernel only accumulates q_j(1) = S11 and the X^2 coefficient c2 = sum E (A_lo - A_hi)(B_lo - B_hi) — two
+    // products per pair instead of four — and q_j(0) is solved from the claim.  Exact field arithmetic: the same bits.
+    GL_DEV void post(ext_t (&res)[3]) const {
         ext_t P = ext_canon(*prefix);
         const ext_t one = ext_one();
+        ext_t rr = ext_zero();
         if (fold) {
-            const ext_t rr = ext_canon(r_ptr ? ld_ext(r_ptr) : r), wp = ext_canon(w[round - 1]);
+            rr = ext_canon(r_ptr ? ld_ext(r_ptr) : r);
+            const ext_t wp = ext_canon(w[round - 1]);
             P = ext_mul(P, ext_add(ext_mul(ext_sub(one, wp), ext_sub(one, rr)), ext_mul(wp, rr)));
             *prefix = P;
         }
         const ext_t wj = ext_canon(w[round]);
-        const ext_t q0 = res[0], q1 = res[1];
-        const ext_t c2 = ext_sub(ext_add(q0, q1), res[2]);
+        ext_t q0, q1, c2;
+        if (derive) {
+            q1 = res[0];
+            c2 = res[1];
+            const ext_t claim = ext_add(qstate[0], ext_mul(rr, ext_add(qstate[1], ext_mul(rr, qstate[2]))));
+            q0 = ext_mul(ext_sub(claim, ext_mul(wj, q1)), ext_canon(inv1mw[round]));
+        } else {
+            q0 = res[0];
+            q1 = res[1];
+            c2 = ext_sub(ext_add(q0, q1), res[2]);
+        }
         const ext_t c1 = ext_sub(ext_sub(q1, q0), c2);
+        qstate[0] = q0; qstate[1] = c1; qstate[2] = c2;
         const ext_t q2 = ext_add(ext_add(q0, ext_mul_base(c1, 2)), ext_mul_base(c2, 4));
         const ext_t q3 = ext_add(ext_add(q0, ext_mul_base(c1, 3)), ext_mul_base(c2, 9));
         // eq(w_j, t) = 1 - w_j + t (2 w_j - 1):  t=1: w_j,  t=2: 3 w_j - 1,  t=3: 5 w_j - 2
@@ -501,6 +586,13 @@ GL_DEV void veq_item(ext_t alo, ext_t ahi, ext_t blo, ext_t bhi, const extmul_t&
     eacc_mac(S11, wh, bhi, b7h);
     eacc_mac(Sx, wl, bhi, b7h);
     eacc_mac(Sx, wh, blo, b7l);
+}
+// claim-derived rounds: q(1) and the X^2 coefficient only (canonical operands: the fold's outputs)
+GL_DEV void veq_item2(ext_t alo, ext_t ahi, ext_t blo, ext_t bhi, const extmul_t& W, eacc& S11, eacc& C2) {
+    const ext_t da = ext_sub(alo, ahi), db = ext_sub(blo, bhi);
+    const ext_t wh = ext_mul_prep_weak(ahi, W), wd = ext_mul_prep_weak(da, W);
+    eacc_mac(S11, wh, bhi, gl_mul7_weak(bhi.c1));
+    eacc_mac(C2, wd, db, gl_mul7_weak(db.c1));
 }
 template <bool FOLD, bool CANON, int MINB>
 __global__ void __launch_bounds__(256, MINB) veq_round_kernel(const __grid_constant__ VeqArgs a) {
@@ -564,8 +656,12 @@ struct VeqTmaCfg {
     static constexpr int STAGES = MINB == 2 ? (FOLD ? 3 : 4) : (FOLD ? 2 : 4);
     static constexpr uint32_t SMEM = STAGES * STAGEB + 2 * STAGES * 8;
 };
-template <bool FOLD, bool CANON, int MINB = 2>
+// DERIVE (FOLD only): claim-derived round — accumulate q(1) and the X^2 coefficient only (VeqFin::post solves q(0) from the
+// running claim).  Its chunk order swaps within a pair only (absorbed by folding with 1 - r), so lo / hi are never exchanged
+// (a 2-way instead of a conflict-free shared-memory read: ~1 % of the row time).
+template <bool FOLD, bool CANON, int MINB = 2, bool DERIVE = false>
 __global__ void __launch_bounds__(256, MINB) veq_tma_kernel(const __grid_constant__ VeqArgs a) {
+    static_assert(FOLD || !DERIVE, "round 0 has no claim to derive from");
     using Cfg = VeqTmaCfg<FOLD, MINB>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr uint32_t ROWB = Cfg::ROWB, STAGEB = Cfg::STAGEB;
@@ -593,7 +689,7 @@ __global__ void __launch_bounds__(256, MINB) veq_tma_kernel(const __grid_constan
     if (tid == 0)
         for (uint32_t i = 0; i < (uint32_t)STAGES && i < nrows; i++) issue(i);
     // per-thread chunk permutation (see above)
-    const uint32_t sx = FOLD ? ((tid >> 1) & 3) : ((tid >> 2) & 1);
+    const uint32_t sx = FOLD ? (DERIVE ? ((tid >> 1) & 1) : ((tid >> 1) & 3)) : ((tid >> 2) & 1);
     const uint32_t hs = FOLD ? (sx >> 1) : sx;            // lo/hi pair swapped for this thread
     const uint32_t toff = FOLD ? tid * 64 : tid * 32;
     extmul_t rm = {0, 0, 0};
@@ -637,7 +733,8 @@ __global__ void __launch_bounds__(256, MINB) veq_tma_kernel(const __grid_constan
             st_ext(a.out[1] + 2 * item + hs, bf);
             st_ext(a.out[1] + 2 * item + (1 - hs), bs);
             extmul_t W; W.c0 = hw0.c0; W.c1 = hw0.c1; W.c1_7 = hw1.c0;
-            veq_item(af, as_, bf, bs, W, Sf, Ss, Sx);
+            if (DERIVE) veq_item2(af, as_, bf, bs, W, Ss, Sx);   // Ss = q(1) part, Sx = X^2-coefficient part
+            else veq_item(af, as_, bf, bs, W, Sf, Ss, Sx);
         } else {
             af = lds_ext(st + toff + ((0 ^ sx) << 4));
             as_ = lds_ext(st + toff + ((1 ^ sx) << 4));
@@ -653,9 +750,14 @@ __global__ void __launch_bounds__(256, MINB) veq_tma_kernel(const __grid_constan
     }
     const ulonglong4 lv = ld_tab(a.L + tid);
     extmul_t Lm; Lm.c0 = lv.x; Lm.c1 = lv.y; Lm.c1_7 = lv.z;
-    const ext_t vf = ext_mul_prep(eacc_weak(Sf), Lm), vs = ext_mul_prep(eacc_weak(Ss), Lm);
-    ext_t acc[3] = {hs ? vs : vf, hs ? vf : vs, ext_mul_prep(eacc_weak(Sx), Lm)};
-    block_finish<3, VeqFin>(acc, a.out_, a.fin);
+    if (DERIVE) {
+        ext_t acc[3] = {ext_mul_prep(eacc_weak(Ss), Lm), ext_mul_prep(eacc_weak(Sx), Lm), ext_zero()};
+        block_finish<3, VeqFin>(acc, a.out_, a.fin);
+    } else {
+        const ext_t vf = ext_mul_prep(eacc_weak(Sf), Lm), vs = ext_mul_prep(eacc_weak(Ss), Lm);
+        ext_t acc[3] = {hs ? vs : vf, hs ? vf : vs, ext_mul_prep(eacc_weak(Sx), Lm)};
+        block_finish<3, VeqFin>(acc, a.out_, a.fin);
+    }
 }
 
 // all tables of the split rounds in one launch: entry = direct product over its variables
@@ -697,8 +799,8 @@ __global__ void __launch_bounds__(CG_THREADS) veq_tables_kernel(const __grid_con
 // leave split mode: out[x] = P * L[x & 255] * H[x >> 8]  =  the eq state a materialised table would hold
 // after the same folds (variables [f, k), prefix P = prod_{i<f} eq(w_i, r_i))
 __global__ void __launch_bounds__(CG_THREADS) veq_materialise_kernel(const ulonglong4* __restrict__ L, const ulonglong4* __restrict__ H,
-                                                                      const ext_t* __restrict__ prefix, uint64_t n, ext_t* __restrict__ out) {
-    const extmul_t P = extmul_prep(ld_ext(prefix));
+                                                                      const ext_t* __restrict__ prefix, ext_t scale, uint64_t n, ext_t* __restrict__ out) {
+    const extmul_t P = extmul_prep(ext_mul(ext_canon(ld_ext(prefix)), scale));   // scale: the rank's constant eq factor (sharded), else 1
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t pair = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; pair < n / 2; pair += stride) {
         const uint64_t b = 2 * pair;
@@ -710,7 +812,7 @@ __global__ void __launch_bounds__(CG_THREADS) veq_materialise_kernel(const ulong
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tail kernel: once every MLE of the layer fits in one CTA's shared memory, ALL remaining rounds
+// Tail kernel (tower_ctail_kernel below): once every MLE of the layer fits in shared memory, ALL remaining rounds
 // (evaluate, challenge, fold ... final evaluations) run in a single persistent launch: no per-round
 // launch or host synchronisation.  The challenge comes from the device-resident challenger or, for
 // the reference's host-side transcript, from a host mailbox in mapped pinned memory (the kernel posts
@@ -754,94 +856,214 @@ GL_DEV const ext_t* tail_slot_ptr(const TowerArgs& t, int slot) {
     slot -= 2 * t.n_prod;
     return t.lk_in[slot >> 2][slot & 3];
 }
+// ---------------------------------------------------------------------------------------------
+// Cluster tail kernel.  The single-CTA tail above starts once an MLE has <= 2048 elements; everything between the
+// streaming rounds and that point used to be one grid-wide hand-off per round (ticket -> last block -> flag: ~14 us
+// of L2 round trips per round).  Here ONE thread-block cluster (<= 16 CTAs, one per SM) takes over as soon as the
+// layer fits the cluster's combined shared memory (16 x ~200 KB: 2^16 elements per MLE for the T3 shape):
+//   * CTA c keeps the contiguous slice [c n/C, (c+1) n/C) of every MLE in its own shared memory (LSB-first binding:
+//     the fold is local);
+//   * per round every CTA evaluates its pairs, stores its partial [p(1), p(2), p(3)] into EVERY CTA's shared memory
+//     through DSMEM (st.shared::cluster), and after one barrier.cluster all CTAs add the C partials themselves, so the
+//     message — and with the device challenger the challenge — is available everywhere with no second hop
+//     (host transcript: CTA 0 posts the message, every CTA polls the host's reply line);
+//   * once an MLE is down to `nt` elements the slices are gathered into CTA 0 (DSMEM stores + one cluster barrier),
+//     the other CTAs exit and CTA 0 finishes the remaining rounds with block barriers only.
+// Folds compact the arrays (slot s moves from s*n to s*n/2), so the live data always sits at the bottom of the
+// region and the top half is free for the gather.  cluster size 1 = the plain single-CTA tail.
+// Sharded prove: every rank computes its slice of the entry state, stores it into every peer's gather buffer over
+// NVLink, and all ranks then run the whole tail replicated (no further exchange).
+#define CG_CT_THREADS 512
+#define CG_CT_MAX_C 16
+#define CG_CT_MAX_NLOC 4096      // elements per MLE per CTA (register staging of the fold: 4 pairs per thread)
+#define CG_CT_GATHER_N 512       // the slices are gathered into CTA 0 once an MLE is down to this many elements (cluster-wide)
+#define CG_CT_SPLIT_PAIRS 256    // rounds with at most this many pairs per CTA split every pair over three threads (one per point)
+#define CG_GATHER_EXT (1u << 18) // ext elements of one gather buffer (per parity): n_slots * n0 must fit
+struct CTailArgs {
+    TailArgs t;                 // as for the single-CTA tail; t.n0 = elements per MLE at entry (after the entry fold)
+    uint32_t n_loc0;            // t.n0 / cluster size
+    uint32_t nt;                // gather into CTA 0 once an MLE has <= nt elements (nt <= n_loc0 / 2, nt >= cluster size)
+    ext_t* gbuf[CG_MAX_RANKS];  // sharded: every rank's gather buffer of this parity ([slot][n0] ext), gbuf[rank] is local
+    uint64_t* gflag[CG_MAX_RANKS];   // sharded: every rank's arrival flags of this parity ([CG_MAX_RANKS])
+    long long* dbg;             // CG_TAIL_DEBUG: CTA 0 records clock64() at [round][0..4] = start, evaluated, exchanged, challenged, folded
+};
+#define CT_STAMP(ph) do { if (ca.dbg && cr == 0 && tid == 0) ca.dbg[(size_t)(j - a.first_round) * 8 + (ph)] = clock64(); } while (0)
+GL_DEV uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+GL_DEV uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+GL_DEV void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+GL_DEV uint32_t dsmem_addr(const void* local, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(cta));
+    return r;
+}
+GL_DEV void dsmem_st_ext(uint32_t addr, ext_t v) {
+    asm volatile("st.shared::cluster.v2.u64 [%0], {%1, %2};" ::"r"(addr), "l"(v.c0), "l"(v.c1) : "memory");
+}
+// res[x] = sum_{i < n} part[i][x] (x = 0, 1, 2; n <= 32 canonical ext partials in shared memory), valid in every lane of the
+// calling warp.  Lane 2x + l adds limb l of output x as a plain 128-bit integer sum (n loads, two carry adds each) and
+// reduces once; six shuffles hand the results round.  Replaces three dependent warp reductions on the round's critical path.
+GL_DEV void warp_sum3_smem(const ext_t (*part)[3], int n, ext_t (&res)[3]) {
+    const int lane = threadIdx.x & 31;
+    uint64_t lo = 0;
+    uint32_t hi = 0;
+    if (lane < 6) {
+        const int x = lane >> 1, l = lane & 1;
+        for (int i = 0; i < n; i++) {
+            const uint64_t v = l ? part[i][x].c1 : part[i][x].c0;
+            lo += v;
+            hi += (lo < v) ? 1u : 0u;
+        }
+    }
+    const uint64_t r = gl_canon(gl_reduce_limbs((uint32_t)lo, (uint32_t)(lo >> 32), hi, 0, 0));
+#pragma unroll
+    for (int x = 0; x < 3; x++) res[x] = ext_make(__shfl_sync(0xffffffffu, r, 2 * x), __shfl_sync(0xffffffffu, r, 2 * x + 1));
+}
 template <bool SIMPLE>
-__global__ void __launch_bounds__(CG_TAIL_THREADS, 1) tower_tail_kernel(const __grid_constant__ TailArgs a) {
-    extern __shared__ ext_t sm[];
-    __shared__ ext_t s_red[CG_TAIL_THREADS / 32][3];
+__global__ void __launch_bounds__(CG_CT_THREADS, 1) tower_ctail_kernel(const __grid_constant__ CTailArgs ca) {
+    extern __shared__ __align__(16) ext_t ct_sm[];
+    __shared__ ext_t s_red[CG_CT_THREADS / 32][3];
+    __shared__ __align__(16) ext_t s_parts[2][CG_CT_MAX_C][3];
     __shared__ ext_t s_r;
+    __shared__ __align__(16) uint64_t s_bc[4];   // host transcript, CTAs != 0: {r.c0, r.c1, (round + 1) ^ mix(r)} written by CTA 0
     __shared__ int s_abort;
+    const TailArgs& a = ca.t;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t C = cluster_nctarank(), cr = cluster_ctarank();
     const int n_slots = 1 + 2 * a.t.n_prod + 4 * a.t.n_logup;
-    uint32_t n = a.n0;
-    if (tid == 0) s_abort = 0;
-    // ---- load (with the entry fold); sharded: my slice goes to smem AND to every peer's gather area
+    const uint32_t n_loc0 = ca.n_loc0;
+    if (tid == 0) { s_abort = 0; s_bc[0] = s_bc[1] = s_bc[2] = 0; }
+    // ---- entry: this CTA's slice [cr * n_loc0, (cr + 1) * n_loc0) of every slot (with the entry fold)
     {
         const CommDev& cm = a.comm;
         const bool sharded = cm.nranks > 1;
-        const uint32_t n_loc = sharded ? a.n0 / (uint32_t)cm.nranks : a.n0;
-        const uint32_t base = sharded ? (uint32_t)cm.rank * n_loc : 0;
-        extmul_t rm = extmul_prep(a.entry_fold ? (a.t.r_ptr ? ld_ext(a.t.r_ptr) : a.t.r) : ext_zero());
-        for (int slot = 0; slot < n_slots; slot++) {
-            const ext_t* src = tail_slot_ptr(a.t, slot);
-            for (uint32_t b = tid; b < n_loc; b += blockDim.x) {
-                ext_t v;
-                if (a.entry_fold) {
-                    ext_t lo = ld_ext(src + 2 * b), hi = ld_ext(src + 2 * b + 1);
-                    if (a.canon) { lo = ext_canon(lo); hi = ext_canon(hi); }
-                    v = ext_fma_prep(lo, ext_sub(hi, lo), rm);
-                } else {
-                    v = ld_ext(src + b);
-                    if (a.canon) v = ext_canon(v);
-                }
-                sm[(size_t)slot * a.n0 + base + b] = v;
-                if (sharded)
-                    for (int p = 0; p < cm.nranks; p++)
-                        if (p != cm.rank) st_ext(&cm.peers[p]->gather.big[a.gather_par][slot][base + b], v);
+        const extmul_t rm = extmul_prep(a.entry_fold ? (a.t.r_ptr ? ld_ext(a.t.r_ptr) : a.t.r) : ext_zero());
+        auto entry_value = [&](const ext_t* src, uint32_t b) -> ext_t {
+            if (a.entry_fold) {
+                ext_t lo, hi;
+                ld_ext2(src + 2 * (uint64_t)b, lo, hi);
+                if (a.canon) { lo = ext_canon(lo); hi = ext_canon(hi); }
+                return ext_fma_prep(lo, ext_sub(hi, lo), rm);
             }
-        }
-        if (sharded) {
+            ext_t v = ld_ext(src + b);
+            if (a.canon) v = ext_canon(v);
+            return v;
+        };
+        if (!sharded) {
+            for (int slot = 0; slot < n_slots; slot++) {
+                const ext_t* src = tail_slot_ptr(a.t, slot);
+                for (uint32_t b = tid; b < n_loc0; b += CG_CT_THREADS) ct_sm[(size_t)slot * n_loc0 + b] = entry_value(src, cr * n_loc0 + b);
+            }
+        } else {
+            // my rank's slice has n_sl = n0 / nranks elements per slot; this CTA computes the part [cr n_sl / C, ..) of it
+            // and stores it into every rank's gather buffer (its own included)
+            const uint32_t n_sl = a.n0 / (uint32_t)cm.nranks, part = n_sl / C ? n_sl / C : 1;
+            const uint32_t b0 = cr * part, b1 = (b0 + part <= n_sl) ? b0 + part : (b0 < n_sl ? n_sl : b0);
+            for (int slot = 0; slot < n_slots; slot++) {
+                const ext_t* src = tail_slot_ptr(a.t, slot);
+                for (uint32_t b = b0 + tid; b < b1; b += CG_CT_THREADS) {
+                    const ext_t v = entry_value(src, b);
+                    const size_t g = (size_t)slot * a.n0 + (size_t)cm.rank * n_sl + b;
+                    for (int p = 0; p < cm.nranks; p++) st_ext(ca.gbuf[p] + g, v);
+                }
+            }
             __threadfence_system();
-            __syncthreads();
-            if (tid < cm.nranks) {
-                *(volatile uint64_t*)&cm.peers[tid]->gather.big_seq[a.gather_par][cm.rank] = a.gather_seq;
-                volatile uint64_t* f = &cm.peers[cm.rank]->gather.big_seq[a.gather_par][tid];
+            cluster_sync_all();
+            if (cr == 0 && tid < cm.nranks) {
+                *(volatile uint64_t*)&ca.gflag[tid][cm.rank] = a.gather_seq;
+                volatile uint64_t* f = &ca.gflag[cm.rank][tid];
                 const long long t0 = clock64();
                 while (*f != a.gather_seq) {
                     if ((unsigned long long)(clock64() - t0) > cm.timeout_cycles) { *cm.d_error = 2; break; }
                 }
                 __threadfence_system();
             }
-            __syncthreads();
+            cluster_sync_all();
+            const ext_t* gb = ca.gbuf[cm.rank];
             for (int slot = 0; slot < n_slots; slot++)
-                for (uint32_t b = tid; b < a.n0; b += blockDim.x) {
-                    if (b >= base && b < base + n_loc) continue;
-                    const volatile uint64_t* src = (const volatile uint64_t*)&cm.peers[cm.rank]->gather.big[a.gather_par][slot][b];
-                    sm[(size_t)slot * a.n0 + b] = ext_make(src[0], src[1]);
+                for (uint32_t b = tid; b < n_loc0; b += CG_CT_THREADS) {
+                    const volatile uint64_t* src = (const volatile uint64_t*)(gb + (size_t)slot * a.n0 + (size_t)cr * n_loc0 + b);
+                    ct_sm[(size_t)slot * n_loc0 + b] = ext_make(src[0], src[1]);
                 }
         }
     }
     __syncthreads();
-    SmemLoader ld{sm, a.n0, a.t.n_prod};
+    ext_t* base = ct_sm;
+    bool dist = C > 1;
+    uint32_t n_cur = a.n0;                  // elements per MLE, cluster-wide
+    uint32_t n_my = n_loc0;                 // elements per MLE held here (= stride between slots: the arrays stay compact)
+    const bool writer = (cr == 0);          // the CTA that publishes messages / challenges / final evaluations
+    uint64_t h = a.d_tr_state ? *a.d_tr_state : 0;
+    int par = 0;
     for (uint32_t j = a.first_round; j < a.num_rounds; j++) {
-        const uint32_t pairs = n >> 1;
-        ecacc H[3];
-        ecacc_zero(H[0]); ecacc_zero(H[1]); ecacc_zero(H[2]);
-        for (uint32_t item = tid; item < pairs; item += blockDim.x) tower_item<SIMPLE>(a.t, ld, item, H);
-        ext_t acc[3] = {ecacc_canon(H[0]), ecacc_canon(H[1]), ecacc_canon(H[2])};
+        if (dist && n_cur <= ca.nt) {
+            // ---- gather the slices into CTA 0 (top half of its region), everyone else leaves
+            ext_t* gdst = ct_sm + ((size_t)n_slots * n_loc0 >> 1);
+            const uint32_t g0 = dsmem_addr(gdst, 0);
+            for (int slot = 0; slot < n_slots; slot++)
+                for (uint32_t b = tid; b < n_my; b += CG_CT_THREADS)
+                    dsmem_st_ext(g0 + (uint32_t)(((size_t)slot * n_cur + (size_t)cr * n_my + b) * sizeof(ext_t)), base[(size_t)slot * n_my + b]);
+            cluster_sync_all();
+            if (cr != 0) return;
+            base = gdst;
+            n_my = n_cur;
+            dist = false;
+        }
+        const uint32_t pairs = n_my >> 1;
+        SmemLoader ld{base, n_my, a.t.n_prod};
+        CT_STAMP(0);
+        if (pairs > CG_CT_SPLIT_PAIRS) {   // throughput mode: one thread evaluates a pair at all three points
+            ecacc H[3];
+            ecacc_zero(H[0]); ecacc_zero(H[1]); ecacc_zero(H[2]);
+            for (uint32_t item = tid; item < pairs; item += CG_CT_THREADS) tower_item<SIMPLE>(a.t, ld, item, H);
+            ext_t acc[3] = {ecacc_canon(H[0]), ecacc_canon(H[1]), ecacc_canon(H[2])};
 #pragma unroll
-        for (int x = 0; x < 3; x++) {
-            const ext_t v = warp_reduce_ext(acc[x]);
-            if (lane == 0) s_red[warp][x] = v;
+            for (int x = 0; x < 3; x++) {
+                const ext_t v = warp_reduce_ext(acc[x]);
+                if (lane == 0) s_red[warp][x] = v;
+            }
+        } else {                           // latency mode: three groups of five warps, group t evaluates point t + 1
+            const int tg = warp / 5;       // warp 15 idles
+            ecacc H1;
+            ecacc_zero(H1);
+            if (tg < 3)
+                for (uint32_t item = tid - 160 * tg; item < pairs; item += 160) tower_item_pt<SIMPLE>(a.t, ld, item, tg, H1);
+            const ext_t v = warp_reduce_ext(ecacc_canon(H1));
+            if (lane == 0) {
+#pragma unroll
+                for (int x = 0; x < 3; x++) s_red[warp][x] = (x == tg) ? v : ext_zero();
+            }
         }
         __syncthreads();
+        CT_STAMP(1);
+        if (dist) {
+            if (warp == 0) {
+                ext_t part[3];
+                warp_sum3_smem(s_red, CG_CT_THREADS / 32, part);
+                if (lane < (int)C) {   // lane l delivers this CTA's partial to CTA l
+                    const uint32_t dst = dsmem_addr(&s_parts[par][cr][0], (uint32_t)lane);
+#pragma unroll
+                    for (int x = 0; x < 3; x++) dsmem_st_ext(dst + 16u * x, part[x]);
+                }
+            }
+            cluster_sync_all();
+        }
+        CT_STAMP(2);
         if (warp == 0) {
             ext_t res[3];
-#pragma unroll
-            for (int x = 0; x < 3; x++) res[x] = warp_reduce_ext(lane < (CG_TAIL_THREADS / 32) ? s_red[lane][x] : ext_zero());
+            if (dist) warp_sum3_smem(s_parts[par], (int)C, res);
+            else warp_sum3_smem(s_red, CG_CT_THREADS / 32, res);
             if (lane == 0) {
                 ext_t r;
+                CT_STAMP(5);
+                if (writer) {
 #pragma unroll
-                for (int x = 0; x < 3; x++) a.d_msgs[(size_t)j * 3 + x] = res[x];
-                if (a.d_tr_state) {
-                    uint64_t h = *a.d_tr_state;
-#pragma unroll
-                    for (int x = 0; x < 3; x++) { cg_tr_absorb(h, res[x].c0); cg_tr_absorb(h, res[x].c1); }
-                    const uint8_t label[14] = {'I','n','t','e','r','n','a','l',' ','r','o','u','n','d'};
-                    cg_tr_append_message(h, label, 14);
-                    r.c0 = cg_tr_squeeze(h);
-                    r.c1 = cg_tr_squeeze(h);
-                    *a.d_tr_state = h;
-                } else {
+                    for (int x = 0; x < 3; x++) a.d_msgs[(size_t)j * 3 + x] = res[x];
+                }
+                if (a.d_tr_state) {   // every CTA runs the (deterministic) challenger on the same message
+                    r = cg_tr_round<3>(h, res);
+                } else if (writer) {
                     TailMailbox* mb = a.mail;
                     mailbox_post<3>(mb, res, (uint64_t)j + 1);
                     const long long t0 = clock64();
@@ -851,51 +1073,102 @@ __global__ void __launch_bounds__(CG_TAIL_THREADS, 1) tower_tail_kernel(const __
                         if (st == 1) break;
                         if (st < 0 || (unsigned long long)(clock64() - t0) > a.timeout_cycles) { s_abort = 1; *a.d_error = 1; break; }
                     }
+                } else {   // CTA 0 forwards the host's challenge into s_bc (below): spin on local shared memory, not on PCIe
+                    const volatile uint64_t* bc = s_bc;
+                    const long long t0 = clock64();
+                    r = ext_zero();
+                    while (true) {
+                        const uint64_t c0 = bc[0], c1 = bc[1], fl = bc[2];
+                        const uint64_t w2[2] = {c0, c1};
+                        if (fl == (((uint64_t)j + 1) ^ cg_mb_mix(w2, 2))) { r = ext_make(c0, c1); break; }
+                        if (fl == ~0ULL || (unsigned long long)(clock64() - t0) > 2 * a.timeout_cycles) { s_abort = 1; break; }
+                    }
                 }
-                a.d_chal[j] = r;
+                CT_STAMP(6);
+                if (writer) a.d_chal[j] = r;
                 s_r = r;
+            }
+            if (dist && writer && !a.d_tr_state) {   // host transcript: lane l hands the challenge (or the abort) to CTA l
+                __syncwarp();
+                const int ab = s_abort;
+                const ext_t rr = s_r;
+                if (lane >= 1 && lane < (int)C) {
+                    const uint64_t w2[2] = {rr.c0, rr.c1};
+                    const uint32_t dst = dsmem_addr(s_bc, (uint32_t)lane);
+                    dsmem_st_ext(dst, rr);
+                    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(dst + 16u), "l"(ab ? ~0ULL : (((uint64_t)j + 1) ^ cg_mb_mix(w2, 2))) : "memory");
+                }
             }
         }
         __syncthreads();
+        CT_STAMP(3);
         if (s_abort) return;
-        // ---- fold every MLE in shared memory: read the pairs, barrier, write the halves
+        // ---- fold every MLE in shared memory, compacting: slot s moves from s * n_my to s * n_my / 2
         const extmul_t rm = extmul_prep(s_r);
-        for (int slot = 0; slot < n_slots; slot++) {
-            ext_t* base = sm + (size_t)slot * a.n0;
-            constexpr int PER = (CG_TAIL_MAX_N / 2 + CG_TAIL_THREADS - 1) / CG_TAIL_THREADS;
+        constexpr int PER = (CG_CT_MAX_NLOC / 2 + CG_CT_THREADS - 1) / CG_CT_THREADS;
+        if ((uint32_t)n_slots * pairs <= (uint32_t)(PER * CG_CT_THREADS)) {   // small round: all slots in one staged pass (one barrier)
             ext_t v[PER];
+            const uint32_t total = (uint32_t)n_slots * pairs, plog = 31 - __clz(pairs);
 #pragma unroll
             for (int c = 0; c < PER; c++) {
-                const uint32_t b = tid + c * CG_TAIL_THREADS;
-                if (b < pairs) {
-                    const ext_t lo = base[2 * b], hi = base[2 * b + 1];
+                const uint32_t i = tid + c * CG_CT_THREADS;
+                if (i < total) {
+                    const uint32_t slot = i >> plog, b = i & (pairs - 1);
+                    const ext_t* src = base + (size_t)slot * n_my;
+                    const ext_t lo = src[2 * b], hi = src[2 * b + 1];
                     v[c] = ext_fma_prep(lo, ext_sub(hi, lo), rm);
                 }
             }
             __syncthreads();
 #pragma unroll
             for (int c = 0; c < PER; c++) {
-                const uint32_t b = tid + c * CG_TAIL_THREADS;
-                if (b < pairs) base[b] = v[c];
+                const uint32_t i = tid + c * CG_CT_THREADS;
+                if (i < total) base[i] = v[c];   // slot * pairs + b == i: the compact layout
+            }
+        } else {
+            for (int slot = 0; slot < n_slots; slot++) {
+                const ext_t* src = base + (size_t)slot * n_my;
+                ext_t* dst = base + (size_t)slot * pairs;
+                ext_t v[PER];
+#pragma unroll
+                for (int c = 0; c < PER; c++) {
+                    const uint32_t b = tid + c * CG_CT_THREADS;
+                    if (b < pairs) {
+                        const ext_t lo = src[2 * b], hi = src[2 * b + 1];
+                        v[c] = ext_fma_prep(lo, ext_sub(hi, lo), rm);
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int c = 0; c < PER; c++) {
+                    const uint32_t b = tid + c * CG_CT_THREADS;
+                    if (b < pairs) dst[b] = v[c];
+                }
             }
         }
         __syncthreads();
-        n = pairs;
+        CT_STAMP(4);
+        n_cur >>= 1;
+        n_my = pairs;
+        par ^= 1;
     }
-    for (int slot = tid; slot < n_slots; slot += blockDim.x) a.d_final[a.final_idx[slot]] = sm[(size_t)slot * a.n0];
+    if (!writer) return;
+    if (a.d_tr_state && tid == 0) *a.d_tr_state = h;
+    for (int slot = tid; slot < n_slots; slot += CG_CT_THREADS) a.d_final[a.final_idx[slot]] = base[slot];
     if (a.mail && tid == 0) {   // host transcript: also post the final evaluations into the mapped mailbox
         volatile uint64_t* f = a.mail->fin;
-        uint64_t h = 0;
+        uint64_t hh = 0;
         for (int slot = 0; slot < n_slots; slot++) {
-            const ext_t v = sm[(size_t)slot * a.n0];
+            const ext_t v = base[slot];
             const uint32_t w = 2u * a.final_idx[slot];
             f[w] = v.c0;
             f[w + 1] = v.c1;
-            h ^= cg_mb_word(v.c0, w) ^ cg_mb_word(v.c1, w + 1);
+            hh ^= cg_mb_word(v.c0, w) ^ cg_mb_word(v.c1, w + 1);
         }
-        a.mail->fin_flag = ((uint64_t)a.num_rounds + 1) ^ h;
+        a.mail->fin_flag = ((uint64_t)a.num_rounds + 1) ^ hh;
     }
 }
+
 // ---------------------------------------------------------------------------------------------
 // Generic monomial-term round evaluation: P = sum_t c_t prod_{i in S_t} f_i, base or ext MLEs
 // (the table extract_mle_relationships_from_monomial_terms hands to prove_generic_sumcheck_gpu,
@@ -1054,12 +1327,7 @@ __global__ void __launch_bounds__(CG_THREADS, 2) tower_mid_kernel(const __grid_c
                     bool abort = false;
                     if (a.d_tr_state) {
                         uint64_t h = *a.d_tr_state;
-#pragma unroll
-                        for (int x = 0; x < 3; x++) { cg_tr_absorb(h, res[x].c0); cg_tr_absorb(h, res[x].c1); }
-                        const uint8_t label[14] = {'I','n','t','e','r','n','a','l',' ','r','o','u','n','d'};
-                        cg_tr_append_message(h, label, 14);
-                        rn.c0 = cg_tr_squeeze(h);
-                        rn.c1 = cg_tr_squeeze(h);
+                        rn = cg_tr_round<3>(h, res);
                         *a.d_tr_state = h;
                     } else {
                         TailMailbox* mb = a.mail;

@@ -517,6 +517,59 @@ def test_tower_large(dev):
     _tower_case(dev, [17, 17], [16], False, seed=77)
 
 
+@pytest.mark.parametrize("case", ["default", "no_derive", "w_one", "w_zero"])
+def test_split_eq_claim_derived_rounds(dev, case):
+    """Split-eq rounds >= 1 accumulate q(1) and the X^2 coefficient only and solve q(0) from the running claim
+    ((1 - w_j) q(0) + w_j q(1) = q_{j-1}(r_{j-1})); the flag CG_SC_NO_DERIVE and a point with w_j = 1 (no inverse of
+    1 - w_j) take the three-sum rounds.  All must give the oracle's bits."""
+    import ceno_b200 as cb
+    k = 21
+    n = 1 << k
+    w = rnd_point(7700, k).copy()
+    if case == "w_one":
+        w[2 * 2], w[2 * 2 + 1] = 1, 0
+    if case == "w_zero":
+        w[2 * 1], w[2 * 1 + 1] = 0, 0
+        w[2 * 3], w[2 * 3 + 1] = 0, 0
+    a_h, b_h = orc.fill_ext(7701, n), orc.fill_ext(7702, n)
+    a = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, a_h)
+    b = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, b_h)
+    terms = [([1, 0], [0, 1, 2])]
+    want = orc.sumcheck_prove([(orc.build_eq_x_r_vec(w), True, k), (a_h, True, k), (b_h, True, k)], terms, k, 3, transcript=orc.Transcript(b"derive"))
+    flags = 64 if case == "no_derive" else 0
+    for devch in (False, True):
+        got = cb.IOPProverState.prove(dev, [cb.EqPolynomial(dev, w), a, b], terms, k, 3, transcript=cb.StandInTranscript(b"derive"),
+                                      device_challenger=devch, flags=flags)
+        for g, x in zip(got, want):
+            assert eq_np(g, x), (case, devch)
+    a.free(); b.free()
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
+def test_cluster_tail_every_cluster_size(dev, cluster, monkeypatch):
+    """The cluster tail kernel (DSMEM partial exchange, gather into CTA 0) at every cluster size, against the oracle:
+    T3 with table and virtual eq (host transcript and device challenger) and a multi-spec tower."""
+    import ceno_b200 as cb
+    monkeypatch.setenv("CG_TAIL_CLUSTER", str(cluster))
+    terms = [([1, 0], [0, 1, 2])]
+    for k in (13, 17, 20):
+        n = 1 << k
+        w = rnd_point(4000 + k, k)
+        a_h, b_h = orc.fill_ext(4100 + k, n), orc.fill_ext(4200 + k, n)
+        a = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, a_h)
+        b = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, b_h)
+        eq = cb.build_eq_x_r_vec(dev, w)
+        want = orc.sumcheck_prove([(orc.build_eq_x_r_vec(w), True, k), (a_h, True, k), (b_h, True, k)], terms, k, 3, transcript=orc.Transcript(b"ct"))
+        for mles in ([eq, a, b], [cb.EqPolynomial(dev, w), a, b]):
+            for devch in (False, True):
+                got = cb.IOPProverState.prove(dev, mles, terms, k, 3, transcript=cb.StandInTranscript(b"ct"), device_challenger=devch)
+                for g, x in zip(got, want):
+                    assert eq_np(g, x), (cluster, k, devch)
+        eq.free(); a.free(); b.free()
+    _tower_case(dev, [15, 14], [14], False, seed=4321 + cluster)
+    _tower_case(dev, [12] * 3, [11, 12], True, seed=99 + cluster)
+
+
 # ------------------------------------------------ full-size, size-independent properties
 def test_t3_k24_verifier_relations(dev):
     """BASELINE headline size (2^24 variables... points): too large for the oracle in seconds, so check
