@@ -167,8 +167,7 @@ def gpu_arm(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        from ceno_b200 import dist as cdist
-        return cdist.bench_sharded(args, rank, world, local)
+        return gpu_arm_sharded(args, rank, world, local)
 
     dev = cb.Device(local)
     lib = dev.lib
@@ -330,6 +329,186 @@ def gpu_arm(args):
     dev.close()
 
 
+def gpu_arm_sharded(args, rank, world, local_rank):
+    """bench.py's N>1 arm: T3-k strong scaling — each rank owns a 1/N slice of the same 2^k instance — plus one
+    weak-scaling measurement (T3-(k + log2 N): every GPU holds a 2^k slice).  Rank 0 checks the proof bit for bit against
+    the oracle's proof of the same instance and reports the roofline of its dominant kernel and the CPU baseline."""
+    import torch
+    import torch.distributed as dist
+    from ceno_b200 import api as cb
+    from ceno_b200 import synth
+    from ceno_b200.dist import eq_slice_scalar
+
+    deg = 3
+    g = world.bit_length() - 1
+    assert 1 << g == world, "number of GPUs must be a power of two"
+    dev = cb.Device(local_rank)
+    seed_a, seed_b, seed_w = SEED_A, SEED_B, SEED_W
+    terms = [([1, 0], [0, 1, 2])]
+
+    def xchg(blob):
+        outs = [None] * world
+        dist.all_gather_object(outs, blob)
+        return outs
+    comm = cb.Comm(dev, rank, world, xchg, barrier=dist.barrier)
+    stream = torch.cuda.Stream()
+    sh = stream.cuda_stream
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            o = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)     # max over ranks
+        dist.barrier()
+        return float(t.item()), o
+
+    def instance(k):
+        """This rank's slices of T3-k, pinned on the host (the e2e source) and resident on the device."""
+        k_local = k - g
+        n_local = 1 << k_local
+        nbytes = 16 * n_local
+        w = synth.fill_ext(seed_w, k)
+        a_h, a_hp = dev.pinned(nbytes)
+        b_h, b_hp = dev.pinned(nbytes)
+        synth.fill_ext(seed_a, n_local, start=rank * n_local, out=a_h)
+        synth.fill_ext(seed_b, n_local, start=rank * n_local, out=b_h)
+        a_d, b_d = dev.alloc(nbytes), dev.alloc(nbytes)
+        dev.h2d(a_d.ptr, a_hp, nbytes)
+        dev.h2d(b_d.ptr, b_hp, nbytes)
+        dev.sync()
+        A = cb.MultilinearExtension(dev, a_d, k_local, True)
+        B = cb.MultilinearExtension(dev, b_d, k_local, True)
+        if getattr(args, "eq", "virtual") == "table":
+            eq_lo = cb.build_eq_x_r_vec(dev, w[:2 * k_local])
+            s = eq_slice_scalar(w[2 * k_local:], rank)
+            EQ = cb.wit_infer_by_monomial_expr(dev, [eq_lo], [(list(s), [0])], k_local)      # eq slice = scalar * eq(w_low, .)
+            eq_lo.free()
+        else:   # eq handed over as its (global) point: split-eq rounds, no eq stream; the rank factor is derived by the library
+            EQ = cb.EqPolynomial(dev, w, num_vars=k_local)
+
+        def step(device_challenger=False, flags=0):
+            return cb.prove_sharded(dev, comm, [EQ, A, B], terms, k, deg, cb.StandInTranscript(b"bench"),
+                                    device_challenger=device_challenger, stream=sh, flags=flags)
+
+        def e2e_step():   # every rank uploads its own slices over its own PCIe link, then the sharded prove
+            dev.h2d(a_d.ptr, a_hp, nbytes, sh)
+            dev.h2d(b_d.ptr, b_hp, nbytes, sh)
+            return step()
+
+        def free():
+            a_d.free(); b_d.free()
+            if hasattr(EQ, "free"):
+                EQ.free()
+            dev.lib.cg_host_free_pinned(dev.ctx, a_hp)
+            dev.lib.cg_host_free_pinned(dev.ctx, b_hp)
+        return step, e2e_step, nbytes, free
+
+    k = args.k
+    k_local = k - g
+    step, e2e_step, nbytes, free_inst = instance(k)
+    clocks = None
+    if rank == 0:
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+    for _ in range(args.warmup):
+        out = step()
+        step(True)
+    l0 = dev.launch_count()
+    ms, out = timed(step, args.steps)
+    launches = dev.launch_count() - l0
+    ms_dev, out_dev = timed(lambda: step(True), args.steps)
+    assert all(np.array_equal(x, y) for x, y in zip(out, out_dev))
+    e2e_step()
+    ms_e2e, out_e2e = timed(e2e_step, max(1, min(args.steps, 5)))
+    assert all(np.array_equal(x, y) for x, y in zip(out, out_e2e))
+    # per-round device time of this rank's kernels (CUDA events on the launching stream)
+    prof = []
+    for _ in range(max(3, min(args.steps, 10))):
+        step(True, flags=4)
+        prof.append(dev.profile_last())
+        dist.barrier()
+    prof = np.mean(np.array(prof), axis=0)
+    clk = clocks.stop() if clocks is not None else None
+    free_inst()
+
+    # ---- weak scaling: every GPU holds a 2^k slice of a T3-(k + log2 N) instance
+    weak = None
+    if getattr(args, "weak", True):
+        kw = k + g
+        wstep, _, _, wfree = instance(kw)
+        for _ in range(min(args.warmup, 2)):
+            wstep()
+        ms_w, out_w = timed(wstep, max(1, min(args.steps, 5)))
+        weak = {"k": kw, "per_gpu_slice_log2": k, "ms_per_step": ms_w, "value": 99 * (1 << kw) / (ms_w * 1e-3) / 1e9, "unit": "Gfield-ops/s",
+                "points_per_s": (1 << kw) / (ms_w * 1e-3), "scaling": "weak",
+                "note": f"T3-{kw} sliced over {world} GPUs (per-GPU work equal to the 1-GPU T3-{k} run), host transcript"}
+        wfree()
+
+    if rank == 0:
+        n = 1 << k
+        ops = 99 * n
+        # ---- parity: the oracle's proof of the very same instance (rank 0's host cores)
+        from oracle import oracle as orc
+        if hasattr(orc, "set_num_threads"):
+            orc.set_num_threads(_physical_cores())
+        cpu_run(min(args.cpu_k, 16))
+        t_cpu, cpu_proof = cpu_run(args.cpu_k)
+        parity_checked = None
+        if args.cpu_k == k:
+            for nm, o in (("host transcript", out), ("device challenger", out_dev), ("e2e from host buffers", out_e2e)):
+                assert_same_proof(o, cpu_proof, f"T3-{k} on {world} GPUs, {nm}")
+            parity_checked = f"oracle k={k}: the {world}-GPU proof (host transcript, device challenger, e2e) is bit-exact"
+        cores = orc.num_threads()
+        cpu_val = 99 * (1 << args.cpu_k) / t_cpu / 1e9
+        # ---- roofline of rank 0's dominant kernel: the fused fix_variable + evaluation of the streaming rounds
+        virt = getattr(args, "eq", "virtual") == "virtual"
+        m = 2 if virt else 3
+        peak, peak_src = read_peaks()
+        n_split = max(2, k_local - 13)                     # rounds 1 .. n_split-1 run the streaming kernel on the local slice
+        rounds = [j for j in range(1, n_split) if j < len(prof)]
+        fused_bytes = [1.5 * m * 16 * (1 << (k_local - j + 1)) for j in rounds]
+        fused_ms = [float(prof[j]) for j in rounds]
+        ach = sum(fused_bytes) / (sum(fused_ms) * 1e-3) / 1e9 if rounds else 0.0
+        roofline = {"bound": "hbm", "kernel": "veq_tma_kernel<FOLD=1> on rank 0's 1/%d slice (its launches include the in-kernel NVLink exchange of the round's partial sums)" % world,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
+                    "bytes_definition": f"per launch 1.5*m*16*n_in over the rank's slice, m = {m} streamed MLEs",
+                    "launches_per_step": len(rounds), "ms_per_step_in_kernel": sum(fused_ms), "round_ms": [round(float(x), 5) for x in prof]}
+        line = {
+            "metric": "sumcheck Gfield-ops/s", "value": ops / (ms * 1e-3) / 1e9, "unit": "Gfield-ops/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64 (Goldilocks, ext2)", "data": "synthetic",
+            "config": workload_config(k, world),
+            "config_detail": {"parallelism": f"hypercube slices x{world}: rank q owns [q 2^{k_local}, (q+1) 2^{k_local}) of every MLE", "eq": getattr(args, "eq", "virtual"),
+                              "exchange": "in-kernel: the round kernel's last block stores its partial sums into every peer's NVLink-mapped mailbox, waits for the N flags, "
+                                          "adds mod p; once the global state fits one thread-block cluster (2^16 elements per MLE) the slices are all-gathered over NVLink "
+                                          "and the remaining rounds run replicated (no further exchange); replicated host transcript",
+                              "per_gpu_inputs_MiB": 3 * 16 * (1 << k_local) >> 20},
+            "points_per_s": n / (ms * 1e-3), "rounds_per_s": k / (ms * 1e-3),
+            "device_challenger": {"ms_per_step": ms_dev, "value": ops / (ms_dev * 1e-3) / 1e9, "unit": "Gfield-ops/s"},
+            "e2e": {"value": ops / (ms_e2e * 1e-3) / 1e9, "unit": "Gfield-ops/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": world * 2 * nbytes + 16 * k, "d2h_bytes_per_step": 16 * (k * deg + 3 + k),
+                    "note": f"every rank uploads its 1/{world} slices of A and B from pinned host memory over its own PCIe link, then the sharded prove; max over ranks"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": {"value": cpu_val, "unit": "Gfield-ops/s", "cores": cores, "kind": "port", "ms": t_cpu * 1e3,
+                             "sample": f"T3-{args.cpu_k} full sumcheck, one run on rank 0's host; oracle port with the reference's decomposition, OpenMP {cores} threads"},
+            "weak_scaling": weak,
+            "clocks": clk,
+            "parity_checked": parity_checked,
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    comm.close()
+    dev.close()
+    dist.destroy_process_group()
+
+
 def _physical_cores():
     """Distinct physical cores in this process's affinity mask (SMT siblings counted once)."""
     try:
@@ -365,6 +544,7 @@ def main():
     ap.add_argument("--k", type=int, default=24, help="log2 hypercube size of the T3 instance")
     ap.add_argument("--eq", default="virtual", choices=["virtual", "table"], help="how eq(w,.) is given to the prover (see the module docstring)")
     ap.add_argument("--cpu-k", type=int, default=24, help="log2 size of the bounded CPU sample")
+    ap.add_argument("--no-weak", dest="weak", action="store_false", help="N>1: skip the weak-scaling measurement (T3-(k + log2 N))")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -269,9 +269,28 @@ GL_DEV void wsum_addw(wsum_t& W, const wsum_t& V) {
 GL_DEV uint64_t wsum_weak(const wsum_t& W) { return gl_reduce_limbs(W.l0, W.l1, W.l2, 0, 0); }
 
 // any u64 -> canonical:  x >= p  <=>  hi == 0xFFFFFFFF and lo != 0, and then x - p = lo - 1
+// Device form: the same borrow chain as gl_sub(x, p) — x - p, and p is added back (as "- EPS") when that borrowed: five
+// carry-chain instructions, no compares or selects (the compare/select form was 8 SASS instructions and a quarter of the
+// round-1 kernel's issue slots).
 GL_HD uint64_t gl_canon(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    uint64_t r;
+    asm("{\n\t"
+        ".reg .u32 x0, x1, m;\n\t"
+        "mov.b64 {x0, x1}, %1;\n\t"
+        "sub.cc.u32 x0, x0, 1;\n\t"
+        "subc.cc.u32 x1, x1, 0xFFFFFFFF;\n\t"
+        "subc.u32 m, 0, 0;\n\t"          // m = -borrow: x < p
+        "sub.cc.u32 x0, x0, m;\n\t"      // borrow: subtract EPS (== add p)
+        "subc.u32 x1, x1, 0;\n\t"
+        "mov.b64 %0, {x0, x1};\n\t"
+        "}"
+        : "=l"(r) : "l"(x));
+    return r;
+#else
     const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
     return (hi == 0xFFFFFFFFu && lo != 0) ? (uint64_t)(lo - 1) : x;
+#endif
 }
 GL_DEV uint64_t acc_canon(const acc_t& A) { return gl_canon(acc_weak(A)); }
 GL_DEV uint64_t cacc_canon(const cacc_t& C) { return gl_canon(cacc_weak(C)); }

@@ -833,6 +833,13 @@ OR_API int64_t or_tower_create_proof(uint32_t n_prod, const uint32_t* prod_layer
     return (int64_t)w;
 }
 
+OR_API void or_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 OR_API int or_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -74,6 +74,11 @@ def num_threads():
     return lib().or_num_threads()
 
 
+def set_num_threads(n):
+    """OpenMP thread count of the C restatement (torchrun exports OMP_NUM_THREADS=1 to its ranks)."""
+    lib().or_set_num_threads(C.c_int(int(n)))
+
+
 # ------------------------------------------------------------------ field
 def gl_mul(a, b):
     return lib().or_gl_mul(a, b)
