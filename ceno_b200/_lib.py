@@ -32,6 +32,19 @@ class CgSchedResult(C.Structure):
 SCHED_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p)
 
 
+class CgBasefoldParams(C.Structure):
+    _fields_ = [("rate_log", C.c_uint32), ("n_queries", C.c_uint32), ("pow_bits", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class CgBasefoldOpening(C.Structure):
+    _fields_ = [("commit", C.c_void_p), ("h_point_ext", C.c_void_p), ("h_evals_ext", C.c_void_p)]
+
+
+class CgPcsTranscriptVt(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("observe_label", C.c_void_p), ("sample_ext", C.c_void_p), ("observe_exts", C.c_void_p),
+                ("observe_base", C.c_void_p), ("sample_bits", C.c_void_p), ("grind", C.c_void_p)]
+
+
 class CgTowerSpec(C.Structure):
     _fields_ = [("leaves", C.c_void_p * 4), ("num_vars", C.c_uint32), ("is_logup", C.c_uint32)]
 
@@ -62,6 +75,8 @@ SYMBOLS = [
     "cg_rotation_next_base_mle", "cg_rotation_selector",
     "cg_sched_execute", "cg_stream_create", "cg_stream_destroy", "cg_ntt", "cg_rs_encode",
     "cg_ecc_quark_selectors", "cg_split_even_odd", "cg_ecc_quark_terms",
+    "cg_basefold_commit", "cg_basefold_commitment_root", "cg_basefold_commitment_codeword", "cg_basefold_commitment_free",
+    "cg_standin_pcs_vt", "cg_basefold_proof_len", "cg_basefold_batch_open",
 ]
 
 _lib = None
@@ -140,6 +155,13 @@ def load():
         "cg_ecc_quark_selectors": (i32, [vp, vp, u32, u64, vp, vp, vp, vp]),
         "cg_split_even_odd": (i32, [vp, P(CgMleDesc), u32, P(vp), P(vp), vp]),
         "cg_ecc_quark_terms": (i32, [vp, vp, vp, vp, vp, vp, u32, u32, P(u32), P(u32)]),
+        "cg_basefold_commit": (i32, [vp, vp, u64, u32, P(CgBasefoldParams), vp, P(vp)]),
+        "cg_basefold_commitment_root": (i32, [vp, vp]),
+        "cg_basefold_commitment_codeword": (i32, [vp, P(vp), P(vp)]),
+        "cg_basefold_commitment_free": (i32, [vp]),
+        "cg_standin_pcs_vt": (None, [vp, P(CgPcsTranscriptVt)]),
+        "cg_basefold_proof_len": (u64, [P(CgBasefoldOpening), u32, P(CgBasefoldParams)]),
+        "cg_basefold_batch_open": (i32, [vp, P(CgBasefoldOpening), u32, P(CgBasefoldParams), P(CgPcsTranscriptVt), vp, u64, vp]),
         "cg_stream_create": (i32, [vp, P(vp)]),
         "cg_stream_destroy": (i32, [vp, vp]),
         "cg_sumcheck_prove_sharded": (i32, [vp, vp, P(CgMleDesc), u32, vp, vp, vp, u32, u32, u32, u32, CHALLENGE_CB, vp, vp, vp, vp, vp, vp]),

@@ -643,6 +643,87 @@ def basefold_style_commit(dev, msg_buf, width, log_n, rate_log=1, stream=None):
     return code, tree, root
 
 
+# ------------------------------------------------------------------- f-2 / a9: Basefold commit + batch_open
+class BasefoldParams:
+    """BasefoldSpec parameters (rate_log / number of queries / proof-of-work bits are upstream-only: parameters here)."""
+
+    def __init__(self, rate_log=1, n_queries=8, pow_bits=0):
+        self.rate_log, self.n_queries, self.pow_bits = rate_log, n_queries, pow_bits
+
+    def c(self):
+        return _lib.CgBasefoldParams(self.rate_log, self.n_queries, self.pow_bits, 0)
+
+
+class BasefoldCommitment:
+    """PCS::CommitmentWithWitness on the device (TraceCommitter::commit_traces, ceno_zkvm/src/scheme/cpu/mod.rs:559-584):
+    the RS-encoded columns (bit-reversed rows) and their Merkle tree.  `msg_buf` (width x 2^num_vars base elements,
+    column-major) must stay alive until the opening."""
+
+    def __init__(self, dev, msg_buf, width, num_vars, params, stream=None):
+        self.dev, self.msg, self.width, self.num_vars, self.params = dev, msg_buf, width, num_vars, params
+        self.h = C.c_void_p()
+        cp = params.c()
+        dev.check(dev.lib.cg_basefold_commit(dev.ctx, C.c_void_p(msg_buf.ptr), width, num_vars, C.byref(cp), C.c_void_p(stream) if stream else None,
+                                             C.byref(self.h)))
+        root = np.zeros(4, np.uint64)
+        dev.check(dev.lib.cg_basefold_commitment_root(self.h, _vp(root)))
+        self.root = root
+
+    def codeword(self):
+        code = C.c_void_p()
+        self.dev.check(self.dev.lib.cg_basefold_commitment_codeword(self.h, C.byref(code), None))
+        n = self.width << (self.num_vars + self.params.rate_log)
+        return DeviceBuffer(self.dev, code.value, 8 * n, owner=False).to_host().reshape(self.width, -1)
+
+    def free(self):
+        if self.h:
+            self.dev.lib.cg_basefold_commitment_free(self.h)
+            self.h = C.c_void_p()
+
+
+def basefold_batch_open(dev, commits, points, evals, params, transcript, stream=None):
+    """OpeningProver::open -> PCS::batch_open (ceno_zkvm/src/scheme/cpu/mod.rs:1415-1457): one opening (point, evals) per
+    commitment.  `transcript` is a StandInTranscript.  Returns the proof parsed into the structure of BasefoldProof:
+    {sumcheck: [(p1, p2)], commits: [digest], final_message: [[ext]], pow_witness, queries: [{index, inputs, commit_phase}]}."""
+    n = len(commits)
+    keep = []
+    ops = (_lib.CgBasefoldOpening * n)()
+    for i, (cm, pt, ev) in enumerate(zip(commits, points, evals)):
+        pt, ev = _u64(pt), _u64(ev)
+        keep += [pt, ev]
+        ops[i].commit, ops[i].h_point_ext, ops[i].h_evals_ext = cm.h.value, pt.ctypes.data, ev.ctypes.data
+    cp = params.c()
+    words = dev.lib.cg_basefold_proof_len(ops, n, C.byref(cp))
+    assert words > 0
+    proof = np.zeros(words, np.uint64)
+    vt = _lib.CgPcsTranscriptVt()
+    dev.lib.cg_standin_pcs_vt(_vp(transcript.state), C.byref(vt))
+    dev.check(dev.lib.cg_basefold_batch_open(dev.ctx, ops, n, C.byref(cp), C.byref(vt), _vp(proof), words, C.c_void_p(stream) if stream else None))
+    # ---- parse
+    rate = params.rate_log
+    max_nv = max(c.num_vars for c in commits)
+    w = [0]
+
+    def take(k):
+        out = [int(x) for x in proof[w[0]:w[0] + k]]
+        w[0] += k
+        return out
+
+    def ext():
+        return tuple(take(2))
+    out = {"sumcheck": [(ext(), ext()) for _ in range(max_nv)], "commits": [take(4) for _ in range(max_nv)],
+           "final_message": [[ext()] for _ in range(n)], "pow_witness": take(1)[0], "queries": []}
+    for _ in range(params.n_queries):
+        q = {"index": take(1)[0], "inputs": [], "commit_phase": []}
+        for c in commits:
+            q["inputs"].append({"opened": take(c.width), "path": [take(4) for _ in range(c.num_vars + rate)]})
+        for r in range(max_nv):
+            q["commit_phase"].append({"sibling": ext(), "path": [take(4) for _ in range(max_nv + rate - r - 1)]})
+        out["queries"].append(q)
+    assert w[0] == words
+    return out
+
+
 # ------------------------------------------------------------------- f-3: EC-sum Quark prover (cpu/mod.rs:72-316)
 SEPTIC_EXTENSION_DEGREE = 7
 

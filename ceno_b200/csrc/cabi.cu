@@ -21,6 +21,7 @@
 #include "sumcheck_kernels.cuh"
 #include "poseidon2.cuh"
 #include "ntt_kernels.cuh"
+#include "basefold.cuh"
 
 #define CG_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -2617,3 +2618,4 @@ CG_EXPORT int cg_rotation_selector(cg_ctx* c, const uint64_t* d_eq_ext, uint64_t
 #include "sched.cuh"
 #include "ntt_host.cuh"
 #include "ecc_host.cuh"
+#include "basefold_host.cuh"

@@ -367,6 +367,60 @@ int cg_ntt(cg_ctx* ctx, uint64_t* d_data, uint32_t log_n, uint64_t n_cols, uint6
 int cg_rs_encode(cg_ctx* ctx, const uint64_t* d_msg, uint64_t width, uint32_t log_n, uint32_t rate_log, uint64_t* d_code,
                  uint32_t flags, cg_stream s);
 
+/* ---- f-2 / a9: Basefold PCS — commit and batch_open.
+ * Replaces TraceCommitter::commit_traces -> PCS::batch_commit (ceno_zkvm/src/scheme/cpu/mod.rs:559-584; GPU
+ * basefold.batch_commit_*, ceno_zkvm/src/scheme/gpu/mod.rs:1062-1509) and OpeningProver::open -> PCS::batch_open
+ * (ceno_zkvm/src/scheme/cpu/mod.rs:1415-1457; GPU ceno_zkvm/src/scheme/gpu/mod.rs:3324-3413).  The protocol itself is in the
+ * un-vendored `mpcs` crate; what is implemented is exactly what the in-tree verifier restatement accepts
+ * (ceno_recursion_v2/src/pcs/mod.rs:1111-1317 replay_basefold, :7494-7727 query checks, :7765-7781 fold rule, :444-592
+ * final claim, :138-145 basecode_log == 0):
+ *   commitment  : every column (an MLE's 2^num_vars evaluations = the message coefficients) RS-encoded at rate 2^-rate_log,
+ *                 codeword rows in bit-reversed order, leaf = PaddingFreeSponge over the row of all columns, 2-to-1 compression;
+ *   batch_open  : batch coefficients 1, a, a^2, ... (label "batch coeffs"); per round: degree-2 sumcheck message
+ *                 [p(1), p(2)], label "commit round", challenge, Merkle commitment of the running codeword as (even, odd) ext
+ *                 pairs (observed after the challenge), fold lo=(a+b)/2, hi=(a-b) g^-bitrev(i)/2, lo + r (hi-lo); smaller
+ *                 codewords join at their height; final message = one ext per opening; proof of work; label
+ *                 "query indices"; per query one opened row + path per commitment and one sibling + path per round.
+ * PARITY UNPINNED for rate_log, the number of queries, proof-of-work bits (parameters), the Poseidon2 constants and the
+ * duplex challenger (behind the vtable), and mixed-height commitments (one matrix per commitment, like the restatement).
+ * Proof layout (u64 words, cg_basefold_proof_len of them), R = max num_vars, Q = n_queries:
+ *   sumcheck R x [p(1).c0 c1 p(2).c0 c1] | commits R x 4 | final message n_openings x 2 | pow witness 1 |
+ *   Q x { index 1 | per opening: row (width) , path (num_vars + rate_log) x 4 | per round r: sibling 2, path (R + rate_log - r - 1) x 4 } */
+typedef struct cg_basefold_params {
+    uint32_t rate_log;   /* BasefoldSpec::get_rate_log()        (upstream; 1 in the tests) */
+    uint32_t n_queries;  /* BasefoldSpec::get_number_queries()  (upstream) */
+    uint32_t pow_bits;   /* proof-of-work bits before the queries (pcs/mod.rs:1255-1259); 0 = none */
+    uint32_t reserved;
+} cg_basefold_params;
+typedef struct cg_pcs_commitment cg_pcs_commitment;   /* PCS::CommitmentWithWitness: codeword matrix + Merkle tree on the device */
+/* d_msg: width x 2^num_vars base elements, column-major (what the reference keeps on the device after matrix_transpose); it
+ * is read again by cg_basefold_batch_open and must stay alive until then.  Needs cg_poseidon2_set_params. */
+int cg_basefold_commit(cg_ctx* ctx, const uint64_t* d_msg, uint64_t width, uint32_t num_vars, const cg_basefold_params* params,
+                       cg_stream s, cg_pcs_commitment** out);
+int cg_basefold_commitment_root(const cg_pcs_commitment* cm, uint64_t h_root[4]);
+/* device pointers of the codeword matrix (width x 2^(num_vars+rate_log), column-major, bit-reversed rows) and the tree */
+int cg_basefold_commitment_codeword(const cg_pcs_commitment* cm, const uint64_t** d_code, const uint64_t** d_tree);
+int cg_basefold_commitment_free(cg_pcs_commitment* cm);
+/* Transcript events of the PCS (the reference hands &mut impl Transcript<E> to batch_open): */
+typedef struct cg_pcs_transcript_vt {
+    void* user;
+    void (*observe_label)(void* user, const char* label);
+    void (*sample_ext)(void* user, uint64_t out_ext[2]);
+    void (*observe_exts)(void* user, const uint64_t* ext, uint64_t n);
+    void (*observe_base)(void* user, const uint64_t* base, uint64_t n);   /* Merkle digests */
+    uint64_t (*sample_bits)(void* user, uint32_t bits);
+    uint64_t (*grind)(void* user, uint32_t bits);                          /* returns the proof-of-work witness */
+} cg_pcs_transcript_vt;
+void cg_standin_pcs_vt(uint64_t* state, cg_pcs_transcript_vt* out);       /* over a stand-in state (NOT Poseidon2) */
+typedef struct cg_basefold_opening {
+    const cg_pcs_commitment* commit;
+    const uint64_t* h_point_ext;   /* num_vars ext (host) */
+    const uint64_t* h_evals_ext;   /* width ext (host): the claimed evaluations of the columns at the point */
+} cg_basefold_opening;
+uint64_t cg_basefold_proof_len(const cg_basefold_opening* ops, uint32_t n_openings, const cg_basefold_params* params);
+int cg_basefold_batch_open(cg_ctx* ctx, const cg_basefold_opening* ops, uint32_t n_openings, const cg_basefold_params* params,
+                           const cg_pcs_transcript_vt* tr, uint64_t* h_proof, uint64_t proof_cap_words, cg_stream s);
+
 /* ---- f-4: chip-level concurrency — ChipScheduler::execute (ceno_zkvm/src/scheme/scheduler.rs:109-400,
  * docs/src/concurrent-chip-proving.md).  Greedy backfilling over 1..8 lanes (0 = the reference's default, 4), one OS
  * thread + one non-default stream per lane: tasks are sorted by estimated memory (descending), the first pending task

@@ -517,6 +517,51 @@ def test_tower_large(dev):
     _tower_case(dev, [17, 17], [16], False, seed=77)
 
 
+@pytest.mark.parametrize("shapes", [[(3, 1)], [(6, 3)], [(5, 2), (5, 1)], [(7, 2), (4, 3), (6, 1)], [(2, 1), (9, 4)], [(14, 5), (12, 3)]])
+def test_basefold_commit_and_batch_open_bit_exact(dev, shapes):
+    """f-2 / a9: commitment roots, every prover message, the final message, the proof-of-work witness and every query opening
+    equal the oracle's (oracle/basefold.py, pinned on the in-tree verifier restatement ceno_recursion_v2/src/pcs/mod.rs);
+    the oracle's verifier accepts the device proof."""
+    import random
+    import ceno_b200 as cb
+    from ceno_b200 import api
+    from oracle import basefold as bf
+    from oracle import pyref as pr
+    rng = random.Random(4242 + len(shapes) + shapes[0][0])
+    p2 = orc.p2_params(seed=5)
+    api.poseidon2_set_params(dev, [[int(p2.ext_rc[r][i]) for i in range(8)] for r in range(8)], [int(x) for x in p2.int_rc], [int(x) for x in p2.diag], 0)
+    params_o = bf.Params(rate_log=1, n_queries=5, pow_bits=3)
+    params_d = api.BasefoldParams(rate_log=1, n_queries=5, pow_bits=3)
+    oc, dc, points, evals, bufs = [], [], [], [], []
+    for nv, width in shapes:
+        cols = [orc.fill_base(rng.randrange(1 << 30), 1 << nv) for _ in range(width)]
+        oc.append(bf.commit(p2, params_o, cols, nv))
+        buf = dev.to_device(np.concatenate(cols))
+        bufs.append(buf)
+        dc.append(api.BasefoldCommitment(dev, buf, width, nv, params_d))
+        assert [int(x) for x in dc[-1].root] == oc[-1]["root"]
+        pt = [(rng.randrange(P), rng.randrange(P)) for _ in range(nv)]
+        points.append(pt)
+        evals.append([tuple(int(x) for x in orc.mle_evaluate(c, False, np.array(pt, dtype=np.uint64).reshape(-1))) for c in cols])
+    want = bf.batch_open(p2, params_o, oc, points, evals, orc.Transcript(b"pcs"))
+    got = api.basefold_batch_open(dev, dc, [np.array(p, dtype=np.uint64).reshape(-1) for p in points],
+                                  [np.array(e, dtype=np.uint64).reshape(-1) for e in evals], params_d, cb.StandInTranscript(b"pcs"))
+    for key in ("sumcheck", "commits", "final_message", "pow_witness"):
+        assert got[key] == want[key] or [list(x) for x in got[key]] == [list(x) for x in want[key]], key
+    assert len(got["queries"]) == len(want["queries"])
+    for g, x in zip(got["queries"], want["queries"]):
+        assert g["index"] == x["index"]
+        for gi, xi in zip(g["inputs"], x["inputs"]):
+            assert gi["opened"] == [int(v) for v in xi["opened"]] and gi["path"] == [list(d) for d in xi["path"]]
+        for gc, xc in zip(g["commit_phase"], x["commit_phase"]):
+            assert tuple(gc["sibling"]) == tuple(xc["sibling"]) and gc["path"] == [list(d) for d in xc["path"]]
+    assert bf.batch_verify(p2, params_o, shapes, [c["root"] for c in oc], points, evals, got, orc.Transcript(b"pcs"))
+    for c in dc:
+        c.free()
+    for b in bufs:
+        b.free()
+
+
 @pytest.mark.parametrize("case", ["default", "no_derive", "w_one", "w_zero"])
 def test_split_eq_claim_derived_rounds(dev, case):
     """Split-eq rounds >= 1 accumulate q(1) and the X^2 coefficient only and solve q(0) from the running claim
