@@ -300,6 +300,19 @@ def gpu_arm(args):
     cpu_val = OPS_PER_PAIR * (1 << args.cpu_k) / t_cpu / 1e9
     cores = orc.num_threads()
 
+    # ---- the other SURVEY §8 rows on the same box (secondary keys; never allowed to break the headline line)
+    rows = None
+    if args.rows:
+        try:
+            for b in (a_d, b_d, eq_d):
+                b.free()
+            dev.lib.cg_pool_trim(dev.ctx)
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_rows
+            rows = bench_rows.run_rows(dev, peak_gbs=peak)
+        except Exception as e:  # noqa: BLE001
+            rows = {"error": repr(e)}
+
     ops = OPS_PER_PAIR * n
     value = ops / (ms * 1e-3) / 1e9
     line = {
@@ -324,6 +337,7 @@ def gpu_arm(args):
                          "sample": f"T3-{args.cpu_k} full sumcheck ({'the whole workload' if args.cpu_k == k else f'1/{1 << (k - args.cpu_k)} of its points'}), one run; oracle port with the reference's decomposition (per-thread chunks folded in place, single-thread tail), OpenMP {cores} threads"},
         "clocks": clk,
         "parity_checked": parity_checked,
+        "rows": rows,
     }
     print(json.dumps(line))
     dev.close()
@@ -544,6 +558,7 @@ def main():
     ap.add_argument("--k", type=int, default=24, help="log2 hypercube size of the T3 instance")
     ap.add_argument("--eq", default="virtual", choices=["virtual", "table"], help="how eq(w,.) is given to the prover (see the module docstring)")
     ap.add_argument("--cpu-k", type=int, default=24, help="log2 size of the bounded CPU sample")
+    ap.add_argument("--no-rows", dest="rows", action="store_false", help="N=1: skip the secondary rows (Z, TOWER, EQ-24, FOLD-24, C-26, RS-26, BATCH-26)")
     ap.add_argument("--no-weak", dest="weak", action="store_false", help="N>1: skip the weak-scaling measurement (T3-(k + log2 N))")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -103,3 +103,34 @@ class SymbolicSepticExtension:
 
     def to_exprs(self):
         return list(self.l)
+
+
+def terms_from_layer_json(layer, challenges):
+    """Import a real circuit's term table (BASELINE config #3): `Layer::main_sumcheck_expression_monomial_terms`
+    (gkr_iop/src/gkr/layer/zerocheck_layer.rs:86-207) dumped with the schema `ceno_b200/layer/1` (tests/golden/SCHEMA.md).
+    `challenges`: ext values by challenge id (ids 0, 1 = the global challenges, 2.. = the alpha powers).
+    Returns (terms in the cg_sumcheck_* layout, n_mles, degree): the scalar of every monomial is resolved against
+    `challenges`, equal products are merged (exact field addition: term order never changes a bit)."""
+    if layer.get("schema") != "ceno_b200/layer/1":
+        raise ValueError("unknown layer schema")
+    n_mles = layer["n_witin"] + layer["n_fixed"] + layer["n_structural_witin"]
+    poly = Poly()
+    for t in layer["monomial_terms"]:
+        sc = t["scalar"]
+        if isinstance(sc, dict):                       # Expression::Challenge(id, pow, scalar, offset)
+            c = challenges[sc["challenge"]]
+            c = (int(c[0]), int(c[1]))
+            v = ext(1)
+            for _ in range(sc.get("pow", 1)):
+                v = ext_mul(v, c)
+            if "scalar" in sc:
+                v = ext_mul(v, ext(*sc["scalar"]))
+            if "offset" in sc:
+                v = ext_add(v, ext(*sc["offset"]))
+        else:
+            v = ext(*sc)
+        prod = tuple(sorted(int(i) for i in t["product"]))
+        if any(i >= n_mles for i in prod):
+            raise ValueError("monomial references a witness id outside witin ++ fixed ++ structural")
+        poly._acc(prod, v)
+    return poly.terms(), n_mles, max(layer.get("max_expr_degree", 0) + 1, poly.degree())

@@ -92,6 +92,76 @@ class ZerocheckLayer:
         return LayerProof(rounds, evals), point.reshape(-1)
 
 
+class RotationPoints:
+    """gkr_iop/src/gkr/layer/sumcheck_layer.rs: RotationPoints { left, right, origin }"""
+
+    def __init__(self, left, right, origin):
+        self.left, self.right, self.origin = left, right, origin
+
+
+def get_rotation_points(point, cyclic_group_log2):
+    """BooleanHypercube::get_rotation_points (gkr_iop/src/gkr/booleanhypercube.rs:124-163).  point: [k, 2] u64."""
+    P = 0xFFFFFFFF00000001
+    pt = [(int(a), int(b)) for a, b in np.asarray(point, dtype=np.uint64).reshape(-1, 2)]
+    one_minus = lambda x: ((1 - x[0]) % P, (-x[1]) % P)
+    L = cyclic_group_log2
+    if L == 5:      # left (0, r0, r1, r2, r3, r5, ..), right (1, r0, 1 - r1, r2, r3, r5, ..)
+        left = [(0, 0)] + pt[:4] + pt[5:]
+        right = [(1, 0), pt[0], one_minus(pt[1])] + pt[2:4] + pt[5:]
+    elif L == 6:    # left (0, r0, .., r4, r6, ..), right (1, 1 - r0, r1, .., r4, r6, ..)
+        left = [(0, 0)] + pt[:5] + pt[6:]
+        right = [(1, 0), one_minus(pt[0]), pt[1]] + pt[2:5] + pt[6:]
+    else:
+        raise ValueError("BooleanHypercube supports 5 or 6 variables")
+    k = len(pt)
+    return np.array(left[:k], dtype=np.uint64), np.array(right[:k], dtype=np.uint64)
+
+
+def prove_rotation(dev, max_num_variables, rotation_cyclic_subgroup_size, rotation_cyclic_group_log2, wit, raw_rotation_exprs, rt,
+                   global_challenges, transcript, stream=None):
+    """prove_rotation (gkr_iop/src/gkr/layer/cpu/mod.rs:249-389): for every (source, target) witness pair prove
+    rotated(source) == target on the cyclic subgroup through
+        0 = sum_b sel(b) * sum_i alpha^i (rotated_i(b) - target_i(b)),
+    a degree-2 sumcheck over [rotated_1, target_1, ..., selector] (the expression of zerocheck_layer.rs:88-104), then turn the
+    evaluation of each rotated MLE into evaluations of its source at the left / right rotation points.
+    raw_rotation_exprs: [(source_wit_id, target_wit_id)].  Returns (LayerProof(rounds, evals [3n, 2]), RotationPoints)."""
+    from .expr import ext_mul
+    P = 0xFFFFFFFF00000001
+    n = len(raw_rotation_exprs)
+    eq = api.build_eq_x_r_vec(dev, rt, stream=stream)
+    rotated = [api.rotation_next_base_mle(dev, wit[src], rotation_cyclic_group_log2) for src, _ in raw_rotation_exprs]
+    selector = api.rotation_selector(dev, eq, rotation_cyclic_subgroup_size, rotation_cyclic_group_log2)
+    alphas = transcript.sample_and_append_challenge_pows(n, b"combine subset evals")     # challenge ids 2.. (global challenges are ids 0, 1)
+    mles, terms = [], []
+    for i, (_, tgt) in enumerate(raw_rotation_exprs):
+        mles += [rotated[i], wit[tgt]]
+        a = (int(alphas[i][0]), int(alphas[i][1]))
+        terms.append(([a[0], a[1]], [2 * n, 2 * i]))
+        terms.append(([(-a[0]) % P, (-a[1]) % P], [2 * n, 2 * i + 1]))
+    mles.append(selector)
+    rounds, evals, origin = api.IOPProverState.prove(dev, mles, terms, max_num_variables, 2, transcript=transcript, stream=stream)
+    origin = origin.reshape(-1, 2)
+    left, right = get_rotation_points(origin, rotation_cyclic_group_log2)
+    r = (int(origin[rotation_cyclic_group_log2 - 1][0]), int(origin[rotation_cyclic_group_log2 - 1][1]))
+    nrm = (r[0] * r[0] - 7 * r[1] * r[1]) % P
+    ni = pow(nrm, P - 2, P)
+    r_inv = (r[0] * ni % P, (-r[1]) * ni % P)
+    one_minus_r = ((1 - r[0]) % P, (-r[1]) % P)
+    out = []
+    for i, (src, _) in enumerate(raw_rotation_exprs):
+        rotated_eval, target_eval = (int(evals[2 * i][0]), int(evals[2 * i][1])), (int(evals[2 * i + 1][0]), int(evals[2 * i + 1][1]))
+        le = wit[src].evaluate(left.reshape(-1))
+        le = (int(le[0]), int(le[1]))
+        t = ext_mul(one_minus_r, le)
+        re = ext_mul(((rotated_eval[0] - t[0]) % P, (rotated_eval[1] - t[1]) % P), r_inv)     # get_rotation_right_eval_from_left
+        out += [le, re, target_eval]
+    out = np.array(out, dtype=np.uint64).reshape(-1, 2)
+    transcript.append_field_element_exts(out.reshape(-1))
+    for m in rotated + [selector, eq]:
+        m.free()
+    return LayerProof(rounds, out), RotationPoints(left, right, origin)
+
+
 class LinearLayer:
     @staticmethod
     def prove(dev, layer, wit, out_point, transcript):

@@ -421,6 +421,104 @@ def rotation_selector(eq, subgroup_size, log2):
     return out
 
 
+def get_rotation_points(point, log2):
+    """BooleanHypercube::get_rotation_points (gkr_iop/src/gkr/booleanhypercube.rs:124-163); point: list of ext tuples."""
+    from . import pyref as pr
+    om = lambda x: pr.esub(pr.ONE, x)
+    if log2 == 5:
+        left = [pr.ZERO] + point[:4] + point[5:]
+        right = [pr.ONE, point[0], om(point[1])] + point[2:4] + point[5:]
+    elif log2 == 6:
+        left = [pr.ZERO] + point[:5] + point[6:]
+        right = [pr.ONE, om(point[0]), point[1]] + point[2:5] + point[6:]
+    else:
+        raise ValueError("BooleanHypercube supports 5 or 6 variables")
+    return left[:len(point)], right[:len(point)]
+
+
+def _alpha_pows(transcript, n):
+    from . import pyref as pr
+    a = transcript.sample(b"combine subset evals")
+    a = (int(a[0]), int(a[1]))
+    out, cur = [], pr.ONE
+    for _ in range(n):
+        out.append(cur)
+        cur = pr.emul(cur, a)
+    return out
+
+
+def prove_rotation(max_num_variables, subgroup_size, log2, wit, raw_rotation_exprs, rt, transcript):
+    """prove_rotation (gkr_iop/src/gkr/layer/cpu/mod.rs:249-389) restated over this oracle's pieces.
+    wit: list of base-field evaluation vectors; raw_rotation_exprs: [(source_wit_id, target_wit_id)]; rt: k ext (u64 pairs).
+    Returns (round_evals, evals [3n ext tuples], (left, right, origin) points)."""
+    from . import pyref as pr
+    n = len(raw_rotation_exprs)
+    eq = build_eq_x_r_vec(rt)
+    rotated = [rotation_next_base_mle(wit[src], log2) for src, _ in raw_rotation_exprs]
+    selector = rotation_selector(eq, subgroup_size, log2)
+    alphas = _alpha_pows(transcript, n)
+    mles, terms = [], []
+    for i, (_, tgt) in enumerate(raw_rotation_exprs):
+        mles += [(rotated[i], False, max_num_variables), (wit[tgt], False, max_num_variables)]
+        a = alphas[i]
+        terms.append(([a[0], a[1]], [2 * n, 2 * i]))
+        terms.append(([(-a[0]) % pr.P, (-a[1]) % pr.P], [2 * n, 2 * i + 1]))
+    mles.append((selector, True, max_num_variables))
+    rounds, fin, chal = sumcheck_prove(mles, terms, max_num_variables, 2, transcript=transcript)
+    origin = [(int(c[0]), int(c[1])) for c in chal]
+    left, right = get_rotation_points(origin, log2)
+    r = origin[log2 - 1]
+    evals = []
+    for i, (src, _) in enumerate(raw_rotation_exprs):
+        rot_e, tgt_e = (int(fin[2 * i][0]), int(fin[2 * i][1])), (int(fin[2 * i + 1][0]), int(fin[2 * i + 1][1]))
+        le = mle_evaluate(wit[src], False, np.array(left, dtype=np.uint64).reshape(-1))
+        le = (int(le[0]), int(le[1]))
+        re = pr.emul(pr.esub(rot_e, pr.emul(pr.esub(pr.ONE, r), le)), pr.einv(r))
+        evals += [le, re, tgt_e]
+    transcript.append_ext(np.array(evals, dtype=np.uint64).reshape(-1))
+    return rounds, evals, (left, right, origin)
+
+
+def verify_rotation(max_num_variables, n, proof_rounds, evals, subgroup_size, log2, rt, transcript):
+    """verify_rotation (gkr_iop/src/gkr/layer/zerocheck_layer.rs:678-790): sumcheck of claim 0 and degree 2, then
+    sel(origin) * sum_i alpha_i ((1 - r) left_i + r right_i - target_i) == the sumcheck's final claim, with
+    sel(origin) = rotation_selector_eval (gkr_iop/src/utils.rs:78-102).  Returns (left, right, origin) or raises."""
+    from . import pyref as pr
+    assert len(evals) == 3 * n
+    alphas = _alpha_pows(transcript, n)
+    transcript.append_message(int(max_num_variables).to_bytes(8, "little"))
+    transcript.append_message(int(2).to_bytes(8, "little"))
+    claim, origin = pr.ZERO, []
+    for j in range(max_num_variables):
+        msg = [(int(e[0]), int(e[1])) for e in proof_rounds[j]]
+        transcript.append_ext(np.array(msg, dtype=np.uint64).reshape(-1))
+        r = transcript.sample(b"Internal round")
+        r = (int(r[0]), int(r[1]))
+        claim = pr.lagrange_eval([pr.esub(claim, msg[0])] + msg, r)
+        origin.append(r)
+    transcript.append_ext(np.array(evals, dtype=np.uint64).reshape(-1))
+    rtl = [(int(a), int(b)) for a, b in np.asarray(rt, dtype=np.uint64).reshape(-1, 2)]
+    group = [int(x) for x in bh_table(log2)][:subgroup_size]
+    oe, ie = pr.build_eq_x_r_vec(rtl[:log2]), pr.build_eq_x_r_vec(origin[:log2])
+    sel = pr.ZERO
+    for b in group:
+        sel = pr.eadd(sel, pr.emul(oe[b], ie[b]))
+    for x, y in zip(rtl[log2:], origin[log2:]):
+        xy = pr.emul(x, y)
+        sel = pr.emul(sel, pr.eadd(pr.esub(pr.esub(pr.eadd(xy, xy), x), y), pr.ONE))
+    r = origin[log2 - 1]
+    got = pr.ZERO
+    for i in range(n):
+        le, re, te = evals[3 * i], evals[3 * i + 1], evals[3 * i + 2]
+        rot = pr.eadd(pr.emul(pr.esub(pr.ONE, r), le), pr.emul(r, re))
+        got = pr.eadd(got, pr.emul(alphas[i], pr.esub(rot, te)))
+    got = pr.emul(got, sel)
+    if got != claim:
+        raise ValueError("rotation verify failed: claim mismatch")
+    left, right = get_rotation_points(origin, log2)
+    return left, right, origin
+
+
 # ------------------------------------------------------------------------------- NTT / RS-encode (a9, f-2)
 def two_adic_generator(bits):
     return int(lib().or_two_adic_generator(C.c_uint32(bits)))

@@ -562,6 +562,29 @@ def test_basefold_commit_and_batch_open_bit_exact(dev, shapes):
         b.free()
 
 
+@pytest.mark.parametrize("log2,subgroup,k,n_rot", [(5, 23, 7, 2), (5, 31, 5, 1), (6, 63, 9, 3), (5, 23, 16, 2)])
+def test_prove_rotation_bit_exact(dev, log2, subgroup, k, n_rot):
+    """f-3: prove_rotation end to end (gkr_iop/src/gkr/layer/cpu/mod.rs:249-389) — rotated MLEs + selector pre-passes, the
+    degree-2 sumcheck, left / right point evaluations — against the restatement (itself accepted by the restated
+    verify_rotation, tests/test_oracle_kat.py)."""
+    import ceno_b200 as cb
+    from ceno_b200 import gkr
+    n = 1 << k
+    src = [orc.fill_base(7000 + i, n) for i in range(n_rot)]
+    wit_h = src + [orc.rotation_next_base_mle(s, log2) for s in src]
+    exprs = [(i, n_rot + i) for i in range(n_rot)]
+    rt = orc.fill_ext(7100 + k, k)
+    rounds, evals, (left, right, origin) = orc.prove_rotation(k, subgroup, log2, wit_h, exprs, rt, orc.Transcript(b"rot"))
+    wit = [cb.MultilinearExtension.from_evaluations_vec(dev, k, w) for w in wit_h]
+    lp, pts = gkr.prove_rotation(dev, k, subgroup, log2, wit, exprs, rt, [], cb.StandInTranscript(b"rot"))
+    assert eq_np(lp.proof, rounds)
+    assert eq_np(lp.evals, np.array(evals, dtype=np.uint64))
+    assert eq_np(pts.left, np.array(left, dtype=np.uint64)) and eq_np(pts.right, np.array(right, dtype=np.uint64))
+    assert eq_np(pts.origin, np.array(origin, dtype=np.uint64))
+    for m in wit:
+        m.free()
+
+
 @pytest.mark.parametrize("case", ["default", "no_derive", "w_one", "w_zero"])
 def test_split_eq_claim_derived_rounds(dev, case):
     """Split-eq rounds >= 1 accumulate q(1) and the X^2 coefficient only and solve q(0) from the running claim

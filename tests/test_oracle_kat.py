@@ -579,3 +579,31 @@ def test_ecc_quark_detects_a_broken_witness():
     for b in range(1 << n):
         total = pr.eadd(total, pr.poly_eval(mles_p, tl, b))
     assert total != pr.ZERO
+
+
+# ------------------------------------------------------------------ prove_rotation (gkr_iop/src/gkr/layer/cpu/mod.rs:249-389)
+@pytest.mark.parametrize("log2,subgroup,k,n_rot", [(5, 23, 7, 2), (5, 31, 5, 1), (6, 63, 8, 3)])
+def test_kat_prove_rotation_is_accepted_by_verify_rotation(log2, subgroup, k, n_rot):
+    """The restated prover's output satisfies the restated verifier (zerocheck_layer.rs:678-790): the degree-2 sumcheck of
+    claim 0 chains to sel(origin) * sum_i alpha_i ((1 - r) left_i + r right_i - target_i), the right evaluation derived from
+    the left one equals the direct evaluation at the right point (the reference's debug assertion, cpu/mod.rs:350-362), and a
+    witness violating the rotation on the subgroup is rejected."""
+    import random
+    rng = random.Random(log2 * 100 + k)
+    n = 1 << k
+    src = [orc.fill_base(7000 + i, n) for i in range(n_rot)]
+    wit = src + [orc.rotation_next_base_mle(s, log2) for s in src]
+    exprs = [(i, n_rot + i) for i in range(n_rot)]
+    rt = orc.fill_ext(7100 + k, k)
+    rounds, evals, (left, right, origin) = orc.prove_rotation(k, subgroup, log2, wit, exprs, rt, orc.Transcript(b"rot"))
+    l2, r2, o2 = orc.verify_rotation(k, n_rot, rounds, evals, subgroup, log2, rt, orc.Transcript(b"rot"))
+    assert (l2, r2, o2) == (left, right, origin)
+    for i, (s, _) in enumerate(exprs):
+        direct = orc.mle_evaluate(wit[s], False, np.array(right, dtype=np.uint64).reshape(-1))
+        assert (int(direct[0]), int(direct[1])) == evals[3 * i + 1]
+    # break the relation at a selected position (group element X^1 = index 2 of the first chunk)
+    bad = [w.copy() for w in wit]
+    bad[n_rot][2] = (int(bad[n_rot][2]) + 1) % P
+    rounds_b, evals_b, _ = orc.prove_rotation(k, subgroup, log2, bad, exprs, rt, orc.Transcript(b"rot"))
+    with pytest.raises(ValueError):
+        orc.verify_rotation(k, n_rot, rounds_b, evals_b, subgroup, log2, rt, orc.Transcript(b"rot"))
