@@ -464,6 +464,48 @@ def gpu_arm_sharded(args, rank, world, local_rank):
                 "note": f"T3-{kw} sliced over {world} GPUs (per-GPU work equal to the 1-GPU T3-{k} run), host transcript"}
         wfree()
 
+    # ---- BASELINE config #5 on N GPUs: 64 base columns x 2^20 rows, row-sharded -> Basefold commitment root
+    config5 = None
+    if getattr(args, "config5", True):
+        try:
+            import ctypes as C
+            from ceno_b200 import dist as cdist
+            c5_w, c5_log, c5_rate = 64, 20, 1
+            vals = synth.fill_base(0x9052, 8 * 8 + 22 + 8)
+            cb.poseidon2_set_params(dev, vals[:64].reshape(8, 8), vals[64:86], vals[86:94], 0)
+            rows_local = (1 << c5_log) // world
+            loc = np.stack([synth.fill_base(4242 + c, rows_local, start=rank * rows_local) for c in range(c5_w)])
+            t_loc = torch.from_numpy(loc.view(np.int64)).cuda()
+
+            def c5_step():
+                root, code_local, tree = cdist.commit_sharded(dev, t_loc, c5_log, c5_rate, rank, world, torch, dist)
+                tree.free()
+                return root
+            root_n = c5_step()
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            e0.record()
+            for _ in range(reps):
+                root_n = c5_step()
+            e1.record()
+            torch.cuda.synchronize()
+            tt = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            config5 = {"workload": "BASELINE #5: 2^26-element batch = 64 base columns x 2^20 rows, row-sharded; RS-encode (rate 1/2) + Poseidon2 Merkle commit",
+                       "n_gpus": world, "ms": float(tt.item()), "root": [int(x) for x in root_n],
+                       "exchange": "NCCL all-to-all rows->columns (RS-encode per column), all-to-all columns->rows (leaf hash per row range), all-gather of subtree roots",
+                       "note": "placeholder Poseidon2 constants; max over ranks, CUDA events"}
+            if rank == 0:   # parity: the single-device commitment of the same matrix on rank 0
+                full = np.concatenate([synth.fill_base(4242 + c, 1 << c5_log) for c in range(c5_w)])
+                buf = dev.to_device(full)
+                cm = cb.BasefoldCommitment(dev, buf, c5_w, c5_log, cb.BasefoldParams(rate_log=c5_rate))
+                config5["root_equals_single_gpu_commit"] = bool([int(x) for x in cm.root] == config5["root"])
+                cm.free(); buf.free()
+        except Exception as e:  # noqa: BLE001
+            config5 = {"error": repr(e)}
+
     if rank == 0:
         n = 1 << k
         ops = 99 * n
@@ -513,6 +555,7 @@ def gpu_arm_sharded(args, rank, world, local_rank):
             "cpu_baseline": {"value": cpu_val, "unit": "Gfield-ops/s", "cores": cores, "kind": "port", "ms": t_cpu * 1e3,
                              "sample": f"T3-{args.cpu_k} full sumcheck, one run on rank 0's host; oracle port with the reference's decomposition, OpenMP {cores} threads"},
             "weak_scaling": weak,
+            "config5": config5,
             "clocks": clk,
             "parity_checked": parity_checked,
         }

@@ -116,3 +116,84 @@ class GpuLocalProver:
 
     def close(self):
         self.st.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config #5 on N GPUs: Basefold commit of a row-sharded witness batch.
+# RS-encoding is per column and global over the rows, the leaf hash is per row and global over the columns, so the
+# commit has two REAL exchange steps (NCCL all-to-all over NVLink — this is where a collective belongs) and one tiny one:
+#   rows -> columns : every rank receives whole columns (a contiguous block of width/N of them) for the transform;
+#   columns -> rows : every rank receives its contiguous range of codeword rows (bit-reversed order, the leaf order) of
+#                     ALL columns — a column-major local matrix, exactly what cg_merkle_commit hashes;
+#   roots           : all-gather of the N subtree roots (32 bytes each); every rank finishes the top log2 N levels.
+# A contiguous aligned range of leaves is a subtree of the global tree, so the root equals the single-GPU commitment's.
+def sharded_commit_layout(width, log_n, rate_log, world):
+    """Shapes of the two exchanges (pure arithmetic; covered by the CPU tests)."""
+    assert width % world == 0 and (1 << log_n) % world == 0
+    rows_local, cols_local, code_rows = (1 << log_n) // world, width // world, 1 << (log_n + rate_log)
+    return {"rows_local": rows_local, "cols_local": cols_local, "code_rows": code_rows, "code_rows_local": code_rows // world}
+
+
+def rows_to_columns(t, world, torch, dist=None):
+    """t: [width, rows_local] (this rank's rows of every column, column-major).  Returns [cols_local, rows] — this rank's
+    whole columns [rank * cols_local, (rank + 1) * cols_local)."""
+    width, rows_local = t.shape
+    cols_local = width // world
+    recv = torch.empty_like(t)
+    if dist is None or world == 1:
+        recv.copy_(t)
+    else:
+        dist.all_to_all_single(recv.view(-1), t.contiguous().view(-1))          # chunk d = columns block d -> rank d
+    return recv.view(world, cols_local, rows_local).permute(1, 0, 2).contiguous().view(cols_local, world * rows_local)
+
+
+def columns_to_rows(code, world, torch, dist=None):
+    """code: [cols_local, code_rows] (whole encoded columns).  Returns [width, code_rows_local]: every column's rows
+    [rank * code_rows_local, ...), column c = source_rank * cols_local + local index (the natural column order)."""
+    cols_local, code_rows = code.shape
+    send = code.view(cols_local, world, code_rows // world).permute(1, 0, 2).contiguous()
+    recv = torch.empty_like(send)
+    if dist is None or world == 1:
+        recv.copy_(send)
+    else:
+        dist.all_to_all_single(recv.view(-1), send.view(-1))
+    return recv.view(world * cols_local, code_rows // world)
+
+
+def commit_sharded(dev, msg_local, log_n, rate_log, rank, world, torch, dist, stream=None):
+    """msg_local: torch int64 CUDA tensor [width, 2^log_n / world] — this rank's contiguous row range of every witness
+    column (canonical Goldilocks values).  Returns (root[4] np.uint64 — identical on every rank and equal to the
+    single-GPU commitment root, code_local tensor, tree DeviceBuffer of the local subtree)."""
+    import ctypes as C
+    from . import api
+    width = msg_local.shape[0]
+    lay = sharded_commit_layout(width, log_n, rate_log, world)
+    cols = rows_to_columns(msg_local, world, torch, dist)                                      # [cols_local, 2^log_n]
+    code = torch.empty((lay["cols_local"], lay["code_rows"]), dtype=torch.int64, device=msg_local.device)
+    torch.cuda.current_stream().synchronize()
+    dev.check(dev.lib.cg_rs_encode(dev.ctx, C.c_void_p(cols.data_ptr()), lay["cols_local"], log_n, rate_log, C.c_void_p(code.data_ptr()),
+                                   api.NTT_BITREV, C.c_void_p(stream) if stream else None))
+    dev.check(dev.lib.cg_stream_sync(dev.ctx, C.c_void_p(stream) if stream else None))
+    code_local = columns_to_rows(code, world, torch, dist)                                     # [width, code_rows_local], column-major
+    torch.cuda.current_stream().synchronize()
+    h_loc = lay["code_rows_local"]
+    tree = dev.alloc(32 * (2 * h_loc - 1))
+    sub = np.zeros(4, np.uint64)
+    dev.check(dev.lib.cg_merkle_commit(dev.ctx, C.c_void_p(code_local.data_ptr()), width, h_loc, 1, C.c_void_p(tree.ptr),
+                                       sub.ctypes.data_as(C.c_void_p), C.c_void_p(stream) if stream else None))
+    # top of the tree: all-gather the subtree roots, compress pairwise on the device
+    roots = torch.from_numpy(sub.view(np.int64).copy()).to(msg_local.device)
+    if world > 1:
+        allr = [torch.empty_like(roots) for _ in range(world)]
+        dist.all_gather(allr, roots)
+        level = torch.stack(allr)                                                              # [world, 4]
+    else:
+        level = roots.view(1, 4)
+    while level.shape[0] > 1:
+        states = level.view(-1, 8).contiguous()                                                # left || right
+        torch.cuda.current_stream().synchronize()
+        dev.check(dev.lib.cg_poseidon2_permute(dev.ctx, C.c_void_p(states.data_ptr()), states.shape[0], C.c_void_p(stream) if stream else None))
+        dev.check(dev.lib.cg_stream_sync(dev.ctx, C.c_void_p(stream) if stream else None))
+        level = states[:, :4].contiguous()
+    root = level.view(-1).cpu().numpy().view(np.uint64).copy()
+    return root, code_local, tree

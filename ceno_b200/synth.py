@@ -24,7 +24,8 @@ def fill_ext(seed, n, out=None, chunk=1 << 22, start=0):
     return out
 
 
-def fill_base(seed, n):
+def fill_base(seed, n, start=0):
+    """n base elements start .. start+n-1 of the stream `seed` (element i <- splitmix64(seed + 2i) mod p)."""
     with np.errstate(over="ignore"):
-        v = _splitmix64(np.arange(0, 2 * n, 2, dtype=np.uint64) + np.uint64(seed))
+        v = _splitmix64(np.arange(2 * start, 2 * (start + n), 2, dtype=np.uint64) + np.uint64(seed))
     return np.where(v >= P, v - P, v)

@@ -76,3 +76,27 @@ def test_sharded_protocol_matches_monolithic_oracle(world, k):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, True) for r in range(world)]
+
+
+def test_sharded_commit_exchange_layout_world_1_2_4():
+    """BASELINE config #5 sharding (rows -> columns -> rows): composing the two exchanges of every rank reproduces the
+    single-device column-major matrices (checked with the exchanges emulated in-process, no GPU, no process group)."""
+    import torch
+    from ceno_b200 import dist as cdist
+    width, log_n, rate_log = 8, 5, 1
+    full = torch.arange(width * (1 << log_n), dtype=torch.int64).view(width, 1 << log_n)
+    for world in (1, 2, 4):
+        lay = cdist.sharded_commit_layout(width, log_n, rate_log, world)
+        locs = [full[:, r * lay["rows_local"]:(r + 1) * lay["rows_local"]].contiguous() for r in range(world)]
+        # emulate all_to_all_single: chunk d of rank s goes to slot s of rank d
+        sends = [t.view(world, -1) for t in locs]
+        recvs = [torch.stack([sends[s][d] for s in range(world)]).view(width, lay["rows_local"]) for d in range(world)]
+        cols = [r.view(world, lay["cols_local"], lay["rows_local"]).permute(1, 0, 2).contiguous().view(lay["cols_local"], -1) for r in recvs]
+        for r in range(world):
+            assert torch.equal(cols[r], full[r * lay["cols_local"]:(r + 1) * lay["cols_local"]])
+        code = [torch.cat([c * 1000, c * 1000 + 1], dim=1) for c in cols]                     # stand-in "codeword" of the right shape
+        sends2 = [c.view(lay["cols_local"], world, lay["code_rows_local"]).permute(1, 0, 2).contiguous() for c in code]
+        for d in range(world):
+            got = torch.stack([sends2[s][d] for s in range(world)]).view(width, lay["code_rows_local"])
+            want = torch.cat(code, dim=0)[:, d * lay["code_rows_local"]:(d + 1) * lay["code_rows_local"]]
+            assert torch.equal(got, want)

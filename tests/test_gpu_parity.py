@@ -833,6 +833,61 @@ def test_sharded_virtual_eq_multi_gpu_bit_exact():
     assert sorted(res) == [(r, True) for r in range(world)]
 
 
+def _dist_commit_worker(rank, world, port, q):
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import ceno_b200 as cb
+    from ceno_b200 import api
+    from ceno_b200 import dist as cdist
+    from oracle import basefold as bf
+    dev = cb.Device(rank)
+    p2 = orc.p2_params(seed=5)
+    api.poseidon2_set_params(dev, [[int(p2.ext_rc[r][i]) for i in range(8)] for r in range(8)], [int(x) for x in p2.int_rc], [int(x) for x in p2.diag], 0)
+    width, log_n, rate_log = 8, 10, 1
+    cols = [orc.fill_base(8800 + c, 1 << log_n) for c in range(width)]
+    rows_local = (1 << log_n) // world
+    loc = np.stack([c[rank * rows_local:(rank + 1) * rows_local] for c in cols]).view(np.int64)
+    t = torch.from_numpy(loc.copy()).cuda()
+    root, code_local, tree = cdist.commit_sharded(dev, t, log_n, rate_log, rank, world, torch, dist)
+    want = bf.commit(p2, bf.Params(rate_log=rate_log), cols, log_n)
+    ok = [int(x) for x in root] == want["root"]
+    # the local code rows are the oracle's codeword rows of this rank's range (bit-reversed order)
+    hl = (1 << (log_n + rate_log)) // world
+    got_rows = code_local.cpu().numpy().view(np.uint64).T
+    ok = ok and [[int(v) for v in r] for r in got_rows] == want["rows"][rank * hl:(rank + 1) * hl]
+    tree.free()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_sharded_commit_multi_gpu_bit_exact():
+    """BASELINE config #5 sharding: row-sharded witness -> all-to-all -> per-column RS-encode -> all-to-all -> row-range leaf hash
+    -> all-gather of subtree roots; the root equals the single-device / oracle commitment root."""
+    import torch
+    import torch.multiprocessing as mp
+    world = 1
+    while world * 2 <= min(torch.cuda.device_count(), 8):
+        world *= 2
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dist_commit_worker, args=(r, world, 29667, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, True) for r in range(world)]
+
+
 def test_sharded_sumcheck_multi_gpu_bit_exact():
     import torch
     import torch.multiprocessing as mp
