@@ -5,5 +5,5 @@ this package is the thin host-side mirror of the reference's interface used by t
 """
 from .api import (CenoB200Error, ChipScheduler, EccQuarkProver, ChipTask, Comm, Device, DeviceBuffer, EqPolynomial, IOPProverState, MultilinearExtension, SelectorType,  # noqa: F401
                   StandInTranscript, Stream, TowerProver, TowerProverSpec, build_eq_x_r_vec, prove_sharded, wit_infer_by_monomial_expr,
-                  BasefoldCommitment, BasefoldParams, basefold_batch_open, poseidon2_set_params)
+                  BasefoldCommitment, BasefoldParams, basefold_batch_open, poseidon2_set_params, VirtualTowerSpec)
 from . import chip, expr, gkr  # noqa: E402,F401

@@ -453,7 +453,40 @@ class TowerProverSpec:
         self.leaves, self.num_vars, self.is_logup = leaves, num_vars, is_logup
 
 
+class VirtualTowerSpec:
+    """A tower spec given by its RECORD MLEs (GpuVirtualInterleavedExt, ceno_zkvm/src/scheme/gpu/mod.rs:2195-2268): the
+    interleaved fan-in leaves are never materialised.  Product: records = the read / write set (default 1).  Logup:
+    records = denominators (default = the challenge alpha), numerators = None for all-one numerators."""
+
+    def __init__(self, records, num_instances, default, is_logup, numerators=None, numerator_default=(1, 0)):
+        self.records, self.num_instances, self.default, self.is_logup = list(records), num_instances, default, is_logup
+        self.numerators, self.numerator_default = (list(numerators) if numerators else []), numerator_default
+
+
 class TowerProver:
+    @classmethod
+    def from_records(cls, dev, vspecs, stream=None):
+        """cg_tower_build_virtual: towers over virtual leaf layers."""
+        self = cls.__new__(cls)
+        self.dev = dev
+        arr = (_lib.CgTowerVSpec * len(vspecs))()
+        keep = []
+
+        def group(g, recs, ninst, default):
+            descs = (_lib.CgMleDesc * max(len(recs), 1))(*[m.desc() for m in recs])
+            keep.append(descs)
+            g.records = C.cast(descs, C.c_void_p) if recs else None
+            g.n_records, g.num_instances = len(recs), ninst
+            g.default_ext[0], g.default_ext[1] = int(default[0]), int(default[1])
+        for i, v in enumerate(vspecs):
+            group(arr[i].q, v.records, v.num_instances, v.default)
+            group(arr[i].p, v.numerators, v.num_instances, v.numerator_default)
+            arr[i].is_logup = 1 if v.is_logup else 0
+        self.h = C.c_void_p()
+        dev.check(dev.lib.cg_tower_build_virtual(dev.ctx, arr, len(vspecs), C.c_void_p(stream) if stream else None, C.byref(self.h)))
+        self.specs, self._keep = vspecs, keep
+        return self
+
     def __init__(self, dev, specs, stream=None):
         self.dev = dev
         arr = (_lib.CgTowerSpec * len(specs))()

@@ -747,6 +747,7 @@ struct cg_sumcheck {
     ext_t pending_r;
     const ext_t* pending_r_ptr = nullptr;   // device challenger: challenge lives on the device
     std::vector<MleState> mles;
+    std::vector<const VirtLeaf*> virt;   // per MLE: its ORIGINAL input is a virtual tower leaf array (null / empty: a plain array)
     TowerLayout tl;
     VeqState veq;
     // device state
@@ -1322,8 +1323,15 @@ static int launch_tower(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& 
     a.r = sc->pending_r;
     a.r_ptr = sc->pending_r_ptr;
     a.out = ro;
+    bool any_virt = false;           // virtual tower leaves: only a launch that reads the original inputs sees them
+    if (src == 0 && !sc->virt.empty()) {
+        for (int p = 0; p < a.n_prod; p++)
+            for (int z = 0; z < 2; z++) { a.virt[1 + 2 * p + z] = sc->virt[tl.prod[2 * p + z]]; any_virt |= a.virt[1 + 2 * p + z] != nullptr; }
+        for (int l = 0; l < a.n_logup; l++)
+            for (int z = 0; z < 4; z++) { a.virt[1 + 2 * a.n_prod + 4 * l + z] = sc->virt[tl.lk[4 * l + z]]; any_virt |= a.virt[1 + 2 * a.n_prod + 4 * l + z] != nullptr; }
+    }
     const bool canon = (src == 0);   // reading caller-provided buffers
-    const bool simple = a.n_prod == 1 && a.n_logup == 0 && a.alpha_one;
+    const bool simple = a.n_prod == 1 && a.n_logup == 0 && a.alpha_one && !any_virt;
     // launch shape: threads x resident blocks per SM (one persistent wave, grid-stride loop)
     static const int cfg = []() { const char* e = getenv("CG_TOWER_CFG"); return e ? atoi(e) : 0; }();
     const int threads = simple ? (cfg == 1 || cfg == 2 ? 128 : (cfg == 3 ? 192 : 256)) : 256;
@@ -1342,7 +1350,10 @@ static int launch_tower(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& 
         else if (cfg == 3) CG_TOWER_LAUNCH2(F, CN, true, 192, 3);                \
         else CG_TOWER_LAUNCH2(F, CN, true, 256, 2);                              \
     } while (0)
-    if (fold) { if (canon) CG_TOWER_LAUNCH(true, true); else CG_TOWER_LAUNCH(true, false); }
+    if (any_virt) {
+        if (fold) tower_round_kernel<true, true, false, 256, 2, true><<<grid, 256, 0, sc->stream>>>(a);
+        else tower_round_kernel<false, true, false, 256, 2, true><<<grid, 256, 0, sc->stream>>>(a);
+    } else if (fold) { if (canon) CG_TOWER_LAUNCH(true, true); else CG_TOWER_LAUNCH(true, false); }
     else { if (canon) CG_TOWER_LAUNCH(false, true); else CG_TOWER_LAUNCH(false, false); }
 #undef CG_TOWER_LAUNCH
 #undef CG_TOWER_LAUNCH2
@@ -1559,6 +1570,8 @@ static bool tail_eligible(const cg_sumcheck* sc) {
     const uint64_t cur = 1ULL << (sc->num_vars - sc->folds);
     const uint64_t n_loc = sc->pending ? cur / 2 : cur;
     if (n_loc < 2) return false;
+    if (sc->folds == 0)                                // virtual tower leaves can only be read by the streaming kernels
+        for (const VirtLeaf* v : sc->virt) if (v) return false;
     const bool sharded = sc->comm && sc->comm->nranks > 1;
     if (sharded && !sc->extra_rounds) return false;   // step API with a comm: per-round exchange only
     const size_t n_slots = 1 + sc->tl.prod.size() + sc->tl.lk.size();
@@ -2246,6 +2259,8 @@ struct TowerSpecState {
     std::vector<const ext_t*> layer; // layer[l] -> base of [a|b] or [p1|p2|q1|q2] with arrays of 2^l ext
     const ext_t* leaves[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ones = false;               // logup numerators implicit ones
+    bool virt = false;               // the leaf layer is described, not stored (cg_tower_build_virtual)
+    const VirtLeaf* d_virt[4] = {nullptr, nullptr, nullptr, nullptr};   // device descriptions of the leaf arrays
 };
 struct cg_tower {
     cg_ctx* ctx = nullptr;
@@ -2268,6 +2283,51 @@ static const ext_t* tower_arr(const TowerSpecState& sp, uint32_t l, uint32_t z) 
         return sp.leaves[z];
     }
     return sp.layer[l] + ((uint64_t)z << l);
+}
+// upper layers of one spec (infer_tower_product_witness / infer_tower_logup_witness, ceno_zkvm/src/scheme/utils.rs:488-659):
+// sp.leaves (or sp.d_virt for a virtual leaf layer), sp.layers, sp.ones are set; allocates and fills sp.layer[]
+static int tower_build_spec(cg_tower* tw, TowerSpecState& sp) {
+    cg_ctx* c = tw->ctx;
+    cudaStream_t st = tw->stream;
+    sp.layer.assign(sp.layers, nullptr);
+    const uint32_t arrs = sp.is_logup ? 4 : 2;
+    // upper layers l = layers-2 .. 0, one pooled block: sum_l arrs * 2^l ext
+    const uint64_t top = sp.layers - 1;   // leaf layer index; arrays there have 2^top ext
+    void* blk = nullptr;
+    const bool ones_arrays = sp.ones && !sp.virt;   // materialised all-one numerators (a virtual spec reads them as "no p arrays")
+    const uint64_t total = (uint64_t)arrs * ((1ULL << top) - 1) + (ones_arrays ? (2ULL << top) : 0);
+    if (total) {
+        CHK(tmp_alloc(c, sizeof(ext_t) * total, &blk, st));
+        tw->owned.push_back(blk);
+    }
+    ext_t* base = (ext_t*)blk;
+    for (uint32_t l = 0; l < top; l++) { sp.layer[l] = base; base += (uint64_t)arrs << l; }
+    if (ones_arrays) {   // input-layer numerators materialised as ones (utils.rs:556-577)
+        sp.layer[top] = base;   // only arrays 0,1 live here; q1,q2 stay in the caller's buffers
+        fill_ext_kernel<<<grid_for(c, 2ULL << top), CG_THREADS, 0, st>>>(base, 2ULL << top, ext_t{1, 0});
+        LAUNCHED(c);
+    }
+    for (int32_t l = (int32_t)top - 1; l >= 0; l--) {
+        const uint64_t n = 2ULL << l;   // points combined = length of layer l+1 arrays
+        ext_t* dst = (ext_t*)sp.layer[l];
+        const bool from_leaves = ((uint32_t)l + 1 == top);
+        if (from_leaves && sp.virt) {
+            if (!sp.is_logup) tower_prod_layer_virt_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, st>>>(sp.d_virt[0], sp.d_virt[1], n, dst);
+            else tower_logup_layer_virt_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, st>>>(sp.d_virt[0], sp.d_virt[1], sp.d_virt[2], sp.d_virt[3], n, dst, dst + n);
+        } else if (!sp.is_logup) {
+            tower_prod_layer_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, st>>>(tower_arr(sp, l + 1, 0), tower_arr(sp, l + 1, 1), n, dst, from_leaves);
+        } else {
+            const bool implicit_ones = from_leaves && sp.ones;
+            tower_logup_layer_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, st>>>(
+                implicit_ones ? nullptr : tower_arr(sp, l + 1, 0), implicit_ones ? nullptr : tower_arr(sp, l + 1, 1),
+                tower_arr(sp, l + 1, 2), tower_arr(sp, l + 1, 3), n, dst, dst + n, from_leaves);
+        }
+        LAUNCHED(c);
+        if (cudaGetLastError() != cudaSuccess) return set_err(c, CG_ERR_CUDA, "tower layer kernel launch failed");
+    }
+    if (sp.layers - 1 > tw->max_round) tw->max_round = sp.layers - 1;
+    if (sp.is_logup) tw->n_logup++; else tw->n_prod++;
+    return CG_OK;
 }
 CG_EXPORT int cg_tower_build(cg_ctx* c, const cg_tower_spec* specs, uint32_t n_specs, cg_stream s, cg_tower** out) {
     if (!c || !specs || !out || n_specs == 0) return set_err(c, CG_ERR_INVALID, "cg_tower_build: bad argument");
@@ -2293,42 +2353,8 @@ CG_EXPORT int cg_tower_build(cg_ctx* c, const cg_tower_spec* specs, uint32_t n_s
                 rc = set_err(c, CG_ERR_INVALID, "tower spec: missing leaf pointer");
                 break;
             }
-            sp.layer.assign(sp.layers, nullptr);
-            const uint32_t arrs = sp.is_logup ? 4 : 2;
-            // upper layers l = layers-2 .. 0, one pooled block: sum_l arrs * 2^l ext
-            const uint64_t top = sp.layers - 1;   // leaf layer index; arrays there have 2^top ext
-            void* blk = nullptr;
-            const uint64_t total = (uint64_t)arrs * ((1ULL << top) - 1) + (sp.ones ? (2ULL << top) : 0);
-            if (total) {
-                rc = tmp_alloc(c, sizeof(ext_t) * total, &blk, st);
-                if (rc != CG_OK) break;
-                tw->owned.push_back(blk);
-            }
-            ext_t* base = (ext_t*)blk;
-            for (uint32_t l = 0; l < top; l++) { sp.layer[l] = base; base += (uint64_t)arrs << l; }
-            if (sp.ones) {   // input-layer numerators materialised as ones (utils.rs:556-577)
-                sp.layer[top] = base;   // only arrays 0,1 live here; q1,q2 stay in the caller's buffers
-                fill_ext_kernel<<<grid_for(c, 2ULL << top), CG_THREADS, 0, st>>>(base, 2ULL << top, ext_t{1, 0});
-                LAUNCHED(c);
-            }
-            for (int32_t l = (int32_t)top - 1; l >= 0 && rc == CG_OK; l--) {
-                const uint64_t n = 2ULL << l;   // points combined = length of layer l+1 arrays
-                ext_t* dst = (ext_t*)sp.layer[l];
-                const bool from_leaves = ((uint32_t)l + 1 == top);
-                if (!sp.is_logup) {
-                    tower_prod_layer_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, st>>>(tower_arr(sp, l + 1, 0), tower_arr(sp, l + 1, 1), n, dst, from_leaves);
-                } else {
-                    const bool implicit_ones = from_leaves && sp.ones;
-                    tower_logup_layer_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, st>>>(
-                        implicit_ones ? nullptr : tower_arr(sp, l + 1, 0), implicit_ones ? nullptr : tower_arr(sp, l + 1, 1),
-                        tower_arr(sp, l + 1, 2), tower_arr(sp, l + 1, 3), n, dst, dst + n, from_leaves);
-                }
-                LAUNCHED(c);
-                if (cudaGetLastError() != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "tower layer kernel launch failed");
-            }
-            if (sp.layers - 1 > tw->max_round) tw->max_round = sp.layers - 1;
-            if (sp.is_logup) tw->n_logup++; else tw->n_prod++;
-            tw->specs.push_back(std::move(sp));
+            rc = tower_build_spec(tw, sp);
+            if (rc == CG_OK) tw->specs.push_back(std::move(sp));
         }
     if (rc != CG_OK) { cg_tower_destroy(tw); return rc; }
     *out = tw;
@@ -2390,6 +2416,120 @@ CG_EXPORT int cg_tower_interleave(cg_ctx* c, const cg_mle_desc* mles, uint32_t n
     tmp_free(d_ptrs, st);
     tmp_free(d_ext, st);
     return rc;
+}
+// ---- virtual leaf layers: the reference's GpuVirtualInterleavedExt (ceno_zkvm/src/scheme/gpu/mod.rs:2195-2268, builders
+// build_prod_tower_from_virtual_ext_batch / build_logup_tower_from_virtual_ext_batch :2365-2402).  A spec is given by its RECORD
+// MLEs; the interleaved fan-in leaves (2^ceil_log2(R) times the rows — 2^33 ext for keccak's 1094 lookup records at 2^22 rows)
+// exist only as descriptions read by the first build level and by rounds 0 / 1 of the leaf-layer sumcheck.
+static int make_virt_limbs(cg_tower* tw, const cg_tower_vgroup& g, const VirtLeaf** d_out /*[2]*/, uint64_t* out_len) {
+    cg_ctx* c = tw->ctx;
+    cudaStream_t st = tw->stream;
+    VirtLeaf h[2];
+    memset(h, 0, sizeof(h));
+    uint64_t np2 = 1;
+    while (np2 < g.num_instances) np2 <<= 1;
+    if (np2 < 2) np2 = 2;
+    const uint32_t l2m = g.n_records ? ceil_log2_u64(g.n_records) : 0;
+    const uint64_t per_fanin_len = np2 / 2 ? np2 / 2 : 1;
+    *out_len = cg_tower_interleave_out_len(g.n_records ? g.n_records : 1, g.num_instances, 2);
+    const uint64_t n_inst_out = *out_len >> l2m;
+    void *d_ptrs = nullptr, *d_ext = nullptr;
+    uint64_t mle_len = 0;
+    if (g.n_records) {
+        std::vector<const void*> ptrs(g.n_records);
+        std::vector<uint32_t> ext(g.n_records);
+        mle_len = g.records[0].len;
+        for (uint32_t i = 0; i < g.n_records; i++) {
+            const cg_mle_desc& m = g.records[i];
+            if (m.is_ext > CG_MLE_EXT || !m.dptr) return set_err(c, CG_ERR_INVALID, "cg_tower_build_virtual: dense record MLEs only");
+            if (m.len != mle_len || m.len > np2) return set_err(c, CG_ERR_INVALID, "cg_tower_build_virtual: records must share one length <= the padded instance count (utils.rs:411-414)");
+            if ((uintptr_t)m.dptr & (m.is_ext ? 15 : 7)) return set_err(c, CG_ERR_INVALID, "cg_tower_build_virtual: misaligned record pointer");
+            ptrs[i] = m.dptr;
+            ext[i] = m.is_ext;
+        }
+        CHK(upload_small(c, ptrs.data(), sizeof(void*) * g.n_records, &d_ptrs, st));
+        tw->owned.push_back(d_ptrs);
+        CHK(upload_small(c, ext.data(), sizeof(uint32_t) * g.n_records, &d_ext, st));
+        tw->owned.push_back(d_ext);
+    }
+    for (int limb = 0; limb < 2; limb++) {
+        VirtLeaf& v = h[limb];
+        v.ptrs = (const void* const*)d_ptrs;
+        v.is_ext = (const uint32_t*)d_ext;
+        v.n_records = g.n_records;
+        v.l2m = l2m;
+        v.row_offset = per_fanin_len * limb;
+        v.def = ext_t{g.default_ext[0] % GL_P, g.default_ext[1] % GL_P};
+        // row counts exactly as interleaving_mles_to_mles takes them (utils.rs:433-456; tower_interleave_kernel)
+        const uint64_t start = v.row_offset;
+        if (g.n_records && start < g.num_instances) {
+            const uint64_t valid = std::min<uint64_t>(per_fanin_len, g.num_instances - start);
+            uint64_t ce = valid, cb = per_fanin_len;
+            if (start + ce > mle_len) ce = 0;
+            if (start + cb > mle_len) cb = 0;
+            v.cnt_ext = std::min(ce, n_inst_out);
+            v.cnt_base = std::min(cb, n_inst_out);
+        }
+    }
+    void* d_v = nullptr;
+    CHK(upload_small(c, h, sizeof(h), &d_v, st));
+    tw->owned.push_back(d_v);
+    d_out[0] = (const VirtLeaf*)d_v;
+    d_out[1] = (const VirtLeaf*)d_v + 1;
+    return CG_OK;
+}
+CG_EXPORT int cg_tower_build_virtual(cg_ctx* c, const cg_tower_vspec* specs, uint32_t n_specs, cg_stream s, cg_tower** out) {
+    if (!c || !specs || !out || n_specs == 0) return set_err(c, CG_ERR_INVALID, "cg_tower_build_virtual: bad argument");
+    cudaStream_t st = S(c, s);
+    CU(c, cudaSetDevice(c->device));
+    uint32_t n_prod = 0, n_logup = 0;
+    for (uint32_t i = 0; i < n_specs; i++) (specs[i].is_logup ? n_logup : n_prod)++;
+    if (n_prod > CG_TOWER_MAX_PROD || n_logup > CG_TOWER_MAX_LOGUP)
+        return set_err(c, CG_ERR_UNSUPPORTED, "cg_tower_build_virtual: at most 8 product and 4 logup specs (materialise the leaves with cg_tower_interleave beyond that)");
+    cg_tower* tw = new cg_tower();
+    tw->ctx = c;
+    tw->stream = st;
+    int rc = CG_OK;
+    for (int pass = 0; pass < 2 && rc == CG_OK; pass++)
+        for (uint32_t i = 0; i < n_specs && rc == CG_OK; i++) {
+            const cg_tower_vspec& in = specs[i];
+            if ((in.is_logup != 0) != (pass == 1)) continue;
+            if (!in.q.n_records || !in.q.records) { rc = set_err(c, CG_ERR_INVALID, "cg_tower_build_virtual: spec without records"); break; }
+            TowerSpecState sp;
+            sp.is_logup = in.is_logup != 0;
+            sp.virt = true;
+            uint64_t len_q = 0, len_p = 0;
+            const VirtLeaf* dq[2];
+            rc = make_virt_limbs(tw, in.q, dq, &len_q);
+            if (rc != CG_OK) break;
+            if (!sp.is_logup) {
+                sp.d_virt[0] = dq[0]; sp.d_virt[1] = dq[1];
+                sp.num_vars = ceil_log2_u64(len_q) + 1;
+                sp.layers = sp.num_vars;
+            } else {
+                sp.d_virt[2] = dq[0]; sp.d_virt[3] = dq[1];
+                cg_tower_vgroup pg = in.p;
+                if (!pg.n_records) {   // numerators all one (utils.rs:556-577): a description with no records and default 1
+                    pg = in.q;
+                    pg.n_records = 0;
+                    pg.records = nullptr;
+                    pg.default_ext[0] = 1; pg.default_ext[1] = 0;
+                }
+                const VirtLeaf* dp[2];
+                rc = make_virt_limbs(tw, pg, dp, &len_p);
+                if (rc != CG_OK) break;
+                if (in.p.n_records && len_p != len_q) { rc = set_err(c, CG_ERR_INVALID, "cg_tower_build_virtual: numerator and denominator groups differ in shape"); break; }
+                sp.d_virt[0] = dp[0]; sp.d_virt[1] = dp[1];
+                sp.num_vars = ceil_log2_u64(len_q);
+                sp.layers = sp.num_vars + 1;
+            }
+            if (sp.num_vars == 0 || sp.num_vars > 34) { rc = set_err(c, CG_ERR_INVALID, "cg_tower_build_virtual: num_vars out of range"); break; }
+            rc = tower_build_spec(tw, sp);
+            if (rc == CG_OK) tw->specs.push_back(std::move(sp));
+        }
+    if (rc != CG_OK) { cg_tower_destroy(tw); return rc; }
+    *out = tw;
+    return CG_OK;
 }
 CG_EXPORT int cg_tower_output_evals(cg_tower* tw, uint32_t spec, uint64_t* h_out) {
     if (!tw || spec >= tw->specs.size() || !h_out) return CG_ERR_INVALID;
@@ -2453,6 +2593,7 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
         const double t1 = now();
         // MLE list in the reference's lift order: eq, then live product specs, then live logup specs
         std::vector<cg_mle_desc> mles;
+        std::vector<const VirtLeaf*> virt{nullptr};
         mles.push_back(cg_mle_desc{d_eq, n, nv, 1});
         TowerLayout tl;
         tl.on = true;
@@ -2466,7 +2607,9 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
             first[si] = (uint32_t)mles.size();
             const uint32_t arrs = sp.is_logup ? 4 : 2;
             for (uint32_t z = 0; z < arrs; z++) {
-                mles.push_back(cg_mle_desc{tower_arr(sp, round, z), n, nv, 1});
+                const bool vleaf = sp.virt && round + 1 == sp.layers;   // the leaf layer of a virtual spec: placeholder pointer + description
+                mles.push_back(cg_mle_desc{vleaf ? (const void*)d_eq : (const void*)tower_arr(sp, round, z), n, nv, 1});
+                virt.push_back(vleaf ? sp.d_virt[z] : nullptr);
                 (sp.is_logup ? tl.lk : tl.prod).push_back((uint32_t)mles.size() - 1);
             }
             if (sp.is_logup) { tl.lk_an.push_back(alpha[tw->n_prod + 2 * my]); tl.lk_ad.push_back(alpha[tw->n_prod + 2 * my + 1]); }
@@ -2500,6 +2643,14 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
         const double t2 = now();
         if (rc == CG_OK) {
             if (fits) sc->tl = tl;
+            bool any_virt = false;
+            for (const VirtLeaf* v : virt) any_virt |= v != nullptr;
+            if (any_virt) {
+                if (!fits) rc = set_err(c, CG_ERR_UNSUPPORTED, "virtual tower leaves need the specialised tower kernels (<= 8 product, <= 4 logup specs)");
+                sc->virt = virt;
+            }
+        }
+        if (rc == CG_OK) {
             tr->sumcheck_begin(tr->user, nv, 3);
             rc = sc_run_host(sc, tr->round_challenge, tr->user, h_proof + w, fin.data(), chal.data());
         }

@@ -303,6 +303,32 @@ GL_DEV void load_pair(const ext_t* __restrict__ in, ext_t* __restrict__ out, uin
 // Evaluation points by subtraction only: nd = lo - hi, f(1) = hi, f(2) = f(1) - nd, f(3) = f(2) - nd.
 // Inner sums and the per-thread round sums are kept as unreduced 160-bit accumulators; each is
 // reduced once (inner: once per item and point; round sums: once per thread).
+// Virtual tower leaves (the reference's GpuVirtualInterleavedExt, ceno_zkvm/src/scheme/gpu/mod.rs:2195-2268): one fan-in limb of
+// interleaving_mles_to_mles (ceno_zkvm/src/scheme/utils.rs:402-462) described instead of materialised —
+//   leaf[s * 2^l2m + i] = record_i[row_offset + s]  (i < n_records, s < the record kind's row count), else `def`.
+// The kernels that read a tower's leaf layer (first level of the build, round 0 / 1 of the leaf-layer sumcheck) take the
+// description; nothing of the leaf layer's size is ever written for the records themselves.
+struct VirtLeaf {
+    const void* const* ptrs;    // device array of n_records record pointers
+    const uint32_t* is_ext;     // device array: record i is ext (16 B) or base (8 B)
+    uint32_t n_records, l2m;    // 2^l2m = records per instance after padding
+    uint64_t row_offset;        // limb * per_fanin_len
+    uint64_t cnt_ext, cnt_base; // rows an ext / a base record contributes to this limb (utils.rs:433-456)
+    ext_t def;                  // padding value: 1 for read / write records, the challenge alpha for lookups
+};
+GL_DEV ext_t virt_leaf(const VirtLeaf& v, uint64_t x) {
+    const uint32_t i = (uint32_t)(x & ((1ULL << v.l2m) - 1));
+    const uint64_t s = x >> v.l2m;
+    if (i < v.n_records) {
+        const uint32_t e = v.is_ext[i];
+        if (s < (e ? v.cnt_ext : v.cnt_base)) {
+            if (e) return ext_canon(ld_ext(reinterpret_cast<const ext_t*>(v.ptrs[i]) + v.row_offset + s));
+            return ext_make(gl_canon(reinterpret_cast<const uint64_t*>(v.ptrs[i])[v.row_offset + s]), 0);
+        }
+    }
+    return v.def;
+}
+#define CG_TOWER_SLOTS (1 + 2 * CG_TOWER_MAX_PROD + 4 * CG_TOWER_MAX_LOGUP)
 struct TowerArgs {
     const ext_t* eq_in;
     ext_t* eq_out;
@@ -315,6 +341,7 @@ struct TowerArgs {
     ext_t alpha_den[CG_TOWER_MAX_LOGUP];
     int n_prod, n_logup;
     int alpha_one;            // every alpha_prod is 1: skip the alpha multiply
+    const VirtLeaf* virt[CG_TOWER_SLOTS];   // VIRT kernels: slot (1 + 2p + z | 1 + 2 n_prod + 4l + z) read through a description (null: plain array)
     uint64_t n_pairs;         // pairs evaluated this launch (after the fold, if FOLD)
     ext_t r;                  // fold challenge (FOLD only) ...
     const ext_t* r_ptr;       // ... or read it from device memory (device challenger)
@@ -466,19 +493,45 @@ GL_DEV void tower_item_pt(const TowerArgs& a, L& ld, uint64_t item, int t, ecacc
     accumulate_point(H, u, at(elo, ehi));
 }
 
-template <bool FOLD, bool CANON>
+// the same pair read through a leaf description (values come back canonical)
+template <bool FOLD>
+GL_DEV void load_pair_virt(const VirtLeaf& v, ext_t* __restrict__ out, uint64_t item, const extmul_t& r, ext_t& lo, ext_t& hi) {
+    if (FOLD) {
+        const ext_t x0 = virt_leaf(v, 4 * item), x1 = virt_leaf(v, 4 * item + 1), x2 = virt_leaf(v, 4 * item + 2), x3 = virt_leaf(v, 4 * item + 3);
+        lo = ext_fma_prep(x0, ext_sub(x1, x0), r);
+        hi = ext_fma_prep(x2, ext_sub(x3, x2), r);
+        st_ext2(out + 2 * item, lo, hi);
+    } else {
+        lo = virt_leaf(v, 2 * item);
+        hi = virt_leaf(v, 2 * item + 1);
+    }
+}
+template <bool FOLD, bool CANON, bool VIRT = false>
 struct GlobalLoader {
     const TowerArgs& a;
     extmul_t rm;
     GL_DEV void eq(uint64_t item, ext_t& lo, ext_t& hi) { load_pair<FOLD, CANON>(a.eq_in, a.eq_out, item, rm, lo, hi); }
-    GL_DEV void prod(int p, int z, uint64_t item, ext_t& lo, ext_t& hi) { load_pair<FOLD, CANON>(a.prod_in[p][z], a.prod_out[p][z], item, rm, lo, hi); }
-    GL_DEV void lk(int l, int z, uint64_t item, ext_t& lo, ext_t& hi) { load_pair<FOLD, CANON>(a.lk_in[l][z], a.lk_out[l][z], item, rm, lo, hi); }
+    GL_DEV void prod(int p, int z, uint64_t item, ext_t& lo, ext_t& hi) {
+        if (VIRT) {
+            const VirtLeaf* v = a.virt[1 + 2 * p + z];
+            if (v) { load_pair_virt<FOLD>(*v, a.prod_out[p][z], item, rm, lo, hi); return; }
+        }
+        load_pair<FOLD, CANON>(a.prod_in[p][z], a.prod_out[p][z], item, rm, lo, hi);
+    }
+    GL_DEV void lk(int l, int z, uint64_t item, ext_t& lo, ext_t& hi) {
+        if (VIRT) {
+            const VirtLeaf* v = a.virt[1 + 2 * a.n_prod + 4 * l + z];
+            if (v) { load_pair_virt<FOLD>(*v, a.lk_out[l][z], item, rm, lo, hi); return; }
+        }
+        load_pair<FOLD, CANON>(a.lk_in[l][z], a.lk_out[l][z], item, rm, lo, hi);
+    }
 };
 
 // THREADS x MINB = launch shape (registers per thread are capped at 65536 / (THREADS * MINB)).
-template <bool FOLD, bool CANON, bool SIMPLE, int THREADS, int MINB>
+// VIRT: some slots are virtual tower leaves (only the launches that read a sumcheck's ORIGINAL inputs can be).
+template <bool FOLD, bool CANON, bool SIMPLE, int THREADS, int MINB, bool VIRT = false>
 __global__ void __launch_bounds__(THREADS, MINB) tower_round_kernel(const __grid_constant__ TowerArgs a) {
-    GlobalLoader<FOLD, CANON> ld{a, {0, 0, 0}};
+    GlobalLoader<FOLD, CANON, VIRT> ld{a, {0, 0, 0}};
     if (FOLD) ld.rm = extmul_prep(a.r_ptr ? ld_ext(a.r_ptr) : a.r);
     ecacc H[3];
     ecacc_zero(H[0]); ecacc_zero(H[1]); ecacc_zero(H[2]);
@@ -1696,6 +1749,27 @@ __global__ void __launch_bounds__(CG_THREADS) tower_logup_layer_kernel(const ext
         } else {
             p = ext_add(a1, a2);
         }
+        st_ext(p_out + x, p);
+        st_ext(q_out + x, ext_mul(a1, a2));
+    }
+}
+// first level above VIRTUAL leaves (description instead of arrays; p1 / p2 null = numerators are all one)
+__global__ void __launch_bounds__(CG_THREADS) tower_prod_layer_virt_kernel(const VirtLeaf* __restrict__ a, const VirtLeaf* __restrict__ b,
+                                                                            uint64_t n, ext_t* __restrict__ out) {
+    const VirtLeaf va = *a, vb = *b;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) st_ext(out + x, ext_mul(virt_leaf(va, x), virt_leaf(vb, x)));
+}
+__global__ void __launch_bounds__(CG_THREADS) tower_logup_layer_virt_kernel(const VirtLeaf* __restrict__ p1, const VirtLeaf* __restrict__ p2,
+                                                                             const VirtLeaf* __restrict__ q1, const VirtLeaf* __restrict__ q2,
+                                                                             uint64_t n, ext_t* __restrict__ p_out, ext_t* __restrict__ q_out) {
+    const VirtLeaf v1 = *q1, v2 = *q2;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) {
+        const ext_t a1 = virt_leaf(v1, x), a2 = virt_leaf(v2, x);
+        ext_t p;
+        if (p1) p = ext_add(ext_mul(a1, virt_leaf(*p2, x)), ext_mul(a2, virt_leaf(*p1, x)));
+        else p = ext_add(a1, a2);
         st_ext(p_out + x, p);
         st_ext(q_out + x, ext_mul(a1, a2));
     }

@@ -265,6 +265,27 @@ uint64_t cg_tower_interleave_out_len(uint32_t n_mles, uint64_t num_instances, ui
 int cg_tower_interleave(cg_ctx* ctx, const cg_mle_desc* mles, uint32_t n_mles, uint64_t num_instances, uint32_t num_limbs,
                         const uint64_t default_ext[2], uint64_t* d_out_ext, cg_stream s);
 typedef struct cg_tower cg_tower;
+/* Virtual leaf layers — the reference's GpuVirtualInterleavedExt (ceno_zkvm/src/scheme/gpu/mod.rs:2195-2268; builders
+ * build_prod_tower_from_virtual_ext_batch / build_logup_tower_from_virtual_ext_batch :2365-2402): a spec is given by its RECORD
+ * MLEs (one value per instance, base or ext, equal length <= next_pow2(num_instances)); the interleaved fan-in leaves
+ * (cg_tower_interleave's output: 2^ceil_log2(R) x rows, e.g. 2^33 ext for keccak's 1094 lookup records at 2^22 rows) are never
+ * materialised — the first build level and rounds 0 / 1 of the leaf-layer sumcheck read the records through the description.
+ * Same proof bits as cg_tower_interleave + cg_tower_build.  At most 8 product + 4 logup specs (the specialised tower kernels).
+ *   product spec: q = the read (or write) records, default 1;   logup spec: q = denominators (default alpha),
+ *   p = numerators (default 1) or p.n_records = 0 for all-one numerators (utils.rs:556-577). */
+typedef struct cg_tower_vgroup {
+    const cg_mle_desc* records;
+    uint32_t n_records;
+    uint32_t reserved;
+    uint64_t num_instances;
+    uint64_t default_ext[2];
+} cg_tower_vgroup;
+typedef struct cg_tower_vspec {
+    cg_tower_vgroup q, p;
+    uint32_t is_logup;
+    uint32_t reserved;
+} cg_tower_vspec;
+int cg_tower_build_virtual(cg_ctx* ctx, const cg_tower_vspec* specs, uint32_t n_specs, cg_stream s, cg_tower** out);
 int cg_tower_build(cg_ctx* ctx, const cg_tower_spec* specs, uint32_t n_specs, cg_stream s, cg_tower** out);
 /* get_output_evals (ceno_zkvm/src/scheme/gpu/mod.rs:369-420): layer-0 values of spec i:
  * 2 ext for a product spec, 4 for a logup spec. */

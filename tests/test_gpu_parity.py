@@ -501,6 +501,57 @@ def test_chip_tower_flow_records_to_proof(dev):
     tw.close()
 
 
+@pytest.mark.parametrize("log_n,ninst,n_r,n_w,n_lk,with_num,base_mix", [
+    (12, 3000, 3, 2, 5, False, False),      # the opcode-chip shape: read / write / lookup groups, padded instances
+    (12, 4096, 1, 4, 9, True, True),        # explicit numerators, base-field records mixed in, full instances
+    (13, 5000, 37, 2, 70, False, False),    # many records per row (keccak-like: padded_ops 64 / 128)
+    (7, 100, 3, 2, 1094, False, False),     # keccak's 1094 lookup records per row (lookup_keccakf.rs:97-101), scaled-down rows
+])
+def test_tower_over_virtual_leaves_bit_exact(dev, log_n, ninst, n_r, n_w, n_lk, with_num, base_mix):
+    """cfg-4: the tower built and proven over VIRTUAL leaf layers (GpuVirtualInterleavedExt: records described, the interleaved
+    fan-in leaves never stored) gives the oracle's proof of the materialised chain, bit for bit."""
+    import ceno_b200 as cb
+    n = 1 << log_n
+    alpha = [12345, 678]
+
+    def recs(seed, cnt):
+        out = []
+        for i in range(cnt):
+            is_ext = not (base_mix and i % 2 == 1)
+            out.append((orc.fill_ext(seed + i, n) if is_ext else orc.fill_base(seed + i, n), is_ext))
+        return out
+
+    def dev_mles(rs):
+        return [(cb.MultilinearExtension.from_evaluations_ext_vec if e else cb.MultilinearExtension.from_evaluations_vec)(dev, log_n, c) for c, e in rs]
+    r_recs, w_recs, lk_recs = recs(9100, n_r), recs(9200, n_w), recs(9300, n_lk)
+    num_recs = recs(9400, n_lk) if with_num else None
+    o_prod, o_lk, vspecs, keep = [], [], [], []
+    for rs in (r_recs, w_recs):
+        want = orc.interleaving_mles_to_mles(rs, ninst, 2, [1, 0])
+        nv = (want[0].size // 2).bit_length()
+        o_prod.append((orc.infer_tower_product_witness(nv, want[0], want[1])[0], nv))
+        ms = dev_mles(rs)
+        keep += ms
+        vspecs.append(cb.VirtualTowerSpec(ms, ninst, [1, 0], False))
+    want = orc.interleaving_mles_to_mles(lk_recs, ninst, 2, alpha)
+    nv = (want[0].size // 2).bit_length() - 1
+    if with_num:
+        wn = orc.interleaving_mles_to_mles(num_recs, ninst, 2, [1, 0])
+        o_lk.append((orc.infer_tower_logup_witness(nv, wn[0], wn[1], want[0], want[1])[0], nv + 1))
+    else:
+        o_lk.append((orc.infer_tower_logup_witness(nv, None, None, want[0], want[1])[0], nv + 1))
+    ms, nms = dev_mles(lk_recs), (dev_mles(num_recs) if with_num else None)
+    keep += ms + (nms or [])
+    vspecs.append(cb.VirtualTowerSpec(ms, ninst, alpha, True, numerators=nms))
+    tw = cb.TowerProver.from_records(dev, vspecs)
+    want_proof, want_point = orc.tower_create_proof(o_prod, o_lk, orc.Transcript(b"virt"))
+    got_proof, got_point = tw.create_proof(cb.StandInTranscript(b"virt"))
+    assert eq_np(got_proof, want_proof) and eq_np(got_point, want_point)
+    tw.close()
+    for m in keep:
+        m.free()
+
+
 @pytest.mark.parametrize("prod_nvs,logup_nvs,with_p", [
     ([4], [], False),                 # test_tower_proof_various_prod_size style (scheme/tests.rs:447-500)
     ([2], [], False), ([10], [], False),
