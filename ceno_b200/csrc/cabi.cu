@@ -39,6 +39,7 @@ struct cg_ctx {
     std::unordered_map<void*, size_t> live;
     size_t used = 0, reserved = 0;
     std::atomic<uint64_t> launches{0};
+    std::atomic<int> live_sc{0};                          // sumchecks alive right now (lanes): persistent kernels shrink when > 1
     std::vector<std::pair<size_t, void*>> pinned_cache;   // reusable pinned staging buffers
     P2Params* d_p2 = nullptr;                             // Poseidon2 constants (caller-supplied, cg_poseidon2_set_params)
     std::vector<float> profile_ms;                        // per-round device time of the last CG_SC_PROFILE run
@@ -808,6 +809,7 @@ CG_EXPORT int cg_sumcheck_destroy(cg_sumcheck* sc) {
     if (!sc) return CG_ERR_INVALID;
     for (void* p : sc->owned) tmp_free(p, sc->stream);   // stream-ordered: no synchronisation needed
     if (sc->h_pinned) pinned_put(sc->ctx, sc->h_pinned, sc->h_pinned_bytes);
+    sc->ctx->live_sc--;
     delete sc;
     return CG_OK;
 }
@@ -923,6 +925,7 @@ static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles,
     CU(c, cudaSetDevice(c->device));
     cg_sumcheck* sc = new cg_sumcheck();
     sc->ctx = c;
+    c->live_sc++;
     sc->stream = st;
     sc->n_mles = n_mles;
     sc->num_vars = num_vars;
@@ -1527,6 +1530,14 @@ static uint32_t tail_nloc_cap(const cg_ctx* c, size_t n_slots) {
     const uint64_t cap = (c->max_smem_optin - 8192) / (n_slots * sizeof(ext_t));
     return cap < 2 ? 0 : std::min<uint32_t>(CG_CT_MAX_NLOC, pow2_floor_u32(cap));
 }
+// Concurrent lanes (ChipScheduler, up to 8 chip proofs at once) share the SMs: a persistent tail that waits for its host
+// transcript on 16 SMs per lane, or a cooperative mid kernel that needs the whole chip to itself, starves the other lanes'
+// streaming and hashing kernels (measured: 6 chips on 8 lanes took LONGER than sequentially).  So the cluster shrinks with
+// the number of sumchecks alive on the context, and the mid kernel is left out when there is more than one.
+static uint32_t lane_cluster_cap(const cg_ctx* c) {
+    const int live = c->live_sc.load();
+    return live <= 1 ? CG_CT_MAX_C : (live <= 2 ? 8u : (live <= 4 ? 4u : 2u));
+}
 static TailPlan tail_plan(const cg_ctx* c, size_t n_slots, uint64_t n0, bool sharded) {
     TailPlan p;
     const uint32_t cap = tail_nloc_cap(c, n_slots);
@@ -1534,7 +1545,7 @@ static TailPlan tail_plan(const cg_ctx* c, size_t n_slots, uint64_t n0, bool sha
     if (sharded && n_slots * n0 > CG_GATHER_EXT) return p;
     const char* fe = getenv("CG_TAIL_CLUSTER");   // testing: cap the cluster size (read per call so one process can sweep it)
     const int force_c = fe ? atoi(fe) : 0;
-    const uint32_t max_c = force_c > 0 ? std::min<uint32_t>((uint32_t)force_c, c->tail_max_c) : c->tail_max_c;
+    const uint32_t max_c = std::min(lane_cluster_cap(c), force_c > 0 ? std::min<uint32_t>((uint32_t)force_c, c->tail_max_c) : c->tail_max_c);
     if (n0 <= std::min<uint32_t>(cap, CG_TAIL_START_N) || max_c == 1) {   // one CTA
         if (n0 > cap) return p;
         p.C = 1; p.n_loc0 = (uint32_t)n0; p.nt = (uint32_t)n0;
@@ -1554,7 +1565,7 @@ static TailPlan tail_plan(const cg_ctx* c, size_t n_slots, uint64_t n0, bool sha
 // largest entry size (elements per MLE, cluster-wide, after the entry fold) the tail accepts for n_slots MLEs
 static uint64_t tail_cap_n0(const cg_ctx* c, size_t n_slots, bool sharded) {
     const char* fe = getenv("CG_TAIL_CLUSTER");
-    const uint32_t max_c = fe && atoi(fe) > 0 ? std::min<uint32_t>((uint32_t)atoi(fe), c->tail_max_c) : c->tail_max_c;
+    const uint32_t max_c = std::min(lane_cluster_cap(c), fe && atoi(fe) > 0 ? std::min<uint32_t>((uint32_t)atoi(fe), c->tail_max_c) : c->tail_max_c);
     uint64_t n = (uint64_t)tail_nloc_cap(c, n_slots) * max_c;
     if (max_c == 1) n = std::min<uint64_t>(n, CG_TAIL_START_N);
     if (sharded) while (n > 1 && n_slots * n > CG_GATHER_EXT) n >>= 1;
@@ -1695,6 +1706,7 @@ static uint32_t tail_entry_round(const cg_sumcheck* sc) {
 static bool mid_eligible(const cg_sumcheck* sc) {
     if (sc->veq.split) return false;
     if (!sc->tl.on || sc->mid_used || (sc->flags & (CG_SC_NO_FUSE | CG_SC_NO_TAIL | CG_SC_NO_MID))) return false;
+    if (sc->ctx->live_sc.load() > 1) return false;   // a cooperative launch needs every SM: not while other lanes are proving
     if (!sc->pending || sc->folds < 1 || sc->round >= sc->num_vars) return false;
     const uint32_t left = sc->num_vars - sc->folds;
     if (left < 3 || left - 2 > CG_MID_MAX_LOG_PAIRS) return false;    // fused round: 2^left elements -> 2^(left-2) pairs
