@@ -109,6 +109,7 @@ static cudaError_t prepare_kernels(size_t max_optin) {
     CG_PREP(optin_smem(veq_tma_kernel<false, false, 3>, max_optin));
     CG_PREP(optin_smem(veq_tma_kernel<true, true, 3>, max_optin));
     CG_PREP(optin_smem(veq_tma_kernel<true, false, 3>, max_optin));
+    CG_PREP(optin_smem(veq_persist_kernel, max_optin));
     CG_PREP(optin_smem(veq_tma_kernel<true, true, 2, true>, max_optin));
     CG_PREP(optin_smem(veq_tma_kernel<true, false, 2, true>, max_optin));
     CG_PREP(preload(tower_mid_kernel<true>));
@@ -768,6 +769,7 @@ struct cg_sumcheck {
     std::vector<void*> owned;
     int* d_error = nullptr;
     unsigned *d_mid_ticket = nullptr, *d_mid_flag = nullptr;
+    unsigned *d_per_ticket = nullptr, *d_per_flag = nullptr;   // persistent split-eq rounds
     bool mid_used = false;
     std::vector<uint64_t> h_coeff;   // term tables stay on the host until a generic kernel needs them
     std::vector<uint32_t> h_off, h_idx;
@@ -977,6 +979,8 @@ static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles,
         sc->d_error = (int*)(b + o_err);
         sc->d_mid_ticket = (unsigned*)(b + 128);
         sc->d_mid_flag = (unsigned*)(b + 192);
+        sc->d_per_ticket = (unsigned*)(b + 320);
+        sc->d_per_flag = (unsigned*)(b + 384);
         sc->d_final = (ext_t*)(b + o_final);
         sc->d_msgs = (ext_t*)(b + o_msgs);
         sc->d_chal = (ext_t*)(b + o_chal);
@@ -1536,7 +1540,9 @@ static uint32_t tail_nloc_cap(const cg_ctx* c, size_t n_slots) {
 // the number of sumchecks alive on the context, and the mid kernel is left out when there is more than one.
 static uint32_t lane_cluster_cap(const cg_ctx* c) {
     const int live = c->live_sc.load();
-    return live <= 1 ? CG_CT_MAX_C : (live <= 2 ? 8u : (live <= 4 ? 4u : 2u));
+    // measured on the 6-chip shard: clusters of 4-8 CTAs (each needing a whole SM of one GPC at the same instant) wait behind
+    // the other lanes' streaming waves — 4 lanes took 120 ms against 61 ms sequentially; pairs are scheduled readily
+    return live <= 1 ? CG_CT_MAX_C : 2u;
 }
 static TailPlan tail_plan(const cg_ctx* c, size_t n_slots, uint64_t n0, bool sharded) {
     TailPlan p;
@@ -1771,6 +1777,69 @@ static int launch_mid(cg_sumcheck* sc, uint64_t* d_tr_state, uint32_t* jt_out) {
     return CG_OK;
 }
 
+// ---- persistent split-eq rounds (veq_persist_kernel): every claim-derived streaming round in one cooperative launch
+static bool persist_eligible(const cg_sumcheck* sc) {
+    static const int on = []() { const char* e = getenv("CG_VEQ_PERSIST"); return e ? atoi(e) : 1; }();
+    static const int use_tma = []() { const char* e = getenv("CG_VEQ_TMA"); return e ? atoi(e) : 1; }();
+    static const int minb = []() { const char* e = getenv("CG_VEQ_MINB"); return e ? atoi(e) : CG_VEQ_MINB_DEFAULT; }();
+    const VeqState& v = sc->veq;
+    if (!on || !use_tma || minb == 3 || !v.split || !v.derive_ok) return false;
+    if (sc->flags & (CG_SC_NO_FUSE | CG_SC_NO_MID | CG_SC_NO_PERSIST | CG_SC_FORCE_GENERIC)) return false;
+    if (!sc->pending || sc->round < 1 || sc->round + 1 >= v.J) return false;   // at least two rounds, after round 0
+    if (sc->ctx->live_sc.load() > 1) return false;                              // cooperative: needs the whole chip
+    return true;
+}
+static int launch_veq_persist(cg_sumcheck* sc, uint64_t* d_tr_state, uint32_t* upto_out) {
+    cg_ctx* c = sc->ctx;
+    const VeqState& v = sc->veq;
+    VeqPersistArgs a;
+    memset(&a, 0, sizeof(a));
+    const uint32_t j0 = sc->round, j1 = v.J, steps = j1 - j0;
+    for (uint32_t i = 0; i <= steps; i++) {
+        a.bufA[i] = (const ext_t*)mle_buf(sc, sc->tl.prod[0], j0 - 1 + i);
+        a.bufB[i] = (const ext_t*)mle_buf(sc, sc->tl.prod[1], j0 - 1 + i);
+    }
+    a.L = v.d_L;
+    a.H = v.d_H;
+    for (uint32_t j = 0; j <= v.J; j++) a.h_off[j] = v.h_off[j];
+    a.k = sc->num_vars;
+    a.j0 = j0;
+    a.j1 = j1;
+    a.canon_first = (j0 == 1) ? 1 : 0;
+    a.r = sc->pending_r;
+    a.r_ptr = sc->pending_r_ptr;
+    a.fin.w = v.d_w;
+    a.fin.inv1mw = v.d_inv1mw;
+    a.fin.prefix = v.d_prefix;
+    a.fin.qstate = v.d_qstate;
+    a.fin.scale = v.scale;
+    a.fin.sharded = (sc->comm && sc->comm->nranks > 1) ? 1 : 0;
+    a.d_msgs = sc->d_msgs;
+    a.d_chal = sc->d_chal;
+    a.d_tr_state = d_tr_state;
+    a.mail = d_tr_state ? nullptr : sc_mailbox(sc);
+    a.d_error = sc->d_error;
+    a.timeout_cycles = c->wait_timeout_cycles;
+    comm_dev(sc->comm, a.comm, steps);
+    a.partials = sc->out.partials;
+    a.ticket = sc->d_per_ticket;
+    a.round_flag = sc->d_per_flag;
+    const uint64_t first_rows = 1ULL << (sc->num_vars - j0 - 1 - CG_VEQ_LO_BITS);
+    uint64_t blocks = (uint64_t)c->sm_count * 2;
+    if (blocks > first_rows) blocks = first_rows;
+    if (blocks > CG_MAX_BLOCKS) blocks = CG_MAX_BLOCKS;
+    void* args[] = {&a};
+    CU(c, cudaLaunchCooperativeKernel((const void*)veq_persist_kernel, dim3((unsigned)blocks), dim3(256), args, VeqTmaCfg<true, 2>::SMEM, sc->stream));
+    LAUNCHED(c);
+    sc->folds += steps;
+    sc->round = j1;
+    sc->pending = true;
+    sc->pending_r_ptr = sc->d_chal + (j1 - 1);
+    sc->evaluated = false;
+    *upto_out = j1;
+    return CG_OK;
+}
+
 static void prof_begin(cg_sumcheck* sc) {
     if (!(sc->flags & CG_SC_PROFILE)) return;
     sc->ev.resize(2 * (size_t)sc->num_vars);
@@ -1808,14 +1877,18 @@ static int sc_run_host(cg_sumcheck* sc, cg_challenge_cb cb, void* user, uint64_t
         uint64_t* msg = h_rounds + (size_t)j * sc->degree * 2;
         prof_mark(sc, j, 0);
         CHK(veq_prepare(sc));
-        if (mid_eligible(sc) || tail_eligible(sc)) {
-            // the device runs every remaining round on its own (cooperative mid kernel, then the shared-memory tail
-            // kernel, both enqueued now); the transcript stays on the host and answers through the mailbox
+        if (persist_eligible(sc) || mid_eligible(sc) || tail_eligible(sc)) {
+            // the device runs every remaining round on its own (persistent split-eq rounds, cooperative mid kernel, then the
+            // shared-memory tail kernel, all enqueued now); the transcript stays on the host and answers through the mailbox
             cg_ctx* c = sc->ctx;
             TailMailbox* mb = sc_mailbox(sc);
             if (j == 0) mailbox_reset(mb);
             uint32_t upto = j;   // rounds [j, upto) are owned by enqueued kernels
             bool done = false;
+            if (persist_eligible(sc)) {
+                CHK(launch_veq_persist(sc, nullptr, &upto));
+                CHK(veq_prepare(sc));   // leave split mode: the eq state is materialised behind the persistent kernel
+            }
             if (mid_eligible(sc)) CHK(launch_mid(sc, nullptr, &upto));
             if (tail_eligible(sc)) {
                 CHK(launch_tail(sc, nullptr, sc->d_msgs, sc->d_chal));
@@ -2058,6 +2131,14 @@ static int sc_run_device(cg_sumcheck* sc, uint64_t* h_state, uint64_t* h_rounds,
     for (uint32_t j = 0; j < sc->num_vars; j++) {
         prof_mark(sc, j, 0);
         CHK(veq_prepare(sc));
+        if (persist_eligible(sc)) {   // every remaining streaming round of the split-eq form in one cooperative launch
+            uint32_t upto = j;
+            CHK(launch_veq_persist(sc, sc->d_tr_state, &upto));
+            prof_mark(sc, j, 1);
+            for (uint32_t jj = j + 1; jj < upto; jj++) { prof_mark(sc, jj, 0); prof_mark(sc, jj, 1); }
+            j = upto - 1;
+            continue;
+        }
         if (mid_eligible(sc)) {    // one cooperative launch for the latency-bound rounds before the tail
             uint32_t upto = j;
             CHK(launch_mid(sc, sc->d_tr_state, &upto));

@@ -813,6 +813,214 @@ __global__ void __launch_bounds__(256, MINB) veq_tma_kernel(const __grid_constan
     }
 }
 
+// ---- persistent split-eq rounds: ONE cooperative launch runs the claim-derived rounds j0 .. j1-1 (every streaming round
+// after the first).  A separate launch per round costs ~18 us of fixed time (launch latency, ring fill, finish chain) that
+// does not shrink with the data — 15 % of a T3-24 step and most of an 8-GPU one.  Here every block keeps its ring and
+// barriers, draws a ticket after its rows, the block that draws the round's last ticket combines the partials, runs the
+// multi-GPU exchange, solves q(0) from the claim, obtains the challenge (device challenger or host mailbox) and releases
+// the round flag the other blocks poll — the hand-off of tower_mid_kernel around the row pipeline of veq_tma_kernel.
+struct VeqPersistArgs {
+    const ext_t* bufA[CG_VEQ_MAX_ROUNDS + 2];   // state of A after f folds, f = j0 - 1 + i   (i = 0: the first round's input)
+    const ext_t* bufB[CG_VEQ_MAX_ROUNDS + 2];
+    const ulonglong4* L;                        // [J][256]
+    const ulonglong4* H;                        // concatenated, H_j at h_off[j]
+    uint64_t h_off[CG_VEQ_MAX_ROUNDS + 1];
+    uint32_t k, j0, j1;
+    int canon_first;                            // the first round reads caller-provided buffers
+    ext_t r;                                    // challenge of the first round's fold ...
+    const ext_t* r_ptr;                         // ... or its device location
+    VeqFin fin;                                 // w, inv1mw, prefix, qstate, scale, sharded (round / fold / r are set per round)
+    ext_t* d_msgs;                              // [round * 3]
+    ext_t* d_chal;                              // [round]
+    uint64_t* d_tr_state;                       // device challenger, or nullptr -> host mailbox
+    TailMailbox* mail;
+    int* d_error;
+    unsigned long long timeout_cycles;
+    CommDev comm;                               // exchange of round j uses sequence comm.seq + (j - j0)
+    ext_t* partials;                            // [gridDim.x * 3]
+    unsigned int* ticket;                       // zero on entry
+    volatile unsigned int* round_flag;          // index of the last finished round + 1
+};
+GL_DEV void mbar_inval(uint32_t bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
+__global__ void __launch_bounds__(256, 2) veq_persist_kernel(const __grid_constant__ VeqPersistArgs a) {
+    using Cfg = VeqTmaCfg<true, 2>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr uint32_t ROWB = Cfg::ROWB, STAGEB = Cfg::STAGEB;
+    extern __shared__ __align__(128) unsigned char veq_smem[];
+    __shared__ ext_t s_part[8][3];
+    __shared__ __align__(32) uint64_t s_msg[2 * 3 + 8];
+    __shared__ ext_t s_r;
+    __shared__ int s_flag;   // 1: this block drew the round's last ticket, 2: abort
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sbase = smem_u32(veq_smem);
+    const uint32_t bar_full = sbase + STAGES * STAGEB, bar_empty = bar_full + STAGES * 8;
+    const uint32_t sx = (tid >> 1) & 1;          // claim-derived chunk order: swap within a pair only
+    const uint32_t toff = tid * 64;
+    ext_t r_cur = ext_canon(a.r_ptr ? ld_ext(a.r_ptr) : a.r);
+    for (uint32_t j = a.j0; j < a.j1; j++) {
+        const uint32_t step = j - a.j0;
+        const ext_t* inA = a.bufA[step];
+        const ext_t* inB = a.bufB[step];
+        ext_t* outA = const_cast<ext_t*>(a.bufA[step + 1]);
+        ext_t* outB = const_cast<ext_t*>(a.bufB[step + 1]);
+        const ulonglong4* Hj = a.H + a.h_off[j];
+        const uint64_t n_rows = 1ULL << (a.k - j - 1 - CG_VEQ_LO_BITS);
+        const uint64_t r0 = n_rows * blockIdx.x / gridDim.x, r1 = n_rows * (blockIdx.x + 1) / gridDim.x;
+        const uint32_t nrows = (uint32_t)(r1 - r0);
+        const bool canon = a.canon_first && step == 0;
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; s++) {
+                if (step) { mbar_inval(bar_full + 8 * s); mbar_inval(bar_empty + 8 * s); }
+                mbar_init(bar_full + 8 * s, 1);
+                mbar_init(bar_empty + 8 * s, 8);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            s_flag = 0;
+        }
+        __syncthreads();
+        auto issue = [&](uint32_t i) {
+            const uint32_t s = i % STAGES;
+            const uint64_t row = r0 + i;
+            const uint32_t dst = sbase + s * STAGEB, bar = bar_full + 8 * s;
+            mbar_expect_tx(bar, 2 * ROWB + 32);
+            tma_load_1d(dst, reinterpret_cast<const unsigned char*>(inA) + row * ROWB, ROWB, bar);
+            tma_load_1d(dst + ROWB, reinterpret_cast<const unsigned char*>(inB) + row * ROWB, ROWB, bar);
+            tma_load_1d(dst + 2 * ROWB, Hj + row, 32, bar);
+        };
+        if (tid == 0)
+            for (uint32_t i = 0; i < (uint32_t)STAGES && i < nrows; i++) issue(i);
+        ext_t rr = r_cur;
+        if (sx & 1) rr = ext_sub(ext_one(), rr);
+        const extmul_t rm = extmul_prep(rr);
+        eacc Ss, Sx;
+        eacc_zero(Ss); eacc_zero(Sx);
+        uint32_t s = 0, ph = 0;
+#pragma unroll 1
+        for (uint32_t i = 0; i < nrows; i++) {
+            if (tid == 0 && i >= 1 && i - 1 + STAGES < nrows) {
+                const uint32_t ps = (i - 1) % STAGES, pph = ((i - 1) / STAGES) & 1;
+                mbar_wait(bar_empty + 8 * ps, pph);
+                issue(i - 1 + STAGES);
+            }
+            mbar_wait(bar_full + 8 * s, ph);
+            const uint32_t st = sbase + s * STAGEB;
+            const uint64_t item = (r0 + i) * 256 + tid;
+            ext_t y0 = lds_ext(st + toff + ((0 ^ sx) << 4)), y1 = lds_ext(st + toff + ((1 ^ sx) << 4));
+            ext_t y2 = lds_ext(st + toff + ((2 ^ sx) << 4)), y3 = lds_ext(st + toff + ((3 ^ sx) << 4));
+            ext_t z0 = lds_ext(st + ROWB + toff + ((0 ^ sx) << 4)), z1 = lds_ext(st + ROWB + toff + ((1 ^ sx) << 4));
+            ext_t z2 = lds_ext(st + ROWB + toff + ((2 ^ sx) << 4)), z3 = lds_ext(st + ROWB + toff + ((3 ^ sx) << 4));
+            const ext_t hw0 = lds_ext(st + 2 * ROWB), hw1 = lds_ext(st + 2 * ROWB + 16);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+            if (canon) {
+                y0 = ext_canon(y0); y1 = ext_canon(y1); y2 = ext_canon(y2); y3 = ext_canon(y3);
+                z0 = ext_canon(z0); z1 = ext_canon(z1); z2 = ext_canon(z2); z3 = ext_canon(z3);
+            }
+            const ext_t af = ext_fma_prep(y0, ext_sub(y1, y0), rm), as_ = ext_fma_prep(y2, ext_sub(y3, y2), rm);
+            const ext_t bf = ext_fma_prep(z0, ext_sub(z1, z0), rm), bs = ext_fma_prep(z2, ext_sub(z3, z2), rm);
+            st_ext(outA + 2 * item, af);
+            st_ext(outA + 2 * item + 1, as_);
+            st_ext(outB + 2 * item, bf);
+            st_ext(outB + 2 * item + 1, bs);
+            extmul_t W; W.c0 = hw0.c0; W.c1 = hw0.c1; W.c1_7 = hw1.c0;
+            veq_item2(af, as_, bf, bs, W, Ss, Sx);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        asm volatile("fence.proxy.async.global;" ::: "memory");   // this round's stores are the next round's bulk-copy sources
+        const ulonglong4 lv = ld_tab(a.L + ((size_t)j << CG_VEQ_LO_BITS) + tid);
+        extmul_t Lm; Lm.c0 = lv.x; Lm.c1 = lv.y; Lm.c1_7 = lv.z;
+        ext_t acc[3] = {ext_mul_prep(eacc_weak(Ss), Lm), ext_mul_prep(eacc_weak(Sx), Lm), ext_zero()};
+#pragma unroll
+        for (int x = 0; x < 2; x++) {
+            const ext_t v = warp_reduce_ext(acc[x]);
+            if (lane == 0) s_part[warp][x] = v;
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int x = 0; x < 2; x++) {
+                const ext_t v = warp_reduce_ext(lane < 8 ? s_part[lane][x] : ext_zero());
+                if (lane == 0) a.partials[(size_t)blockIdx.x * 3 + x] = v;
+            }
+            if (lane == 0) {
+                __threadfence();   // partial + this block's folded outputs are visible before the ticket
+                const unsigned tk = atomicAdd(a.ticket, 1u);
+                if (tk == gridDim.x * (step + 1) - 1) s_flag = 1;
+            }
+        }
+        __syncthreads();
+        if (s_flag == 1) {   // last block of the round: combine, exchange, solve q(0), challenge, release
+            __threadfence();
+            ext_t res[3];
+#pragma unroll
+            for (int x = 0; x < 2; x++) {
+                ext_t v = ext_zero();
+                for (unsigned b = tid; b < gridDim.x; b += blockDim.x) {
+                    const ulonglong2 p = __ldcg(reinterpret_cast<const ulonglong2*>(&a.partials[(size_t)b * 3 + x]));
+                    v = ext_add(v, ext_make(p.x, p.y));
+                }
+                v = warp_reduce_ext(v);
+                if (lane == 0) s_part[warp][x] = v;
+            }
+            __syncthreads();
+            if (warp == 0) {
+#pragma unroll
+                for (int x = 0; x < 2; x++) res[x] = warp_reduce_ext(lane < 8 ? s_part[lane][x] : ext_zero());
+                res[2] = ext_zero();
+                VeqFin fin = a.fin;
+                fin.round = j;
+                fin.fold = 1;
+                fin.derive = 1;
+                fin.r = r_cur;
+                fin.r_ptr = nullptr;
+                if (lane == 0) fin.pre(res);
+                if (a.comm.nranks > 1) comm_exchange<3>(res, a.comm, a.comm.seq + step, s_msg);
+                if (lane == 0) {
+                    fin.post(res);
+                    ext_t rn = ext_zero();
+#pragma unroll
+                    for (int x = 0; x < 3; x++) a.d_msgs[(size_t)j * 3 + x] = res[x];
+                    bool abort = false;
+                    if (a.d_tr_state) {
+                        uint64_t h = *a.d_tr_state;
+                        rn = cg_tr_round<3>(h, res);
+                        *a.d_tr_state = h;
+                    } else {
+                        TailMailbox* mb = a.mail;
+                        mailbox_post<3>(mb, res, (uint64_t)j + 1);
+                        const long long t0 = clock64();
+                        while (true) {
+                            const int st = mailbox_poll(mb, (uint64_t)j + 1, rn);
+                            if (st == 1) break;
+                            if (st < 0 || (unsigned long long)(clock64() - t0) > a.timeout_cycles) { abort = true; *a.d_error = 1; break; }
+                        }
+                    }
+                    a.d_chal[j] = rn;
+                    __threadfence();
+                    *a.round_flag = abort ? 0xFFFFFFFFu : (j + 1);   // release
+                }
+            }
+        }
+        if (tid == 0) {   // every block: wait for the round to be released, pick up the challenge
+            const long long t0 = clock64();
+            unsigned fl;
+            while ((fl = *a.round_flag) < j + 1) {
+                if ((unsigned long long)(clock64() - t0) > 2 * a.timeout_cycles) { fl = 0xFFFFFFFFu; break; }
+            }
+            if (fl == 0xFFFFFFFFu) s_flag = 2;
+            else {
+                const ulonglong2 p = __ldcg(reinterpret_cast<const ulonglong2*>(&a.d_chal[j]));
+                s_r = ext_make(p.x, p.y);
+            }
+        }
+        __syncthreads();
+        if (s_flag == 2) return;
+        __threadfence();   // acquire: the other blocks' folded outputs (the gpu-scope fence also invalidates L1)
+        r_cur = s_r;
+    }
+}
+
 // all tables of the split rounds in one launch: entry = direct product over its variables
 struct VeqTabArgs {
     const ext_t* w;

@@ -157,6 +157,7 @@ int cg_mle_evaluate(cg_ctx* ctx, const cg_mle_desc* mle, const uint64_t* h_point
 #define CG_SC_NO_TAIL 8u       /* one launch per round to the end (no persistent shared-memory tail kernel) */
 #define CG_SC_NO_PLAN 16u      /* evaluate monomial terms one by one (no grouping by shared ext factors) */
 #define CG_SC_NO_MID 32u       /* no cooperative persistent kernel for the mid-size rounds */
+#define CG_SC_NO_PERSIST 128u  /* one launch per split-eq round (no persistent cooperative round kernel; testing / per-launch profiling) */
 #define CG_SC_NO_DERIVE 64u    /* split-eq rounds accumulate all three bilinear sums (no claim-derived q(0); testing) */
 #define CG_SC_PROFILE 4u       /* time each round's kernels with CUDA events on the launching stream */
 int cg_sumcheck_create(cg_ctx* ctx, const cg_mle_desc* mles, uint32_t n_mles,

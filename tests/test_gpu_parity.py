@@ -636,7 +636,7 @@ def test_prove_rotation_bit_exact(dev, log2, subgroup, k, n_rot):
         m.free()
 
 
-@pytest.mark.parametrize("case", ["default", "no_derive", "w_one", "w_zero"])
+@pytest.mark.parametrize("case", ["default", "no_derive", "no_persist", "w_one", "w_zero"])
 def test_split_eq_claim_derived_rounds(dev, case):
     """Split-eq rounds >= 1 accumulate q(1) and the X^2 coefficient only and solve q(0) from the running claim
     ((1 - w_j) q(0) + w_j q(1) = q_{j-1}(r_{j-1})); the flag CG_SC_NO_DERIVE and a point with w_j = 1 (no inverse of
@@ -655,7 +655,7 @@ def test_split_eq_claim_derived_rounds(dev, case):
     b = cb.MultilinearExtension.from_evaluations_ext_vec(dev, k, b_h)
     terms = [([1, 0], [0, 1, 2])]
     want = orc.sumcheck_prove([(orc.build_eq_x_r_vec(w), True, k), (a_h, True, k), (b_h, True, k)], terms, k, 3, transcript=orc.Transcript(b"derive"))
-    flags = 64 if case == "no_derive" else 0
+    flags = 64 if case == "no_derive" else (128 if case == "no_persist" else 0)   # CG_SC_NO_DERIVE / CG_SC_NO_PERSIST
     for devch in (False, True):
         got = cb.IOPProverState.prove(dev, [cb.EqPolynomial(dev, w), a, b], terms, k, 3, transcript=cb.StandInTranscript(b"derive"),
                                       device_challenger=devch, flags=flags)
