@@ -75,7 +75,8 @@ SYMBOLS = [
     "cg_launch_count", "cg_build_eq", "cg_selector_compute", "cg_fix_variable", "cg_mle_evaluate", "cg_sumcheck_create",
     "cg_sumcheck_round_eval", "cg_sumcheck_bind", "cg_sumcheck_final_evals", "cg_sumcheck_round", "cg_sumcheck_peek",
     "cg_sumcheck_destroy", "cg_sumcheck_prove", "cg_sumcheck_prove_standin_device", "cg_standin_init",
-    "cg_standin_append_message", "cg_standin_append_ext", "cg_standin_sample", "cg_standin_challenge_cb", "cg_tower_interleave_out_len", "cg_tower_interleave", "cg_tower_build", "cg_tower_build_virtual",
+    "cg_standin_append_message", "cg_standin_append_ext", "cg_standin_sample", "cg_standin_challenge_cb", "cg_tower_interleave_out_len", "cg_tower_interleave", "cg_tower_build", "cg_tower_build_virtual", "cg_tower_build_sharded", "cg_tower_build_virtual_sharded",
+    "cg_comm_arena_create", "cg_comm_arena_connect",
     "cg_tower_output_evals", "cg_tower_proof_len", "cg_tower_point_len", "cg_tower_create_proof", "cg_tower_destroy",
     "cg_standin_vt", "cg_wit_infer_by_monomial_expr", "cg_profile_last",
     "cg_comm_create", "cg_comm_connect", "cg_comm_destroy", "cg_sumcheck_attach_comm", "cg_sumcheck_prove_sharded",
@@ -141,6 +142,10 @@ def load():
         "cg_tower_interleave": (i32, [vp, P(CgMleDesc), u32, u64, u32, vp, vp, vp]),
         "cg_tower_build": (i32, [vp, P(CgTowerSpec), u32, vp, P(vp)]),
         "cg_tower_build_virtual": (i32, [vp, P(CgTowerVSpec), u32, vp, P(vp)]),
+        "cg_tower_build_sharded": (i32, [vp, vp, P(CgTowerSpec), u32, vp, P(vp)]),
+        "cg_tower_build_virtual_sharded": (i32, [vp, vp, P(CgTowerVSpec), u32, vp, P(vp)]),
+        "cg_comm_arena_create": (i32, [vp, sz, vp]),
+        "cg_comm_arena_connect": (i32, [vp, vp]),
         "cg_tower_output_evals": (i32, [vp, u32, vp]),
         "cg_tower_proof_len": (u64, [vp]),
         "cg_tower_point_len": (u32, [vp]),

@@ -392,6 +392,16 @@ class Comm:
         if barrier:
             barrier()
 
+    def create_arena(self, nbytes, exchange_handles):
+        """Peer-mapped arena for sharded towers (cg_comm_arena_create / _connect): the same size on every rank."""
+        handle = (C.c_uint8 * 64)()
+        self.dev.check(self.dev.lib.cg_comm_arena_create(self.h, nbytes, handle))
+        blobs = exchange_handles(bytes(handle))
+        allh = (C.c_uint8 * (64 * self.nranks)).from_buffer_copy(b"".join(blobs))
+        self.dev.check(self.dev.lib.cg_comm_arena_connect(self.h, allh))
+        if self.barrier:
+            self.barrier()
+
     def close(self):
         if self.h:
             if self.barrier:
@@ -465,8 +475,26 @@ class VirtualTowerSpec:
 
 class TowerProver:
     @classmethod
-    def from_records(cls, dev, vspecs, stream=None):
-        """cg_tower_build_virtual: towers over virtual leaf layers."""
+    def sharded(cls, dev, comm, specs, stream=None):
+        """cg_tower_build_sharded: `specs` carry this rank's slice of both fan-in halves of every leaf array and the GLOBAL
+        num_vars; create_proof returns the global proof on every rank."""
+        self = cls.__new__(cls)
+        self.dev = dev
+        arr = (_lib.CgTowerSpec * len(specs))()
+        for i, s in enumerate(specs):
+            for z in range(4):
+                m = s.leaves[z] if z < len(s.leaves) else None
+                arr[i].leaves[z] = m.buf.ptr if m is not None else None
+            arr[i].num_vars = s.num_vars
+            arr[i].is_logup = 1 if s.is_logup else 0
+        self.h = C.c_void_p()
+        dev.check(dev.lib.cg_tower_build_sharded(dev.ctx, comm.h, arr, len(specs), C.c_void_p(stream) if stream else None, C.byref(self.h)))
+        self.specs = specs
+        return self
+
+    @classmethod
+    def from_records(cls, dev, vspecs, stream=None, comm=None):
+        """cg_tower_build_virtual (comm=None) / cg_tower_build_virtual_sharded: towers over virtual leaf layers."""
         self = cls.__new__(cls)
         self.dev = dev
         arr = (_lib.CgTowerVSpec * len(vspecs))()
@@ -483,7 +511,10 @@ class TowerProver:
             group(arr[i].p, v.numerators, v.num_instances, v.numerator_default)
             arr[i].is_logup = 1 if v.is_logup else 0
         self.h = C.c_void_p()
-        dev.check(dev.lib.cg_tower_build_virtual(dev.ctx, arr, len(vspecs), C.c_void_p(stream) if stream else None, C.byref(self.h)))
+        if comm is not None:
+            dev.check(dev.lib.cg_tower_build_virtual_sharded(dev.ctx, comm.h, arr, len(vspecs), C.c_void_p(stream) if stream else None, C.byref(self.h)))
+        else:
+            dev.check(dev.lib.cg_tower_build_virtual(dev.ctx, arr, len(vspecs), C.c_void_p(stream) if stream else None, C.byref(self.h)))
         self.specs, self._keep = vspecs, keep
         return self
 

@@ -472,7 +472,7 @@ static int build_eq_dev(cg_ctx* c, const ext_t* d_point, uint32_t k, ext_t* d_ou
     int rc = eq_small(c, d_point, lo_k, (ext_t*)L, st);
     if (rc == CG_OK) rc = build_eq_dev(c, d_point + lo_k, hi_k, (ext_t*)H, 0, 1ULL << hi_k, st);
     if (rc == CG_OK) {
-        eq_outer_kernel<<<grid_for(c, n / 2, 8), CG_THREADS, 0, st>>>((const ext_t*)L, (const ext_t*)H, lo_k, n, start, end, d_out);
+        eq_outer_kernel<<<grid_for(c, n / CG_EQ_PER_THREAD, 8), CG_THREADS, 0, st>>>((const ext_t*)L, (const ext_t*)H, lo_k, n, start, end, d_out);
         LAUNCHED(c);
         if (cudaGetLastError() != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "eq_outer_kernel launch failed");
     }
@@ -599,6 +599,11 @@ struct cg_comm {
     CommBuf* peers[CG_MAX_RANKS] = {nullptr};
     uint64_t seq = 1;        // next exchange sequence number (identical on every rank)
     uint64_t gather_calls = 0;
+    uint64_t bar_seq = 0;    // rank barriers so far (identical on every rank)
+    // peer-mapped arena (sharded tower layers are written by the partner ranks' layer kernels over NVLink): every rank allocates
+    // the same size and carves it with the same sequence of requests, so an offset means the same buffer on every rank
+    char* arena[CG_MAX_RANKS] = {nullptr};
+    size_t arena_bytes = 0, arena_off = 0;
     int* d_error = nullptr;
     unsigned long long* d_dbg = nullptr;
 };
@@ -647,10 +652,50 @@ CG_EXPORT int cg_comm_connect(cg_comm* cm, const uint8_t* all_handles) {
     }
     return CG_OK;
 }
+CG_EXPORT int cg_comm_arena_create(cg_comm* cm, size_t bytes, uint8_t handle_out[64]) {
+    if (!cm || !handle_out || bytes == 0) return CG_ERR_INVALID;
+    cg_ctx* c = cm->ctx;
+    if (cm->arena[cm->rank]) return set_err(c, CG_ERR_STATE, "cg_comm_arena_create: the arena exists already");
+    CU(c, cudaSetDevice(c->device));
+    void* p = nullptr;
+    CU(c, cudaMalloc(&p, bytes));
+    cm->arena[cm->rank] = (char*)p;
+    cm->arena_bytes = bytes;
+    cudaIpcMemHandle_t h;
+    memset(&h, 0, sizeof(h));
+    if (cm->nranks > 1) CU(c, cudaIpcGetMemHandle(&h, p));
+    memcpy(handle_out, &h, 64);
+    return CG_OK;
+}
+CG_EXPORT int cg_comm_arena_connect(cg_comm* cm, const uint8_t* all_handles) {
+    if (!cm || !all_handles || !cm->arena[cm->rank]) return CG_ERR_INVALID;
+    cg_ctx* c = cm->ctx;
+    CU(c, cudaSetDevice(c->device));
+    for (int p = 0; p < cm->nranks; p++) {
+        if (p == cm->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all_handles + 64 * (size_t)p, 64);
+        void* ptr = nullptr;
+        CU(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        cm->arena[p] = (char*)ptr;
+    }
+    return CG_OK;
+}
+// bump allocation: the same call sequence on every rank yields the same offsets
+static int arena_alloc(cg_comm* cm, size_t bytes, size_t* off) {
+    const size_t a = (cm->arena_off + 255) & ~(size_t)255;
+    if (!cm->arena[cm->rank] || a + bytes > cm->arena_bytes) return set_err(cm->ctx, CG_ERR_OOM, "sharded tower: the peer arena is too small (cg_comm_arena_create)");
+    *off = a;
+    cm->arena_off = a + bytes;
+    return CG_OK;
+}
+static int comm_barrier(cg_comm* cm, cudaStream_t st);
 CG_EXPORT int cg_comm_destroy(cg_comm* cm) {
     if (!cm) return CG_ERR_INVALID;
     cudaSetDevice(cm->ctx->device);
     cudaDeviceSynchronize();
+    for (int p = 0; p < cm->nranks; p++)
+        if (cm->arena[p]) { if (p == cm->rank) cudaFree(cm->arena[p]); else cudaIpcCloseMemHandle(cm->arena[p]); }
     if (cm->d_dbg) {   // CG_COMM_DEBUG: dump the last exchanges' wait times
         std::vector<unsigned long long> h(1024 * 4);
         cudaMemcpy(h.data(), cm->d_dbg, h.size() * 8, cudaMemcpyDeviceToHost);
@@ -678,6 +723,15 @@ static void comm_dev(cg_comm* cm, CommDev& d, uint64_t n_exchanges) {
     d.d_error = cm->d_error;
     d.timeout_cycles = cm->ctx->wait_timeout_cycles;
     d.dbg = cm->d_dbg;
+}
+static int comm_barrier(cg_comm* cm, cudaStream_t st) {
+    if (!cm || cm->nranks <= 1) return CG_OK;
+    CommDev d;
+    comm_dev(cm, d, 0);
+    comm_barrier_kernel<<<1, 32, 0, st>>>(d, ++cm->bar_seq);
+    cm->ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) return set_err(cm->ctx, CG_ERR_CUDA, "comm_barrier_kernel launch failed");
+    return CG_OK;
 }
 static int comm_check(cg_comm* cm, cudaStream_t st) {
     if (!cm || cm->nranks <= 1) return CG_OK;
@@ -918,6 +972,10 @@ static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles,
                            "mixed num_vars (the frontloaded batched main sumcheck) is served by cg_sumcheck_prove, not by the step API");
         if (mles[i].is_ext == CG_MLE_EQ) {   // virtual eq: dptr is the HOST point
             if (!mles[i].dptr && num_vars) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: virtual eq MLE without a point");
+            cudaPointerAttributes pa;          // every other kind carries a device pointer in this field: catch the mix-up
+            if (mles[i].dptr && cudaPointerGetAttributes(&pa, mles[i].dptr) == cudaSuccess && pa.type == cudaMemoryTypeDevice)
+                return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: a CG_MLE_EQ descriptor carries its point in HOST memory (dptr is a device pointer)");
+            cudaGetLastError();
             continue;
         }
         if (mles[i].is_ext > CG_MLE_EQ) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: unknown MLE kind");
@@ -2192,6 +2250,52 @@ CG_EXPORT int cg_sumcheck_prove_standin_device(cg_ctx* c, const cg_mle_desc* mle
 }
 
 
+// the rounds of a sharded sumcheck whose state `sc` was created with (comm, extra_rounds = log2 nranks); consumes sc
+static int sc_run_sharded(cg_ctx* c, cg_comm* cm, cg_sumcheck* sc, uint32_t n_mles, const uint64_t* coeff, const uint32_t* off, const uint32_t* idx,
+                          uint32_t n_terms, uint32_t num_vars_global, uint32_t degree, uint32_t flags, cg_challenge_cb cb, void* user,
+                          uint64_t* h_standin_state, uint64_t* h_rounds, uint64_t* h_final, uint64_t* h_chal, cg_stream s) {
+    int g = 0;
+    while ((1 << g) < cm->nranks) g++;
+    const uint32_t k_local = num_vars_global - g;
+    cudaStream_t st = S(c, s);
+    std::vector<uint64_t> fin_local(2 * (size_t)(n_mles ? n_mles : 1));
+    int rc = h_standin_state ? sc_run_device(sc, h_standin_state, h_rounds, fin_local.data(), h_chal)
+                             : sc_run_host(sc, cb, user, h_rounds, fin_local.data(), h_chal);
+    if (rc == CG_OK) rc = comm_check(cm, st);
+    if (rc != CG_OK || g == 0 || sc->extra_done) {
+        if (rc == CG_OK && h_final) memcpy(h_final, fin_local.data(), sizeof(uint64_t) * 2 * n_mles);
+        cg_sumcheck_destroy(sc);
+        return rc;
+    }
+    // all-gather the m final local evaluations (they sit in sc->d_final) into every mailbox
+    const int par = (int)(cm->gather_calls++ & 1);
+    CommDev cd;
+    comm_dev(cm, cd, 1);
+    comm_allgather_kernel<<<1, 64, 0, st>>>(sc->d_final, (int)n_mles, cd, par);
+    LAUNCHED(c);
+    if (cudaGetLastError() != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "comm_allgather_kernel launch failed");
+    if (k_local == 0 && rc == CG_OK) {
+        // zero local rounds: d_final was never written by a fold; the single local values are the inputs
+        rc = set_err(c, CG_ERR_UNSUPPORTED, "sharded prove needs at least one local variable per rank");
+    }
+    cg_sumcheck* sc2 = nullptr;
+    if (rc == CG_OK) {
+        std::vector<cg_mle_desc> gd(n_mles);
+        for (uint32_t i = 0; i < n_mles; i++) gd[i] = cg_mle_desc{&cm->mine->gather.v[par][i][0], (uint64_t)cm->nranks, (uint32_t)g, 1u};
+        rc = cg_sumcheck_create(c, gd.data(), n_mles, coeff, off, idx, n_terms, (uint32_t)g, degree, flags, s, &sc2);
+        if (rc == CG_OK) sc2->profile_append = true;
+    }
+    if (rc == CG_OK) {
+        uint64_t* r2 = h_rounds + (size_t)k_local * degree * 2;
+        uint64_t* c2 = h_chal ? h_chal + (size_t)k_local * 2 : nullptr;
+        rc = h_standin_state ? sc_run_device(sc2, h_standin_state, r2, h_final, c2) : sc_run_host(sc2, cb, user, r2, h_final, c2, k_local);
+    }
+    if (rc == CG_OK) rc = comm_check(cm, st);
+    if (sc2) cg_sumcheck_destroy(sc2);
+    cg_sumcheck_destroy(sc);
+    return rc;
+}
+
 // Sharded prove: this rank holds the slice [rank 2^(k-g), (rank+1) 2^(k-g)) of every MLE
 // (descs carry num_vars = k - g).  Rounds 0..k-g-1 run locally with the in-kernel NVLink exchange of
 // the partial sums; the final local evaluations are all-gathered into every rank's mailbox and the
@@ -2232,42 +2336,7 @@ CG_EXPORT int cg_sumcheck_prove_sharded(cg_ctx* c, cg_comm* cm, const cg_mle_des
     cg_sumcheck* sc = nullptr;
     // the persistent tail kernel continues through the replicated rounds when it can (extra_rounds = g)
     CHK(sc_create_terms(c, mles, n_mles, coeff, off, idx, n_terms, k_local, degree, flags, s, n_veq ? &veq_scale : nullptr, &sc, cm, (uint32_t)g));
-    std::vector<uint64_t> fin_local(2 * (size_t)(n_mles ? n_mles : 1));
-    int rc = h_standin_state ? sc_run_device(sc, h_standin_state, h_rounds, fin_local.data(), h_chal)
-                             : sc_run_host(sc, cb, user, h_rounds, fin_local.data(), h_chal);
-    if (rc == CG_OK) rc = comm_check(cm, st);
-    if (rc != CG_OK || g == 0 || sc->extra_done) {
-        if (rc == CG_OK && h_final) memcpy(h_final, fin_local.data(), sizeof(uint64_t) * 2 * n_mles);
-        cg_sumcheck_destroy(sc);
-        return rc;
-    }
-    // all-gather the m final local evaluations (they sit in sc->d_final) into every mailbox
-    const int par = (int)(cm->gather_calls++ & 1);
-    CommDev cd;
-    comm_dev(cm, cd, 1);
-    comm_allgather_kernel<<<1, 64, 0, st>>>(sc->d_final, (int)n_mles, cd, par);
-    LAUNCHED(c);
-    if (cudaGetLastError() != cudaSuccess) rc = set_err(c, CG_ERR_CUDA, "comm_allgather_kernel launch failed");
-    if (k_local == 0 && rc == CG_OK) {
-        // zero local rounds: d_final was never written by a fold; the single local values are the inputs
-        rc = set_err(c, CG_ERR_UNSUPPORTED, "sharded prove needs at least one local variable per rank");
-    }
-    cg_sumcheck* sc2 = nullptr;
-    if (rc == CG_OK) {
-        std::vector<cg_mle_desc> gd(n_mles);
-        for (uint32_t i = 0; i < n_mles; i++) gd[i] = cg_mle_desc{&cm->mine->gather.v[par][i][0], (uint64_t)cm->nranks, (uint32_t)g, 1u};
-        rc = cg_sumcheck_create(c, gd.data(), n_mles, coeff, off, idx, n_terms, (uint32_t)g, degree, flags, s, &sc2);
-        if (rc == CG_OK) sc2->profile_append = true;
-    }
-    if (rc == CG_OK) {
-        uint64_t* r2 = h_rounds + (size_t)k_local * degree * 2;
-        uint64_t* c2 = h_chal ? h_chal + (size_t)k_local * 2 : nullptr;
-        rc = h_standin_state ? sc_run_device(sc2, h_standin_state, r2, h_final, c2) : sc_run_host(sc2, cb, user, r2, h_final, c2, k_local);
-    }
-    if (rc == CG_OK) rc = comm_check(cm, st);
-    if (sc2) cg_sumcheck_destroy(sc2);
-    cg_sumcheck_destroy(sc);
-    return rc;
+    return sc_run_sharded(c, cm, sc, n_mles, coeff, off, idx, n_terms, num_vars_global, degree, flags, cb, user, h_standin_state, h_rounds, h_final, h_chal, s);
 }
 
 // ------------------------------------------------------------------- fold / evaluate helpers
@@ -2349,7 +2418,8 @@ struct TowerSpecState {
     bool is_logup = false;
     uint32_t num_vars = 0;
     uint32_t layers = 0;             // witness.len(): product num_vars, logup num_vars + 1
-    std::vector<const ext_t*> layer; // layer[l] -> base of [a|b] or [p1|p2|q1|q2] with arrays of 2^l ext
+    std::vector<const ext_t*> layer; // layer[l] -> base of [a|b] or [p1|p2|q1|q2] with arrays of len[l] ext
+    std::vector<uint64_t> len;       // array length of layer l on this rank: 2^l, or 2^l / nranks for a distributed layer
     const ext_t* leaves[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ones = false;               // logup numerators implicit ones
     bool virt = false;               // the leaf layer is described, not stored (cg_tower_build_virtual)
@@ -2362,7 +2432,12 @@ struct cg_tower {
     std::vector<void*> owned;
     uint32_t max_round = 0;          // max_round_index
     uint32_t n_prod = 0, n_logup = 0;
+    // sharded tower (cg_tower_build_sharded): layers >= dist_from are sliced over the ranks of `comm` (rank r holds the slice r of
+    // BOTH halves of a layer), smaller layers are replicated
+    cg_comm* comm = nullptr;
+    uint32_t g = 0, dist_from = UINT32_MAX;
 };
+static bool layer_distributed(const cg_tower* tw, uint32_t l) { return tw->comm && l >= tw->dist_from; }
 CG_EXPORT int cg_tower_destroy(cg_tower* tw) {
     if (!tw) return CG_ERR_INVALID;
     for (void* p : tw->owned) tmp_free(p, tw->stream);
@@ -2375,60 +2450,112 @@ static const ext_t* tower_arr(const TowerSpecState& sp, uint32_t l, uint32_t z) 
         if (!sp.is_logup) return sp.leaves[z];
         return sp.leaves[z];
     }
-    return sp.layer[l] + ((uint64_t)z << l);
+    return sp.layer[l] + (uint64_t)z * sp.len[l];
 }
 // upper layers of one spec (infer_tower_product_witness / infer_tower_logup_witness, ceno_zkvm/src/scheme/utils.rs:488-659):
 // sp.leaves (or sp.d_virt for a virtual leaf layer), sp.layers, sp.ones are set; allocates and fills sp.layer[]
 static int tower_build_spec(cg_tower* tw, TowerSpecState& sp) {
     cg_ctx* c = tw->ctx;
     cudaStream_t st = tw->stream;
+    cg_comm* cm = tw->comm;
+    const int N = cm ? cm->nranks : 1, rank = cm ? cm->rank : 0;
     sp.layer.assign(sp.layers, nullptr);
+    sp.len.assign(sp.layers, 0);
     const uint32_t arrs = sp.is_logup ? 4 : 2;
-    // upper layers l = layers-2 .. 0, one pooled block: sum_l arrs * 2^l ext
-    const uint64_t top = sp.layers - 1;   // leaf layer index; arrays there have 2^top ext
-    void* blk = nullptr;
+    const uint64_t top = sp.layers - 1;   // leaf layer index; arrays there have 2^top ext (globally)
+    for (uint32_t l = 0; l <= top; l++) sp.len[l] = layer_distributed(tw, l) ? ((1ULL << l) / N) : (1ULL << l);
+    if (cm && !layer_distributed(tw, (uint32_t)top)) return set_err(c, CG_ERR_UNSUPPORTED, "sharded tower: the leaf layer is too small to slice (build it on one rank)");
+    // storage: layers written by peers (distributed ones and the first replicated one) live in the peer arena, at the same
+    // offset on every rank; the rest in one pooled block
+    std::vector<size_t> arena_off(sp.layers, SIZE_MAX);
+    uint64_t pooled = 0;
     const bool ones_arrays = sp.ones && !sp.virt;   // materialised all-one numerators (a virtual spec reads them as "no p arrays")
-    const uint64_t total = (uint64_t)arrs * ((1ULL << top) - 1) + (ones_arrays ? (2ULL << top) : 0);
-    if (total) {
-        CHK(tmp_alloc(c, sizeof(ext_t) * total, &blk, st));
+    for (uint32_t l = 0; l < top; l++) {
+        const bool peer_written = cm && layer_distributed(tw, l + 1);
+        if (peer_written) CHK(arena_alloc(cm, sizeof(ext_t) * arrs * sp.len[l], &arena_off[l]));
+        else pooled += (uint64_t)arrs * sp.len[l];
+    }
+    if (ones_arrays) pooled += 2 * sp.len[top];
+    void* blk = nullptr;
+    if (pooled) {
+        CHK(tmp_alloc(c, sizeof(ext_t) * pooled, &blk, st));
         tw->owned.push_back(blk);
     }
     ext_t* base = (ext_t*)blk;
-    for (uint32_t l = 0; l < top; l++) { sp.layer[l] = base; base += (uint64_t)arrs << l; }
+    for (uint32_t l = 0; l < top; l++) {
+        if (arena_off[l] != SIZE_MAX) sp.layer[l] = (const ext_t*)(cm->arena[rank] + arena_off[l]);
+        else { sp.layer[l] = base; base += (uint64_t)arrs * sp.len[l]; }
+    }
     if (ones_arrays) {   // input-layer numerators materialised as ones (utils.rs:556-577)
         sp.layer[top] = base;   // only arrays 0,1 live here; q1,q2 stay in the caller's buffers
-        fill_ext_kernel<<<grid_for(c, 2ULL << top), CG_THREADS, 0, st>>>(base, 2ULL << top, ext_t{1, 0});
+        fill_ext_kernel<<<grid_for(c, 2 * sp.len[top]), CG_THREADS, 0, st>>>(base, 2 * sp.len[top], ext_t{1, 0});
         LAUNCHED(c);
     }
     for (int32_t l = (int32_t)top - 1; l >= 0; l--) {
-        const uint64_t n = 2ULL << l;   // points combined = length of layer l+1 arrays
-        ext_t* dst = (ext_t*)sp.layer[l];
+        const uint64_t n = 2 * sp.len[l + 1] / 2 * 1;   // results of this launch = length of this rank's layer l+1 arrays
+        const uint64_t n_res = sp.len[l + 1];
+        (void)n;
         const bool from_leaves = ((uint32_t)l + 1 == top);
+        // destinations: array `zlo` takes results of the low half of the combined index, `zhi` of the high half
+        auto dst_for = [&](uint32_t z_first) {   // z_first: 0 for (a|b) / (p1|p2), 2 for (q1|q2)
+            TowerDst t;
+            memset(&t, 0, sizeof(t));
+            if (!cm || !layer_distributed(tw, l + 1)) {          // one device / replicated source: both halves are local and contiguous
+                t.d[0] = (ext_t*)sp.layer[l] + (uint64_t)z_first * sp.len[l];
+                t.n_dst = 1;
+            } else if (layer_distributed(tw, l)) {               // shuffle: my results are two slices of ONE half of layer l
+                const uint32_t part = rank < N / 2 ? 0 : 1;
+                const size_t off = arena_off[l] + sizeof(ext_t) * (uint64_t)(z_first + part) * sp.len[l];
+                t.d[0] = (ext_t*)(cm->arena[(2 * rank) % N] + off);
+                t.d[1] = (ext_t*)(cm->arena[(2 * rank + 1) % N] + off);
+                t.split = 1;
+                t.n_dst = 2;
+            } else {                                             // all-gather into the first replicated layer
+                const uint32_t part = rank < N / 2 ? 0 : 1;
+                const size_t off = arena_off[l] + sizeof(ext_t) * ((uint64_t)(z_first + part) * sp.len[l] + (uint64_t)(rank % (N / 2)) * n_res);
+                for (int p = 0; p < N; p++) t.d[p] = (ext_t*)(cm->arena[p] + off);
+                t.n_dst = N;
+            }
+            return t;
+        };
+        const TowerDst d0 = dst_for(0), d2 = dst_for(2);
         if (from_leaves && sp.virt) {
-            if (!sp.is_logup) tower_prod_layer_virt_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, st>>>(sp.d_virt[0], sp.d_virt[1], n, dst);
-            else tower_logup_layer_virt_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, st>>>(sp.d_virt[0], sp.d_virt[1], sp.d_virt[2], sp.d_virt[3], n, dst, dst + n);
+            if (!sp.is_logup) tower_prod_layer_virt_kernel<<<grid_for(c, n_res, 8), CG_THREADS, 0, st>>>(sp.d_virt[0], sp.d_virt[1], n_res, d0);
+            else tower_logup_layer_virt_kernel<<<grid_for(c, n_res, 8), CG_THREADS, 0, st>>>(sp.d_virt[0], sp.d_virt[1], sp.d_virt[2], sp.d_virt[3], n_res, d0, d2);
         } else if (!sp.is_logup) {
-            tower_prod_layer_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, st>>>(tower_arr(sp, l + 1, 0), tower_arr(sp, l + 1, 1), n, dst, from_leaves);
+            tower_prod_layer_kernel<<<grid_for(c, n_res, 8), CG_THREADS, 0, st>>>(tower_arr(sp, l + 1, 0), tower_arr(sp, l + 1, 1), n_res, d0, from_leaves);
         } else {
             const bool implicit_ones = from_leaves && sp.ones;
-            tower_logup_layer_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, st>>>(
+            tower_logup_layer_kernel<<<grid_for(c, n_res, 8), CG_THREADS, 0, st>>>(
                 implicit_ones ? nullptr : tower_arr(sp, l + 1, 0), implicit_ones ? nullptr : tower_arr(sp, l + 1, 1),
-                tower_arr(sp, l + 1, 2), tower_arr(sp, l + 1, 3), n, dst, dst + n, from_leaves);
+                tower_arr(sp, l + 1, 2), tower_arr(sp, l + 1, 3), n_res, d0, d2, from_leaves);
         }
         LAUNCHED(c);
         if (cudaGetLastError() != cudaSuccess) return set_err(c, CG_ERR_CUDA, "tower layer kernel launch failed");
+        if (cm && layer_distributed(tw, l + 1)) CHK(comm_barrier(cm, st));   // the partners' stores into my layer l are complete
     }
     if (sp.layers - 1 > tw->max_round) tw->max_round = sp.layers - 1;
     if (sp.is_logup) tw->n_logup++; else tw->n_prod++;
     return CG_OK;
 }
-CG_EXPORT int cg_tower_build(cg_ctx* c, const cg_tower_spec* specs, uint32_t n_specs, cg_stream s, cg_tower** out) {
+#define CG_TOWER_DIST_MIN_LOCAL_LOG 12   // a layer is sliced over the ranks while every rank keeps >= 2^12 entries per array
+static void tower_set_comm(cg_tower* tw, cg_comm* cm) {
+    if (!cm || cm->nranks <= 1) return;
+    tw->comm = cm;
+    tw->g = 0;
+    while ((1 << tw->g) < cm->nranks) tw->g++;
+    tw->dist_from = tw->g + CG_TOWER_DIST_MIN_LOCAL_LOG;
+    cm->arena_off = 0;   // one sharded tower at a time owns the arena ...
+    comm_barrier(cm, tw->stream);   // ... and no rank may still be reading the previous tower's layers out of it
+}
+static int tower_build_impl(cg_ctx* c, cg_comm* cm, const cg_tower_spec* specs, uint32_t n_specs, cg_stream s, cg_tower** out) {
     if (!c || !specs || !out || n_specs == 0) return set_err(c, CG_ERR_INVALID, "cg_tower_build: bad argument");
     cudaStream_t st = S(c, s);
     CU(c, cudaSetDevice(c->device));
     cg_tower* tw = new cg_tower();
     tw->ctx = c;
     tw->stream = st;
+    tower_set_comm(tw, cm);
     int rc = CG_OK;
     // reference order: product specs first, then logup specs (cpu/mod.rs:405-413)
     for (int pass = 0; pass < 2 && rc == CG_OK; pass++)
@@ -2452,6 +2579,13 @@ CG_EXPORT int cg_tower_build(cg_ctx* c, const cg_tower_spec* specs, uint32_t n_s
     if (rc != CG_OK) { cg_tower_destroy(tw); return rc; }
     *out = tw;
     return CG_OK;
+}
+CG_EXPORT int cg_tower_build(cg_ctx* c, const cg_tower_spec* specs, uint32_t n_specs, cg_stream s, cg_tower** out) {
+    return tower_build_impl(c, nullptr, specs, n_specs, s, out);
+}
+CG_EXPORT int cg_tower_build_sharded(cg_ctx* c, cg_comm* cm, const cg_tower_spec* specs, uint32_t n_specs, cg_stream s, cg_tower** out) {
+    if (!cm) return set_err(c, CG_ERR_INVALID, "cg_tower_build_sharded: null comm");
+    return tower_build_impl(c, cm, specs, n_specs, s, out);
 }
 static uint32_t ceil_log2_u64(uint64_t x) { uint32_t l = 0; while ((1ULL << l) < x) l++; return l; }
 CG_EXPORT uint64_t cg_tower_interleave_out_len(uint32_t n_mles, uint64_t num_instances, uint32_t num_limbs) {
@@ -2571,7 +2705,15 @@ static int make_virt_limbs(cg_tower* tw, const cg_tower_vgroup& g, const VirtLea
     d_out[1] = (const VirtLeaf*)d_v + 1;
     return CG_OK;
 }
+static int tower_build_virtual_impl(cg_ctx* c, cg_comm* cm, const cg_tower_vspec* specs, uint32_t n_specs, cg_stream s, cg_tower** out);
 CG_EXPORT int cg_tower_build_virtual(cg_ctx* c, const cg_tower_vspec* specs, uint32_t n_specs, cg_stream s, cg_tower** out) {
+    return tower_build_virtual_impl(c, nullptr, specs, n_specs, s, out);
+}
+CG_EXPORT int cg_tower_build_virtual_sharded(cg_ctx* c, cg_comm* cm, const cg_tower_vspec* specs, uint32_t n_specs, cg_stream s, cg_tower** out) {
+    if (!cm) return set_err(c, CG_ERR_INVALID, "cg_tower_build_virtual_sharded: null comm");
+    return tower_build_virtual_impl(c, cm, specs, n_specs, s, out);
+}
+static int tower_build_virtual_impl(cg_ctx* c, cg_comm* cm, const cg_tower_vspec* specs, uint32_t n_specs, cg_stream s, cg_tower** out) {
     if (!c || !specs || !out || n_specs == 0) return set_err(c, CG_ERR_INVALID, "cg_tower_build_virtual: bad argument");
     cudaStream_t st = S(c, s);
     CU(c, cudaSetDevice(c->device));
@@ -2582,6 +2724,8 @@ CG_EXPORT int cg_tower_build_virtual(cg_ctx* c, const cg_tower_vspec* specs, uin
     cg_tower* tw = new cg_tower();
     tw->ctx = c;
     tw->stream = st;
+    tower_set_comm(tw, cm);
+    const uint32_t gbits = tw->g;   // sharded: the local leaf arrays are 1 / 2^g of the global ones
     int rc = CG_OK;
     for (int pass = 0; pass < 2 && rc == CG_OK; pass++)
         for (uint32_t i = 0; i < n_specs && rc == CG_OK; i++) {
@@ -2597,7 +2741,7 @@ CG_EXPORT int cg_tower_build_virtual(cg_ctx* c, const cg_tower_vspec* specs, uin
             if (rc != CG_OK) break;
             if (!sp.is_logup) {
                 sp.d_virt[0] = dq[0]; sp.d_virt[1] = dq[1];
-                sp.num_vars = ceil_log2_u64(len_q) + 1;
+                sp.num_vars = ceil_log2_u64(len_q) + 1 + gbits;
                 sp.layers = sp.num_vars;
             } else {
                 sp.d_virt[2] = dq[0]; sp.d_virt[3] = dq[1];
@@ -2613,7 +2757,7 @@ CG_EXPORT int cg_tower_build_virtual(cg_ctx* c, const cg_tower_vspec* specs, uin
                 if (rc != CG_OK) break;
                 if (in.p.n_records && len_p != len_q) { rc = set_err(c, CG_ERR_INVALID, "cg_tower_build_virtual: numerator and denominator groups differ in shape"); break; }
                 sp.d_virt[0] = dp[0]; sp.d_virt[1] = dp[1];
-                sp.num_vars = ceil_log2_u64(len_q);
+                sp.num_vars = ceil_log2_u64(len_q) + gbits;
                 sp.layers = sp.num_vars + 1;
             }
             if (sp.num_vars == 0 || sp.num_vars > 34) { rc = set_err(c, CG_ERR_INVALID, "cg_tower_build_virtual: num_vars out of range"); break; }
@@ -2677,12 +2821,24 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
     double t_eq = 0, t_create = 0, t_run = 0, t_fin = 0;
     auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     for (uint32_t round = 1; round <= tw->max_round; round++) {
-        const uint32_t nv = rt_len;
+        const uint32_t nv_glob = rt_len;
+        const bool dist = layer_distributed(tw, round);   // this layer's arrays are rank slices (top g index bits = rank)
+        const uint32_t nv = dist ? nv_glob - tw->g : nv_glob;
         const uint64_t n = 1ULL << nv;
         void* d_eq = nullptr;
         const double t0 = now();
         CHK(tmp_alloc(c, sizeof(ext_t) * n, &d_eq, tw->stream));
         int rc = cg_build_eq(c, rt.data(), nv, (uint64_t*)d_eq, 0, n, tw->stream);
+        if (rc == CG_OK && dist) {   // eq(rt, .) on my slice = eq(rt_top, rank) * eq(rt_low, .)
+            ext_t sc_{1, 0};
+            for (uint32_t b = 0; b < tw->g; b++) {
+                ext_t w{rt[2 * (nv + b)] % GL_P, rt[2 * (nv + b) + 1] % GL_P};
+                if (!((tw->comm->rank >> b) & 1)) w = ext_t{hx_submod(1, w.c0), hx_submod(0, w.c1)};
+                sc_ = hx_mul(sc_, w);
+            }
+            scale_ext_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, tw->stream>>>((ext_t*)d_eq, n, sc_);
+            LAUNCHED(c);
+        }
         const double t1 = now();
         // MLE list in the reference's lift order: eq, then live product specs, then live logup specs
         std::vector<cg_mle_desc> mles;
@@ -2729,10 +2885,12 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
                 coeff.push_back(tl.lk_ad[l].c0); coeff.push_back(tl.lk_ad[l].c1);
                 idx.insert(idx.end(), {0u, q1, q2}); off.push_back((uint32_t)idx.size());
             }
-            rc = cg_sumcheck_create(c, mles.data(), (uint32_t)mles.size(), coeff.data(), off.data(), idx.data(),
-                                    (uint32_t)off.size() - 1, nv, 3, CG_SC_FORCE_GENERIC, tw->stream, &sc);
+            if (dist) rc = sc_create_terms(c, mles.data(), (uint32_t)mles.size(), coeff.data(), off.data(), idx.data(), (uint32_t)off.size() - 1, nv, 3,
+                                           CG_SC_FORCE_GENERIC, tw->stream, nullptr, &sc, tw->comm, tw->g);
+            else rc = cg_sumcheck_create(c, mles.data(), (uint32_t)mles.size(), coeff.data(), off.data(), idx.data(),
+                                         (uint32_t)off.size() - 1, nv, 3, CG_SC_FORCE_GENERIC, tw->stream, &sc);
         }
-        std::vector<uint64_t> fin(2 * mles.size()), chal(2 * (size_t)nv);
+        std::vector<uint64_t> fin(2 * mles.size()), chal(2 * (size_t)nv_glob);
         const double t2 = now();
         if (rc == CG_OK) {
             if (fits) sc->tl = tl;
@@ -2744,8 +2902,14 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
             }
         }
         if (rc == CG_OK) {
-            tr->sumcheck_begin(tr->user, nv, 3);
-            rc = sc_run_host(sc, tr->round_challenge, tr->user, h_proof + w, fin.data(), chal.data());
+            tr->sumcheck_begin(tr->user, nv_glob, 3);
+            if (dist) {
+                rc = sc_run_sharded(c, tw->comm, sc, (uint32_t)mles.size(), coeff.data(), off.data(), idx.data(), (uint32_t)off.size() - 1, nv_glob, 3,
+                                    CG_SC_FORCE_GENERIC, tr->round_challenge, tr->user, nullptr, h_proof + w, fin.data(), chal.data(), tw->stream);
+                sc = nullptr;   // consumed
+            } else {
+                rc = sc_run_host(sc, tr->round_challenge, tr->user, h_proof + w, fin.data(), chal.data());
+            }
         }
         const double t3 = now();
         if (sc) cg_sumcheck_destroy(sc);
@@ -2755,7 +2919,7 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
             t_eq += t1 - t0; t_create += t2 - t1; t_run += t3 - t2; t_fin += now() - t3;
             fprintf(stderr, "[tower] layer %2u nv=%2u eq %.0f create %.0f run %.0f destroy %.0f us\n", round, nv, t1 - t0, t2 - t1, t3 - t2, now() - t3);
         }
-        w += (uint64_t)nv * 3 * 2;
+        w += (uint64_t)nv_glob * 3 * 2;
         for (int pass = 0; pass < 2; pass++)
             for (size_t si = 0; si < tw->specs.size(); si++) {
                 const TowerSpecState& sp = tw->specs[si];
@@ -2767,10 +2931,10 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
             }
         uint64_t rm[2];
         tr->sample(tr->user, "merge", rm);
-        memcpy(rt.data(), chal.data(), sizeof(uint64_t) * 2 * nv);
-        rt[2 * nv] = rm[0];
-        rt[2 * nv + 1] = rm[1];
-        rt_len = nv + 1;
+        memcpy(rt.data(), chal.data(), sizeof(uint64_t) * 2 * nv_glob);
+        rt[2 * nv_glob] = rm[0];
+        rt[2 * nv_glob + 1] = rm[1];
+        rt_len = nv_glob + 1;
         alpha_pows(tr, n_alpha, alpha);
     }
     memcpy(h_point, rt.data(), sizeof(uint64_t) * 2 * rt_len);

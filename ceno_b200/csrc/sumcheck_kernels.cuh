@@ -48,6 +48,7 @@ struct CommGather {
 struct CommBuf {
     CommSlot slots[CG_COMM_RING][CG_MAX_RANKS];
     CommGather gather;
+    uint64_t bar[CG_MAX_RANKS];        // rank barrier: bar[p] = last barrier sequence rank p has reached
 };
 struct CommDev {
     int rank, nranks;               // nranks <= 1: no exchange
@@ -119,6 +120,20 @@ GL_DEV void comm_exchange(ext_t (&res)[D], const CommDev& cm, uint64_t seq, uint
     }
 #pragma unroll
     for (int x = 0; x < D; x++) res[x] = warp_reduce_ext(got[x]);
+}
+// rank barrier over the mailboxes (sharded tower build: every rank's peer stores of a level are complete before the next
+// level reads them).  Launched after the kernels whose stores it orders; the system fence publishes them.
+__global__ void comm_barrier_kernel(const __grid_constant__ CommDev cm, uint64_t seq) {
+    __threadfence_system();
+    if ((int)threadIdx.x < cm.nranks) {
+        *(volatile uint64_t*)&cm.peers[threadIdx.x]->bar[cm.rank] = seq;
+        volatile uint64_t* f = &cm.peers[cm.rank]->bar[threadIdx.x];
+        const long long t0 = clock64();
+        while (*f < seq) {
+            if ((unsigned long long)(clock64() - t0) > cm.timeout_cycles) { *cm.d_error = 2; break; }
+        }
+        __threadfence_system();
+    }
 }
 // all-gather of the m final local evaluations into every rank's gather area [par][mle][rank]
 __global__ void comm_allgather_kernel(const ext_t* __restrict__ d_final, int m, const __grid_constant__ CommDev cm, int par) {
@@ -1801,21 +1816,26 @@ __global__ void __launch_bounds__(1024) eq_small_kernel(const ext_t* __restrict_
     for (uint32_t b = threadIdx.x; b < (1u << k); b += blockDim.x) out[b] = s_eq[b];
 }
 // Large table: out[hi * 2^lo_k + lo] = L[lo] * H[hi], prefix mask [start, end) fused.
-// Each thread produces 2 consecutive outputs (one 256-bit store).
+// One ext product per output is ~65 instructions for 16 bytes written, so the kernel is issue-bound, not write-bound: a thread
+// keeps ONE H entry (with 7 c1 prepared once) for 8 consecutive outputs and the four independent product pairs overlap.
+#define CG_EQ_PER_THREAD 8
 __global__ void __launch_bounds__(CG_THREADS) eq_outer_kernel(const ext_t* __restrict__ L, const ext_t* __restrict__ H,
                                                                uint32_t lo_k, uint64_t n, uint64_t start, uint64_t end,
                                                                ext_t* __restrict__ out) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t lo_mask = (1ULL << lo_k) - 1;
-    for (uint64_t pair = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; pair < n / 2; pair += stride) {
-        const uint64_t b = 2 * pair;
-        const ext_t h = ld_ext(H + (b >> lo_k));
-        ext_t l0, l1;
-        ld_ext2(L + (b & lo_mask), l0, l1);
-        ext_t v0 = ext_mul(l0, h), v1 = ext_mul(l1, h);
-        if (b < start || b >= end) v0 = ext_zero();
-        if (b + 1 < start || b + 1 >= end) v1 = ext_zero();
-        st_ext2(out + b, v0, v1);
+    constexpr uint64_t CHUNK = (uint64_t)CG_THREADS * CG_EQ_PER_THREAD;   // 2048 consecutive outputs per block step: one H entry (lo_k >= 11)
+    for (uint64_t c0 = (uint64_t)blockIdx.x * CHUNK; c0 < n; c0 += (uint64_t)gridDim.x * CHUNK) {
+        const extmul_t hm = extmul_prep(ld_ext(H + (c0 >> lo_k)));
+#pragma unroll
+        for (int q = 0; q < CG_EQ_PER_THREAD / 2; q++) {
+            const uint64_t b = c0 + (uint64_t)q * (2 * CG_THREADS) + 2 * threadIdx.x;   // a warp covers 1 KB contiguous per step
+            ext_t l0, l1;
+            ld_ext2(L + (b & lo_mask), l0, l1);
+            ext_t v0 = ext_mul_prep(l0, hm), v1 = ext_mul_prep(l1, hm);
+            if (b < start || b >= end) v0 = ext_zero();
+            if (b + 1 < start || b + 1 >= end) v1 = ext_zero();
+            st_ext2(out + b, v0, v1);
+        }
     }
 }
 // generic mask passes for the selector variants (gkr_iop/src/selector.rs:141-243)
@@ -1931,20 +1951,39 @@ __global__ void __launch_bounds__(256) tower_interleave_kernel(const __grid_cons
 // tower witness layers (infer_tower_product_witness / infer_tower_logup_witness,
 // ceno_zkvm/src/scheme/utils.rs:488-659).  Layer l buffer = [a | b] (product) or [p1|p2|q1|q2]
 // (logup), each 2^l ext; layer l = pointwise combination of layer l+1's arrays over 2^(l+1) points.
+// Where the n results of a launch go.  One device: d[0].  SHARDED tower (rows sliced over the ranks): the
+// combined array is the next layer's (low half | high half), and the rank that must hold a slice of both halves is not the
+// rank that computed it, so the layer kernel stores straight into the owners' peer-mapped buffers over NVLink —
+//   split != 0: results [0, n/2) -> d[0], [n/2, n) -> d[1]   (perfect shuffle: ranks 2r and 2r+1 mod N);
+//   split == 0: every result -> d[0 .. n_dst)                (all-gather into the first replicated layer).
+struct TowerDst {
+    ext_t* d[CG_MAX_RANKS];
+    int n_dst;
+    int split;
+};
+GL_DEV void tower_store(const TowerDst& t, uint64_t x, uint64_t n, ext_t v) {
+    if (t.split) {
+        const uint64_t h = n >> 1;
+        st_ext((x < h ? t.d[0] : t.d[1]) + (x < h ? x : x - h), v);
+    } else {
+#pragma unroll 1
+        for (int p = 0; p < t.n_dst; p++) st_ext(t.d[p] + x, v);
+    }
+}
 __global__ void __launch_bounds__(CG_THREADS) tower_prod_layer_kernel(const ext_t* __restrict__ a, const ext_t* __restrict__ b,
-                                                                       uint64_t n, ext_t* __restrict__ out, int canon) {
+                                                                       uint64_t n, const __grid_constant__ TowerDst out, int canon) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) {
         ext_t u = ld_ext(a + x), v = ld_ext(b + x);
         if (canon) { u = ext_canon(u); v = ext_canon(v); }
-        st_ext(out + x, ext_mul(u, v));
+        tower_store(out, x, n, ext_mul(u, v));
     }
 }
 // p_out[x] = q1 p2 + q2 p1 (or q1 + q2 when numerators are implicit ones), q_out[x] = q1 q2
 __global__ void __launch_bounds__(CG_THREADS) tower_logup_layer_kernel(const ext_t* __restrict__ p1, const ext_t* __restrict__ p2,
                                                                         const ext_t* __restrict__ q1, const ext_t* __restrict__ q2,
-                                                                        uint64_t n, ext_t* __restrict__ p_out, ext_t* __restrict__ q_out,
-                                                                        int canon) {
+                                                                        uint64_t n, const __grid_constant__ TowerDst p_out,
+                                                                        const __grid_constant__ TowerDst q_out, int canon) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) {
         ext_t a1 = ld_ext(q1 + x), a2 = ld_ext(q2 + x);
@@ -1957,20 +1996,21 @@ __global__ void __launch_bounds__(CG_THREADS) tower_logup_layer_kernel(const ext
         } else {
             p = ext_add(a1, a2);
         }
-        st_ext(p_out + x, p);
-        st_ext(q_out + x, ext_mul(a1, a2));
+        tower_store(p_out, x, n, p);
+        tower_store(q_out, x, n, ext_mul(a1, a2));
     }
 }
 // first level above VIRTUAL leaves (description instead of arrays; p1 / p2 null = numerators are all one)
 __global__ void __launch_bounds__(CG_THREADS) tower_prod_layer_virt_kernel(const VirtLeaf* __restrict__ a, const VirtLeaf* __restrict__ b,
-                                                                            uint64_t n, ext_t* __restrict__ out) {
+                                                                            uint64_t n, const __grid_constant__ TowerDst out) {
     const VirtLeaf va = *a, vb = *b;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) st_ext(out + x, ext_mul(virt_leaf(va, x), virt_leaf(vb, x)));
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) tower_store(out, x, n, ext_mul(virt_leaf(va, x), virt_leaf(vb, x)));
 }
 __global__ void __launch_bounds__(CG_THREADS) tower_logup_layer_virt_kernel(const VirtLeaf* __restrict__ p1, const VirtLeaf* __restrict__ p2,
                                                                              const VirtLeaf* __restrict__ q1, const VirtLeaf* __restrict__ q2,
-                                                                             uint64_t n, ext_t* __restrict__ p_out, ext_t* __restrict__ q_out) {
+                                                                             uint64_t n, const __grid_constant__ TowerDst p_out,
+                                                                             const __grid_constant__ TowerDst q_out) {
     const VirtLeaf v1 = *q1, v2 = *q2;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) {
@@ -1978,8 +2018,8 @@ __global__ void __launch_bounds__(CG_THREADS) tower_logup_layer_virt_kernel(cons
         ext_t p;
         if (p1) p = ext_add(ext_mul(a1, virt_leaf(*p2, x)), ext_mul(a2, virt_leaf(*p1, x)));
         else p = ext_add(a1, a2);
-        st_ext(p_out + x, p);
-        st_ext(q_out + x, ext_mul(a1, a2));
+        tower_store(p_out, x, n, p);
+        tower_store(q_out, x, n, ext_mul(a1, a2));
     }
 }
 // ---------------------------------------------------------------------------------------------

@@ -287,6 +287,20 @@ typedef struct cg_tower_vspec {
     uint32_t reserved;
 } cg_tower_vspec;
 int cg_tower_build_virtual(cg_ctx* ctx, const cg_tower_vspec* specs, uint32_t n_specs, cg_stream s, cg_tower** out);
+/* SHARDED towers (BASELINE config #4: a chip's rows sliced over the GPUs of one box; new — the reference is single-device).
+ * Rank r passes its slice r of BOTH fan-in halves of every leaf array (cg_tower_build_sharded: leaves[] point to the local
+ * slices, num_vars is the GLOBAL one) or its slice of the record MLEs with the two fan-in row blocks back to back
+ * (cg_tower_build_virtual_sharded: exactly a chip of rows / nranks rows).  A layer stays sliced while every rank keeps
+ * >= 2^12 entries per array; the layer kernels store their products straight into the owning partner ranks' peer-mapped
+ * buffers over NVLink (results [0, n/2) to rank 2r mod N, [n/2, n) to rank 2r+1 mod N: the rank that needs a slice of both
+ * halves of the next layer is not the one that computed it), small layers are all-gathered and replicated.
+ * cg_tower_create_proof then runs the big layers' sumchecks sharded (in-kernel exchange of the round sums, early all-gather
+ * into the replicated cluster tail) and the small ones replicated; the proof is identical on every rank and equal to the
+ * single-device proof.  Needs a peer arena (cg_comm_arena_create / _connect, same size on every rank, >= the sliced layers). */
+int cg_comm_arena_create(cg_comm* comm, size_t bytes, uint8_t handle_out[64]);
+int cg_comm_arena_connect(cg_comm* comm, const uint8_t* all_handles /* nranks * 64 bytes, rank order */);
+int cg_tower_build_sharded(cg_ctx* ctx, cg_comm* comm, const cg_tower_spec* specs, uint32_t n_specs, cg_stream s, cg_tower** out);
+int cg_tower_build_virtual_sharded(cg_ctx* ctx, cg_comm* comm, const cg_tower_vspec* specs, uint32_t n_specs, cg_stream s, cg_tower** out);
 int cg_tower_build(cg_ctx* ctx, const cg_tower_spec* specs, uint32_t n_specs, cg_stream s, cg_tower** out);
 /* get_output_evals (ceno_zkvm/src/scheme/gpu/mod.rs:369-420): layer-0 values of spec i:
  * 2 ext for a product spec, 4 for a logup spec. */

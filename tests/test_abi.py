@@ -118,5 +118,6 @@ def test_integration_doc_binds_only_declared_symbols():
     assert rust and rust <= declared, sorted(rust - declared)
     design = open(os.path.join(root, "DESIGN.md")).read()
     named = {n for n in re.findall(r"`(cg_[a-z0-9_]+)`", design) if not n.endswith("_")}
-    structs = {"cg_mle_desc", "cg_challenge_cb", "cg_transcript_vt", "cg_tower_spec", "cg_sched_task", "cg_sched_result", "cg_stream", "cg_ctx"}
+    structs = {"cg_mle_desc", "cg_challenge_cb", "cg_transcript_vt", "cg_tower_spec", "cg_sched_task", "cg_sched_result", "cg_stream", "cg_ctx",
+               "cg_pcs_transcript_vt", "cg_tower_vspec", "cg_tower_vgroup", "cg_basefold_params", "cg_basefold_opening", "cg_pcs_commitment"}
     assert named - structs <= declared, sorted(named - structs - declared)

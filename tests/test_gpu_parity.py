@@ -939,6 +939,96 @@ def test_sharded_commit_multi_gpu_bit_exact():
     assert sorted(res) == [(r, True) for r in range(world)]
 
 
+def _dist_tower_worker(rank, world, port, q):
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import ceno_b200 as cb
+    dev = cb.Device(rank)
+
+    def xchg(blob):
+        outs = [None] * world
+        dist.all_gather_object(outs, blob)
+        return outs
+    comm = cb.Comm(dev, rank, world, xchg, barrier=dist.barrier)
+    comm.create_arena(256 << 20, xchg)
+    ok = True
+    # (a) materialised leaves: 2 product specs of different depth + 1 logup spec with explicit numerators
+    prod_nvs, logup_nvs = [17, 16], [15]
+    o_prod, o_lk, specs, keep = [], [], [], []
+    for i, nv in enumerate(prod_nvs):
+        half = 1 << (nv - 1)
+        f1, f2 = orc.fill_ext(6100 + 2 * i, half), orc.fill_ext(6101 + 2 * i, half)
+        o_prod.append((orc.infer_tower_product_witness(nv, f1, f2)[0], nv))
+        loc = half // world
+        ms = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, (nv - 1) - (world.bit_length() - 1), x[2 * rank * loc:2 * (rank + 1) * loc]) for x in (f1, f2)]
+        keep += ms
+        specs.append(cb.TowerProverSpec(ms, nv, False))
+    for i, nv in enumerate(logup_nvs):
+        n = 1 << nv
+        arrs = [orc.fill_ext(6200 + 4 * i + z, n) for z in range(4)]
+        o_lk.append((orc.infer_tower_logup_witness(nv, *arrs)[0], nv + 1))
+        loc = n // world
+        ms = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, nv - (world.bit_length() - 1), x[2 * rank * loc:2 * (rank + 1) * loc]) for x in arrs]
+        keep += ms
+        specs.append(cb.TowerProverSpec(ms, nv, True))
+    want_proof, want_point = orc.tower_create_proof(o_prod, o_lk, orc.Transcript(b"shtower"))
+    tw = cb.TowerProver.sharded(dev, comm, specs)
+    got_proof, got_point = tw.create_proof(cb.StandInTranscript(b"shtower"))
+    ok = ok and np.array_equal(got_proof, want_proof) and np.array_equal(got_point, want_point)
+    tw.close()
+    # (b) virtual leaves: every rank holds its rows of both fan-in blocks of 5 lookup records (a chip of rows / world rows)
+    log_n, n_rec, alpha = 14, 5, [12345, 678]
+    n = 1 << log_n
+    recs = [orc.fill_ext(6300 + i, n) for i in range(n_rec)]
+    want = orc.interleaving_mles_to_mles([(r, True) for r in recs], n, 2, alpha)
+    nv = (want[0].size // 2).bit_length() - 1
+    o_lk2 = [(orc.infer_tower_logup_witness(nv, None, None, want[0], want[1])[0], nv + 1)]
+    want_proof2, want_point2 = orc.tower_create_proof([], o_lk2, orc.Transcript(b"shvirt"))
+    hl = (n // 2) // world                      # rows of one fan-in block per rank
+    loc_recs = []
+    for r in recs:
+        rr = r.reshape(-1, 2)
+        loc_recs.append(np.concatenate([rr[rank * hl:(rank + 1) * hl], rr[n // 2 + rank * hl:n // 2 + (rank + 1) * hl]]).reshape(-1))
+    ms = [cb.MultilinearExtension.from_evaluations_ext_vec(dev, log_n - (world.bit_length() - 1), x) for x in loc_recs]
+    tw2 = cb.TowerProver.from_records(dev, [cb.VirtualTowerSpec(ms, n // world, alpha, True)], comm=comm)
+    got_proof2, got_point2 = tw2.create_proof(cb.StandInTranscript(b"shvirt"))
+    ok = ok and np.array_equal(got_proof2, want_proof2) and np.array_equal(got_point2, want_point2)
+    tw2.close()
+    dist.barrier()
+    comm.close()
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_sharded_tower_multi_gpu_bit_exact():
+    """cfg-4: the tower built and proven over rank slices (layer kernels store into the partner ranks' buffers over NVLink,
+    big layers' sumchecks sharded, small layers replicated) gives the oracle's single-device proof — with materialised leaves
+    and with virtual leaves."""
+    import torch
+    import torch.multiprocessing as mp
+    world = 1
+    while world * 2 <= min(torch.cuda.device_count(), 8):
+        world *= 2
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dist_tower_worker, args=(r, world, 29681, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, True) for r in range(world)]
+
+
 def test_sharded_sumcheck_multi_gpu_bit_exact():
     import torch
     import torch.multiprocessing as mp
