@@ -961,6 +961,14 @@ static int veq_prepare(cg_sumcheck* sc) {   // before evaluating round sc->round
     return CG_OK;
 }
 
+// A caller that runs many sumchecks back to back on one stream (the tower prover: one per layer, sizes doubling) lends ONE
+// workspace instead of a fresh pooled block per sumcheck: the stream-ordered pool fragments under a doubling size sequence and
+// re-maps gigabytes per allocation (measured on the keccak tower: 107 ms of allocation against 129 ms of kernels).
+struct ScWorkspace {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+static thread_local const ScWorkspace* tl_lent_ws = nullptr;
 static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, uint32_t num_vars, uint32_t degree,
                             uint32_t flags, cudaStream_t st, cg_sumcheck** out) {
     if (!c || !out || (n_mles && !mles)) return set_err(c, CG_ERR_INVALID, "cg_sumcheck_create: null argument");
@@ -1020,7 +1028,11 @@ static int sc_create_common(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles,
                 rc = set_err(c, CG_ERR_CUDA, "pad copy failed");
         }
     }
-    if (rc == CG_OK && num_vars >= 1) rc = sc_alloc(sc, (size_t)n_mles * ws_per(n) * sizeof(ext_t), &sc->ws);
+    if (rc == CG_OK && num_vars >= 1) {
+        const size_t need = (size_t)n_mles * ws_per(n) * sizeof(ext_t);
+        if (tl_lent_ws && tl_lent_ws->ptr && tl_lent_ws->bytes >= need) sc->ws = tl_lent_ws->ptr;   // lent by the caller (not owned)
+        else rc = sc_alloc(sc, need, &sc->ws);
+    }
     if (rc == CG_OK) {
         // one slab for the small per-sumcheck state: [ticket | error | final | msgs | chal | partials]
         auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -2817,6 +2829,31 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
     uint32_t rt_len = 1;
     tr->sample(tr->user, "product_sum", rt.data());
     uint64_t w = 0;
+    // one eq buffer and one fold workspace for every layer's sumcheck (sized for the largest layer)
+    ScWorkspace lent;
+    void* d_eq_all = nullptr;
+    {
+        size_t max_ws = 0, max_eq = 0;
+        for (uint32_t round = 1; round <= tw->max_round; round++) {
+            const uint32_t nvl = layer_distributed(tw, round) ? round - tw->g : round;
+            size_t m = 1;
+            for (const auto& sp : tw->specs) if (round < sp.layers) m += sp.is_logup ? 4 : 2;
+            max_ws = std::max(max_ws, m * (size_t)ws_per(1ULL << nvl) * sizeof(ext_t));
+            max_eq = std::max(max_eq, sizeof(ext_t) << nvl);
+        }
+        CHK(tmp_alloc(c, max_eq, &d_eq_all, tw->stream));
+        if (tmp_alloc(c, max_ws, &lent.ptr, tw->stream) == CG_OK) lent.bytes = max_ws;   // on failure the layers allocate their own
+    }
+    struct LendGuard {
+        const ScWorkspace* prev;
+        explicit LendGuard(const ScWorkspace* w) : prev(tl_lent_ws) { tl_lent_ws = w; }
+        ~LendGuard() { tl_lent_ws = prev; }
+    } lend_guard(&lent);
+    struct FreeGuard {
+        void *a, *b;
+        cudaStream_t st;
+        ~FreeGuard() { tmp_free(a, st); tmp_free(b, st); }
+    } free_guard{d_eq_all, lent.ptr, tw->stream};
     static const bool trace = getenv("CG_TOWER_TRACE") != nullptr;   // host-side time per phase, summed over the layers
     double t_eq = 0, t_create = 0, t_run = 0, t_fin = 0;
     auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -2825,9 +2862,8 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
         const bool dist = layer_distributed(tw, round);   // this layer's arrays are rank slices (top g index bits = rank)
         const uint32_t nv = dist ? nv_glob - tw->g : nv_glob;
         const uint64_t n = 1ULL << nv;
-        void* d_eq = nullptr;
+        void* d_eq = d_eq_all;
         const double t0 = now();
-        CHK(tmp_alloc(c, sizeof(ext_t) * n, &d_eq, tw->stream));
         int rc = cg_build_eq(c, rt.data(), nv, (uint64_t*)d_eq, 0, n, tw->stream);
         if (rc == CG_OK && dist) {   // eq(rt, .) on my slice = eq(rt_top, rank) * eq(rt_low, .)
             ext_t sc_{1, 0};
@@ -2913,7 +2949,6 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
         }
         const double t3 = now();
         if (sc) cg_sumcheck_destroy(sc);
-        tmp_free(d_eq, tw->stream);
         if (rc != CG_OK) return rc;
         if (trace) {
             t_eq += t1 - t0; t_create += t2 - t1; t_run += t3 - t2; t_fin += now() - t3;
