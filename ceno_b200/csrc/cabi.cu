@@ -777,6 +777,7 @@ struct TowerLayout {           // MLE indices of the specialised (tower-shaped) 
     std::vector<ext_t> lk_an, lk_ad;
     bool alpha_one = false;
 };
+#define CG_SC_INT_DEFER_VEQ (1u << 30)   // internal: the caller decides about split-eq rounds after create (tower layers)
 struct VeqState {               // a virtual eq MLE (CG_MLE_EQ) handled by the split-eq kernels
     bool split = false;         // split rounds active: the eq state is not materialised yet
     bool have = false;          // a virtual eq was declared (point recorded)
@@ -788,9 +789,19 @@ struct VeqState {               // a virtual eq MLE (CG_MLE_EQ) handled by the s
     ext_t* d_inv1mw = nullptr;  // 1 / (1 - w_j), host-computed
     ext_t* d_qstate = nullptr;  // coefficients of the previous round's q(X): the running claim of the claim-derived rounds
     bool derive_ok = false;     // every 1 - w_j is invertible (else the rounds accumulate all three sums)
+    bool have_claim = false;    // the caller knows the claimed sum (tower layers): round 0 is claim-derived as well
+    ext_t claim0{0, 0};
     ext_t scale{1, 0};          // sharded prove: eq(w_top, rank) — the constant factor of eq on this rank's slice
     ulonglong4 *d_L = nullptr, *d_H = nullptr;
     uint64_t h_off[CG_VEQ_MAX_ROUNDS + 1] = {0};
+    // general tower layouts (tveq_round_kernel): S alpha-folded copies of every H entry; launches that read virtual leaves
+    // (rounds 0 / 1) use the lanes-over-high mapping with their own low / high tables
+    bool general = false;
+    uint32_t S = 0;
+    ulonglong4* d_UA = nullptr;
+    bool m1 = false;
+    uint32_t m1_lo[2] = {0, 0};
+    ulonglong4 *d_LR[2] = {nullptr, nullptr}, *d_HS[2] = {nullptr, nullptr};
 };
 struct cg_sumcheck {
     cg_ctx* ctx = nullptr;
@@ -804,6 +815,7 @@ struct cg_sumcheck {
     const ext_t* pending_r_ptr = nullptr;   // device challenger: challenge lives on the device
     std::vector<MleState> mles;
     std::vector<const VirtLeaf*> virt;   // per MLE: its ORIGINAL input is a virtual tower leaf array (null / empty: a plain array)
+    uint32_t virt_l2m = 0;               // log2 of the padded record count of the virtual leaves (index layout of their rows)
     TowerLayout tl;
     VeqState veq;
     // device state
@@ -887,19 +899,29 @@ static int veq_build_full(cg_sumcheck* sc, uint32_t i, const uint64_t* h_point) 
 }
 static uint32_t log2_u64(uint64_t x);
 static uint64_t tail_cap_n0(const cg_ctx* c, size_t n_slots, bool sharded);
+// split rounds run until the cluster tail can take the (materialised) state over: it enters at round J with a pending
+// fold, i.e. with 2^(k - J) elements per MLE (cluster-wide; sharded: times the rank count).  0: too small for split rounds.
+static uint32_t veq_split_rounds(const cg_ctx* c, uint32_t k, size_t n_slots, bool sharded, uint32_t extra_rounds) {
+    if (k < 2 + CG_VEQ_LO_BITS) return 0;
+    const uint32_t cap_log = log2_u64(std::max<uint64_t>(2, tail_cap_n0(c, n_slots, sharded)));
+    const uint32_t loc_log = cap_log > extra_rounds ? cap_log - extra_rounds : 1;
+    uint32_t J = k > loc_log ? k - loc_log : 1;
+    if (J > k - 1 - CG_VEQ_LO_BITS) J = k - 1 - CG_VEQ_LO_BITS;   // a round needs at least one row of 256 pairs
+    if (J > CG_VEQ_MAX_ROUNDS) J = CG_VEQ_MAX_ROUNDS;
+    return J;
+}
 // split mode: upload the point, build every round's L/H tables in one launch
 static int veq_setup_split(cg_sumcheck* sc) {
     cg_ctx* c = sc->ctx;
     VeqState& v = sc->veq;
     const uint32_t k = sc->num_vars;
-    // split rounds run until the cluster tail can take the (materialised) state over: it enters at round J with a pending
-    // fold, i.e. with 2^(k - J) elements per MLE (cluster-wide; sharded: times the rank count)
     const bool sharded = sc->comm && sc->comm->nranks > 1;
-    const uint32_t cap_log = log2_u64(std::max<uint64_t>(2, tail_cap_n0(c, 3, sharded)));
-    const uint32_t loc_log = cap_log > sc->extra_rounds ? cap_log - sc->extra_rounds : 1;
-    v.J = k > loc_log ? k - loc_log : 1;
-    if (v.J > k - 1 - CG_VEQ_LO_BITS) v.J = k - 1 - CG_VEQ_LO_BITS;   // a round needs at least one row of 256 pairs
-    if (v.J > CG_VEQ_MAX_ROUNDS) v.J = CG_VEQ_MAX_ROUNDS;
+    const TowerLayout& tl = sc->tl;
+    bool any_virt = false;
+    for (const VirtLeaf* q : sc->virt) any_virt |= q != nullptr;
+    v.general = !(tl.alpha_one && tl.prod.size() == 2 && tl.lk.empty() && !any_virt);
+    v.J = veq_split_rounds(c, k, v.general ? sc->n_mles : 3, sharded, sc->extra_rounds);
+    if (v.J == 0 || (any_virt && (v.J < 2 || sc->virt_l2m < 3))) return set_err(c, CG_ERR_STATE, "split-eq rounds: shape not eligible");
     v.h_off[0] = 0;
     for (uint32_t j = 0; j < v.J; j++) v.h_off[j + 1] = v.h_off[j] + (1ULL << (k - j - 1 - CG_VEQ_LO_BITS));
     // one upload: [w (k ext) | 1 / (1 - w_j) (k ext) | prefix = 1 | q-state (3 ext)]
@@ -914,12 +936,13 @@ static int veq_setup_split(cg_sumcheck* sc) {
     v.derive_ok = !(sc->flags & CG_SC_NO_DERIVE);
     for (uint32_t j = 0; j < k; j++) {
         const ext_t om{hx_submod(1, v.h_point[2 * j]), hx_submod(0, v.h_point[2 * j + 1])};
-        if (om.c0 == 0 && om.c1 == 0) { if (j >= 1 && j < v.J) v.derive_ok = false; continue; }
+        if (om.c0 == 0 && om.c1 == 0) { if (j >= 1 && j < v.J) v.derive_ok = false; if (j == 0) v.have_claim = false; continue; }
         const ext_t iv = hx_inv(om);
         v.h_up[2 * (k + j)] = iv.c0;
         v.h_up[2 * (k + j) + 1] = iv.c1;
     }
     v.h_up[2 * (2 * (size_t)k)] = 1;   // prefix = 1
+    if (v.have_claim) { v.h_up[2 * (2 * (size_t)k + 1)] = v.claim0.c0; v.h_up[2 * (2 * (size_t)k + 1) + 1] = v.claim0.c1; }   // q-state: q_{-1}(0) = the claimed sum
     CU(c, cudaMemcpyAsync(v.d_w, v.h_up.data(), sizeof(uint64_t) * v.h_up.size(), cudaMemcpyHostToDevice, sc->stream));   // v lives as long as sc
     CHK(sc_alloc(sc, sizeof(ulonglong4) * ((size_t)v.J << CG_VEQ_LO_BITS), &p));
     v.d_L = (ulonglong4*)p;
@@ -929,9 +952,44 @@ static int veq_setup_split(cg_sumcheck* sc) {
     memset(&a, 0, sizeof(a));
     a.w = v.d_w; a.k = k; a.J = v.J; a.L = v.d_L; a.H = v.d_H;
     for (uint32_t j = 0; j <= v.J; j++) a.h_off[j] = v.h_off[j];
+    if (v.general) {   // weight slots: one per product spec (alpha), two per logup spec (numerator / denominator alpha)
+        v.S = (uint32_t)(tl.prod_alpha.size() + 2 * tl.lk_an.size());
+        if (v.S == 0 || v.S > CG_TVEQ_MAX_SLOTS) return set_err(c, CG_ERR_STATE, "split-eq rounds: spec count out of range");
+        for (size_t i = 0; i < tl.prod_alpha.size(); i++) a.alpha[i] = tl.prod_alpha[i];
+        for (size_t l = 0; l < tl.lk_an.size(); l++) {
+            a.alpha[tl.prod_alpha.size() + 2 * l] = tl.lk_an[l];
+            a.alpha[tl.prod_alpha.size() + 2 * l + 1] = tl.lk_ad[l];
+        }
+        CHK(sc_alloc(sc, sizeof(ulonglong4) * v.h_off[v.J] * v.S, &p));
+        v.d_UA = (ulonglong4*)p;
+        a.UA = v.d_UA;
+        a.S = v.S;
+    }
     veq_tables_kernel<<<grid_for(c, ((uint64_t)v.J << CG_VEQ_LO_BITS) + v.h_off[v.J], 8), CG_THREADS, 0, sc->stream>>>(a);
     LAUNCHED(c);
     CU(c, cudaGetLastError());
+    if (any_virt) {   // rounds 0 and 1 read the leaves: lanes over the record rows, loop over the record index
+        v.m1 = true;
+        for (uint32_t j = 0; j < 2; j++) {
+            v.m1_lo[j] = sc->virt_l2m - 1 - j;   // item bits below the row index
+            if (v.m1_lo[j] > k - j - 1) v.m1_lo[j] = k - j - 1;
+            VeqRangeArgs ra;
+            memset(&ra, 0, sizeof(ra));
+            ra.w = v.d_w;
+            ra.v0 = j + 1; ra.nb = v.m1_lo[j]; ra.S = v.S;
+            memcpy(ra.alpha, a.alpha, sizeof(ra.alpha));
+            CHK(sc_alloc(sc, sizeof(ulonglong4) * v.S << ra.nb, &p));
+            v.d_LR[j] = ra.out = (ulonglong4*)p;
+            veq_range_table_kernel<<<grid_for(c, 1ULL << ra.nb, 8), CG_THREADS, 0, sc->stream>>>(ra);
+            LAUNCHED(c);
+            ra.v0 = j + 1 + v.m1_lo[j]; ra.nb = k - ra.v0; ra.S = 0;
+            CHK(sc_alloc(sc, sizeof(ulonglong4) << ra.nb, &p));
+            v.d_HS[j] = ra.out = (ulonglong4*)p;
+            veq_range_table_kernel<<<grid_for(c, 1ULL << ra.nb, 8), CG_THREADS, 0, sc->stream>>>(ra);
+            LAUNCHED(c);
+        }
+        CU(c, cudaGetLastError());
+    }
     v.split = true;
     return CG_OK;
 }
@@ -1210,9 +1268,9 @@ static int sc_create_terms(cg_ctx* c, const cg_mle_desc* mles, uint32_t n_mles, 
             sc->tl.alpha_one = (al.c0 == 1 && al.c1 == 0);
         }
     }
-    if (rc == CG_OK && sc->veq.have) {
-        if (veq_scale) sc->veq.scale = *veq_scale;
-        const bool split_ok = sc->tl.on && sc->tl.eq == sc->veq.idx && sc->tl.alpha_one && sc->tl.prod.size() == 2 && sc->tl.lk.empty() &&
+    if (rc == CG_OK && sc->veq.have && veq_scale) sc->veq.scale = *veq_scale;
+    if (rc == CG_OK && sc->veq.have && !(flags & CG_SC_INT_DEFER_VEQ)) {   // (deferred: the tower prover sets its layout first)
+        const bool split_ok = sc->tl.on && sc->tl.eq == sc->veq.idx && sc->tl.prod.size() == 2 && sc->tl.lk.empty() &&
                               !(flags & (CG_SC_NO_FUSE | CG_SC_FORCE_GENERIC)) && num_vars >= 20 && num_vars <= 32;
         rc = split_ok ? veq_setup_split(sc) : veq_build_full(sc, sc->veq.idx, sc->veq.h_point.data());
     }
@@ -1372,18 +1430,17 @@ static int launch_veq(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro
     CU(c, cudaGetLastError());
     return CG_OK;
 }
-// tower-shaped kernel: evaluate state f (fold==false) or fold f-1 -> f and evaluate (fold==true)
-static int launch_tower(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro) {
-    if (sc->veq.split) return launch_veq(sc, f, fold, ro);
-    cg_ctx* c = sc->ctx;
+// the layer's arrays for a launch that evaluates state f (fold==false) or folds f-1 -> f and evaluates (fold==true)
+static void fill_tower_args(cg_sumcheck* sc, uint32_t f, bool fold, bool with_eq, TowerArgs& a, bool& any_virt) {
     const TowerLayout& tl = sc->tl;
-    TowerArgs a;
     memset(&a, 0, sizeof(a));
     const uint32_t src = fold ? f - 1 : f;
     auto in = [&](uint32_t i) { return (const ext_t*)mle_buf(sc, i, src); };
     auto outp = [&](uint32_t i) { return fold ? (ext_t*)mle_buf(sc, i, f) : (ext_t*)nullptr; };
-    a.eq_in = in(tl.eq);
-    a.eq_out = outp(tl.eq);
+    if (with_eq) {
+        a.eq_in = in(tl.eq);
+        a.eq_out = outp(tl.eq);
+    }
     a.n_prod = (int)tl.prod_alpha.size();
     a.n_logup = (int)tl.lk_an.size();
     for (int p = 0; p < a.n_prod; p++) {
@@ -1399,14 +1456,82 @@ static int launch_tower(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& 
     a.n_pairs = 1ULL << (sc->num_vars - f - 1);
     a.r = sc->pending_r;
     a.r_ptr = sc->pending_r_ptr;
-    a.out = ro;
-    bool any_virt = false;           // virtual tower leaves: only a launch that reads the original inputs sees them
+    any_virt = false;                // virtual tower leaves: only a launch that reads the original inputs sees them
     if (src == 0 && !sc->virt.empty()) {
         for (int p = 0; p < a.n_prod; p++)
             for (int z = 0; z < 2; z++) { a.virt[1 + 2 * p + z] = sc->virt[tl.prod[2 * p + z]]; any_virt |= a.virt[1 + 2 * p + z] != nullptr; }
         for (int l = 0; l < a.n_logup; l++)
             for (int z = 0; z < 4; z++) { a.virt[1 + 2 * a.n_prod + 4 * l + z] = sc->virt[tl.lk[4 * l + z]]; any_virt |= a.virt[1 + 2 * a.n_prod + 4 * l + z] != nullptr; }
     }
+}
+// split-eq round of a general tower layout (tveq_round_kernel)
+static int launch_tveq(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro) {
+    cg_ctx* c = sc->ctx;
+    const VeqState& v = sc->veq;
+    TVeqArgs a;
+    memset(&a, 0, sizeof(a));
+    bool any_virt = false;
+    fill_tower_args(sc, f, fold, false, a.t, any_virt);
+    const uint32_t src = fold ? f - 1 : f;
+    a.S = v.S;
+    if (any_virt) {
+        if (!v.m1 || f > 1) return set_err(c, CG_ERR_STATE, "split-eq rounds: no tables for a virtual-leaf launch");
+        a.U = v.d_LR[f];
+        a.F = v.d_HS[f];
+        a.lo_bits = v.m1_lo[f];
+    } else {
+        a.U = v.d_UA + v.h_off[f] * v.S;
+        a.F = v.d_L + ((size_t)f << CG_VEQ_LO_BITS);
+    }
+    a.fin.w = v.d_w;
+    a.fin.inv1mw = v.d_inv1mw;
+    a.fin.prefix = v.d_prefix;
+    a.fin.qstate = v.d_qstate;
+    a.fin.scale = v.scale;
+    a.fin.sharded = (sc->comm && sc->comm->nranks > 1) ? 1 : 0;
+    a.fin.round = f;
+    a.fin.fold = fold ? 1 : 0;
+    a.fin.r = sc->pending_r;
+    a.fin.r_ptr = sc->pending_r_ptr;
+    const bool derive = v.derive_ok && (fold || (f == 0 && v.have_claim));
+    a.fin.derive = derive ? 1 : 0;
+    a.out_ = ro;
+    const bool canon = (src == 0);
+    uint64_t blocks = (uint64_t)c->sm_count * 2;   // one resident wave (2 blocks per SM)
+    if (!any_virt) blocks = std::min<uint64_t>(blocks, a.t.n_pairs >> CG_VEQ_LO_BITS);
+    else {
+        const uint64_t n_lo = 1ULL << a.lo_bits, units = (a.t.n_pairs >> a.lo_bits) * (n_lo / std::min<uint64_t>(n_lo, 256));
+        blocks = std::min<uint64_t>(blocks, (units + 255) / 256);
+    }
+    const unsigned grid = (unsigned)(blocks ? blocks : 1);
+#define CG_TVEQ(F, CN, DR, VR) tveq_round_kernel<F, CN, DR, VR><<<grid, 256, 0, sc->stream>>>(a)
+    if (any_virt) {
+        if (!fold) { if (derive) CG_TVEQ(false, true, true, true); else CG_TVEQ(false, true, false, true); }
+        else if (derive) CG_TVEQ(true, true, true, true);
+        else CG_TVEQ(true, true, false, true);
+    } else if (!fold) {
+        if (derive) CG_TVEQ(false, true, true, false);   // round 0 with a known claim (f == 0: caller-provided buffers)
+        else if (canon) CG_TVEQ(false, true, false, false);
+        else CG_TVEQ(false, false, false, false);
+    } else if (derive) {
+        if (canon) CG_TVEQ(true, true, true, false); else CG_TVEQ(true, false, true, false);
+    } else {
+        if (canon) CG_TVEQ(true, true, false, false); else CG_TVEQ(true, false, false, false);
+    }
+#undef CG_TVEQ
+    LAUNCHED(c);
+    CU(c, cudaGetLastError());
+    return CG_OK;
+}
+// tower-shaped kernel: evaluate state f (fold==false) or fold f-1 -> f and evaluate (fold==true)
+static int launch_tower(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& ro) {
+    if (sc->veq.split) return sc->veq.general ? launch_tveq(sc, f, fold, ro) : launch_veq(sc, f, fold, ro);
+    cg_ctx* c = sc->ctx;
+    TowerArgs a;
+    bool any_virt = false;
+    fill_tower_args(sc, f, fold, true, a, any_virt);
+    a.out = ro;
+    const uint32_t src = fold ? f - 1 : f;
     const bool canon = (src == 0);   // reading caller-provided buffers
     const bool simple = a.n_prod == 1 && a.n_logup == 0 && a.alpha_one && !any_virt;
     // launch shape: threads x resident blocks per SM (one persistent wave, grid-stride loop)
@@ -1853,7 +1978,7 @@ static bool persist_eligible(const cg_sumcheck* sc) {
     static const int use_tma = []() { const char* e = getenv("CG_VEQ_TMA"); return e ? atoi(e) : 1; }();
     static const int minb = []() { const char* e = getenv("CG_VEQ_MINB"); return e ? atoi(e) : CG_VEQ_MINB_DEFAULT; }();
     const VeqState& v = sc->veq;
-    if (!on || !use_tma || minb == 3 || !v.split || !v.derive_ok) return false;
+    if (!on || !use_tma || minb == 3 || !v.split || v.general || !v.derive_ok) return false;
     if (sc->flags & (CG_SC_NO_FUSE | CG_SC_NO_MID | CG_SC_NO_PERSIST | CG_SC_FORCE_GENERIC)) return false;
     if (!sc->pending || sc->round < 1 || sc->round + 1 >= v.J) return false;   // at least two rounds, after round 0
     if (sc->ctx->live_sc.load() > 1) return false;                              // cooperative: needs the whole chip
@@ -2436,6 +2561,7 @@ struct TowerSpecState {
     bool ones = false;               // logup numerators implicit ones
     bool virt = false;               // the leaf layer is described, not stored (cg_tower_build_virtual)
     const VirtLeaf* d_virt[4] = {nullptr, nullptr, nullptr, nullptr};   // device descriptions of the leaf arrays
+    uint32_t virt_l2m = 0;           // log2 of the padded record count (leaf index = row << l2m | record)
 };
 struct cg_tower {
     cg_ctx* ctx = nullptr;
@@ -2747,6 +2873,7 @@ static int tower_build_virtual_impl(cg_ctx* c, cg_comm* cm, const cg_tower_vspec
             TowerSpecState sp;
             sp.is_logup = in.is_logup != 0;
             sp.virt = true;
+            sp.virt_l2m = ceil_log2_u64(in.q.n_records);
             uint64_t len_q = 0, len_p = 0;
             const VirtLeaf* dq[2];
             rc = make_virt_limbs(tw, in.q, dq, &len_q);
@@ -2832,14 +2959,37 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
     // one eq buffer and one fold workspace for every layer's sumcheck (sized for the largest layer)
     ScWorkspace lent;
     void* d_eq_all = nullptr;
+    // Layers large enough for split-eq rounds hand eq over as its point (no table is built, streamed or folded before the
+    // cluster tail takes over); CG_TOWER_VEQ=0 keeps the table everywhere (A/B switch).
+    struct LayerPlan { uint32_t nv; size_t slots; bool any_virt; uint32_t vl2m; bool veq; };
+    auto layer_plan = [&](uint32_t round) {
+        LayerPlan lp{};
+        const bool dist = layer_distributed(tw, round);
+        lp.nv = dist ? round - tw->g : round;
+        lp.slots = 1;
+        uint32_t np = 0, nl = 0;
+        for (const auto& sp : tw->specs) {
+            if (round >= sp.layers) continue;
+            lp.slots += sp.is_logup ? 4 : 2;
+            (sp.is_logup ? nl : np)++;
+            if (sp.virt && round + 1 == sp.layers && !lp.any_virt) { lp.any_virt = true; lp.vl2m = sp.virt_l2m; }
+        }
+        // Below 2^20 points a layer's time is launch latency, and the split form costs two more launches (tables, hand-over
+        // to the tail) than building the table.  Read per call: one process can compare both paths (tests force 2^10).
+        const char* e = getenv("CG_TOWER_VEQ");
+        const char* em = getenv("CG_TOWER_VEQ_MIN_NV");
+        const int on = (e ? atoi(e) : 1) && lp.nv >= (uint32_t)(em ? atoi(em) : 20);
+        const bool fits = np <= CG_TOWER_MAX_PROD && nl <= CG_TOWER_MAX_LOGUP;
+        const uint32_t J = (on && fits && lp.nv <= 32) ? veq_split_rounds(c, lp.nv, lp.slots, dist && tw->comm->nranks > 1, dist ? tw->g : 0) : 0;
+        lp.veq = J >= 1 && (!lp.any_virt || (J >= 2 && lp.vl2m >= 3));
+        return lp;
+    };
     {
-        size_t max_ws = 0, max_eq = 0;
+        size_t max_ws = 0, max_eq = sizeof(ext_t) * 2;
         for (uint32_t round = 1; round <= tw->max_round; round++) {
-            const uint32_t nvl = layer_distributed(tw, round) ? round - tw->g : round;
-            size_t m = 1;
-            for (const auto& sp : tw->specs) if (round < sp.layers) m += sp.is_logup ? 4 : 2;
-            max_ws = std::max(max_ws, m * (size_t)ws_per(1ULL << nvl) * sizeof(ext_t));
-            max_eq = std::max(max_eq, sizeof(ext_t) << nvl);
+            const LayerPlan lp = layer_plan(round);
+            max_ws = std::max(max_ws, lp.slots * (size_t)ws_per(1ULL << lp.nv) * sizeof(ext_t));
+            if (!lp.veq) max_eq = std::max(max_eq, sizeof(ext_t) << lp.nv);
         }
         CHK(tmp_alloc(c, max_eq, &d_eq_all, tw->stream));
         if (tmp_alloc(c, max_ws, &lent.ptr, tw->stream) == CG_OK) lent.bytes = max_ws;   // on failure the layers allocate their own
@@ -2854,6 +3004,8 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
         cudaStream_t st;
         ~FreeGuard() { tmp_free(a, st); tmp_free(b, st); }
     } free_guard{d_eq_all, lent.ptr, tw->stream};
+    ext_t next_claim{0, 0};      // the claimed sum of the next layer's sumcheck, as the verifier derives it from this layer's evaluations
+    bool have_claim = false;
     static const bool trace = getenv("CG_TOWER_TRACE") != nullptr;   // host-side time per phase, summed over the layers
     double t_eq = 0, t_create = 0, t_run = 0, t_fin = 0;
     auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -2864,22 +3016,28 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
         const uint64_t n = 1ULL << nv;
         void* d_eq = d_eq_all;
         const double t0 = now();
-        int rc = cg_build_eq(c, rt.data(), nv, (uint64_t*)d_eq, 0, n, tw->stream);
-        if (rc == CG_OK && dist) {   // eq(rt, .) on my slice = eq(rt_top, rank) * eq(rt_low, .)
-            ext_t sc_{1, 0};
+        const LayerPlan lp = layer_plan(round);
+        ext_t sc_{1, 0};
+        if (dist)   // eq(rt, .) on my slice = eq(rt_top, rank) * eq(rt_low, .)
             for (uint32_t b = 0; b < tw->g; b++) {
                 ext_t w{rt[2 * (nv + b)] % GL_P, rt[2 * (nv + b) + 1] % GL_P};
                 if (!((tw->comm->rank >> b) & 1)) w = ext_t{hx_submod(1, w.c0), hx_submod(0, w.c1)};
                 sc_ = hx_mul(sc_, w);
             }
-            scale_ext_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, tw->stream>>>((ext_t*)d_eq, n, sc_);
-            LAUNCHED(c);
+        int rc = CG_OK;
+        if (!lp.veq) {
+            rc = cg_build_eq(c, rt.data(), nv, (uint64_t*)d_eq, 0, n, tw->stream);
+            if (rc == CG_OK && dist) {
+                scale_ext_kernel<<<grid_for(c, n, 8), CG_THREADS, 0, tw->stream>>>((ext_t*)d_eq, n, sc_);
+                LAUNCHED(c);
+            }
         }
         const double t1 = now();
         // MLE list in the reference's lift order: eq, then live product specs, then live logup specs
         std::vector<cg_mle_desc> mles;
         std::vector<const VirtLeaf*> virt{nullptr};
-        mles.push_back(cg_mle_desc{d_eq, n, nv, 1});
+        if (lp.veq) mles.push_back(cg_mle_desc{rt.data(), n, nv, CG_MLE_EQ});   // the point itself (host memory)
+        else mles.push_back(cg_mle_desc{d_eq, n, nv, 1});
         TowerLayout tl;
         tl.on = true;
         tl.eq = 0;
@@ -2921,10 +3079,11 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
                 coeff.push_back(tl.lk_ad[l].c0); coeff.push_back(tl.lk_ad[l].c1);
                 idx.insert(idx.end(), {0u, q1, q2}); off.push_back((uint32_t)idx.size());
             }
+            const uint32_t fl = CG_SC_FORCE_GENERIC | (lp.veq ? CG_SC_INT_DEFER_VEQ : 0u);
             if (dist) rc = sc_create_terms(c, mles.data(), (uint32_t)mles.size(), coeff.data(), off.data(), idx.data(), (uint32_t)off.size() - 1, nv, 3,
-                                           CG_SC_FORCE_GENERIC, tw->stream, nullptr, &sc, tw->comm, tw->g);
-            else rc = cg_sumcheck_create(c, mles.data(), (uint32_t)mles.size(), coeff.data(), off.data(), idx.data(),
-                                         (uint32_t)off.size() - 1, nv, 3, CG_SC_FORCE_GENERIC, tw->stream, &sc);
+                                           fl, tw->stream, lp.veq ? &sc_ : nullptr, &sc, tw->comm, tw->g);
+            else rc = sc_create_terms(c, mles.data(), (uint32_t)mles.size(), coeff.data(), off.data(), idx.data(),
+                                      (uint32_t)off.size() - 1, nv, 3, fl, tw->stream, nullptr, &sc);
         }
         std::vector<uint64_t> fin(2 * mles.size()), chal(2 * (size_t)nv_glob);
         const double t2 = now();
@@ -2935,6 +3094,12 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
             if (any_virt) {
                 if (!fits) rc = set_err(c, CG_ERR_UNSUPPORTED, "virtual tower leaves need the specialised tower kernels (<= 8 product, <= 4 logup specs)");
                 sc->virt = virt;
+            }
+            if (rc == CG_OK && lp.veq) {   // (lp.veq implies fits)
+                sc->virt_l2m = lp.vl2m;
+                sc->veq.have_claim = have_claim && !getenv("CG_TOWER_VEQ_NOCLAIM");   // (testing: three-sum round 0)
+                sc->veq.claim0 = next_claim;
+                rc = veq_setup_split(sc);
             }
         }
         if (rc == CG_OK) {
@@ -2971,6 +3136,25 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
         rt[2 * nv_glob + 1] = rm[1];
         rt_len = nv_glob + 1;
         alpha_pows(tr, n_alpha, alpha);
+        // next claim = sum over the specs still alive of alpha * v(point, merge), v(point, y) = (1 - y) first half + y second half
+        {
+            const ext_t rme{rm[0] % GL_P, rm[1] % GL_P}, omr{hx_submod(1, rme.c0), hx_submod(0, rme.c1)};
+            next_claim = ext_t{0, 0};
+            uint32_t pi2 = 0, li2 = 0;
+            for (size_t si = 0; si < tw->specs.size(); si++) {
+                const TowerSpecState& sp = tw->specs[si];
+                const uint32_t my = sp.is_logup ? li2++ : pi2++;
+                if (round + 1 >= sp.layers) continue;
+                auto F = [&](uint32_t z) { return ext_t{fin[2 * (first[si] + z)] % GL_P, fin[2 * (first[si] + z) + 1] % GL_P}; };
+                auto merged = [&](uint32_t z) { return hx_add(hx_mul(F(z), omr), hx_mul(F(z + 1), rme)); };
+                if (!sp.is_logup) next_claim = hx_add(next_claim, hx_mul(alpha[my], merged(0)));
+                else {
+                    next_claim = hx_add(next_claim, hx_mul(alpha[tw->n_prod + 2 * my], merged(0)));
+                    next_claim = hx_add(next_claim, hx_mul(alpha[tw->n_prod + 2 * my + 1], merged(2)));
+                }
+            }
+            have_claim = true;
+        }
     }
     memcpy(h_point, rt.data(), sizeof(uint64_t) * 2 * rt_len);
     if (trace) fprintf(stderr, "[tower] total: eq %.0f create %.0f run %.0f destroy %.0f us\n", t_eq, t_create, t_run, t_fin);

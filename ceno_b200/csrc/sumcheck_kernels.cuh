@@ -684,6 +684,127 @@ __global__ void __launch_bounds__(256, MINB) veq_round_kernel(const __grid_const
     ext_t acc[3] = {ext_mul_prep(eacc_weak(S00), Lm), ext_mul_prep(eacc_weak(S11), Lm), ext_mul_prep(eacc_weak(Sx), Lm)};
     block_finish<3, VeqFin>(acc, a.out_, a.fin);
 }
+// ---- split-eq rounds for the GENERAL tower-layer polynomial (any number of product / logup specs with their alphas, virtual
+// leaves): the eq factor of CpuTowerProver::create_proof's layer sumcheck (ceno_zkvm/src/scheme/cpu/mod.rs:417-485) handed
+// over as its point.  With E(x) = F[fixed part of x] * U[uniform part of x]:
+//   q(X) = sum_x E(x) g(X, x),  g = sum_p alpha_p a_p b_p + sum_l [ an_l (p1 q2 + p2 q1) + ad_l q1 q2 ]   (degree 2 in X)
+// the alphas are folded into the uniform weights on the host side of the launch (table U holds S = n_prod + 2 n_logup
+// prepared entries alpha_s * U per index), one operand of every product is weighted, the thread-fixed part F is applied once
+// per thread, and (claim-derived rounds) only q(1) and the X^2 coefficient are accumulated:
+//   product spec:  q(1) += (W a_hi) b_hi,   c2 += (W da) db                                 (d. = lo - hi)
+//   logup spec:    q(1) += (Wn p1 + Wd q1)_hi q2_hi + (Wn p2)_hi q1_hi,   c2 likewise on the differences
+// i.e. 4 / 10 extension multiplications per pair instead of 12 / 21 with a streamed eq table evaluated at three points.
+// Two index mappings: rows of 256 pairs with the lanes over the LOW item bits (F = low table, U = one row weight per block
+// step), or — launches that read virtual leaves, whose neighbouring items are different record arrays — lanes over the HIGH
+// item bits (the record rows, contiguous in memory) and a loop over the low bits (U = low table, F = high table).
+struct TVeqArgs {
+    TowerArgs t;               // eq_in / eq_out / out unused
+    const ulonglong4* U;       // uniform part: S prepared entries {c0, c1, 7 c1, -} per index, alpha folded in
+    const ulonglong4* F;       // thread-fixed part
+    uint32_t S;
+    uint32_t lo_bits;          // lanes-over-high mapping: item = (hi << lo_bits) | lo, U indexed by lo, F by hi
+    VeqFin fin;
+    RoundOut out_;
+};
+GL_DEV extmul_t tab_mul(const ulonglong4* p) {
+    const ulonglong4 v = ld_tab(p);
+    extmul_t m; m.c0 = v.x; m.c1 = v.y; m.c1_7 = v.z;
+    return m;
+}
+// one pair of every spec; loaders return canonical values
+template <bool DERIVE, class L>
+GL_DEV void tveq_item(const TowerArgs& a, L& ld, uint64_t item, const ulonglong4* __restrict__ U, eacc& S0, eacc& S1, eacc& C2) {
+    for (int p = 0; p < a.n_prod; p++) {
+        const extmul_t W = tab_mul(U + p);
+        ext_t alo, ahi, blo, bhi;
+        ld.prod(p, 0, item, alo, ahi);
+        ld.prod(p, 1, item, blo, bhi);
+        const ext_t db = ext_sub(blo, bhi);
+        if (DERIVE) {
+            const ext_t wh = ext_mul_prep_weak(ahi, W), wd = ext_mul_prep_weak(ext_sub(alo, ahi), W);
+            eacc_mac(S1, wh, bhi, gl_mul7_weak(bhi.c1));
+            eacc_mac(C2, wd, db, gl_mul7_weak(db.c1));
+        } else {
+            const ext_t wl = ext_mul_prep(alo, W), wh = ext_mul_prep(ahi, W);   // canonical: their difference is taken
+            eacc_mac(S0, wl, blo, gl_mul7_weak(blo.c1));
+            eacc_mac(S1, wh, bhi, gl_mul7_weak(bhi.c1));
+            eacc_mac(C2, ext_sub(wl, wh), db, gl_mul7_weak(db.c1));
+        }
+    }
+    for (int l = 0; l < a.n_logup; l++) {
+        const extmul_t Wn = tab_mul(U + a.n_prod + 2 * l), Wd = tab_mul(U + a.n_prod + 2 * l + 1);
+        ext_t p1lo, p1hi, p2lo, p2hi, q1lo, q1hi, q2lo, q2hi;
+        ld.lk(l, 0, item, p1lo, p1hi);
+        ld.lk(l, 1, item, p2lo, p2hi);
+        ld.lk(l, 2, item, q1lo, q1hi);
+        ld.lk(l, 3, item, q2lo, q2hi);
+        const ext_t dq1 = ext_sub(q1lo, q1hi), dq2 = ext_sub(q2lo, q2hi);
+        if (DERIVE) {
+            eacc E;
+            eacc_mul_prep(E, p1hi, Wn);
+            eacc_mac_prep(E, q1hi, Wd);
+            eacc_mac(S1, eacc_weak(E), q2hi, gl_mul7_weak(q2hi.c1));
+            eacc_mac(S1, ext_mul_prep_weak(p2hi, Wn), q1hi, gl_mul7_weak(q1hi.c1));
+            eacc_mul_prep(E, ext_sub(p1lo, p1hi), Wn);
+            eacc_mac_prep(E, dq1, Wd);
+            eacc_mac(C2, eacc_weak(E), dq2, gl_mul7_weak(dq2.c1));
+            eacc_mac(C2, ext_mul_prep_weak(ext_sub(p2lo, p2hi), Wn), dq1, gl_mul7_weak(dq1.c1));
+        } else {
+            eacc E;
+            eacc_mul_prep(E, p1lo, Wn);
+            eacc_mac_prep(E, q1lo, Wd);
+            const ext_t ul = eacc_canon(E), vl = ext_mul_prep(p2lo, Wn);
+            eacc_mul_prep(E, p1hi, Wn);
+            eacc_mac_prep(E, q1hi, Wd);
+            const ext_t uh = eacc_canon(E), vh = ext_mul_prep(p2hi, Wn);
+            eacc_mac(S0, ul, q2lo, gl_mul7_weak(q2lo.c1));
+            eacc_mac(S0, vl, q1lo, gl_mul7_weak(q1lo.c1));
+            eacc_mac(S1, uh, q2hi, gl_mul7_weak(q2hi.c1));
+            eacc_mac(S1, vh, q1hi, gl_mul7_weak(q1hi.c1));
+            eacc_mac(C2, ext_sub(ul, uh), dq2, gl_mul7_weak(dq2.c1));
+            eacc_mac(C2, ext_sub(vl, vh), dq1, gl_mul7_weak(dq1.c1));
+        }
+    }
+}
+// VIRT selects the lanes-over-high mapping as well as the leaf loaders
+template <bool FOLD, bool CANON, bool DERIVE, bool VIRT>
+__global__ void __launch_bounds__(256, 2) tveq_round_kernel(const __grid_constant__ TVeqArgs a) {
+    GlobalLoader<FOLD, CANON, VIRT> ld{a.t, {0, 0, 0}};
+    if (FOLD) ld.rm = extmul_prep(a.t.r_ptr ? ld_ext(a.t.r_ptr) : a.t.r);
+    const uint32_t S = a.S;
+    ext_t s0 = ext_zero(), s1 = ext_zero(), c2 = ext_zero();
+    eacc S0, S1, C2;
+    if (!VIRT) {
+        const uint64_t n_rows = a.t.n_pairs >> CG_VEQ_LO_BITS;
+        const uint64_t r0 = n_rows * blockIdx.x / gridDim.x, r1 = n_rows * (blockIdx.x + 1) / gridDim.x;
+        eacc_zero(S0); eacc_zero(S1); eacc_zero(C2);
+        for (uint64_t row = r0; row < r1; row++)
+            tveq_item<DERIVE>(a.t, ld, row * 256 + threadIdx.x, a.U + row * S, S0, S1, C2);
+        const extmul_t Fm = tab_mul(a.F + threadIdx.x);
+        if (!DERIVE) s0 = ext_mul_prep(eacc_weak(S0), Fm);
+        s1 = ext_mul_prep(eacc_weak(S1), Fm);
+        c2 = ext_mul_prep(eacc_weak(C2), Fm);
+    } else {
+        const uint64_t n_lo = 1ULL << a.lo_bits, n_hi = a.t.n_pairs >> a.lo_bits;
+        const uint64_t chunk = n_lo < 256 ? n_lo : 256;
+        const uint64_t units = n_hi * (n_lo / chunk), stride = (uint64_t)gridDim.x * blockDim.x;
+        for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < units; g += stride) {
+            const uint64_t c = g / n_hi, hi = g - c * n_hi;   // consecutive lanes: consecutive record rows
+            eacc_zero(S0); eacc_zero(S1); eacc_zero(C2);
+            for (uint64_t lo = c * chunk; lo < (c + 1) * chunk; lo++)
+                tveq_item<DERIVE>(a.t, ld, (hi << a.lo_bits) + lo, a.U + lo * S, S0, S1, C2);
+            const extmul_t Fm = tab_mul(a.F + hi);
+            if (!DERIVE) s0 = ext_add(s0, ext_mul_prep(eacc_weak(S0), Fm));
+            s1 = ext_add(s1, ext_mul_prep(eacc_weak(S1), Fm));
+            c2 = ext_add(c2, ext_mul_prep(eacc_weak(C2), Fm));
+        }
+    }
+    // VeqFin::post takes (q(1), c2, -) when deriving, (q(0), q(1), q(0) + q(1) - c2) otherwise
+    ext_t acc[3];
+    if (DERIVE) { acc[0] = s1; acc[1] = c2; acc[2] = ext_zero(); }
+    else { acc[0] = s0; acc[1] = s1; acc[2] = ext_sub(ext_add(s0, s1), c2); }
+    block_finish<3, VeqFin>(acc, a.out_, a.fin);
+}
 // ---- the same round with TMA staging: rows (256 pairs = 16 KB per MLE when folding, 8 KB in round 0) are
 // brought into a shared-memory ring by 1-D bulk copies (cp.async.bulk, mbarrier complete_tx), so DRAM latency is
 // hidden by the ring depth instead of by resident warps (the register-heavy lazy accumulators allow only 16
@@ -1037,12 +1158,16 @@ __global__ void __launch_bounds__(256, 2) veq_persist_kernel(const __grid_consta
 }
 
 // all tables of the split rounds in one launch: entry = direct product over its variables
+#define CG_TVEQ_MAX_SLOTS (CG_TOWER_MAX_PROD + 2 * CG_TOWER_MAX_LOGUP)
 struct VeqTabArgs {
     const ext_t* w;
     uint32_t k, J;
     ulonglong4* L;                              // [J][256]
     ulonglong4* H;                              // concatenated, H_j at h_off[j]
     uint64_t h_off[CG_VEQ_MAX_ROUNDS + 1];
+    ulonglong4* UA;                             // general tower layouts: S alpha-folded copies of every H entry, [entry][slot]
+    uint32_t S;
+    ext_t alpha[CG_TVEQ_MAX_SLOTS];
 };
 __global__ void __launch_bounds__(CG_THREADS) veq_tables_kernel(const __grid_constant__ VeqTabArgs a) {
     const uint64_t n_lo = (uint64_t)a.J << CG_VEQ_LO_BITS, total = n_lo + a.h_off[a.J];
@@ -1070,6 +1195,34 @@ __global__ void __launch_bounds__(CG_THREADS) veq_tables_kernel(const __grid_con
             v = ext_mul(v, ((x >> i) & 1) ? wi : ext_sub(ext_one(), wi));
         }
         *dst = make_ulonglong4(v.c0, v.c1, gl_canon(gl_mul7_weak(v.c1)), 0ULL);
+        if (e >= n_lo)
+            for (uint32_t sl = 0; sl < a.S; sl++) {
+                const ext_t av = ext_mul(ext_canon(a.alpha[sl]), v);
+                a.UA[(e - n_lo) * a.S + sl] = make_ulonglong4(av.c0, av.c1, gl_canon(gl_mul7_weak(av.c1)), 0ULL);
+            }
+    }
+}
+// one eq table over the variables [v0, v0 + nb) of the point, optionally as S alpha-folded copies per entry (the tables of the
+// lanes-over-high mapping)
+struct VeqRangeArgs {
+    const ext_t* w;
+    uint32_t v0, nb, S;
+    ext_t alpha[CG_TVEQ_MAX_SLOTS];
+    ulonglong4* out;
+};
+__global__ void __launch_bounds__(CG_THREADS) veq_range_table_kernel(const __grid_constant__ VeqRangeArgs a) {
+    const uint64_t total = 1ULL << a.nb, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
+        ext_t v = ext_one();
+        for (uint32_t i = 0; i < a.nb; i++) {
+            const ext_t wi = ext_canon(a.w[a.v0 + i]);
+            v = ext_mul(v, ((x >> i) & 1) ? wi : ext_sub(ext_one(), wi));
+        }
+        if (a.S == 0) { a.out[x] = make_ulonglong4(v.c0, v.c1, gl_canon(gl_mul7_weak(v.c1)), 0ULL); continue; }
+        for (uint32_t sl = 0; sl < a.S; sl++) {
+            const ext_t av = ext_mul(ext_canon(a.alpha[sl]), v);
+            a.out[x * a.S + sl] = make_ulonglong4(av.c0, av.c1, gl_canon(gl_mul7_weak(av.c1)), 0ULL);
+        }
     }
 }
 // leave split mode: out[x] = P * L[x & 255] * H[x >> 8]  =  the eq state a materialised table would hold

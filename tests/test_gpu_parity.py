@@ -506,11 +506,14 @@ def test_chip_tower_flow_records_to_proof(dev):
     (12, 4096, 1, 4, 9, True, True),        # explicit numerators, base-field records mixed in, full instances
     (13, 5000, 37, 2, 70, False, False),    # many records per row (keccak-like: padded_ops 64 / 128)
     (7, 100, 3, 2, 1094, False, False),     # keccak's 1094 lookup records per row (lookup_keccakf.rs:97-101), scaled-down rows
+    (10, 1000, 9, 12, 40, True, True),      # leaf layers of 2^14 .. 2^16 read by the split-eq rounds (lanes over the record rows)
+    (9, 512, 16, 16, 300, False, True),
 ])
-def test_tower_over_virtual_leaves_bit_exact(dev, log_n, ninst, n_r, n_w, n_lk, with_num, base_mix):
+def test_tower_over_virtual_leaves_bit_exact(dev, monkeypatch, log_n, ninst, n_r, n_w, n_lk, with_num, base_mix):
     """cfg-4: the tower built and proven over VIRTUAL leaf layers (GpuVirtualInterleavedExt: records described, the interleaved
     fan-in leaves never stored) gives the oracle's proof of the materialised chain, bit for bit."""
     import ceno_b200 as cb
+    monkeypatch.setenv("CG_TOWER_VEQ_MIN_NV", "10")   # split-eq rounds on these scaled-down layers too
     n = 1 << log_n
     alpha = [12345, 678]
 
@@ -566,6 +569,22 @@ def test_tower_proof_bit_exact(dev, prod_nvs, logup_nvs, with_p):
 
 def test_tower_large(dev):
     _tower_case(dev, [17, 17], [16], False, seed=77)
+
+
+@pytest.mark.parametrize("prod_nvs,logup_nvs,with_p,env", [
+    ([16, 15], [15], True, {}),                                   # layers >= 2^13 run split-eq rounds (tveq_round_kernel), claim-derived
+    ([], [16, 14], False, {}),
+    ([15] * 3, [14], False, {"CG_TOWER_VEQ_NOCLAIM": "1"}),       # round 0 without a claim: the three-sum variant
+    ([16], [15], True, {"CG_TAIL_CLUSTER": "1"}),                 # small tail: more split rounds per layer
+    ([16, 15], [15], True, {"CG_TOWER_VEQ": "0"}),                # A/B: the eq table everywhere
+])
+def test_tower_split_eq_layers_bit_exact(dev, monkeypatch, prod_nvs, logup_nvs, with_p, env):
+    """The eq factor of a tower layer's sumcheck stays virtual on large layers (ceno_zkvm/src/scheme/cpu/mod.rs:417-485 without
+    the eq table): same proof as the oracle's table formulation, bit for bit."""
+    monkeypatch.setenv("CG_TOWER_VEQ_MIN_NV", "10")   # (default: layers of 2^20 points and more)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _tower_case(dev, prod_nvs, logup_nvs, with_p, seed=4100 + len(prod_nvs) + 3 * len(logup_nvs))
 
 
 @pytest.mark.parametrize("shapes", [[(3, 1)], [(6, 3)], [(5, 2), (5, 1)], [(7, 2), (4, 3), (6, 1)], [(2, 1), (9, 4)], [(14, 5), (12, 3)]])
@@ -979,10 +998,13 @@ def _dist_tower_worker(rank, world, port, q):
         keep += ms
         specs.append(cb.TowerProverSpec(ms, nv, True))
     want_proof, want_point = orc.tower_create_proof(o_prod, o_lk, orc.Transcript(b"shtower"))
-    tw = cb.TowerProver.sharded(dev, comm, specs)
-    got_proof, got_point = tw.create_proof(cb.StandInTranscript(b"shtower"))
-    ok = ok and np.array_equal(got_proof, want_proof) and np.array_equal(got_point, want_point)
-    tw.close()
+    for veq_min in ("10", "64"):   # sliced layers with split-eq rounds (eq handed over as its point), then with eq tables
+        os.environ["CG_TOWER_VEQ_MIN_NV"] = veq_min
+        tw = cb.TowerProver.sharded(dev, comm, specs)
+        got_proof, got_point = tw.create_proof(cb.StandInTranscript(b"shtower"))
+        ok = ok and np.array_equal(got_proof, want_proof) and np.array_equal(got_point, want_point)
+        tw.close()
+    os.environ["CG_TOWER_VEQ_MIN_NV"] = "10"
     # (b) virtual leaves: every rank holds its rows of both fan-in blocks of 5 lookup records (a chip of rows / world rows)
     log_n, n_rec, alpha = 14, 5, [12345, 678]
     n = 1 << log_n
