@@ -816,6 +816,8 @@ struct cg_sumcheck {
     std::vector<MleState> mles;
     std::vector<const VirtLeaf*> virt;   // per MLE: its ORIGINAL input is a virtual tower leaf array (null / empty: a plain array)
     uint32_t virt_l2m = 0;               // log2 of the padded record count of the virtual leaves (index layout of their rows)
+    struct VirtHost { uint32_t n_records = 0, l2m = 0; ext_t def{0, 0}; };
+    std::vector<VirtHost> virt_h;        // host copy of what the split-eq launches need to know about each virtual slot
     TowerLayout tl;
     VeqState veq;
     // device state
@@ -1479,6 +1481,49 @@ static int launch_tveq(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& r
         a.U = v.d_LR[f];
         a.F = v.d_HS[f];
         a.lo_bits = v.m1_lo[f];
+        const TowerLayout& tl = sc->tl;
+        const bool info = sc->virt_h.size() == sc->virt.size();
+        auto is_one = [](const ext_t& e) { return e.c0 == 1 && e.c1 == 0; };
+        for (size_t l = 0; info && l < tl.lk_an.size(); l++) {   // numerators described as "no records, default one"
+            const uint32_t i0 = tl.lk[4 * l], i1 = tl.lk[4 * l + 1];
+            if (sc->virt[i0] && sc->virt[i1] && !sc->virt_h[i0].n_records && !sc->virt_h[i1].n_records && is_one(sc->virt_h[i0].def) && is_one(sc->virt_h[i1].def))
+                a.t.pone_mask |= 1u << l;
+        }
+        // record padding: items past every slot's records are constant pairs; their sum is added per chunk
+        const uint64_t n_lo = 1ULL << a.lo_bits, chunk = std::min<uint64_t>(n_lo, 256);
+        a.pad_lo = (uint32_t)n_lo;
+        bool all_virt = info;
+        uint64_t pad = 0;
+        for (size_t i = 1; all_virt && i < sc->virt.size(); i++) {
+            if (!sc->virt[i] || sc->virt_h[i].l2m != sc->virt_l2m) all_virt = false;   // (one index layout for every slot)
+            else pad = std::max<uint64_t>(pad, ((uint64_t)sc->virt_h[i].n_records + (2ULL << f) - 1) >> (f + 1));
+        }
+        if (all_virt && pad < n_lo && n_lo / chunk <= CG_TVEQ_PAD_CHUNKS && (n_lo << f) << 1 == (1ULL << sc->virt_l2m)) {
+            // K = value of the layer polynomial on an all-default pair (per unit of eq weight), e[lo] = eq over the low variables
+            ext_t K{0, 0};
+            auto D = [&](uint32_t i) { return sc->virt_h[i].def; };
+            for (size_t p = 0; p < tl.prod_alpha.size(); p++) K = hx_add(K, hx_mul(tl.prod_alpha[p], hx_mul(D(tl.prod[2 * p]), D(tl.prod[2 * p + 1]))));
+            for (size_t l = 0; l < tl.lk_an.size(); l++) {
+                const uint32_t p1 = tl.lk[4 * l], p2 = tl.lk[4 * l + 1], q1 = tl.lk[4 * l + 2], q2 = tl.lk[4 * l + 3];
+                K = hx_add(K, hx_mul(tl.lk_an[l], hx_add(hx_mul(D(p1), D(q2)), hx_mul(D(p2), D(q1)))));
+                K = hx_add(K, hx_mul(tl.lk_ad[l], hx_mul(D(q1), D(q2))));
+            }
+            std::vector<ext_t> e(n_lo);
+            e[0] = ext_t{1, 0};
+            for (uint32_t b = 0; b < a.lo_bits; b++) {
+                const ext_t w{v.h_point[2 * (f + 1 + b)], v.h_point[2 * (f + 1 + b) + 1]}, om{hx_submod(1, w.c0), hx_submod(0, w.c1)};
+                for (uint64_t x = 0; x < (1ULL << b); x++) {
+                    e[x | (1ULL << b)] = hx_mul(e[x], w);
+                    e[x] = hx_mul(e[x], om);
+                }
+            }
+            for (uint64_t ch = 0; ch < n_lo / chunk; ch++) {
+                ext_t sum{0, 0};
+                for (uint64_t lo = std::max(ch * chunk, pad); lo < (ch + 1) * chunk; lo++) sum = hx_add(sum, e[lo]);
+                a.pad_sum[ch] = hx_mul(K, sum);
+            }
+            a.pad_lo = (uint32_t)pad;
+        }
     } else {
         a.U = v.d_UA + v.h_off[f] * v.S;
         a.F = v.d_L + ((size_t)f << CG_VEQ_LO_BITS);
@@ -2562,6 +2607,8 @@ struct TowerSpecState {
     bool virt = false;               // the leaf layer is described, not stored (cg_tower_build_virtual)
     const VirtLeaf* d_virt[4] = {nullptr, nullptr, nullptr, nullptr};   // device descriptions of the leaf arrays
     uint32_t virt_l2m = 0;           // log2 of the padded record count (leaf index = row << l2m | record)
+    uint32_t virt_nrec[4] = {0, 0, 0, 0};   // per leaf array: record count and padding value of its description
+    ext_t virt_def[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
 };
 struct cg_tower {
     cg_ctx* ctx = nullptr;
@@ -2878,12 +2925,17 @@ static int tower_build_virtual_impl(cg_ctx* c, cg_comm* cm, const cg_tower_vspec
             const VirtLeaf* dq[2];
             rc = make_virt_limbs(tw, in.q, dq, &len_q);
             if (rc != CG_OK) break;
+            const ext_t dq_def{in.q.default_ext[0] % GL_P, in.q.default_ext[1] % GL_P};
             if (!sp.is_logup) {
                 sp.d_virt[0] = dq[0]; sp.d_virt[1] = dq[1];
+                sp.virt_nrec[0] = sp.virt_nrec[1] = in.q.n_records;
+                sp.virt_def[0] = sp.virt_def[1] = dq_def;
                 sp.num_vars = ceil_log2_u64(len_q) + 1 + gbits;
                 sp.layers = sp.num_vars;
             } else {
                 sp.d_virt[2] = dq[0]; sp.d_virt[3] = dq[1];
+                sp.virt_nrec[2] = sp.virt_nrec[3] = in.q.n_records;
+                sp.virt_def[2] = sp.virt_def[3] = dq_def;
                 cg_tower_vgroup pg = in.p;
                 if (!pg.n_records) {   // numerators all one (utils.rs:556-577): a description with no records and default 1
                     pg = in.q;
@@ -2896,6 +2948,8 @@ static int tower_build_virtual_impl(cg_ctx* c, cg_comm* cm, const cg_tower_vspec
                 if (rc != CG_OK) break;
                 if (in.p.n_records && len_p != len_q) { rc = set_err(c, CG_ERR_INVALID, "cg_tower_build_virtual: numerator and denominator groups differ in shape"); break; }
                 sp.d_virt[0] = dp[0]; sp.d_virt[1] = dp[1];
+                sp.virt_nrec[0] = sp.virt_nrec[1] = pg.n_records;
+                sp.virt_def[0] = sp.virt_def[1] = ext_t{pg.default_ext[0] % GL_P, pg.default_ext[1] % GL_P};
                 sp.num_vars = ceil_log2_u64(len_q) + gbits;
                 sp.layers = sp.num_vars + 1;
             }
@@ -3036,6 +3090,7 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
         // MLE list in the reference's lift order: eq, then live product specs, then live logup specs
         std::vector<cg_mle_desc> mles;
         std::vector<const VirtLeaf*> virt{nullptr};
+        std::vector<cg_sumcheck::VirtHost> virt_h(1);
         if (lp.veq) mles.push_back(cg_mle_desc{rt.data(), n, nv, CG_MLE_EQ});   // the point itself (host memory)
         else mles.push_back(cg_mle_desc{d_eq, n, nv, 1});
         TowerLayout tl;
@@ -3053,6 +3108,9 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
                 const bool vleaf = sp.virt && round + 1 == sp.layers;   // the leaf layer of a virtual spec: placeholder pointer + description
                 mles.push_back(cg_mle_desc{vleaf ? (const void*)d_eq : (const void*)tower_arr(sp, round, z), n, nv, 1});
                 virt.push_back(vleaf ? sp.d_virt[z] : nullptr);
+                cg_sumcheck::VirtHost vh;
+                if (vleaf) { vh.n_records = sp.virt_nrec[z]; vh.l2m = sp.virt_l2m; vh.def = sp.virt_def[z]; }
+                virt_h.push_back(vh);
                 (sp.is_logup ? tl.lk : tl.prod).push_back((uint32_t)mles.size() - 1);
             }
             if (sp.is_logup) { tl.lk_an.push_back(alpha[tw->n_prod + 2 * my]); tl.lk_ad.push_back(alpha[tw->n_prod + 2 * my + 1]); }
@@ -3094,6 +3152,7 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
             if (any_virt) {
                 if (!fits) rc = set_err(c, CG_ERR_UNSUPPORTED, "virtual tower leaves need the specialised tower kernels (<= 8 product, <= 4 logup specs)");
                 sc->virt = virt;
+                sc->virt_h = virt_h;
             }
             if (rc == CG_OK && lp.veq) {   // (lp.veq implies fits)
                 sc->virt_l2m = lp.vl2m;

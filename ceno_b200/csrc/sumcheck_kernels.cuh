@@ -357,6 +357,7 @@ struct TowerArgs {
     int n_prod, n_logup;
     int alpha_one;            // every alpha_prod is 1: skip the alpha multiply
     const VirtLeaf* virt[CG_TOWER_SLOTS];   // VIRT kernels: slot (1 + 2p + z | 1 + 2 n_prod + 4l + z) read through a description (null: plain array)
+    uint32_t pone_mask;       // split-eq VIRT launches: logup spec l's numerators are the constant one (no records: utils.rs:556-577)
     uint64_t n_pairs;         // pairs evaluated this launch (after the fold, if FOLD)
     ext_t r;                  // fold challenge (FOLD only) ...
     const ext_t* r_ptr;       // ... or read it from device memory (device challenger)
@@ -533,6 +534,8 @@ struct GlobalLoader {
         }
         load_pair<FOLD, CANON>(a.prod_in[p][z], a.prod_out[p][z], item, rm, lo, hi);
     }
+    // a slot whose values are one known constant: the fold's output is the constant
+    GL_DEV void store_const(ext_t* out, uint64_t item, ext_t v) { if (FOLD) st_ext2(out + 2 * item, v, v); }
     GL_DEV void lk(int l, int z, uint64_t item, ext_t& lo, ext_t& hi) {
         if (VIRT) {
             const VirtLeaf* v = a.virt[1 + 2 * a.n_prod + 4 * l + z];
@@ -697,12 +700,17 @@ __global__ void __launch_bounds__(256, MINB) veq_round_kernel(const __grid_const
 // Two index mappings: rows of 256 pairs with the lanes over the LOW item bits (F = low table, U = one row weight per block
 // step), or — launches that read virtual leaves, whose neighbouring items are different record arrays — lanes over the HIGH
 // item bits (the record rows, contiguous in memory) and a loop over the low bits (U = low table, F = high table).
+#define CG_TVEQ_PAD_CHUNKS 8
 struct TVeqArgs {
     TowerArgs t;               // eq_in / eq_out / out unused
     const ulonglong4* U;       // uniform part: S prepared entries {c0, c1, 7 c1, -} per index, alpha folded in
     const ulonglong4* F;       // thread-fixed part
     uint32_t S;
     uint32_t lo_bits;          // lanes-over-high mapping: item = (hi << lo_bits) | lo, U indexed by lo, F by hi
+    // ... whose items lo >= pad_lo lie in the record padding of EVERY slot (all values default, lo == hi): their constant
+    // contribution to q(0) = q(1), summed per chunk of 256 items with the U weights, comes from the host (pad_sum)
+    uint32_t pad_lo;
+    ext_t pad_sum[CG_TVEQ_PAD_CHUNKS];
     VeqFin fin;
     RoundOut out_;
 };
@@ -734,6 +742,21 @@ GL_DEV void tveq_item(const TowerArgs& a, L& ld, uint64_t item, const ulonglong4
     for (int l = 0; l < a.n_logup; l++) {
         const extmul_t Wn = tab_mul(U + a.n_prod + 2 * l), Wd = tab_mul(U + a.n_prod + 2 * l + 1);
         ext_t p1lo, p1hi, p2lo, p2hi, q1lo, q1hi, q2lo, q2hi;
+        if ((a.pone_mask >> l) & 1) {   // p1 = p2 = 1:  g = an (q1 + q2) + ad q1 q2 = (an + ad q1) q2 + an q1, differences of p vanish
+            ld.store_const(a.lk_out[l][0], item, ext_one());
+            ld.store_const(a.lk_out[l][1], item, ext_one());
+            ld.lk(l, 2, item, q1lo, q1hi);
+            ld.lk(l, 3, item, q2lo, q2hi);
+            const ext_t wn = ext_make(Wn.c0, Wn.c1), dq1 = ext_sub(q1lo, q1hi), dq2 = ext_sub(q2lo, q2hi);
+            if (!DERIVE) {
+                eacc_mac(S0, ext_add(ext_mul_prep(q1lo, Wd), wn), q2lo, gl_mul7_weak(q2lo.c1));
+                eacc_mac(S0, wn, q1lo, gl_mul7_weak(q1lo.c1));
+            }
+            eacc_mac(S1, ext_add(ext_mul_prep(q1hi, Wd), wn), q2hi, gl_mul7_weak(q2hi.c1));
+            eacc_mac(S1, wn, q1hi, gl_mul7_weak(q1hi.c1));
+            eacc_mac(C2, ext_mul_prep_weak(dq1, Wd), dq2, gl_mul7_weak(dq2.c1));
+            continue;
+        }
         ld.lk(l, 0, item, p1lo, p1hi);
         ld.lk(l, 1, item, p2lo, p2hi);
         ld.lk(l, 2, item, q1lo, q1hi);
@@ -791,11 +814,27 @@ __global__ void __launch_bounds__(256, 2) tveq_round_kernel(const __grid_constan
         for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < units; g += stride) {
             const uint64_t c = g / n_hi, hi = g - c * n_hi;   // consecutive lanes: consecutive record rows
             eacc_zero(S0); eacc_zero(S1); eacc_zero(C2);
-            for (uint64_t lo = c * chunk; lo < (c + 1) * chunk; lo++)
+            const uint64_t lo0 = c * chunk, lo1 = lo0 + chunk;
+            const uint64_t live = a.pad_lo < lo0 ? lo0 : (a.pad_lo < lo1 ? a.pad_lo : lo1);
+            for (uint64_t lo = lo0; lo < live; lo++)
                 tveq_item<DERIVE>(a.t, ld, (hi << a.lo_bits) + lo, a.U + lo * S, S0, S1, C2);
             const extmul_t Fm = tab_mul(a.F + hi);
-            if (!DERIVE) s0 = ext_add(s0, ext_mul_prep(eacc_weak(S0), Fm));
-            s1 = ext_add(s1, ext_mul_prep(eacc_weak(S1), Fm));
+            ext_t t0 = ext_zero(), t1 = eacc_canon(S1);
+            if (!DERIVE) t0 = eacc_canon(S0);
+            if (live < lo1) {   // record padding: every slot holds its default on both sides of the pair
+                if (FOLD)
+                    for (uint64_t lo = live; lo < lo1; lo++) {
+                        const uint64_t item = (hi << a.lo_bits) + lo;
+                        for (int p = 0; p < a.t.n_prod; p++)
+                            for (int z = 0; z < 2; z++) ld.store_const(a.t.prod_out[p][z], item, a.t.virt[1 + 2 * p + z]->def);
+                        for (int l = 0; l < a.t.n_logup; l++)
+                            for (int z = 0; z < 4; z++) ld.store_const(a.t.lk_out[l][z], item, a.t.virt[1 + 2 * a.t.n_prod + 4 * l + z]->def);
+                    }
+                t1 = ext_add(t1, a.pad_sum[c]);
+                if (!DERIVE) t0 = ext_add(t0, a.pad_sum[c]);
+            }
+            if (!DERIVE) s0 = ext_add(s0, ext_mul_prep(t0, Fm));
+            s1 = ext_add(s1, ext_mul_prep(t1, Fm));
             c2 = ext_add(c2, ext_mul_prep(eacc_weak(C2), Fm));
         }
     }
@@ -2153,12 +2192,37 @@ __global__ void __launch_bounds__(CG_THREADS) tower_logup_layer_kernel(const ext
         tower_store(q_out, x, n, ext_mul(a1, a2));
     }
 }
-// first level above VIRTUAL leaves (description instead of arrays; p1 / p2 null = numerators are all one)
+// first level above VIRTUAL leaves (description instead of arrays; p1 / p2 null = numerators are all one).
+// Iteration order: neighbouring leaves are DIFFERENT record arrays (leaf = row << l2m | record), so consecutive lanes take
+// consecutive rows of one record pair (contiguous 16-byte reads) and every thread writes the pair's two results as one
+// 32-byte store.
+GL_DEV void tower_store2(const TowerDst& t, uint64_t x, uint64_t n, ext_t v0, ext_t v1) {   // x even
+    if (t.split) {
+        const uint64_t h = n >> 1;
+        st_ext2((x < h ? t.d[0] : t.d[1]) + (x < h ? x : x - h), v0, v1);
+    } else {
+#pragma unroll 1
+        for (int p = 0; p < t.n_dst; p++) st_ext2(t.d[p] + x, v0, v1);
+    }
+}
+GL_DEV uint64_t virt_pair_index(uint64_t g, uint64_t n, uint32_t l2m) {   // unit g of n / 2 -> even leaf index
+    const uint32_t rows_log = 63 - __clzll((long long)n) - l2m;
+    if (l2m == 0 || rows_log < 5) return 2 * g;
+    const uint64_t s = g & ((1ULL << rows_log) - 1), i2 = g >> rows_log;
+    return (s << l2m) | (2 * i2);
+}
 __global__ void __launch_bounds__(CG_THREADS) tower_prod_layer_virt_kernel(const VirtLeaf* __restrict__ a, const VirtLeaf* __restrict__ b,
                                                                             uint64_t n, const __grid_constant__ TowerDst out) {
     const VirtLeaf va = *a, vb = *b;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) tower_store(out, x, n, ext_mul(virt_leaf(va, x), virt_leaf(vb, x)));
+    if (n < 2) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) tower_store(out, 0, n, ext_mul(virt_leaf(va, 0), virt_leaf(vb, 0)));
+        return;
+    }
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n / 2; g += stride) {
+        const uint64_t x = virt_pair_index(g, n, va.l2m);
+        tower_store2(out, x, n, ext_mul(virt_leaf(va, x), virt_leaf(vb, x)), ext_mul(virt_leaf(va, x + 1), virt_leaf(vb, x + 1)));
+    }
 }
 __global__ void __launch_bounds__(CG_THREADS) tower_logup_layer_virt_kernel(const VirtLeaf* __restrict__ p1, const VirtLeaf* __restrict__ p2,
                                                                              const VirtLeaf* __restrict__ q1, const VirtLeaf* __restrict__ q2,
@@ -2166,13 +2230,30 @@ __global__ void __launch_bounds__(CG_THREADS) tower_logup_layer_virt_kernel(cons
                                                                              const __grid_constant__ TowerDst q_out) {
     const VirtLeaf v1 = *q1, v2 = *q2;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) {
+    // numerators described as "no records, default one" (utils.rs:556-577) need no multiplication
+    const bool ones = !p1 || (p1->n_records == 0 && p2->n_records == 0 && p1->def.c0 == 1 && p1->def.c1 == 0 && p2->def.c0 == 1 && p2->def.c1 == 0);
+    auto one = [&](uint64_t x, ext_t& p, ext_t& q) {
         const ext_t a1 = virt_leaf(v1, x), a2 = virt_leaf(v2, x);
-        ext_t p;
-        if (p1) p = ext_add(ext_mul(a1, virt_leaf(*p2, x)), ext_mul(a2, virt_leaf(*p1, x)));
+        if (!ones) p = ext_add(ext_mul(a1, virt_leaf(*p2, x)), ext_mul(a2, virt_leaf(*p1, x)));
         else p = ext_add(a1, a2);
-        tower_store(p_out, x, n, p);
-        tower_store(q_out, x, n, ext_mul(a1, a2));
+        q = ext_mul(a1, a2);
+    };
+    if (n < 2) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            ext_t p, q;
+            one(0, p, q);
+            tower_store(p_out, 0, n, p);
+            tower_store(q_out, 0, n, q);
+        }
+        return;
+    }
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n / 2; g += stride) {
+        const uint64_t x = virt_pair_index(g, n, v1.l2m);
+        ext_t pa, qa, pb, qb;
+        one(x, pa, qa);
+        one(x + 1, pb, qb);
+        tower_store2(p_out, x, n, pa, pb);
+        tower_store2(q_out, x, n, qa, qb);
     }
 }
 // ---------------------------------------------------------------------------------------------
