@@ -1546,7 +1546,7 @@ static int launch_tveq(cg_sumcheck* sc, uint32_t f, bool fold, const RoundOut& r
     if (!any_virt) blocks = std::min<uint64_t>(blocks, a.t.n_pairs >> CG_VEQ_LO_BITS);
     else {
         const uint64_t n_lo = 1ULL << a.lo_bits, units = (a.t.n_pairs >> a.lo_bits) * (n_lo / std::min<uint64_t>(n_lo, 256));
-        blocks = std::min<uint64_t>(blocks, (units + 255) / 256);
+        blocks = std::min<uint64_t>(blocks, (4 * units + 255) / 256);   // four lanes per unit
     }
     const unsigned grid = (unsigned)(blocks ? blocks : 1);
 #define CG_TVEQ(F, CN, DR, VR) tveq_round_kernel<F, CN, DR, VR><<<grid, 256, 0, sc->stream>>>(a)

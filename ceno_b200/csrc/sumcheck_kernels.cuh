@@ -810,26 +810,29 @@ __global__ void __launch_bounds__(256, 2) tveq_round_kernel(const __grid_constan
     } else {
         const uint64_t n_lo = 1ULL << a.lo_bits, n_hi = a.t.n_pairs >> a.lo_bits;
         const uint64_t chunk = n_lo < 256 ? n_lo : 256;
-        const uint64_t units = n_hi * (n_lo / chunk), stride = (uint64_t)gridDim.x * blockDim.x;
-        for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < units; g += stride) {
-            const uint64_t c = g / n_hi, hi = g - c * n_hi;   // consecutive lanes: consecutive record rows
+        // A unit = (chunk c, row hi) is shared by FOUR neighbouring lanes (items lo = q, q + 4, ...): a warp covers 8 consecutive
+        // rows, so every record read is a full 128-byte line and the four lanes' folded outputs (32 B each) form one line too.
+        const uint64_t units = n_hi * (n_lo / chunk), stride = ((uint64_t)gridDim.x * blockDim.x) >> 2;
+        const uint32_t q = threadIdx.x & 3;
+        for (uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2; g < units; g += stride) {
+            const uint64_t c = g / n_hi, hi = g - c * n_hi;
             eacc_zero(S0); eacc_zero(S1); eacc_zero(C2);
             const uint64_t lo0 = c * chunk, lo1 = lo0 + chunk;
             const uint64_t live = a.pad_lo < lo0 ? lo0 : (a.pad_lo < lo1 ? a.pad_lo : lo1);
-            for (uint64_t lo = lo0; lo < live; lo++)
-                tveq_item<DERIVE>(a.t, ld, (hi << a.lo_bits) + lo, a.U + lo * S, S0, S1, C2);
+            for (uint64_t lo = lo0 + q; lo < lo1; lo += 4) {
+                const uint64_t item = (hi << a.lo_bits) + lo;
+                if (lo < live) tveq_item<DERIVE>(a.t, ld, item, a.U + lo * S, S0, S1, C2);
+                else if (FOLD) {   // record padding: every slot holds its default on both sides of the pair
+                    for (int p = 0; p < a.t.n_prod; p++)
+                        for (int z = 0; z < 2; z++) ld.store_const(a.t.prod_out[p][z], item, a.t.virt[1 + 2 * p + z]->def);
+                    for (int l = 0; l < a.t.n_logup; l++)
+                        for (int z = 0; z < 4; z++) ld.store_const(a.t.lk_out[l][z], item, a.t.virt[1 + 2 * a.t.n_prod + 4 * l + z]->def);
+                }
+            }
             const extmul_t Fm = tab_mul(a.F + hi);
             ext_t t0 = ext_zero(), t1 = eacc_canon(S1);
             if (!DERIVE) t0 = eacc_canon(S0);
-            if (live < lo1) {   // record padding: every slot holds its default on both sides of the pair
-                if (FOLD)
-                    for (uint64_t lo = live; lo < lo1; lo++) {
-                        const uint64_t item = (hi << a.lo_bits) + lo;
-                        for (int p = 0; p < a.t.n_prod; p++)
-                            for (int z = 0; z < 2; z++) ld.store_const(a.t.prod_out[p][z], item, a.t.virt[1 + 2 * p + z]->def);
-                        for (int l = 0; l < a.t.n_logup; l++)
-                            for (int z = 0; z < 4; z++) ld.store_const(a.t.lk_out[l][z], item, a.t.virt[1 + 2 * a.t.n_prod + 4 * l + z]->def);
-                    }
+            if (live < lo1 && q == 0) {   // the padding's constant contribution, once per unit
                 t1 = ext_add(t1, a.pad_sum[c]);
                 if (!DERIVE) t0 = ext_add(t0, a.pad_sum[c]);
             }
@@ -2207,9 +2210,12 @@ GL_DEV void tower_store2(const TowerDst& t, uint64_t x, uint64_t n, ext_t v0, ex
 }
 GL_DEV uint64_t virt_pair_index(uint64_t g, uint64_t n, uint32_t l2m) {   // unit g of n / 2 -> even leaf index
     const uint32_t rows_log = 63 - __clzll((long long)n) - l2m;
-    if (l2m == 0 || rows_log < 5) return 2 * g;
-    const uint64_t s = g & ((1ULL << rows_log) - 1), i2 = g >> rows_log;
-    return (s << l2m) | (2 * i2);
+    if (l2m < 3 || rows_log < 3) return 2 * g;
+    // four neighbouring lanes: four consecutive leaf pairs of one row (one 128-byte line of results); the warp's eight lane
+    // quads: eight consecutive rows (one 128-byte line of every record read)
+    const uint64_t q = g & 3, u = g >> 2;
+    const uint64_t s = u & ((1ULL << rows_log) - 1), i8 = u >> rows_log;
+    return (s << l2m) | (8 * i8 + 2 * q);
 }
 __global__ void __launch_bounds__(CG_THREADS) tower_prod_layer_virt_kernel(const VirtLeaf* __restrict__ a, const VirtLeaf* __restrict__ b,
                                                                             uint64_t n, const __grid_constant__ TowerDst out) {
