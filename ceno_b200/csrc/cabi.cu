@@ -3043,7 +3043,8 @@ CG_EXPORT int cg_tower_create_proof(cg_tower* tw, const cg_transcript_vt* tr, ui
         for (uint32_t round = 1; round <= tw->max_round; round++) {
             const LayerPlan lp = layer_plan(round);
             max_ws = std::max(max_ws, lp.slots * (size_t)ws_per(1ULL << lp.nv) * sizeof(ext_t));
-            if (!lp.veq) max_eq = std::max(max_eq, sizeof(ext_t) << lp.nv);
+            // (below 2^20 the plan may change with the number of live sumchecks on the context: always keep room for the table)
+            if (!lp.veq || lp.nv < 20) max_eq = std::max(max_eq, sizeof(ext_t) << lp.nv);
         }
         CHK(tmp_alloc(c, max_eq, &d_eq_all, tw->stream));
         if (tmp_alloc(c, max_ws, &lent.ptr, tw->stream) == CG_OK) lent.bytes = max_ws;   // on failure the layers allocate their own
