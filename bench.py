@@ -518,6 +518,19 @@ def gpu_arm_sharded(args, rank, world, local_rank):
         except Exception as e:  # noqa: BLE001
             config5 = {"error": repr(e)}
 
+    # ---- BASELINE config #4 shape on N GPUs: the keccak lookup tower (1094 records per row, virtual leaves), 2^17 rows per GPU
+    config4 = None
+    if getattr(args, "config4", True):
+        try:
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+            import bench_rows
+            config4 = bench_rows.keccak_tower_row(dev, 17, comm=comm, xchg=xchg, barrier=dist.barrier, world=world, rank=rank)
+            digests = [None] * world
+            dist.all_gather_object(digests, config4.pop("proof_digest"))
+            config4["proof_identical_on_all_ranks"] = len(set(digests)) == 1
+        except Exception as e:  # noqa: BLE001
+            config4 = {"error": repr(e)}
+
     if rank == 0:
         n = 1 << k
         ops = 99 * n
@@ -568,6 +581,7 @@ def gpu_arm_sharded(args, rank, world, local_rank):
                              "sample": f"T3-{args.cpu_k} full sumcheck, one run on rank 0's host; oracle port with the reference's decomposition, OpenMP {cores} threads"},
             "weak_scaling": weak,
             "config5": config5,
+            "config4": config4,
             "clocks": clk,
             "parity_checked": parity_checked,
         }
@@ -615,6 +629,7 @@ def main():
     ap.add_argument("--cpu-k", type=int, default=24, help="log2 size of the bounded CPU sample")
     ap.add_argument("--no-rows", dest="rows", action="store_false", help="N=1: skip the secondary rows (Z, TOWER, EQ-24, FOLD-24, C-26, RS-26, BATCH-26)")
     ap.add_argument("--no-weak", dest="weak", action="store_false", help="N>1: skip the weak-scaling measurement (T3-(k + log2 N))")
+    ap.add_argument("--no-config4", dest="config4", action="store_false", help="N>1: skip the sharded keccak lookup tower (BASELINE config #4 shape, 2^17 rows per GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -21,6 +21,47 @@ from ceno_b200 import _lib, api, synth
 P = 0xFFFFFFFF00000001
 
 
+def keccak_tower_row(dev, rows_log_local, n_rec=1094, comm=None, xchg=None, barrier=None, world=1, rank=0):
+    """BASELINE config #4's tower: the keccak-f chip's 1094 lookup records per row (ceno_zkvm/src/precompiles/lookup_keccakf.rs:97-101)
+    over VIRTUAL leaves, 2^rows_log_local rows on this GPU (times `world` GPUs when sharded: every rank holds its rows of both
+    fan-in blocks).  Returns build / prove wall-clock ms between device synchronisations (rank barriers when sharded)."""
+    n_loc = 1 << rows_log_local
+    g = world.bit_length() - 1
+    l2m = (n_rec - 1).bit_length()
+    if comm is not None:
+        comm.create_arena(16 * 4 * ((1 << (l2m + rows_log_local - 1)) + (1 << 22)), xchg)
+    big = dev.alloc(16 * n_loc * n_rec)
+    chunk = synth.fill_ext(77 + rank, n_loc)
+    pin, pinp = dev.pinned(chunk.nbytes)
+    pin[:] = chunk
+    for i in range(n_rec):                       # same values in every record (content does not change the cost)
+        dev.h2d(big.ptr + 16 * n_loc * i, pinp, chunk.nbytes)
+    dev.sync()
+    recs = [cb.MultilinearExtension(dev, cb.DeviceBuffer(dev, big.ptr + 16 * n_loc * i, 16 * n_loc, owner=False), rows_log_local, True) for i in range(n_rec)]
+    sync = (lambda: (dev.sync(), barrier())) if barrier else dev.sync
+
+    def run():
+        sync()
+        t0 = time.perf_counter()
+        tw = cb.TowerProver.from_records(dev, [cb.VirtualTowerSpec(recs, n_loc, [12345, 678], True)], comm=comm)
+        sync()
+        t1 = time.perf_counter()
+        proof, _ = tw.create_proof(cb.StandInTranscript(b"keccak"))
+        sync()
+        t2 = time.perf_counter()
+        tw.close()
+        return (t1 - t0) * 1e3, (t2 - t1) * 1e3, proof
+    run()
+    b_ms, p_ms, proof = run()
+    big.free()
+    dev.lib.cg_host_free_pinned(dev.ctx, pinp)
+    return {"workload": "BASELINE #4 shape: keccak-f lookup tower, 1094 ext records per row, virtual leaves", "n_gpus": world,
+            "rows_log": rows_log_local + g, "rows_per_gpu_log": rows_log_local, "records": n_rec, "record_bytes_per_gpu": 16 * n_loc * n_rec,
+            "virtual_leaf_ext_elements": 4 << (l2m + rows_log_local + g - 1), "tower_layers": l2m + rows_log_local + g,
+            "build_ms": b_ms, "prove_ms": p_ms, "proof_digest": int(np.bitwise_xor.reduce(proof)),
+            "timing": "host wall clock between device synchronisations" + (" and rank barriers (build includes the NVLink layer shuffles)" if comm is not None else "")}
+
+
 def run_rows(dev, peak_gbs=None, cpu=False):
     """All secondary rows on `dev`; returns the dict.  peak_gbs: measured HBM peak for the `frac_of_hbm_peak` fields."""
     out = {}
@@ -185,6 +226,11 @@ def run_rows(dev, peak_gbs=None, cpu=False):
         out["C-26"]["bound"] = "integer issue (Poseidon2: ~14 k instructions per permutation), not HBM"
     for b in (mat, code, tree2, eq20, fold_out):
         b.free()
+    # ---------------------------------------------------------------- KECCAK: config #4's lookup tower, one GPU's 2^17 rows
+    try:
+        out["KECCAK-17"] = keccak_tower_row(dev, 17)
+    except Exception as e:  # noqa: BLE001
+        out["KECCAK-17"] = {"error": repr(e)}
     return out
 
 
