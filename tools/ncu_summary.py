@@ -29,7 +29,10 @@ def to_bytes(value, unit):
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):   # already exported on the GPU box (`ncu -i rep --page raw --csv`; reports can exceed the copy-back limit)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw[raw.index('"ID"'):])))
     hdr, units, launches = rows[0], rows[1], rows[2:]
     keep = [i for i, h in enumerate(hdr) if any(h == k or h.startswith(k) for k in KEEP) and ".min" not in h and ".max.pct" not in h]
