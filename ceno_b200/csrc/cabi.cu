@@ -1888,7 +1888,8 @@ static int launch_tail(cg_sumcheck* sc, uint64_t* d_tr_state, ext_t* d_msgs, ext
     ca.n_loc0 = tp.n_loc0;
     ca.nt = tp.nt;
     static long long* d_dbg = nullptr;
-    if (getenv("CG_TAIL_DEBUG")) {
+    if (getenv("CG_TAIL_DEBUG") && d_tr_state) {   // device challenger only: the dump below synchronises the stream, and a kernel
+                                                   // that waits for the host's answer would never get it
         if (!d_dbg) cudaMalloc((void**)&d_dbg, 64 * 8 * sizeof(long long));
         cudaMemsetAsync(d_dbg, 0, 64 * 8 * sizeof(long long), sc->stream);
         ca.dbg = d_dbg;
