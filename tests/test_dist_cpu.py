@@ -100,3 +100,38 @@ def test_sharded_commit_exchange_layout_world_1_2_4():
             got = torch.stack([sends2[s][d] for s in range(world)]).view(width, lay["code_rows_local"])
             want = torch.cat(code, dim=0)[:, d * lay["code_rows_local"]:(d + 1) * lay["code_rows_local"]]
             assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_tower_shuffle_rule(world):
+    """The placement rule of the sharded tower build (cg_tower_build_sharded, ceno_b200/csrc/cabi.cu: tower_build_spec /
+    TowerDst), simulated with numpy: rank r holds slice r of BOTH fan-in halves of a layer; its products are one contiguous
+    piece of ONE half of the next layer up, whose two sub-slices belong to ranks 2r mod N and 2r+1 mod N.  After every level
+    each rank must again hold slice r of both halves (so layer sumchecks and the next level stay local), and the global layer
+    must equal the single-device layer (ceno_zkvm/src/scheme/utils.rs:606-652: low half | high half of the product array)."""
+    P = 0xFFFFFFFF00000001
+    rng = np.random.default_rng(5 + world)
+    top = 4 + world.bit_length()                      # arrays of the leaf layer: 2^top elements each (globally)
+    a = [int(x) for x in rng.integers(0, P, 1 << top, dtype=np.uint64)]
+    b = [int(x) for x in rng.integers(0, P, 1 << top, dtype=np.uint64)]
+    local = []                                        # local[r] = (slice r of a, slice r of b)
+    m = (1 << top) // world
+    for r in range(world):
+        local.append((a[r * m:(r + 1) * m], b[r * m:(r + 1) * m]))
+    ga, gb = a, b
+    for level in range(top - 1, world.bit_length() - 2, -1):   # while every rank still keeps at least one element per array
+        res = [ga[x] * gb[x] % P for x in range(len(ga))]  # single device: layer `level` = (low half | high half) of the products
+        half = len(res) // 2
+        ga, gb = res[:half], res[half:]
+        m2 = len(local[0][0]) // 2                         # slice length of the new layer
+        new = [([None] * m2, [None] * m2) for _ in range(world)]
+        for r in range(world):
+            mine = [x * y % P for x, y in zip(*local[r])]  # a contiguous piece of ONE half of the new layer
+            part = 0 if r < world // 2 else 1
+            for sub, dst in ((0, (2 * r) % world), (1, (2 * r + 1) % world)):
+                new[dst][part][:] = mine[sub * m2:(sub + 1) * m2]
+        local = new
+        for r in range(world):
+            assert local[r][0] == ga[r * m2:(r + 1) * m2] and local[r][1] == gb[r * m2:(r + 1) * m2], (level, r)
+        if m2 == 1:
+            break
