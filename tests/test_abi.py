@@ -121,3 +121,16 @@ def test_integration_doc_binds_only_declared_symbols():
     structs = {"cg_mle_desc", "cg_challenge_cb", "cg_transcript_vt", "cg_tower_spec", "cg_sched_task", "cg_sched_result", "cg_stream", "cg_ctx",
                "cg_pcs_transcript_vt", "cg_tower_vspec", "cg_tower_vgroup", "cg_basefold_params", "cg_basefold_opening", "cg_pcs_commitment"}
     assert named - structs <= declared, sorted(named - structs - declared)
+
+
+def test_rust_bindings_are_generated_from_the_header():
+    """bindings/rust/ceno_b200_sys/src/lib.rs (what a ceno maintainer links against) is generated from the header: it must be up to
+    date and declare exactly the header's functions."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_bindings.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rs = open(os.path.join(ROOT, "bindings", "rust", "ceno_b200_sys", "src", "lib.rs")).read()
+    assert sorted(re.findall(r"pub fn (cg_[a-z0-9_]+)\(", rs)) == header_symbols()
+    for st in ("cg_mle_desc", "cg_tower_spec", "cg_tower_vspec", "cg_transcript_vt", "cg_pcs_transcript_vt", "cg_basefold_opening", "cg_sched_task"):
+        assert f"pub struct {st} " in rs
